@@ -1,0 +1,82 @@
+"""Load a handful of dependency-free reference files IN PLACE (no copying) so the oracle can be
+pinned against the real reference.  Build-container only: ``/root/reference`` does not exist on
+the GPU box, so nothing that runs there may call this (``available()`` guards).
+
+Loadable as files (torch-only deps): ``connectomics/inference/window.py`` (needs one symbol from
+``..config.hardware``, stubbed), ``connectomics/models/architectures/{registry,base}.py``,
+``connectomics/chunked/{chunk_grid,halo}.py``.  ``import connectomics.<pkg>`` itself fails here
+(monai / omegaconf / h5py are not installed) — see SURVEY.md §8(c).
+"""
+
+from __future__ import annotations
+
+import importlib.util
+import os
+import sys
+import types
+
+REF_ROOT = os.environ.get("PCB_REFERENCE_ROOT", "/root/reference")
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(REF_ROOT, "connectomics", "inference", "window.py"))
+
+
+def _stub(name, path=None, **attrs):
+    if name in sys.modules and not getattr(sys.modules[name], "__pcb_stub__", False):
+        return sys.modules[name]
+    m = types.ModuleType(name)
+    m.__path__ = [path] if path else []
+    m.__pcb_stub__ = True
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+    return m
+
+
+def _load(modname, relpath):
+    if modname in sys.modules and not getattr(sys.modules[modname], "__pcb_stub__", False):
+        return sys.modules[modname]
+    sys.dont_write_bytecode = True  # /root/reference is read-only
+    spec = importlib.util.spec_from_file_location(modname, os.path.join(REF_ROOT, relpath))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[modname] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _base_stubs():
+    c = os.path.join(REF_ROOT, "connectomics")
+    _stub("connectomics", c)
+    _stub("connectomics.config")
+    _stub("connectomics.config.hardware", resolve_accelerator_type=lambda requested="auto": "cpu")
+    _stub("connectomics.inference", os.path.join(c, "inference"))
+    _stub("connectomics.models", os.path.join(c, "models"))
+    _stub("connectomics.models.architectures", os.path.join(c, "models", "architectures"))
+    _stub("connectomics.chunked", os.path.join(c, "chunked"))
+
+
+def ref_window():
+    _base_stubs()
+    return _load("connectomics.inference.window", "connectomics/inference/window.py")
+
+
+def ref_registry():
+    _base_stubs()
+    return _load("connectomics.models.architectures.registry",
+                 "connectomics/models/architectures/registry.py")
+
+
+def ref_base():
+    _base_stubs()
+    return _load("connectomics.models.architectures.base",
+                 "connectomics/models/architectures/base.py")
+
+
+def ref_chunk_grid():
+    _base_stubs()
+    return _load("connectomics.chunked.chunk_grid", "connectomics/chunked/chunk_grid.py")
+
+
+def ref_halo():
+    ref_chunk_grid()
+    return _load("connectomics.chunked.halo", "connectomics/chunked/halo.py")

@@ -1,0 +1,76 @@
+"""Pin the MedNeXt restatement by what the reference constrains (see oracle/mednext_oracle.py)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.mednext_oracle import MedNeXt, MedNeXtBlock, create_mednext_v1
+
+
+def _count(m):
+    return sum(p.numel() for n, p in m.named_parameters())
+
+
+@pytest.mark.parametrize("size,k,quoted", [("S", 3, 5.6), ("B", 3, 10.5), ("M", 3, 17.6), ("L", 3, 61.8),
+                                           ("S", 5, 5.9), ("B", 5, 11.0), ("M", 5, 18.3), ("L", 5, 63.0)])
+def test_param_counts_match_reference_docstring(size, k, quoted):
+    # mednext_models.py:309-312 quotes these (in millions); deep-supervision heads included upstream
+    n = _count(create_mednext_v1(1, 2, size, kernel_size=k, deep_supervision=True)) / 1e6
+    assert abs(n - quoted) < 0.1, (size, k, n)  # docstring quotes one decimal (5.98 -> "5.9")
+
+
+def test_reference_feature_identities():
+    # reference tests/unit/test_mednext_features.py:26-55
+    torch.manual_seed(0)
+    m = MedNeXt(1, 16, 3, exp_r=2, kernel_size=3, deep_supervision=False, do_res=True,
+                do_res_up_down=True, block_counts=[1] * 9).eval()
+    x = torch.rand(1, 1, 32, 32, 32)  # 16^3 would hit GroupNorm on a single voxel at the bottleneck
+    with torch.no_grad():
+        f = m.forward_features(x)
+        assert f.shape == (1, 16, 32, 32, 32)
+        assert torch.allclose(m.forward_output(f), m(x))
+    ds = MedNeXt(1, 16, 3, exp_r=2, kernel_size=3, deep_supervision=True, do_res=True,
+                 do_res_up_down=True, block_counts=[1] * 9).eval()
+    with torch.no_grad():
+        outs = ds(x)
+    assert isinstance(outs, list) and len(outs) == 5
+    assert [tuple(o.shape[2:]) for o in outs] == [(32,) * 3, (16,) * 3, (8,) * 3, (4,) * 3, (2,) * 3]
+
+
+def test_introspected_attributes():
+    # mednext_models.py:99-126,215-231
+    m = create_mednext_v1(1, 2, "S", 3, False)
+    b = m.dec_block_0[0]
+    assert isinstance(b, MedNeXtBlock) and b.conv1.kernel_size == (3, 3, 3)
+    assert b.conv2.out_channels // b.conv2.in_channels == 2
+    assert isinstance(b.norm, torch.nn.GroupNorm) and b.do_res and b.dim == "3d" and not b.grn
+    assert m.stem.out_channels == 32 and not m.do_ds and hasattr(m, "outside_block_checkpointing")
+    keys = set(m.state_dict().keys())
+    for k in ["stem.weight", "enc_block_0.0.conv1.weight", "enc_block_0.1.norm.bias", "down_0.res_conv.weight",
+              "bottleneck.1.conv3.bias", "up_3.conv1.weight", "up_0.res_conv.bias", "dec_block_0.1.conv2.weight",
+              "out_0.conv_out.weight", "dummy_tensor"]:
+        assert k in keys, k
+    assert m.up_0.conv1.weight.shape == (64, 1, 3, 3, 3) and m.up_0.res_conv.weight.shape == (64, 32, 1, 1, 1)
+    assert m.out_0.conv_out.weight.shape == (32, 2, 1, 1, 1)
+
+
+def test_regression_vector(mednext_tiny_golden):
+    g = mednext_tiny_golden
+    torch.manual_seed(0)
+    net = MedNeXt(in_channels=1, n_channels=16, n_classes=2, exp_r=2, kernel_size=3, deep_supervision=True,
+                  do_res=True, do_res_up_down=True, block_counts=[1] * 9).eval()
+    assert _count(net) == int(g["n_params"][0])
+    with torch.no_grad():
+        outs = net(torch.from_numpy(g["x"]))
+    for i, o in enumerate(outs):
+        assert np.allclose(o.numpy(), g[f"out{i}"], rtol=1e-4, atol=1e-5), i
+
+
+def test_checkpointed_matches_plain():
+    torch.manual_seed(0)
+    m = MedNeXt(1, 16, 1, exp_r=2, kernel_size=3, do_res=True, do_res_up_down=True, block_counts=[1] * 9)
+    x = torch.rand(1, 1, 32, 32, 32)
+    y0 = m(x).sum()
+    g0 = torch.autograd.grad(y0, m.stem.weight)[0]
+    m.outside_block_checkpointing = True
+    g1 = torch.autograd.grad(m(x).sum(), m.stem.weight)[0]
+    assert torch.allclose(g0, g1, rtol=1e-4, atol=1e-6)
