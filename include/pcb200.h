@@ -1,0 +1,103 @@
+/* pcb200 — C ABI of the B200-native hot path for PyTorch Connectomics.
+ *
+ * The reference (PytorchConnectomics/pytorch_connectomics) is pure Python; it has no FFI.  Its
+ * "operator API" for this path is (1) the architecture registry / nn.Module forward contract and
+ * (2) the sliding-window engine callable.  This header is the boundary a reference maintainer
+ * would bind (ctypes stub in INTEGRATION.md): plain C, device/host pointers + sizes, every call
+ * enqueues on the caller's cudaStream_t and never synchronises.  Each entry point cites the
+ * reference code it replaces (paths relative to the reference repo root).
+ *
+ * Conventions
+ *   - return 0 (PCB_OK) or a negative pcb_status; pcb_last_error() gives a thread-local message.
+ *   - the caller owns every buffer; the library owns nothing but a few __constant__ tables.
+ *   - activations inside the network are channels-last bf16:  [N, D, H, W, C]  ("NDHWC").
+ *   - tensors crossing the reference API are NCDHW in the caller's dtype (pcb_dtype).
+ *   - stream is a cudaStream_t passed as void*.
+ */
+#ifndef PCB200_H
+#define PCB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum { PCB_OK = 0, PCB_ERR_INVALID = -1, PCB_ERR_CUDA = -2, PCB_ERR_UNSUPPORTED = -3 } pcb_status;
+typedef enum { PCB_F32 = 0, PCB_F16 = 1, PCB_BF16 = 2 } pcb_dtype;
+typedef enum { PCB_BLEND_CONSTANT = 0, PCB_BLEND_BUMP = 1, PCB_BLEND_DISTANCE = 2 } pcb_blend;
+typedef enum { PCB_PAD_CONSTANT = 0, PCB_PAD_REFLECT = 1, PCB_PAD_REPLICATE = 2, PCB_PAD_CIRCULAR = 3 } pcb_pad;
+typedef enum { PCB_GRID_EAGER = 0, PCB_GRID_LAZY = 1, PCB_GRID_LAZY_SNAP = 2 } pcb_grid;
+/* depthwise-conv flavour of a MedNeXt block (upstream nnunet_mednext blocks.py) */
+typedef enum { PCB_DW_SAME = 0, PCB_DW_DOWN = 1, PCB_DW_UP = 2 } pcb_dw_mode;
+
+const char* pcb_last_error(void);
+int pcb_version(void);
+/* 1 when the library was built for sm_100a and the current device is cc 10.x */
+int pcb_device_ok(void);
+
+/* ------------------------------------------------------------------ sliding window: host INT logic
+ * connectomics/inference/window.py:57-89  compute_scan_interval (Python round() = half-even) */
+int pcb_sw_scan_interval(const int64_t image[3], const int64_t roi[3], const double overlap[3],
+                         int64_t interval_out[3]);
+/* window.py:92-134 dense_patch_slices (PCB_GRID_EAGER) and lazy.py:269-365 window offsets
+ * (PCB_GRID_LAZY / _SNAP, region filter `off < stop && off+roi > start`; pass region=NULL for all).
+ * Writes up to `capacity` window starts (z,y,x triples, z-major product order) and the total count. */
+int pcb_sw_plan(int grid_kind, const int64_t image[3], const int64_t roi[3], const double overlap[3],
+                const int64_t region[6], int64_t* starts_out, int64_t capacity, int64_t* count_out);
+
+/* ------------------------------------------------------------------ sliding window: device kernels
+ * window.py:137-243  importance map built in `dtype` arithmetic (bump / constant / distance).
+ * roi is left-padded with 1s to 3-D; `ndim` says how many trailing axes are real. */
+int pcb_sw_importance_map(int blend, const int64_t roi[3], int ndim, int dtype, double min_value,
+                          void* map_out, void* stream);
+/* window.py:464-527 _extract_padded_patch_batch: gather n windows [n,C,roi] from vol [1,C,D,H,W];
+ * `starts` is a HOST array of n (z,y,x) triples; pad per window relative to the in-image crop. */
+int pcb_sw_extract(const void* vol, int dtype, int64_t C, const int64_t image[3], const int64_t roi[3],
+                   const int64_t* starts, int64_t n, int pad_mode, double cval, void* out, void* stream);
+/* window.py:648-655 _accumulate for ONE window: value[:, lo:hi] += pred[plo:phi]*map ; weight += map
+ * (all in `dtype` arithmetic, mul then add, no FMA — bit-identical to the torch expression).
+ * pred is [Cout, roi] ; boxes allow the clipped sub-box form of lazy.py:1216-1227. */
+int pcb_sw_accumulate(const void* pred, const void* map, void* value, void* weight, int dtype,
+                      int64_t Cout, const int64_t roi[3], const int64_t out_size[3],
+                      const int64_t pred_lo[3], const int64_t out_lo[3], const int64_t box[3],
+                      void* stream);
+/* window.py:275-294 normalize_weighted_accumulator: value /= clamp_min(weight, 1e-4) (in place). */
+int pcb_sw_normalize(void* value, const void* weight, int dtype, int64_t Cout, int64_t nvox, void* stream);
+
+/* ------------------------------------------------------------------ MedNeXt forward ops
+ * (upstream nnunet_mednext blocks.py / MedNextV1.py as built by
+ *  connectomics/models/architectures/mednext_models.py:374-380,479)
+ *
+ * stem: Conv3d(Cin, C, k=1).  x NCDHW in `in_dtype`  ->  out NDHWC bf16. w [C,Cin] f32, b [C] f32. */
+int pcb_stem_fwd(const void* x, int in_dtype, const float* w, const float* b, void* out,
+                 int64_t N, int64_t Cin, int64_t C, int64_t nvox, void* stream);
+/* conv1 of a block: depthwise k^3 conv (SAME: stride 1 pad k/2; DOWN: stride 2 pad k/2;
+ * UP: ConvTranspose stride 2 pad k/2 -> spatial 2s-1), + bias, bf16 output, and the per-(n,c)
+ * sum / sum-of-squares of the rounded output for GroupNorm(num_groups=C) — accumulated into
+ * `stats` [N, 2, C] float64 (sums, then sums of squares) which the caller zeroes.  w is [k^3, C] f32 (tap-major), b [C] f32. */
+int pcb_dwconv_fwd(const void* x, const float* w, const float* b, void* y, double* stats,
+                   int64_t N, const int64_t in_size[3], int64_t C, int k, int mode, void* stream);
+/* norm -> conv2 (1x1, C->H) -> GELU -> conv3 (1x1, H->Co) [+ residual | + res_conv(x)] fused on
+ * tcgen05: two back-to-back GEMMs per 128-voxel tile, the expanded tensor never leaves the SM.
+ *   y      [N, Vy, C]  bf16   dw-conv output;   stats [N,2,C] f64 (sum, sumsq over Vy voxels)
+ *   gamma,beta [C] f32 (GroupNorm affine, eps 1e-5);  w2 [H,C] bf16, b2 [H] f32; w3 [Co,H] bf16, b3 [Co] f32
+ *   mode SAME: out[v] = mlp(y[v]) + (res ? res[v] : 0)                        (do_res)
+ *   mode DOWN: out[v] = mlp(y[v]) + (wr ? wr*xs[2v] + br : 0)                 (res_conv stride 2)
+ *   mode UP  : out over (2s)^3; o with any coord 0 -> res[o] (skip) only; else
+ *              mlp(y[o-1]) + (wr ? (o-1 all even ? wr*xs[(o-1)/2] : 0) + br : 0) + (res ? res[o] : 0)
+ *   xs [N, Vin, Cr] bf16 with spatial size xs_size, wr [Co,Cr] bf16, br [Co] f32 ; out [N, Vout, Co] bf16. */
+int pcb_mlp_fwd(const void* y, const double* stats, const float* gamma, const float* beta,
+                const void* w2, const float* b2, const void* w3, const float* b3,
+                const void* res, const void* xs, const void* wr, const float* br, void* out,
+                int64_t N, const int64_t out_size[3], const int64_t xs_size[3], int64_t C, int64_t H,
+                int64_t Co, int64_t Cr, int mode, void* stream);
+/* OutBlock ConvTranspose3d(C, ncls, k=1): x NDHWC bf16 -> out NCDHW in `out_dtype`.
+ * w [C, ncls] f32 (ConvTranspose layout), b [ncls] f32. */
+int pcb_head_fwd(const void* x, const float* w, const float* b, void* out, int out_dtype,
+                 int64_t N, int64_t C, int64_t ncls, int64_t nvox, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCB200_H */

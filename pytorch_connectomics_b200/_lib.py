@@ -1,0 +1,110 @@
+"""ctypes binding of ``csrc/libpcb200.so`` (the C ABI declared in ``include/pcb200.h``).
+
+The product path has NO CPU fallback: if the shared library is missing, or a CUDA op is asked to
+run without a Blackwell device, a ``RuntimeError`` is raised.  Bad arguments surface as
+``ValueError`` (status PCB_ERR_INVALID) with the library's message, mirroring the reference's
+error behaviour for the same misuse.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import sys
+from typing import Optional, Sequence
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libpcb200.so")
+SOURCES = ["pcb_api.cu", "sw_kernels.cu", "mednext_fwd.cu", "mednext_bwd.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+PCB_F32, PCB_F16, PCB_BF16 = 0, 1, 2
+BLEND = {"constant": 0, "bump": 1, "distance": 2}
+PAD = {"constant": 0, "reflect": 1, "replicate": 2, "circular": 3}
+GRID_EAGER, GRID_LAZY, GRID_LAZY_SNAP = 0, 1, 2
+DW_SAME, DW_DOWN, DW_UP = 0, 1, 2
+
+_DTYPES = {torch.float32: PCB_F32, torch.float16: PCB_F16, torch.bfloat16: PCB_BF16}
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA sources into ``csrc/libpcb200.so`` with nvcc for sm_100a (in-tree)."""
+    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    deps = srcs + [os.path.join(CSRC, "pcb_common.cuh"), os.path.join(_HERE, "..", "include", "pcb200.h")]
+    if not force and os.path.exists(LIB_PATH):
+        t = os.path.getmtime(LIB_PATH)
+        if all(os.path.getmtime(d) <= t for d in deps if os.path.exists(d)):
+            return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + srcs
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    subprocess.run(cmd, check=True, cwd=CSRC)
+    return LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"pcb200: CUDA extension {LIB_PATH} is missing — run `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "There is no CPU fallback for this path.")
+        _lib = ctypes.CDLL(LIB_PATH)
+        _lib.pcb_last_error.restype = ctypes.c_char_p
+        _lib.pcb_version.restype = ctypes.c_int
+    return _lib
+
+
+def check(status: int, what: str = "") -> None:
+    if status == 0:
+        return
+    msg = lib().pcb_last_error().decode("utf-8", "replace")
+    if status == -1:
+        raise ValueError(msg or f"pcb200: invalid argument in {what}")
+    raise RuntimeError(f"pcb200 {what} failed (status {status}): {msg}")
+
+
+def require_device(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"pcb200: {what} needs a CUDA tensor on a B200 (sm_100a); got device={t.device}. "
+            "There is no CPU fallback for this path.")
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    try:
+        return _DTYPES[dt]
+    except KeyError:
+        raise ValueError(f"pcb200: unsupported dtype {dt}; expected float32/float16/bfloat16") from None
+
+
+def i64x(vals: Sequence[int]):
+    return (ctypes.c_int64 * len(vals))(*[int(v) for v in vals])
+
+
+def f64x(vals: Sequence[float]):
+    return (ctypes.c_double * len(vals))(*[float(v) for v in vals])
+
+
+def ptr(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def exported_symbols():
+    """Names declared in include/pcb200.h (parsed) — used by the CPU-side load test."""
+    import re
+    hdr = os.path.join(_HERE, "..", "include", "pcb200.h")
+    txt = open(hdr).read()
+    return sorted(set(re.findall(r"\b(pcb_[a-z0-9_]+)\s*\(", txt)))

@@ -1,0 +1,202 @@
+"""Functional layer between the MedNeXt modules and the C ABI (``include/pcb200.h``).
+
+Every function here enqueues hand-written sm_100a kernels on ``torch.cuda.current_stream()``; torch
+is used for allocation and for autograd bookkeeping only.  Activations are channels-last bf16
+``[N, D, H, W, C]``.  ``torch.autograd.Function`` wrappers store, per block, the block input and the
+depthwise-conv output (+ its GroupNorm statistics); the expanded ``[V, r*C]`` tensor is never stored —
+backward recomputes it on the tensor cores (the reference's ``outside_block`` checkpointing recomputes
+whole blocks; this is the same trade at a finer grain).
+"""
+
+from __future__ import annotations
+
+import ctypes
+import weakref
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from .. import _lib as L
+
+_BF16 = torch.bfloat16
+
+# ----------------------------------------------------------------------------- weight repacking cache
+_CACHE: Dict[Tuple[int, str], tuple] = {}
+
+
+def _pack_dw(w):      # [C,1,k,k,k] -> [k^3, C] f32 (tap-major)
+    c = w.shape[0]
+    return w.reshape(c, -1).t().contiguous().float()
+
+
+def _pack_pw(w):      # Conv3d 1x1 [O,I,1,1,1] -> [O,I] bf16
+    return w.reshape(w.shape[0], w.shape[1]).contiguous().to(_BF16)
+
+
+def _pack_pw_t(w):    # ConvTranspose3d 1x1 [I,O,1,1,1] -> [O,I] bf16
+    return w.reshape(w.shape[0], w.shape[1]).t().contiguous().to(_BF16)
+
+
+def _pack_f32(w):
+    return w.reshape(-1).contiguous().float()
+
+
+def _pack_head(w):    # ConvTranspose3d 1x1 [C,ncls,1,1,1] -> [C,ncls] f32
+    return w.reshape(w.shape[0], w.shape[1]).contiguous().float()
+
+
+def _pack_head_conv(w):  # Conv3d 1x1 [ncls,C,1,1,1] -> [C,ncls] f32
+    return w.reshape(w.shape[0], w.shape[1]).t().contiguous().float()
+
+
+_PACKERS = {"dw": _pack_dw, "pw": _pack_pw, "pw_t": _pack_pw_t, "f32": _pack_f32, "head": _pack_head,
+            "head_conv": _pack_head_conv}
+
+
+def packed(p: torch.Tensor, kind: str) -> torch.Tensor:
+    """Kernel-layout copy of a parameter, refreshed when the parameter changes (optimizer step,
+    load_state_dict, .to(device))."""
+    key = (id(p), kind)
+    ent = _CACHE.get(key)
+    if ent is not None and ent[0] == p._version and ent[1]() is p and ent[2] == p.data_ptr():
+        return ent[3]
+    with torch.no_grad():
+        t = _PACKERS[kind](p.detach())
+    if len(_CACHE) > 8192:
+        for k in [k for k, e in _CACHE.items() if e[1]() is None]:
+            del _CACHE[k]
+    _CACHE[key] = (p._version, weakref.ref(p), p.data_ptr(), t)
+    return t
+
+
+# ----------------------------------------------------------------------------- helpers
+def as_channels_last(x: torch.Tensor) -> torch.Tensor:
+    """Accept [N,D,H,W,C] bf16 (internal) or an NCDHW tensor/view; return contiguous [N,D,H,W,C] bf16."""
+    if getattr(x, "_pcb_cl", False):
+        return x
+    if x.dim() != 5:
+        raise ValueError(f"expected a 5-D tensor, got shape {tuple(x.shape)}")
+    L.require_device(x, "channels-last conversion")
+    y = x.permute(0, 2, 3, 4, 1)
+    if y.dtype != _BF16:
+        y = y.to(_BF16)
+    y = y.contiguous()
+    y._pcb_cl = True
+    return y
+
+
+def _mark(t: torch.Tensor) -> torch.Tensor:
+    t._pcb_cl = True
+    return t
+
+
+def _out_size(mode: int, k: int, size: Sequence[int]) -> Tuple[List[int], List[int]]:
+    """(dw-conv output size, block output size) for an input spatial size."""
+    p = k // 2
+    if mode == L.DW_SAME:
+        return list(size), list(size)
+    if mode == L.DW_DOWN:
+        o = [(s + 2 * p - k) // 2 + 1 for s in size]
+        return o, o
+    y = [(s - 1) * 2 - 2 * p + k for s in size]      # ConvTranspose, 2s-1 for k=3,5,7 with pad k//2
+    return y, [v + 1 for v in y]
+
+
+# ----------------------------------------------------------------------------- raw forward launches
+def stem_forward(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    x = x.contiguous()
+    n, cin = int(x.shape[0]), int(x.shape[1])
+    c = int(w.shape[0])
+    out = torch.empty((n, *x.shape[2:], c), device=x.device, dtype=_BF16)
+    nvox = int(x.shape[2] * x.shape[3] * x.shape[4])
+    L.check(L.lib().pcb_stem_fwd(L.ptr(x), L.dtype_code(x.dtype), L.ptr(packed(w, "f32")), L.ptr(packed(b, "f32")),
+                                 L.ptr(out), ctypes.c_int64(n), ctypes.c_int64(cin), ctypes.c_int64(c),
+                                 ctypes.c_int64(nvox), L.stream_ptr(x.device)), "pcb_stem_fwd")
+    return _mark(out)
+
+
+def block_forward(x: torch.Tensor, skip: Optional[torch.Tensor], params: List[torch.Tensor], mode: int, k: int,
+                  do_res: bool, has_rc: bool):
+    """Returns (out, y, stats).  x: [N,D,H,W,C] bf16."""
+    w1, b1, gamma, beta, w2, b2, w3, b3 = params[:8]
+    n, size, c = int(x.shape[0]), [int(s) for s in x.shape[1:4]], int(x.shape[4])
+    h, co = int(w2.shape[0]), int(w3.shape[0])
+    ysize, osize = _out_size(mode, k, size)
+    dev = x.device
+    st = L.stream_ptr(dev)
+    lib = L.lib()
+    y = torch.empty((n, *ysize, c), device=dev, dtype=_BF16)
+    stats = torch.zeros((n, 2, c), device=dev, dtype=torch.float64)
+    L.check(lib.pcb_dwconv_fwd(L.ptr(x), L.ptr(packed(w1, "dw")), L.ptr(packed(b1, "f32")), L.ptr(y), L.ptr(stats),
+                               ctypes.c_int64(n), L.i64x(size), ctypes.c_int64(c), ctypes.c_int(k),
+                               ctypes.c_int(mode), st), "pcb_dwconv_fwd")
+    out = torch.empty((n, *osize, co), device=dev, dtype=_BF16)
+    res = None
+    if mode == L.DW_SAME and do_res:
+        res = x
+    elif mode == L.DW_UP and skip is not None:
+        res = skip
+        if tuple(skip.shape) != tuple(out.shape):
+            raise ValueError(f"skip shape {tuple(skip.shape)} != up-block output shape {tuple(out.shape)}")
+    wr = br = None
+    cr = 0
+    if has_rc:
+        wr = packed(params[8], "pw_t" if mode == L.DW_UP else "pw")
+        br = packed(params[9], "f32")
+        cr = c
+    L.check(lib.pcb_mlp_fwd(L.ptr(y), L.ptr(stats), L.ptr(packed(gamma, "f32")), L.ptr(packed(beta, "f32")),
+                            L.ptr(packed(w2, "pw")), L.ptr(packed(b2, "f32")), L.ptr(packed(w3, "pw")),
+                            L.ptr(packed(b3, "f32")), L.ptr(res), L.ptr(x if has_rc else None), L.ptr(wr), L.ptr(br),
+                            L.ptr(out), ctypes.c_int64(n), L.i64x(osize), L.i64x(size), ctypes.c_int64(c),
+                            ctypes.c_int64(h), ctypes.c_int64(co), ctypes.c_int64(cr), ctypes.c_int(mode), st),
+            "pcb_mlp_fwd")
+    return _mark(out), y, stats
+
+
+def head_forward(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, out_dtype: torch.dtype,
+                 conv_layout: bool = False) -> torch.Tensor:
+    n, c = int(x.shape[0]), int(x.shape[4])
+    wk = packed(w, "head_conv" if conv_layout else "head")
+    ncls = int(wk.shape[1])
+    out = torch.empty((n, ncls, *x.shape[1:4]), device=x.device, dtype=out_dtype)
+    nvox = int(x.shape[1] * x.shape[2] * x.shape[3])
+    L.check(L.lib().pcb_head_fwd(L.ptr(x), L.ptr(wk), L.ptr(packed(b, "f32")), L.ptr(out),
+                                 ctypes.c_int(L.dtype_code(out_dtype)), ctypes.c_int64(n), ctypes.c_int64(c),
+                                 ctypes.c_int64(ncls), ctypes.c_int64(nvox), L.stream_ptr(x.device)), "pcb_head_fwd")
+    return out
+
+
+# ----------------------------------------------------------------------------- autograd wrappers
+def _needs_grad(*ts) -> bool:
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in ts)
+
+
+def stem_apply(x, w, b):
+    L.require_device(x, "MedNeXt stem")
+    if _needs_grad(x, w, b):
+        from . import _mednext_bwd as B
+        return _mark(B.StemFn.apply(x, w, b))
+    return stem_forward(x, w, b)
+
+
+def block_apply(x, skip, params, mode, k, do_res, has_rc):
+    x = as_channels_last(x)
+    if skip is not None:
+        skip = as_channels_last(skip)
+    if _needs_grad(x, skip, *params):
+        from . import _mednext_bwd as B
+        return _mark(B.BlockFn.apply(x, skip, mode, k, do_res, has_rc, *params))
+    return block_forward(x, skip, params, mode, k, do_res, has_rc)[0]
+
+
+def head_apply(x, w, b, out_dtype, conv_layout=False):
+    x = as_channels_last(x)
+    if _needs_grad(x, w, b):
+        from . import _mednext_bwd as B
+        return B.HeadFn.apply(x, w, b, out_dtype, conv_layout)
+    return head_forward(x, w, b, out_dtype, conv_layout)
+
+
+def pointwise_apply(x, w, b):
+    raise NotImplementedError("pcb200: task-head input_projection (hidden_channels != feature width) "
+                              "is not implemented in the B200 engine yet")

@@ -1,0 +1,435 @@
+"""MedNeXt on the B200 engine — drop-in for what
+``connectomics/models/architectures/mednext_models.py`` builds from the third-party
+``nnunet_mednext`` package (``:23-32,374-380,479``).
+
+Module / attribute names and ``state_dict`` keys are the upstream ones
+(``stem``, ``enc_block_{l}.{i}.{conv1,norm,conv2,conv3}``, ``down_{l}``/``up_{l}`` with ``res_conv``,
+``bottleneck``, ``dec_block_{l}``, ``out_{k}.conv_out``, ``dummy_tensor``), so reference checkpoints
+load unchanged (``training/model_weights.py:74`` loads into ``model.model``).  The ``nn.Conv3d`` /
+``nn.GroupNorm`` children are *parameter containers only* (same shapes, same default init as
+upstream); the arithmetic runs in hand-written sm_100a kernels through the C ABI
+(``include/pcb200.h``): activations travel channels-last bf16 ``[N,D,H,W,C]`` between kernels.
+
+There is no PyTorch/CPU fallback: ``forward`` on a non-CUDA tensor raises ``RuntimeError``.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from typing import Any, Dict, List, Mapping, Optional, Sequence, Union
+
+import torch
+import torch.nn as nn
+
+from .. import _lib as L
+from .base import ConnectomicsModel
+from .registry import register_architecture
+from . import _mednext_ops as ops
+
+
+def _unsupported(what: str):
+    raise NotImplementedError(
+        f"pcb200 MedNeXt: {what} is not implemented in the B200 engine yet (3-D, GroupNorm, no GRN only).")
+
+
+class MedNeXtBlock(nn.Module):
+    """upstream blocks.py::MedNeXtBlock — conv1 (depthwise k^3) -> GroupNorm(C groups) -> conv2 (1x1,
+    C->rC) -> GELU -> conv3 (1x1, rC->Cout) [+ x].  ``forward`` takes/returns channels-last bf16."""
+
+    _dw_mode = L.DW_SAME
+
+    def __init__(self, in_channels: int, out_channels: int, exp_r: int = 4, kernel_size: int = 7,
+                 do_res: bool = True, norm_type: str = "group", n_groups=None, dim: str = "3d",
+                 grn: bool = False):
+        super().__init__()
+        if dim != "3d":
+            _unsupported("dim='2d'")
+        if norm_type != "group":
+            _unsupported("norm_type='layer'")
+        if grn:
+            _unsupported("grn=True")
+        if n_groups is not None and n_groups != in_channels:
+            _unsupported("n_groups != in_channels")
+        self.do_res = do_res
+        self.dim = dim
+        self.grn = grn
+        self.conv1 = nn.Conv3d(in_channels, in_channels, kernel_size, 1, kernel_size // 2, groups=in_channels)
+        self.norm = nn.GroupNorm(num_groups=in_channels, num_channels=in_channels)
+        self.conv2 = nn.Conv3d(in_channels, exp_r * in_channels, 1)
+        self.act = nn.GELU()
+        self.conv3 = nn.Conv3d(exp_r * in_channels, out_channels, 1)
+
+    def _params(self) -> List[torch.Tensor]:
+        p = [self.conv1.weight, self.conv1.bias, self.norm.weight, self.norm.bias,
+             self.conv2.weight, self.conv2.bias, self.conv3.weight, self.conv3.bias]
+        rc = getattr(self, "res_conv", None)
+        if rc is not None:
+            p += [rc.weight, rc.bias]
+        return p
+
+    def forward(self, x: torch.Tensor, skip: Optional[torch.Tensor] = None) -> torch.Tensor:
+        has_rc = getattr(self, "res_conv", None) is not None
+        return ops.block_apply(x, skip, self._params(), self._dw_mode, self.conv1.kernel_size[0],
+                               bool(self.do_res), has_rc)
+
+
+class MedNeXtDownBlock(MedNeXtBlock):
+    """upstream blocks.py::MedNeXtDownBlock — stride-2 depthwise conv1; residual = Conv3d(k=1, stride 2)."""
+
+    _dw_mode = L.DW_DOWN
+
+    def __init__(self, in_channels, out_channels, exp_r=4, kernel_size=7, do_res=False,
+                 norm_type="group", dim="3d", grn=False):
+        super().__init__(in_channels, out_channels, exp_r, kernel_size, do_res=False,
+                         norm_type=norm_type, dim=dim, grn=grn)
+        self.resample_do_res = do_res
+        if do_res:
+            self.res_conv = nn.Conv3d(in_channels, out_channels, 1, stride=2)
+        self.conv1 = nn.Conv3d(in_channels, in_channels, kernel_size, 2, kernel_size // 2, groups=in_channels)
+
+
+class MedNeXtUpBlock(MedNeXtBlock):
+    """upstream blocks.py::MedNeXtUpBlock — transposed stride-2 depthwise conv1 (spatial 2s-1), block
+    output zero-padded by one voxel at the front of each axis; residual = ConvTranspose3d(k=1, stride 2)."""
+
+    _dw_mode = L.DW_UP
+
+    def __init__(self, in_channels, out_channels, exp_r=4, kernel_size=7, do_res=False,
+                 norm_type="group", dim="3d", grn=False):
+        super().__init__(in_channels, out_channels, exp_r, kernel_size, do_res=False,
+                         norm_type=norm_type, dim=dim, grn=grn)
+        self.resample_do_res = do_res
+        if do_res:
+            self.res_conv = nn.ConvTranspose3d(in_channels, out_channels, 1, stride=2)
+        self.conv1 = nn.ConvTranspose3d(in_channels, in_channels, kernel_size, 2, kernel_size // 2,
+                                        groups=in_channels)
+
+
+class OutBlock(nn.Module):
+    """upstream blocks.py::OutBlock — ConvTranspose3d(C, n_classes, k=1). channels-last bf16 in,
+    NCDHW out."""
+
+    def __init__(self, in_channels, n_classes, dim="3d"):
+        super().__init__()
+        if dim != "3d":
+            _unsupported("dim='2d'")
+        self.conv_out = nn.ConvTranspose3d(in_channels, n_classes, 1)
+
+    def forward(self, x: torch.Tensor, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+        return ops.head_apply(x, self.conv_out.weight, self.conv_out.bias, out_dtype)
+
+
+class MedNeXt(nn.Module):
+    """upstream MedNextV1.py::MedNeXt (+ the fork's forward_features / forward_output)."""
+
+    def __init__(self, in_channels: int, n_channels: int, n_classes: int,
+                 exp_r: Union[int, Sequence[int]] = 4, kernel_size: int = 7,
+                 enc_kernel_size: int = None, dec_kernel_size: int = None,
+                 deep_supervision: bool = False, do_res: bool = False, do_res_up_down: bool = False,
+                 checkpoint_style: str = None, block_counts: Sequence[int] = (2,) * 9,
+                 norm_type: str = "group", dim: str = "3d", grn: bool = False):
+        super().__init__()
+        self.do_ds = deep_supervision
+        if checkpoint_style not in (None, "outside_block"):
+            raise ValueError(f"checkpoint_style must be None or 'outside_block', got {checkpoint_style!r}")
+        # The engine always recomputes the expanded tensor in backward and stores only the block input
+        # and the depthwise output, so the flag is kept for API compatibility and changes nothing.
+        self.inside_block_checkpointing = False
+        self.outside_block_checkpointing = checkpoint_style == "outside_block"
+        if dim != "3d":
+            _unsupported("dim='2d'")
+        if kernel_size is not None:
+            enc_kernel_size = dec_kernel_size = kernel_size
+        if n_channels % 16 != 0:
+            raise ValueError(f"pcb200 MedNeXt needs base_channels to be a multiple of 16, got {n_channels}")
+        exp_r = [exp_r] * len(block_counts) if isinstance(exp_r, int) else list(exp_r)
+        n = n_channels
+        kw = dict(norm_type=norm_type, dim=dim, grn=grn)
+        self.stem = nn.Conv3d(in_channels, n, 1)
+
+        def stage(c, i, k):
+            return nn.Sequential(*[MedNeXtBlock(c, c, exp_r[i], k, do_res=do_res, **kw)
+                                   for _ in range(block_counts[i])])
+
+        ek, dk = enc_kernel_size, dec_kernel_size
+        self.enc_block_0 = stage(n, 0, ek)
+        self.down_0 = MedNeXtDownBlock(n, 2 * n, exp_r[1], ek, do_res=do_res_up_down, **kw)
+        self.enc_block_1 = stage(2 * n, 1, ek)
+        self.down_1 = MedNeXtDownBlock(2 * n, 4 * n, exp_r[2], ek, do_res=do_res_up_down, **kw)
+        self.enc_block_2 = stage(4 * n, 2, ek)
+        self.down_2 = MedNeXtDownBlock(4 * n, 8 * n, exp_r[3], ek, do_res=do_res_up_down, **kw)
+        self.enc_block_3 = stage(8 * n, 3, ek)
+        self.down_3 = MedNeXtDownBlock(8 * n, 16 * n, exp_r[4], ek, do_res=do_res_up_down, **kw)
+        self.bottleneck = stage(16 * n, 4, dk)
+        self.up_3 = MedNeXtUpBlock(16 * n, 8 * n, exp_r[5], dk, do_res=do_res_up_down, **kw)
+        self.dec_block_3 = stage(8 * n, 5, dk)
+        self.up_2 = MedNeXtUpBlock(8 * n, 4 * n, exp_r[6], dk, do_res=do_res_up_down, **kw)
+        self.dec_block_2 = stage(4 * n, 6, dk)
+        self.up_1 = MedNeXtUpBlock(4 * n, 2 * n, exp_r[7], dk, do_res=do_res_up_down, **kw)
+        self.dec_block_1 = stage(2 * n, 7, dk)
+        self.up_0 = MedNeXtUpBlock(2 * n, n, exp_r[8], dk, do_res=do_res_up_down, **kw)
+        self.dec_block_0 = stage(n, 8, dk)
+        self.out_0 = OutBlock(n, n_classes, dim)
+        self.dummy_tensor = nn.Parameter(torch.tensor([1.0]), requires_grad=True)
+        if deep_supervision:
+            self.out_1 = OutBlock(2 * n, n_classes, dim)
+            self.out_2 = OutBlock(4 * n, n_classes, dim)
+            self.out_3 = OutBlock(8 * n, n_classes, dim)
+            self.out_4 = OutBlock(16 * n, n_classes, dim)
+        self.block_counts = list(block_counts)
+        self.output_dtype: Optional[torch.dtype] = None   # None -> same dtype as the input
+
+    # ---- channels-last trunk
+    def _trunk(self, x: torch.Tensor) -> List[torch.Tensor]:
+        L.require_device(x, "MedNeXt.forward")
+        if x.dim() != 5:
+            raise ValueError(f"MedNeXt expects (B, C, D, H, W); got shape {tuple(x.shape)}")
+        if any(int(s) % 16 for s in x.shape[2:]):
+            raise ValueError(f"MedNeXt input spatial size must be divisible by 16, got {tuple(x.shape[2:])}")
+        x = ops.stem_apply(x, self.stem.weight, self.stem.bias)
+        r0 = self.enc_block_0(x)
+        x = self.down_0(r0)
+        r1 = self.enc_block_1(x)
+        x = self.down_1(r1)
+        r2 = self.enc_block_2(x)
+        x = self.down_2(r2)
+        r3 = self.enc_block_3(x)
+        x = self.down_3(r3)
+        b = self.bottleneck(x)
+        d3 = self.dec_block_3(self.up_3(b, r3))       # skip add fused into the up block's epilogue
+        d2 = self.dec_block_2(self.up_2(d3, r2))
+        d1 = self.dec_block_1(self.up_1(d2, r1))
+        f0 = self.dec_block_0(self.up_0(d1, r0))
+        return [f0, d1, d2, d3, b]
+
+    def _odt(self, x: torch.Tensor) -> torch.dtype:
+        return self.output_dtype or (x.dtype if x.dtype in (torch.float16, torch.bfloat16, torch.float32)
+                                     else torch.float32)
+
+    def forward_features(self, x: torch.Tensor) -> torch.Tensor:
+        """Shared full-resolution feature map [B, n, D, H, W] (NCDHW view of the channels-last tensor)."""
+        return self._trunk(x)[0].permute(0, 4, 1, 2, 3)
+
+    def forward_output(self, features: torch.Tensor) -> torch.Tensor:
+        return self.out_0(ops.as_channels_last(features), torch.float32 if features.dtype == torch.bfloat16
+                          and self.output_dtype is None else (self.output_dtype or features.dtype))
+
+    def forward(self, x: torch.Tensor):
+        odt = self._odt(x)
+        f = self._trunk(x)
+        y = self.out_0(f[0], odt)
+        if self.do_ds:
+            return [y, self.out_1(f[1], odt), self.out_2(f[2], odt), self.out_3(f[3], odt), self.out_4(f[4], odt)]
+        return y
+
+
+_V1 = {
+    "S": dict(exp_r=2, block_counts=[2] * 9, checkpoint_style=None),
+    "B": dict(exp_r=[2, 3, 4, 4, 4, 4, 4, 3, 2], block_counts=[2] * 9, checkpoint_style=None),
+    "M": dict(exp_r=[2, 3, 4, 4, 4, 4, 4, 3, 2], block_counts=[3, 4, 4, 4, 4, 4, 4, 4, 3],
+              checkpoint_style="outside_block"),
+    "L": dict(exp_r=[3, 4, 8, 8, 8, 8, 8, 4, 3], block_counts=[3, 4, 8, 8, 8, 8, 8, 4, 3],
+              checkpoint_style="outside_block"),
+}
+
+
+def create_mednext_v1(num_input_channels, num_classes, model_id, kernel_size=3, deep_supervision=False):
+    """upstream create_mednext_v1.py size table (n_channels 32, do_res, do_res_up_down)."""
+    s = _V1[model_id]
+    return MedNeXt(num_input_channels, 32, num_classes, exp_r=s["exp_r"], kernel_size=kernel_size,
+                   deep_supervision=deep_supervision, do_res=True, do_res_up_down=True,
+                   block_counts=s["block_counts"], checkpoint_style=s["checkpoint_style"])
+
+
+# ----------------------------------------------------------------------------- reference wrappers
+class MedNeXtWrapper(ConnectomicsModel):
+    """``mednext_models.py:38-89`` — list -> {"output", "ds_1".."ds_4"} when deep supervision is on."""
+
+    def __init__(self, model: nn.Module, deep_supervision: bool = False):
+        super().__init__()
+        self.model = model
+        self.supports_deep_supervision = deep_supervision
+        self.output_scales = 5 if deep_supervision else 1
+
+    def forward(self, x):
+        out = self.model(x)
+        if self.supports_deep_supervision and isinstance(out, list):
+            return {"output": out[0], "ds_1": out[1], "ds_2": out[2], "ds_3": out[3], "ds_4": out[4]}
+        return out
+
+
+def _cfg_value(cfg: Any, key: str, default: Any = None) -> Any:
+    return cfg.get(key, default) if isinstance(cfg, Mapping) else getattr(cfg, key, default)
+
+
+class MedNeXtTaskHead(nn.Module):
+    """``mednext_models.py:129-194`` — 1x1 in-projection -> N MedNeXt blocks -> 1x1 projection, on the
+    shared channels-last feature map."""
+
+    def __init__(self, in_channels: int, out_channels: int, num_blocks: int,
+                 hidden_channels: Optional[int] = None, *, exp_r: int, kernel_size: int, do_res: bool,
+                 norm_type: str, dim: str, grn: bool):
+        super().__init__()
+        if num_blocks < 0:
+            raise ValueError(f"MedNeXt task head num_blocks must be >= 0, got {num_blocks}")
+        if out_channels <= 0:
+            raise ValueError(f"MedNeXt task head out_channels must be positive, got {out_channels}")
+        hidden_channels = in_channels if hidden_channels is None else hidden_channels
+        if hidden_channels <= 0:
+            raise ValueError(f"MedNeXt task head hidden_channels must be positive, got {hidden_channels}")
+        if hidden_channels > in_channels:
+            raise ValueError("MedNeXt task head hidden_channels must not exceed the shared feature width "
+                             f"({hidden_channels} > {in_channels})")
+        if dim not in ("2d", "3d"):
+            raise ValueError(f"MedNeXt task head dim must be '2d' or '3d', got {dim}")
+        if dim != "3d":
+            _unsupported("dim='2d'")
+        self.input_projection = (nn.Conv3d(in_channels, hidden_channels, 1)
+                                 if hidden_channels != in_channels else nn.Identity())
+        blocks = [MedNeXtBlock(hidden_channels, hidden_channels, exp_r, kernel_size, do_res=do_res,
+                               norm_type=norm_type, dim=dim, grn=grn) for _ in range(num_blocks)]
+        self.blocks = nn.Sequential(*blocks) if blocks else nn.Identity()
+        self.projection = nn.Conv3d(hidden_channels, out_channels, 1)
+        self.hidden_channels = hidden_channels
+
+    def forward(self, x: torch.Tensor, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+        x = ops.as_channels_last(x)
+        if not isinstance(self.input_projection, nn.Identity):
+            x = ops.pointwise_apply(x, self.input_projection.weight, self.input_projection.bias)
+        x = self.blocks(x)
+        # Conv3d weight is [out, in, 1,1,1]; the head kernel takes the ConvTranspose layout [in, out]
+        return ops.head_apply(x, self.projection.weight, self.projection.bias, out_dtype, conv_layout=True)
+
+
+def _infer_head_block_kwargs(model: nn.Module) -> Dict[str, Any]:
+    # mednext_models.py:99-126
+    if not hasattr(model, "dec_block_0") or len(model.dec_block_0) == 0:
+        raise ValueError("MedNeXt trunk must expose a non-empty dec_block_0 to build task heads.")
+    ref = model.dec_block_0[0]
+    if not isinstance(ref, MedNeXtBlock):
+        raise TypeError("Expected MedNeXt dec_block_0 to contain MedNeXtBlock instances for multi-head reuse.")
+    k = ref.conv1.kernel_size
+    k = k[0] if isinstance(k, tuple) else k
+    return {"exp_r": ref.conv2.out_channels // ref.conv2.in_channels, "kernel_size": int(k),
+            "do_res": ref.do_res, "norm_type": "group" if isinstance(ref.norm, nn.GroupNorm) else "layer",
+            "dim": ref.dim, "grn": ref.grn}
+
+
+class MedNeXtMultiHeadWrapper(ConnectomicsModel):
+    """``mednext_models.py:197-273`` — named task heads on the shared features; returns
+    ``{"output": {head: tensor}}``; deep-supervision trunks are rejected."""
+
+    def __init__(self, model: nn.Module, heads: Mapping[str, Any], *, primary_head: Optional[str] = None):
+        super().__init__()
+        if getattr(model, "do_ds", False):
+            raise ValueError("MedNeXtMultiHeadWrapper does not support deep supervision yet. "
+                             "Disable deep supervision for the trunk first.")
+        if not hasattr(model, "forward_features"):
+            raise ValueError("MedNeXt trunk must expose forward_features() before using MedNeXtMultiHeadWrapper.")
+        if not heads:
+            raise ValueError("MedNeXtMultiHeadWrapper requires at least one named task head.")
+        self.model = model
+        self.supports_deep_supervision = False
+        self.output_scales = 1
+        self.feature_channels = int(model.stem.out_channels)
+        self.head_block_kwargs = _infer_head_block_kwargs(model)
+        task_heads, specs = {}, {}
+        for name, hc in heads.items():
+            oc = int(_cfg_value(hc, "out_channels", hc))
+            nb = int(_cfg_value(hc, "num_blocks", 0))
+            hid = _cfg_value(hc, "hidden_channels", None)
+            hid = int(hid) if hid is not None else None
+            task_heads[name] = MedNeXtTaskHead(self.feature_channels, oc, nb, hid, **self.head_block_kwargs)
+            specs[name] = {"out_channels": oc, "num_blocks": nb, "hidden_channels": hid or self.feature_channels}
+        self.heads = nn.ModuleDict(task_heads)
+        self.head_specs = specs
+        primary = primary_head or next(iter(self.heads.keys()))
+        if primary not in self.heads:
+            raise ValueError(f"primary_head '{primary}' is not one of the configured heads: {sorted(self.heads.keys())}")
+        self.primary_head = primary
+
+    def forward_features(self, x):
+        return self.model.forward_features(x)
+
+    def forward_heads(self, features):
+        odt = self.model.output_dtype or (torch.float32 if features.dtype == torch.bfloat16 else features.dtype)
+        return {name: head(features, odt) for name, head in self.heads.items()}
+
+    def forward(self, x):
+        odt = self.model._odt(x)
+        f = self.model._trunk(x)[0]
+        return {"output": {name: head(f, odt) for name, head in self.heads.items()}}
+
+
+# ----------------------------------------------------------------------------- builders
+def _heads_cfg(cfg):
+    raw = getattr(cfg.model, "heads", None)
+    if not raw:
+        return {}, None
+    return dict(raw), getattr(cfg.model, "primary_head", None)
+
+
+def _num_classes(cfg, head_cfg) -> int:
+    # mednext_models.py:284-291
+    if head_cfg:
+        return max(1, sum(int(_cfg_value(s, "out_channels", 0)) for s in head_cfg.values()))
+    return int(cfg.model.out_channels)
+
+
+@register_architecture("mednext")
+def build_mednext(cfg) -> ConnectomicsModel:
+    """MedNeXt S/B/M/L (k in 3/5/7) on the B200 engine (``mednext_models.py:303-397``)."""
+    mcfg = cfg.model.mednext
+    size = getattr(mcfg, "size", "S")
+    k = getattr(mcfg, "kernel_size", 3)
+    ds = getattr(getattr(cfg.model, "loss", None), "deep_supervision", False)
+    head_cfg, primary = _heads_cfg(cfg)
+    if size not in ("S", "B", "M", "L"):
+        raise ValueError(f"MedNeXt model_size must be 'S', 'B', 'M', or 'L'. Got: {size}\n"
+                         "Model sizes:\n  - S (Small): 5.6M params\n  - B (Base): 10.5M params\n"
+                         "  - M (Medium): 17.6M params\n  - L (Large): 61.8M params")
+    if k not in (3, 5, 7):
+        raise ValueError(f"MedNeXt kernel_size must be 3, 5, or 7. Got: {k}\nRecommended: Start with kernel_size=3")
+    model = create_mednext_v1(cfg.model.in_channels, _num_classes(cfg, head_cfg), size, k, ds)
+    style = getattr(mcfg, "checkpoint_style", None)
+    if style is not None:
+        if style != "outside_block":
+            raise ValueError(f"model.mednext.checkpoint_style must be None or 'outside_block', got: {style!r}")
+        model.outside_block_checkpointing = True
+    if head_cfg:
+        return MedNeXtMultiHeadWrapper(model, head_cfg, primary_head=primary)
+    return MedNeXtWrapper(model, deep_supervision=ds)
+
+
+@register_architecture("mednext_custom")
+def build_mednext_custom(cfg) -> ConnectomicsModel:
+    """MedNeXt with explicit architecture parameters (``mednext_models.py:400-483``)."""
+    head_cfg, primary = _heads_cfg(cfg)
+    m = cfg.model.mednext
+    params = dict(
+        in_channels=cfg.model.in_channels, n_channels=getattr(m, "base_channels", 32),
+        n_classes=_num_classes(cfg, head_cfg), exp_r=getattr(m, "exp_r", 4),
+        kernel_size=getattr(m, "kernel_size", 7),
+        deep_supervision=getattr(cfg.model.loss, "deep_supervision", False),
+        do_res=getattr(m, "do_res", True), do_res_up_down=getattr(m, "do_res_up_down", True),
+        block_counts=getattr(m, "block_counts", [2] * 9), checkpoint_style=getattr(m, "checkpoint_style", None),
+        norm_type=getattr(m, "norm", "group"), dim=getattr(m, "dim", "3d"), grn=getattr(m, "grn", False))
+    if params["dim"] not in ("2d", "3d"):
+        raise ValueError(f"mednext_dim must be '2d' or '3d', got: {params['dim']}")
+    if params["norm_type"] not in ("group", "layer"):
+        raise ValueError(f"mednext_norm must be 'group' or 'layer', got: {params['norm_type']}")
+    if len(params["block_counts"]) != 9:
+        raise ValueError("mednext_block_counts must have exactly 9 elements (one per level), "
+                         f"got {len(params['block_counts'])}")
+    if isinstance(params["exp_r"], (list, tuple)) or hasattr(params["exp_r"], "__iter__"):
+        params["exp_r"] = [int(v) for v in params["exp_r"]]
+    params["block_counts"] = [int(v) for v in params["block_counts"]]
+    model = MedNeXt(**params)
+    if head_cfg:
+        return MedNeXtMultiHeadWrapper(model, head_cfg, primary_head=primary)
+    return MedNeXtWrapper(model, deep_supervision=params["deep_supervision"])
+
+
+__all__ = ["MedNeXt", "MedNeXtBlock", "MedNeXtDownBlock", "MedNeXtUpBlock", "OutBlock", "MedNeXtWrapper",
+           "MedNeXtTaskHead", "MedNeXtMultiHeadWrapper", "build_mednext", "build_mednext_custom",
+           "create_mednext_v1"]

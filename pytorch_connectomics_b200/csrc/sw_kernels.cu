@@ -1,0 +1,339 @@
+// pcb200 — sliding-window tiled inference: integer grid logic (host) and the crop/pad,
+// overlap-add and normalise kernels (device).  Behaviour follows the reference's
+// connectomics/inference/window.py and the grid part of inference/lazy.py (cited per function
+// in include/pcb200.h).  All of this is HBM-bound streaming work: 128-bit-friendly contiguous
+// x-rows, one pass per tensor, no atomics (windows are accumulated in launch order, so fp sums
+// associate exactly like the reference's sequential `+=`).
+#include <math.h>
+#include <vector>
+
+#include "../../include/pcb200.h"
+#include "pcb_common.cuh"
+
+namespace pcb {
+
+// ---- dtype-generic "compute in fp32, round to T after every op" arithmetic (torch CPU/CUDA
+//      elementwise semantics for f16/bf16)
+template <typename T> struct DT;
+template <> struct DT<float> {
+  __host__ __device__ static float ld(float v) { return v; }
+  __host__ __device__ static float st(float v) { return v; }
+};
+template <> struct DT<__half> {
+  __host__ __device__ static float ld(__half v) { return __half2float(v); }
+  __host__ __device__ static __half st(float v) { return __float2half_rn(v); }
+};
+template <> struct DT<__nv_bfloat16> {
+  __host__ __device__ static float ld(__nv_bfloat16 v) { return __bfloat162float(v); }
+  __host__ __device__ static __nv_bfloat16 st(float v) { return __float2bfloat16_rn(v); }
+};
+template <typename T> __host__ __device__ inline float rnd(float v) { return DT<T>::ld(DT<T>::st(v)); }
+
+static inline double clamp01(double o) { return o < 0.0 ? 0.0 : (o > 0.99 ? 0.99 : o); }
+
+// window.py:107-118
+static void axis_starts_eager(int64_t img, int64_t roi, int64_t stride, std::vector<int64_t>& out) {
+  out.clear();
+  if (img <= roi) { out.push_back(0); return; }
+  if (stride < 1) stride = 1;
+  for (int64_t s = 0; s <= img - roi; s += stride) out.push_back(s);
+  if (out.back() != img - roi) out.push_back(img - roi);
+}
+// lazy.py:269-286 (_snap_offsets with border_pad = roi - stride)
+static void axis_starts_lazy(int64_t img, int64_t roi, int64_t stride, std::vector<int64_t>& out) {
+  out.clear();
+  if (img <= roi) { out.push_back(0); return; }
+  if (stride < 1) stride = 1;
+  int64_t bp = roi - stride; if (bp < 0) bp = 0;
+  const int64_t lo = -bp, hi = img - roi + bp;
+  for (int64_t s = lo; s <= hi; s += stride) out.push_back(s);
+  if (out.empty() || out.back() != hi) out.push_back(hi);
+}
+
+template <typename T>
+static void host_axis_kernel_bump(int64_t n, std::vector<float>& k) {
+  // window.py:178-187 evaluated op-by-op in dtype T
+  const float tiny = sizeof(T) == 4 ? 1.17549435e-38f : (std::is_same<T, __half>::value ? 6.103515625e-05f : 1.17549435e-38f);
+  k.resize(n);
+  float mx = -INFINITY;
+  const float denom_n = (float)((double)n + 1.0);
+  for (int64_t i = 0; i < n; ++i) {
+    float idx = rnd<T>((float)i);
+    float u = rnd<T>(idx + 1.0f);
+    u = rnd<T>(u / denom_n);
+    u = rnd<T>(u * 2.0f);
+    u = rnd<T>(u - 1.0f);
+    float d = rnd<T>(1.0f - rnd<T>(u * u));
+    if (d < tiny) d = tiny;
+    float e = rnd<T>(expf(rnd<T>(-1.0f / d)));
+    k[i] = e;
+    if (e > mx) mx = e;
+  }
+  if (mx < tiny) mx = tiny;
+  for (int64_t i = 0; i < n; ++i) k[i] = rnd<T>(k[i] / mx);
+}
+
+template <typename T>
+__global__ void imap_kernel(T* __restrict__ out, const float* __restrict__ k0, const float* __restrict__ k1,
+                            const float* __restrict__ k2, int64_t n0, int64_t n1, int64_t n2, int blend,
+                            float tiny, float min_value) {
+  const int64_t total = n0 * n1 * n2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t x = i % n2, y = (i / n2) % n1, z = i / (n1 * n2);
+    float v;
+    if (blend == PCB_BLEND_CONSTANT) {
+      v = 1.0f;
+      if (min_value > 0.f) v = fmaxf(v, min_value);
+    } else if (blend == PCB_BLEND_BUMP) {
+      v = rnd<T>(rnd<T>(k0[z] * k1[y]) * k2[x]);
+      v = fmaxf(v, tiny);
+      if (min_value > 0.f) v = fmaxf(v, min_value);
+    } else {  // distance transform: min over axes of min(i+1, n-i)  (window.py:234-243)
+      v = fminf(fminf(k0[z], k1[y]), k2[x]);
+    }
+    out[i] = DT<T>::st(v);
+  }
+}
+
+struct ExtractArgs {
+  int64_t C, D, H, W, r0, r1, r2;
+  float cval;
+  int mode;
+};
+
+__device__ __forceinline__ int64_t pad_index(int64_t p, int64_t lo, int64_t hi, int mode) {
+  // coordinate p outside the in-image crop [lo,hi) -> source index (relative to the crop, like
+  // F.pad applied to the cropped tensor, window.py:492-522)
+  if (p >= lo && p < hi) return p;
+  if (mode == PCB_PAD_REFLECT) return p < lo ? lo + (lo - p) : (hi - 1) - (p - (hi - 1));
+  if (mode == PCB_PAD_REPLICATE) return p < lo ? lo : hi - 1;
+  if (mode == PCB_PAD_CIRCULAR) { int64_t n = hi - lo; int64_t m = (p - lo) % n; if (m < 0) m += n; return lo + m; }
+  return -1;
+}
+
+template <typename T>
+__global__ void extract_kernel(const T* __restrict__ vol, T* __restrict__ out, const int64_t* __restrict__ starts,
+                               const int* __restrict__ modes, ExtractArgs a) {
+  const int64_t w = blockIdx.y;  // window in batch
+  const int64_t s0 = starts[3 * w], s1 = starts[3 * w + 1], s2 = starts[3 * w + 2];
+  const int mode = modes[w];
+  const int64_t lo0 = max((int64_t)0, s0), hi0 = min(a.D, s0 + a.r0);
+  const int64_t lo1 = max((int64_t)0, s1), hi1 = min(a.H, s1 + a.r1);
+  const int64_t lo2 = max((int64_t)0, s2), hi2 = min(a.W, s2 + a.r2);
+  const int64_t per = a.C * a.r0 * a.r1 * a.r2;
+  const T cv = DT<T>::st(a.cval);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < per; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t x = i % a.r2, y = (i / a.r2) % a.r1, z = (i / (a.r2 * a.r1)) % a.r0, c = i / (a.r2 * a.r1 * a.r0);
+    const int64_t pz = pad_index(s0 + z, lo0, hi0, mode), py = pad_index(s1 + y, lo1, hi1, mode),
+                  px = pad_index(s2 + x, lo2, hi2, mode);
+    T v = cv;
+    if (pz >= 0 && py >= 0 && px >= 0) v = vol[((c * a.D + pz) * a.H + py) * a.W + px];
+    out[w * per + i] = v;
+  }
+}
+
+struct AccArgs {
+  int64_t Cout, r0, r1, r2, o0, o1, o2, p0, p1, p2, q0, q1, q2, b0, b1, b2;
+};
+
+template <typename T>
+__global__ void accumulate_kernel(const T* __restrict__ pred, const T* __restrict__ map, T* __restrict__ value,
+                                  T* __restrict__ weight, AccArgs a) {
+  const int64_t nbox = a.b0 * a.b1 * a.b2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nbox; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t x = i % a.b2, y = (i / a.b2) % a.b1, z = i / (a.b2 * a.b1);
+    const int64_t pi = ((a.p0 + z) * a.r1 + (a.p1 + y)) * a.r2 + (a.p2 + x);   // index in the window
+    const int64_t oi = ((a.q0 + z) * a.o1 + (a.q1 + y)) * a.o2 + (a.q2 + x);   // index in the output
+    const float w = DT<T>::ld(map[pi]);
+    weight[oi] = DT<T>::st(__fadd_rn(DT<T>::ld(weight[oi]), w));
+    const int64_t pstride = a.r0 * a.r1 * a.r2, ostride = a.o0 * a.o1 * a.o2;
+    for (int64_t c = 0; c < a.Cout; ++c) {
+      const float prod = rnd<T>(__fmul_rn(DT<T>::ld(pred[c * pstride + pi]), w));
+      value[c * ostride + oi] = DT<T>::st(__fadd_rn(DT<T>::ld(value[c * ostride + oi]), prod));
+    }
+  }
+}
+
+template <typename T>
+__global__ void normalize_kernel(T* __restrict__ value, const T* __restrict__ weight, int64_t Cout, int64_t nvox,
+                                 float floor_) {
+  const int64_t total = Cout * nvox;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const float d = rnd<T>(fmaxf(DT<T>::ld(weight[i % nvox]), floor_));
+    value[i] = DT<T>::st(__fdiv_rn(DT<T>::ld(value[i]), d));
+  }
+}
+
+static inline int grid_for(int64_t n, int threads = 256) {
+  int64_t b = (n + threads - 1) / threads;
+  const int64_t cap = 148 * 16;  // a few waves of resident CTAs per SM; grid-stride covers the rest
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace pcb
+
+using namespace pcb;
+
+extern "C" int pcb_sw_scan_interval(const int64_t image[3], const int64_t roi[3], const double overlap[3],
+                                    int64_t out[3]) {
+  PCB_CHECK_ARG(image && roi && overlap && out, "pcb_sw_scan_interval: null argument");
+  for (int a = 0; a < 3; ++a) {
+    PCB_CHECK_ARG(roi[a] > 0, "roi_size must contain positive values");
+    if (image[a] <= roi[a]) { out[a] = image[a]; continue; }
+    // Python: max(1, int(round(roi * (1 - ov))))  — round() is round-half-even == nearbyint
+    const double v = nearbyint((double)roi[a] * (1.0 - clamp01(overlap[a])));
+    out[a] = v < 1.0 ? 1 : (int64_t)v;
+  }
+  return PCB_OK;
+}
+
+extern "C" int pcb_sw_plan(int grid_kind, const int64_t image[3], const int64_t roi[3], const double overlap[3],
+                           const int64_t region[6], int64_t* starts_out, int64_t capacity, int64_t* count_out) {
+  PCB_CHECK_ARG(image && roi && overlap && count_out, "pcb_sw_plan: null argument");
+  PCB_CHECK_ARG(grid_kind >= PCB_GRID_EAGER && grid_kind <= PCB_GRID_LAZY_SNAP, "pcb_sw_plan: bad grid kind %d", grid_kind);
+  std::vector<int64_t> ax[3];
+  int64_t iv[3];
+  if (grid_kind == PCB_GRID_LAZY_SNAP) {
+    for (int a = 0; a < 3; ++a) {  // lazy.py:311-314: int(roi * (1 - overlap)) truncation, overlap NOT clamped
+      const double v = (double)roi[a] * (1.0 - overlap[a]);
+      iv[a] = (int64_t)v; if (iv[a] < 1) iv[a] = 1;
+    }
+  } else {
+    int rc = pcb_sw_scan_interval(image, roi, overlap, iv);
+    if (rc) return rc;
+  }
+  for (int a = 0; a < 3; ++a) {
+    if (grid_kind == PCB_GRID_EAGER) axis_starts_eager(image[a], roi[a], iv[a], ax[a]);
+    else axis_starts_lazy(image[a], roi[a], iv[a], ax[a]);
+    if (region) {  // lazy.py:351-358
+      std::vector<int64_t> keep;
+      for (int64_t o : ax[a]) if (o < region[3 + a] && o + roi[a] > region[a]) keep.push_back(o);
+      ax[a].swap(keep);
+    }
+  }
+  const int64_t total = (int64_t)ax[0].size() * (int64_t)ax[1].size() * (int64_t)ax[2].size();
+  *count_out = total;
+  if (starts_out) {
+    int64_t i = 0;
+    for (int64_t z : ax[0]) for (int64_t y : ax[1]) for (int64_t x : ax[2]) {
+      if (i >= capacity) return PCB_OK;
+      starts_out[3 * i] = z; starts_out[3 * i + 1] = y; starts_out[3 * i + 2] = x; ++i;
+    }
+  }
+  return PCB_OK;
+}
+
+template <typename T>
+static int imap_impl(int blend, const int64_t roi[3], int ndim, double min_value, void* out, cudaStream_t st) {
+  std::vector<float> k[3];
+  const bool is_half = std::is_same<T, __half>::value;
+  const float tiny = is_half ? 6.103515625e-05f : 1.17549435e-38f;
+  for (int a = 0; a < 3; ++a) {
+    if (blend == PCB_BLEND_BUMP) host_axis_kernel_bump<T>(roi[a], k[a]);
+    else {
+      k[a].resize(roi[a]);
+      if (a < 3 - ndim) { for (auto& v : k[a]) v = INFINITY; continue; }  // padded leading axis
+      for (int64_t i = 0; i < roi[a]; ++i) {
+        const float c = rnd<T>((float)i);
+        k[a][i] = fminf(rnd<T>(c + 1.0f), rnd<T>(rnd<T>((float)roi[a]) - c));
+      }
+    }
+  }
+  float* dk = nullptr;
+  const int64_t tot = roi[0] + roi[1] + roi[2];
+  if (cudaMallocAsync(&dk, tot * sizeof(float), st) != cudaSuccess) { set_error("imap: cudaMallocAsync failed"); return PCB_ERR_CUDA; }
+  cudaMemcpyAsync(dk, k[0].data(), roi[0] * 4, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dk + roi[0], k[1].data(), roi[1] * 4, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dk + roi[0] + roi[1], k[2].data(), roi[2] * 4, cudaMemcpyHostToDevice, st);
+  cudaStreamSynchronize(st);  // host staging vectors die at return (one-off setup call, not the tile loop)
+  const int64_t n = roi[0] * roi[1] * roi[2];
+  const float mv = min_value > 0 ? rnd<T>((float)min_value) : 0.f;
+  imap_kernel<T><<<grid_for(n), 256, 0, st>>>((T*)out, dk, dk + roi[0], dk + roi[0] + roi[1], roi[0], roi[1], roi[2],
+                                               blend, tiny, mv);
+  cudaFreeAsync(dk, st);
+  PCB_CHECK_LAUNCH("pcb_sw_importance_map");
+  return PCB_OK;
+}
+
+extern "C" int pcb_sw_importance_map(int blend, const int64_t roi[3], int ndim, int dtype, double min_value,
+                                     void* map_out, void* stream) {
+  PCB_CHECK_ARG(roi && map_out, "pcb_sw_importance_map: null argument");
+  PCB_CHECK_ARG(roi[0] > 0 && roi[1] > 0 && roi[2] > 0, "roi_size must contain positive values");
+  PCB_CHECK_ARG(blend >= 0 && blend <= 2, "unsupported blending mode %d", blend);
+  PCB_CHECK_ARG(ndim >= 1 && ndim <= 3, "ndim must be 1..3");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == PCB_F32) return imap_impl<float>(blend, roi, ndim, min_value, map_out, st);
+  if (dtype == PCB_F16) return imap_impl<__half>(blend, roi, ndim, min_value, map_out, st);
+  if (dtype == PCB_BF16) return imap_impl<__nv_bfloat16>(blend, roi, ndim, min_value, map_out, st);
+  set_error("pcb_sw_importance_map: bad dtype %d", dtype);
+  return PCB_ERR_INVALID;
+}
+
+extern "C" int pcb_sw_extract(const void* vol, int dtype, int64_t C, const int64_t image[3], const int64_t roi[3],
+                              const int64_t* starts, int64_t n, int pad_mode, double cval, void* out, void* stream) {
+  PCB_CHECK_ARG(vol && image && roi && starts && out, "pcb_sw_extract: null argument");
+  PCB_CHECK_ARG(n > 0 && n <= 65535, "pcb_sw_extract: batch of %lld windows unsupported", (long long)n);
+  PCB_CHECK_ARG(pad_mode >= 0 && pad_mode <= 3, "pcb_sw_extract: bad padding mode %d", pad_mode);
+  cudaStream_t st = (cudaStream_t)stream;
+  // per-window fallback to constant when a reflect/circular pad >= the cropped dim (window.py:509-518)
+  std::vector<int> modes(n, pad_mode);
+  for (int64_t w = 0; w < n; ++w) {
+    if (pad_mode != PCB_PAD_REFLECT && pad_mode != PCB_PAD_CIRCULAR) break;
+    for (int a = 0; a < 3; ++a) {
+      const int64_t s = starts[3 * w + a], e = s + roi[a];
+      const int64_t lo = s > 0 ? s : 0, hi = e < image[a] ? e : image[a];
+      const int64_t before = s < 0 ? -s : 0, after = e > image[a] ? e - image[a] : 0;
+      if (before >= hi - lo || after >= hi - lo) modes[w] = PCB_PAD_CONSTANT;
+    }
+  }
+  int64_t* dstarts = nullptr;
+  const size_t sb = n * 3 * sizeof(int64_t), mb = n * sizeof(int);
+  if (cudaMallocAsync(&dstarts, sb + mb, st) != cudaSuccess) { set_error("extract: cudaMallocAsync failed"); return PCB_ERR_CUDA; }
+  int* dmodes = (int*)((char*)dstarts + sb);
+  cudaMemcpyAsync(dstarts, starts, sb, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(dmodes, modes.data(), mb, cudaMemcpyHostToDevice, st);
+  cudaStreamSynchronize(st);  // `modes` is a host temporary
+  ExtractArgs a{C, image[0], image[1], image[2], roi[0], roi[1], roi[2], (float)cval, pad_mode};
+  const int64_t per = C * roi[0] * roi[1] * roi[2];
+  dim3 grid(grid_for(per), (unsigned)n);
+  if (dtype == PCB_F32) extract_kernel<float><<<grid, 256, 0, st>>>((const float*)vol, (float*)out, dstarts, dmodes, a);
+  else if (dtype == PCB_F16) extract_kernel<__half><<<grid, 256, 0, st>>>((const __half*)vol, (__half*)out, dstarts, dmodes, a);
+  else if (dtype == PCB_BF16) extract_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)vol, (__nv_bfloat16*)out, dstarts, dmodes, a);
+  else { cudaFreeAsync(dstarts, st); set_error("pcb_sw_extract: bad dtype %d", dtype); return PCB_ERR_INVALID; }
+  cudaFreeAsync(dstarts, st);
+  PCB_CHECK_LAUNCH("pcb_sw_extract");
+  return PCB_OK;
+}
+
+extern "C" int pcb_sw_accumulate(const void* pred, const void* map, void* value, void* weight, int dtype,
+                                 int64_t Cout, const int64_t roi[3], const int64_t out_size[3],
+                                 const int64_t pred_lo[3], const int64_t out_lo[3], const int64_t box[3],
+                                 void* stream) {
+  PCB_CHECK_ARG(pred && map && value && weight && roi && out_size && pred_lo && out_lo && box, "pcb_sw_accumulate: null argument");
+  for (int a = 0; a < 3; ++a) {
+    PCB_CHECK_ARG(box[a] > 0 && pred_lo[a] >= 0 && pred_lo[a] + box[a] <= roi[a], "pcb_sw_accumulate: window box outside the ROI");
+    PCB_CHECK_ARG(out_lo[a] >= 0 && out_lo[a] + box[a] <= out_size[a], "pcb_sw_accumulate: box outside the accumulator");
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  AccArgs a{Cout, roi[0], roi[1], roi[2], out_size[0], out_size[1], out_size[2], pred_lo[0], pred_lo[1], pred_lo[2],
+            out_lo[0], out_lo[1], out_lo[2], box[0], box[1], box[2]};
+  const int64_t nbox = box[0] * box[1] * box[2];
+  if (dtype == PCB_F32) accumulate_kernel<float><<<grid_for(nbox), 256, 0, st>>>((const float*)pred, (const float*)map, (float*)value, (float*)weight, a);
+  else if (dtype == PCB_F16) accumulate_kernel<__half><<<grid_for(nbox), 256, 0, st>>>((const __half*)pred, (const __half*)map, (__half*)value, (__half*)weight, a);
+  else if (dtype == PCB_BF16) accumulate_kernel<__nv_bfloat16><<<grid_for(nbox), 256, 0, st>>>((const __nv_bfloat16*)pred, (const __nv_bfloat16*)map, (__nv_bfloat16*)value, (__nv_bfloat16*)weight, a);
+  else { set_error("pcb_sw_accumulate: bad dtype %d", dtype); return PCB_ERR_INVALID; }
+  PCB_CHECK_LAUNCH("pcb_sw_accumulate");
+  return PCB_OK;
+}
+
+extern "C" int pcb_sw_normalize(void* value, const void* weight, int dtype, int64_t Cout, int64_t nvox, void* stream) {
+  PCB_CHECK_ARG(value && weight && Cout > 0 && nvox > 0, "pcb_sw_normalize: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n = Cout * nvox;
+  if (dtype == PCB_F32) normalize_kernel<float><<<grid_for(n), 256, 0, st>>>((float*)value, (const float*)weight, Cout, nvox, 1.0e-4f);
+  else if (dtype == PCB_F16) normalize_kernel<__half><<<grid_for(n), 256, 0, st>>>((__half*)value, (const __half*)weight, Cout, nvox, 1.0e-4f);
+  else if (dtype == PCB_BF16) normalize_kernel<__nv_bfloat16><<<grid_for(n), 256, 0, st>>>((__nv_bfloat16*)value, (const __nv_bfloat16*)weight, Cout, nvox, 1.0e-4f);
+  else { set_error("pcb_sw_normalize: bad dtype %d", dtype); return PCB_ERR_INVALID; }
+  PCB_CHECK_LAUNCH("pcb_sw_normalize");
+  return PCB_OK;
+}

@@ -1,0 +1,13 @@
+"""Sliding-window inference on the B200 engine (drop-in for ``connectomics.inference`` window API)."""
+
+from .window import (EagerSlidingWindowEngine, apply_border_mask, build_sliding_accumulator_weight_maps,
+                     build_sliding_importance_map, build_sliding_inferer, compute_importance_map,
+                     compute_scan_interval, dense_patch_slices, is_distance_transform_blending,
+                     normalize_weighted_accumulator, resolve_border_mask, resolve_inferer_overlap,
+                     resolve_inferer_roi_size, resolve_model_output_dtype)
+
+__all__ = ["EagerSlidingWindowEngine", "apply_border_mask", "build_sliding_accumulator_weight_maps",
+           "build_sliding_importance_map", "build_sliding_inferer", "compute_importance_map",
+           "compute_scan_interval", "dense_patch_slices", "is_distance_transform_blending",
+           "normalize_weighted_accumulator", "resolve_border_mask", "resolve_inferer_overlap",
+           "resolve_inferer_roi_size", "resolve_model_output_dtype"]

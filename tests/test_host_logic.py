@@ -1,0 +1,151 @@
+"""CPU-side tests: the C-ABI library loads and exports every declared symbol; integer grid logic
+(host C code) is bit-exact with the reference-generated golden vectors; registry seam semantics
+(reference tests/unit/test_architecture_registry.py:55-200)."""
+import ctypes
+import warnings
+from types import SimpleNamespace as NS
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.make_goldens import GRID_CASES
+from oracle import window_oracle as O
+from pytorch_connectomics_b200 import _lib
+from pytorch_connectomics_b200 import architectures as A
+from pytorch_connectomics_b200.inference import window as W
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    _lib.build()
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.lib()
+    names = _lib.exported_symbols()
+    assert len(names) >= 12
+    for n in names:
+        assert hasattr(lib, n), n
+    assert lib.pcb_version() >= 100
+
+
+def test_grid_bit_exact_vs_reference_goldens(window_goldens):
+    g = window_goldens
+    for i, (img, roi, ov) in enumerate(GRID_CASES):
+        assert list(W.compute_scan_interval(img, roi, overlap=ov)) == g[f"grid{i}_interval"].tolist()
+        starts = W._plan(_lib.GRID_EAGER, img, roi, ov)
+        assert len(starts) == int(g[f"grid{i}_count"][0])
+        if f"grid{i}_starts" in g:
+            assert np.array_equal(np.asarray(starts, dtype=np.int64), g[f"grid{i}_starts"])
+            iv = W.compute_scan_interval(img, roi, overlap=ov)
+            assert W.dense_patch_slices(img, roi, iv, return_slice=False) == starts
+        for a in range(3):
+            assert sorted({s[a] for s in starts}) == g[f"grid{i}_axis{a}"].tolist()
+
+
+def test_lazy_grid_matches_oracle():
+    for img, roi, ov in [((2048,) * 3, (160,) * 3, 0.5), ((12, 14, 13), (6, 6, 6), 0.5), ((100, 90, 80), (32, 16, 24), 0.3)]:
+        for snap, kind in ((False, _lib.GRID_LAZY), (True, _lib.GRID_LAZY_SNAP)):
+            per_axis = O.lazy_axis_offsets(img, roi, (ov,) * 3, snap)
+            n = len(per_axis[0]) * len(per_axis[1]) * len(per_axis[2])
+            starts = W._plan(kind, img, roi, ov)
+            assert len(starts) == n
+            if n < 50000:
+                for a in range(3):
+                    assert sorted({s[a] for s in starts}) == per_axis[a]
+    recs = O.lazy_region_records((12, 14, 13), (6, 6, 6), (0.5,) * 3, (3, 2, 4), (9, 11, 13), False)
+    starts = W._plan(_lib.GRID_LAZY, (12, 14, 13), (6, 6, 6), 0.5, region=((3, 2, 4), (9, 11, 13)))
+    assert [r[0] for r in recs] == starts
+
+
+def test_scan_interval_errors_and_rounding():
+    assert W.compute_scan_interval((64,) * 3, (10,) * 3, overlap=0.75) == (2, 2, 2)    # 2.5 -> 2 (half-even)
+    assert W.compute_scan_interval((64,) * 3, (14,) * 3, overlap=0.75) == (4, 4, 4)    # 3.5 -> 4
+    assert W.compute_scan_interval((5, 64), (8, 8), overlap=(0.5, 2.0)) == (5, 1)       # clamp 0.99 -> max(1, round(.08))
+    with pytest.raises(ValueError):
+        W.compute_scan_interval((8, 8, 8), (0, 8, 8), overlap=0.5)
+
+
+def test_registry_seam():
+    assert A.is_architecture_available("mednext") and A.is_architecture_available("mednext_custom")
+    assert A.list_architectures() == sorted(A.list_architectures())
+    with pytest.raises(ValueError, match="not found"):
+        A.get_architecture_builder("nope")
+
+    @A.register_architecture("tmp_arch")
+    def _b(cfg):
+        """doc line"""
+        return torch.nn.Identity()
+
+    assert A.get_architecture_builder("tmp_arch") is _b
+    assert A.get_architecture_info()["tmp_arch"]["doc"] == "doc line"
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        A.register_architecture("tmp_arch")(_b)
+    assert any(issubclass(w.category, UserWarning) for w in rec)
+    A.unregister_architecture("tmp_arch")
+    with pytest.raises(ValueError):
+        A.unregister_architecture("tmp_arch")
+
+
+def _cfg(**mednext):
+    return NS(model=NS(arch=NS(type="mednext"), in_channels=1, out_channels=2, mednext=NS(**mednext),
+                       loss=NS(deep_supervision=False)))
+
+
+def test_builders_validation_and_state_dict_parity():
+    from oracle.mednext_oracle import create_mednext_v1
+    m = A.build_model(_cfg(size="S", kernel_size=3))
+    info = m.get_model_info()
+    assert info["name"] == "MedNeXtWrapper" and info["parameters"] == info["trainable_parameters"]
+    ref = create_mednext_v1(1, 2, "S", 3, False)
+    assert list(ref.state_dict().keys()) == list(m.model.state_dict().keys())
+    m.model.load_state_dict(ref.state_dict(), strict=True)
+    with pytest.raises(ValueError, match="model_size"):
+        A.build_model(_cfg(size="XL", kernel_size=3))
+    with pytest.raises(ValueError, match="kernel_size"):
+        A.build_model(_cfg(size="S", kernel_size=4))
+    with pytest.raises(ValueError, match="checkpoint_style"):
+        A.build_model(_cfg(size="S", kernel_size=3, checkpoint_style="inside"))
+    assert A.build_model(_cfg(size="S", kernel_size=3, checkpoint_style="outside_block")).model.outside_block_checkpointing
+    cfg = _cfg(size="S", kernel_size=3)
+    cfg.model.heads = {"aff": {"out_channels": 3, "num_blocks": 1}, "sdt": {"out_channels": 1}}
+    mh = A.build_model(cfg)
+    assert mh.primary_head == "aff" and mh.feature_channels == 32
+    assert mh.head_specs["sdt"] == {"out_channels": 1, "num_blocks": 0, "hidden_channels": 32}
+    cfg.model.primary_head = "nope"
+    with pytest.raises(ValueError, match="primary_head"):
+        A.build_model(cfg)
+
+
+def test_no_cpu_fallback():
+    m = A.build_model(_cfg(size="S", kernel_size=3))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 1, 32, 32, 32))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        W.build_sliding_importance_map((8, 8, 8), mode="bump", device="cpu")
+    eng = W.EagerSlidingWindowEngine(roi_size=(8, 8, 8), sw_batch_size=1, overlap=0.5, mode="bump",
+                                     padding_mode="constant", cval=0.0)
+    with pytest.raises(ValueError):
+        eng(inputs=torch.zeros(2, 1, 8, 8, 8), network=lambda t: t)
+    with pytest.raises(ValueError):
+        eng(inputs=torch.zeros(1, 8, 8), network=lambda t: t)
+
+
+def test_config_resolvers():
+    cfg = NS(inference=NS(sliding_window=NS(window_size=[16, 32, 32], overlap=[0.5, 1.5, -1], sw_batch_size=None,
+                                            blending="Bump ", padding_mode="reflect", cval=0.5, border_mask=[2])),
+             data=NS(dataloader=NS(batch_size=3)))
+    assert W.resolve_inferer_roi_size(cfg) == (16, 32, 32)
+    assert W.resolve_inferer_overlap(cfg, (16, 32, 32)) == (0.5, 0.99, 0.0)
+    rt = W._resolve_sliding_window_runtime(cfg, (16, 32, 32))
+    assert rt["sw_batch_size"] == 3 and rt["mode"] == "bump" and rt["padding_mode"] == "reflect" and rt["cval"] == 0.5
+    assert W.resolve_border_mask(cfg, 3) == [2, 2, 2]
+    eng = W.build_sliding_inferer(cfg)
+    assert eng.roi_size == (16, 32, 32) and eng.sw_batch_size == 3
+    assert W.build_sliding_inferer(NS()) is None
+    assert W.resolve_model_output_dtype(NS(inference=NS(model=NS(output_dtype="torch.float16")))) == torch.float16
+    with pytest.raises(ValueError):
+        W.resolve_model_output_dtype(NS(inference=NS(model=NS(output_dtype="int8"))))
+    assert W.is_distance_transform_blending("BANIS")
