@@ -50,12 +50,12 @@ template <int K, int MODE>
 __global__ void __launch_bounds__(256) dwconv_kernel(const uint4* __restrict__ x, const float* __restrict__ w,
                                                      const float* __restrict__ bias, uint4* __restrict__ y,
                                                      double* __restrict__ stats, DwArgs a) {
-  extern __shared__ float s_stats[];  // [2*C]
+  extern __shared__ double s_stats[];  // [2*C] float64: sums stay order-independent to ~1e-16
   constexpr int P = K / 2;
   constexpr int S = (MODE == PCB_DW_DOWN) ? 2 : 1;
   const int C = a.C, CH = C >> 3;
   const int n = blockIdx.y;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_stats[i] = 0.f;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_stats[i] = 0.0;
   __syncthreads();
 
   const int nstrip = (a.Wo + DW_XB - 1) / DW_XB;
@@ -179,13 +179,13 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const uint4* __restrict__ x
   if (active && (!shuffle_ok || (threadIdx.x & 31) < CH)) {
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      atomicAdd(&s_stats[cc * 8 + c], ssum[c]);
-      atomicAdd(&s_stats[C + cc * 8 + c], ssq[c]);
+      atomicAdd(&s_stats[cc * 8 + c], (double)ssum[c]);
+      atomicAdd(&s_stats[C + cc * 8 + c], (double)ssq[c]);
     }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x)
-    atomicAdd(&stats[(int64_t)n * 2 * C + i], (double)s_stats[i]);
+    atomicAdd(&stats[(int64_t)n * 2 * C + i], s_stats[i]);
 }
 
 // ============================================================================ fused MLP (tcgen05)
@@ -513,7 +513,7 @@ extern "C" int pcb_dwconv_fwd(const void* x, const float* w, const float* b, voi
   PCB_CHECK_ARG(a.Do > 0 && a.Ho > 0 && a.Wo > 0, "pcb_dwconv_fwd: empty output");
   const int64_t items = (int64_t)a.Do * a.Ho * ((a.Wo + DW_XB - 1) / DW_XB) * (C / 8);
   dim3 grid((unsigned)((items + 255) / 256), (unsigned)N);
-  const size_t smem = 2 * C * sizeof(float);
+  const size_t smem = 2 * C * sizeof(double);
   cudaStream_t st = (cudaStream_t)stream;
   if (k == 3) launch_dw<3>(mode, grid, smem, st, (const uint4*)x, w, b, (uint4*)y, stats, a);
   else if (k == 5) launch_dw<5>(mode, grid, smem, st, (const uint4*)x, w, b, (uint4*)y, stats, a);
