@@ -97,6 +97,52 @@ int pcb_mlp_fwd(const void* y, const double* stats, const float* gamma, const fl
 int pcb_head_fwd(const void* x, const float* w, const float* b, void* out, int out_dtype,
                  int64_t N, int64_t C, int64_t ncls, int64_t nvox, void* stream);
 
+/* gradient of pcb_dwconv_fwd w.r.t. its input, with the forward stencil kernel in the dual mode
+ * (SAME<-SAME with flipped taps supplied by the caller, DOWN<-UP, UP<-DOWN); optional fused add:
+ * add_mode 1: dx[o] += add[o]; add_mode 2: dx[o] += add[o/2] where every coordinate of o is even. */
+int pcb_dwconv_bwd_data(const void* dy, const float* w, const void* add, int add_mode, void* dx, int64_t N,
+                        const int64_t dy_size[3], const int64_t dx_size[3], int64_t C, int k, int fwd_mode,
+                        void* stream);
+
+/* ------------------------------------------------------------------ MedNeXt backward ops (training:
+ * what autograd + cuDNN do for the reference under training/lightning/model.py:863-910)
+ *
+ * fused dgrad of pcb_mlp_fwd on tcgen05: recomputes Hpre = norm(y) W2^T, dG = dOut W3, writes
+ * Hact = GELU(Hpre+b2) and dh = dG*GELU'(.) (bf16 [N,Vy,H]), dYhat = dh W2 (bf16 [N,Vy,C]) and the
+ * GroupNorm-backward sums gstats [N,2,C] f64 (sum g, sum g*xhat; caller zeroes).
+ * w3t = conv3.weight^T [H,Co] bf16, w2t = conv2.weight^T [C,H] bf16.  y_size = spatial size of y;
+ * mode UP reads dOut at o = p+1 (dOut spatial = y_size+1). */
+int pcb_mlp_bwd(const void* y, const double* stats, const float* gamma, const float* beta, const void* w2,
+                const float* b2, const void* w3t, const void* w2t, const void* dout, void* hact, void* dh,
+                void* dyhat, double* gstats, int64_t N, const int64_t y_size[3], int64_t C, int64_t H,
+                int64_t Co, int mode, void* stream);
+/* weight gradients: dW[m*ldm + n*ldn] = sum_{sample, v in box} A[mapA(v), m] * B[mapB(v), n]
+ * (m < Ma, n < Nb), db[m] = sum A[mapA(v), m] when `ones`; split-K persistent tcgen05 GEMM with
+ * MN-major operands + deterministic second-stage reduction over `workspace`
+ * (pcb_tn_workspace_floats floats).  Row maps: 0 identity, 1 v+1 per axis, 2 2v, 3 2v+1 (into a
+ * tensor of spatial size a_size / b_size).  stats/gamma/beta != NULL applies GroupNorm to B. */
+int64_t pcb_tn_workspace_floats(int64_t Ma, int64_t Nb, int ones, int64_t N, const int64_t box[3]);
+int pcb_tn_gemm(const void* A, const void* B, const double* stats, const float* gamma, const float* beta,
+                float* workspace, float* dW, int64_t ldm, int64_t ldn, float* db, int64_t N,
+                const int64_t box[3], int mapA, const int64_t a_size[3], int64_t a_cols, int64_t Ma,
+                int mapB, const int64_t b_size[3], int64_t Nb, int ones, void* stream);
+/* row-gather 1x1 conv: out[n, r, :] = A[n, map(r), :K] W[Nw,K]^T (+bias), bf16 in/out (res-conv data
+ * gradients; MedNeXtTaskHead.input_projection, mednext_models.py:169-173). */
+int pcb_pw_fwd(const void* A, const void* W, const float* bias, void* out, int64_t N, const int64_t out_box[3],
+               int map, const int64_t a_size[3], int64_t K, int64_t Nw, void* stream);
+/* GroupNorm(num_groups=C) backward: dy = rstd*gamma*(g - S1/V - xhat*S2/V) (bf16) and dsum[c] += sum dy. */
+int pcb_gn_bwd(const void* g, const void* y, const double* stats, const double* gstats, const float* gamma,
+               void* dy, double* dsum, int64_t N, int64_t C, int64_t V, void* stream);
+/* depthwise weight gradient dW[tap, c] += sum_v center[v,c] * neigh[stride*v - k/2 + tap, c]  (f64 [k^3, C]). */
+int pcb_dwconv_wgrad(const void* center, const void* neigh, double* dW, int64_t N, const int64_t c_size[3],
+                     const int64_t n_size[3], int64_t C, int k, int stride, void* stream);
+/* OutBlock backward: dX (NDHWC bf16), dW [C,ncls] f64 +=, db [ncls] f64 += ; dout NCDHW in `dtype`. */
+int pcb_head_bwd(const void* dout, int dtype, const void* x, const float* w, void* dx, double* dW, double* db,
+                 int64_t N, int64_t C, int64_t ncls, int64_t nvox, void* stream);
+/* stem backward: dW [C,Cin] f64 +=, db [C] f64 += from g (NDHWC bf16) and the NCDHW input. */
+int pcb_stem_bwd(const void* g, const void* x, int in_dtype, double* dW, double* db, int64_t N, int64_t Cin,
+                 int64_t C, int64_t nvox, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

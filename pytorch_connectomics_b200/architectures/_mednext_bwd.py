@@ -1,14 +1,197 @@
-"""autograd.Function wrappers for the MedNeXt ops (backward kernels: csrc/mednext_bwd.cu)."""
+"""``torch.autograd.Function`` wrappers: forward = the inference kernels, backward = csrc/mednext_bwd.cu.
+
+Saved per block: the block input ``x``, the depthwise output ``y`` (bf16) and its GroupNorm
+statistics.  Backward recomputes the expanded activation on the tensor cores (``pcb_mlp_bwd``),
+reduces the weight gradients with a split-K tcgen05 GEMM (``pcb_tn_gemm``), then runs GroupNorm
+backward, the depthwise weight gradient and the depthwise data gradient (the forward stencil kernel
+in its dual mode).  Replaces autograd+cuDNN under ``training/lightning/model.py:863-910``.
+"""
 
 from __future__ import annotations
 
+import ctypes
+from typing import List, Optional
+
 import torch
 
+from .. import _lib as L
+from . import _mednext_ops as ops
 
-class _NotYet(torch.autograd.Function):
+_BF16 = torch.bfloat16
+MAP_IDENT, MAP_PLUS1, MAP_TIMES2, MAP_TIMES2P1 = 0, 1, 2, 3
+
+
+def _pack_pw_T(w):   # Conv3d 1x1 [O,I,1,1,1] -> [I,O] bf16
+    return w.reshape(w.shape[0], w.shape[1]).t().contiguous().to(_BF16)
+
+
+def _pack_dw_flip(w):  # [C,1,k,k,k] -> flipped taps, [k^3, C] f32
+    c = w.shape[0]
+    return w.flip(2, 3, 4).reshape(c, -1).t().contiguous().float()
+
+
+ops._PACKERS.setdefault("pw_T", _pack_pw_T)
+ops._PACKERS.setdefault("dw_flip", _pack_dw_flip)
+
+
+def _cl_grad(g: torch.Tensor) -> torch.Tensor:
+    g = g.contiguous()
+    return g if g.dtype == _BF16 else g.to(_BF16)
+
+
+def _tn(A, B, stats, gamma, beta, dW, ldm, ldn, db, n, box, map_a, a_size, a_cols, ma, map_b, b_size, nb, st):
+    lib = L.lib()
+    lib.pcb_tn_workspace_floats.restype = ctypes.c_int64
+    ones = 1 if db is not None else 0
+    nfl = int(lib.pcb_tn_workspace_floats(ctypes.c_int64(ma), ctypes.c_int64(nb), ones, ctypes.c_int64(n), L.i64x(box)))
+    ws = torch.empty(nfl, device=A.device, dtype=torch.float32)
+    L.check(lib.pcb_tn_gemm(L.ptr(A), L.ptr(B), L.ptr(stats), L.ptr(gamma), L.ptr(beta), L.ptr(ws), L.ptr(dW),
+                            ctypes.c_int64(ldm), ctypes.c_int64(ldn), L.ptr(db), ctypes.c_int64(n), L.i64x(box),
+                            map_a, L.i64x(a_size), ctypes.c_int64(a_cols), ctypes.c_int64(ma), map_b, L.i64x(b_size),
+                            ctypes.c_int64(nb), ones, st), "pcb_tn_gemm")
+
+
+class BlockFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, *a):
-        raise NotImplementedError("pcb200: MedNeXt backward kernels are not built yet; run under torch.no_grad()")
+    def forward(ctx, x, skip, mode, k, do_res, has_rc, *params):
+        out, y, stats = ops.block_forward(x, skip, list(params), mode, k, do_res, has_rc)
+        ctx.save_for_backward(x, y, stats, *params)
+        ctx.cfg = (mode, k, do_res, has_rc, skip is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        mode, k, do_res, has_rc, has_skip = ctx.cfg
+        x, y, stats, *params = ctx.saved_tensors
+        w1, b1, gamma, beta, w2, b2, w3, b3 = params[:8]
+        dout = _cl_grad(dout)
+        dev = x.device
+        lib = L.lib()
+        st = L.stream_ptr(dev)
+        n, xsize, c = int(x.shape[0]), [int(s) for s in x.shape[1:4]], int(x.shape[4])
+        ysize = [int(s) for s in y.shape[1:4]]
+        osize = [int(s) for s in dout.shape[1:4]]
+        h, co = int(w2.shape[0]), int(w3.shape[0])
+        vy = ysize[0] * ysize[1] * ysize[2]
+        g_f32, b_f32 = ops.packed(gamma, "f32"), ops.packed(beta, "f32")
+
+        hact = torch.empty((n, vy, h), device=dev, dtype=_BF16)
+        dh = torch.empty((n, vy, h), device=dev, dtype=_BF16)
+        dyhat = torch.empty((n, *ysize, c), device=dev, dtype=_BF16)
+        gstats = torch.zeros((n, 2, c), device=dev, dtype=torch.float64)
+        L.check(lib.pcb_mlp_bwd(L.ptr(y), L.ptr(stats), L.ptr(g_f32), L.ptr(b_f32), L.ptr(ops.packed(w2, "pw")),
+                                L.ptr(ops.packed(b2, "f32")), L.ptr(ops.packed(w3, "pw_T")), L.ptr(ops.packed(w2, "pw_T")),
+                                L.ptr(dout), L.ptr(hact), L.ptr(dh), L.ptr(dyhat), L.ptr(gstats), ctypes.c_int64(n),
+                                L.i64x(ysize), ctypes.c_int64(c), ctypes.c_int64(h), ctypes.c_int64(co), mode, st),
+                "pcb_mlp_bwd")
+        # ---- pointwise weight gradients (+ bias gradients through the all-ones column)
+        dw3 = torch.empty((co, h), device=dev, dtype=torch.float32)
+        db3 = torch.empty((co,), device=dev, dtype=torch.float32)
+        _tn(dout, hact, None, None, None, dw3, h, 1, db3, n, ysize, MAP_PLUS1 if mode == L.DW_UP else MAP_IDENT,
+            osize, co, co, MAP_IDENT, ysize, h, st)
+        dw2 = torch.empty((h, c), device=dev, dtype=torch.float32)
+        db2 = torch.empty((h,), device=dev, dtype=torch.float32)
+        _tn(dh, y, stats, g_f32, b_f32, dw2, c, 1, db2, n, ysize, MAP_IDENT, ysize, h, h, MAP_IDENT, ysize, c, st)
+        del hact, dh
+        # ---- GroupNorm backward
+        dy = torch.empty_like(y)
+        db1 = torch.zeros((c,), device=dev, dtype=torch.float64)
+        L.check(lib.pcb_gn_bwd(L.ptr(dyhat), L.ptr(y), L.ptr(stats), L.ptr(gstats), L.ptr(g_f32), L.ptr(dy), L.ptr(db1),
+                               ctypes.c_int64(n), ctypes.c_int64(c), ctypes.c_int64(vy), st), "pcb_gn_bwd")
+        dgamma = gstats[:, 1].sum(0).float()
+        dbeta = gstats[:, 0].sum(0).float()
+        del dyhat
+        # ---- depthwise weight gradient
+        dw1 = torch.zeros((k * k * k, c), device=dev, dtype=torch.float64)
+        if mode == L.DW_UP:
+            cen, nei, csz, nsz, stride = x, dy, xsize, ysize, 2
+        else:
+            cen, nei, csz, nsz, stride = dy, x, ysize, xsize, (2 if mode == L.DW_DOWN else 1)
+        L.check(lib.pcb_dwconv_wgrad(L.ptr(cen), L.ptr(nei), L.ptr(dw1), ctypes.c_int64(n), L.i64x(csz), L.i64x(nsz),
+                                     ctypes.c_int64(c), k, stride, st), "pcb_dwconv_wgrad")
+        grads_rc: List[Optional[torch.Tensor]] = []
+        add, add_mode = None, 0
+        if has_rc:
+            wr = params[8]
+            if mode == L.DW_DOWN:   # Conv3d(C, Co, 1, stride 2): weight [Co, C]
+                r = torch.empty((n, *osize, c), device=dev, dtype=_BF16)
+                L.check(lib.pcb_pw_fwd(L.ptr(dout), L.ptr(ops.packed(wr, "pw_T")), None, L.ptr(r), ctypes.c_int64(n),
+                                       L.i64x(osize), MAP_IDENT, L.i64x(osize), ctypes.c_int64(co), ctypes.c_int64(c), st),
+                        "pcb_pw_fwd")
+                dwr = torch.empty((co, c), device=dev, dtype=torch.float32)
+                _tn(dout, x, None, None, None, dwr, c, 1, None, n, osize, MAP_IDENT, osize, co, co, MAP_TIMES2, xsize, c, st)
+                add, add_mode = r, 2
+            else:                   # ConvTranspose3d(C, Co, 1, stride 2): weight [C, Co]
+                r = torch.empty((n, *xsize, c), device=dev, dtype=_BF16)
+                L.check(lib.pcb_pw_fwd(L.ptr(dout), L.ptr(ops.packed(wr, "pw")), None, L.ptr(r), ctypes.c_int64(n),
+                                       L.i64x(xsize), MAP_TIMES2P1, L.i64x(osize), ctypes.c_int64(co), ctypes.c_int64(c), st),
+                        "pcb_pw_fwd")
+                dwr = torch.empty((c, co), device=dev, dtype=torch.float32)
+                _tn(dout, x, None, None, None, dwr, 1, co, None, n, xsize, MAP_TIMES2P1, osize, co, co, MAP_IDENT, xsize, c, st)
+                add, add_mode = r, 1
+            grads_rc = [dwr.reshape(params[8].shape), db3.clone()]
+        elif mode == L.DW_SAME and do_res:
+            add, add_mode = dout, 1
+        # ---- depthwise data gradient (+ residual / res-conv gradient)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            wk = ops.packed(w1, "dw_flip" if mode == L.DW_SAME else "dw")
+            L.check(lib.pcb_dwconv_bwd_data(L.ptr(dy), L.ptr(wk), L.ptr(add), add_mode, L.ptr(dx), ctypes.c_int64(n),
+                                            L.i64x(ysize), L.i64x(xsize), ctypes.c_int64(c), k, mode, st),
+                    "pcb_dwconv_bwd_data")
+        dskip = dout if (has_skip and ctx.needs_input_grad[1]) else None
+        grads = [dw1.t().reshape(w1.shape).float(), db1.float(), dgamma, dbeta,
+                 dw2.reshape(w2.shape), db2, dw3.reshape(w3.shape), db3] + grads_rc
+        return (dx, dskip, None, None, None, None, *grads)
 
 
-StemFn = BlockFn = HeadFn = _NotYet
+class StemFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b):
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError("pcb200: gradient w.r.t. the input volume is not implemented")
+        out = ops.stem_forward(x, w, b)
+        ctx.save_for_backward(x.contiguous(), w)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        g = _cl_grad(g)
+        n, cin, c = int(x.shape[0]), int(x.shape[1]), int(w.shape[0])
+        nvox = int(x.shape[2] * x.shape[3] * x.shape[4])
+        dw = torch.zeros((c, cin), device=g.device, dtype=torch.float64)
+        db = torch.zeros((c,), device=g.device, dtype=torch.float64)
+        L.check(L.lib().pcb_stem_bwd(L.ptr(g), L.ptr(x), L.dtype_code(x.dtype), L.ptr(dw), L.ptr(db), ctypes.c_int64(n),
+                                     ctypes.c_int64(cin), ctypes.c_int64(c), ctypes.c_int64(nvox), L.stream_ptr(g.device)),
+                "pcb_stem_bwd")
+        return None, dw.float().reshape(w.shape), db.float()
+
+
+class HeadFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, out_dtype, conv_layout):
+        out = ops.head_forward(x, w, b, out_dtype, conv_layout)
+        ctx.save_for_backward(x, w)
+        ctx.conv_layout = conv_layout
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w = ctx.saved_tensors
+        dout = dout.contiguous()
+        if dout.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+            dout = dout.float()
+        n, c = int(x.shape[0]), int(x.shape[4])
+        wk = ops.packed(w, "head_conv" if ctx.conv_layout else "head")
+        ncls = int(wk.shape[1])
+        nvox = int(x.shape[1] * x.shape[2] * x.shape[3])
+        dx = torch.empty_like(x)
+        dw = torch.zeros((c, ncls), device=x.device, dtype=torch.float64)
+        db = torch.zeros((ncls,), device=x.device, dtype=torch.float64)
+        L.check(L.lib().pcb_head_bwd(L.ptr(dout), L.dtype_code(dout.dtype), L.ptr(x), L.ptr(wk), L.ptr(dx), L.ptr(dw),
+                                     L.ptr(db), ctypes.c_int64(n), ctypes.c_int64(c), ctypes.c_int64(ncls),
+                                     ctypes.c_int64(nvox), L.stream_ptr(x.device)), "pcb_head_bwd")
+        dwp = (dw.t() if ctx.conv_layout else dw).float().reshape(w.shape)
+        return dx, dwp, db.float(), None, None

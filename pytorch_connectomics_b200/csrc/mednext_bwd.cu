@@ -1,0 +1,950 @@
+// pcb200 — MedNeXt backward kernels for sm_100a (training path).
+//
+//   mlp_bwd_kernel   per 128-voxel tile, all on tcgen05 with fp32 accumulators in TMEM:
+//                      Hpre = norm(y) W2^T ; dG = dOut W3 ; h = Hpre + b2 ;
+//                      Hact = GELU(h) ; dh = dG * GELU'(h) ; dYhat = dh W2
+//                    writes Hact, dh (bf16, consumed by the weight-gradient GEMMs), dYhat (bf16) and the
+//                    two per-(n,c) GroupNorm-backward sums  S1 = sum g, S2 = sum g*xhat  (float64).
+//   tn_gemm_kernel   weight gradients  D[m,n] = sum_v A[v,m] B[v,n]  (reduction over voxels) as a
+//                    persistent split-K tcgen05 GEMM with MN-major operands (the [voxel, channel]
+//                    tiles are fed untransposed), optional GroupNorm-apply on B, optional all-ones
+//                    column (bias gradients), partial sums per CTA + deterministic second stage.
+//   pw_kernel        row-gather 1x1 conv  out[r,:] = A[map(r),:] W^T (+b)   (res-conv data gradients,
+//                    task-head projections)
+//   gn_dy_kernel     dy = rstd*gamma*(g - S1/V - xhat*S2/V)  + per-channel sum(dy) (= conv1 bias grad)
+//   dw_wgrad_kernel  depthwise weight gradient  dW[c,tap] = sum_v center[v,c] * neigh[S v - P + tap, c]
+//   head_bwd / stem_bwd kernels (CUDA cores; tiny channel counts on one side)
+#include "../../include/pcb200.h"
+#include "pcb_common.cuh"
+
+namespace pcb {
+
+enum RowMap { MAP_IDENT = 0, MAP_PLUS1 = 1, MAP_TIMES2 = 2, MAP_TIMES2P1 = 3 };
+constexpr int DW_XB_WG = 4;   // centre voxels per thread along W in the depthwise weight-gradient kernel
+
+// source row for tile voxel `v` (linear index in a box of size d0 x d1 x d2) in a tensor whose
+// spatial size is (s1, s2 trailing dims): identity / +1 on every axis / *2 / *2+1.
+__device__ __forceinline__ int64_t map_row(int kind, int64_t v, int d1, int d2, int s1, int s2) {
+  if (kind == MAP_IDENT) return v;
+  const int x = (int)(v % d2), y = (int)((v / d2) % d1), z = (int)(v / ((int64_t)d2 * d1));
+  if (kind == MAP_PLUS1) return ((int64_t)(z + 1) * s1 + (y + 1)) * s2 + (x + 1);
+  if (kind == MAP_TIMES2) return ((int64_t)(2 * z) * s1 + 2 * y) * s2 + 2 * x;
+  return ((int64_t)(2 * z + 1) * s1 + (2 * y + 1)) * s2 + (2 * x + 1);
+}
+
+// 16 per-lane values -> column totals over the 32 lanes with 16 shuffles (recursive halving).
+// Afterwards lane l holds the total of column  8*b4 + 4*b3 + 2*b2 + b1  (bits of l) in v[0].
+__device__ __forceinline__ void warp_colsum16(float* v, int lane) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float send = (lane & 16) ? v[k] : v[k + 8], keep = (lane & 16) ? v[k + 8] : v[k];
+    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float send = (lane & 8) ? v[k] : v[k + 4], keep = (lane & 8) ? v[k + 4] : v[k];
+    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const float send = (lane & 4) ? v[k] : v[k + 2], keep = (lane & 4) ? v[k + 2] : v[k];
+    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  {
+    const float send = (lane & 2) ? v[0] : v[1], keep = (lane & 2) ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+__device__ __forceinline__ int colsum16_col(int lane) {
+  return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+}
+
+__device__ __forceinline__ void stage_rows_k(uint8_t* dst, const uint4* __restrict__ src, int rows, int kc8,
+                                             int64_t pitch8, int tid) {
+  const uint32_t sbo = kc8 * 128;
+  for (int q = tid; q < rows * kc8; q += 128) {
+    const int r = q / kc8, c8 = q - r * kc8;
+    *reinterpret_cast<uint4*>(dst + (r >> 3) * sbo + c8 * 128 + (r & 7) * 16) = __ldg(src + (int64_t)r * pitch8 + c8);
+  }
+}
+
+// ============================================================================ fused MLP backward (dgrad)
+struct MlpBwdArgs {
+  const uint4* y; const double* stats; const float* gamma; const float* beta;
+  const uint4* w2; const float* b2; const uint4* w3t; const uint4* w2t; const uint4* dout;
+  uint4* hact; uint4* dh; uint4* dyhat; double* gstats;
+  int y1, y2;            // trailing spatial dims of y
+  int o1, o2;            // trailing spatial dims of dout
+  int C, H, Co;
+  int KC, KCo, N1, Ct;
+  int mode;
+  int64_t Vy, Vout;
+  float inv_count;
+};
+
+__global__ void __launch_bounds__(128) mlp_bwd_kernel(MlpBwdArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n = blockIdx.y, ct = blockIdx.z;
+  const int64_t tile0 = (int64_t)blockIdx.x * 128;
+
+  uint8_t* sA = smem;                                // [128 x KC]   norm(y) chunk
+  uint8_t* sD = sA + 128 * a.KC * 2;                 // [128 x KCo]  dOut chunk
+  uint8_t* sW2 = sD + 128 * a.KCo * 2;               // [N1 x KC]
+  uint8_t* sW3t = sW2 + a.N1 * a.KC * 2;             // [N1 x KCo]
+  uint8_t* sDh = sW3t + a.N1 * a.KCo * 2;            // [128 x N1]
+  uint8_t* sW2t = sDh + 128 * a.N1 * 2;              // [Ct x N1]
+  float* sScale = reinterpret_cast<float*>(sW2t + a.Ct * a.N1 * 2);   // [C] gamma*rstd
+  float* sShift = sScale + a.C;                      // [C] beta - mean*gamma*rstd
+  float* sRstd = sShift + a.C;                       // [C]
+  float* sMR = sRstd + a.C;                          // [C] mean*rstd
+  double* sG = reinterpret_cast<double*>(sMR + a.C); // [2*Ct] S1,S2 partials
+  int64_t* sRowO = reinterpret_cast<int64_t*>(sG + 2 * a.Ct);   // [128] row in dout (or -1)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sRowO + 128);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+
+  const uint32_t tmem_cols = tmem_cols_pow2(2 * a.N1 + a.Ct);
+  if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
+  if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  for (int c = tid; c < a.C; c += 128) {
+    const double s = a.stats[(int64_t)n * 2 * a.C + c], q = a.stats[(int64_t)n * 2 * a.C + a.C + c];
+    const double mean = s * (double)a.inv_count;
+    double var = q * (double)a.inv_count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + 1e-5));
+    const float g = a.gamma[c] * rstd;
+    sScale[c] = g; sShift[c] = a.beta[c] - (float)mean * g; sRstd[c] = rstd; sMR[c] = (float)mean * rstd;
+  }
+  for (int i = tid; i < 2 * a.Ct; i += 128) sG[i] = 0.0;
+  {
+    const int64_t p = tile0 + tid;
+    sRowO[tid] = p < a.Vy ? map_row(a.mode == PCB_DW_UP ? MAP_PLUS1 : MAP_IDENT, p, a.y1, a.y2, a.o1, a.o2) : -1;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t acc1 = tmem_base, accG = tmem_base + a.N1, accD = tmem_base + 2 * a.N1;
+  uint32_t ph = 0;
+  const int nkc = a.C / a.KC, nko = a.Co / a.KCo, nhc = a.H / a.N1;
+  const int kc8 = a.KC >> 3, ko8 = a.KCo >> 3, n18 = a.N1 >> 3;
+  const uint32_t idescH = umma_idesc_bf16(128, a.N1, 0, 0), idescD = umma_idesc_bf16(128, a.Ct, 0, 0);
+  const uint4* yn = a.y + (int64_t)n * a.Vy * (a.C >> 3);
+  const uint4* dn = a.dout + (int64_t)n * a.Vout * (a.Co >> 3);
+  const int64_t prow = tile0 + tid;
+  const bool row_ok = prow < a.Vy;
+
+  for (int hc = 0; hc < nhc; ++hc) {
+    // ---- Hpre = norm(y) * W2[hc]^T
+    for (int kc = 0; kc < nkc; ++kc) {
+      if (!(nkc == 1 && hc > 0)) {
+        const uint32_t sbo = kc8 * 128;
+        for (int q = tid; q < 128 * kc8; q += 128) {
+          const int r = q / kc8, c8 = q - r * kc8;
+          uint4 v = make_uint4(0, 0, 0, 0);
+          if (tile0 + r < a.Vy) {
+            float f[8];
+            unpack8(__ldg(yn + (tile0 + r) * (a.C >> 3) + kc * kc8 + c8), f);
+            const int c0 = kc * a.KC + c8 * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sScale[c0 + j], sShift[c0 + j]);
+            v = pack8(f);
+          }
+          *reinterpret_cast<uint4*>(sA + (r >> 3) * sbo + c8 * 128 + (r & 7) * 16) = v;
+        }
+      }
+      stage_rows_k(sW2, a.w2 + (int64_t)hc * a.N1 * (a.C >> 3) + kc * kc8, a.N1, kc8, a.C >> 3, tid);
+      fence_proxy_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        const uint64_t ad = umma_desc(smem_u32(sA), 128, kc8 * 128), bd = umma_desc(smem_u32(sW2), 128, kc8 * 128);
+        for (int k = 0; k < a.KC / 16; ++k)
+          umma_bf16(acc1, ad + (uint64_t)(k * 16), bd + (uint64_t)(k * 16), idescH, (kc > 0 || k > 0) ? 1u : 0u);
+        tc_commit(bar);
+      }
+      mbar_wait(bar, ph); ph ^= 1;
+    }
+    // ---- dG = dOut * W3[:, hc]   (B operand = W3^T rows hc*N1.., K = Co)
+    for (int kc = 0; kc < nko; ++kc) {
+      if (!(nko == 1 && hc > 0)) {
+        const uint32_t sbo = ko8 * 128;
+        for (int q = tid; q < 128 * ko8; q += 128) {
+          const int r = q / ko8, c8 = q - r * ko8;
+          const int64_t ro = sRowO[r];
+          uint4 v = make_uint4(0, 0, 0, 0);
+          if (ro >= 0) v = __ldg(dn + ro * (a.Co >> 3) + kc * ko8 + c8);
+          *reinterpret_cast<uint4*>(sD + (r >> 3) * sbo + c8 * 128 + (r & 7) * 16) = v;
+        }
+      }
+      stage_rows_k(sW3t, a.w3t + (int64_t)hc * a.N1 * (a.Co >> 3) + kc * ko8, a.N1, ko8, a.Co >> 3, tid);
+      fence_proxy_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        const uint64_t ad = umma_desc(smem_u32(sD), 128, ko8 * 128), bd = umma_desc(smem_u32(sW3t), 128, ko8 * 128);
+        for (int k = 0; k < a.KCo / 16; ++k)
+          umma_bf16(accG, ad + (uint64_t)(k * 16), bd + (uint64_t)(k * 16), idescH, (kc > 0 || k > 0) ? 1u : 0u);
+        tc_commit(bar);
+      }
+      mbar_wait(bar, ph); ph ^= 1;
+    }
+    tc_fence_after();
+    // ---- W2^T[ct tile, hc] for the dYhat GEMM
+    stage_rows_k(sW2t, a.w2t + (int64_t)ct * a.Ct * (a.H >> 3) + hc * n18, a.Ct, n18, a.H >> 3, tid);
+    // ---- epilogue: Hact = GELU(h), dh = dG * GELU'(h)
+    {
+      const uint32_t t1 = acc1 + ((uint32_t)(warp * 32) << 16), tg = accG + ((uint32_t)(warp * 32) << 16);
+      const uint32_t sbo = n18 * 128;
+      uint8_t* dst = sDh + (tid >> 3) * sbo + (tid & 7) * 16;
+      const int64_t grow = ((int64_t)n * a.Vy + prow) * (a.H >> 3) + hc * n18;
+      for (int c16 = 0; c16 < a.N1 / 16; ++c16) {
+        uint32_t v1[16], vg[16];
+        tmem_ld16(t1 + c16 * 16, v1);
+        tmem_ld16(tg + c16 * 16, vg);
+        tmem_ld_wait();
+        float ha[16], dhv[16];
+        const float* bp = a.b2 + hc * a.N1 + c16 * 16;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float h = __uint_as_float(v1[j]) + __ldg(bp + j);
+          ha[j] = gelu_f(h);
+          dhv[j] = __uint_as_float(vg[j]) * gelu_grad_f(h);
+        }
+        const uint4 d0 = pack8(dhv), d1 = pack8(dhv + 8);
+        *reinterpret_cast<uint4*>(dst + (c16 * 2) * 128) = d0;
+        *reinterpret_cast<uint4*>(dst + (c16 * 2 + 1) * 128) = d1;
+        if (row_ok && ct == 0) {
+          a.hact[grow + c16 * 2] = pack8(ha);
+          a.hact[grow + c16 * 2 + 1] = pack8(ha + 8);
+          a.dh[grow + c16 * 2] = d0;
+          a.dh[grow + c16 * 2 + 1] = d1;
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    // ---- dYhat[:, ct tile] += dh * W2[hc, ct tile]
+    if (tid == 0) {
+      tc_fence_after();
+      const uint64_t ad = umma_desc(smem_u32(sDh), 128, n18 * 128), bd = umma_desc(smem_u32(sW2t), 128, n18 * 128);
+      for (int k = 0; k < a.N1 / 16; ++k)
+        umma_bf16(accD, ad + (uint64_t)(k * 16), bd + (uint64_t)(k * 16), idescD, (hc > 0 || k > 0) ? 1u : 0u);
+      tc_commit(bar);
+    }
+    mbar_wait(bar, ph); ph ^= 1;
+  }
+  tc_fence_after();
+  // ---- final epilogue: g = dYhat -> bf16; S1 += g, S2 += g * xhat
+  {
+    const uint32_t td = accD + ((uint32_t)(warp * 32) << 16);
+    const int64_t yrow = ((int64_t)n * a.Vy + prow) * (a.C >> 3) + ct * (a.Ct >> 3);
+    for (int c16 = 0; c16 < a.Ct / 16; ++c16) {
+      uint32_t v[16];
+      tmem_ld16(td + c16 * 16, v);
+      tmem_ld_wait();
+      float g[16], gx[16];
+      const int c0 = ct * a.Ct + c16 * 16;
+      if (row_ok) {
+        float yv[16];
+        unpack8(__ldg(a.y + yrow + c16 * 2), yv);
+        unpack8(__ldg(a.y + yrow + c16 * 2 + 1), yv + 8);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          g[j] = round_bf16(__uint_as_float(v[j]));
+          gx[j] = g[j] * fmaf(yv[j], sRstd[c0 + j], -sMR[c0 + j]);
+        }
+        a.dyhat[yrow + c16 * 2] = pack8(g);
+        a.dyhat[yrow + c16 * 2 + 1] = pack8(g + 8);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { g[j] = 0.f; gx[j] = 0.f; }
+      }
+      warp_colsum16(g, lane);
+      warp_colsum16(gx, lane);
+      if (!(lane & 1)) {
+        const int col = c16 * 16 + colsum16_col(lane);
+        atomicAdd(&sG[col], (double)g[0]);
+        atomicAdd(&sG[a.Ct + col], (double)gx[0]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  for (int i = tid; i < a.Ct; i += 128) {
+    atomicAdd(&a.gstats[(int64_t)n * 2 * a.C + ct * a.Ct + i], sG[i]);
+    atomicAdd(&a.gstats[(int64_t)n * 2 * a.C + a.C + ct * a.Ct + i], sG[a.Ct + i]);
+  }
+  if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ============================================================================ TN (split-K) wgrad GEMM
+struct TnArgs {
+  const uint4* A; const uint4* B;
+  float* part;                  // [P][Mtot][Ncols_tot] fp32 partial sums
+  const double* stats; const float* gamma; const float* beta;   // GroupNorm-apply on B (nullable)
+  int64_t a_pitch8, b_pitch8;   // row pitch (uint4 units)
+  int64_t a_sample8, b_sample8; // per-sample stride (uint4 units)
+  int Ma, Nb;                   // valid A columns (M of D), B columns (N of D without the ones block)
+  int ones;                     // append an all-ones column block (16 wide) to B chunk 0
+  int mapA, mapB;
+  int d1, d2;                   // iteration box trailing dims (tile voxel -> coordinates)
+  int as1, as2, bs1, bs2;       // trailing spatial dims of the A / B tensors (for the row maps)
+  int64_t V;                    // voxels per sample in the iteration box
+  int N;                        // samples
+  int Mtot, Ncols_tot;
+  float inv_count;
+};
+
+constexpr int TN_NCHUNK = 128;
+
+__global__ void __launch_bounds__(128) tn_gemm_kernel(TnArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int mt = blockIdx.y, nc = blockIdx.z;
+  const int m0 = mt * 128;
+  const int mvalid = min(128, a.Ma - m0), m8n = mvalid >> 3;
+  const int n0 = nc * TN_NCHUNK;
+  const int nb = min(TN_NCHUNK, a.Nb - n0), nb8 = nb >> 3;
+  const bool ones = a.ones && nc == 0;
+  const int ncols = nb + (ones ? 16 : 0);
+  // MN-major canonical layout: 16 B chunk (8 channels of voxel v) of channel-group g at g*SBO + v*16.
+  // SBO padded so a quarter-warp's 8 stores land on 8 distinct 16 B bank groups.
+  const uint32_t padA = m8n >= 8 ? 16 : (m8n >= 4 ? 32 : 64), padB = nb8 >= 8 ? 16 : (nb8 >= 4 ? 32 : 64);
+  const uint32_t sboA = 2048 + padA, sboB = 2048 + padB;
+  const uint32_t stageA = 16 * sboA, stageB = ((TN_NCHUNK >> 3) + 2) * sboB;
+  uint8_t* sA0 = smem;
+  uint8_t* sB0 = sA0 + 2 * stageA;
+  float* sScale = reinterpret_cast<float*>(sB0 + 2 * stageB);   // [nb]
+  float* sShift = sScale + TN_NCHUNK;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sShift + TN_NCHUNK);   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
+
+  const uint32_t tmem_cols = tmem_cols_pow2(ncols);
+  if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
+  if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_mbar_init(); }
+  // zero both A stages once: channel groups beyond the valid ones stay zero for the whole kernel
+  for (uint32_t i = tid * 16; i < 2 * stageA + 2 * stageB; i += 128 * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t acc = *tmem_slot;
+  const uint32_t idesc = umma_idesc_bf16(128, ncols, 1, 1);
+
+  const int64_t tps = (a.V + 127) / 128;           // tiles per sample
+  const int64_t ntiles = tps * a.N;
+  int cur_n = -1;
+  uint32_t it = 0;
+  uint32_t phase[2] = {0, 0};
+  for (int64_t g = blockIdx.x; g < ntiles; g += gridDim.x, ++it) {
+    const int n = (int)(g / tps);
+    const int64_t v0 = (g - (int64_t)n * tps) * 128;
+    const int s = it & 1;
+    if (it >= 2) { mbar_wait(&bar[s], phase[s]); phase[s] ^= 1; }
+    if (a.stats != nullptr && n != cur_n) {   // GroupNorm affine of this sample for the B channels
+      __syncthreads();
+      for (int c = tid; c < nb; c += 128) {
+        const int cg = n0 + c;
+        const double sm = a.stats[(int64_t)n * 2 * a.Nb + cg], q = a.stats[(int64_t)n * 2 * a.Nb + a.Nb + cg];
+        const double mean = sm * (double)a.inv_count;
+        double var = q * (double)a.inv_count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const float gg = a.gamma[cg] * (float)(1.0 / sqrt(var + 1e-5));
+        sScale[c] = gg; sShift[c] = a.beta[cg] - (float)mean * gg;
+      }
+      __syncthreads();
+    }
+    cur_n = n;
+    uint8_t* sA = sA0 + s * stageA;
+    uint8_t* sB = sB0 + s * stageB;
+    const uint4* An = a.A + (int64_t)n * a.a_sample8;
+    const uint4* Bn = a.B + (int64_t)n * a.b_sample8;
+    for (int q = tid; q < 128 * m8n; q += 128) {
+      const int v = q / m8n, g8 = q - v * m8n;
+      uint4 val = make_uint4(0, 0, 0, 0);
+      if (v0 + v < a.V) {
+        const int64_t r = map_row(a.mapA, v0 + v, a.d1, a.d2, a.as1, a.as2);
+        val = __ldg(An + r * a.a_pitch8 + (m0 >> 3) + g8);
+      }
+      *reinterpret_cast<uint4*>(sA + g8 * sboA + v * 16) = val;
+    }
+    for (int q = tid; q < 128 * nb8; q += 128) {
+      const int v = q / nb8, g8 = q - v * nb8;
+      uint4 val = make_uint4(0, 0, 0, 0);
+      if (v0 + v < a.V) {
+        const int64_t r = map_row(a.mapB, v0 + v, a.d1, a.d2, a.bs1, a.bs2);
+        val = __ldg(Bn + r * a.b_pitch8 + (n0 >> 3) + g8);
+        if (a.stats != nullptr) {
+          float f[8];
+          unpack8(val, f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sScale[g8 * 8 + j], sShift[g8 * 8 + j]);
+          val = pack8(f);
+        }
+      }
+      *reinterpret_cast<uint4*>(sB + g8 * sboB + v * 16) = val;
+    }
+    if (ones) {   // column nb = 1.0 for valid voxels (bf16 0x3F80), the other 15 columns zero
+      const int v = tid;
+      *reinterpret_cast<uint4*>(sB + nb8 * sboB + v * 16) = make_uint4((v0 + v < a.V) ? 0x3F80u : 0u, 0, 0, 0);
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint64_t ad = umma_desc(smem_u32(sA), 128, sboA), bd = umma_desc(smem_u32(sB), 128, sboB);
+      for (int k = 0; k < 8; ++k)   // 128 voxels = 8 x K16; K-groups of 8 voxels are LBO = 128 B apart
+        umma_bf16(acc, ad + (uint64_t)(k * 16), bd + (uint64_t)(k * 16), idesc, (it > 0 || k > 0) ? 1u : 0u);
+      tc_commit(&bar[s]);
+    }
+  }
+  // drain: the last commit covers all earlier MMAs
+  if (it > 0) {
+    const int s = (it - 1) & 1;
+    mbar_wait(&bar[s], phase[s]);
+    if (it > 1) { const int s2 = it & 1; mbar_wait(&bar[s2], phase[s2]); }
+  }
+  tc_fence_after();
+  {
+    const uint32_t trow = acc + ((uint32_t)(warp * 32) << 16);
+    float* prow = a.part + ((int64_t)blockIdx.x * a.Mtot + m0 + tid) * a.Ncols_tot;
+    for (int c16 = 0; c16 < ncols / 16; ++c16) {
+      uint32_t v[16];
+      tmem_ld16(trow + c16 * 16, v);
+      tmem_ld_wait();
+      if (it == 0) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0u;   // this CTA had no tile: contribute zeros
+      }
+      if (tid < mvalid) {
+        const int col0 = (c16 * 16 < nb) ? (n0 + c16 * 16) : a.Nb;   // ones block lives after all Nb columns
+        float4* dst = reinterpret_cast<float4*>(prow + col0);
+        dst[0] = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
+        dst[1] = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
+        dst[2] = make_float4(__uint_as_float(v[8]), __uint_as_float(v[9]), __uint_as_float(v[10]), __uint_as_float(v[11]));
+        dst[3] = make_float4(__uint_as_float(v[12]), __uint_as_float(v[13]), __uint_as_float(v[14]), __uint_as_float(v[15]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(acc, tmem_cols);
+}
+
+// second stage: dW[m*ldm + n*ldn] = sum_p part[p][m][n] (n < Nw) ; db[m] = sum_p part[p][m][Nw]
+__global__ void reduce_partials_kernel(const float* __restrict__ part, int P, int M, int Mtot, int Ncols_tot, int Nw,
+                                       float* __restrict__ dW, int64_t ldm, int64_t ldn, float* __restrict__ db) {
+  const int64_t total = (int64_t)M * (Nw + (db ? 1 : 0));
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int m = (int)(i / (Nw + (db ? 1 : 0))), nn = (int)(i - (int64_t)m * (Nw + (db ? 1 : 0)));
+    float s = 0.f;
+    for (int p = 0; p < P; ++p) s += part[((int64_t)p * Mtot + m) * Ncols_tot + nn];
+    if (nn < Nw) dW[m * ldm + nn * ldn] = s;
+    else db[m] = s;
+  }
+}
+
+// ============================================================================ row-gather 1x1 conv (K-major)
+struct PwArgs {
+  const uint4* A; const uint4* W; const float* bias; uint4* out;
+  int K, Nw, KC, NT;
+  int map, d1, d2, s1, s2;
+  int64_t Vout, Vin;
+};
+
+__global__ void __launch_bounds__(128) pw_kernel(PwArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int n = blockIdx.y, nt = blockIdx.z;
+  const int64_t tile0 = (int64_t)blockIdx.x * 128;
+  uint8_t* sA = smem;                       // [128 x KC]
+  uint8_t* sW = sA + 128 * a.KC * 2;        // [NT x KC]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sW + a.NT * a.KC * 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const uint32_t tmem_cols = tmem_cols_pow2(a.NT);
+  if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
+  if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t acc = *tmem_slot;
+  const uint32_t idesc = umma_idesc_bf16(128, a.NT, 0, 0);
+  const int kc8 = a.KC >> 3;
+  uint32_t ph = 0;
+  const uint4* An = a.A + (int64_t)n * a.Vin * (a.K >> 3);
+  for (int kc = 0; kc < a.K / a.KC; ++kc) {
+    const uint32_t sbo = kc8 * 128;
+    for (int q = tid; q < 128 * kc8; q += 128) {
+      const int r = q / kc8, c8 = q - r * kc8;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (tile0 + r < a.Vout) v = __ldg(An + map_row(a.map, tile0 + r, a.d1, a.d2, a.s1, a.s2) * (a.K >> 3) + kc * kc8 + c8);
+      *reinterpret_cast<uint4*>(sA + (r >> 3) * sbo + c8 * 128 + (r & 7) * 16) = v;
+    }
+    stage_rows_k(sW, a.W + (int64_t)nt * a.NT * (a.K >> 3) + kc * kc8, a.NT, kc8, a.K >> 3, tid);
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint64_t ad = umma_desc(smem_u32(sA), 128, kc8 * 128), bd = umma_desc(smem_u32(sW), 128, kc8 * 128);
+      for (int k = 0; k < a.KC / 16; ++k)
+        umma_bf16(acc, ad + (uint64_t)(k * 16), bd + (uint64_t)(k * 16), idesc, (kc > 0 || k > 0) ? 1u : 0u);
+      tc_commit(bar);
+    }
+    mbar_wait(bar, ph); ph ^= 1;
+  }
+  tc_fence_after();
+  {
+    const int64_t r = tile0 + tid;
+    const uint32_t trow = acc + ((uint32_t)(warp * 32) << 16);
+    const int64_t orow = ((int64_t)n * a.Vout + r) * (a.Nw >> 3) + nt * (a.NT >> 3);
+    for (int c16 = 0; c16 < a.NT / 16; ++c16) {
+      uint32_t v[16];
+      tmem_ld16(trow + c16 * 16, v);
+      tmem_ld_wait();
+      if (r >= a.Vout) continue;
+      float o[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(v[j]) + (a.bias ? __ldg(a.bias + nt * a.NT + c16 * 16 + j) : 0.f);
+      a.out[orow + c16 * 2] = pack8(o);
+      a.out[orow + c16 * 2 + 1] = pack8(o + 8);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(acc, tmem_cols);
+}
+
+// ============================================================================ GroupNorm backward -> dy
+// dy = rstd*gamma*(g - S1/V - xhat*S2/V), xhat = (y-mean)*rstd ; dsum[c] += sum dy (conv1 bias grad)
+__global__ void __launch_bounds__(256) gn_dy_kernel(const uint4* __restrict__ g, const uint4* __restrict__ y,
+                                                    const double* __restrict__ stats, const double* __restrict__ gstats,
+                                                    const float* __restrict__ gamma, uint4* __restrict__ dy,
+                                                    double* __restrict__ dsum, int C, int64_t V, float inv_count) {
+  extern __shared__ double s_sum[];   // [C] doubles, then 5*[C] floats
+  float* s_k = reinterpret_cast<float*>(s_sum + C);   // mean, rstd, gamma*rstd, S1/V, S2/V
+  const int CH = C >> 3, n = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    s_sum[c] = 0.0;
+    const double sm = stats[(int64_t)n * 2 * C + c], q = stats[(int64_t)n * 2 * C + C + c];
+    const double mean = sm * (double)inv_count;
+    double var = q * (double)inv_count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + 1e-5));
+    s_k[c] = (float)mean; s_k[C + c] = rstd; s_k[2 * C + c] = gamma[c] * rstd;
+    s_k[3 * C + c] = (float)(gstats[(int64_t)n * 2 * C + c] * (double)inv_count);
+    s_k[4 * C + c] = (float)(gstats[(int64_t)n * 2 * C + C + c] * (double)inv_count);
+  }
+  __syncthreads();
+  const int64_t items = V * CH;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;   // multiple of CH when CH | 256
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  int cc_fixed = -1;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < items; i += stride) {
+    const int cc = (int)(i % CH);
+    if (cc_fixed >= 0 && cc != cc_fixed) {   // non power-of-two CH: flush and restart
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { atomicAdd(&s_sum[cc_fixed * 8 + j], (double)acc[j]); acc[j] = 0.f; }
+    }
+    cc_fixed = cc;
+    float gv[8], yv[8], o[8];
+    unpack8(__ldg(g + (int64_t)n * items + i), gv);
+    unpack8(__ldg(y + (int64_t)n * items + i), yv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cc * 8 + j;
+      const float xh = (yv[j] - s_k[c]) * s_k[C + c];
+      o[j] = round_bf16(s_k[2 * C + c] * (gv[j] - s_k[3 * C + c] - xh * s_k[4 * C + c]));
+      acc[j] += o[j];
+    }
+    dy[(int64_t)n * items + i] = pack8(o);
+  }
+  if (cc_fixed >= 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&s_sum[cc_fixed * 8 + j], (double)acc[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&dsum[i], s_sum[i]);
+}
+
+// ============================================================================ depthwise weight gradient
+// dW[tap][c] += sum_v center[v,c] * neigh[S*v - P + tap, c]; one (dz,dy) tap row per blockIdx.y
+struct DwWgArgs {
+  int c0, c1, c2;   // center spatial size
+  int n0, n1, n2;   // neighbour spatial size
+  int C, S;
+};
+
+template <int K>
+__global__ void __launch_bounds__(256) dw_wgrad_kernel(const uint4* __restrict__ center, const uint4* __restrict__ neigh,
+                                                       double* __restrict__ dW, DwWgArgs a) {
+  extern __shared__ double s_acc[];   // [K][C]
+  constexpr int P = K / 2;
+  const int C = a.C, CH = C >> 3;
+  const int dz = blockIdx.y / K, dyy = blockIdx.y % K;
+  const int n = blockIdx.z;
+  for (int i = threadIdx.x; i < K * C; i += blockDim.x) s_acc[i] = 0.0;
+  __syncthreads();
+  const int nstrip = (a.c2 + DW_XB_WG - 1) / DW_XB_WG;
+  const int64_t items = (int64_t)a.c0 * a.c1 * nstrip * CH;
+  float acc[K][8];
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[k][j] = 0.f;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const uint4* cn = center + (int64_t)n * a.c0 * a.c1 * a.c2 * CH;
+  const uint4* nn = neigh + (int64_t)n * a.n0 * a.n1 * a.n2 * CH;
+  int cc_fixed = -1;
+  for (int64_t item = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; item < items; item += stride) {
+    const int cc = (int)(item % CH);
+    if (cc_fixed >= 0 && cc != cc_fixed) {
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { atomicAdd(&s_acc[k * C + cc_fixed * 8 + j], (double)acc[k][j]); acc[k][j] = 0.f; }
+    }
+    cc_fixed = cc;
+    int64_t t = item / CH;
+    const int xs = (int)(t % nstrip); t /= nstrip;
+    const int cy = (int)(t % a.c1), cz = (int)(t / a.c1);
+    const int iz = cz * a.S - P + dz, iy = cy * a.S - P + dyy;
+    if (iz < 0 || iz >= a.n0 || iy < 0 || iy >= a.n1) continue;
+    const uint4* crow = cn + ((int64_t)cz * a.c1 + cy) * a.c2 * CH + cc;
+    const uint4* nrow = nn + ((int64_t)iz * a.n1 + iy) * a.n2 * CH + cc;
+#pragma unroll
+    for (int j = 0; j < DW_XB_WG; ++j) {
+      const int cx = xs * DW_XB_WG + j;
+      if (cx >= a.c2) break;
+      float cv[8];
+      unpack8(__ldg(crow + (int64_t)cx * CH), cv);
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const int ix = cx * a.S - P + k;
+        if (ix < 0 || ix >= a.n2) continue;
+        float nv[8];
+        unpack8(__ldg(nrow + (int64_t)ix * CH), nv);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[k][c] = fmaf(cv[c], nv[c], acc[k][c]);
+      }
+    }
+  }
+  if (cc_fixed >= 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&s_acc[k * C + cc_fixed * 8 + j], (double)acc[k][j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * C; i += blockDim.x)
+    atomicAdd(&dW[(int64_t)((dz * K + dyy) * K) * C + i], s_acc[i]);
+}
+
+// ============================================================================ head / stem backward
+// head: out[n,k,v] = sum_c x[v,c] w[c,k] + b[k].   dX[v,c] = sum_k dO[k,v] w[c,k];
+//       dW[c,k] += sum_v x[v,c] dO[k,v]; db[k] += sum_v dO[k,v]     (float64 accumulators)
+template <typename TO>
+__global__ void __launch_bounds__(128) head_bwd_kernel(const TO* __restrict__ dO, const uint4* __restrict__ x,
+                                                       const float* __restrict__ w, uint4* __restrict__ dX,
+                                                       double* __restrict__ dW, double* __restrict__ db,
+                                                       int C, int ncls, int64_t V, int TV) {
+  extern __shared__ float sm[];
+  float* s_w = sm;                      // [C][ncls]
+  float* s_do = s_w + C * ncls;         // [ncls][TV]
+  float* s_x = s_do + ncls * TV;        // [TV][C+1]
+  const int n = blockIdx.y, tid = threadIdx.x, CH = C >> 3;
+  for (int i = tid; i < C * ncls; i += 128) s_w[i] = w[i];
+  const int npair = C * ncls;
+  // each thread owns pairs (c,k) = tid, tid+128, ... ; accumulate over the CTA's tiles
+  float wacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // supports C*ncls <= 1024
+  float bacc = 0.f;
+  for (int64_t t0 = (int64_t)blockIdx.x * TV; t0 < V; t0 += (int64_t)gridDim.x * TV) {
+    __syncthreads();
+    const int64_t v = t0 + tid;
+    const bool mine = tid < TV && v < V;
+    if (tid < TV) {
+      for (int k = 0; k < ncls; ++k) s_do[k * TV + tid] = mine ? (float)dO[((int64_t)n * ncls + k) * V + v] : 0.f;
+      for (int c8 = 0; c8 < CH; ++c8) {
+        float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (mine) unpack8(__ldg(x + ((int64_t)n * V + v) * CH + c8), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s_x[tid * (C + 1) + c8 * 8 + j] = f[j];
+      }
+    }
+    __syncthreads();
+    if (mine) {
+      for (int c8 = 0; c8 < CH; ++c8) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float s = 0.f;
+          for (int k = 0; k < ncls; ++k) s = fmaf(s_do[k * TV + tid], s_w[(c8 * 8 + j) * ncls + k], s);
+          o[j] = s;
+        }
+        dX[((int64_t)n * V + v) * CH + c8] = pack8(o);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int pr = tid + u * 128;
+      if (pr < npair) {
+        const int c = pr / ncls, k = pr - c * ncls;
+        float s = 0.f;
+        for (int vv = 0; vv < TV; ++vv) s = fmaf(s_x[vv * (C + 1) + c], s_do[k * TV + vv], s);
+        wacc[u] += s;
+      }
+    }
+    if (tid < ncls) {
+      float s = 0.f;
+      for (int vv = 0; vv < TV; ++vv) s += s_do[tid * TV + vv];
+      bacc += s;
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int pr = tid + u * 128;
+    if (pr < npair) atomicAdd(&dW[pr], (double)wacc[u]);
+  }
+  if (tid < ncls) atomicAdd(&db[tid], (double)bacc);
+}
+
+// stem: out[v,c] = sum_ci x[ci,v] w[c,ci] + b[c].  dW[c,ci] += sum_v g[v,c] x[ci,v]; db[c] += sum_v g[v,c]
+template <typename TIn>
+__global__ void __launch_bounds__(256) stem_bwd_kernel(const uint4* __restrict__ g, const TIn* __restrict__ x,
+                                                       double* __restrict__ dW, double* __restrict__ db, int Cin,
+                                                       int C, int64_t V) {
+  extern __shared__ double s_acc[];   // [C*(Cin+1)]
+  const int CH = C >> 3, n = blockIdx.y;
+  for (int i = threadIdx.x; i < C * (Cin + 1); i += blockDim.x) s_acc[i] = 0.0;
+  __syncthreads();
+  const int64_t items = V * CH;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int ci = 0; ci <= Cin; ++ci) {   // ci == Cin: bias column (x = 1)
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int cc_fixed = -1;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < items; i += stride) {
+      const int cc = (int)(i % CH);
+      const int64_t v = i / CH;
+      if (cc_fixed >= 0 && cc != cc_fixed) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { atomicAdd(&s_acc[(cc_fixed * 8 + j) * (Cin + 1) + ci], (double)acc[j]); acc[j] = 0.f; }
+      }
+      cc_fixed = cc;
+      float gv[8];
+      unpack8(__ldg(g + (int64_t)n * items + i), gv);
+      const float xv = ci < Cin ? (float)x[((int64_t)n * Cin + ci) * V + v] : 1.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(gv[j], xv, acc[j]);
+    }
+    if (cc_fixed >= 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&s_acc[(cc_fixed * 8 + j) * (Cin + 1) + ci], (double)acc[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * (Cin + 1); i += blockDim.x) {
+    const int c = i / (Cin + 1), ci = i - c * (Cin + 1);
+    if (ci < Cin) atomicAdd(&dW[c * Cin + ci], s_acc[i]);
+    else atomicAdd(&db[c], s_acc[i]);
+  }
+}
+
+static inline int pick_chunk_b(int64_t n, int cap) {
+  for (int c = cap; c >= 16; c >>= 1)
+    if (n % c == 0) return c;
+  return 0;
+}
+
+}  // namespace pcb
+
+using namespace pcb;
+
+extern "C" int pcb_mlp_bwd(const void* y, const double* stats, const float* gamma, const float* beta, const void* w2,
+                           const float* b2, const void* w3t, const void* w2t, const void* dout, void* hact, void* dh,
+                           void* dyhat, double* gstats, int64_t N, const int64_t y_size[3], int64_t C, int64_t H,
+                           int64_t Co, int mode, void* stream) {
+  PCB_CHECK_ARG(y && stats && gamma && beta && w2 && b2 && w3t && w2t && dout && hact && dh && dyhat && gstats && y_size,
+                "pcb_mlp_bwd: null argument");
+  PCB_CHECK_ARG(C % 16 == 0 && H % 16 == 0 && Co % 16 == 0, "pcb_mlp_bwd: channel counts must be multiples of 16");
+  PCB_CHECK_ARG(N > 0 && N <= 65535, "pcb_mlp_bwd: bad batch");
+  MlpBwdArgs a;
+  a.y = (const uint4*)y; a.stats = stats; a.gamma = gamma; a.beta = beta; a.w2 = (const uint4*)w2; a.b2 = b2;
+  a.w3t = (const uint4*)w3t; a.w2t = (const uint4*)w2t; a.dout = (const uint4*)dout; a.hact = (uint4*)hact;
+  a.dh = (uint4*)dh; a.dyhat = (uint4*)dyhat; a.gstats = gstats;
+  a.y1 = (int)y_size[1]; a.y2 = (int)y_size[2];
+  a.C = (int)C; a.H = (int)H; a.Co = (int)Co; a.mode = mode;
+  a.Vy = y_size[0] * y_size[1] * y_size[2];
+  if (mode == PCB_DW_UP) { a.o1 = a.y1 + 1; a.o2 = a.y2 + 1; a.Vout = (y_size[0] + 1) * (int64_t)a.o1 * a.o2; }
+  else { a.o1 = a.y1; a.o2 = a.y2; a.Vout = a.Vy; }
+  a.KC = pick_chunk_b(C, 128); a.KCo = pick_chunk_b(Co, 128); a.N1 = pick_chunk_b(H, 64);
+  a.Ct = C <= 256 ? (int)C : 256;
+  PCB_CHECK_ARG(C % a.Ct == 0, "pcb_mlp_bwd: C=%lld must be <=256 or a multiple of 256", (long long)C);
+  a.inv_count = (float)(1.0 / (double)a.Vy);
+  const size_t smem = (size_t)128 * a.KC * 2 + (size_t)128 * a.KCo * 2 + (size_t)a.N1 * a.KC * 2 + (size_t)a.N1 * a.KCo * 2 +
+                      (size_t)128 * a.N1 * 2 + (size_t)a.Ct * a.N1 * 2 + (size_t)4 * C * sizeof(float) +
+                      (size_t)2 * a.Ct * sizeof(double) + 128 * sizeof(int64_t) + 16;
+  PCB_CHECK_ARG(smem <= 227 * 1024, "pcb_mlp_bwd: tile needs %zu B shared memory", smem);
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+      set_error("pcb_mlp_bwd: cudaFuncSetAttribute failed"); return PCB_ERR_CUDA;
+    }
+    configured = true;
+  }
+  dim3 grid((unsigned)((a.Vy + 127) / 128), (unsigned)N, (unsigned)(C / a.Ct));
+  mlp_bwd_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(a);
+  PCB_CHECK_LAUNCH("pcb_mlp_bwd");
+  return PCB_OK;
+}
+
+static inline int tn_num_ctas(int64_t ntiles) { return (int)(ntiles < 148 ? ntiles : 148); }
+
+extern "C" int64_t pcb_tn_workspace_floats(int64_t Ma, int64_t Nb, int ones, int64_t N, const int64_t box[3]) {
+  const int64_t ntiles = (box[0] * box[1] * box[2] + 127) / 128 * N;
+  const int64_t Mtot = (Ma + 127) / 128 * 128, Nc = Nb + (ones ? 16 : 0);
+  return (int64_t)tn_num_ctas(ntiles) * Mtot * Nc;
+}
+
+extern "C" int pcb_tn_gemm(const void* A, const void* B, const double* stats, const float* gamma, const float* beta,
+                           float* workspace, float* dW, int64_t ldm, int64_t ldn, float* db, int64_t N,
+                           const int64_t box[3], int mapA, const int64_t a_size[3], int64_t a_cols, int64_t Ma,
+                           int mapB, const int64_t b_size[3], int64_t Nb, int ones, void* stream) {
+  PCB_CHECK_ARG(A && B && workspace && dW && box && a_size && b_size, "pcb_tn_gemm: null argument");
+  PCB_CHECK_ARG(Ma % 16 == 0 && Nb % 16 == 0 && Ma > 0 && Nb > 0 && a_cols >= Ma && a_cols % 8 == 0,
+                "pcb_tn_gemm: Ma/Nb must be positive multiples of 16");
+  PCB_CHECK_ARG((db == nullptr) == (ones == 0), "pcb_tn_gemm: db and ones must come together");
+  TnArgs a;
+  a.A = (const uint4*)A; a.B = (const uint4*)B; a.part = workspace; a.stats = stats; a.gamma = gamma; a.beta = beta;
+  a.a_pitch8 = a_cols / 8; a.b_pitch8 = Nb / 8;
+  const int64_t Va = a_size[0] * a_size[1] * a_size[2], Vb = b_size[0] * b_size[1] * b_size[2];
+  a.a_sample8 = Va * a.a_pitch8; a.b_sample8 = Vb * a.b_pitch8;
+  a.Ma = (int)Ma; a.Nb = (int)Nb; a.ones = ones; a.mapA = mapA; a.mapB = mapB;
+  a.d1 = (int)box[1]; a.d2 = (int)box[2];
+  a.as1 = (int)a_size[1]; a.as2 = (int)a_size[2]; a.bs1 = (int)b_size[1]; a.bs2 = (int)b_size[2];
+  a.V = box[0] * box[1] * box[2]; a.N = (int)N;
+  a.Mtot = (int)((Ma + 127) / 128 * 128); a.Ncols_tot = (int)(Nb + (ones ? 16 : 0));
+  a.inv_count = (float)(1.0 / (double)Vb);
+  const int64_t ntiles = (a.V + 127) / 128 * N;
+  const int P = tn_num_ctas(ntiles);
+  const int mt = a.Mtot / 128, ncn = (int)((Nb + TN_NCHUNK - 1) / TN_NCHUNK);
+  const size_t smem = 2 * (size_t)16 * (2048 + 64) + 2 * (size_t)((TN_NCHUNK >> 3) + 2) * (2048 + 64) +
+                      2 * TN_NCHUNK * sizeof(float) + 64;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(tn_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+      set_error("pcb_tn_gemm: cudaFuncSetAttribute failed"); return PCB_ERR_CUDA;
+    }
+    configured = true;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((unsigned)P, (unsigned)mt, (unsigned)ncn);
+  tn_gemm_kernel<<<grid, 128, smem, st>>>(a);
+  PCB_CHECK_LAUNCH("pcb_tn_gemm");
+  const int64_t total = Ma * (Nb + (db ? 1 : 0));
+  reduce_partials_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(workspace, P, (int)Ma, a.Mtot, a.Ncols_tot,
+                                                                         (int)Nb, dW, ldm, ldn, db);
+  PCB_CHECK_LAUNCH("pcb_tn_gemm(reduce)");
+  return PCB_OK;
+}
+
+extern "C" int pcb_pw_fwd(const void* A, const void* W, const float* bias, void* out, int64_t N, const int64_t out_box[3],
+                          int map, const int64_t a_size[3], int64_t K, int64_t Nw, void* stream) {
+  PCB_CHECK_ARG(A && W && out && out_box && a_size, "pcb_pw_fwd: null argument");
+  PCB_CHECK_ARG(K % 16 == 0 && Nw % 16 == 0 && K > 0 && Nw > 0, "pcb_pw_fwd: K and N must be multiples of 16");
+  PwArgs a;
+  a.A = (const uint4*)A; a.W = (const uint4*)W; a.bias = bias; a.out = (uint4*)out;
+  a.K = (int)K; a.Nw = (int)Nw; a.KC = pick_chunk_b(K, 128); a.NT = Nw <= 256 ? (int)Nw : 256;
+  PCB_CHECK_ARG(Nw % a.NT == 0, "pcb_pw_fwd: N must be <=256 or a multiple of 256");
+  a.map = map; a.d1 = (int)out_box[1]; a.d2 = (int)out_box[2]; a.s1 = (int)a_size[1]; a.s2 = (int)a_size[2];
+  a.Vout = out_box[0] * out_box[1] * out_box[2]; a.Vin = a_size[0] * a_size[1] * a_size[2];
+  const size_t smem = (size_t)128 * a.KC * 2 + (size_t)a.NT * a.KC * 2 + 32;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(pw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+      set_error("pcb_pw_fwd: cudaFuncSetAttribute failed"); return PCB_ERR_CUDA;
+    }
+    configured = true;
+  }
+  dim3 grid((unsigned)((a.Vout + 127) / 128), (unsigned)N, (unsigned)(Nw / a.NT));
+  pw_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(a);
+  PCB_CHECK_LAUNCH("pcb_pw_fwd");
+  return PCB_OK;
+}
+
+extern "C" int pcb_gn_bwd(const void* g, const void* y, const double* stats, const double* gstats, const float* gamma,
+                          void* dy, double* dsum, int64_t N, int64_t C, int64_t V, void* stream) {
+  PCB_CHECK_ARG(g && y && stats && gstats && gamma && dy && dsum, "pcb_gn_bwd: null argument");
+  PCB_CHECK_ARG(C % 8 == 0 && C > 0 && V > 0 && N > 0 && N <= 65535, "pcb_gn_bwd: bad shape");
+  const int64_t items = V * (C / 8);
+  int blocks = (int)((items + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  dim3 grid((unsigned)blocks, (unsigned)N);
+  gn_dy_kernel<<<grid, 256, C * sizeof(double) + 5 * C * sizeof(float), (cudaStream_t)stream>>>((const uint4*)g, (const uint4*)y, stats, gstats, gamma,
+                                                                     (uint4*)dy, dsum, (int)C, V, (float)(1.0 / (double)V));
+  PCB_CHECK_LAUNCH("pcb_gn_bwd");
+  return PCB_OK;
+}
+
+extern "C" int pcb_dwconv_wgrad(const void* center, const void* neigh, double* dW, int64_t N, const int64_t c_size[3],
+                                const int64_t n_size[3], int64_t C, int k, int stride, void* stream) {
+  PCB_CHECK_ARG(center && neigh && dW && c_size && n_size, "pcb_dwconv_wgrad: null argument");
+  PCB_CHECK_ARG(k == 3 || k == 5 || k == 7, "MedNeXt kernel_size must be 3, 5, or 7. Got: %d", k);
+  PCB_CHECK_ARG(C % 8 == 0 && C > 0 && (stride == 1 || stride == 2) && N > 0 && N <= 65535, "pcb_dwconv_wgrad: bad shape");
+  DwWgArgs a{(int)c_size[0], (int)c_size[1], (int)c_size[2], (int)n_size[0], (int)n_size[1], (int)n_size[2], (int)C, stride};
+  const int64_t items = (int64_t)a.c0 * a.c1 * ((a.c2 + DW_XB_WG - 1) / DW_XB_WG) * (C / 8);
+  int blocks = (int)((items + 255) / 256);
+  const int cap = 148 * 2;
+  if (blocks > cap) blocks = cap;
+  dim3 grid((unsigned)blocks, (unsigned)(k * k), (unsigned)N);
+  const size_t smem = (size_t)k * C * sizeof(double);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (k == 3) dw_wgrad_kernel<3><<<grid, 256, smem, st>>>((const uint4*)center, (const uint4*)neigh, dW, a);
+  else if (k == 5) dw_wgrad_kernel<5><<<grid, 256, smem, st>>>((const uint4*)center, (const uint4*)neigh, dW, a);
+  else dw_wgrad_kernel<7><<<grid, 256, smem, st>>>((const uint4*)center, (const uint4*)neigh, dW, a);
+  PCB_CHECK_LAUNCH("pcb_dwconv_wgrad");
+  return PCB_OK;
+}
+
+extern "C" int pcb_head_bwd(const void* dout, int dtype, const void* x, const float* w, void* dx, double* dW, double* db,
+                            int64_t N, int64_t C, int64_t ncls, int64_t nvox, void* stream) {
+  PCB_CHECK_ARG(dout && x && w && dx && dW && db, "pcb_head_bwd: null argument");
+  PCB_CHECK_ARG(C % 8 == 0 && C > 0 && ncls > 0 && C * ncls <= 1024 && ncls <= 128, "pcb_head_bwd: C*ncls must be <= 1024");
+  const int TV = C <= 128 ? 128 : 32;
+  const size_t smem = (size_t)(C * ncls + ncls * TV + TV * (C + 1)) * sizeof(float);
+  PCB_CHECK_ARG(smem <= 200 * 1024, "pcb_head_bwd: shared memory");
+  int blocks = (int)((nvox + TV - 1) / TV);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  dim3 grid((unsigned)blocks, (unsigned)N);
+  cudaStream_t st = (cudaStream_t)stream;
+#define PCB_HEAD_BWD(T)                                                                                                    \
+  do {                                                                                                                     \
+    cudaFuncSetAttribute(head_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);                     \
+    head_bwd_kernel<T><<<grid, 128, smem, st>>>((const T*)dout, (const uint4*)x, w, (uint4*)dx, dW, db, (int)C, (int)ncls, nvox, TV); \
+  } while (0)
+  if (dtype == PCB_F32) PCB_HEAD_BWD(float);
+  else if (dtype == PCB_F16) PCB_HEAD_BWD(__half);
+  else if (dtype == PCB_BF16) PCB_HEAD_BWD(__nv_bfloat16);
+  else { set_error("pcb_head_bwd: bad dtype %d", dtype); return PCB_ERR_INVALID; }
+#undef PCB_HEAD_BWD
+  PCB_CHECK_LAUNCH("pcb_head_bwd");
+  return PCB_OK;
+}
+
+extern "C" int pcb_stem_bwd(const void* g, const void* x, int in_dtype, double* dW, double* db, int64_t N, int64_t Cin,
+                            int64_t C, int64_t nvox, void* stream) {
+  PCB_CHECK_ARG(g && x && dW && db, "pcb_stem_bwd: null argument");
+  PCB_CHECK_ARG(C % 8 == 0 && C > 0 && Cin > 0 && Cin <= 16, "pcb_stem_bwd: Cin must be <= 16");
+  const int64_t items = nvox * (C / 8);
+  int blocks = (int)((items + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  dim3 grid((unsigned)blocks, (unsigned)N);
+  const size_t smem = (size_t)C * (Cin + 1) * sizeof(double);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (in_dtype == PCB_F32) stem_bwd_kernel<float><<<grid, 256, smem, st>>>((const uint4*)g, (const float*)x, dW, db, (int)Cin, (int)C, nvox);
+  else if (in_dtype == PCB_F16) stem_bwd_kernel<__half><<<grid, 256, smem, st>>>((const uint4*)g, (const __half*)x, dW, db, (int)Cin, (int)C, nvox);
+  else if (in_dtype == PCB_BF16) stem_bwd_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>((const uint4*)g, (const __nv_bfloat16*)x, dW, db, (int)Cin, (int)C, nvox);
+  else { set_error("pcb_stem_bwd: bad dtype %d", in_dtype); return PCB_ERR_INVALID; }
+  PCB_CHECK_LAUNCH("pcb_stem_bwd");
+  return PCB_OK;
+}

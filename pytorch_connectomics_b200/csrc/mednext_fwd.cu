@@ -44,12 +44,15 @@ constexpr int DW_XB = 4;  // outputs per thread along W
 
 struct DwArgs {
   int D, H, W, Do, Ho, Wo, C;
+  int add_mode;  // 0 none, 1 add[o] (same index), 2 add[(o/2)] where every coordinate of o is even
+  int a1, a2;    // H, W of the compact `add` tensor (add_mode 2)
 };
 
 template <int K, int MODE>
 __global__ void __launch_bounds__(256) dwconv_kernel(const uint4* __restrict__ x, const float* __restrict__ w,
                                                      const float* __restrict__ bias, uint4* __restrict__ y,
-                                                     double* __restrict__ stats, DwArgs a) {
+                                                     double* __restrict__ stats, const uint4* __restrict__ add,
+                                                     DwArgs a) {
   extern __shared__ double s_stats[];  // [2*C] float64: sums stay order-independent to ~1e-16
   constexpr int P = K / 2;
   constexpr int S = (MODE == PCB_DW_DOWN) ? 2 : 1;
@@ -144,8 +147,8 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const uint4* __restrict__ x
         }
       }
     }
-    float bv[8];
-    {
+    float bv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (bias != nullptr) {
       const float4* bp = reinterpret_cast<const float4*>(bias + cc * 8);
       const float4 b0 = __ldg(bp), b1 = __ldg(bp + 1);
       bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
@@ -155,6 +158,19 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const uint4* __restrict__ x
     for (int j = 0; j < DW_XB; ++j) {
       if (ox0 + j >= a.Wo) continue;
       float o[8];
+      if (a.add_mode == 1) {
+        float f[8];
+        unpack8(__ldg(add + ((((int64_t)n * a.Do + oz) * a.Ho + oy) * a.Wo + ox0 + j) * CH + cc), f);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[j][c] += f[c];
+      } else if (a.add_mode == 2) {
+        if (!((oz | oy | (ox0 + j)) & 1)) {
+          float f[8];
+          unpack8(__ldg(add + ((((int64_t)n * ((a.Do + 1) >> 1) + (oz >> 1)) * a.a1 + (oy >> 1)) * a.a2 + ((ox0 + j) >> 1)) * CH + cc), f);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[j][c] += f[c];
+        }
+      }
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         o[c] = round_bf16(acc[j][c] + bv[c]);
@@ -166,6 +182,7 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const uint4* __restrict__ x
   }
   // per-channel partial statistics: warp shuffle over lanes sharing a channel chunk, then shared
   // atomics, then one float64 atomic per channel per CTA
+  if (stats == nullptr) return;   // uniform across the grid (backward-data use)
   const bool shuffle_ok = (CH <= 32) && ((32 % CH) == 0);
   if (shuffle_ok) {
     for (int off = 16; off >= CH; off >>= 1) {
@@ -491,35 +508,56 @@ extern "C" int pcb_stem_fwd(const void* x, int in_dtype, const float* w, const f
 
 template <int K>
 static void launch_dw(int mode, dim3 grid, size_t smem, cudaStream_t st, const uint4* x, const float* w, const float* b,
-                      uint4* y, double* stats, DwArgs a) {
-  if (mode == PCB_DW_SAME) dwconv_kernel<K, PCB_DW_SAME><<<grid, 256, smem, st>>>(x, w, b, y, stats, a);
-  else if (mode == PCB_DW_DOWN) dwconv_kernel<K, PCB_DW_DOWN><<<grid, 256, smem, st>>>(x, w, b, y, stats, a);
-  else dwconv_kernel<K, PCB_DW_UP><<<grid, 256, smem, st>>>(x, w, b, y, stats, a);
+                      uint4* y, double* stats, const uint4* add, DwArgs a) {
+  if (mode == PCB_DW_SAME) dwconv_kernel<K, PCB_DW_SAME><<<grid, 256, smem, st>>>(x, w, b, y, stats, add, a);
+  else if (mode == PCB_DW_DOWN) dwconv_kernel<K, PCB_DW_DOWN><<<grid, 256, smem, st>>>(x, w, b, y, stats, add, a);
+  else dwconv_kernel<K, PCB_DW_UP><<<grid, 256, smem, st>>>(x, w, b, y, stats, add, a);
 }
 
-extern "C" int pcb_dwconv_fwd(const void* x, const float* w, const float* b, void* y, double* stats, int64_t N,
-                              const int64_t in_size[3], int64_t C, int k, int mode, void* stream) {
-  PCB_CHECK_ARG(x && w && b && y && stats && in_size, "pcb_dwconv_fwd: null argument");
+static int dwconv_launch(const void* x, const float* w, const float* b, void* y, double* stats, const void* add,
+                         int add_mode, int64_t N, const int64_t in_size[3], const int64_t* out_size, int64_t C, int k,
+                         int mode, void* stream, const char* what) {
+  PCB_CHECK_ARG(x && w && y && in_size, "%s: null argument", what);
   PCB_CHECK_ARG(k == 3 || k == 5 || k == 7, "MedNeXt kernel_size must be 3, 5, or 7. Got: %d", k);
-  PCB_CHECK_ARG(mode >= PCB_DW_SAME && mode <= PCB_DW_UP, "pcb_dwconv_fwd: bad mode %d", mode);
-  PCB_CHECK_ARG(C > 0 && C % 8 == 0 && C <= 4096, "pcb_dwconv_fwd: C must be a multiple of 8 (got %lld)", (long long)C);
-  PCB_CHECK_ARG(N > 0 && N <= 65535, "pcb_dwconv_fwd: bad batch %lld", (long long)N);
+  PCB_CHECK_ARG(mode >= PCB_DW_SAME && mode <= PCB_DW_UP, "%s: bad mode %d", what, mode);
+  PCB_CHECK_ARG(C > 0 && C % 8 == 0 && C <= 4096, "%s: C must be a multiple of 8 (got %lld)", what, (long long)C);
+  PCB_CHECK_ARG(N > 0 && N <= 65535, "%s: bad batch %lld", what, (long long)N);
   DwArgs a;
   a.D = (int)in_size[0]; a.H = (int)in_size[1]; a.W = (int)in_size[2]; a.C = (int)C;
+  a.add_mode = add ? add_mode : 0; a.a1 = a.a2 = 0;
   const int p = k / 2;
-  if (mode == PCB_DW_SAME) { a.Do = a.D; a.Ho = a.H; a.Wo = a.W; }
+  if (out_size) { a.Do = (int)out_size[0]; a.Ho = (int)out_size[1]; a.Wo = (int)out_size[2]; }
+  else if (mode == PCB_DW_SAME) { a.Do = a.D; a.Ho = a.H; a.Wo = a.W; }
   else if (mode == PCB_DW_DOWN) { a.Do = (a.D + 2 * p - k) / 2 + 1; a.Ho = (a.H + 2 * p - k) / 2 + 1; a.Wo = (a.W + 2 * p - k) / 2 + 1; }
   else { a.Do = (a.D - 1) * 2 - 2 * p + k; a.Ho = (a.H - 1) * 2 - 2 * p + k; a.Wo = (a.W - 1) * 2 - 2 * p + k; }
-  PCB_CHECK_ARG(a.Do > 0 && a.Ho > 0 && a.Wo > 0, "pcb_dwconv_fwd: empty output");
+  PCB_CHECK_ARG(a.Do > 0 && a.Ho > 0 && a.Wo > 0, "%s: empty output", what);
+  if (a.add_mode == 2) { a.a1 = (a.Ho + 1) >> 1; a.a2 = (a.Wo + 1) >> 1; }
   const int64_t items = (int64_t)a.Do * a.Ho * ((a.Wo + DW_XB - 1) / DW_XB) * (C / 8);
   dim3 grid((unsigned)((items + 255) / 256), (unsigned)N);
   const size_t smem = 2 * C * sizeof(double);
   cudaStream_t st = (cudaStream_t)stream;
-  if (k == 3) launch_dw<3>(mode, grid, smem, st, (const uint4*)x, w, b, (uint4*)y, stats, a);
-  else if (k == 5) launch_dw<5>(mode, grid, smem, st, (const uint4*)x, w, b, (uint4*)y, stats, a);
-  else launch_dw<7>(mode, grid, smem, st, (const uint4*)x, w, b, (uint4*)y, stats, a);
-  PCB_CHECK_LAUNCH("pcb_dwconv_fwd");
+  if (k == 3) launch_dw<3>(mode, grid, smem, st, (const uint4*)x, w, b, (uint4*)y, stats, (const uint4*)add, a);
+  else if (k == 5) launch_dw<5>(mode, grid, smem, st, (const uint4*)x, w, b, (uint4*)y, stats, (const uint4*)add, a);
+  else launch_dw<7>(mode, grid, smem, st, (const uint4*)x, w, b, (uint4*)y, stats, (const uint4*)add, a);
+  PCB_CHECK_LAUNCH(what);
   return PCB_OK;
+}
+
+extern "C" int pcb_dwconv_fwd(const void* x, const float* w, const float* b, void* y, double* stats, int64_t N,
+                              const int64_t in_size[3], int64_t C, int k, int mode, void* stream) {
+  PCB_CHECK_ARG(b && stats, "pcb_dwconv_fwd: null argument");
+  return dwconv_launch(x, w, b, y, stats, nullptr, 0, N, in_size, nullptr, C, k, mode, stream, "pcb_dwconv_fwd");
+}
+
+extern "C" int pcb_dwconv_bwd_data(const void* dy, const float* w, const void* add, int add_mode, void* dx, int64_t N,
+                                   const int64_t dy_size[3], const int64_t dx_size[3], int64_t C, int k, int fwd_mode,
+                                   void* stream) {
+  PCB_CHECK_ARG(dx_size, "pcb_dwconv_bwd_data: null argument");
+  // gradient of a SAME conv is a SAME conv with the flipped taps (caller flips); of a stride-2 conv the
+  // transposed conv; of the transposed conv the stride-2 conv — all with the forward stencil kernel.
+  const int mode = fwd_mode == PCB_DW_SAME ? PCB_DW_SAME : (fwd_mode == PCB_DW_DOWN ? PCB_DW_UP : PCB_DW_DOWN);
+  return dwconv_launch(dy, w, nullptr, dx, nullptr, add, add_mode, N, dy_size, dx_size, C, k, mode, stream,
+                       "pcb_dwconv_bwd_data");
 }
 
 extern "C" int pcb_mlp_fwd(const void* y, const double* stats, const float* gamma, const float* beta, const void* w2,

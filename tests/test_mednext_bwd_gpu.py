@@ -1,0 +1,186 @@
+"""GPU parity of the training path: gradients of the B200 kernels vs autograd on the CPU oracle.
+
+Same tolerance statement as tests/test_mednext_gpu.py: errors are relative L2 against the fp32
+oracle gradients, compared with the error of the oracle run under torch.autocast(bfloat16) (the
+reference's own bf16 training path); the engine may be at most 1.5x that + a small slack."""
+import pytest
+import torch
+
+from oracle import mednext_oracle as OM
+from pytorch_connectomics_b200 import _lib as L
+from pytorch_connectomics_b200.architectures import _mednext_ops as ops
+from pytorch_connectomics_b200.architectures import mednext as PM
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-12))
+
+
+def cl(x):
+    return ops.as_channels_last(x.to(DEV))
+
+
+def ncdhw(x):
+    return x.permute(0, 4, 1, 2, 3).float().cpu()
+
+
+def _grads_oracle(mod, x, gout, autocast, extra=None):
+    mod.zero_grad()
+    x = x.clone().requires_grad_(True)
+    if autocast:
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            out = mod(x) if extra is None else extra + mod(x)
+    else:
+        out = mod(x) if extra is None else extra + mod(x)
+    (out.float() * gout).sum().backward()
+    return x.grad.clone(), {k: p.grad.clone() for k, p in mod.named_parameters() if p.grad is not None}
+
+
+def _compare(label, got_dx, got_p, ref32, refbf, slack=4e-3):
+    dx32, p32 = ref32
+    dxbf, pbf = refbf
+    worst = 0.0
+    e, eb = rel(got_dx, dx32), rel(dxbf, dx32)
+    print(f"{label}: dx engine {e:.3e} vs bf16-path {eb:.3e}")
+    assert e <= 1.5 * eb + slack, (label, "dx", e, eb)
+    for k in p32:
+        e, eb = rel(got_p[k], p32[k]), rel(pbf[k], p32[k])
+        print(f"   {k:18s} engine {e:.3e}  bf16-path {eb:.3e}")
+        assert e <= 1.5 * eb + slack, (label, k, e, eb)
+        worst = max(worst, e)
+    return worst
+
+
+def _mk_pair(kind, cin, cout, r, k):
+    torch.manual_seed(2)
+    cls_o = {"same": OM.MedNeXtBlock, "down": OM.MedNeXtDownBlock, "up": OM.MedNeXtUpBlock}[kind]
+    cls_p = {"same": PM.MedNeXtBlock, "down": PM.MedNeXtDownBlock, "up": PM.MedNeXtUpBlock}[kind]
+    o = cls_o(cin, cout, r, k, do_res=True, norm_type="group")
+    with torch.no_grad():
+        o.norm.weight.uniform_(0.5, 1.5)
+        o.norm.bias.uniform_(-0.5, 0.5)
+    p = cls_p(cin, cout, r, k, do_res=True, norm_type="group")
+    p.load_state_dict(o.state_dict(), strict=True)
+    return o, p.to(DEV)
+
+
+@pytest.mark.parametrize("kind,cin,cout,r,k,size", [
+    ("same", 32, 32, 2, 3, (16, 16, 16)),
+    ("same", 16, 16, 4, 3, (9, 10, 11)),
+    ("same", 64, 64, 3, 5, (8, 8, 8)),
+    ("same", 256, 256, 2, 3, (4, 6, 4)),
+    ("same", 512, 512, 2, 3, (4, 4, 4)),
+    ("down", 32, 64, 2, 3, (16, 16, 16)),
+    ("down", 16, 32, 4, 3, (10, 12, 14)),
+    ("down", 256, 512, 2, 3, (4, 4, 4)),
+    ("up", 64, 32, 2, 3, (8, 8, 8)),
+    ("up", 32, 16, 4, 3, (5, 6, 7)),
+    ("up", 512, 256, 2, 3, (2, 2, 2)),
+])
+def test_block_backward(kind, cin, cout, r, k, size):
+    o, p = _mk_pair(kind, cin, cout, r, k)
+    torch.manual_seed(3)
+    x = torch.randn(2, cin, *size).bfloat16().float()
+    with torch.no_grad():
+        oshape = o(x).shape
+    gout = torch.randn(oshape).bfloat16().float()
+    ref32 = _grads_oracle(o, x, gout, False)
+    refbf = _grads_oracle(o, x, gout, True)
+    xc = cl(x).requires_grad_(True)
+    out = p(xc)
+    out.backward(cl(gout))
+    torch.cuda.synchronize()
+    got_p = {k_: q.grad for k_, q in p.named_parameters()}
+    assert set(got_p) == set(ref32[1])
+    _compare(f"{kind} C={cin}->{cout} r={r} k={k}", ncdhw(xc.grad), got_p, ref32, refbf)
+
+
+def test_up_block_backward_with_skip():
+    o, p = _mk_pair("up", 64, 32, 2, 3)
+    torch.manual_seed(4)
+    x = torch.randn(1, 64, 6, 6, 6).bfloat16().float()
+    skip = torch.randn(1, 32, 12, 12, 12).bfloat16().float()
+    gout = torch.randn(1, 32, 12, 12, 12).bfloat16().float()
+    ref32 = _grads_oracle(o, x, gout, False, extra=skip)
+    refbf = _grads_oracle(o, x, gout, True, extra=skip)
+    xc, sc = cl(x).requires_grad_(True), cl(skip).requires_grad_(True)
+    p(xc, sc).backward(cl(gout))
+    _compare("up+skip", ncdhw(xc.grad), {k: q.grad for k, q in p.named_parameters()}, ref32, refbf)
+    assert torch.equal(ncdhw(sc.grad), gout)   # d(skip) is the incoming gradient, untouched
+
+
+@pytest.mark.parametrize("c,ncls", [(32, 1), (32, 3), (16, 12), (512, 2)])
+def test_head_backward(c, ncls):
+    torch.manual_seed(5)
+    o = OM.OutBlock(c, ncls)
+    x = torch.randn(2, c, 6, 7, 8).bfloat16().float()
+    gout = torch.randn(2, ncls, 6, 7, 8)
+    xr = x.clone().requires_grad_(True)
+    (o(xr) * gout).sum().backward()
+    w, b = o.conv_out.weight.detach().to(DEV).requires_grad_(True), o.conv_out.bias.detach().to(DEV).requires_grad_(True)
+    xc = cl(x).requires_grad_(True)
+    out = ops.head_apply(xc, w, b, torch.float32)
+    out.backward(gout.to(DEV))
+    assert rel(ncdhw(xc.grad), xr.grad) < 6e-3          # bf16 rounding of dX only
+    assert rel(w.grad, o.conv_out.weight.grad) < 1e-4
+    assert rel(b.grad, o.conv_out.bias.grad) < 1e-5
+
+
+def test_stem_backward():
+    torch.manual_seed(6)
+    conv = torch.nn.Conv3d(2, 32, 1)
+    x = torch.rand(2, 2, 8, 12, 16)
+    gout = torch.randn(2, 32, 8, 12, 16).bfloat16().float()
+    (conv(x) * gout).sum().backward()
+    w, b = conv.weight.detach().to(DEV).requires_grad_(True), conv.bias.detach().to(DEV).requires_grad_(True)
+    out = ops.stem_apply(x.to(DEV), w, b)
+    out.backward(cl(gout))
+    assert rel(w.grad, conv.weight.grad) < 1e-4 and rel(b.grad, conv.bias.grad) < 1e-5
+
+
+def test_tiny_network_training_step_matches_oracle():
+    kw = dict(in_channels=1, n_channels=16, n_classes=2, exp_r=2, kernel_size=3, deep_supervision=True,
+              do_res=True, do_res_up_down=True, block_counts=[1] * 9)
+    torch.manual_seed(0)
+    o = OM.MedNeXt(**kw)
+    p = PM.MedNeXt(**kw)
+    p.load_state_dict(o.state_dict(), strict=True)
+    p.to(DEV)
+    torch.manual_seed(1)
+    x = torch.rand(2, 1, 32, 32, 32)
+    tgt = [(torch.rand(2, 2, 32 >> i, 32 >> i, 32 >> i) > 0.85).float() for i in range(5)]
+    wts = [1.0, 0.5, 0.25, 0.125, 0.0625]
+    bce = torch.nn.functional.binary_cross_entropy_with_logits
+
+    def loss_of(outs, dev):
+        return sum(w * bce(t.float(), g.to(dev)) for w, t, g in zip(wts, outs, tgt))
+
+    l32 = loss_of(o(x), "cpu")
+    l32.backward()
+    g32 = {k: q.grad.clone() for k, q in o.named_parameters() if q.grad is not None}
+    o.zero_grad()
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        outs = o(x)
+    lbf = loss_of(outs, "cpu")
+    lbf.backward()
+    gbf = {k: q.grad.clone() for k, q in o.named_parameters() if q.grad is not None}
+
+    lg = loss_of(p(x.to(DEV)), DEV)
+    lg.backward()
+    torch.cuda.synchronize()
+    print(f"loss fp32 {l32.item():.6f}  bf16-path {lbf.item():.6f}  engine {lg.item():.6f}")
+    assert abs(lg.item() - l32.item()) <= 1.5 * abs(lbf.item() - l32.item()) + 2e-3
+    gg = {k: q.grad for k, q in p.named_parameters() if q.grad is not None}
+    assert set(gg) == set(g32)
+    num = den = numb = 0.0
+    for k in g32:
+        num += float((gg[k].cpu() - g32[k]).norm() ** 2)
+        numb += float((gbf[k] - g32[k]).norm() ** 2)
+        den += float(g32[k].norm() ** 2)
+    e, eb = (num / den) ** 0.5, (numb / den) ** 0.5
+    print(f"all-parameter gradient rel-L2: engine {e:.3e}  reference-bf16-path {eb:.3e}")
+    assert e <= 1.5 * eb + 5e-3
