@@ -33,6 +33,8 @@ typedef enum { PCB_DW_SAME = 0, PCB_DW_DOWN = 1, PCB_DW_UP = 2 } pcb_dw_mode;
 
 const char* pcb_last_error(void);
 int pcb_version(void);
+/* number of pcb200 kernels launched by this process so far (bench.py reports the delta) */
+int64_t pcb_launch_count(void);
 /* 1 when the library was built for sm_100a and the current device is cc 10.x */
 int pcb_device_ok(void);
 

@@ -60,7 +60,53 @@ def lib() -> ctypes.CDLL:
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.pcb_last_error.restype = ctypes.c_char_p
         _lib.pcb_version.restype = ctypes.c_int
+        _lib.pcb_launch_count.restype = ctypes.c_int64
+        _lib.pcb_tn_workspace_floats.restype = ctypes.c_int64
     return _lib
+
+
+def launch_count() -> int:
+    return int(lib().pcb_launch_count())
+
+
+# ---- optional per-op CUDA-event timing (bench.py roofline leg); None = disabled, zero overhead
+_PROF = None
+
+
+class prof:
+    """``with prof("mlp_fwd:C32..."):`` records start/stop events on the current stream when enabled."""
+
+    __slots__ = ("name", "e0")
+
+    def __init__(self, name: str):
+        self.name = name
+        self.e0 = None
+
+    def __enter__(self):
+        if _PROF is not None and (not _PROF["want"] or self.name in _PROF["want"]):
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.e0 is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _PROF["ev"].setdefault(self.name, []).append((self.e0, e1))
+        return False
+
+
+def prof_start(want=()):
+    global _PROF
+    _PROF = {"want": set(want), "ev": {}}
+
+
+def prof_stop():
+    """Returns {name: [ms, ...]} (synchronises)."""
+    global _PROF
+    p, _PROF = _PROF, None
+    torch.cuda.synchronize()
+    return {k: [a.elapsed_time(b) for a, b in v] for k, v in (p["ev"] if p else {}).items()}
 
 
 def check(status: int, what: str = "") -> None:

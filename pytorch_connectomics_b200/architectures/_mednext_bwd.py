@@ -79,11 +79,12 @@ class BlockFn(torch.autograd.Function):
         dh = torch.empty((n, vy, h), device=dev, dtype=_BF16)
         dyhat = torch.empty((n, *ysize, c), device=dev, dtype=_BF16)
         gstats = torch.zeros((n, 2, c), device=dev, dtype=torch.float64)
-        L.check(lib.pcb_mlp_bwd(L.ptr(y), L.ptr(stats), L.ptr(g_f32), L.ptr(b_f32), L.ptr(ops.packed(w2, "pw")),
-                                L.ptr(ops.packed(b2, "f32")), L.ptr(ops.packed(w3, "pw_T")), L.ptr(ops.packed(w2, "pw_T")),
-                                L.ptr(dout), L.ptr(hact), L.ptr(dh), L.ptr(dyhat), L.ptr(gstats), ctypes.c_int64(n),
-                                L.i64x(ysize), ctypes.c_int64(c), ctypes.c_int64(h), ctypes.c_int64(co), mode, st),
-                "pcb_mlp_bwd")
+        with L.prof(f"mlp_bwd:m{mode}C{c}H{h}Co{co}V{vy}"):
+          L.check(lib.pcb_mlp_bwd(L.ptr(y), L.ptr(stats), L.ptr(g_f32), L.ptr(b_f32), L.ptr(ops.packed(w2, "pw")),
+                                  L.ptr(ops.packed(b2, "f32")), L.ptr(ops.packed(w3, "pw_T")), L.ptr(ops.packed(w2, "pw_T")),
+                                  L.ptr(dout), L.ptr(hact), L.ptr(dh), L.ptr(dyhat), L.ptr(gstats), ctypes.c_int64(n),
+                                  L.i64x(ysize), ctypes.c_int64(c), ctypes.c_int64(h), ctypes.c_int64(co), mode, st),
+                  "pcb_mlp_bwd")
         # ---- pointwise weight gradients (+ bias gradients through the all-ones column)
         dw3 = torch.empty((co, h), device=dev, dtype=torch.float32)
         db3 = torch.empty((co,), device=dev, dtype=torch.float32)

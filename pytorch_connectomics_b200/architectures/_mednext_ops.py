@@ -127,9 +127,11 @@ def block_forward(x: torch.Tensor, skip: Optional[torch.Tensor], params: List[to
     lib = L.lib()
     y = torch.empty((n, *ysize, c), device=dev, dtype=_BF16)
     stats = torch.zeros((n, 2, c), device=dev, dtype=torch.float64)
-    L.check(lib.pcb_dwconv_fwd(L.ptr(x), L.ptr(packed(w1, "dw")), L.ptr(packed(b1, "f32")), L.ptr(y), L.ptr(stats),
-                               ctypes.c_int64(n), L.i64x(size), ctypes.c_int64(c), ctypes.c_int(k),
-                               ctypes.c_int(mode), st), "pcb_dwconv_fwd")
+    vy = ysize[0] * ysize[1] * ysize[2]
+    with L.prof(f"dwconv_fwd:m{mode}C{c}V{vy}"):
+        L.check(lib.pcb_dwconv_fwd(L.ptr(x), L.ptr(packed(w1, "dw")), L.ptr(packed(b1, "f32")), L.ptr(y), L.ptr(stats),
+                                   ctypes.c_int64(n), L.i64x(size), ctypes.c_int64(c), ctypes.c_int(k),
+                                   ctypes.c_int(mode), st), "pcb_dwconv_fwd")
     out = torch.empty((n, *osize, co), device=dev, dtype=_BF16)
     res = None
     if mode == L.DW_SAME and do_res:
@@ -144,12 +146,14 @@ def block_forward(x: torch.Tensor, skip: Optional[torch.Tensor], params: List[to
         wr = packed(params[8], "pw_t" if mode == L.DW_UP else "pw")
         br = packed(params[9], "f32")
         cr = c
-    L.check(lib.pcb_mlp_fwd(L.ptr(y), L.ptr(stats), L.ptr(packed(gamma, "f32")), L.ptr(packed(beta, "f32")),
-                            L.ptr(packed(w2, "pw")), L.ptr(packed(b2, "f32")), L.ptr(packed(w3, "pw")),
-                            L.ptr(packed(b3, "f32")), L.ptr(res), L.ptr(x if has_rc else None), L.ptr(wr), L.ptr(br),
-                            L.ptr(out), ctypes.c_int64(n), L.i64x(osize), L.i64x(size), ctypes.c_int64(c),
-                            ctypes.c_int64(h), ctypes.c_int64(co), ctypes.c_int64(cr), ctypes.c_int(mode), st),
-            "pcb_mlp_fwd")
+    vo = osize[0] * osize[1] * osize[2]
+    with L.prof(f"mlp_fwd:m{mode}C{c}H{h}Co{co}V{vo}"):
+        L.check(lib.pcb_mlp_fwd(L.ptr(y), L.ptr(stats), L.ptr(packed(gamma, "f32")), L.ptr(packed(beta, "f32")),
+                                L.ptr(packed(w2, "pw")), L.ptr(packed(b2, "f32")), L.ptr(packed(w3, "pw")),
+                                L.ptr(packed(b3, "f32")), L.ptr(res), L.ptr(x if has_rc else None), L.ptr(wr), L.ptr(br),
+                                L.ptr(out), ctypes.c_int64(n), L.i64x(osize), L.i64x(size), ctypes.c_int64(c),
+                                ctypes.c_int64(h), ctypes.c_int64(co), ctypes.c_int64(cr), ctypes.c_int(mode), st),
+                "pcb_mlp_fwd")
     return _mark(out), y, stats
 
 

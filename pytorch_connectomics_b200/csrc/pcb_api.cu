@@ -13,10 +13,13 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_add_fetch(&g_launches, 1ULL, __ATOMIC_RELAXED); }
 }  // namespace pcb
 
 extern "C" const char* pcb_last_error(void) { return pcb::g_err; }
 extern "C" int pcb_version(void) { return 100; }
+extern "C" int64_t pcb_launch_count(void) { return (int64_t)__atomic_load_n(&pcb::g_launches, __ATOMIC_RELAXED); }
 extern "C" int pcb_device_ok(void) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) { pcb::set_error("no CUDA device"); cudaGetLastError(); return 0; }

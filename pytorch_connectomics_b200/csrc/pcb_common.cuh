@@ -10,6 +10,7 @@ namespace pcb {
 
 // ----------------------------------------------------------------------------- error plumbing
 void set_error(const char* fmt, ...);
+void count_launch();
 #define PCB_CHECK_ARG(cond, ...)                                   \
   do {                                                             \
     if (!(cond)) {                                                 \
@@ -19,6 +20,7 @@ void set_error(const char* fmt, ...);
   } while (0)
 #define PCB_CHECK_LAUNCH(what)                                     \
   do {                                                             \
+    pcb::count_launch();                                           \
     cudaError_t e__ = cudaGetLastError();                          \
     if (e__ != cudaSuccess) {                                      \
       pcb::set_error("%s: %s", what, cudaGetErrorString(e__));     \

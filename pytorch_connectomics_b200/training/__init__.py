@@ -1,0 +1,2 @@
+"""Data-parallel training step plumbing (DDP seam, ``training/lightning/trainer.py:231-256``)."""
+from .ddp import FlatGradArena, allreduce_gradients  # noqa: F401

@@ -1,0 +1,56 @@
+"""DDP seam on the B200 box: one flat gradient arena + ONE NCCL all-reduce per optimizer step.
+
+The reference gets data parallelism from Lightning's ``DDPStrategy`` -> ``torch.nn.parallel.
+DistributedDataParallel`` (``connectomics/training/lightning/trainer.py:231-256,314-334``): bucketed
+all-reduce of every gradient, ``find_unused_parameters=True`` for MedNeXt (unused deep-supervision
+heads and ``dummy_tensor``).  Here every parameter's ``.grad`` is a view into one contiguous fp32 arena,
+so autograd accumulates straight into it (in place), parameters that receive no gradient simply stay
+zero (the ``find_unused_parameters`` semantics without the graph walk), and the exchange step is a single
+``all_reduce(SUM)`` over NVLink followed by a scale by 1/world (gradient mean, as DDP).  With
+``accumulate_grad_batches`` > 1 call :func:`allreduce_gradients` only on the boundary micro-step.
+"""
+
+from __future__ import annotations
+
+from typing import Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+class FlatGradArena:
+    def __init__(self, params: Iterable[torch.nn.Parameter]):
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("FlatGradArena: no trainable parameters")
+        dev = self.params[0].device
+        total = sum(p.numel() for p in self.params)
+        self.buffer = torch.zeros(total, device=dev, dtype=torch.float32)
+        off = 0
+        for p in self.params:
+            if p.dtype != torch.float32 or p.device != dev:
+                raise ValueError("FlatGradArena expects fp32 parameters on one device")
+            p.grad = self.buffer[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero(self) -> None:
+        """Use instead of ``optimizer.zero_grad()`` (which would detach the views when set_to_none)."""
+        self.buffer.zero_()
+
+    def rebind(self) -> None:
+        """Re-attach ``.grad`` views if something replaced them (e.g. ``zero_grad(set_to_none=True)``)."""
+        off = 0
+        for p in self.params:
+            view = self.buffer[off:off + p.numel()].view_as(p)
+            if p.grad is None or p.grad.data_ptr() != view.data_ptr():
+                p.grad = view
+            off += p.numel()
+
+    def allreduce(self, group: Optional[dist.ProcessGroup] = None) -> None:
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.buffer, op=dist.ReduceOp.SUM, group=group)
+            self.buffer.mul_(1.0 / dist.get_world_size(group))
+
+
+def allreduce_gradients(arena: FlatGradArena, group: Optional[dist.ProcessGroup] = None) -> None:
+    arena.allreduce(group)
