@@ -63,10 +63,12 @@ __device__ __forceinline__ int colsum16_col(int lane) {
 __device__ __forceinline__ void stage_rows_k(uint8_t* dst, const uint4* __restrict__ src, int rows, int kc8,
                                              int64_t pitch8, int tid) {
   const uint32_t sbo = kc8 * 128;
-  for (int q = tid; q < rows * kc8; q += 128) {
-    const int r = q / kc8, c8 = q - r * kc8;
-    *reinterpret_cast<uint4*>(dst + (r >> 3) * sbo + c8 * 128 + (r & 7) * 16) = __ldg(src + (int64_t)r * pitch8 + c8);
-  }
+  staged_copy<8>(rows * kc8, tid, 128,
+      [&](int q) { const int r = q >> __ffs(kc8) - 1, c8 = q & (kc8 - 1); return __ldg(src + (int64_t)r * pitch8 + c8); },
+      [&](int q, const uint4& v) {
+        const int r = q >> __ffs(kc8) - 1, c8 = q & (kc8 - 1);
+        *reinterpret_cast<uint4*>(dst + (r >> 3) * sbo + c8 * 128 + (r & 7) * 16) = v;
+      });
 }
 
 // ============================================================================ fused MLP backward (dgrad)
@@ -140,19 +142,24 @@ __global__ void __launch_bounds__(128) mlp_bwd_kernel(MlpBwdArgs a) {
     for (int kc = 0; kc < nkc; ++kc) {
       if (!(nkc == 1 && hc > 0)) {
         const uint32_t sbo = kc8 * 128;
-        for (int q = tid; q < 128 * kc8; q += 128) {
-          const int r = q / kc8, c8 = q - r * kc8;
-          uint4 v = make_uint4(0, 0, 0, 0);
-          if (tile0 + r < a.Vy) {
-            float f[8];
-            unpack8(__ldg(yn + (tile0 + r) * (a.C >> 3) + kc * kc8 + c8), f);
-            const int c0 = kc * a.KC + c8 * 8;
+        staged_copy<8>(128 * kc8, tid, 128,
+            [&](int q) {
+              const int r = q >> __ffs(kc8) - 1, c8 = q & (kc8 - 1);
+              return tile0 + r < a.Vy ? __ldg(yn + (tile0 + r) * (a.C >> 3) + kc * kc8 + c8) : make_uint4(0, 0, 0, 0);
+            },
+            [&](int q, const uint4& raw) {
+              const int r = q >> __ffs(kc8) - 1, c8 = q & (kc8 - 1);
+              uint4 v = make_uint4(0, 0, 0, 0);
+              if (tile0 + r < a.Vy) {
+                float f[8];
+                unpack8(raw, f);
+                const int c0 = kc * a.KC + c8 * 8;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sScale[c0 + j], sShift[c0 + j]);
-            v = pack8(f);
-          }
-          *reinterpret_cast<uint4*>(sA + (r >> 3) * sbo + c8 * 128 + (r & 7) * 16) = v;
-        }
+                for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sScale[c0 + j], sShift[c0 + j]);
+                v = pack8(f);
+              }
+              *reinterpret_cast<uint4*>(sA + (r >> 3) * sbo + c8 * 128 + (r & 7) * 16) = v;
+            });
       }
       stage_rows_k(sW2, a.w2 + (int64_t)hc * a.N1 * (a.C >> 3) + kc * kc8, a.N1, kc8, a.C >> 3, tid);
       fence_proxy_async_smem();
@@ -170,13 +177,16 @@ __global__ void __launch_bounds__(128) mlp_bwd_kernel(MlpBwdArgs a) {
     for (int kc = 0; kc < nko; ++kc) {
       if (!(nko == 1 && hc > 0)) {
         const uint32_t sbo = ko8 * 128;
-        for (int q = tid; q < 128 * ko8; q += 128) {
-          const int r = q / ko8, c8 = q - r * ko8;
-          const int64_t ro = sRowO[r];
-          uint4 v = make_uint4(0, 0, 0, 0);
-          if (ro >= 0) v = __ldg(dn + ro * (a.Co >> 3) + kc * ko8 + c8);
-          *reinterpret_cast<uint4*>(sD + (r >> 3) * sbo + c8 * 128 + (r & 7) * 16) = v;
-        }
+        staged_copy<8>(128 * ko8, tid, 128,
+            [&](int q) {
+              const int r = q >> __ffs(ko8) - 1, c8 = q & (ko8 - 1);
+              const int64_t ro = sRowO[r];
+              return ro >= 0 ? __ldg(dn + ro * (a.Co >> 3) + kc * ko8 + c8) : make_uint4(0, 0, 0, 0);
+            },
+            [&](int q, const uint4& v) {
+              const int r = q >> __ffs(ko8) - 1, c8 = q & (ko8 - 1);
+              *reinterpret_cast<uint4*>(sD + (r >> 3) * sbo + c8 * 128 + (r & 7) * 16) = v;
+            });
       }
       stage_rows_k(sW3t, a.w3t + (int64_t)hc * a.N1 * (a.Co >> 3) + kc * ko8, a.N1, ko8, a.Co >> 3, tid);
       fence_proxy_async_smem();
@@ -209,8 +219,9 @@ __global__ void __launch_bounds__(128) mlp_bwd_kernel(MlpBwdArgs a) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float h = __uint_as_float(v1[j]) + __ldg(bp + j);
-          ha[j] = gelu_f(h);
-          dhv[j] = __uint_as_float(vg[j]) * gelu_grad_f(h);
+          float gr;
+          gelu_fast_vg(h, ha[j], gr);
+          dhv[j] = __uint_as_float(vg[j]) * gr;
         }
         const uint4 d0 = pack8(dhv), d1 = pack8(dhv + 8);
         *reinterpret_cast<uint4*>(dst + (c16 * 2) * 128) = d0;
@@ -309,24 +320,26 @@ __global__ void __launch_bounds__(128) tn_gemm_kernel(TnArgs a) {
   const int n0 = nc * TN_NCHUNK;
   const int nb = min(TN_NCHUNK, a.Nb - n0), nb8 = nb >> 3;
   const bool ones = a.ones && nc == 0;
+  const bool m8pow2 = (m8n & (m8n - 1)) == 0, n8pow2 = (nb8 & (nb8 - 1)) == 0;
+  const int m8sh = __ffs(m8n) - 1, n8sh = __ffs(nb8) - 1;
   const int ncols = nb + (ones ? 16 : 0);
   // MN-major canonical layout: 16 B chunk (8 channels of voxel v) of channel-group g at g*SBO + v*16.
   // SBO padded so a quarter-warp's 8 stores land on 8 distinct 16 B bank groups.
   const uint32_t padA = m8n >= 8 ? 16 : (m8n >= 4 ? 32 : 64), padB = nb8 >= 8 ? 16 : (nb8 >= 4 ? 32 : 64);
   const uint32_t sboA = 2048 + padA, sboB = 2048 + padB;
   const uint32_t stageA = 16 * sboA, stageB = ((TN_NCHUNK >> 3) + 2) * sboB;
-  uint8_t* sA0 = smem;
-  uint8_t* sB0 = sA0 + 2 * stageA;
-  float* sScale = reinterpret_cast<float*>(sB0 + 2 * stageB);   // [nb]
+  uint8_t* sA = smem;                 // single stage: several CTAs per SM overlap load / MMA phases
+  uint8_t* sB = sA + stageA;
+  float* sScale = reinterpret_cast<float*>(sB + stageB);   // [nb]
   float* sShift = sScale + TN_NCHUNK;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sShift + TN_NCHUNK);   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sShift + TN_NCHUNK);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
 
   const uint32_t tmem_cols = tmem_cols_pow2(ncols);
   if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
-  if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_mbar_init(); }
-  // zero both A stages once: channel groups beyond the valid ones stay zero for the whole kernel
-  for (uint32_t i = tid * 16; i < 2 * stageA + 2 * stageB; i += 128 * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
+  if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  // zero the stage once: channel groups beyond the valid ones stay zero for the whole kernel
+  for (uint32_t i = tid * 16; i < stageA + stageB; i += 128 * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -337,12 +350,11 @@ __global__ void __launch_bounds__(128) tn_gemm_kernel(TnArgs a) {
   const int64_t ntiles = tps * a.N;
   int cur_n = -1;
   uint32_t it = 0;
-  uint32_t phase[2] = {0, 0};
+  uint32_t ph = 0;
   for (int64_t g = blockIdx.x; g < ntiles; g += gridDim.x, ++it) {
     const int n = (int)(g / tps);
     const int64_t v0 = (g - (int64_t)n * tps) * 128;
-    const int s = it & 1;
-    if (it >= 2) { mbar_wait(&bar[s], phase[s]); phase[s] ^= 1; }
+    if (it >= 1) { mbar_wait(bar, ph); ph ^= 1; }   // previous tile's MMAs have consumed the stage
     if (a.stats != nullptr && n != cur_n) {   // GroupNorm affine of this sample for the B channels
       __syncthreads();
       for (int c = tid; c < nb; c += 128) {
@@ -357,35 +369,38 @@ __global__ void __launch_bounds__(128) tn_gemm_kernel(TnArgs a) {
       __syncthreads();
     }
     cur_n = n;
-    uint8_t* sA = sA0 + s * stageA;
-    uint8_t* sB = sB0 + s * stageB;
     const uint4* An = a.A + (int64_t)n * a.a_sample8;
     const uint4* Bn = a.B + (int64_t)n * a.b_sample8;
-    for (int q = tid; q < 128 * m8n; q += 128) {
-      const int v = q / m8n, g8 = q - v * m8n;
-      uint4 val = make_uint4(0, 0, 0, 0);
-      if (v0 + v < a.V) {
-        const int64_t r = map_row(a.mapA, v0 + v, a.d1, a.d2, a.as1, a.as2);
-        val = __ldg(An + r * a.a_pitch8 + (m0 >> 3) + g8);
-      }
-      *reinterpret_cast<uint4*>(sA + g8 * sboA + v * 16) = val;
-    }
-    for (int q = tid; q < 128 * nb8; q += 128) {
-      const int v = q / nb8, g8 = q - v * nb8;
-      uint4 val = make_uint4(0, 0, 0, 0);
-      if (v0 + v < a.V) {
-        const int64_t r = map_row(a.mapB, v0 + v, a.d1, a.d2, a.bs1, a.bs2);
-        val = __ldg(Bn + r * a.b_pitch8 + (n0 >> 3) + g8);
-        if (a.stats != nullptr) {
-          float f[8];
-          unpack8(val, f);
+    staged_copy<8>(128 * m8n, tid, 128,
+        [&](int q) {
+          const int v = m8pow2 ? (q >> m8sh) : (q / m8n), g8 = q - v * m8n;
+          if (v0 + v >= a.V) return make_uint4(0, 0, 0, 0);
+          const int64_t r = map_row(a.mapA, v0 + v, a.d1, a.d2, a.as1, a.as2);
+          return __ldg(An + r * a.a_pitch8 + (m0 >> 3) + g8);
+        },
+        [&](int q, const uint4& val) {
+          const int v = m8pow2 ? (q >> m8sh) : (q / m8n), g8 = q - v * m8n;
+          *reinterpret_cast<uint4*>(sA + g8 * sboA + v * 16) = val;
+        });
+    staged_copy<8>(128 * nb8, tid, 128,
+        [&](int q) {
+          const int v = n8pow2 ? (q >> n8sh) : (q / nb8), g8 = q - v * nb8;
+          if (v0 + v >= a.V) return make_uint4(0, 0, 0, 0);
+          const int64_t r = map_row(a.mapB, v0 + v, a.d1, a.d2, a.bs1, a.bs2);
+          return __ldg(Bn + r * a.b_pitch8 + (n0 >> 3) + g8);
+        },
+        [&](int q, const uint4& raw) {
+          const int v = n8pow2 ? (q >> n8sh) : (q / nb8), g8 = q - v * nb8;
+          uint4 val = raw;
+          if (a.stats != nullptr && v0 + v < a.V) {
+            float f[8];
+            unpack8(raw, f);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sScale[g8 * 8 + j], sShift[g8 * 8 + j]);
-          val = pack8(f);
-        }
-      }
-      *reinterpret_cast<uint4*>(sB + g8 * sboB + v * 16) = val;
-    }
+            for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sScale[g8 * 8 + j], sShift[g8 * 8 + j]);
+            val = pack8(f);
+          }
+          *reinterpret_cast<uint4*>(sB + g8 * sboB + v * 16) = val;
+        });
     if (ones) {   // column nb = 1.0 for valid voxels (bf16 0x3F80), the other 15 columns zero
       const int v = tid;
       *reinterpret_cast<uint4*>(sB + nb8 * sboB + v * 16) = make_uint4((v0 + v < a.V) ? 0x3F80u : 0u, 0, 0, 0);
@@ -397,15 +412,10 @@ __global__ void __launch_bounds__(128) tn_gemm_kernel(TnArgs a) {
       const uint64_t ad = umma_desc(smem_u32(sA), 128, sboA), bd = umma_desc(smem_u32(sB), 128, sboB);
       for (int k = 0; k < 8; ++k)   // 128 voxels = 8 x K16; K-groups of 8 voxels are LBO = 128 B apart
         umma_bf16(acc, ad + (uint64_t)(k * 16), bd + (uint64_t)(k * 16), idesc, (it > 0 || k > 0) ? 1u : 0u);
-      tc_commit(&bar[s]);
+      tc_commit(bar);
     }
   }
-  // drain: the last commit covers all earlier MMAs
-  if (it > 0) {
-    const int s = (it - 1) & 1;
-    mbar_wait(&bar[s], phase[s]);
-    if (it > 1) { const int s2 = it & 1; mbar_wait(&bar[s2], phase[s2]); }
-  }
+  if (it > 0) mbar_wait(bar, ph);   // drain
   tc_fence_after();
   {
     const uint32_t trow = acc + ((uint32_t)(warp * 32) << 16);
@@ -476,12 +486,16 @@ __global__ void __launch_bounds__(128) pw_kernel(PwArgs a) {
   const uint4* An = a.A + (int64_t)n * a.Vin * (a.K >> 3);
   for (int kc = 0; kc < a.K / a.KC; ++kc) {
     const uint32_t sbo = kc8 * 128;
-    for (int q = tid; q < 128 * kc8; q += 128) {
-      const int r = q / kc8, c8 = q - r * kc8;
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (tile0 + r < a.Vout) v = __ldg(An + map_row(a.map, tile0 + r, a.d1, a.d2, a.s1, a.s2) * (a.K >> 3) + kc * kc8 + c8);
-      *reinterpret_cast<uint4*>(sA + (r >> 3) * sbo + c8 * 128 + (r & 7) * 16) = v;
-    }
+    staged_copy<8>(128 * kc8, tid, 128,
+        [&](int q) {
+          const int r = q >> __ffs(kc8) - 1, c8 = q & (kc8 - 1);
+          if (tile0 + r >= a.Vout) return make_uint4(0, 0, 0, 0);
+          return __ldg(An + map_row(a.map, tile0 + r, a.d1, a.d2, a.s1, a.s2) * (a.K >> 3) + kc * kc8 + c8);
+        },
+        [&](int q, const uint4& v) {
+          const int r = q >> __ffs(kc8) - 1, c8 = q & (kc8 - 1);
+          *reinterpret_cast<uint4*>(sA + (r >> 3) * sbo + c8 * 128 + (r & 7) * 16) = v;
+        });
     stage_rows_k(sW, a.W + (int64_t)nt * a.NT * (a.K >> 3) + kc * kc8, a.NT, kc8, a.K >> 3, tid);
     fence_proxy_async_smem();
     __syncthreads();
@@ -641,6 +655,141 @@ __global__ void __launch_bounds__(256) dw_wgrad_kernel(const uint4* __restrict__
     atomicAdd(&dW[(int64_t)((dz * K + dyy) * K) * C + i], s_acc[i]);
 }
 
+// ---------------------------------------------------------------------------- tiled SAME-mode dw wgrad
+// Persistent CTAs loop over 4x8x16 bricks (32 channels): the dy brick and the x brick (+halo) are staged in
+// shared memory once, thread (tap row (dz,dy), channel chunk, row partition) slides along W keeping the K
+// x-taps in registers, so every staged voxel is read ~K^2/partitions times from shared memory instead of
+// K^2 times from L2.  Accumulators live in registers across bricks; one f64 reduction per CTA at the end.
+constexpr int WT_Z = 4, WT_Y = 8, WT_X = 16;
+
+template <int K>
+__global__ void __launch_bounds__(256, 2) dw_wgrad_same_tiled_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x,
+                                                                  double* __restrict__ dW, int D, int H, int W, int C,
+                                                                  int tiles_y, int tiles_x, int nbricks, int N) {
+  constexpr int P = K / 2;
+  constexpr int BZ = WT_Z + 2 * P, BY = WT_Y + 2 * P, BX = WT_X + 2 * P, PITCH = BX + 1;
+  constexpr int NPART = 256 / (K * K * 4);      // row partitions (threads beyond K*K*4*NPART idle)
+  extern __shared__ __align__(16) uint8_t dsm[];
+  uint4* s_x = reinterpret_cast<uint4*>(dsm);                      // [BZ][BY][PITCH][4]
+  uint4* s_dy = s_x + BZ * BY * PITCH * 4;                         // [WT_Z][WT_Y][WT_X][4]
+  double* s_red = reinterpret_cast<double*>(s_dy + WT_Z * WT_Y * WT_X * 4);   // [K^3][32]
+  const int tid = threadIdx.x, CH = C >> 3, cg = blockIdx.y;
+  const int cc = tid & 3, tr = (tid >> 2) % (K * K), part = (tid >> 2) / (K * K);
+  const int dz = tr / K, dyy = tr % K;
+  const bool worker = part < NPART;
+  uint64_t acc[K][4];
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[k][c] = 0ull;
+  for (int i = tid; i < K * K * K * 32; i += 256) s_red[i] = 0.0;
+
+  for (int b = blockIdx.x; b < nbricks * N; b += gridDim.x) {
+    const int n = b / nbricks;
+    int t = b - n * nbricks;
+    const int tx = t % tiles_x; t /= tiles_x;
+    const int ty = t % tiles_y, tz = t / tiles_y;
+    const int z0 = tz * WT_Z, y0 = ty * WT_Y, x0 = tx * WT_X;
+    const uint4* xn = x + (int64_t)n * D * H * W * CH + cg * 4;
+    const uint4* dn = dy + (int64_t)n * D * H * W * CH + cg * 4;
+    __syncthreads();   // previous brick fully consumed
+    staged_copy<8>(BZ * BY * BX * 4, tid, 256,
+        [&](int q) {
+          const int c4 = q & 3, v = q >> 2;
+          const int bx = v % BX, by = (v / BX) % BY, bz = v / (BX * BY);
+          const int gz = z0 + bz - P, gy = y0 + by - P, gx = x0 + bx - P;
+          if (gz < 0 || gz >= D || gy < 0 || gy >= H || gx < 0 || gx >= W) return make_uint4(0, 0, 0, 0);
+          return __ldg(xn + (((int64_t)gz * H + gy) * W + gx) * CH + c4);
+        },
+        [&](int q, const uint4& v4) {
+          const int c4 = q & 3, v = q >> 2;
+          const int bx = v % BX, by = (v / BX) % BY, bz = v / (BX * BY);
+          s_x[((bz * BY + by) * PITCH + bx) * 4 + c4] = v4;
+        });
+    staged_copy<8>(WT_Z * WT_Y * WT_X * 4, tid, 256,
+        [&](int q) {
+          const int c4 = q & 3, v = q >> 2;
+          const int bx = v % WT_X, by = (v / WT_X) % WT_Y, bz = v / (WT_X * WT_Y);
+          const int gz = z0 + bz, gy = y0 + by, gx = x0 + bx;
+          if (gz >= D || gy >= H || gx >= W) return make_uint4(0, 0, 0, 0);
+          return __ldg(dn + (((int64_t)gz * H + gy) * W + gx) * CH + c4);
+        },
+        [&](int q, const uint4& v4) { s_dy[q] = v4; });
+    __syncthreads();
+    if (worker) {
+      for (int r = part; r < WT_Z * WT_Y; r += NPART) {     // (z,y) rows of the brick owned by this partition
+        const int lz = r / WT_Y, ly = r % WT_Y;
+        const uint4* xrow = s_x + (((lz + dz) * BY + (ly + dyy)) * PITCH) * 4 + cc;
+        const uint4* drow = s_dy + ((lz * WT_Y + ly) * WT_X) * 4 + cc;
+        uint64_t win[K][4];                                  // sliding window of K x-taps
+#pragma unroll
+        for (int k = 0; k < K - 1; ++k) {
+          const uint4 v4 = xrow[k * 4];
+          win[k + 1][0] = pk2(bf16_lo(v4.x), bf16_hi(v4.x)); win[k + 1][1] = pk2(bf16_lo(v4.y), bf16_hi(v4.y));
+          win[k + 1][2] = pk2(bf16_lo(v4.z), bf16_hi(v4.z)); win[k + 1][3] = pk2(bf16_lo(v4.w), bf16_hi(v4.w));
+        }
+#pragma unroll 4
+        for (int xx = 0; xx < WT_X; ++xx) {
+#pragma unroll
+          for (int k = 0; k < K - 1; ++k)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) win[k][c] = win[k + 1][c];
+          const uint4 v4 = xrow[(xx + K - 1) * 4];
+          win[K - 1][0] = pk2(bf16_lo(v4.x), bf16_hi(v4.x)); win[K - 1][1] = pk2(bf16_lo(v4.y), bf16_hi(v4.y));
+          win[K - 1][2] = pk2(bf16_lo(v4.z), bf16_hi(v4.z)); win[K - 1][3] = pk2(bf16_lo(v4.w), bf16_hi(v4.w));
+          const uint4 d4 = drow[xx * 4];
+          uint64_t d[4];
+          d[0] = pk2(bf16_lo(d4.x), bf16_hi(d4.x)); d[1] = pk2(bf16_lo(d4.y), bf16_hi(d4.y));
+          d[2] = pk2(bf16_lo(d4.z), bf16_hi(d4.z)); d[3] = pk2(bf16_lo(d4.w), bf16_hi(d4.w));
+#pragma unroll
+          for (int k = 0; k < K; ++k)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[k][c] = fma2(d[c], win[k][c], acc[k][c]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (worker) {
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float a0, a1;
+        upk2(acc[k][c], a0, a1);
+        atomicAdd(&s_red[((dz * K + dyy) * K + k) * 32 + cc * 8 + 2 * c], (double)a0);
+        atomicAdd(&s_red[((dz * K + dyy) * K + k) * 32 + cc * 8 + 2 * c + 1], (double)a1);
+      }
+  }
+  __syncthreads();
+  for (int i = tid; i < K * K * K * 32; i += 256) atomicAdd(&dW[(int64_t)(i >> 5) * C + cg * 32 + (i & 31)], s_red[i]);
+}
+
+template <int K>
+static bool launch_dw_wgrad_tiled(cudaStream_t st, const uint4* dy, const uint4* x, double* dW, int D, int H, int W, int C, int N) {
+  constexpr int P = K / 2;
+  const size_t smem = (size_t)(WT_Z + 2 * P) * (WT_Y + 2 * P) * (WT_X + 2 * P + 1) * 64 + (size_t)WT_Z * WT_Y * WT_X * 64 +
+                      (size_t)K * K * K * 32 * 8;
+  if (smem > 227 * 1024) return false;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(dw_wgrad_same_tiled_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (cudaFuncSetAttribute(dw_wgrad_same_tiled_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    configured = true;
+  }
+  const int tz = (D + WT_Z - 1) / WT_Z, ty = (H + WT_Y - 1) / WT_Y, tx = (W + WT_X - 1) / WT_X;
+  const int64_t nb = (int64_t)tz * ty * tx;
+  if (nb * N >= (1ll << 31)) return false;
+  int ctas = 148 * 2;
+  if (nb * N < ctas) ctas = (int)(nb * N);
+  dim3 grid((unsigned)ctas, (unsigned)(C / 32));
+  dw_wgrad_same_tiled_kernel<K><<<grid, 256, smem, st>>>(dy, x, dW, D, H, W, C, ty, tx, (int)nb, N);
+  return true;
+}
+
 // ============================================================================ head / stem backward
 // head: out[n,k,v] = sum_c x[v,c] w[c,k] + b[k].   dX[v,c] = sum_k dO[k,v] w[c,k];
 //       dW[c,k] += sum_v x[v,c] dO[k,v]; db[k] += sum_v dO[k,v]     (float64 accumulators)
@@ -787,6 +936,7 @@ extern "C" int pcb_mlp_bwd(const void* y, const double* stats, const float* gamm
   PCB_CHECK_ARG(smem <= 227 * 1024, "pcb_mlp_bwd: tile needs %zu B shared memory", smem);
   static bool configured = false;
   if (!configured) {
+    cudaFuncSetAttribute(mlp_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (cudaFuncSetAttribute(mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
       set_error("pcb_mlp_bwd: cudaFuncSetAttribute failed"); return PCB_ERR_CUDA;
     }
@@ -798,12 +948,18 @@ extern "C" int pcb_mlp_bwd(const void* y, const double* stats, const float* gamm
   return PCB_OK;
 }
 
-static inline int tn_num_ctas(int64_t ntiles) { return (int)(ntiles < 148 ? ntiles : 148); }
+static inline int tn_num_ctas(int64_t ntiles, int64_t Mtot, int64_t Nc) {
+  int64_t p = 148 * 3;                                  // three single-stage CTAs per SM
+  const int64_t cap = (int64_t)(96 << 20) / (Mtot * Nc * 4);   // keep the partial-sum workspace <= 96 MB
+  if (p > cap) p = cap < 1 ? 1 : cap;
+  if (p > ntiles) p = ntiles;
+  return (int)p;
+}
 
 extern "C" int64_t pcb_tn_workspace_floats(int64_t Ma, int64_t Nb, int ones, int64_t N, const int64_t box[3]) {
   const int64_t ntiles = (box[0] * box[1] * box[2] + 127) / 128 * N;
   const int64_t Mtot = (Ma + 127) / 128 * 128, Nc = Nb + (ones ? 16 : 0);
-  return (int64_t)tn_num_ctas(ntiles) * Mtot * Nc;
+  return (int64_t)tn_num_ctas(ntiles, Mtot, Nc) * Mtot * Nc;
 }
 
 extern "C" int pcb_tn_gemm(const void* A, const void* B, const double* stats, const float* gamma, const float* beta,
@@ -826,12 +982,13 @@ extern "C" int pcb_tn_gemm(const void* A, const void* B, const double* stats, co
   a.Mtot = (int)((Ma + 127) / 128 * 128); a.Ncols_tot = (int)(Nb + (ones ? 16 : 0));
   a.inv_count = (float)(1.0 / (double)Vb);
   const int64_t ntiles = (a.V + 127) / 128 * N;
-  const int P = tn_num_ctas(ntiles);
+  const int P = tn_num_ctas(ntiles, a.Mtot, a.Ncols_tot);
   const int mt = a.Mtot / 128, ncn = (int)((Nb + TN_NCHUNK - 1) / TN_NCHUNK);
-  const size_t smem = 2 * (size_t)16 * (2048 + 64) + 2 * (size_t)((TN_NCHUNK >> 3) + 2) * (2048 + 64) +
+  const size_t smem = (size_t)16 * (2048 + 64) + (size_t)((TN_NCHUNK >> 3) + 2) * (2048 + 64) +
                       2 * TN_NCHUNK * sizeof(float) + 64;
   static bool configured = false;
   if (!configured) {
+    cudaFuncSetAttribute(tn_gemm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (cudaFuncSetAttribute(tn_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
       set_error("pcb_tn_gemm: cudaFuncSetAttribute failed"); return PCB_ERR_CUDA;
     }
@@ -891,6 +1048,14 @@ extern "C" int pcb_dwconv_wgrad(const void* center, const void* neigh, double* d
   PCB_CHECK_ARG(center && neigh && dW && c_size && n_size, "pcb_dwconv_wgrad: null argument");
   PCB_CHECK_ARG(k == 3 || k == 5 || k == 7, "MedNeXt kernel_size must be 3, 5, or 7. Got: %d", k);
   PCB_CHECK_ARG(C % 8 == 0 && C > 0 && (stride == 1 || stride == 2) && N > 0 && N <= 65535, "pcb_dwconv_wgrad: bad shape");
+  cudaStream_t st0 = (cudaStream_t)stream;
+  if (stride == 1 && C % 32 == 0 && c_size[0] == n_size[0] && c_size[1] == n_size[1] && c_size[2] == n_size[2]) {
+    bool ok = false;
+    if (k == 3) ok = launch_dw_wgrad_tiled<3>(st0, (const uint4*)center, (const uint4*)neigh, dW, (int)c_size[0], (int)c_size[1], (int)c_size[2], (int)C, (int)N);
+    else if (k == 5) ok = launch_dw_wgrad_tiled<5>(st0, (const uint4*)center, (const uint4*)neigh, dW, (int)c_size[0], (int)c_size[1], (int)c_size[2], (int)C, (int)N);
+    else ok = launch_dw_wgrad_tiled<7>(st0, (const uint4*)center, (const uint4*)neigh, dW, (int)c_size[0], (int)c_size[1], (int)c_size[2], (int)C, (int)N);
+    if (ok) { PCB_CHECK_LAUNCH("pcb_dwconv_wgrad(tiled)"); return PCB_OK; }
+  }
   DwWgArgs a{(int)c_size[0], (int)c_size[1], (int)c_size[2], (int)n_size[0], (int)n_size[1], (int)n_size[2], (int)C, stride};
   const int64_t items = (int64_t)a.c0 * a.c1 * ((a.c2 + DW_XB_WG - 1) / DW_XB_WG) * (C / 8);
   int blocks = (int)((items + 255) / 256);

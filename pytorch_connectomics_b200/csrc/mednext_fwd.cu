@@ -13,6 +13,8 @@
 //                    layout, the expanded [128 x H] tile lives only in TMEM/shared memory.
 //   head_kernel      OutBlock 1x1x1 (C -> ncls), NDHWC bf16 -> NCDHW(any dtype)  (HBM-bound)
 #include "../../include/pcb200.h"
+#include <stdlib.h>
+
 #include "pcb_common.cuh"
 
 namespace pcb {
@@ -205,6 +207,175 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const uint4* __restrict__ x
     atomicAdd(&stats[(int64_t)n * 2 * C + i], s_stats[i]);
 }
 
+// ---------------------------------------------------------------------------- tiled SAME-mode stencil
+// One CTA = one 4x8x16 output brick x 32 channels.  The (4+2P)x(8+2P)x(16+2P) input brick is staged in
+// shared memory with batched, fully coalesced 128-bit loads (zero fill outside the volume); every thread
+// owns 8 consecutive outputs along W for 8 channels (64 fp32 accumulators, packed FFMA2), so each staged
+// input column is read once per (dz,dy) row and reused by up to K taps x 8 outputs.  Row pitch is padded by
+// one voxel (64 B) so a quarter-warp's LDS.128 touches 8 distinct 16 B bank groups.
+constexpr int DT_Z = 4, DT_Y = 8, DT_X = 16, DT_XB = 8;
+
+template <int K>
+__global__ void __launch_bounds__(256, 2) dwconv_same_tiled_kernel(const uint4* __restrict__ x, const float* __restrict__ w,
+                                                                const float* __restrict__ bias, uint4* __restrict__ y,
+                                                                double* __restrict__ stats, const uint4* __restrict__ add,
+                                                                DwArgs a, int tiles_y, int tiles_x) {
+  constexpr int P = K / 2;
+  constexpr int BZ = DT_Z + 2 * P, BY = DT_Y + 2 * P, BX = DT_X + 2 * P, PITCH = BX + 1;   // voxels
+  extern __shared__ __align__(16) uint8_t dsm[];
+  uint4* s_in = reinterpret_cast<uint4*>(dsm);                       // [BZ][BY][PITCH][4 chunks]
+  float* s_w = reinterpret_cast<float*>(s_in + BZ * BY * PITCH * 4); // [K^3][32]
+  double* s_stats = reinterpret_cast<double*>(s_w + K * K * K * 32); // [64]
+  const int tid = threadIdx.x;
+  const int CH = a.C >> 3;
+  const int cg = blockIdx.y;                 // 32-channel group
+  const int n = blockIdx.z;
+  int t = blockIdx.x;
+  const int tx = t % tiles_x; t /= tiles_x;
+  const int ty = t % tiles_y;
+  const int tz = t / tiles_y;
+  const int z0 = tz * DT_Z, y0 = ty * DT_Y, x0 = tx * DT_X;
+
+  for (int i = tid; i < K * K * K * 32; i += 256) s_w[i] = w[(i >> 5) * a.C + cg * 32 + (i & 31)];
+  if (tid < 64) s_stats[tid] = 0.0;
+  const uint4* xn = x + (int64_t)n * a.D * a.H * a.W * CH + cg * 4;
+  staged_copy<8>(BZ * BY * BX * 4, tid, 256,
+      [&](int q) {
+        const int cc = q & 3, v = q >> 2;
+        const int bx = v % BX, by = (v / BX) % BY, bz = v / (BX * BY);
+        const int gz = z0 + bz - P, gy = y0 + by - P, gx = x0 + bx - P;
+        if (gz < 0 || gz >= a.D || gy < 0 || gy >= a.H || gx < 0 || gx >= a.W) return make_uint4(0, 0, 0, 0);
+        return __ldg(xn + (((int64_t)gz * a.H + gy) * a.W + gx) * CH + cc);
+      },
+      [&](int q, const uint4& v4) {
+        const int cc = q & 3, v = q >> 2;
+        const int bx = v % BX, by = (v / BX) % BY, bz = v / (BX * BY);
+        s_in[((bz * BY + by) * PITCH + bx) * 4 + cc] = v4;
+      });
+  __syncthreads();
+
+  const int cc = tid & 3, ly = (tid >> 2) & 7, xb = (tid >> 5) & 1, lz = tid >> 6;
+  uint64_t acc[DT_XB][4];
+#pragma unroll
+  for (int j = 0; j < DT_XB; ++j)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[j][c] = 0ull;
+#pragma unroll 1
+  for (int dz = 0; dz < K; ++dz) {
+#pragma unroll 1
+    for (int dy = 0; dy < K; ++dy) {
+      uint64_t wv[K][4];
+#pragma unroll
+      for (int dx = 0; dx < K; ++dx) {
+        const float4* wp = reinterpret_cast<const float4*>(s_w + ((dz * K + dy) * K + dx) * 32 + cc * 8);
+        const float4 w0 = wp[0], w1 = wp[1];
+        wv[dx][0] = pk2(w0.x, w0.y); wv[dx][1] = pk2(w0.z, w0.w); wv[dx][2] = pk2(w1.x, w1.y); wv[dx][3] = pk2(w1.z, w1.w);
+      }
+      const uint4* row = s_in + (((lz + dz) * BY + (ly + dy)) * PITCH + xb * DT_XB) * 4 + cc;
+#pragma unroll
+      for (int i = 0; i < DT_XB + K - 1; ++i) {
+        const uint4 v4 = row[i * 4];
+        uint64_t f[4];
+        f[0] = pk2(bf16_lo(v4.x), bf16_hi(v4.x)); f[1] = pk2(bf16_lo(v4.y), bf16_hi(v4.y));
+        f[2] = pk2(bf16_lo(v4.z), bf16_hi(v4.z)); f[3] = pk2(bf16_lo(v4.w), bf16_hi(v4.w));
+#pragma unroll
+        for (int dx = 0; dx < K; ++dx) {
+          const int j = i - dx;
+          if (j >= 0 && j < DT_XB) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[j][c] = fma2(f[c], wv[dx][c], acc[j][c]);
+          }
+        }
+      }
+    }
+  }
+  float bv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (bias != nullptr) {
+    const float4* bp = reinterpret_cast<const float4*>(bias + cg * 32 + cc * 8);
+    const float4 b0 = __ldg(bp), b1 = __ldg(bp + 1);
+    bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+  }
+  float ssum[8], ssq[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) { ssum[c] = 0.f; ssq[c] = 0.f; }
+  const int oz = z0 + lz, oy = y0 + ly;
+  if (oz < a.D && oy < a.H) {
+    const int64_t rowoff = ((((int64_t)n * a.D + oz) * a.H + oy) * a.W) * CH + cg * 4 + cc;
+    uint4 addv[DT_XB];
+    if (add != nullptr) {
+#pragma unroll
+      for (int j = 0; j < DT_XB; ++j) {
+        const int ox = x0 + xb * DT_XB + j;
+        addv[j] = ox < a.W ? __ldg(add + rowoff + (int64_t)ox * CH) : make_uint4(0, 0, 0, 0);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < DT_XB; ++j) {
+      const int ox = x0 + xb * DT_XB + j;
+      if (ox >= a.W) continue;
+      float o[8];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) upk2(acc[j][c], o[2 * c], o[2 * c + 1]);
+      if (add != nullptr) {
+        float f[8];
+        unpack8(addv[j], f);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) o[c] += f[c];
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        o[c] = round_bf16(o[c] + bv[c]);
+        ssum[c] += o[c];
+        ssq[c] = fmaf(o[c], o[c], ssq[c]);
+      }
+      y[rowoff + (int64_t)ox * CH] = pack8(o);
+    }
+  }
+  if (stats == nullptr) return;
+  // lanes sharing a channel chunk differ in bits 2..4 (ly low bits) -> butterfly, then shared/global f64 atomics
+#pragma unroll
+  for (int off = 4; off <= 16; off <<= 1) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      ssum[c] += __shfl_xor_sync(0xffffffffu, ssum[c], off);
+      ssq[c] += __shfl_xor_sync(0xffffffffu, ssq[c], off);
+    }
+  }
+  if ((tid & 31) < 4) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      atomicAdd(&s_stats[cc * 8 + c], (double)ssum[c]);
+      atomicAdd(&s_stats[32 + cc * 8 + c], (double)ssq[c]);
+    }
+  }
+  __syncthreads();
+  if (tid < 64) {
+    const int which = tid >> 5, c = tid & 31;
+    atomicAdd(&stats[(int64_t)n * 2 * a.C + which * a.C + cg * 32 + c], s_stats[tid]);
+  }
+}
+
+template <int K>
+static bool launch_dw_tiled(cudaStream_t st, const uint4* x, const float* w, const float* b, uint4* y, double* stats,
+                            const uint4* add, DwArgs a, int64_t N) {
+  constexpr int P = K / 2;
+  const size_t smem = (size_t)(DT_Z + 2 * P) * (DT_Y + 2 * P) * (DT_X + 2 * P + 1) * 64 + (size_t)K * K * K * 32 * 4 + 64 * 8;
+  if (smem > 227 * 1024) return false;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(dwconv_same_tiled_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (cudaFuncSetAttribute(dwconv_same_tiled_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    configured = true;
+  }
+  const int tz = (a.D + DT_Z - 1) / DT_Z, ty = (a.H + DT_Y - 1) / DT_Y, tx = (a.W + DT_X - 1) / DT_X;
+  dim3 grid((unsigned)(tz * ty * tx), (unsigned)(a.C / 32), (unsigned)N);
+  dwconv_same_tiled_kernel<K><<<grid, 256, smem, st>>>(x, w, b, y, stats, add, a, ty, tx);
+  return true;
+}
+
 // ============================================================================ fused MLP (tcgen05)
 struct MlpArgs {
   const uint4* y; const double* stats; const float* gamma; const float* beta;
@@ -223,14 +394,15 @@ struct MlpArgs {
 __device__ __forceinline__ void stage_weights(uint8_t* dst, const uint4* __restrict__ src, int rows, int kc8,
                                               int64_t pitch8, int tid) {
   const uint32_t sbo = kc8 * 128;
-  for (int q = tid; q < rows * kc8; q += 128) {
-    const int r = q / kc8, c8 = q - r * kc8;
-    const uint4 v = __ldg(src + (int64_t)r * pitch8 + c8);
-    *reinterpret_cast<uint4*>(dst + (r >> 3) * sbo + c8 * 128 + (r & 7) * 16) = v;
-  }
+  staged_copy<8>(rows * kc8, tid, 128,
+      [&](int q) { const int r = q >> __ffs(kc8) - 1, c8 = q & (kc8 - 1); return __ldg(src + (int64_t)r * pitch8 + c8); },
+      [&](int q, const uint4& v) {
+        const int r = q >> __ffs(kc8) - 1, c8 = q & (kc8 - 1);
+        *reinterpret_cast<uint4*>(dst + (r >> 3) * sbo + c8 * 128 + (r & 7) * 16) = v;
+      });
 }
 
-__global__ void __launch_bounds__(128) mlp_kernel(MlpArgs a) {
+__global__ void __launch_bounds__(128, 4) mlp_kernel(MlpArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5;
   const int n = blockIdx.y, cot = blockIdx.z;
@@ -305,20 +477,25 @@ __global__ void __launch_bounds__(128) mlp_kernel(MlpArgs a) {
     for (int kc = 0; kc < nkc; ++kc) {
       if (!(nkc == 1 && hc > 0)) {  // single K chunk: the normalised A tile stays resident
         const uint32_t sbo = kc8 * 128;
-        for (int q = tid; q < 128 * kc8; q += 128) {
-          const int r = q / kc8, c8 = q - r * kc8;
-          const int64_t ry = sRowY[r];
-          uint4 v = make_uint4(0, 0, 0, 0);
-          if (ry >= 0) {
-            float f[8];
-            unpack8(__ldg(yn + ry * (a.C >> 3) + kc * kc8 + c8), f);
-            const int c0 = kc * a.KC + c8 * 8;
+        staged_copy<8>(128 * kc8, tid, 128,
+            [&](int q) {
+              const int r = q >> __ffs(kc8) - 1, c8 = q & (kc8 - 1);
+              const int64_t ry = sRowY[r];
+              return ry >= 0 ? __ldg(yn + ry * (a.C >> 3) + kc * kc8 + c8) : make_uint4(0, 0, 0, 0);
+            },
+            [&](int q, const uint4& raw) {
+              const int r = q >> __ffs(kc8) - 1, c8 = q & (kc8 - 1);
+              uint4 v = make_uint4(0, 0, 0, 0);
+              if (sRowY[r] >= 0) {
+                float f[8];
+                unpack8(raw, f);
+                const int c0 = kc * a.KC + c8 * 8;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sScale[c0 + j], sShift[c0 + j]);
-            v = pack8(f);
-          }
-          *reinterpret_cast<uint4*>(sA + (r >> 3) * sbo + c8 * 128 + (r & 7) * 16) = v;
-        }
+                for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sScale[c0 + j], sShift[c0 + j]);
+                v = pack8(f);
+              }
+              *reinterpret_cast<uint4*>(sA + (r >> 3) * sbo + c8 * 128 + (r & 7) * 16) = v;
+            });
       }
       stage_weights(sW2, a.w2 + (int64_t)hc * a.N1 * (a.C >> 3) + kc * kc8, a.N1, kc8, a.C >> 3, tid);
       fence_proxy_async_smem();
@@ -349,9 +526,13 @@ __global__ void __launch_bounds__(128) mlp_kernel(MlpArgs a) {
         tmem_ld16(trow + c16 * 16, v);
         tmem_ld_wait();
         float g[16];
-        const float* bp = a.b2 + hc * a.N1 + c16 * 16;
+        const float4* bp = reinterpret_cast<const float4*>(a.b2 + hc * a.N1 + c16 * 16);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) g[j] = gelu_f(__uint_as_float(v[j]) + __ldg(bp + j));
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 b = __ldg(bp + j4);
+          gelu_fast2(__uint_as_float(v[4 * j4]) + b.x, __uint_as_float(v[4 * j4 + 1]) + b.y, g[4 * j4], g[4 * j4 + 1]);
+          gelu_fast2(__uint_as_float(v[4 * j4 + 2]) + b.z, __uint_as_float(v[4 * j4 + 3]) + b.w, g[4 * j4 + 2], g[4 * j4 + 3]);
+        }
         *reinterpret_cast<uint4*>(dst + (c16 * 2) * 128) = pack8(g);
         *reinterpret_cast<uint4*>(dst + (c16 * 2 + 1) * 128) = pack8(g + 8);
       }
@@ -377,13 +558,16 @@ __global__ void __launch_bounds__(128) mlp_kernel(MlpArgs a) {
     const uint4* xn = a.xs + (int64_t)n * a.Vin * (a.Cr >> 3);
     for (int kc = 0; kc < a.Cr / a.KCr; ++kc) {
       const uint32_t sbo = kr8 * 128;
-      for (int q = tid; q < 128 * kr8; q += 128) {
-        const int r = q / kr8, c8 = q - r * kr8;
-        const int64_t rx = sRowX[r];
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (rx >= 0) v = __ldg(xn + rx * (a.Cr >> 3) + kc * kr8 + c8);
-        *reinterpret_cast<uint4*>(sA + (r >> 3) * sbo + c8 * 128 + (r & 7) * 16) = v;
-      }
+      staged_copy<8>(128 * kr8, tid, 128,
+          [&](int q) {
+            const int r = q >> __ffs(kr8) - 1, c8 = q & (kr8 - 1);
+            const int64_t rx = sRowX[r];
+            return rx >= 0 ? __ldg(xn + rx * (a.Cr >> 3) + kc * kr8 + c8) : make_uint4(0, 0, 0, 0);
+          },
+          [&](int q, const uint4& v) {
+            const int r = q >> __ffs(kr8) - 1, c8 = q & (kr8 - 1);
+            *reinterpret_cast<uint4*>(sA + (r >> 3) * sbo + c8 * 128 + (r & 7) * 16) = v;
+          });
       stage_weights(sW3, a.wr + (int64_t)cot * a.CoT * (a.Cr >> 3) + kc * kr8, a.CoT, kr8, a.Cr >> 3, tid);
       fence_proxy_async_smem();
       __syncthreads();
@@ -439,6 +623,329 @@ __global__ void __launch_bounds__(128) mlp_kernel(MlpArgs a) {
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ============================================================================ persistent fused MLP (levels 0/1)
+// Same math as mlp_kernel, restructured for the HBM-bound top levels (C <= 64):
+//   * persistent: one CTA per SM loops over 128-voxel tiles; W2 / W3 / Wr and the GroupNorm affine of every
+//     sample stay resident in shared memory for the whole kernel;
+//   * warp-specialised: 4 loader warps (batched 128-bit loads of the next tile, GN-apply, K-major staging),
+//     1 MMA warp (one thread issues tcgen05.mma), 2 x 4 epilogue warps that alternate tiles
+//     (TMEM -> +b2 -> GELU -> bf16 -> shared;  TMEM -> +b3 (+br) + residual -> HBM);
+//   * TMEM accumulators and the A / H shared-memory tiles are double buffered; every hand-off is an
+//     mbarrier (tcgen05.commit on the MMA side), there is no __syncthreads in the tile loop.
+struct MlpFusedArgs {
+  MlpArgs m;
+  int N;             // samples
+  int nst;           // A-tile stages (4: one loader warp per stage; 2: two warps per stage)
+  int64_t tps;       // tiles per sample
+  int64_t ntiles;    // N * tps
+};
+
+constexpr int MF_LOAD_WARPS = 4, MF_EPI_WARPS = 8, MF_THREADS = 32 * (MF_LOAD_WARPS + MF_EPI_WARPS + 1);
+
+__device__ __forceinline__ void mf_row_sources(const MlpArgs& a, int ov, int& ry, int& rx) {
+  ry = -1; rx = -1;
+  if (ov >= (int)a.Vout) return;
+  if (a.mode == PCB_DW_UP) {
+    const int ox = ov % a.o2, t = ov / a.o2, oy = t % a.o1, oz = t / a.o1;
+    if (ox >= 1 && oy >= 1 && oz >= 1) {
+      ry = ((oz - 1) * (a.o1 - 1) + (oy - 1)) * (a.o2 - 1) + (ox - 1);
+      if (!((ox - 1) & 1) && !((oy - 1) & 1) && !((oz - 1) & 1))
+        rx = (((oz - 1) >> 1) * a.x1 + ((oy - 1) >> 1)) * a.x2 + ((ox - 1) >> 1);
+    }
+  } else if (a.mode == PCB_DW_DOWN) {
+    const int ox = ov % a.o2, t = ov / a.o2, oy = t % a.o1, oz = t / a.o1;
+    ry = ov;
+    rx = ((2 * oz) * a.x1 + 2 * oy) * a.x2 + 2 * ox;
+  } else {
+    ry = ov;
+  }
+}
+
+__global__ void __launch_bounds__(MF_THREADS, 1) mlp_fused_kernel(MlpFusedArgs fa) {
+  const MlpArgs& a = fa.m;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int c8n = a.C >> 3, h8n = a.H >> 3, r8n = a.Cr >> 3;
+  const bool has_rc = a.wr != nullptr;
+  const int NST = fa.nst;   // A-tile stages (4 or 2)
+  // ---- shared memory carve-up (all operand tiles in the K-major no-swizzle canonical layout)
+  uint8_t* sW2 = smem;                                   // [H x C]
+  uint8_t* sW3 = sW2 + a.H * a.C * 2;                    // [Co x H]
+  uint8_t* sWr = sW3 + a.Co * a.H * 2;                   // [Co x Cr]
+  uint8_t* sA = sWr + (has_rc ? a.Co * a.Cr * 2 : 0);    // NST x [128 x C]
+  uint8_t* sX = sA + NST * 128 * a.C * 2;                // NST x [128 x Cr]
+  uint8_t* sH = sX + (has_rc ? NST * 128 * a.Cr * 2 : 0);   // 2 x [128 x H]
+  float* sScale = reinterpret_cast<float*>(sH + 2 * 128 * a.H * 2);   // [N][C]
+  float* sShift = sScale + fa.N * a.C;                   // [N][C]
+  float* sB2 = sShift + fa.N * a.C;                      // [H]
+  float* sB3 = sB2 + a.H;                                // [Co]  (b3 + br)
+  int* sRow = reinterpret_cast<int*>(sB3 + a.Co);        // [4 loader warps][2][128] row sources of the tile in flight
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRow + 4 * 2 * 128);
+  uint64_t* a_full = bars;          // [4] loaders -> MMA
+  uint64_t* a_empty = bars + 4;     // [4] MMA -> loaders
+  uint64_t* acc1_full = bars + 8;   // [2] MMA -> epilogue
+  uint64_t* h_full = bars + 10;     // [2] epilogue -> MMA
+  uint64_t* acc2_full = bars + 12;  // [2] MMA -> epilogue
+  uint64_t* acc2_empty = bars + 14; // [2] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const uint32_t tmem_cols = tmem_cols_pow2(2 * (a.H + a.Co));
+  if (warp == MF_LOAD_WARPS + MF_EPI_WARPS) tmem_alloc(tmem_slot, tmem_cols);
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) { mbar_init(&a_full[i], 32 * (MF_LOAD_WARPS / NST)); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc1_full[i], 1); mbar_init(&h_full[i], 128); mbar_init(&acc2_full[i], 1); mbar_init(&acc2_empty[i], 128);
+    }
+    fence_mbar_init();
+  }
+  // resident weights, biases, GroupNorm affine of every sample
+  {
+    const uint32_t sbo2 = c8n * 128;
+    for (int q = tid; q < a.H * c8n; q += MF_THREADS) {
+      const int r = q / c8n, c8 = q - r * c8n;
+      *reinterpret_cast<uint4*>(sW2 + (r >> 3) * sbo2 + c8 * 128 + (r & 7) * 16) = __ldg(a.w2 + (int64_t)r * c8n + c8);
+    }
+    const uint32_t sbo3 = h8n * 128;
+    for (int q = tid; q < a.Co * h8n; q += MF_THREADS) {
+      const int r = q / h8n, c8 = q - r * h8n;
+      *reinterpret_cast<uint4*>(sW3 + (r >> 3) * sbo3 + c8 * 128 + (r & 7) * 16) = __ldg(a.w3 + (int64_t)r * h8n + c8);
+    }
+    if (has_rc) {
+      const uint32_t sbor = r8n * 128;
+      for (int q = tid; q < a.Co * r8n; q += MF_THREADS) {
+        const int r = q / r8n, c8 = q - r * r8n;
+        *reinterpret_cast<uint4*>(sWr + (r >> 3) * sbor + c8 * 128 + (r & 7) * 16) = __ldg(a.wr + (int64_t)r * r8n + c8);
+      }
+    }
+    for (int i = tid; i < a.H; i += MF_THREADS) sB2[i] = a.b2[i];
+    for (int i = tid; i < a.Co; i += MF_THREADS) sB3[i] = a.b3[i] + (has_rc ? a.br[i] : 0.f);
+    for (int i = tid; i < fa.N * a.C; i += MF_THREADS) {
+      const int n = i / a.C, c = i - n * a.C;
+      const double sm = a.stats[(int64_t)n * 2 * a.C + c], q = a.stats[(int64_t)n * 2 * a.C + a.C + c];
+      const double mean = sm * (double)a.inv_count;
+      double var = q * (double)a.inv_count - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const float g = a.gamma[c] * (float)(1.0 / sqrt(var + 1e-5));
+      sScale[i] = g;
+      sShift[i] = a.beta[c] - (float)mean * g;
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // TMEM columns: acc1[g] at g*H, acc2[g] at 2H + g*Co
+
+  if (warp < MF_LOAD_WARPS) {
+    // ===================================================================== loaders
+    // NST == 4: every warp owns the tiles  it == warp (mod 4)  and stage `warp` (4 tiles of loads in flight
+    // per SM); NST == 2: warp pairs {0,1} / {2,3} own the even / odd tiles.
+    const int wpg = MF_LOAD_WARPS / NST;             // warps per loader group (1 or 2)
+    const int grp = warp / wpg;                      // loader group = stage
+    const int lt = (warp - grp * wpg) * 32 + lane;   // thread index inside the group
+    const int nthr = wpg * 32;
+    const uint32_t sboA = c8n * 128, sboX = r8n * 128;
+    const int csh = __ffs(c8n) - 1, rsh = r8n > 0 ? __ffs(r8n) - 1 : 0;
+    const bool cpow2 = (c8n & (c8n - 1)) == 0, rpow2 = (r8n & (r8n - 1)) == 0;
+    int* rowY = sRow + grp * 256;
+    int* rowX = rowY + 128;
+    int64_t it = grp;
+    for (int64_t g = blockIdx.x + (int64_t)grp * gridDim.x; g < fa.ntiles; g += (int64_t)NST * gridDim.x, it += NST) {
+      const int64_t use = it / NST;                  // how many times this stage has been filled before
+      if (use >= 1) mbar_wait(&a_empty[grp], (uint32_t)((use - 1) & 1));
+      const int n = (int)(g / fa.tps);
+      const int tile0 = (int)((g - (int64_t)n * fa.tps) * 128);
+      if (wpg == 1) __syncwarp(); else asm volatile("bar.sync %0, 64;" ::"r"(1 + grp) : "memory");   // table reuse
+      for (int r = lt; r < 128; r += nthr) {
+        int ry, rx;
+        mf_row_sources(a, tile0 + r, ry, rx);
+        rowY[r] = ry; rowX[r] = rx;
+      }
+      if (wpg == 1) __syncwarp(); else asm volatile("bar.sync %0, 64;" ::"r"(1 + grp) : "memory");
+      const uint4* yn = a.y + (int64_t)n * a.Vy * c8n;
+      const float* sc = sScale + n * a.C;
+      const float* sh = sShift + n * a.C;
+      uint8_t* dA = sA + grp * 128 * a.C * 2;
+      staged_copy<8>(128 * c8n, lt, nthr,
+          [&](int q) {
+            const int r = cpow2 ? (q >> csh) : (q / c8n), c8 = q - r * c8n;
+            const int ry = rowY[r];
+            return ry >= 0 ? __ldg(yn + (int64_t)ry * c8n + c8) : make_uint4(0, 0, 0, 0);
+          },
+          [&](int q, const uint4& raw) {
+            const int r = cpow2 ? (q >> csh) : (q / c8n), c8 = q - r * c8n;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (rowY[r] >= 0) {
+              const float4* scp = reinterpret_cast<const float4*>(sc + c8 * 8);
+              const float4* shp = reinterpret_cast<const float4*>(sh + c8 * 8);
+              const float4 s0 = scp[0], s1 = scp[1], t0 = shp[0], t1 = shp[1];
+              float a0, a1, a2, a3, a4, a5, a6, a7;
+              upk2(fma2(pk2(bf16_lo(raw.x), bf16_hi(raw.x)), pk2(s0.x, s0.y), pk2(t0.x, t0.y)), a0, a1);
+              upk2(fma2(pk2(bf16_lo(raw.y), bf16_hi(raw.y)), pk2(s0.z, s0.w), pk2(t0.z, t0.w)), a2, a3);
+              upk2(fma2(pk2(bf16_lo(raw.z), bf16_hi(raw.z)), pk2(s1.x, s1.y), pk2(t1.x, t1.y)), a4, a5);
+              upk2(fma2(pk2(bf16_lo(raw.w), bf16_hi(raw.w)), pk2(s1.z, s1.w), pk2(t1.z, t1.w)), a6, a7);
+              v.x = pack_bf16(a0, a1); v.y = pack_bf16(a2, a3); v.z = pack_bf16(a4, a5); v.w = pack_bf16(a6, a7);
+            }
+            *reinterpret_cast<uint4*>(dA + (r >> 3) * sboA + c8 * 128 + (r & 7) * 16) = v;
+          });
+      if (has_rc) {
+        const uint4* xn = a.xs + (int64_t)n * a.Vin * r8n;
+        uint8_t* dX = sX + grp * 128 * a.Cr * 2;
+        staged_copy<8>(128 * r8n, lt, nthr,
+            [&](int q) {
+              const int r = rpow2 ? (q >> rsh) : (q / r8n), c8 = q - r * r8n;
+              const int rx = rowX[r];
+              return rx >= 0 ? __ldg(xn + (int64_t)rx * r8n + c8) : make_uint4(0, 0, 0, 0);
+            },
+            [&](int q, const uint4& v) {
+              const int r = rpow2 ? (q >> rsh) : (q / r8n), c8 = q - r * r8n;
+              *reinterpret_cast<uint4*>(dX + (r >> 3) * sboX + c8 * 128 + (r & 7) * 16) = v;
+            });
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&a_full[grp]);
+    }
+  } else if (warp == MF_LOAD_WARPS + MF_EPI_WARPS) {
+    // ===================================================================== MMA issuer (one thread)
+    if (lane == 0) {
+      const uint32_t idesc1 = umma_idesc_bf16(128, a.H, 0, 0), idesc2 = umma_idesc_bf16(128, a.Co, 0, 0);
+      const uint64_t dW2 = umma_desc(smem_u32(sW2), 128, c8n * 128);
+      const uint64_t dW3 = umma_desc(smem_u32(sW3), 128, h8n * 128);
+      const uint64_t dWr = has_rc ? umma_desc(smem_u32(sWr), 128, r8n * 128) : 0;
+      auto second_half = [&](int64_t j) {   // GEMM2 (+ res-GEMM) of local tile j
+        const int gj = (int)(j & 1), sj = (int)(j % NST);
+        mbar_wait(&h_full[gj], (uint32_t)((j >> 1) & 1));
+        if (j >= 2) mbar_wait(&acc2_empty[gj], (uint32_t)(((j >> 1) - 1) & 1));
+        tc_fence_after();
+        const uint32_t acc2 = tmem_base + 2 * a.H + gj * a.Co;
+        const uint64_t dH = umma_desc(smem_u32(sH + gj * 128 * a.H * 2), 128, h8n * 128);
+        for (int k = 0; k < a.H / 16; ++k) umma_bf16(acc2, dH + (uint64_t)(k * 16), dW3 + (uint64_t)(k * 16), idesc2, k > 0 ? 1u : 0u);
+        if (has_rc) {
+          const uint64_t dX = umma_desc(smem_u32(sX + sj * 128 * a.Cr * 2), 128, r8n * 128);
+          for (int k = 0; k < a.Cr / 16; ++k) umma_bf16(acc2, dX + (uint64_t)(k * 16), dWr + (uint64_t)(k * 16), idesc2, 1u);
+        }
+        tc_commit(&acc2_full[gj]);
+        if (has_rc) tc_commit(&a_empty[sj]);
+      };
+      int64_t it = 0;
+      for (int64_t g = blockIdx.x; g < fa.ntiles; g += gridDim.x, ++it) {
+        const int s = (int)(it % NST), gacc = (int)(it & 1);
+        mbar_wait(&a_full[s], (uint32_t)((it / NST) & 1));
+        tc_fence_after();
+        const uint32_t acc1 = tmem_base + gacc * a.H;
+        const uint64_t dA = umma_desc(smem_u32(sA + s * 128 * a.C * 2), 128, c8n * 128);
+        for (int k = 0; k < a.C / 16; ++k) umma_bf16(acc1, dA + (uint64_t)(k * 16), dW2 + (uint64_t)(k * 16), idesc1, k > 0 ? 1u : 0u);
+        tc_commit(&acc1_full[gacc]);
+        if (!has_rc) tc_commit(&a_empty[s]);
+        if (it >= 1) second_half(it - 1);
+      }
+      if (it >= 1) second_half(it - 1);
+    }
+  } else {
+    // ===================================================================== epilogue warpgroups
+    const int eg = (warp - MF_LOAD_WARPS) >> 2;          // 0 / 1: which tiles (it & 1) this group owns
+    const int wq = warp & 3;                             // TMEM lane quarter this warp may access
+    const int row = wq * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
+    const uint32_t sboH = h8n * 128;
+    const int co8 = a.Co >> 3;
+    const bool prefetch = a.res != nullptr && co8 <= 8;
+    int64_t it = eg;
+    for (int64_t g = blockIdx.x + (int64_t)eg * gridDim.x; g < fa.ntiles; g += 2 * (int64_t)gridDim.x, it += 2) {
+      const uint32_t par = (uint32_t)((it >> 1) & 1);
+      const int n = (int)(g / fa.tps);
+      const int ovi = (int)((g - (int64_t)n * fa.tps) * 128) + row;
+      int ry, rx;
+      mf_row_sources(a, ovi, ry, rx);
+      const bool in_range = ovi < (int)a.Vout, valid = in_range && ry >= 0;
+      const int64_t orow = ((int64_t)n * a.Vout + ovi) * co8;
+      uint4 rpre[8];                                     // residual / skip row, in flight during epilogue 1
+      if (prefetch) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) rpre[c] = (c < co8 && in_range) ? __ldg(a.res + orow + c) : make_uint4(0, 0, 0, 0);
+      }
+      // ---- epilogue 1: acc1 -> +b2 -> GELU -> bf16 -> sH[eg]
+      mbar_wait(&acc1_full[eg], par);
+      tc_fence_after();
+      {
+        const uint32_t trow = tmem_base + eg * a.H + lane_off;
+        uint8_t* dst = sH + eg * 128 * a.H * 2 + (row >> 3) * sboH + (row & 7) * 16;
+        for (int c16 = 0; c16 < a.H / 16; ++c16) {
+          uint32_t v[16];
+          tmem_ld16(trow + c16 * 16, v);
+          tmem_ld_wait();
+          float gl[16];
+          const float4* bp = reinterpret_cast<const float4*>(sB2 + c16 * 16);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 b = bp[j4];
+            gelu_fast2p(add2(pk2(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1])), pk2(b.x, b.y)), gl[4 * j4], gl[4 * j4 + 1]);
+            gelu_fast2p(add2(pk2(__uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3])), pk2(b.z, b.w)), gl[4 * j4 + 2], gl[4 * j4 + 3]);
+          }
+          *reinterpret_cast<uint4*>(dst + (c16 * 2) * 128) = pack8(gl);
+          *reinterpret_cast<uint4*>(dst + (c16 * 2 + 1) * 128) = pack8(gl + 8);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(&h_full[eg]);
+      // ---- epilogue 2: acc2 -> +b3 (+br) (+residual / skip) -> bf16 -> HBM
+      mbar_wait(&acc2_full[eg], par);
+      tc_fence_after();
+      {
+        const uint32_t trow = tmem_base + 2 * a.H + eg * a.Co + lane_off;
+#pragma unroll 1
+        for (int c16 = 0; c16 < a.Co / 16; ++c16) {
+          uint32_t v[16];
+          tmem_ld16(trow + c16 * 16, v);
+          uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0, 0, 0);
+          if (prefetch) {
+            // constant-index selection keeps rpre in registers
+#pragma unroll
+            for (int c = 0; c < 4; ++c) if (c == c16) { r0 = rpre[2 * c]; r1 = rpre[2 * c + 1]; }
+          } else if (a.res != nullptr && in_range) {
+            r0 = __ldg(a.res + orow + c16 * 2); r1 = __ldg(a.res + orow + c16 * 2 + 1);
+          }
+          tmem_ld_wait();
+          if (!in_range) continue;
+          const float4* b3p = reinterpret_cast<const float4*>(sB3 + c16 * 16);
+          const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+          uint32_t ow[8];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 b = b3p[j4];
+            uint64_t lo = pk2(bf16_lo(rw[2 * j4]), bf16_hi(rw[2 * j4])), hi = pk2(bf16_lo(rw[2 * j4 + 1]), bf16_hi(rw[2 * j4 + 1]));
+            if (valid) {
+              lo = add2(lo, add2(pk2(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1])), pk2(b.x, b.y)));
+              hi = add2(hi, add2(pk2(__uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3])), pk2(b.z, b.w)));
+            }
+            float e0, e1, e2, e3;
+            upk2(lo, e0, e1);
+            upk2(hi, e2, e3);
+            ow[2 * j4] = pack_bf16(e0, e1);
+            ow[2 * j4 + 1] = pack_bf16(e2, e3);
+          }
+          a.out[orow + c16 * 2] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+          a.out[orow + c16 * 2 + 1] = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc2_empty[eg]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MF_LOAD_WARPS + MF_EPI_WARPS) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+static size_t mlp_fused_smem(const MlpArgs& a, int N, int nst) {
+  const bool rc = a.wr != nullptr;
+  return (size_t)a.H * a.C * 2 + (size_t)a.Co * a.H * 2 + (rc ? (size_t)a.Co * a.Cr * 2 : 0) + (size_t)nst * 128 * a.C * 2 +
+         (rc ? (size_t)nst * 128 * a.Cr * 2 : 0) + (size_t)2 * 128 * a.H * 2 + (size_t)2 * N * a.C * 4 + (size_t)(a.H + a.Co) * 4 +
+         4 * 2 * 128 * 4 + 16 * 8 + 16 + 128;
 }
 
 // ============================================================================ head (OutBlock)
@@ -532,10 +1039,18 @@ static int dwconv_launch(const void* x, const float* w, const float* b, void* y,
   else { a.Do = (a.D - 1) * 2 - 2 * p + k; a.Ho = (a.H - 1) * 2 - 2 * p + k; a.Wo = (a.W - 1) * 2 - 2 * p + k; }
   PCB_CHECK_ARG(a.Do > 0 && a.Ho > 0 && a.Wo > 0, "%s: empty output", what);
   if (a.add_mode == 2) { a.a1 = (a.Ho + 1) >> 1; a.a2 = (a.Wo + 1) >> 1; }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mode == PCB_DW_SAME && C % 32 == 0 && a.add_mode != 2 && a.Do == a.D && a.Ho == a.H && a.Wo == a.W &&
+      (int64_t)((a.D + DT_Z - 1) / DT_Z) * ((a.H + DT_Y - 1) / DT_Y) * ((a.W + DT_X - 1) / DT_X) < (1ll << 31) && N <= 65535) {
+    bool ok = false;
+    if (k == 3) ok = launch_dw_tiled<3>(st, (const uint4*)x, w, b, (uint4*)y, stats, (const uint4*)add, a, N);
+    else if (k == 5) ok = launch_dw_tiled<5>(st, (const uint4*)x, w, b, (uint4*)y, stats, (const uint4*)add, a, N);
+    else ok = launch_dw_tiled<7>(st, (const uint4*)x, w, b, (uint4*)y, stats, (const uint4*)add, a, N);
+    if (ok) { PCB_CHECK_LAUNCH(what); return PCB_OK; }
+  }
   const int64_t items = (int64_t)a.Do * a.Ho * ((a.Wo + DW_XB - 1) / DW_XB) * (C / 8);
   dim3 grid((unsigned)((items + 255) / 256), (unsigned)N);
   const size_t smem = 2 * C * sizeof(double);
-  cudaStream_t st = (cudaStream_t)stream;
   if (k == 3) launch_dw<3>(mode, grid, smem, st, (const uint4*)x, w, b, (uint4*)y, stats, (const uint4*)add, a);
   else if (k == 5) launch_dw<5>(mode, grid, smem, st, (const uint4*)x, w, b, (uint4*)y, stats, (const uint4*)add, a);
   else launch_dw<7>(mode, grid, smem, st, (const uint4*)x, w, b, (uint4*)y, stats, (const uint4*)add, a);
@@ -603,11 +1118,37 @@ extern "C" int pcb_mlp_fwd(const void* y, const double* stats, const float* gamm
   PCB_CHECK_ARG(smem <= 227 * 1024, "pcb_mlp_fwd: tile needs %zu B shared memory", smem);
   static size_t configured = 0;
   if (smem > configured) {
+    cudaFuncSetAttribute(mlp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (cudaFuncSetAttribute(mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)) != cudaSuccess) {
       set_error("pcb_mlp_fwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
       return PCB_ERR_CUDA;
     }
     configured = 227 * 1024;
+  }
+  // top levels: persistent warp-specialised kernel (weights resident, single K / hidden chunk)
+  {
+    int nst = 4;
+    size_t fsm = mlp_fused_smem(a, (int)N, nst);
+    if (fsm > 227 * 1024) { nst = 2; fsm = mlp_fused_smem(a, (int)N, nst); }
+    const bool pow2 = ((C & (C - 1)) == 0) && ((H & (H - 1)) == 0 || true);
+    if (getenv("PCB_NO_FUSED") == nullptr && C <= 64 && H <= 256 && Co <= 128 && (!wr || Cr <= 64) && 2 * (H + Co) <= 512 &&
+        N <= 8 && fsm <= 227 * 1024 && pow2 && a.Vout < (1ll << 30) && a.Vin < (1ll << 30)) {
+      static bool fconf = false;
+      if (!fconf) {
+        cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+          set_error("pcb_mlp_fwd: cudaFuncSetAttribute(fused) failed"); return PCB_ERR_CUDA;
+        }
+        fconf = true;
+      }
+      MlpFusedArgs fa;
+      fa.m = a; fa.N = (int)N; fa.nst = nst; fa.tps = (a.Vout + 127) / 128; fa.ntiles = fa.tps * N;
+      int ctas = 148;
+      if (fa.ntiles < ctas) ctas = (int)fa.ntiles;
+      mlp_fused_kernel<<<ctas, MF_THREADS, fsm, (cudaStream_t)stream>>>(fa);
+      PCB_CHECK_LAUNCH("pcb_mlp_fwd(fused)");
+      return PCB_OK;
+    }
   }
   dim3 grid((unsigned)((a.Vout + 127) / 128), (unsigned)N, (unsigned)(Co / a.CoT));
   mlp_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(a);

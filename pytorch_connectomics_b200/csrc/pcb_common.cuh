@@ -57,6 +57,70 @@ __device__ __forceinline__ uint4 ldg_nc(const void* p) {
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
 }
+// ---- packed fp32x2 arithmetic (Blackwell FFMA2/FMUL2/FADD2: two fp32 lanes per instruction)
+__device__ __forceinline__ uint64_t pk2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float tanh_mufu(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// GELU(x) = x*Phi(x) with Phi(x) ~= 0.5*(1 + tanh(x*(c0 + c1 s + c2 s^2))), s = min(x^2, 64).
+// Minimax fit of the 3-term odd polynomial against the exact erf form on [-8, 8]:
+// |GELU err| < 3.0e-5, |GELU' err| < 9.5e-5 (tools/fit_gelu.py); the MUFU tanh.approx.f32 adds a
+// relative 2^-11 on tanh.  Both are far below the bf16 rounding (2^-9) applied to the result.
+#define PCB_GELU_C0 0.797482750f
+#define PCB_GELU_C1 0.0369853532f
+#define PCB_GELU_C2 (-3.46672670e-4f)
+__device__ __forceinline__ void gelu_fast2p(uint64_t x, float& y0, float& y1);
+__device__ __forceinline__ void gelu_fast2(float x0, float x1, float& y0, float& y1) {
+  gelu_fast2p(pk2(x0, x1), y0, y1);
+}
+__device__ __forceinline__ void gelu_fast2p(uint64_t x, float& y0, float& y1) {
+  float s0, s1;
+  upk2(mul2(x, x), s0, s1);
+  const uint64_t s = pk2(fminf(s0, 64.f), fminf(s1, 64.f));
+  uint64_t p = fma2(pk2(PCB_GELU_C2, PCB_GELU_C2), s, pk2(PCB_GELU_C1, PCB_GELU_C1));
+  p = fma2(p, s, pk2(PCB_GELU_C0, PCB_GELU_C0));
+  float u0, u1;
+  upk2(mul2(x, p), u0, u1);
+  const uint64_t t = pk2(tanh_mufu(u0), tanh_mufu(u1));
+  const uint64_t h = mul2(x, pk2(0.5f, 0.5f));
+  upk2(fma2(h, t, h), y0, y1);
+}
+// value and derivative (backward): GELU' = 0.5(1+t) + 0.5 x (1-t^2) (c0 + 3 c1 s + 5 c2 s^2)
+__device__ __forceinline__ void gelu_fast_vg(float x, float& val, float& grad) {
+  const float s = fminf(x * x, 64.f);
+  const float p = fmaf(fmaf(PCB_GELU_C2, s, PCB_GELU_C1), s, PCB_GELU_C0);
+  const float dp = fmaf(fmaf(5.f * PCB_GELU_C2, s, 3.f * PCB_GELU_C1), s, PCB_GELU_C0);
+  const float t = tanh_mufu(x * p);
+  const float h = 0.5f * x;
+  val = fmaf(h, t, h);
+  const float cdf = fmaf(0.5f, t, 0.5f);
+  grad = fmaf(h * fmaf(-t, t, 1.f), (x * x < 64.f) ? dp : 0.f, cdf);
+}
+
 // exact (erf) GELU and its derivative, fp32
 __device__ __forceinline__ float gelu_f(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
@@ -67,12 +131,35 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   return cdf + x * pdf;
 }
 
+// Staging copy with memory-level parallelism: issue up to B independent 128-bit global loads per
+// thread, THEN run the (convert +) shared-memory stores — a plain load->store loop serialises on
+// DRAM latency because the compiler cannot hoist loads across the aliasing shared stores.
+template <int B, typename LoadF, typename StoreF>
+__device__ __forceinline__ void staged_copy(int total, int tid, int nthreads, LoadF load, StoreF store) {
+  for (int q0 = tid; q0 < total; q0 += nthreads * B) {
+    uint4 v[B];
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+      const int q = q0 + b * nthreads;
+      if (q < total) v[b] = load(q);
+    }
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+      const int q = q0 + b * nthreads;
+      if (q < total) store(q, v[b]);
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
 __device__ __forceinline__ void fence_mbar_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
