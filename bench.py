@@ -97,7 +97,7 @@ def cpu_train_rate(steps: int, warmup: int, side: int = 64):
     un-vendored nnunet_mednext modules the reference builds) — fp32 forward + loss + backward + AdamW
     on a bounded sample (one `side`^3 crop per step), scaled to 160^3 sub-volumes by voxel count."""
     from oracle.mednext_oracle import create_mednext_v1
-    cores = os.cpu_count() or 1
+    cores = min(os.cpu_count() or 1, 32)   # oneDNN stops scaling (and regresses) beyond ~32 threads at this size
     torch.set_num_threads(cores)
     torch.manual_seed(0)
     net = create_mednext_v1(1, 1, "S", 3, False)
@@ -123,7 +123,7 @@ def cpu_train_rate(steps: int, warmup: int, side: int = 64):
 
 def cpu_infer_rate(steps: int, warmup: int, side: int = 64):
     from oracle.mednext_oracle import create_mednext_v1
-    cores = os.cpu_count() or 1
+    cores = min(os.cpu_count() or 1, 32)
     torch.set_num_threads(cores)
     torch.manual_seed(0)
     net = create_mednext_v1(1, 1, "S", 3, False).eval()

@@ -196,3 +196,26 @@ class HeadFn(torch.autograd.Function):
                                      ctypes.c_int64(nvox), L.stream_ptr(x.device)), "pcb_head_bwd")
         dwp = (dw.t() if ctx.conv_layout else dw).float().reshape(w.shape)
         return dx, dwp, db.float(), None, None
+
+
+class PointwiseFn(torch.autograd.Function):
+    """1x1 conv (channels-last bf16): forward pcb_pw_fwd; backward dX = dOut W, dW = dOut^T X (+db)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        out = ops.pointwise_forward(x, ops.packed(w, "pw"), ops.packed(b, "f32"))
+        ctx.save_for_backward(x, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w = ctx.saved_tensors
+        dout = _cl_grad(dout)
+        n, size, k = int(x.shape[0]), [int(s) for s in x.shape[1:4]], int(x.shape[4])
+        nw = int(w.shape[0])
+        dx = ops.pointwise_forward(dout, ops.packed(w, "pw_T"), None) if ctx.needs_input_grad[0] else None
+        dw = torch.empty((nw, k), device=x.device, dtype=torch.float32)
+        db = torch.empty((nw,), device=x.device, dtype=torch.float32)
+        _tn(dout, x, None, None, None, dw, k, 1, db, n, size, MAP_IDENT, size, nw, nw, MAP_IDENT, size, k,
+            L.stream_ptr(x.device))
+        return dx, dw.reshape(w.shape), db

@@ -201,6 +201,22 @@ def head_apply(x, w, b, out_dtype, conv_layout=False):
     return head_forward(x, w, b, out_dtype, conv_layout)
 
 
+def pointwise_forward(x: torch.Tensor, w_packed: torch.Tensor, b: Optional[torch.Tensor]) -> torch.Tensor:
+    """1x1 conv on channels-last bf16: out[..., :] = x[..., :] @ w_packed[N,K]^T + b   (tcgen05 GEMM)."""
+    n, size, k = int(x.shape[0]), [int(s) for s in x.shape[1:4]], int(x.shape[4])
+    nw = int(w_packed.shape[0])
+    if k % 16 or nw % 16:
+        raise ValueError(f"pcb200: 1x1 projection needs channel counts that are multiples of 16 (got {k}->{nw})")
+    out = torch.empty((n, *size, nw), device=x.device, dtype=_BF16)
+    L.check(L.lib().pcb_pw_fwd(L.ptr(x), L.ptr(w_packed), L.ptr(b), L.ptr(out), ctypes.c_int64(n), L.i64x(size), 0,
+                               L.i64x(size), ctypes.c_int64(k), ctypes.c_int64(nw), L.stream_ptr(x.device)), "pcb_pw_fwd")
+    return _mark(out)
+
+
 def pointwise_apply(x, w, b):
-    raise NotImplementedError("pcb200: task-head input_projection (hidden_channels != feature width) "
-                              "is not implemented in the B200 engine yet")
+    """MedNeXtTaskHead.input_projection (``mednext_models.py:169-173``): Conv3d(C, hidden, 1)."""
+    x = as_channels_last(x)
+    if _needs_grad(x, w, b):
+        from . import _mednext_bwd as B
+        return _mark(B.PointwiseFn.apply(x, w, b))
+    return pointwise_forward(x, packed(w, "pw"), packed(b, "f32"))

@@ -6,7 +6,14 @@ from .window import (EagerSlidingWindowEngine, apply_border_mask, build_sliding_
                      normalize_weighted_accumulator, resolve_border_mask, resolve_inferer_overlap,
                      resolve_inferer_roi_size, resolve_model_output_dtype)
 
-__all__ = ["EagerSlidingWindowEngine", "apply_border_mask", "build_sliding_accumulator_weight_maps",
+from .lazy import lazy_predict_region, lazy_predict_volume, lazy_sliding_window, lazy_window_records
+from .chunked import (ChunkRef, build_chunk_grid, chunks_for_rank, resolve_chunk_shape, resolve_external_chunk_shard,
+                      resolve_halo_region, run_chunked_prediction, stitch_chunks)
+
+__all__ = ["lazy_predict_region", "lazy_predict_volume", "lazy_sliding_window", "lazy_window_records", "ChunkRef",
+           "build_chunk_grid", "chunks_for_rank", "resolve_chunk_shape", "resolve_external_chunk_shard",
+           "resolve_halo_region", "run_chunked_prediction", "stitch_chunks",
+           "EagerSlidingWindowEngine", "apply_border_mask", "build_sliding_accumulator_weight_maps",
            "build_sliding_importance_map", "build_sliding_inferer", "compute_importance_map",
            "compute_scan_interval", "dense_patch_slices", "is_distance_transform_blending",
            "normalize_weighted_accumulator", "resolve_border_mask", "resolve_inferer_overlap",

@@ -2,6 +2,7 @@
 (host C code) is bit-exact with the reference-generated golden vectors; registry seam semantics
 (reference tests/unit/test_architecture_registry.py:55-200)."""
 import ctypes
+import os
 import warnings
 from types import SimpleNamespace as NS
 
@@ -149,3 +150,79 @@ def test_config_resolvers():
     with pytest.raises(ValueError):
         W.resolve_model_output_dtype(NS(inference=NS(model=NS(output_dtype="int8"))))
     assert W.is_distance_transform_blending("BANIS")
+
+
+def test_chunk_grid_and_halo_vs_reference_goldens(window_goldens):
+    from pytorch_connectomics_b200.inference import chunked as C
+    g = window_goldens
+    chunks = C.build_chunk_grid((100, 64, 70), (48, 64, 32))
+    assert np.array_equal(np.asarray([c.start for c in chunks]), g["chunk_starts"])
+    assert np.array_equal(np.asarray([c.stop for c in chunks]), g["chunk_stops"])
+    assert chunks[0].key == "z0_y0_x0" and chunks[-1].key == "z2_y0_x2"
+    halos = [C.resolve_halo_region(c, (100, 64, 70), halo=(8, 4, 6)) for c in chunks]
+    assert np.array_equal(np.asarray([h[0] for h in halos]), g["halo_read_start"])
+    assert np.array_equal(np.asarray([h[1] for h in halos]), g["halo_read_stop"])
+    assert np.array_equal(np.asarray([[s.start for s in h[2]] + [s.stop for s in h[2]] for h in halos]), g["halo_core"])
+    # round-robin rank assignment (chunked.py:471) partitions the grid
+    owned = [i for r in range(4) for i, _ in C.chunks_for_rank(chunks, r, 4)]
+    assert sorted(owned) == list(range(len(chunks)))
+    assert [i for i, _ in C.chunks_for_rank(chunks, 1, 4)] == [1, 5]
+    with pytest.raises(ValueError):
+        C.build_chunk_grid((10, 10), (4, 4, 4))
+    assert C.resolve_chunk_shape((32, 32, 32), (100, 20, 64), "z") == (32, 20, 64)
+    assert C.resolve_chunk_shape((32, 32, 32), (100, 20, 64)) == (32, 20, 32)
+    assert C.resolve_external_chunk_shard(None, None) is None and C.resolve_external_chunk_shard(1, 4) == (1, 4)
+    for bad in ((None, 2), (2, 2), (0, 0)):
+        with pytest.raises(ValueError):
+            C.resolve_external_chunk_shard(*bad)
+
+
+def test_lazy_records_match_oracle():
+    from pytorch_connectomics_b200.inference.lazy import lazy_window_records
+    for snap in (False, True):
+        got = lazy_window_records((12, 14, 13), (6, 6, 6), (0.5,) * 3, (3, 2, 4), (9, 11, 13), snap)
+        want = O.lazy_region_records((12, 14, 13), (6, 6, 6), (0.5,) * 3, (3, 2, 4), (9, 11, 13), snap)
+        assert [(r[0], r[1], tuple(h - l for l, h in zip(r[1], r[2])), r[3]) for r in want] == got
+
+
+def _ddp_worker(rank, world, port, q):
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pytorch_connectomics_b200.training import FlatGradArena
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(4, 8), torch.nn.ReLU(), torch.nn.Linear(8, 2), torch.nn.Linear(2, 2))
+    for p in net[3].parameters():          # an unused head: never receives a gradient (find_unused_parameters)
+        pass
+    arena = FlatGradArena(net.parameters())
+    x = torch.full((3, 4), float(rank + 1))
+    arena.zero()
+    net[2](net[1](net[0](x))).sum().backward()
+    arena.allreduce()
+    q.put((rank, arena.buffer.clone()))
+    dist.destroy_process_group()
+
+
+def test_flat_arena_allreduce_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    assert torch.equal(res[0], res[1])                      # identical averaged gradients on both ranks
+    # reference: mean of the two per-rank gradients computed in-process
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(4, 8), torch.nn.ReLU(), torch.nn.Linear(8, 2), torch.nn.Linear(2, 2))
+    gs = []
+    for r in range(2):
+        net.zero_grad()
+        net[2](net[1](net[0](torch.full((3, 4), float(r + 1))))).sum().backward()
+        gs.append(torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in net.parameters()]))
+    assert torch.allclose(res[0], (gs[0] + gs[1]) / 2, atol=1e-6)
+    assert res[0][-6:].abs().sum() == 0                     # the unused head stays zero (no hang, no None grads)

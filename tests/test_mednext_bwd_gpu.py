@@ -184,3 +184,42 @@ def test_tiny_network_training_step_matches_oracle():
     e, eb = (num / den) ** 0.5, (numb / den) ** 0.5
     print(f"all-parameter gradient rel-L2: engine {e:.3e}  reference-bf16-path {eb:.3e}")
     assert e <= 1.5 * eb + 5e-3
+
+
+def test_multihead_wrapper_forward_backward():
+    from types import SimpleNamespace as NS
+    from pytorch_connectomics_b200.architectures import build_model
+    cfg = NS(model=NS(arch=NS(type="mednext_custom"), in_channels=1, out_channels=2,
+                      mednext=NS(base_channels=16, exp_r=2, kernel_size=3, block_counts=[1] * 9),
+                      loss=NS(deep_supervision=False),
+                      heads={"aff": {"out_channels": 3, "num_blocks": 1}, "sdt": {"out_channels": 1}}))
+    torch.manual_seed(0)
+    m = build_model(cfg).to(DEV)
+    x = torch.rand(1, 1, 32, 32, 32, device=DEV)
+    out = m(x)
+    assert set(out["output"]) == {"aff", "sdt"}
+    assert out["output"]["aff"].shape == (1, 3, 32, 32, 32) and out["output"]["sdt"].shape == (1, 1, 32, 32, 32)
+    (out["output"]["aff"].float().mean() + out["output"]["sdt"].float().mean()).backward()
+    got = {k for k, p in m.named_parameters() if p.grad is not None}
+    assert "heads.aff.blocks.0.conv2.weight" in got and "heads.sdt.projection.weight" in got and "model.stem.weight" in got
+    assert "model.out_0.conv_out.weight" not in got      # trunk projection unused by the multi-head wrapper
+    with torch.no_grad():
+        f = m.forward_features(x)
+        heads = m.forward_heads(f)
+    assert torch.allclose(heads["aff"], out["output"]["aff"].detach(), rtol=1e-4, atol=1e-5)
+
+
+def test_pointwise_projection_matches_conv():
+    torch.manual_seed(1)
+    conv = torch.nn.Conv3d(32, 16, 1)
+    x = torch.randn(1, 32, 6, 7, 8).bfloat16().float()
+    gout = torch.randn(1, 16, 6, 7, 8).bfloat16().float()
+    xr = x.clone().requires_grad_(True)
+    (conv(xr) * gout).sum().backward()
+    w, b = conv.weight.detach().to(DEV).requires_grad_(True), conv.bias.detach().to(DEV).requires_grad_(True)
+    xc = cl(x).requires_grad_(True)
+    out = ops.pointwise_apply(xc, w, b)
+    with torch.no_grad():
+        assert rel(ncdhw(out), conv(x)) < 5e-3
+    out.backward(cl(gout))
+    assert rel(ncdhw(xc.grad), xr.grad) < 6e-3 and rel(w.grad, conv.weight.grad) < 5e-3 and rel(b.grad, conv.bias.grad) < 1e-4
