@@ -181,6 +181,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--volume", type=int, default=480)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-ops", action="store_true", help="time every pcb200 op with CUDA events (stderr table)")
     a = ap.parse_args()
     a.warmup = max(3, a.warmup) if a.impl == "pcb200" else a.warmup
     if a.impl == "reference":
@@ -240,7 +241,7 @@ def main():
             step(*pool[i % 4])
         barrier()
         dom = f"mlp_fwd:m0C32H64Co32V{SIDE ** 3}"
-        L.prof_start([dom, f"mlp_bwd:m0C32H64Co32V{SIDE ** 3}", f"dwconv_fwd:m0C32V{SIDE ** 3}"])
+        L.prof_start([] if a.profile_ops else [dom, f"mlp_bwd:m0C32H64Co32V{SIDE ** 3}", f"dwconv_fwd:m0C32V{SIDE ** 3}"])
         l0 = L.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         w0 = time.time()
@@ -331,6 +332,12 @@ def main():
             dist.destroy_process_group()
         return
 
+    if a.profile_ops:
+        tot = sum(sum(v) for v in prof.values())
+        for k, v in sorted(prof.items(), key=lambda kv: -sum(kv[1])):
+            print(f"{k:40s} n={len(v) // a.steps:3d}/step  {sum(v) / a.steps:8.3f} ms/step  avg {sum(v) / len(v):7.3f} ms",
+                  file=sys.stderr)
+        print(f"{'sum of timed ops':40s} {tot / a.steps:8.3f} ms/step of {ms / a.steps:.3f}", file=sys.stderr)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

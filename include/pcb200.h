@@ -118,6 +118,15 @@ int pcb_mlp_bwd(const void* y, const double* stats, const float* gamma, const fl
                 const float* b2, const void* w3t, const void* w2t, const void* dout, void* hact, void* dh,
                 void* dyhat, double* gstats, int64_t N, const int64_t y_size[3], int64_t C, int64_t H,
                 int64_t Co, int mode, void* stream);
+/* levels 0/1 (3H+C+Co <= 512): persistent kernel doing pcb_mlp_bwd AND both pointwise weight gradients with
+ * Hact/dh kept on chip (TMEM-resident wgrad accumulators, bias grads via an all-ones MN-major row).
+ * dW3 [Co,H], db3 [Co], dW2 [H,C], db2 [H] fp32 are overwritten; workspace from ..._workspace_floats. */
+int pcb_mlp_bwd_fused_supported(int64_t C, int64_t H, int64_t Co, int64_t N, const int64_t y_size[3], int mode);
+int64_t pcb_mlp_bwd_fused_workspace_floats(int64_t C, int64_t H, int64_t Co, int64_t N, const int64_t y_size[3]);
+int pcb_mlp_bwd_fused(const void* y, const double* stats, const float* gamma, const float* beta, const void* w2,
+                      const float* b2, const void* w3t, const void* w2t, const void* dout, void* dyhat,
+                      double* gstats, float* workspace, float* dW3, float* db3, float* dW2, float* db2, int64_t N,
+                      const int64_t y_size[3], int64_t C, int64_t H, int64_t Co, int mode, void* stream);
 /* weight gradients: dW[m*ldm + n*ldn] = sum_{sample, v in box} A[mapA(v), m] * B[mapB(v), n]
  * (m < Ma, n < Nb), db[m] = sum A[mapA(v), m] when `ones`; split-K persistent tcgen05 GEMM with
  * MN-major operands + deterministic second-stage reduction over `workspace`

@@ -62,6 +62,7 @@ def lib() -> ctypes.CDLL:
         _lib.pcb_version.restype = ctypes.c_int
         _lib.pcb_launch_count.restype = ctypes.c_int64
         _lib.pcb_tn_workspace_floats.restype = ctypes.c_int64
+        _lib.pcb_mlp_bwd_fused_workspace_floats.restype = ctypes.c_int64
     return _lib
 
 

@@ -45,10 +45,11 @@ def _tn(A, B, stats, gamma, beta, dW, ldm, ldn, db, n, box, map_a, a_size, a_col
     ones = 1 if db is not None else 0
     nfl = int(lib.pcb_tn_workspace_floats(ctypes.c_int64(ma), ctypes.c_int64(nb), ones, ctypes.c_int64(n), L.i64x(box)))
     ws = torch.empty(nfl, device=A.device, dtype=torch.float32)
-    L.check(lib.pcb_tn_gemm(L.ptr(A), L.ptr(B), L.ptr(stats), L.ptr(gamma), L.ptr(beta), L.ptr(ws), L.ptr(dW),
+    with L.prof(f"tn_gemm:M{ma}N{nb}V{box[0] * box[1] * box[2]}"):
+      L.check(lib.pcb_tn_gemm(L.ptr(A), L.ptr(B), L.ptr(stats), L.ptr(gamma), L.ptr(beta), L.ptr(ws), L.ptr(dW),
                             ctypes.c_int64(ldm), ctypes.c_int64(ldn), L.ptr(db), ctypes.c_int64(n), L.i64x(box),
-                            map_a, L.i64x(a_size), ctypes.c_int64(a_cols), ctypes.c_int64(ma), map_b, L.i64x(b_size),
-                            ctypes.c_int64(nb), ones, st), "pcb_tn_gemm")
+                              map_a, L.i64x(a_size), ctypes.c_int64(a_cols), ctypes.c_int64(ma), map_b, L.i64x(b_size),
+                              ctypes.c_int64(nb), ones, st), "pcb_tn_gemm")
 
 
 class BlockFn(torch.autograd.Function):
@@ -75,30 +76,42 @@ class BlockFn(torch.autograd.Function):
         vy = ysize[0] * ysize[1] * ysize[2]
         g_f32, b_f32 = ops.packed(gamma, "f32"), ops.packed(beta, "f32")
 
-        hact = torch.empty((n, vy, h), device=dev, dtype=_BF16)
-        dh = torch.empty((n, vy, h), device=dev, dtype=_BF16)
         dyhat = torch.empty((n, *ysize, c), device=dev, dtype=_BF16)
         gstats = torch.zeros((n, 2, c), device=dev, dtype=torch.float64)
-        with L.prof(f"mlp_bwd:m{mode}C{c}H{h}Co{co}V{vy}"):
-          L.check(lib.pcb_mlp_bwd(L.ptr(y), L.ptr(stats), L.ptr(g_f32), L.ptr(b_f32), L.ptr(ops.packed(w2, "pw")),
-                                  L.ptr(ops.packed(b2, "f32")), L.ptr(ops.packed(w3, "pw_T")), L.ptr(ops.packed(w2, "pw_T")),
-                                  L.ptr(dout), L.ptr(hact), L.ptr(dh), L.ptr(dyhat), L.ptr(gstats), ctypes.c_int64(n),
-                                  L.i64x(ysize), ctypes.c_int64(c), ctypes.c_int64(h), ctypes.c_int64(co), mode, st),
-                  "pcb_mlp_bwd")
-        # ---- pointwise weight gradients (+ bias gradients through the all-ones column)
         dw3 = torch.empty((co, h), device=dev, dtype=torch.float32)
         db3 = torch.empty((co,), device=dev, dtype=torch.float32)
-        _tn(dout, hact, None, None, None, dw3, h, 1, db3, n, ysize, MAP_PLUS1 if mode == L.DW_UP else MAP_IDENT,
-            osize, co, co, MAP_IDENT, ysize, h, st)
         dw2 = torch.empty((h, c), device=dev, dtype=torch.float32)
         db2 = torch.empty((h,), device=dev, dtype=torch.float32)
-        _tn(dh, y, stats, g_f32, b_f32, dw2, c, 1, db2, n, ysize, MAP_IDENT, ysize, h, h, MAP_IDENT, ysize, c, st)
-        del hact, dh
+        common = (L.ptr(y), L.ptr(stats), L.ptr(g_f32), L.ptr(b_f32), L.ptr(ops.packed(w2, "pw")),
+                  L.ptr(ops.packed(b2, "f32")), L.ptr(ops.packed(w3, "pw_T")), L.ptr(ops.packed(w2, "pw_T")), L.ptr(dout))
+        if lib.pcb_mlp_bwd_fused_supported(ctypes.c_int64(c), ctypes.c_int64(h), ctypes.c_int64(co), ctypes.c_int64(n),
+                                           L.i64x(ysize), mode) == 1:
+            # levels 0/1: data gradient + both pointwise weight gradients in one persistent kernel
+            nfl = int(lib.pcb_mlp_bwd_fused_workspace_floats(ctypes.c_int64(c), ctypes.c_int64(h), ctypes.c_int64(co),
+                                                             ctypes.c_int64(n), L.i64x(ysize)))
+            ws = torch.empty(nfl, device=dev, dtype=torch.float32)
+            with L.prof(f"mlp_bwd_fused:m{mode}C{c}H{h}Co{co}V{vy}"):
+                L.check(lib.pcb_mlp_bwd_fused(*common, L.ptr(dyhat), L.ptr(gstats), L.ptr(ws), L.ptr(dw3), L.ptr(db3),
+                                              L.ptr(dw2), L.ptr(db2), ctypes.c_int64(n), L.i64x(ysize), ctypes.c_int64(c),
+                                              ctypes.c_int64(h), ctypes.c_int64(co), mode, st), "pcb_mlp_bwd_fused")
+        else:
+            hact = torch.empty((n, vy, h), device=dev, dtype=_BF16)
+            dh = torch.empty((n, vy, h), device=dev, dtype=_BF16)
+            with L.prof(f"mlp_bwd:m{mode}C{c}H{h}Co{co}V{vy}"):
+                L.check(lib.pcb_mlp_bwd(*common, L.ptr(hact), L.ptr(dh), L.ptr(dyhat), L.ptr(gstats), ctypes.c_int64(n),
+                                        L.i64x(ysize), ctypes.c_int64(c), ctypes.c_int64(h), ctypes.c_int64(co), mode, st),
+                        "pcb_mlp_bwd")
+            # pointwise weight gradients (+ bias gradients through the all-ones column)
+            _tn(dout, hact, None, None, None, dw3, h, 1, db3, n, ysize, MAP_PLUS1 if mode == L.DW_UP else MAP_IDENT,
+                osize, co, co, MAP_IDENT, ysize, h, st)
+            _tn(dh, y, stats, g_f32, b_f32, dw2, c, 1, db2, n, ysize, MAP_IDENT, ysize, h, h, MAP_IDENT, ysize, c, st)
+            del hact, dh
         # ---- GroupNorm backward
         dy = torch.empty_like(y)
         db1 = torch.zeros((c,), device=dev, dtype=torch.float64)
-        L.check(lib.pcb_gn_bwd(L.ptr(dyhat), L.ptr(y), L.ptr(stats), L.ptr(gstats), L.ptr(g_f32), L.ptr(dy), L.ptr(db1),
-                               ctypes.c_int64(n), ctypes.c_int64(c), ctypes.c_int64(vy), st), "pcb_gn_bwd")
+        with L.prof(f"gn_bwd:C{c}V{vy}"):
+          L.check(lib.pcb_gn_bwd(L.ptr(dyhat), L.ptr(y), L.ptr(stats), L.ptr(gstats), L.ptr(g_f32), L.ptr(dy), L.ptr(db1),
+                                 ctypes.c_int64(n), ctypes.c_int64(c), ctypes.c_int64(vy), st), "pcb_gn_bwd")
         dgamma = gstats[:, 1].sum(0).float()
         dbeta = gstats[:, 0].sum(0).float()
         del dyhat
@@ -108,8 +121,9 @@ class BlockFn(torch.autograd.Function):
             cen, nei, csz, nsz, stride = x, dy, xsize, ysize, 2
         else:
             cen, nei, csz, nsz, stride = dy, x, ysize, xsize, (2 if mode == L.DW_DOWN else 1)
-        L.check(lib.pcb_dwconv_wgrad(L.ptr(cen), L.ptr(nei), L.ptr(dw1), ctypes.c_int64(n), L.i64x(csz), L.i64x(nsz),
-                                     ctypes.c_int64(c), k, stride, st), "pcb_dwconv_wgrad")
+        with L.prof(f"dw_wgrad:m{mode}C{c}V{vy}"):
+          L.check(lib.pcb_dwconv_wgrad(L.ptr(cen), L.ptr(nei), L.ptr(dw1), ctypes.c_int64(n), L.i64x(csz), L.i64x(nsz),
+                                       ctypes.c_int64(c), k, stride, st), "pcb_dwconv_wgrad")
         grads_rc: List[Optional[torch.Tensor]] = []
         add, add_mode = None, 0
         if has_rc:
@@ -138,9 +152,10 @@ class BlockFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             wk = ops.packed(w1, "dw_flip" if mode == L.DW_SAME else "dw")
-            L.check(lib.pcb_dwconv_bwd_data(L.ptr(dy), L.ptr(wk), L.ptr(add), add_mode, L.ptr(dx), ctypes.c_int64(n),
-                                            L.i64x(ysize), L.i64x(xsize), ctypes.c_int64(c), k, mode, st),
-                    "pcb_dwconv_bwd_data")
+            with L.prof(f"dw_bwd_data:m{mode}C{c}V{vy}"):
+              L.check(lib.pcb_dwconv_bwd_data(L.ptr(dy), L.ptr(wk), L.ptr(add), add_mode, L.ptr(dx), ctypes.c_int64(n),
+                                              L.i64x(ysize), L.i64x(xsize), ctypes.c_int64(c), k, mode, st),
+                      "pcb_dwconv_bwd_data")
         dskip = dout if (has_skip and ctx.needs_input_grad[1]) else None
         grads = [dw1.t().reshape(w1.shape).float(), db1.float(), dgamma, dbeta,
                  dw2.reshape(w2.shape), db2, dw3.reshape(w3.shape), db3] + grads_rc

@@ -15,6 +15,8 @@
 //   dw_wgrad_kernel  depthwise weight gradient  dW[c,tap] = sum_v center[v,c] * neigh[S v - P + tap, c]
 //   head_bwd / stem_bwd kernels (CUDA cores; tiny channel counts on one side)
 #include "../../include/pcb200.h"
+#include <stdlib.h>
+
 #include "pcb_common.cuh"
 
 namespace pcb {
@@ -61,9 +63,9 @@ __device__ __forceinline__ int colsum16_col(int lane) {
 }
 
 __device__ __forceinline__ void stage_rows_k(uint8_t* dst, const uint4* __restrict__ src, int rows, int kc8,
-                                             int64_t pitch8, int tid) {
+                                             int64_t pitch8, int tid, int nthreads = 128) {
   const uint32_t sbo = kc8 * 128;
-  staged_copy<8>(rows * kc8, tid, 128,
+  staged_copy<8>(rows * kc8, tid, nthreads,
       [&](int q) { const int r = q >> __ffs(kc8) - 1, c8 = q & (kc8 - 1); return __ldg(src + (int64_t)r * pitch8 + c8); },
       [&](int q, const uint4& v) {
         const int r = q >> __ffs(kc8) - 1, c8 = q & (kc8 - 1);
@@ -289,6 +291,322 @@ __global__ void __launch_bounds__(128) mlp_bwd_kernel(MlpBwdArgs a) {
     atomicAdd(&a.gstats[(int64_t)n * 2 * a.C + a.C + ct * a.Ct + i], sG[a.Ct + i]);
   }
   if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ============================================================================ persistent fused MLP backward
+// Levels 0/1 (3H + C + Co <= 512 TMEM columns): one kernel per block does the data gradient AND both
+// pointwise weight gradients.  Per 128-voxel tile:
+//   G1 Hpre = Yhat W2^T      G2 dG = dOut W3          (K-major operands, fp32 in TMEM)
+//   E1 Hact = GELU(Hpre+b2), dh = dG*GELU'            (bf16 tiles in shared memory only)
+//   G3 dYhat = dh W2         -> E2: bf16 to HBM + GroupNorm-backward sums
+//   G4 dW3^T[h,co] += Hact^T dOut     G5 dW2^T[c,h] += Yhat^T dh
+// G4/G5 read the SAME shared tiles through MN-major descriptors (LBO/SBO swapped), reduce over the 128
+// voxels of the tile, and keep accumulating into TMEM across all tiles of the persistent CTA.  The A tiles
+// of G5 carries one extra 8x16 B core matrix per row group holding [1,0,..,0]: in the MN-major view that is
+// an all-ones M-row, so row C of dW2^T is db2 = sum dh — that bias
+// gradient comes out of the tensor cores for free; db3 = sum dOut is a column sum of the staged dOut tile.
+// Hact / dh never touch HBM, no split-K GEMM launches.
+struct MlpBwdFusedArgs {
+  MlpBwdArgs m;
+  float* part3;      // [P][129][Co]  partial dW3^T rows 0..H-1, row 128 = partial db3
+  float* part2;      // [P][128][H]   partial dW2^T (+ row C = db2)
+  int N;
+  int64_t tps, ntiles;
+};
+
+constexpr int BF_PF = 8;          // prefetch depth: (C/8 + Co/8) * 128 / 256 <= 8 chunks per thread
+constexpr int BF_THREADS = 256;   // two warpgroups: same TMEM lane quarters, each takes half of the columns
+
+__global__ void __launch_bounds__(BF_THREADS, 2) mlp_bwd_fused_kernel(MlpBwdFusedArgs fa) {
+  const MlpBwdArgs& a = fa.m;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = tid & 127, half = tid >> 7, wq = warp & 3;   // tile row, column half, TMEM lane quarter
+  const int c8n = a.C >> 3, h8n = a.H >> 3, o8n = a.Co >> 3;
+  const uint32_t pitchA = (c8n + 1) * 128, pitchH = h8n * 128, pitchD = o8n * 128, pitchDh = h8n * 128;
+  uint8_t* sW2 = smem;                                 // [H x C]   K-major (B of G1)
+  uint8_t* sW3t = sW2 + a.H * a.C * 2;                 // [H x Co]  K-major (B of G2)
+  uint8_t* sW2t = sW3t + a.H * a.Co * 2;               // [C x H]   K-major (B of G3)
+  uint8_t* sA = sW2t + a.C * a.H * 2;                  // [128 x C]  + ones core matrix per row group
+  uint8_t* sD = sA + 16 * pitchA;                      // [128 x Co]
+  uint8_t* sH = sD + 16 * pitchD;                      // [128 x H]
+  uint8_t* sDh = sH + 16 * pitchH;                     // [128 x H]
+  uint8_t* sY = sDh + 16 * pitchDh;                    // [128][C*2+16] raw y rows (x-hat in E2)
+  uint8_t* sTail = sY + 128 * (a.C * 2 + 16);          // 2 KB of finite padding read by the M>valid rows
+  float* sScale = reinterpret_cast<float*>(sTail + 2048);   // [N][C] gamma*rstd
+  float* sShift = sScale + fa.N * a.C;                 // [N][C]
+  float* sRstd = sShift + fa.N * a.C;                  // [N][C]
+  float* sMR = sRstd + fa.N * a.C;                     // [N][C] mean*rstd
+  float* sB2 = sMR + fa.N * a.C;                       // [H]
+  double* sG = reinterpret_cast<double*>(sB2 + a.H);   // [2*C] S1,S2 partials of the current sample
+  int* sRowO = reinterpret_cast<int*>(sG + 2 * a.C);   // [128]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sRowO + 128);   // [0] G1+G2 / G3 done, [1] G4+G5 done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
+
+  const uint32_t ncols = 3 * a.H + a.C + a.Co;
+  const uint32_t tmem_cols = tmem_cols_pow2(ncols);
+  if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
+  if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_mbar_init(); }
+  // resident weights (K-major), biases, per-sample GroupNorm constants, ones core matrices, finite tail
+  stage_rows_k(sW2, a.w2, a.H, c8n, c8n, tid, BF_THREADS);
+  stage_rows_k(sW3t, a.w3t, a.H, o8n, o8n, tid, BF_THREADS);
+  stage_rows_k(sW2t, a.w2t, a.C, h8n, h8n, tid, BF_THREADS);
+  for (int i = tid; i < a.H; i += BF_THREADS) sB2[i] = a.b2[i];
+  for (int i = tid; i < fa.N * a.C; i += BF_THREADS) {
+    const int n = i / a.C, c = i - n * a.C;
+    const double sm = a.stats[(int64_t)n * 2 * a.C + c], q = a.stats[(int64_t)n * 2 * a.C + a.C + c];
+    const double mean = sm * (double)a.inv_count;
+    double var = q * (double)a.inv_count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + 1e-5));
+    const float g = a.gamma[c] * rstd;
+    sScale[i] = g; sShift[i] = a.beta[c] - (float)mean * g; sRstd[i] = rstd; sMR[i] = (float)mean * rstd;
+  }
+  {
+    const uint4 one = make_uint4(0x3F80u, 0, 0, 0);   // bf16 [1,0,0,0,0,0,0,0]
+    // 16 row groups x 8 voxels: ones core matrix of sA (chunk index c8n)
+    if (tid < 128) {
+      *reinterpret_cast<uint4*>(sA + (tid >> 3) * pitchA + c8n * 128 + (tid & 7) * 16) = one;
+      *reinterpret_cast<uint4*>(sTail + tid * 16) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  for (int i = tid; i < 2 * a.C; i += BF_THREADS) sG[i] = 0.0;
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t acc1 = tmem_base, accG = tmem_base + a.H, accD = tmem_base + 2 * a.H;
+  const uint32_t accW3 = accD + a.C, accW2 = accW3 + a.Co;
+  const uint32_t idescH = umma_idesc_bf16(128, a.H, 0, 0), idescD = umma_idesc_bf16(128, a.C, 0, 0);
+  const uint32_t idescW3 = umma_idesc_bf16(128, a.Co, 1, 1), idescW2 = umma_idesc_bf16(128, a.H, 1, 1);
+  uint32_t ph0 = 0, ph1 = 0;
+  int cur_n = -1;
+  int64_t it = 0;
+  float db3acc = 0.f;   // thread t < Co: running sum_v dOut[v, t]
+  const int csh = __ffs(c8n) - 1, osh = __ffs(o8n) - 1;
+  const int nchunk_y = 128 * c8n, nchunk_o = 128 * o8n;
+  const int ypitch = a.C * 2 + 16;
+  uint4 pre[BF_PF];     // next tile's y / dOut chunks, in flight while the current tile is processed
+  auto prefetch = [&](int64_t gt) {
+    const int pn = (int)(gt / fa.tps);
+    const int pt0 = (int)((gt - (int64_t)pn * fa.tps) * 128);
+    const uint4* pyn = a.y + (int64_t)pn * a.Vy * c8n;
+    const uint4* pdn = a.dout + (int64_t)pn * a.Vout * o8n;
+#pragma unroll
+    for (int b = 0; b < BF_PF; ++b) {
+      const int q = tid + b * BF_THREADS;
+      pre[b] = make_uint4(0, 0, 0, 0);
+      if (q < nchunk_y) {
+        const int r = q >> csh, c8 = q & (c8n - 1);
+        if (pt0 + r < (int)a.Vy) pre[b] = __ldg(pyn + (int64_t)(pt0 + r) * c8n + c8);
+      } else if (q < nchunk_y + nchunk_o) {
+        const int qo = q - nchunk_y, r = qo >> osh, c8 = qo & (o8n - 1);
+        if (pt0 + r < (int)a.Vy) {
+          const int64_t ro = map_row(a.mode == PCB_DW_UP ? MAP_PLUS1 : MAP_IDENT, pt0 + r, a.y1, a.y2, a.o1, a.o2);
+          pre[b] = __ldg(pdn + ro * o8n + c8);
+        }
+      }
+    }
+  };
+  if ((int64_t)blockIdx.x < fa.ntiles) prefetch(blockIdx.x);
+  for (int64_t g = blockIdx.x; g < fa.ntiles; g += gridDim.x, ++it) {
+    const int n = (int)(g / fa.tps);
+    const int tile0 = (int)((g - (int64_t)n * fa.tps) * 128);
+    if (n != cur_n) {   // flush the GroupNorm-backward partial sums of the previous sample
+      if (cur_n >= 0) {
+        __syncthreads();
+        for (int i = tid; i < a.C; i += BF_THREADS) {
+          atomicAdd(&a.gstats[(int64_t)cur_n * 2 * a.C + i], sG[i]);
+          atomicAdd(&a.gstats[(int64_t)cur_n * 2 * a.C + a.C + i], sG[a.C + i]);
+          sG[i] = 0.0; sG[a.C + i] = 0.0;
+        }
+        __syncthreads();
+      }
+      cur_n = n;
+    }
+    const float* sc = sScale + n * a.C; const float* sh = sShift + n * a.C;
+    if (it >= 1) { mbar_wait(&bar[1], ph1); ph1 ^= 1; }   // G4/G5 of the previous tile have consumed the tiles
+    __syncthreads();                                      // every thread is done with E2's reads of sY
+    // the tile's global loads were issued one iteration ago (software prefetch): convert + stage them now
+#pragma unroll
+    for (int b = 0; b < BF_PF; ++b) {
+      const int q = tid + b * BF_THREADS;
+      if (q < nchunk_y) {
+        const int r = q >> csh, c8 = q & (c8n - 1);
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (tile0 + r < (int)a.Vy) {
+          float f[8];
+          unpack8(pre[b], f);
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) f[jj] = fmaf(f[jj], sc[c8 * 8 + jj], sh[c8 * 8 + jj]);
+          v = pack8(f);
+        }
+        *reinterpret_cast<uint4*>(sA + (r >> 3) * pitchA + c8 * 128 + (r & 7) * 16) = v;
+        *reinterpret_cast<uint4*>(sY + r * ypitch + c8 * 16) = pre[b];
+      } else if (q < nchunk_y + nchunk_o) {
+        const int qo = q - nchunk_y, r = qo >> osh, c8 = qo & (o8n - 1);
+        *reinterpret_cast<uint4*>(sD + (r >> 3) * pitchD + c8 * 128 + (r & 7) * 16) = pre[b];
+      }
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint64_t dA = umma_desc(smem_u32(sA), 128, pitchA), dW2 = umma_desc(smem_u32(sW2), 128, c8n * 128);
+      for (int k = 0; k < a.C / 16; ++k) umma_bf16(acc1, dA + (uint64_t)(k * 16), dW2 + (uint64_t)(k * 16), idescH, k > 0 ? 1u : 0u);
+      const uint64_t dD = umma_desc(smem_u32(sD), 128, pitchD), dW3 = umma_desc(smem_u32(sW3t), 128, o8n * 128);
+      for (int k = 0; k < a.Co / 16; ++k) umma_bf16(accG, dD + (uint64_t)(k * 16), dW3 + (uint64_t)(k * 16), idescH, k > 0 ? 1u : 0u);
+      tc_commit(&bar[0]);
+    }
+    if (tid < a.Co) {   // conv3 bias gradient: column sums of the staged dOut tile (overlaps the MMAs)
+      const uint8_t* col = sD + (tid >> 3) * 128 + (tid & 7) * 2;
+      float sacc = 0.f;
+#pragma unroll 8
+      for (int r = 0; r < 128; ++r)
+        sacc += __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(col + (r >> 3) * pitchD + (r & 7) * 16)) << 16);
+      db3acc += sacc;
+    }
+    mbar_wait(&bar[0], ph0); ph0 ^= 1;
+    tc_fence_after();
+    // ---- E1: Hact -> sH, dh -> sDh   (warpgroup `half` handles its half of the hidden columns)
+    {
+      const uint32_t t1 = acc1 + ((uint32_t)(wq * 32) << 16), tg = accG + ((uint32_t)(wq * 32) << 16);
+      uint8_t* dH = sH + (row >> 3) * pitchH + (row & 7) * 16;
+      uint8_t* dDh = sDh + (row >> 3) * pitchDh + (row & 7) * 16;
+      const int nch = a.H / 16, c_lo = half * ((nch + 1) >> 1), c_hi = half ? nch : ((nch + 1) >> 1);
+      for (int c16 = c_lo; c16 < c_hi; ++c16) {
+        uint32_t v1[16], vg[16];
+        tmem_ld16(t1 + c16 * 16, v1);
+        tmem_ld16(tg + c16 * 16, vg);
+        tmem_ld_wait();
+        uint32_t hw[8], dw[8];
+        const float4* bp = reinterpret_cast<const float4*>(sB2 + c16 * 16);
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 b = bp[j4];
+          uint64_t va, ga, vb, gb;
+          gelu_fast_vg2(add2(pk2(__uint_as_float(v1[4 * j4]), __uint_as_float(v1[4 * j4 + 1])), pk2(b.x, b.y)), va, ga);
+          gelu_fast_vg2(add2(pk2(__uint_as_float(v1[4 * j4 + 2]), __uint_as_float(v1[4 * j4 + 3])), pk2(b.z, b.w)), vb, gb);
+          ga = mul2(ga, pk2(__uint_as_float(vg[4 * j4]), __uint_as_float(vg[4 * j4 + 1])));
+          gb = mul2(gb, pk2(__uint_as_float(vg[4 * j4 + 2]), __uint_as_float(vg[4 * j4 + 3])));
+          float e0, e1;
+          upk2(va, e0, e1); hw[2 * j4] = pack_bf16(e0, e1);
+          upk2(vb, e0, e1); hw[2 * j4 + 1] = pack_bf16(e0, e1);
+          upk2(ga, e0, e1); dw[2 * j4] = pack_bf16(e0, e1);
+          upk2(gb, e0, e1); dw[2 * j4 + 1] = pack_bf16(e0, e1);
+        }
+        *reinterpret_cast<uint4*>(dH + (c16 * 2) * 128) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        *reinterpret_cast<uint4*>(dH + (c16 * 2 + 1) * 128) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+        *reinterpret_cast<uint4*>(dDh + (c16 * 2) * 128) = make_uint4(dw[0], dw[1], dw[2], dw[3]);
+        *reinterpret_cast<uint4*>(dDh + (c16 * 2 + 1) * 128) = make_uint4(dw[4], dw[5], dw[6], dw[7]);
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      // G3: dYhat = dh W2
+      const uint64_t dDhK = umma_desc(smem_u32(sDh), 128, pitchDh), dW2t = umma_desc(smem_u32(sW2t), 128, h8n * 128);
+      for (int k = 0; k < a.H / 16; ++k) umma_bf16(accD, dDhK + (uint64_t)(k * 16), dW2t + (uint64_t)(k * 16), idescD, k > 0 ? 1u : 0u);
+      tc_commit(&bar[0]);
+      // G4: dW3^T[h (+ones row), co] += Hact^T dOut ; G5: dW2^T[c (+ones row), h] += Yhat^T dh   (K = 128 voxels)
+      const uint64_t aH = umma_desc(smem_u32(sH), pitchH, 128), bD = umma_desc(smem_u32(sD), pitchD, 128);
+      const uint64_t aA = umma_desc(smem_u32(sA), pitchA, 128), bDh = umma_desc(smem_u32(sDh), pitchDh, 128);
+      for (int k = 0; k < 8; ++k)
+        umma_bf16(accW3, aH + (uint64_t)(k * 2 * (pitchH >> 4)), bD + (uint64_t)(k * 2 * (pitchD >> 4)), idescW3, (it > 0 || k > 0) ? 1u : 0u);
+      for (int k = 0; k < 8; ++k)
+        umma_bf16(accW2, aA + (uint64_t)(k * 2 * (pitchA >> 4)), bDh + (uint64_t)(k * 2 * (pitchDh >> 4)), idescW2, (it > 0 || k > 0) ? 1u : 0u);
+      tc_commit(&bar[1]);
+    }
+    if (g + gridDim.x < fa.ntiles) prefetch(g + gridDim.x);   // next tile's loads fly during E2
+    mbar_wait(&bar[0], ph0); ph0 ^= 1;
+    tc_fence_after();
+    // ---- E2: g = dYhat -> bf16 ; S1 += g ; S2 += g*xhat
+    {
+      const int prow = tile0 + row;
+      const bool row_ok = prow < (int)a.Vy;
+      const uint32_t td = accD + ((uint32_t)(wq * 32) << 16);
+      const int ncd = a.C / 16, d_lo = half * ((ncd + 1) >> 1), d_hi = half ? ncd : ((ncd + 1) >> 1);
+      const int64_t yrow = ((int64_t)n * a.Vy + prow) * c8n;
+      const float* rs = sRstd + n * a.C; const float* mr = sMR + n * a.C;
+      for (int c16 = d_lo; c16 < d_hi; ++c16) {
+        uint32_t v[16];
+        tmem_ld16(td + c16 * 16, v);
+        const uint4 y0 = *reinterpret_cast<const uint4*>(sY + row * ypitch + c16 * 32);
+        const uint4 y1 = *reinterpret_cast<const uint4*>(sY + row * ypitch + c16 * 32 + 16);
+        tmem_ld_wait();
+        float gq[16], gx[16];
+        if (row_ok) {
+          float yv[16];
+          unpack8(y0, yv);
+          unpack8(y1, yv + 8);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            gq[j] = round_bf16(__uint_as_float(v[j]));
+            gx[j] = gq[j] * fmaf(yv[j], rs[c16 * 16 + j], -mr[c16 * 16 + j]);
+          }
+          a.dyhat[yrow + c16 * 2] = pack8(gq);
+          a.dyhat[yrow + c16 * 2 + 1] = pack8(gq + 8);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { gq[j] = 0.f; gx[j] = 0.f; }
+        }
+        warp_colsum16(gq, lane);
+        warp_colsum16(gx, lane);
+        if (!(lane & 1)) {
+          const int col = c16 * 16 + colsum16_col(lane);
+          atomicAdd(&sG[col], (double)gq[0]);
+          atomicAdd(&sG[a.C + col], (double)gx[0]);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (cur_n >= 0) {
+    for (int i = tid; i < a.C; i += BF_THREADS) {
+      atomicAdd(&a.gstats[(int64_t)cur_n * 2 * a.C + i], sG[i]);
+      atomicAdd(&a.gstats[(int64_t)cur_n * 2 * a.C + a.C + i], sG[a.C + i]);
+    }
+  }
+  if (it >= 1) mbar_wait(&bar[1], ph1);
+  tc_fence_after();
+  // ---- weight-gradient partials of this CTA: dW3^T rows 0..H (row H = db3), dW2^T rows 0..C (row C = db2)
+  {
+    const uint32_t lo = (uint32_t)(wq * 32) << 16;
+    float* p3 = fa.part3 + ((int64_t)blockIdx.x * 129 + row) * a.Co;
+    if (tid < a.Co) fa.part3[((int64_t)blockIdx.x * 129 + 128) * a.Co + tid] = db3acc;
+    for (int c16 = half; c16 < a.Co / 16; c16 += 2) {
+      uint32_t v[16];
+      tmem_ld16(accW3 + lo + c16 * 16, v);
+      tmem_ld_wait();
+      if (row < a.H) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) p3[c16 * 16 + j] = it > 0 ? __uint_as_float(v[j]) : 0.f;
+      }
+    }
+    float* p2 = fa.part2 + ((int64_t)blockIdx.x * 128 + row) * a.H;
+    for (int c16 = half; c16 < a.H / 16; c16 += 2) {
+      uint32_t v[16];
+      tmem_ld16(accW2 + lo + c16 * 16, v);
+      tmem_ld_wait();
+      if (row <= a.C) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) p2[c16 * 16 + j] = it > 0 ? __uint_as_float(v[j]) : 0.f;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+static size_t mlp_bwd_fused_smem(int C, int H, int Co, int N) {
+  return (size_t)H * C * 2 + (size_t)H * Co * 2 + (size_t)C * H * 2 + (size_t)16 * (C / 8 + 1) * 128 + (size_t)16 * (Co / 8) * 128 +
+         (size_t)16 * (H / 8) * 128 + (size_t)16 * (H / 8) * 128 + (size_t)128 * (C * 2 + 16) + 2048 + (size_t)4 * N * C * 4 + (size_t)H * 4 +
+         (size_t)2 * C * 8 + 128 * 4 + 2 * 8 + 16 + 128;
 }
 
 // ============================================================================ TN (split-K) wgrad GEMM
@@ -945,6 +1263,76 @@ extern "C" int pcb_mlp_bwd(const void* y, const double* stats, const float* gamm
   dim3 grid((unsigned)((a.Vy + 127) / 128), (unsigned)N, (unsigned)(C / a.Ct));
   mlp_bwd_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(a);
   PCB_CHECK_LAUNCH("pcb_mlp_bwd");
+  return PCB_OK;
+}
+
+
+static bool mlp_bwd_fused_ok(int64_t C, int64_t H, int64_t Co, int64_t N, int64_t Vy, int64_t Vout) {
+  auto pow2 = [](int64_t v) { return v > 0 && (v & (v - 1)) == 0; };
+  return getenv("PCB_NO_FUSED_BWD") == nullptr && pow2(C) && pow2(Co) && pow2(H) && C <= 64 && Co <= 128 && H < 128 + 1 && H % 16 == 0 &&
+         3 * H + C + Co <= 512 && (C + Co) / 8 * 128 <= 8 * 256 && N <= 8 && Vy < (1ll << 30) && Vout < (1ll << 30) &&
+         mlp_bwd_fused_smem((int)C, (int)H, (int)Co, (int)N) <= 227 * 1024;
+}
+
+extern "C" int pcb_mlp_bwd_fused_supported(int64_t C, int64_t H, int64_t Co, int64_t N, const int64_t y_size[3], int mode) {
+  const int64_t Vy = y_size[0] * y_size[1] * y_size[2];
+  const int64_t Vout = mode == PCB_DW_UP ? (y_size[0] + 1) * (y_size[1] + 1) * (y_size[2] + 1) : Vy;
+  return mlp_bwd_fused_ok(C, H, Co, N, Vy, Vout) ? 1 : 0;
+}
+
+static int mlp_bwd_fused_ctas(int64_t ntiles, uint32_t tmem_cols) {
+  int64_t p = 148 * (tmem_cols <= 256 ? 2 : 1);
+  if (p > ntiles) p = ntiles;
+  return (int)p;
+}
+
+extern "C" int64_t pcb_mlp_bwd_fused_workspace_floats(int64_t C, int64_t H, int64_t Co, int64_t N, const int64_t y_size[3]) {
+  const int64_t ntiles = (y_size[0] * y_size[1] * y_size[2] + 127) / 128 * N;
+  const int P = mlp_bwd_fused_ctas(ntiles, tmem_cols_pow2((uint32_t)(3 * H + C + Co)));
+  return (int64_t)P * (129 * Co + 128 * H);
+}
+
+extern "C" int pcb_mlp_bwd_fused(const void* y, const double* stats, const float* gamma, const float* beta, const void* w2,
+                                 const float* b2, const void* w3t, const void* w2t, const void* dout, void* dyhat,
+                                 double* gstats, float* workspace, float* dW3, float* db3, float* dW2, float* db2, int64_t N,
+                                 const int64_t y_size[3], int64_t C, int64_t H, int64_t Co, int mode, void* stream) {
+  PCB_CHECK_ARG(y && stats && gamma && beta && w2 && b2 && w3t && w2t && dout && dyhat && gstats && workspace && dW3 && db3 &&
+                dW2 && db2 && y_size, "pcb_mlp_bwd_fused: null argument");
+  MlpBwdFusedArgs fa;
+  MlpBwdArgs& a = fa.m;
+  a.y = (const uint4*)y; a.stats = stats; a.gamma = gamma; a.beta = beta; a.w2 = (const uint4*)w2; a.b2 = b2;
+  a.w3t = (const uint4*)w3t; a.w2t = (const uint4*)w2t; a.dout = (const uint4*)dout; a.hact = nullptr; a.dh = nullptr;
+  a.dyhat = (uint4*)dyhat; a.gstats = gstats;
+  a.y1 = (int)y_size[1]; a.y2 = (int)y_size[2];
+  a.C = (int)C; a.H = (int)H; a.Co = (int)Co; a.mode = mode;
+  a.Vy = y_size[0] * y_size[1] * y_size[2];
+  if (mode == PCB_DW_UP) { a.o1 = a.y1 + 1; a.o2 = a.y2 + 1; a.Vout = (y_size[0] + 1) * (int64_t)a.o1 * a.o2; }
+  else { a.o1 = a.y1; a.o2 = a.y2; a.Vout = a.Vy; }
+  PCB_CHECK_ARG(mlp_bwd_fused_ok(C, H, Co, N, a.Vy, a.Vout), "pcb_mlp_bwd_fused: unsupported shape C=%lld H=%lld Co=%lld", (long long)C, (long long)H, (long long)Co);
+  a.KC = (int)C; a.KCo = (int)Co; a.N1 = (int)H; a.Ct = (int)C;
+  a.inv_count = (float)(1.0 / (double)a.Vy);
+  fa.N = (int)N; fa.tps = (a.Vy + 127) / 128; fa.ntiles = fa.tps * N;
+  const uint32_t tcols = tmem_cols_pow2((uint32_t)(3 * H + C + Co));
+  const int P = mlp_bwd_fused_ctas(fa.ntiles, tcols);
+  fa.part3 = workspace; fa.part2 = workspace + (int64_t)P * 129 * Co;
+  const size_t smem = mlp_bwd_fused_smem((int)C, (int)H, (int)Co, (int)N);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(mlp_bwd_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (cudaFuncSetAttribute(mlp_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+      set_error("pcb_mlp_bwd_fused: cudaFuncSetAttribute failed"); return PCB_ERR_CUDA;
+    }
+    configured = true;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  mlp_bwd_fused_kernel<<<P, BF_THREADS, smem, st>>>(fa);
+  PCB_CHECK_LAUNCH("pcb_mlp_bwd_fused");
+  // second stage: dW3[co,h] = sum_p part3[p][h][co] ; db3[co] = sum_p part3[p][H][co]   (and the same for W2)
+  reduce_partials_kernel<<<(unsigned)((H * Co + 255) / 256), 256, 0, st>>>(fa.part3, P, (int)H, 129, (int)Co, (int)Co, dW3, 1, H, nullptr);
+  reduce_partials_kernel<<<1, 256, 0, st>>>(fa.part3 + 128 * Co, P, 1, 129, (int)Co, (int)Co, db3, 0, 1, nullptr);
+  reduce_partials_kernel<<<(unsigned)((C * H + 255) / 256), 256, 0, st>>>(fa.part2, P, (int)C, 128, (int)H, (int)H, dW2, 1, C, nullptr);
+  reduce_partials_kernel<<<1, 256, 0, st>>>(fa.part2 + C * H, P, 1, 128, (int)H, (int)H, db2, 0, 1, nullptr);
+  PCB_CHECK_LAUNCH("pcb_mlp_bwd_fused(reduce)");
   return PCB_OK;
 }
 

@@ -121,6 +121,25 @@ __device__ __forceinline__ void gelu_fast_vg(float x, float& val, float& grad) {
   grad = fmaf(h * fmaf(-t, t, 1.f), (x * x < 64.f) ? dp : 0.f, cdf);
 }
 
+// packed pair version: (x0,x1) -> values and derivatives, ~10 issue slots per element
+__device__ __forceinline__ void gelu_fast_vg2(uint64_t x, uint64_t& val, uint64_t& grad) {
+  float s0, s1;
+  upk2(mul2(x, x), s0, s1);
+  const uint64_t s = pk2(fminf(s0, 64.f), fminf(s1, 64.f));
+  const uint64_t p = fma2(fma2(pk2(PCB_GELU_C2, PCB_GELU_C2), s, pk2(PCB_GELU_C1, PCB_GELU_C1)), s, pk2(PCB_GELU_C0, PCB_GELU_C0));
+  const uint64_t dp = fma2(fma2(pk2(5.f * PCB_GELU_C2, 5.f * PCB_GELU_C2), s, pk2(3.f * PCB_GELU_C1, 3.f * PCB_GELU_C1)), s,
+                           pk2(PCB_GELU_C0, PCB_GELU_C0));
+  float u0, u1;
+  upk2(mul2(x, p), u0, u1);
+  const float t0 = tanh_mufu(u0), t1 = tanh_mufu(u1);
+  const uint64_t t = pk2(t0, t1), nt = pk2(-t0, -t1);
+  const uint64_t h = mul2(x, pk2(0.5f, 0.5f));
+  val = fma2(h, t, h);
+  const uint64_t cdf = fma2(pk2(0.5f, 0.5f), t, pk2(0.5f, 0.5f));
+  const uint64_t sech2 = fma2(nt, t, pk2(1.f, 1.f));          // 1 - t^2 (exactly 0 once tanh saturates)
+  grad = fma2(mul2(h, sech2), dp, cdf);
+}
+
 // exact (erf) GELU and its derivative, fp32
 __device__ __forceinline__ float gelu_f(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
