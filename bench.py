@@ -59,7 +59,7 @@ class Clocks:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -171,6 +171,9 @@ def workload_config(a, world):
 
 
 # ----------------------------------------------------------------------------- our arm
+T0 = time.time()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -182,6 +185,7 @@ def main():
     ap.add_argument("--volume", type=int, default=480)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-ops", action="store_true", help="time every pcb200 op with CUDA events (stderr table)")
+    ap.add_argument("--no-graph", action="store_true", help="run the timed steps eagerly instead of as one CUDA graph")
     a = ap.parse_args()
     a.warmup = max(3, a.warmup) if a.impl == "pcb200" else a.warmup
     if a.impl == "reference":
@@ -189,6 +193,11 @@ def main():
 
     import torch.distributed as dist
     from pytorch_connectomics_b200 import _lib as L
+
+    def dbg(msg):
+        if os.environ.get("PCB_BENCH_DEBUG"):
+            print(f"[bench r{os.environ.get('RANK', '0')} +{time.time() - T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
     from pytorch_connectomics_b200.architectures import build_model
     from pytorch_connectomics_b200.training import FlatGradArena
 
@@ -199,6 +208,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        dbg("process group up")
     if not os.path.exists(L.LIB_PATH):
         L.build()
     if L.lib().pcb_device_ok() != 1:
@@ -223,7 +233,7 @@ def main():
     if a.mode == "train":
         model.train()
         arena = FlatGradArena(model.parameters())
-        opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.01, fused=True)
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.01, fused=True, capturable=True)
         nb = a.batch
         shape = (nb, 1, SIDE, SIDE, SIDE)
         # a small pool of distinct resident inputs (fp16 volumes, as the data pipeline delivers them)
@@ -239,22 +249,54 @@ def main():
 
         for i in range(a.warmup):
             step(*pool[i % 4])
+            dbg(f"warmup step {i} enqueued")
         barrier()
+        dbg("warmup done")
         dom = f"mlp_fwd:m0C32H64Co32V{SIDE ** 3}"
-        L.prof_start([] if a.profile_ops else [dom, f"mlp_bwd:m0C32H64Co32V{SIDE ** 3}", f"dwconv_fwd:m0C32V{SIDE ** 3}"])
+        # (1) instrumented eager pass: per-launch CUDA events around the dominant kernel (roofline leg)
+        nprof = a.steps if (a.no_graph or a.profile_ops) else min(3, a.steps)
+        L.prof_start([] if a.profile_ops else [dom, f"mlp_bwd_fused:m0C32H64Co32V{SIDE ** 3}", f"dwconv_fwd:m0C32V{SIDE ** 3}"])
         l0 = L.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         w0 = time.time()
         e0.record()
-        for i in range(a.steps):
+        for i in range(nprof):
             step(*pool[i % 4])
         e1.record()
         barrier()
         w1 = time.time()
-        launches = L.launch_count() - l0
+        launches_per_step = (L.launch_count() - l0) // max(1, nprof)
         prof = L.prof_stop()
+        ms_eager = max_over_ranks(e0.elapsed_time(e1)) / nprof
+        # (2) timed region: the same step captured once as a CUDA graph and replayed K times
+        graphed = None
+        run = step
+        dbg(f"eager pass done: {ms_eager:.2f} ms/step")
+        # NCCL collectives inside a captured graph are left for a later round: data-parallel runs time eager steps
+        if not (a.no_graph or a.profile_ops or (world > 1 and not os.environ.get("PCB_GRAPH_DDP"))):
+            try:
+                from pytorch_connectomics_b200.training import GraphedTrainStep
+                graphed = GraphedTrainStep(model, bce_dice_loss, opt, arena, pool[0][0], pool[0][1], warmup=1)
+                run = graphed
+            except Exception as exc:   # keep the bench alive; say so in the JSON line
+                print(f"[bench] CUDA-graph capture failed, timing eager steps: {exc!r}", file=sys.stderr)
+                graphed = None
+                arena.rebind()
+        for i in range(2):
+            run(*pool[i % 4])
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.time()
+        e0.record()
+        for i in range(a.steps):
+            run(*pool[i % 4])
+        e1.record()
+        barrier()
+        w1 = time.time()
+        launches = launches_per_step * a.steps
         ms = max_over_ranks(e0.elapsed_time(e1))
         value = world * nb * a.steps / (ms / 1e3)
+        dbg(f"timed region done: {ms / a.steps:.2f} ms/step")
 
         # ---- end to end: pinned host batch -> H2D -> step -> loss D2H, every step
         hx = [torch.rand(shape).half().pin_memory() for _ in range(2)]
@@ -262,6 +304,8 @@ def main():
         h2d = hx[0].numel() * 2 + ht[0].numel() * 4
 
         def e2e_step(i):
+            if graphed is not None:      # pinned host -> static device buffers -> graph replay -> loss D2H
+                return float(graphed(hx[i % 2], ht[i % 2]).item())
             x = hx[i % 2].to(dev, non_blocking=True)
             t = ht[i % 2].to(dev, non_blocking=True)
             return float(step(x, t).item())
@@ -276,6 +320,7 @@ def main():
         f1.record()
         barrier()
         ms_e2e = max_over_ranks(f0.elapsed_time(f1))
+        dbg("e2e done")
         e2e = {"value": world * nb * a.steps / (ms_e2e / 1e3), "unit": "sub-volumes/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
         metric, unit = METRIC_TRAIN, "sub-volumes/s"
@@ -358,6 +403,9 @@ def main():
            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "bf16", "data": "synthetic", "config": workload_config(a, world), "e2e": e2e,
            "gpu_launches": int(launches), "roofline": roof,
+           "execution": ({"timed_region": "cuda_graph_replay" if graphed is not None else "eager",
+                          "eager_ms_per_step": ms_eager, "roofline_timed_in": f"instrumented eager pass of {nprof} steps"}
+                         if a.mode == "train" else {"timed_region": "eager"}),
            "clocks": clocks.window(w0, w1) if clocks else None}
     if clocks:
         clocks.stop()
