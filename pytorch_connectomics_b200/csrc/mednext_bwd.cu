@@ -1011,7 +1011,7 @@ __global__ void __launch_bounds__(256, 2) dw_wgrad_same_tiled_kernel(const uint4
     const uint4* xn = x + (int64_t)n * D * H * W * CH + cg * 4;
     const uint4* dn = dy + (int64_t)n * D * H * W * CH + cg * 4;
     __syncthreads();   // previous brick fully consumed
-    staged_copy<8>(BZ * BY * BX * 4, tid, 256,
+    staged_copy<((BZ * BY * BX * 4 + 255) / 256 <= 17 ? (BZ * BY * BX * 4 + 255) / 256 : 8)>(BZ * BY * BX * 4, tid, 256,
         [&](int q) {
           const int c4 = q & 3, v = q >> 2;
           const int bx = v % BX, by = (v / BX) % BY, bz = v / (BX * BY);

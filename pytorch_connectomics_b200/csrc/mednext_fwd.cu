@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(256, 2) dwconv_same_tiled_kernel(const uint4* 
   for (int i = tid; i < K * K * K * 32; i += 256) s_w[i] = w[(i >> 5) * a.C + cg * 32 + (i & 31)];
   if (tid < 64) s_stats[tid] = 0.0;
   const uint4* xn = x + (int64_t)n * a.D * a.H * a.W * CH + cg * 4;
-  staged_copy<8>(BZ * BY * BX * 4, tid, 256,
+  staged_copy<((BZ * BY * BX * 4 + 255) / 256 <= 17 ? (BZ * BY * BX * 4 + 255) / 256 : 8)>(BZ * BY * BX * 4, tid, 256,   // whole brick in flight at once
       [&](int q) {
         const int cc = q & 3, v = q >> 2;
         const int bx = v % BX, by = (v / BX) % BY, bz = v / (BX * BY);
