@@ -208,3 +208,32 @@ def test_mednext_s_shapes_and_parity():
     check(got, want, want_bf, "MedNeXt-S 32^3", slack=2e-3)
     with pytest.raises(ValueError):
         p(torch.rand(1, 1, 20, 32, 32, device=DEV))
+
+
+def test_full_size_config2_forward_parity():
+    """BASELINE configs[1] at full size: MedNeXt-S, 1x1x160^3.  One oracle forward on the host cores (tens of
+    seconds) against the engine; same two-number tolerance statement as the small cases."""
+    import os
+    torch.set_num_threads(min(os.cpu_count() or 1, 32))
+    torch.manual_seed(0)
+    o = OM.create_mednext_v1(1, 1, "S", 3, False).eval()
+    p = PM.create_mednext_v1(1, 1, "S", 3, False).eval()
+    p.load_state_dict(o.state_dict(), strict=True)
+    p.to(DEV)
+    x = torch.rand(1, 1, 160, 160, 160).half().float()
+    with torch.no_grad():
+        got = p(x.to(DEV).half())
+        want = o(x)
+        f1 = p.forward_features(x.to(DEV).half())
+        f2 = p.forward_features(x.to(DEV).half())
+    want_bf = autocast_ref(o, x)
+    assert got.shape == (1, 1, 160, 160, 160) and torch.isfinite(got).all()
+    check(got, want, want_bf, "MedNeXt-S 160^3 (config 2)", slack=2e-3)
+    # run-to-run determinism of the whole trunk at full size (fp64 statistics, ordered blending of nothing else)
+    assert (f1.float() - f2.float()).abs().max().item() <= 1e-2 * f1.float().abs().max().item()
+    # size-independent property: thresholded sigmoid agrees with the oracle (Jaccard of the binary masks ~ 1)
+    from oracle.window_oracle import binary_jaccard
+    j = binary_jaccard((torch.sigmoid(got.float()).cpu() > 0.5).numpy().astype("float32"),
+                       (torch.sigmoid(want) > 0.5).numpy().astype("float32"), 0.5)
+    print(f"Jaccard(engine mask, oracle mask) at 160^3 = {j:.5f}")
+    assert j > 0.99
