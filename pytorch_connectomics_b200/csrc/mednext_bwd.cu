@@ -762,15 +762,32 @@ __global__ void __launch_bounds__(128) tn_gemm_kernel(TnArgs a) {
 }
 
 // second stage: dW[m*ldm + n*ldn] = sum_p part[p][m][n] (n < Nw) ; db[m] = sum_p part[p][m][Nw]
-__global__ void reduce_partials_kernel(const float* __restrict__ part, int P, int M, int Mtot, int Ncols_tot, int Nw,
-                                       float* __restrict__ dW, int64_t ldm, int64_t ldn, float* __restrict__ db) {
-  const int64_t total = (int64_t)M * (Nw + (db ? 1 : 0));
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int m = (int)(i / (Nw + (db ? 1 : 0))), nn = (int)(i - (int64_t)m * (Nw + (db ? 1 : 0)));
+// 256 threads = 32 outputs x 8 partial-index lanes; fixed summation order -> run-to-run deterministic.
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ part, int P, int M, int Mtot,
+                                                              int Ncols_tot, int Nw, float* __restrict__ dW, int64_t ldm,
+                                                              int64_t ldn, float* __restrict__ db) {
+  __shared__ float s_red[8][33];
+  const int ncol = Nw + (db ? 1 : 0);
+  const int64_t total = (int64_t)M * ncol;
+  const int lane_o = threadIdx.x & 31, pg = threadIdx.x >> 5;
+  for (int64_t base = (int64_t)blockIdx.x * 32; base < total; base += (int64_t)gridDim.x * 32) {
+    const int64_t i = base + lane_o;
     float s = 0.f;
-    for (int p = 0; p < P; ++p) s += part[((int64_t)p * Mtot + m) * Ncols_tot + nn];
-    if (nn < Nw) dW[m * ldm + nn * ldn] = s;
-    else db[m] = s;
+    int m = 0, nn = 0;
+    if (i < total) {
+      m = (int)(i / ncol); nn = (int)(i - (int64_t)m * ncol);
+      for (int p = pg; p < P; p += 8) s += part[((int64_t)p * Mtot + m) * Ncols_tot + nn];
+    }
+    s_red[pg][lane_o] = s;
+    __syncthreads();
+    if (pg == 0 && i < total) {
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += s_red[k][lane_o];
+      if (nn < Nw) dW[m * ldm + nn * ldn] = t;
+      else db[m] = t;
+    }
+    __syncthreads();
   }
 }
 
@@ -1328,10 +1345,10 @@ extern "C" int pcb_mlp_bwd_fused(const void* y, const double* stats, const float
   mlp_bwd_fused_kernel<<<P, BF_THREADS, smem, st>>>(fa);
   PCB_CHECK_LAUNCH("pcb_mlp_bwd_fused");
   // second stage: dW3[co,h] = sum_p part3[p][h][co] ; db3[co] = sum_p part3[p][H][co]   (and the same for W2)
-  reduce_partials_kernel<<<(unsigned)((H * Co + 255) / 256), 256, 0, st>>>(fa.part3, P, (int)H, 129, (int)Co, (int)Co, dW3, 1, H, nullptr);
-  reduce_partials_kernel<<<1, 256, 0, st>>>(fa.part3 + 128 * Co, P, 1, 129, (int)Co, (int)Co, db3, 0, 1, nullptr);
-  reduce_partials_kernel<<<(unsigned)((C * H + 255) / 256), 256, 0, st>>>(fa.part2, P, (int)C, 128, (int)H, (int)H, dW2, 1, C, nullptr);
-  reduce_partials_kernel<<<1, 256, 0, st>>>(fa.part2 + C * H, P, 1, 128, (int)H, (int)H, db2, 0, 1, nullptr);
+  reduce_partials_kernel<<<(unsigned)((H * Co + 31) / 32), 256, 0, st>>>(fa.part3, P, (int)H, 129, (int)Co, (int)Co, dW3, 1, H, nullptr);
+  reduce_partials_kernel<<<(unsigned)((Co + 31) / 32), 256, 0, st>>>(fa.part3 + 128 * Co, P, 1, 129, (int)Co, (int)Co, db3, 0, 1, nullptr);
+  reduce_partials_kernel<<<(unsigned)((C * H + 31) / 32), 256, 0, st>>>(fa.part2, P, (int)C, 128, (int)H, (int)H, dW2, 1, C, nullptr);
+  reduce_partials_kernel<<<(unsigned)((H + 31) / 32), 256, 0, st>>>(fa.part2 + C * H, P, 1, 128, (int)H, (int)H, db2, 0, 1, nullptr);
   PCB_CHECK_LAUNCH("pcb_mlp_bwd_fused(reduce)");
   return PCB_OK;
 }
@@ -1387,7 +1404,7 @@ extern "C" int pcb_tn_gemm(const void* A, const void* B, const double* stats, co
   tn_gemm_kernel<<<grid, 128, smem, st>>>(a);
   PCB_CHECK_LAUNCH("pcb_tn_gemm");
   const int64_t total = Ma * (Nb + (db ? 1 : 0));
-  reduce_partials_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(workspace, P, (int)Ma, a.Mtot, a.Ncols_tot,
+  reduce_partials_kernel<<<(unsigned)((total + 31) / 32), 256, 0, st>>>(workspace, P, (int)Ma, a.Mtot, a.Ncols_tot,
                                                                          (int)Nb, dW, ldm, ldn, db);
   PCB_CHECK_LAUNCH("pcb_tn_gemm(reduce)");
   return PCB_OK;
