@@ -226,3 +226,41 @@ def test_flat_arena_allreduce_gloo_world2():
         gs.append(torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in net.parameters()]))
     assert torch.allclose(res[0], (gs[0] + gs[1]) / 2, atol=1e-6)
     assert res[0][-6:].abs().sum() == 0                     # the unused head stays zero (no hang, no None grads)
+
+
+def _reduce_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pytorch_connectomics_b200.inference.lazy_distributed import (make_accumulator_reducer, should_shard_windows,
+                                                                      validate_patch_shard)
+    assert should_shard_windows(True) and not should_shard_windows(False)
+    validate_patch_shard(3, 6, "cpu")
+    v = torch.full((1, 2, 3, 3, 3), float(rank + 1))
+    w = torch.full((1, 1, 3, 3, 3), 0.5)
+    out = make_accumulator_reducer()(v, w)
+    q.put((rank, None if out is None else (out[0].clone(), out[1].clone())))
+    try:
+        validate_patch_shard(0 if rank == 1 else 2, 2, "cpu")
+        q.put((rank, "no error"))
+    except RuntimeError as e:
+        q.put((rank, "empty" in str(e)))
+    dist.destroy_process_group()
+
+
+def test_accumulator_reduce_to_root_gloo_world2():
+    # reference lazy_distributed.py:78-169: SUM onto rank 0, None elsewhere, empty-shard check
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_reduce_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(4)]
+    for p in procs:
+        p.join(timeout=60)
+    first = {r: v for r, v in got if not isinstance(v, (bool, str))}
+    assert first[1] is None
+    assert torch.equal(first[0][0], torch.full((1, 2, 3, 3, 3), 3.0)) and torch.equal(first[0][1], torch.full((1, 1, 3, 3, 3), 1.0))
+    assert all(v is True for r, v in got if isinstance(v, (bool, str)))
