@@ -154,6 +154,33 @@ int pcb_head_bwd(const void* dout, int dtype, const void* x, const float* w, voi
 int pcb_stem_bwd(const void* g, const void* x, int in_dtype, double* dW, double* db, int64_t N, int64_t Cin,
                  int64_t C, int64_t nvox, void* stream);
 
+/* ------------------------------------------------------------------ dense conv path (MONAI UNet, `monai_unet`)
+ * (monai.networks.blocks.{Convolution,ResidualUnit,ADN} as built by
+ *  connectomics/models/architectures/monai_models.py:235-248)
+ *
+ * Conv3d (transposed=0: src = o*stride + t - pad) / ConvTranspose3d (transposed=1: src = (o + pad - t)/stride) as an
+ * implicit GEMM on tcgen05.  x NDHWC bf16 [N,in_size,Ci], w bf16 [k^3][Co][Ci] (tap-major, K-major rows),
+ * bias f32 [Co] or NULL, out NDHWC bf16 [N,out_size,Co].  Ci, Co padded to multiples of 16.  The same entry
+ * point computes data gradients with repacked weights (conv <-> transposed conv). */
+int pcb_conv_fwd(const void* x, const void* w, const float* bias, void* out, int64_t N, const int64_t in_size[3],
+                 const int64_t out_size[3], int64_t Ci, int64_t Co, int k, int stride, int pad, int transposed,
+                 void* stream);
+/* weight gradient of one tap: dW[co*ldm + ci*ldn] = sum_o dy[o,co] * x[src(o,tap),ci]; db[co] = sum dy (optional). */
+int pcb_conv_wgrad_tap(const void* dy, const void* x, float* workspace, float* dW, int64_t ldm, int64_t ldn, float* db,
+                       int64_t N, const int64_t out_size[3], const int64_t in_size[3], int64_t Co, int64_t Ci,
+                       const int tap[3], int stride, int pad, int transposed, void* stream);
+/* per-channel sum / sum of squares over `rows` channels-last bf16 rows (BatchNorm batch statistics), f64 [2,C] +=. */
+int pcb_channel_stats(const void* x, double* stats, int64_t C, int64_t rows, void* stream);
+/* ADN "NA": y = PReLU(x*scale + shift) with BatchNorm folded into the per-channel affine; slope = device float. */
+int pcb_bn_act_fwd(const void* x, const float* scale, const float* shift, const float* slope, void* out, int64_t C,
+                   int64_t rows, void* stream);
+/* dz = dy*PReLU'(z) (bf16); red[0..C) += dz, red[C..2C) += dz*xhat, red[2C] += dy*min(z,0)  (f64, caller zeroes). */
+int pcb_bn_act_bwd(const void* dy, const void* x, const float* scale, const float* shift, const float* mean,
+                   const float* rstd, const float* slope, void* dz, double* red, int64_t C, int64_t rows, void* stream);
+/* BatchNorm backward with batch statistics (pooled sums replicated per sample in stats/gstats [N,2,C]). */
+int pcb_bn_bwd(const void* g, const void* x, const double* stats, const double* gstats, const float* gamma,
+               void* dx, double* dsum, int64_t N, int64_t C, int64_t V, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

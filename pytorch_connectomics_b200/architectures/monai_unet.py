@@ -1,0 +1,402 @@
+"""MONAI ``UNet`` on the B200 engine — drop-in for what ``build_monai_unet``
+(``connectomics/models/architectures/monai_models.py:197-250``) gets from ``monai.networks.nets.UNet``
+(BASELINE config 1, ``tutorials/minimal.yaml``).
+
+Module / child names follow MONAI (``Convolution`` = Sequential{conv, adn{N,D,A}}, ``ResidualUnit`` =
+{conv{unit0..}, residual}, ``SkipConnection.submodule``), so ``state_dict`` keys are the MONAI ones
+(``model.0.conv.unit0.conv.weight`` …) and reference checkpoints load unchanged.  The torch children are
+parameter/buffer containers; the arithmetic runs in ``csrc/dense_conv.cu`` (implicit-GEMM conv on tcgen05,
+BatchNorm+PReLU, their backward) and ``csrc/mednext_bwd.cu`` (split-K weight-gradient GEMM) on channels-last
+bf16 activations whose channel counts are zero-padded to multiples of 16.  Not yet on hand-written kernels
+(plain tensor plumbing for now): the residual ``+`` and the skip ``cat``.
+Supported: 3-D, ``norm="batch"``, ``dropout=0``, ``upsample_mode="deconv"`` — anything else raises.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from typing import List, Sequence
+
+import torch
+import torch.nn as nn
+
+from .. import _lib as L
+from . import _mednext_ops as ops
+from .base import ConnectomicsModel
+from .registry import register_architecture
+
+_BF16 = torch.bfloat16
+
+
+def _pad16(c: int) -> int:
+    return (int(c) + 15) // 16 * 16
+
+
+def _pad_mat(w: torch.Tensor, rows: int, cols: int) -> torch.Tensor:
+    """[..., r, c] -> zero-padded [..., rows, cols] bf16 contiguous."""
+    out = torch.zeros(w.shape[:-2] + (rows, cols), device=w.device, dtype=_BF16)
+    out[..., : w.shape[-2], : w.shape[-1]] = w.to(_BF16)
+    return out.contiguous()
+
+
+def _pack(kind: str):
+    def conv_fwd(w):       # Conv3d [Co,Ci,k,k,k] -> [k^3][Co][Ci]
+        co, ci = w.shape[:2]
+        return _pad_mat(w.permute(2, 3, 4, 0, 1).reshape(-1, co, ci), _pad16(co), _pad16(ci))
+
+    def conv_dgrad_s1(w):  # flipped taps, [k^3][Ci][Co]
+        co, ci = w.shape[:2]
+        return _pad_mat(w.flip(2, 3, 4).permute(2, 3, 4, 1, 0).reshape(-1, ci, co), _pad16(ci), _pad16(co))
+
+    def conv_dgrad_s2(w):  # unflipped, [k^3][Ci][Co]  (used by the transposed gather)
+        co, ci = w.shape[:2]
+        return _pad_mat(w.permute(2, 3, 4, 1, 0).reshape(-1, ci, co), _pad16(ci), _pad16(co))
+
+    def convt_fwd(w):      # ConvTranspose3d [Ci,Co,k,k,k] -> [k^3][Co][Ci]
+        ci, co = w.shape[:2]
+        return _pad_mat(w.permute(2, 3, 4, 1, 0).reshape(-1, co, ci), _pad16(co), _pad16(ci))
+
+    def convt_dgrad(w):    # [k^3][Ci][Co]
+        ci, co = w.shape[:2]
+        return _pad_mat(w.permute(2, 3, 4, 0, 1).reshape(-1, ci, co), _pad16(ci), _pad16(co))
+
+    def vec16(v):
+        out = torch.zeros(_pad16(v.numel()), device=v.device, dtype=torch.float32)
+        out[: v.numel()] = v.reshape(-1).float()
+        return out
+
+    def ones16(v):
+        out = torch.ones(_pad16(v.numel()), device=v.device, dtype=torch.float32)
+        out[: v.numel()] = v.reshape(-1).float()
+        return out
+
+    return {"conv_fwd": conv_fwd, "conv_dgrad_s1": conv_dgrad_s1, "conv_dgrad_s2": conv_dgrad_s2, "convt_fwd": convt_fwd,
+            "convt_dgrad": convt_dgrad, "vec16": vec16, "ones16": ones16}[kind]
+
+
+for _k in ("conv_fwd", "conv_dgrad_s1", "conv_dgrad_s2", "convt_fwd", "convt_dgrad", "vec16", "ones16"):
+    ops._PACKERS.setdefault(_k, _pack(_k))
+
+
+def _conv_launch(x, w_packed, bias, out_size, ci_p, co_p, k, stride, pad, transposed):
+    n = int(x.shape[0])
+    in_size = [int(s) for s in x.shape[1:4]]
+    out = torch.empty((n, *out_size, co_p), device=x.device, dtype=_BF16)
+    L.check(L.lib().pcb_conv_fwd(L.ptr(x), L.ptr(w_packed), L.ptr(bias), L.ptr(out), ctypes.c_int64(n), L.i64x(in_size),
+                                 L.i64x(out_size), ctypes.c_int64(ci_p), ctypes.c_int64(co_p), k, stride, pad,
+                                 1 if transposed else 0, L.stream_ptr(x.device)), "pcb_conv_fwd")
+    return out
+
+
+class ConvFn(torch.autograd.Function):
+    """Conv3d / ConvTranspose3d (+bias) on padded channels-last bf16 through the implicit-GEMM kernel."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, k, stride, pad, transposed):
+        in_size = [int(s) for s in x.shape[1:4]]
+        if transposed:
+            ci, co = int(weight.shape[0]), int(weight.shape[1])
+            out_size = [(s - 1) * stride - 2 * pad + k + (stride - 1) for s in in_size]   # output_padding = stride-1
+            wp = ops.packed(weight, "convt_fwd")
+        else:
+            co, ci = int(weight.shape[0]), int(weight.shape[1])
+            out_size = [(s + 2 * pad - k) // stride + 1 for s in in_size]
+            wp = ops.packed(weight, "conv_fwd")
+        if int(x.shape[4]) != _pad16(ci):
+            raise ValueError(f"conv expects {_pad16(ci)} (padded) input channels, got {int(x.shape[4])}")
+        bp = ops.packed(bias, "vec16") if bias is not None else None
+        out = _conv_launch(x, wp, bp, out_size, _pad16(ci), _pad16(co), k, stride, pad, transposed)
+        ctx.save_for_backward(x, weight)
+        ctx.cfg = (k, stride, pad, transposed, bias is not None, ci, co, in_size, out_size)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        k, stride, pad, transposed, has_bias, ci, co, in_size, out_size = ctx.cfg
+        dy = dy.contiguous()
+        n, cip, cop = int(x.shape[0]), _pad16(ci), _pad16(co)
+        lib, st, dev = L.lib(), L.stream_ptr(x.device), x.device
+        dx = None
+        if ctx.needs_input_grad[0]:
+            if transposed:      # gradient of a transposed conv is the strided conv
+                dx = _conv_launch(dy, ops.packed(weight, "convt_dgrad"), None, in_size, cop, cip, k, stride, pad, False)
+            elif stride == 1:   # same-size conv with flipped taps
+                dx = _conv_launch(dy, ops.packed(weight, "conv_dgrad_s1"), None, in_size, cop, cip, k, 1, pad, False)
+            else:               # gradient of a strided conv is the transposed gather
+                dx = _conv_launch(dy, ops.packed(weight, "conv_dgrad_s2"), None, in_size, cop, cip, k, stride, pad, True)
+        # weight gradient: one split-K GEMM per tap, D[co, ci] = sum_o dy[o,co] * x[src(o,tap), ci]
+        k3 = k * k * k
+        if transposed:
+            dwp = torch.zeros((cip, cop, k3), device=dev, dtype=torch.float32)
+            ldm, ldn = k3, cop * k3
+        else:
+            dwp = torch.zeros((cop, cip, k3), device=dev, dtype=torch.float32)
+            ldm, ldn = cip * k3, k3
+        dbp = torch.zeros((cop,), device=dev, dtype=torch.float32)
+        nfl = int(lib.pcb_tn_workspace_floats(ctypes.c_int64(cop), ctypes.c_int64(cip), 1, ctypes.c_int64(n), L.i64x(out_size)))
+        ws = torch.empty(nfl, device=dev, dtype=torch.float32)
+        for t in range(k3):
+            tap = (ctypes.c_int * 3)(t // (k * k), (t // k) % k, t % k)
+            dst = ctypes.c_void_p(dwp.data_ptr() + 4 * t)
+            L.check(lib.pcb_conv_wgrad_tap(L.ptr(dy), L.ptr(x), L.ptr(ws), dst, ctypes.c_int64(ldm), ctypes.c_int64(ldn),
+                                           L.ptr(dbp) if t == 0 else None, ctypes.c_int64(n), L.i64x(out_size), L.i64x(in_size),
+                                           ctypes.c_int64(cop), ctypes.c_int64(cip), tap, stride, pad, 1 if transposed else 0,
+                                           st), "pcb_conv_wgrad_tap")
+        if transposed:
+            dw = dwp[:ci, :co].reshape(ci, co, k, k, k)
+        else:
+            dw = dwp[:co, :ci].reshape(co, ci, k, k, k)
+        return dx, dw.contiguous(), (dbp[:co].clone() if has_bias else None), None, None, None, None
+
+
+class BnActFn(torch.autograd.Function):
+    """ADN "NDA" with BatchNorm + PReLU (dropout 0): y = PReLU(BN(x)); batch statistics in training mode."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, slope, running_mean, running_var, training, momentum, eps, c_real):
+        n, cp = int(x.shape[0]), int(x.shape[4])
+        v = int(x.shape[1] * x.shape[2] * x.shape[3])
+        rows = n * v
+        lib, st = L.lib(), L.stream_ptr(x.device)
+        g16, b16 = ops.packed(gamma, "ones16"), ops.packed(beta, "vec16")
+        if training:
+            stats = torch.zeros((2, cp), device=x.device, dtype=torch.float64)
+            L.check(lib.pcb_channel_stats(L.ptr(x), L.ptr(stats), ctypes.c_int64(cp), ctypes.c_int64(rows), st), "pcb_channel_stats")
+            mean64 = stats[0] / rows
+            var64 = (stats[1] / rows - mean64 * mean64).clamp_min(0.0)
+            with torch.no_grad():   # running statistics as nn.BatchNorm3d: momentum update with the unbiased variance
+                running_mean.mul_(1 - momentum).add_(mean64[:c_real].float(), alpha=momentum)
+                running_var.mul_(1 - momentum).add_((var64[:c_real] * (rows / max(rows - 1, 1))).float(), alpha=momentum)
+        else:
+            stats = None
+            mean64 = torch.zeros(cp, device=x.device, dtype=torch.float64)
+            var64 = torch.ones(cp, device=x.device, dtype=torch.float64)
+            mean64[:c_real] = running_mean.double()
+            var64[:c_real] = running_var.double()
+        rstd = (1.0 / torch.sqrt(var64 + eps)).float()
+        mean = mean64.float()
+        scale = (g16 * rstd).contiguous()
+        shift = (b16 - mean * scale).contiguous()
+        slope_f = slope.detach().reshape(-1)[:1].float().contiguous()
+        out = torch.empty_like(x)
+        L.check(lib.pcb_bn_act_fwd(L.ptr(x), L.ptr(scale), L.ptr(shift), L.ptr(slope_f), L.ptr(out), ctypes.c_int64(cp),
+                                   ctypes.c_int64(rows), st), "pcb_bn_act_fwd")
+        ctx.save_for_backward(x, scale, shift, mean, rstd, slope_f, g16, stats if stats is not None else mean64)
+        ctx.cfg = (training, c_real, n, v, cp)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, scale, shift, mean, rstd, slope_f, g16, stats = ctx.saved_tensors
+        training, c_real, n, v, cp = ctx.cfg
+        dy = dy.contiguous()
+        lib, st = L.lib(), L.stream_ptr(x.device)
+        rows = n * v
+        red = torch.zeros(2 * cp + 1, device=x.device, dtype=torch.float64)
+        dz = torch.empty_like(x)
+        L.check(lib.pcb_bn_act_bwd(L.ptr(dy), L.ptr(x), L.ptr(scale), L.ptr(shift), L.ptr(mean), L.ptr(rstd), L.ptr(slope_f),
+                                   L.ptr(dz), L.ptr(red), ctypes.c_int64(cp), ctypes.c_int64(rows), st), "pcb_bn_act_bwd")
+        if training:
+            dx = torch.empty_like(x)
+            stats_rep = stats.reshape(1, 2, cp).expand(n, 2, cp).contiguous()
+            gst_rep = red[: 2 * cp].reshape(1, 2, cp).expand(n, 2, cp).contiguous()
+            dsum = torch.zeros(cp, device=x.device, dtype=torch.float64)
+            L.check(lib.pcb_bn_bwd(L.ptr(dz), L.ptr(x), L.ptr(stats_rep), L.ptr(gst_rep), L.ptr(g16), L.ptr(dx), L.ptr(dsum),
+                                   ctypes.c_int64(n), ctypes.c_int64(cp), ctypes.c_int64(v), st), "pcb_bn_bwd")
+        else:               # eval mode: BatchNorm is a fixed affine
+            dx = (dz.float() * scale).to(_BF16)
+        dgamma = red[cp: cp + c_real].float()
+        dbeta = red[:c_real].float()
+        dslope = red[2 * cp].float().reshape(1)
+        return dx, dgamma, dbeta, dslope, None, None, None, None, None, None
+
+
+# ----------------------------------------------------------------------------- MONAI-named module tree
+def _unsupported(what):
+    raise NotImplementedError(f"pcb200 monai_unet: {what} is not implemented in the B200 engine yet "
+                              "(3-D, norm='batch', dropout=0, upsample_mode='deconv' only).")
+
+
+class ADN(nn.Sequential):
+    def __init__(self, channels: int, dropout):
+        super().__init__()
+        self.add_module("N", nn.BatchNorm3d(channels))
+        if dropout is not None:
+            self.add_module("D", nn.Dropout(float(dropout)))
+        self.add_module("A", nn.PReLU())
+
+    def forward(self, x):
+        bn = self.N
+        return BnActFn.apply(x, bn.weight, bn.bias, self.A.weight, bn.running_mean, bn.running_var,
+                             bool(self.training and bn.track_running_stats), float(bn.momentum or 0.1), float(bn.eps),
+                             int(bn.num_features))
+
+
+class Convolution(nn.Sequential):
+    def __init__(self, in_channels, out_channels, strides=1, kernel_size=3, dropout=0.0, bias=True, conv_only=False,
+                 is_transposed=False):
+        super().__init__()
+        pad = (kernel_size - 1) // 2
+        if is_transposed:
+            conv = nn.ConvTranspose3d(in_channels, out_channels, kernel_size, stride=strides, padding=pad,
+                                      output_padding=strides - 1, bias=bias)
+        else:
+            conv = nn.Conv3d(in_channels, out_channels, kernel_size, stride=strides, padding=pad, bias=bias)
+        self.add_module("conv", conv)
+        if not conv_only:
+            self.add_module("adn", ADN(out_channels, dropout))
+        self._cfg = (kernel_size, strides, pad, bool(is_transposed))
+
+    def forward(self, x):
+        k, s, p, tr = self._cfg
+        y = ConvFn.apply(x, self.conv.weight, self.conv.bias, k, s, p, tr)
+        if hasattr(self, "adn"):
+            if self.training and self.adn.N.track_running_stats:
+                with torch.no_grad():
+                    self.adn.N.num_batches_tracked += 1
+            y = self.adn(y)
+        return y
+
+
+class ResidualUnit(nn.Module):
+    def __init__(self, in_channels, out_channels, strides=1, kernel_size=3, subunits=2, dropout=0.0, bias=True,
+                 last_conv_only=False):
+        super().__init__()
+        self.conv = nn.Sequential()
+        self.residual: nn.Module = nn.Identity()
+        sch, sst = in_channels, strides
+        for su in range(max(1, subunits)):
+            only = last_conv_only and su == max(1, subunits) - 1
+            self.conv.add_module(f"unit{su:d}", Convolution(sch, out_channels, sst, kernel_size, dropout, bias, only))
+            sch, sst = out_channels, 1
+        self._res_cfg = None
+        if strides != 1 or in_channels != out_channels:
+            rk, rp = (kernel_size, (kernel_size - 1) // 2) if strides != 1 else (1, 0)
+            self.residual = nn.Conv3d(in_channels, out_channels, rk, strides, rp, bias=bias)
+            self._res_cfg = (rk, strides, rp)
+
+    def forward(self, x):
+        cx = self.conv(x)
+        if self._res_cfg is None:
+            res = x
+        else:
+            rk, rs, rp = self._res_cfg
+            res = ConvFn.apply(x, self.residual.weight, self.residual.bias, rk, rs, rp, False)
+        return cx + res
+
+
+class SkipConnection(nn.Module):
+    def __init__(self, submodule: nn.Module, c_in: int):
+        super().__init__()
+        self.submodule = submodule
+        self._c_in = c_in
+
+    def forward(self, x):
+        y = self.submodule(x)
+        # cat([x, y], channel) on the REAL channels, re-padded to a multiple of 16 for the consuming conv
+        cx, cy = self._c_in, self._c_out
+        cat = torch.cat([x[..., :cx], y[..., :cy]], dim=-1)
+        padc = _pad16(cx + cy) - (cx + cy)
+        if padc:
+            cat = torch.nn.functional.pad(cat, (0, padc))
+        return cat.contiguous()
+
+
+class UNet(nn.Module):
+    """monai.networks.nets.UNet (3-D, batch norm, PReLU, deconv upsampling) on the B200 engine."""
+
+    def __init__(self, spatial_dims: int, in_channels: int, out_channels: int, channels: Sequence[int], strides: Sequence[int],
+                 kernel_size: int = 3, up_kernel_size: int = 3, num_res_units: int = 0, norm="batch", dropout: float = 0.0,
+                 bias: bool = True):
+        super().__init__()
+        if spatial_dims != 3:
+            _unsupported("spatial_dims != 3")
+        if norm != "batch":
+            _unsupported(f"norm={norm!r}")
+        if dropout not in (0, 0.0, None):
+            _unsupported("dropout > 0")
+        if kernel_size != 3 or up_kernel_size != 3:
+            _unsupported("kernel_size != 3")
+        if len(channels) < 2:
+            raise ValueError("the length of `channels` should be no less than 2.")
+        if len(strides) < len(channels) - 1:
+            raise ValueError("the length of `strides` should equal to `len(channels) - 1`.")
+        if any(s not in (1, 2) for s in strides):
+            _unsupported("strides other than 1 or 2")
+        self.dimensions, self.kernel_size, self.num_res_units = spatial_dims, kernel_size, num_res_units
+        self.in_channels, self.out_channels, self.dropout, self.bias = in_channels, out_channels, dropout, bias
+        self.n_down = sum(1 for s in strides[: len(channels) - 1] if s == 2)
+
+        def block(inc, outc, ch, st, is_top):
+            c, s = ch[0], st[0]
+            if len(ch) > 2:
+                sub, upc, sub_out = block(c, c, ch[1:], st[1:], False), c * 2, c
+            else:
+                sub, upc, sub_out = self._down(c, ch[1], 1), c + ch[1], ch[1]
+            skip = SkipConnection(sub, c)
+            skip._c_out = sub_out
+            return nn.Sequential(self._down(inc, c, s), skip, self._up(upc, outc, s, is_top))
+
+        self.model = block(in_channels, out_channels, list(channels), list(strides), True)
+
+    def _down(self, i, o, s):
+        if self.num_res_units > 0:
+            return ResidualUnit(i, o, s, self.kernel_size, self.num_res_units, self.dropout, self.bias)
+        return Convolution(i, o, s, self.kernel_size, self.dropout, self.bias)
+
+    def _up(self, i, o, s, is_top):
+        conv = Convolution(i, o, s, 3, self.dropout, self.bias, conv_only=is_top and self.num_res_units == 0,
+                           is_transposed=True)
+        if self.num_res_units > 0:
+            return nn.Sequential(conv, ResidualUnit(o, o, 1, self.kernel_size, 1, self.dropout, self.bias, last_conv_only=is_top))
+        return conv
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        L.require_device(x, "monai_unet forward")
+        if x.dim() != 5:
+            raise ValueError(f"monai_unet expects (B, C, D, H, W); got shape {tuple(x.shape)}")
+        div = 2 ** self.n_down
+        if any(int(s) % div for s in x.shape[2:]):
+            raise ValueError(f"monai_unet input spatial size must be divisible by {div}, got {tuple(x.shape[2:])}")
+        c = int(x.shape[1])
+        h = x.permute(0, 2, 3, 4, 1)
+        padc = _pad16(c) - c
+        if padc:
+            h = torch.nn.functional.pad(h, (0, padc))
+        h = h.to(_BF16).contiguous()
+        y = self.model(h)
+        return y[..., : self.out_channels].permute(0, 4, 1, 2, 3).to(x.dtype if x.dtype != torch.float64 else torch.float32).contiguous()
+
+
+class MONAIModelWrapper(ConnectomicsModel):
+    """``monai_models.py:29-56`` — ConnectomicsModel interface; squeezes a singleton depth for 2-D nets."""
+
+    def __init__(self, model: nn.Module):
+        super().__init__()
+        self.model = model
+        self.supports_deep_supervision = False
+        self.output_scales = 1
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.model(x)
+
+
+@register_architecture("monai_unet")
+def build_monai_unet(cfg) -> ConnectomicsModel:
+    """MONAI UNet with residual units on the B200 engine (``monai_models.py:197-250``)."""
+    m = cfg.model.monai
+    size = getattr(cfg.model, "input_size", None)
+    dims = len(size) if size else getattr(m, "spatial_dims", 3)
+    channels = list(getattr(m, "filters", [32, 64, 128, 256, 512]))
+    mode = getattr(m, "upsample_mode", "deconv")
+    if mode and mode != "deconv":
+        _unsupported(f"upsample_mode={mode!r}")
+    norm = getattr(m, "norm", "batch")
+    model = UNet(spatial_dims=dims, in_channels=cfg.model.in_channels, out_channels=cfg.model.out_channels,
+                 channels=channels, strides=[2] * (len(channels) - 1), num_res_units=getattr(m, "num_res_units", 2),
+                 kernel_size=getattr(m, "kernel_size", 3), norm=norm, dropout=getattr(m, "dropout", 0.0))
+    return MONAIModelWrapper(model)
+
+
+__all__ = ["UNet", "MONAIModelWrapper", "build_monai_unet"]

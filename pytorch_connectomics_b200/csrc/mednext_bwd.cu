@@ -619,6 +619,7 @@ struct TnArgs {
   int Ma, Nb;                   // valid A columns (M of D), B columns (N of D without the ones block)
   int ones;                     // append an all-ones column block (16 wide) to B chunk 0
   int mapA, mapB;
+  int tz, ty, tx, tstride, tpad, bs0;   // conv-tap row map for B (mapB 4: conv, 5: transposed conv)
   int d1, d2;                   // iteration box trailing dims (tile voxel -> coordinates)
   int as1, as2, bs1, bs2;       // trailing spatial dims of the A / B tensors (for the row maps)
   int64_t V;                    // voxels per sample in the iteration box
@@ -704,7 +705,25 @@ __global__ void __launch_bounds__(128) tn_gemm_kernel(TnArgs a) {
         [&](int q) {
           const int v = n8pow2 ? (q >> n8sh) : (q / nb8), g8 = q - v * nb8;
           if (v0 + v >= a.V) return make_uint4(0, 0, 0, 0);
-          const int64_t r = map_row(a.mapB, v0 + v, a.d1, a.d2, a.bs1, a.bs2);
+          int64_t r;
+          if (a.mapB >= 4) {   // dense-conv weight gradient: B row = input voxel feeding output voxel v through this tap
+            const int64_t ov = v0 + v;
+            const int ox = (int)(ov % a.d2), oy = (int)((ov / a.d2) % a.d1), oz = (int)(ov / ((int64_t)a.d2 * a.d1));
+            int iz, iy, ix;
+            bool ok = true;
+            if (a.mapB == 4) {
+              iz = oz * a.tstride + a.tz - a.tpad; iy = oy * a.tstride + a.ty - a.tpad; ix = ox * a.tstride + a.tx - a.tpad;
+            } else {
+              const int qz = oz + a.tpad - a.tz, qy = oy + a.tpad - a.ty, qx = ox + a.tpad - a.tx;
+              ok = qz >= 0 && qy >= 0 && qx >= 0 && (qz % a.tstride == 0) && (qy % a.tstride == 0) && (qx % a.tstride == 0);
+              iz = qz / a.tstride; iy = qy / a.tstride; ix = qx / a.tstride;
+            }
+            ok = ok && iz >= 0 && iz < a.bs0 && iy >= 0 && iy < a.bs1 && ix >= 0 && ix < a.bs2;
+            if (!ok) return make_uint4(0, 0, 0, 0);
+            r = ((int64_t)iz * a.bs1 + iy) * a.bs2 + ix;
+          } else {
+            r = map_row(a.mapB, v0 + v, a.d1, a.d2, a.bs1, a.bs2);
+          }
           return __ldg(Bn + r * a.b_pitch8 + (n0 >> 3) + g8);
         },
         [&](int q, const uint4& raw) {
@@ -1367,10 +1386,33 @@ extern "C" int64_t pcb_tn_workspace_floats(int64_t Ma, int64_t Nb, int ones, int
   return (int64_t)tn_num_ctas(ntiles, Mtot, Nc) * Mtot * Nc;
 }
 
+static int tn_gemm_impl(const void* A, const void* B, const double* stats, const float* gamma, const float* beta,
+                        float* workspace, float* dW, int64_t ldm, int64_t ldn, float* db, int64_t N,
+                        const int64_t box[3], int mapA, const int64_t a_size[3], int64_t a_cols, int64_t Ma,
+                        int mapB, const int64_t b_size[3], int64_t Nb, int ones, const int* tap, void* stream);
+
 extern "C" int pcb_tn_gemm(const void* A, const void* B, const double* stats, const float* gamma, const float* beta,
                            float* workspace, float* dW, int64_t ldm, int64_t ldn, float* db, int64_t N,
                            const int64_t box[3], int mapA, const int64_t a_size[3], int64_t a_cols, int64_t Ma,
                            int mapB, const int64_t b_size[3], int64_t Nb, int ones, void* stream) {
+  PCB_CHECK_ARG(mapB >= 0 && mapB <= 3, "pcb_tn_gemm: bad mapB");
+  return tn_gemm_impl(A, B, stats, gamma, beta, workspace, dW, ldm, ldn, db, N, box, mapA, a_size, a_cols, Ma, mapB, b_size, Nb,
+                      ones, nullptr, stream);
+}
+
+extern "C" int pcb_conv_wgrad_tap(const void* dy, const void* x, float* workspace, float* dW, int64_t ldm, int64_t ldn, float* db,
+                                  int64_t N, const int64_t out_size[3], const int64_t in_size[3], int64_t Co, int64_t Ci,
+                                  const int tap[3], int stride, int pad, int transposed, void* stream) {
+  PCB_CHECK_ARG(tap, "pcb_conv_wgrad_tap: null tap");
+  const int t[5] = {tap[0], tap[1], tap[2], stride, pad};
+  return tn_gemm_impl(dy, x, nullptr, nullptr, nullptr, workspace, dW, ldm, ldn, db, N, out_size, MAP_IDENT, out_size, Co, Co,
+                      transposed ? 5 : 4, in_size, Ci, db ? 1 : 0, t, stream);
+}
+
+static int tn_gemm_impl(const void* A, const void* B, const double* stats, const float* gamma, const float* beta,
+                        float* workspace, float* dW, int64_t ldm, int64_t ldn, float* db, int64_t N,
+                        const int64_t box[3], int mapA, const int64_t a_size[3], int64_t a_cols, int64_t Ma,
+                        int mapB, const int64_t b_size[3], int64_t Nb, int ones, const int* tap, void* stream) {
   PCB_CHECK_ARG(A && B && workspace && dW && box && a_size && b_size, "pcb_tn_gemm: null argument");
   PCB_CHECK_ARG(Ma % 16 == 0 && Nb % 16 == 0 && Ma > 0 && Nb > 0 && a_cols >= Ma && a_cols % 8 == 0,
                 "pcb_tn_gemm: Ma/Nb must be positive multiples of 16");
@@ -1383,6 +1425,9 @@ extern "C" int pcb_tn_gemm(const void* A, const void* B, const double* stats, co
   a.Ma = (int)Ma; a.Nb = (int)Nb; a.ones = ones; a.mapA = mapA; a.mapB = mapB;
   a.d1 = (int)box[1]; a.d2 = (int)box[2];
   a.as1 = (int)a_size[1]; a.as2 = (int)a_size[2]; a.bs1 = (int)b_size[1]; a.bs2 = (int)b_size[2];
+  a.bs0 = (int)b_size[0];
+  a.tz = a.ty = a.tx = 0; a.tstride = 1; a.tpad = 0;
+  if (tap) { a.tz = tap[0]; a.ty = tap[1]; a.tx = tap[2]; a.tstride = tap[3]; a.tpad = tap[4]; }
   a.V = box[0] * box[1] * box[2]; a.N = (int)N;
   a.Mtot = (int)((Ma + 127) / 128 * 128); a.Ncols_tot = (int)(Nb + (ones ? 16 : 0));
   a.inv_count = (float)(1.0 / (double)Vb);
@@ -1434,8 +1479,23 @@ extern "C" int pcb_pw_fwd(const void* A, const void* W, const float* bias, void*
   return PCB_OK;
 }
 
+static int gn_bwd_impl(const void* g, const void* y, const double* stats, const double* gstats, const float* gamma,
+                       void* dy, double* dsum, int64_t N, int64_t C, int64_t V, double count, void* stream);
+
 extern "C" int pcb_gn_bwd(const void* g, const void* y, const double* stats, const double* gstats, const float* gamma,
                           void* dy, double* dsum, int64_t N, int64_t C, int64_t V, void* stream) {
+  return gn_bwd_impl(g, y, stats, gstats, gamma, dy, dsum, N, C, V, (double)V, stream);
+}
+
+/* BatchNorm (batch statistics) backward: same formula with statistics pooled over the batch; `stats` / `gstats`
+ * hold the pooled sums replicated for every sample ([N,2,C]) and the element count is N*V. */
+extern "C" int pcb_bn_bwd(const void* g, const void* x, const double* stats, const double* gstats, const float* gamma,
+                          void* dx, double* dsum, int64_t N, int64_t C, int64_t V, void* stream) {
+  return gn_bwd_impl(g, x, stats, gstats, gamma, dx, dsum, N, C, V, (double)(N * V), stream);
+}
+
+static int gn_bwd_impl(const void* g, const void* y, const double* stats, const double* gstats, const float* gamma,
+                       void* dy, double* dsum, int64_t N, int64_t C, int64_t V, double count, void* stream) {
   PCB_CHECK_ARG(g && y && stats && gstats && gamma && dy && dsum, "pcb_gn_bwd: null argument");
   PCB_CHECK_ARG(C % 8 == 0 && C > 0 && V > 0 && N > 0 && N <= 65535, "pcb_gn_bwd: bad shape");
   const int64_t items = V * (C / 8);
@@ -1443,7 +1503,7 @@ extern "C" int pcb_gn_bwd(const void* g, const void* y, const double* stats, con
   if (blocks > 148 * 8) blocks = 148 * 8;
   dim3 grid((unsigned)blocks, (unsigned)N);
   gn_dy_kernel<<<grid, 256, C * sizeof(double) + 5 * C * sizeof(float), (cudaStream_t)stream>>>((const uint4*)g, (const uint4*)y, stats, gstats, gamma,
-                                                                     (uint4*)dy, dsum, (int)C, V, (float)(1.0 / (double)V));
+                                                                     (uint4*)dy, dsum, (int)C, V, (float)(1.0 / count));
   PCB_CHECK_LAUNCH("pcb_gn_bwd");
   return PCB_OK;
 }

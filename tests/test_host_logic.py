@@ -264,3 +264,23 @@ def test_accumulator_reduce_to_root_gloo_world2():
     assert first[1] is None
     assert torch.equal(first[0][0], torch.full((1, 2, 3, 3, 3), 3.0)) and torch.equal(first[0][1], torch.full((1, 1, 3, 3, 3), 1.0))
     assert all(v is True for r, v in got if isinstance(v, (bool, str)))
+
+
+def test_monai_unet_builder_and_state_dict_keys():
+    from oracle.monai_unet_oracle import UNet as OracleUNet
+    cfg = NS(model=NS(arch=NS(type="monai_unet"), in_channels=1, out_channels=1, input_size=[32, 64, 64],
+                      monai=NS(filters=[16, 32, 64], num_res_units=1, kernel_size=3, dropout=0.0)))
+    m = A.build_model(cfg)
+    assert type(m).__name__ == "MONAIModelWrapper" and not m.supports_deep_supervision
+    ref = OracleUNet(3, 1, 1, [16, 32, 64], [2, 2], num_res_units=1)
+    sd_ref, sd = ref.state_dict(), m.model.state_dict()
+    assert list(sd_ref.keys()) == list(sd.keys())
+    assert all(sd_ref[k].shape == sd[k].shape for k in sd_ref)
+    m.model.load_state_dict(sd_ref, strict=True)
+    assert "model.0.conv.unit0.adn.A.weight" in sd and "model.1.submodule.2.0.conv.weight" in sd
+    assert m.get_model_info()["parameters"] == sum(p.numel() for p in ref.parameters())
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 1, 32, 64, 64))
+    cfg.model.monai.norm = "group"
+    with pytest.raises(NotImplementedError):
+        A.build_model(cfg)
