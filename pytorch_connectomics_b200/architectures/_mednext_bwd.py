@@ -34,6 +34,59 @@ ops._PACKERS.setdefault("pw_T", _pack_pw_T)
 ops._PACKERS.setdefault("dw_flip", _pack_dw_flip)
 
 
+import os
+
+_SIDE = {}
+
+
+def _overlap_enabled() -> bool:
+    return os.environ.get("PCB_BWD_OVERLAP", "1") != "0"
+
+
+class _Side:
+    """Runs weight-gradient kernels (off the data-gradient critical path) on a second stream.
+
+    ``fork()`` makes the side stream wait for everything enqueued so far on the main stream; work launched
+    inside ``with side:`` goes to the side stream (``L.stream_ptr`` follows torch's current stream);
+    ``join()`` makes the main stream wait for the side stream before the gradients are handed to autograd.
+    Tensors that were allocated on the main stream and are read on the side stream are registered with
+    ``record_stream`` so the caching allocator does not recycle them early."""
+
+    def __init__(self, device):
+        self.device = device
+        self.main = torch.cuda.current_stream(device)
+        self.enabled = _overlap_enabled()
+        if self.enabled:
+            key = (device.index if device.index is not None else torch.cuda.current_device())
+            if key not in _SIDE:
+                _SIDE[key] = torch.cuda.Stream(device=device)
+            self.stream = _SIDE[key]
+        self.used = False
+
+    def fork(self, *tensors):
+        if self.enabled:
+            self.stream.wait_stream(self.main)
+            for t in tensors:
+                if t is not None:
+                    t.record_stream(self.stream)
+            self.used = True
+
+    def __enter__(self):
+        if self.enabled:
+            self._ctx = torch.cuda.stream(self.stream)
+            self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.enabled:
+            self._ctx.__exit__(*exc)
+        return False
+
+    def join(self):
+        if self.enabled and self.used:
+            self.main.wait_stream(self.stream)
+
+
 def _cl_grad(g: torch.Tensor) -> torch.Tensor:
     g = g.contiguous()
     return g if g.dtype == _BF16 else g.to(_BF16)
@@ -75,6 +128,7 @@ class BlockFn(torch.autograd.Function):
         h, co = int(w2.shape[0]), int(w3.shape[0])
         vy = ysize[0] * ysize[1] * ysize[2]
         g_f32, b_f32 = ops.packed(gamma, "f32"), ops.packed(beta, "f32")
+        side = _Side(dev)
 
         dyhat = torch.empty((n, *ysize, c), device=dev, dtype=_BF16)
         gstats = torch.zeros((n, 2, c), device=dev, dtype=torch.float64)
@@ -101,10 +155,13 @@ class BlockFn(torch.autograd.Function):
                 L.check(lib.pcb_mlp_bwd(*common, L.ptr(hact), L.ptr(dh), L.ptr(dyhat), L.ptr(gstats), ctypes.c_int64(n),
                                         L.i64x(ysize), ctypes.c_int64(c), ctypes.c_int64(h), ctypes.c_int64(co), mode, st),
                         "pcb_mlp_bwd")
-            # pointwise weight gradients (+ bias gradients through the all-ones column)
-            _tn(dout, hact, None, None, None, dw3, h, 1, db3, n, ysize, MAP_PLUS1 if mode == L.DW_UP else MAP_IDENT,
-                osize, co, co, MAP_IDENT, ysize, h, st)
-            _tn(dh, y, stats, g_f32, b_f32, dw2, c, 1, db2, n, ysize, MAP_IDENT, ysize, h, h, MAP_IDENT, ysize, c, st)
+            # pointwise weight gradients (+ bias gradients through the all-ones column) — side stream
+            side.fork(dout, hact, dh, y, stats, dw3, db3, dw2, db2)
+            with side:
+                sst = L.stream_ptr(dev)
+                _tn(dout, hact, None, None, None, dw3, h, 1, db3, n, ysize, MAP_PLUS1 if mode == L.DW_UP else MAP_IDENT,
+                    osize, co, co, MAP_IDENT, ysize, h, sst)
+                _tn(dh, y, stats, g_f32, b_f32, dw2, c, 1, db2, n, ysize, MAP_IDENT, ysize, h, h, MAP_IDENT, ysize, c, sst)
             del hact, dh
         # ---- GroupNorm backward
         dy = torch.empty_like(y)
@@ -115,15 +172,17 @@ class BlockFn(torch.autograd.Function):
         dgamma = gstats[:, 1].sum(0).float()
         dbeta = gstats[:, 0].sum(0).float()
         del dyhat
-        # ---- depthwise weight gradient
+        # ---- depthwise weight gradient (side stream: only needs dy and x)
         dw1 = torch.zeros((k * k * k, c), device=dev, dtype=torch.float64)
         if mode == L.DW_UP:
             cen, nei, csz, nsz, stride = x, dy, xsize, ysize, 2
         else:
             cen, nei, csz, nsz, stride = dy, x, ysize, xsize, (2 if mode == L.DW_DOWN else 1)
-        with L.prof(f"dw_wgrad:m{mode}C{c}V{vy}"):
-          L.check(lib.pcb_dwconv_wgrad(L.ptr(cen), L.ptr(nei), L.ptr(dw1), ctypes.c_int64(n), L.i64x(csz), L.i64x(nsz),
-                                       ctypes.c_int64(c), k, stride, st), "pcb_dwconv_wgrad")
+        side.fork(dy, x, dw1, dout)
+        with side:
+            with L.prof(f"dw_wgrad:m{mode}C{c}V{vy}"):
+                L.check(lib.pcb_dwconv_wgrad(L.ptr(cen), L.ptr(nei), L.ptr(dw1), ctypes.c_int64(n), L.i64x(csz), L.i64x(nsz),
+                                             ctypes.c_int64(c), k, stride, L.stream_ptr(dev)), "pcb_dwconv_wgrad")
         grads_rc: List[Optional[torch.Tensor]] = []
         add, add_mode = None, 0
         if has_rc:
@@ -134,7 +193,10 @@ class BlockFn(torch.autograd.Function):
                                        L.i64x(osize), MAP_IDENT, L.i64x(osize), ctypes.c_int64(co), ctypes.c_int64(c), st),
                         "pcb_pw_fwd")
                 dwr = torch.empty((co, c), device=dev, dtype=torch.float32)
-                _tn(dout, x, None, None, None, dwr, c, 1, None, n, osize, MAP_IDENT, osize, co, co, MAP_TIMES2, xsize, c, st)
+                dwr.record_stream(side.stream) if side.enabled else None
+                with side:
+                    _tn(dout, x, None, None, None, dwr, c, 1, None, n, osize, MAP_IDENT, osize, co, co, MAP_TIMES2, xsize, c,
+                        L.stream_ptr(dev))
                 add, add_mode = r, 2
             else:                   # ConvTranspose3d(C, Co, 1, stride 2): weight [C, Co]
                 r = torch.empty((n, *xsize, c), device=dev, dtype=_BF16)
@@ -142,9 +204,11 @@ class BlockFn(torch.autograd.Function):
                                        L.i64x(xsize), MAP_TIMES2P1, L.i64x(osize), ctypes.c_int64(co), ctypes.c_int64(c), st),
                         "pcb_pw_fwd")
                 dwr = torch.empty((c, co), device=dev, dtype=torch.float32)
-                _tn(dout, x, None, None, None, dwr, 1, co, None, n, xsize, MAP_TIMES2P1, osize, co, co, MAP_IDENT, xsize, c, st)
+                dwr.record_stream(side.stream) if side.enabled else None
+                with side:
+                    _tn(dout, x, None, None, None, dwr, 1, co, None, n, xsize, MAP_TIMES2P1, osize, co, co, MAP_IDENT, xsize, c,
+                        L.stream_ptr(dev))
                 add, add_mode = r, 1
-            grads_rc = [dwr.reshape(params[8].shape), db3.clone()]
         elif mode == L.DW_SAME and do_res:
             add, add_mode = dout, 1
         # ---- depthwise data gradient (+ residual / res-conv gradient)
@@ -157,6 +221,9 @@ class BlockFn(torch.autograd.Function):
                                               L.i64x(ysize), L.i64x(xsize), ctypes.c_int64(c), k, mode, st),
                       "pcb_dwconv_bwd_data")
         dskip = dout if (has_skip and ctx.needs_input_grad[1]) else None
+        side.join()   # weight gradients are complete before autograd accumulates them on the main stream
+        if has_rc:
+            grads_rc = [dwr.reshape(params[8].shape), db3.clone()]
         grads = [dw1.t().reshape(w1.shape).float(), db1.float(), dgamma, dbeta,
                  dw2.reshape(w2.shape), db2, dw3.reshape(w3.shape), db3] + grads_rc
         return (dx, dskip, None, None, None, None, *grads)
