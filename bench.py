@@ -5,9 +5,9 @@
     python bench.py --impl reference --steps K --warmup W    # reference CPU arm (oracle port)
     python bench.py --mode infer ...                         # sliding-window inference workload
 
-Workload (BASELINE.json configs[1]): MedNeXt-S, 1-channel 160^3 crops, bf16 compute, per-GPU batch 1,
+Workload (BASELINE.json configs[1]): MedNeXt-S, 1-channel 160^3 crops, bf16 compute, per-GPU batch 4 (--batch),
 BCE-with-logits + Dice loss, AdamW(lr 1e-3, wd 0.01) — one "step" = forward + loss + backward + gradient
-all-reduce (N>1) + optimizer step on one synthetic sub-volume per GPU.  `value` = sub-volumes/s over all
+all-reduce (N>1) + optimizer step on one synthetic batch per GPU.  `value` = sub-volumes/s over all
 ranks with inputs resident in HBM; `e2e` = the same step through the public API with the batch copied from
 pinned host memory every step and the loss read back.  Inputs are regenerated (different tensors) each step
 and each step touches >1 GB of activations, far beyond the 126 MB L2, so no explicit L2 flush is needed.
@@ -162,7 +162,7 @@ def run_reference(a):
 
 def workload_config(a, world):
     if a.mode == "train":
-        return {"workload": f"MedNeXt-S k3 train step, 1x1x{SIDE}^3 crop per GPU, BCE+Dice, AdamW (BASELINE configs[1])",
+        return {"workload": f"MedNeXt-S k3 train step, {a.batch}x1x{SIDE}^3 crops per GPU, BCE+Dice, AdamW (BASELINE configs[1])",
                 "global_batch": world * a.batch, "crop": [SIDE] * 3, "parallelism": f"dp{world}",
                 "l2": "inputs+activations >> 126 MB L2 per step (no explicit flush)"}
     return {"workload": f"MedNeXt-S sliding-window inference, {a.volume}^3 volume per GPU, {SIDE}^3 tiles, 50% overlap, bump",
@@ -244,7 +244,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="pcb200", choices=["pcb200", "reference"])
     ap.add_argument("--mode", default="train", choices=["train", "infer"])
-    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--batch", type=int, default=4, help="sub-volumes per GPU per step (tutorials/mito_lucchi++ trains with 4)")
     ap.add_argument("--volume", type=int, default=480)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-ops", action="store_true", help="time every pcb200 op with CUDA events (stderr table)")
