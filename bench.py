@@ -183,8 +183,10 @@ KERNELS = {
     "tn_gemm": "pcb::tn_gemm_kernel (split-K wgrad GEMM, tcgen05 MN-major)",
     "gn_bwd": "pcb::gn_dy_kernel (GroupNorm backward)",
 }
-NCU_TRAFFIC = {  # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures in profiles/
-    "mlp_fwd:m0C32H64Co32V4096000": 524441344 + 234754048,     # profiles/r01_mlp_fused_l0_final.ncu-rep
+NCU_TRAFFIC = {  # dram__bytes_read.sum + dram__bytes_write.sum PER SAMPLE (captures at batch 1, profiles/*.ncu-rep)
+    "mlp_fwd:m0C32H64Co32V4096000": 524441344 + 234754048,     # r01_mlp_fused_l0_final.ncu-rep
+    "mlp_fwd:m2C64H128Co32V4096000": 843630080 + 245193984,    # r01_mlp_fused_up0.ncu-rep
+    "mlp_bwd_fused:m2C64H128Co32V4019679": 773626624 + 480401664,   # r01_mlp_bwd_fused_up0.ncu-rep
 }
 
 
@@ -224,7 +226,7 @@ def build_roofline(prof, a, peak_gbs, measured, step_ms, nsteps):
         nbytes = _op_bytes(op, key, batch)
         ach = nbytes / (avg_ms / 1e3) / 1e9 if nbytes else None
         rows.append({"kernel": KERNELS.get(op, op), "launch_class": key, "bound": "hbm", "achieved": ach, "peak": peak_gbs,
-                     "unit": "GB/s", "frac": (ach / peak_gbs) if ach else None, "traffic": NCU_TRAFFIC.get(key),
+                     "unit": "GB/s", "frac": (ach / peak_gbs) if ach else None, "traffic": (NCU_TRAFFIC[key] * batch) if key in NCU_TRAFFIC else None,
                      "avg_launch_ms": avg_ms, "launches_timed": len(dts), "algorithmic_bytes": nbytes,
                      "op_ms_per_step": g["ms"], "share_of_step": g["ms"] / step_ms})
     roof = dict(rows[0])
