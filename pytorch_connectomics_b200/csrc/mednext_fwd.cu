@@ -638,6 +638,7 @@ struct MlpFusedArgs {
   MlpArgs m;
   int N;             // samples
   int nst;           // A-tile stages (4: one loader warp per stage; 2: two warps per stage)
+  int nsx;           // xs-tile stages (<= nst)
   int64_t tps;       // tiles per sample
   int64_t ntiles;    // N * tps
 };
@@ -670,13 +671,14 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_fused_kernel(MlpFusedArgs f
   const int c8n = a.C >> 3, h8n = a.H >> 3, r8n = a.Cr >> 3;
   const bool has_rc = a.wr != nullptr;
   const int NST = fa.nst;   // A-tile stages (4 or 2)
+  const int NSX = fa.nsx;   // res-conv source (xs) tile stages: NST, or 2 when shared memory is short
   // ---- shared memory carve-up (all operand tiles in the K-major no-swizzle canonical layout)
   uint8_t* sW2 = smem;                                   // [H x C]
   uint8_t* sW3 = sW2 + a.H * a.C * 2;                    // [Co x H]
   uint8_t* sWr = sW3 + a.Co * a.H * 2;                   // [Co x Cr]
   uint8_t* sA = sWr + (has_rc ? a.Co * a.Cr * 2 : 0);    // NST x [128 x C]
-  uint8_t* sX = sA + NST * 128 * a.C * 2;                // NST x [128 x Cr]
-  uint8_t* sH = sX + (has_rc ? NST * 128 * a.Cr * 2 : 0);   // 2 x [128 x H]
+  uint8_t* sX = sA + NST * 128 * a.C * 2;                // NSX x [128 x Cr]
+  uint8_t* sH = sX + (has_rc ? NSX * 128 * a.Cr * 2 : 0);   // 2 x [128 x H]
   float* sScale = reinterpret_cast<float*>(sH + 2 * 128 * a.H * 2);   // [N][C]
   float* sShift = sScale + fa.N * a.C;                   // [N][C]
   float* sB2 = sShift + fa.N * a.C;                      // [H]
@@ -793,7 +795,14 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_fused_kernel(MlpFusedArgs f
           });
       if (has_rc) {
         const uint4* xn = a.xs + (int64_t)n * a.Vin * r8n;
-        uint8_t* dX = sX + grp * 128 * a.Cr * 2;
+        const int sx = (int)(it % NSX);
+        // with fewer xs stages than A stages the slot was last used NSX tiles ago: its res-GEMM (second half of
+        // that tile, committed on that tile's a_empty barrier) must have retired before it is overwritten
+        if (NSX < NST && it >= NSX) {
+          const int64_t jt = it - NSX;
+          mbar_wait(&a_empty[jt % NST], (uint32_t)((jt / NST) & 1));
+        }
+        uint8_t* dX = sX + sx * 128 * a.Cr * 2;
         staged_copy<8>(128 * r8n, lt, nthr,
             [&](int q) {
               const int r = rpow2 ? (q >> rsh) : (q / r8n), c8 = q - r * r8n;
@@ -824,7 +833,7 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_fused_kernel(MlpFusedArgs f
         const uint64_t dH = umma_desc(smem_u32(sH + gj * 128 * a.H * 2), 128, h8n * 128);
         for (int k = 0; k < a.H / 16; ++k) umma_bf16(acc2, dH + (uint64_t)(k * 16), dW3 + (uint64_t)(k * 16), idesc2, k > 0 ? 1u : 0u);
         if (has_rc) {
-          const uint64_t dX = umma_desc(smem_u32(sX + sj * 128 * a.Cr * 2), 128, r8n * 128);
+          const uint64_t dX = umma_desc(smem_u32(sX + (int)(j % NSX) * 128 * a.Cr * 2), 128, r8n * 128);
           for (int k = 0; k < a.Cr / 16; ++k) umma_bf16(acc2, dX + (uint64_t)(k * 16), dWr + (uint64_t)(k * 16), idesc2, 1u);
         }
         tc_commit(&acc2_full[gj]);
@@ -941,10 +950,10 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_fused_kernel(MlpFusedArgs f
   if (warp == MF_LOAD_WARPS + MF_EPI_WARPS) tmem_dealloc(tmem_base, tmem_cols);
 }
 
-static size_t mlp_fused_smem(const MlpArgs& a, int N, int nst) {
+static size_t mlp_fused_smem(const MlpArgs& a, int N, int nst, int nsx) {
   const bool rc = a.wr != nullptr;
   return (size_t)a.H * a.C * 2 + (size_t)a.Co * a.H * 2 + (rc ? (size_t)a.Co * a.Cr * 2 : 0) + (size_t)nst * 128 * a.C * 2 +
-         (rc ? (size_t)nst * 128 * a.Cr * 2 : 0) + (size_t)2 * 128 * a.H * 2 + (size_t)2 * N * a.C * 4 + (size_t)(a.H + a.Co) * 4 +
+         (rc ? (size_t)nsx * 128 * a.Cr * 2 : 0) + (size_t)2 * 128 * a.H * 2 + (size_t)2 * N * a.C * 4 + (size_t)(a.H + a.Co) * 4 +
          4 * 2 * 128 * 4 + 16 * 8 + 16 + 128;
 }
 
@@ -1127,9 +1136,10 @@ extern "C" int pcb_mlp_fwd(const void* y, const double* stats, const float* gamm
   }
   // top levels: persistent warp-specialised kernel (weights resident, single K / hidden chunk)
   {
-    int nst = 4;
-    size_t fsm = mlp_fused_smem(a, (int)N, nst);
-    if (fsm > 227 * 1024) { nst = 2; fsm = mlp_fused_smem(a, (int)N, nst); }
+    int nst = 4, nsx = 4;
+    size_t fsm = mlp_fused_smem(a, (int)N, nst, nsx);
+    if (fsm > 227 * 1024) { nsx = 2; fsm = mlp_fused_smem(a, (int)N, nst, nsx); }     // 4 A stages, 2 xs stages
+    if (fsm > 227 * 1024) { nst = 2; fsm = mlp_fused_smem(a, (int)N, nst, nsx); }
     const bool pow2 = ((C & (C - 1)) == 0) && ((H & (H - 1)) == 0 || true);
     if (getenv("PCB_NO_FUSED") == nullptr && C <= 64 && H <= 256 && Co <= 128 && (!wr || Cr <= 64) && 2 * (H + Co) <= 512 &&
         N <= 8 && fsm <= 227 * 1024 && pow2 && a.Vout < (1ll << 30) && a.Vin < (1ll << 30)) {
@@ -1142,7 +1152,7 @@ extern "C" int pcb_mlp_fwd(const void* y, const double* stats, const float* gamm
         fconf = true;
       }
       MlpFusedArgs fa;
-      fa.m = a; fa.N = (int)N; fa.nst = nst; fa.tps = (a.Vout + 127) / 128; fa.ntiles = fa.tps * N;
+      fa.m = a; fa.N = (int)N; fa.nst = nst; fa.nsx = nsx; fa.tps = (a.Vout + 127) / 128; fa.ntiles = fa.tps * N;
       int ctas = 148;
       if (fa.ntiles < ctas) ctas = (int)fa.ntiles;
       mlp_fused_kernel<<<ctas, MF_THREADS, fsm, (cudaStream_t)stream>>>(fa);
