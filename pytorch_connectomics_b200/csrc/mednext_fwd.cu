@@ -641,7 +641,15 @@ struct MlpFusedArgs {
   int nsx;           // xs-tile stages (<= nst)
   int64_t tps;       // tiles per sample
   int64_t ntiles;    // N * tps
+  int fast;          // warp-per-tile register loader (C, Cr in {32, 64}; nst == 4)
+  uint32_t dm2, dm1; // magic multipliers of the exact division by o2 / o1 (n < 2^31):  n / d == (n * dm) >> ds
+  int ds2, ds1;
 };
+
+// exact n / d for 0 <= n < 2^31 with m = ceil(2^(31+l) / d), l = ceil(log2 d), shift = 31 + l (host: mf_magic)
+__device__ __forceinline__ int mf_fdiv(int n, uint32_t m, int sh) {
+  return (int)(((uint64_t)(uint32_t)n * (uint64_t)m) >> sh);
+}
 
 constexpr int MF_LOAD_WARPS = 4, MF_EPI_WARPS = 8, MF_THREADS = 32 * (MF_LOAD_WARPS + MF_EPI_WARPS + 1);
 
@@ -661,6 +669,83 @@ __device__ __forceinline__ void mf_row_sources(const MlpArgs& a, int ov, int& ry
     rx = ((2 * oz) * a.x1 + 2 * oy) * a.x2 + 2 * ox;
   } else {
     ry = ov;
+  }
+}
+
+// row sources of output voxel ov with the two divisions done by multiplication (same result as mf_row_sources)
+__device__ __forceinline__ void mf_row_sources_fast(const MlpFusedArgs& fa, int ov, int& ry, int& rx) {
+  const MlpArgs& a = fa.m;
+  ry = -1; rx = -1;
+  if (ov >= (int)a.Vout) return;
+  if (a.mode == PCB_DW_SAME) { ry = ov; return; }
+  const int t = mf_fdiv(ov, fa.dm2, fa.ds2), ox = ov - t * a.o2;
+  const int oz = mf_fdiv(t, fa.dm1, fa.ds1), oy = t - oz * a.o1;
+  if (a.mode == PCB_DW_UP) {
+    if (ox >= 1 && oy >= 1 && oz >= 1) {
+      ry = ((oz - 1) * (a.o1 - 1) + (oy - 1)) * (a.o2 - 1) + (ox - 1);
+      if (!(((ox - 1) | (oy - 1) | (oz - 1)) & 1))
+        rx = (((oz - 1) >> 1) * a.x1 + ((oy - 1) >> 1)) * a.x2 + ((ox - 1) >> 1);
+    }
+  } else {
+    ry = ov;
+    rx = ((2 * oz) * a.x1 + 2 * oy) * a.x2 + 2 * ox;
+  }
+}
+
+// One warp stages a [128 x 8*C8N] bf16 tile into the K-major canonical layout.  lane = (chunk slot, row inside
+// the 8-row core matrix): the 8 lanes of a quarter-warp fill one 128-byte core matrix per 128-bit shared store
+// (conflict-free) and every global request covers whole 32-byte sectors.  The lane's channels are fixed, so the
+// GroupNorm affine (NORM) stays in registers for the tile.  TAB: row sources come from `tab` (-1 = zero row),
+// otherwise rows row0 .. row0+nvalid-1 are read in order.  8 loads are in flight per lane before the first store.
+template <int C8N, bool NORM, bool TAB>
+__device__ __forceinline__ void mf_stage_tile(uint8_t* __restrict__ dst, const uint4* __restrict__ src,
+                                              const int* __restrict__ tab, int row0, int nvalid,
+                                              const float* __restrict__ sc, const float* __restrict__ sh, int lane) {
+  static_assert(C8N == 4 || C8N == 8, "C8N");
+  constexpr int J = C8N / 4;      // chunks per lane per row group
+  constexpr int RGB = 8 / J;      // row groups per batch of 8 loads
+  const int rl = lane & 7, cs = lane >> 3;
+  uint64_t ps[J][4], pt[J][4];
+  if (NORM) {
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const float4* sp = reinterpret_cast<const float4*>(sc + (cs + 4 * j) * 8);
+      const float4* tp = reinterpret_cast<const float4*>(sh + (cs + 4 * j) * 8);
+      const float4 s0 = sp[0], s1 = sp[1], t0 = tp[0], t1 = tp[1];
+      ps[j][0] = pk2(s0.x, s0.y); ps[j][1] = pk2(s0.z, s0.w); ps[j][2] = pk2(s1.x, s1.y); ps[j][3] = pk2(s1.z, s1.w);
+      pt[j][0] = pk2(t0.x, t0.y); pt[j][1] = pk2(t0.z, t0.w); pt[j][2] = pk2(t1.x, t1.y); pt[j][3] = pk2(t1.z, t1.w);
+    }
+  }
+  uint8_t* dl = dst + cs * 128 + rl * 16;
+#pragma unroll 1
+  for (int b = 0; b < 16 / RGB; ++b) {
+    uint4 v[8];
+    uint32_t ok = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int rg = b * RGB + k / J, j = k % J;
+      const int r = rg * 8 + rl;
+      int ry;
+      if (TAB) ry = tab[r]; else ry = r < nvalid ? row0 + r : -1;
+      v[k] = make_uint4(0, 0, 0, 0);
+      if (ry >= 0) { v[k] = __ldg(src + (int64_t)ry * C8N + (cs + 4 * j)); ok |= 1u << k; }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int rg = b * RGB + k / J, j = k % J;
+      uint4 o = v[k];
+      if (NORM) {
+        const bool live = (ok >> k) & 1u;
+        float a0, a1, a2, a3, a4, a5, a6, a7;
+        upk2(fma2(pk2(bf16_lo(o.x), bf16_hi(o.x)), ps[j][0], pt[j][0]), a0, a1);
+        upk2(fma2(pk2(bf16_lo(o.y), bf16_hi(o.y)), ps[j][1], pt[j][1]), a2, a3);
+        upk2(fma2(pk2(bf16_lo(o.z), bf16_hi(o.z)), ps[j][2], pt[j][2]), a4, a5);
+        upk2(fma2(pk2(bf16_lo(o.w), bf16_hi(o.w)), ps[j][3], pt[j][3]), a6, a7);
+        o.x = live ? pack_bf16(a0, a1) : 0u; o.y = live ? pack_bf16(a2, a3) : 0u;
+        o.z = live ? pack_bf16(a4, a5) : 0u; o.w = live ? pack_bf16(a6, a7) : 0u;
+      }
+      *reinterpret_cast<uint4*>(dl + rg * (C8N * 128) + j * 512) = o;
+    }
   }
 }
 
@@ -755,6 +840,50 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_fused_kernel(MlpFusedArgs f
     int* rowY = sRow + grp * 256;
     int* rowX = rowY + 128;
     int64_t it = grp;
+    if (fa.fast) {
+      // ---- warp-per-tile register loader (NST == 4): warp w owns stage w and the tiles  it == w (mod 4)
+      const bool tabY = a.mode == PCB_DW_UP;
+      int uses = 0;
+      for (int64_t g = blockIdx.x + (int64_t)warp * gridDim.x; g < fa.ntiles; g += 4ll * gridDim.x, it += 4, ++uses) {
+        if (uses >= 1) mbar_wait(&a_empty[warp], (uint32_t)((uses - 1) & 1));
+        const int n = (int)(g / fa.tps);
+        const int tile0 = (int)((g - (int64_t)n * fa.tps) * 128);
+        const int nvalid = min(128, (int)a.Vout - tile0);
+        if (tabY || has_rc) {
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            int ry, rx;
+            mf_row_sources_fast(fa, tile0 + lane + 32 * k, ry, rx);
+            rowY[lane + 32 * k] = ry; rowX[lane + 32 * k] = rx;
+          }
+          __syncwarp();
+        }
+        const uint4* yn = a.y + (int64_t)n * a.Vy * c8n;
+        const float* sc = sScale + n * a.C;
+        const float* sh = sShift + n * a.C;
+        uint8_t* dA = sA + warp * 128 * a.C * 2;
+        if (c8n == 8) {
+          if (tabY) mf_stage_tile<8, true, true>(dA, yn, rowY, tile0, nvalid, sc, sh, lane);
+          else mf_stage_tile<8, true, false>(dA, yn, rowY, tile0, nvalid, sc, sh, lane);
+        } else {
+          if (tabY) mf_stage_tile<4, true, true>(dA, yn, rowY, tile0, nvalid, sc, sh, lane);
+          else mf_stage_tile<4, true, false>(dA, yn, rowY, tile0, nvalid, sc, sh, lane);
+        }
+        if (has_rc) {
+          const uint4* xn = a.xs + (int64_t)n * a.Vin * r8n;
+          if (NSX < 4 && it >= NSX) {                 // see the generic loader below
+            const int64_t jt = it - NSX;
+            mbar_wait(&a_empty[jt & 3], (uint32_t)((jt >> 2) & 1));
+          }
+          uint8_t* dX = sX + (int)(it % NSX) * 128 * a.Cr * 2;
+          if (r8n == 8) mf_stage_tile<8, false, true>(dX, xn, rowX, 0, 0, nullptr, nullptr, lane);
+          else mf_stage_tile<4, false, true>(dX, xn, rowX, 0, 0, nullptr, nullptr, lane);
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&a_full[warp]);
+      }
+    } else
     for (int64_t g = blockIdx.x + (int64_t)grp * gridDim.x; g < fa.ntiles; g += (int64_t)NST * gridDim.x, it += NST) {
       const int64_t use = it / NST;                  // how many times this stage has been filled before
       if (use >= 1) mbar_wait(&a_empty[grp], (uint32_t)((use - 1) & 1));
@@ -948,6 +1077,15 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_fused_kernel(MlpFusedArgs f
   tc_fence_before();
   __syncthreads();
   if (warp == MF_LOAD_WARPS + MF_EPI_WARPS) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// magic numbers of mf_fdiv: l = ceil(log2 d), m = ceil(2^(31+l) / d) (< 2^32), shift = 31 + l
+static void mf_magic(uint32_t d, uint32_t& m, int& sh) {
+  int l = 0;
+  while ((1ull << l) < d) ++l;
+  const unsigned __int128 p = (unsigned __int128)1 << (31 + l);
+  m = (uint32_t)((p + d - 1) / d);
+  sh = 31 + l;
 }
 
 static size_t mlp_fused_smem(const MlpArgs& a, int N, int nst, int nsx) {
@@ -1153,6 +1291,9 @@ extern "C" int pcb_mlp_fwd(const void* y, const double* stats, const float* gamm
       }
       MlpFusedArgs fa;
       fa.m = a; fa.N = (int)N; fa.nst = nst; fa.nsx = nsx; fa.tps = (a.Vout + 127) / 128; fa.ntiles = fa.tps * N;
+      fa.fast = nst == 4 && (C == 32 || C == 64) && (!wr || Cr == 32 || Cr == 64) && getenv("PCB_OLD_LOADER") == nullptr;
+      mf_magic((uint32_t)(a.o2 > 0 ? a.o2 : 1), fa.dm2, fa.ds2);
+      mf_magic((uint32_t)(a.o1 > 0 ? a.o1 : 1), fa.dm1, fa.ds1);
       int ctas = 148;
       if (fa.ntiles < ctas) ctas = (int)fa.ntiles;
       mlp_fused_kernel<<<ctas, MF_THREADS, fsm, (cudaStream_t)stream>>>(fa);
