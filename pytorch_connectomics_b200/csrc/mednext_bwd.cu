@@ -16,6 +16,7 @@
 //   head_bwd / stem_bwd kernels (CUDA cores; tiny channel counts on one side)
 #include "../../include/pcb200.h"
 #include <stdlib.h>
+#include <string.h>
 
 #include "pcb_common.cuh"
 
@@ -1019,14 +1020,17 @@ constexpr int WT_Z = 4, WT_Y = 8, WT_X = 16;
 template <int K>
 __global__ void __launch_bounds__(256, 2) dw_wgrad_same_tiled_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x,
                                                                   double* __restrict__ dW, int D, int H, int W, int C,
-                                                                  int tiles_y, int tiles_x, int nbricks, int N) {
+                                                                  int tiles_y, int tiles_x, int nbricks, int N,
+                                                                  const __grid_constant__ CUtensorMap tmap_x,
+                                                                  const __grid_constant__ CUtensorMap tmap_dy, int use_tma) {
   constexpr int P = K / 2;
   constexpr int BZ = WT_Z + 2 * P, BY = WT_Y + 2 * P, BX = WT_X + 2 * P, PITCH = BX + 1;
   constexpr int NPART = 256 / (K * K * 4);      // row partitions (threads beyond K*K*4*NPART idle)
-  extern __shared__ __align__(16) uint8_t dsm[];
+  extern __shared__ __align__(128) uint8_t dsm[];
   uint4* s_x = reinterpret_cast<uint4*>(dsm);                      // [BZ][BY][PITCH][4]
   uint4* s_dy = s_x + BZ * BY * PITCH * 4;                         // [WT_Z][WT_Y][WT_X][4]
   double* s_red = reinterpret_cast<double*>(s_dy + WT_Z * WT_Y * WT_X * 4);   // [K^3][32]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_red + K * K * K * 32);      // TMA completion barrier
   const int tid = threadIdx.x, CH = C >> 3, cg = blockIdx.y;
   const int cc = tid & 3, tr = (tid >> 2) % (K * K), part = (tid >> 2) / (K * K);
   const int dz = tr / K, dyy = tr % K;
@@ -1037,6 +1041,8 @@ __global__ void __launch_bounds__(256, 2) dw_wgrad_same_tiled_kernel(const uint4
 #pragma unroll
     for (int c = 0; c < 4; ++c) acc[k][c] = 0ull;
   for (int i = tid; i < K * K * K * 32; i += 256) s_red[i] = 0.0;
+  if (use_tma && tid == 0) { mbar_init(s_bar, 1); fence_mbar_init(); fence_proxy_async_smem(); }
+  uint32_t tma_phase = 0;
 
   for (int b = blockIdx.x; b < nbricks * N; b += gridDim.x) {
     const int n = b / nbricks;
@@ -1047,6 +1053,16 @@ __global__ void __launch_bounds__(256, 2) dw_wgrad_same_tiled_kernel(const uint4
     const uint4* xn = x + (int64_t)n * D * H * W * CH + cg * 4;
     const uint4* dn = dy + (int64_t)n * D * H * W * CH + cg * 4;
     __syncthreads();   // previous brick fully consumed
+    if (use_tma) {
+      // both bricks arrive as bulk tensor copies (zero fill outside the volume) on one mbarrier
+      if (tid == 0) {
+        mbar_arrive_expect_tx(s_bar, (uint32_t)(BZ * BY * PITCH * 64 + WT_Z * WT_Y * WT_X * 64));
+        tma_load_5d(s_x, &tmap_x, cg * 32, x0 - P, y0 - P, z0 - P, n, s_bar);
+        tma_load_5d(s_dy, &tmap_dy, cg * 32, x0, y0, z0, n, s_bar);
+      }
+      mbar_wait(s_bar, tma_phase);
+      tma_phase ^= 1;
+    } else {
     staged_copy<((BZ * BY * BX * 4 + 255) / 256 <= 17 ? (BZ * BY * BX * 4 + 255) / 256 : 8)>(BZ * BY * BX * 4, tid, 256,
         [&](int q) {
           const int c4 = q & 3, v = q >> 2;
@@ -1069,6 +1085,7 @@ __global__ void __launch_bounds__(256, 2) dw_wgrad_same_tiled_kernel(const uint4
           return __ldg(dn + (((int64_t)gz * H + gy) * W + gx) * CH + c4);
         },
         [&](int q, const uint4& v4) { s_dy[q] = v4; });
+    }
     __syncthreads();
     if (worker) {
       for (int r = part; r < WT_Z * WT_Y; r += NPART) {     // (z,y) rows of the brick owned by this partition
@@ -1123,8 +1140,13 @@ template <int K>
 static bool launch_dw_wgrad_tiled(cudaStream_t st, const uint4* dy, const uint4* x, double* dW, int D, int H, int W, int C, int N) {
   constexpr int P = K / 2;
   const size_t smem = (size_t)(WT_Z + 2 * P) * (WT_Y + 2 * P) * (WT_X + 2 * P + 1) * 64 + (size_t)WT_Z * WT_Y * WT_X * 64 +
-                      (size_t)K * K * K * 32 * 8;
+                      (size_t)K * K * K * 32 * 8 + 16;
   if (smem > 227 * 1024) return false;
+  CUtensorMap tmx, tmd;
+  memset(&tmx, 0, sizeof(tmx)); memset(&tmd, 0, sizeof(tmd));
+  static const bool no_tma = getenv("PCB_NO_TMA") != nullptr;
+  const int use_tma = !no_tma && make_brick_tensor_map(&tmx, x, N, D, H, W, C, WT_Z + 2 * P, WT_Y + 2 * P, WT_X + 2 * P + 1) &&
+                      make_brick_tensor_map(&tmd, dy, N, D, H, W, C, WT_Z, WT_Y, WT_X);
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(dw_wgrad_same_tiled_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -1140,7 +1162,7 @@ static bool launch_dw_wgrad_tiled(cudaStream_t st, const uint4* dy, const uint4*
   int ctas = 148 * 2;
   if (nb * N < ctas) ctas = (int)(nb * N);
   dim3 grid((unsigned)ctas, (unsigned)(C / 32));
-  dw_wgrad_same_tiled_kernel<K><<<grid, 256, smem, st>>>(dy, x, dW, D, H, W, C, ty, tx, (int)nb, N);
+  dw_wgrad_same_tiled_kernel<K><<<grid, 256, smem, st>>>(dy, x, dW, D, H, W, C, ty, tx, (int)nb, N, tmx, tmd, use_tma);
   return true;
 }
 

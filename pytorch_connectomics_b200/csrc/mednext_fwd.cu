@@ -14,6 +14,7 @@
 //   head_kernel      OutBlock 1x1x1 (C -> ncls), NDHWC bf16 -> NCDHW(any dtype)  (HBM-bound)
 #include "../../include/pcb200.h"
 #include <stdlib.h>
+#include <string.h>
 
 #include "pcb_common.cuh"
 
@@ -219,13 +220,15 @@ template <int K>
 __global__ void __launch_bounds__(256, 2) dwconv_same_tiled_kernel(const uint4* __restrict__ x, const float* __restrict__ w,
                                                                 const float* __restrict__ bias, uint4* __restrict__ y,
                                                                 double* __restrict__ stats, const uint4* __restrict__ add,
-                                                                DwArgs a, int tiles_y, int tiles_x) {
+                                                                DwArgs a, int tiles_y, int tiles_x,
+                                                                const __grid_constant__ CUtensorMap tmap, int use_tma) {
   constexpr int P = K / 2;
   constexpr int BZ = DT_Z + 2 * P, BY = DT_Y + 2 * P, BX = DT_X + 2 * P, PITCH = BX + 1;   // voxels
-  extern __shared__ __align__(16) uint8_t dsm[];
+  extern __shared__ __align__(128) uint8_t dsm[];
   uint4* s_in = reinterpret_cast<uint4*>(dsm);                       // [BZ][BY][PITCH][4 chunks]
   float* s_w = reinterpret_cast<float*>(s_in + BZ * BY * PITCH * 4); // [K^3][32]
   double* s_stats = reinterpret_cast<double*>(s_w + K * K * K * 32); // [64]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stats + 64);       // TMA completion barrier
   const int tid = threadIdx.x;
   const int CH = a.C >> 3;
   const int cg = blockIdx.y;                 // 32-channel group
@@ -236,9 +239,24 @@ __global__ void __launch_bounds__(256, 2) dwconv_same_tiled_kernel(const uint4* 
   const int tz = t / tiles_y;
   const int z0 = tz * DT_Z, y0 = ty * DT_Y, x0 = tx * DT_X;
 
+  if (use_tma) {
+    // the whole input brick (halo included, zero-filled outside the volume) is one bulk tensor copy: box
+    // [1][BZ][BY][PITCH][32 ch] of the [N][D][H][W][C] tensor at (n, z0-P, y0-P, x0-P, cg*32)
+    if (tid == 0) {
+      mbar_init(s_bar, 1);
+      fence_mbar_init();
+      fence_proxy_async_smem();
+      mbar_arrive_expect_tx(s_bar, (uint32_t)(BZ * BY * PITCH * 64));
+      tma_load_5d(s_in, &tmap, cg * 32, x0 - P, y0 - P, z0 - P, n, s_bar);
+    }
+  }
   for (int i = tid; i < K * K * K * 32; i += 256) s_w[i] = w[(i >> 5) * a.C + cg * 32 + (i & 31)];
   if (tid < 64) s_stats[tid] = 0.0;
   const uint4* xn = x + (int64_t)n * a.D * a.H * a.W * CH + cg * 4;
+  if (use_tma) {
+    __syncthreads();            // barrier init visible to every waiter
+    mbar_wait(s_bar, 0);
+  } else
   staged_copy<((BZ * BY * BX * 4 + 255) / 256 <= 17 ? (BZ * BY * BX * 4 + 255) / 256 : 8)>(BZ * BY * BX * 4, tid, 256,   // whole brick in flight at once
       [&](int q) {
         const int cc = q & 3, v = q >> 2;
@@ -359,8 +377,12 @@ template <int K>
 static bool launch_dw_tiled(cudaStream_t st, const uint4* x, const float* w, const float* b, uint4* y, double* stats,
                             const uint4* add, DwArgs a, int64_t N) {
   constexpr int P = K / 2;
-  const size_t smem = (size_t)(DT_Z + 2 * P) * (DT_Y + 2 * P) * (DT_X + 2 * P + 1) * 64 + (size_t)K * K * K * 32 * 4 + 64 * 8;
+  const size_t smem = (size_t)(DT_Z + 2 * P) * (DT_Y + 2 * P) * (DT_X + 2 * P + 1) * 64 + (size_t)K * K * K * 32 * 4 + 64 * 8 + 16;
   if (smem > 227 * 1024) return false;
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  static const bool no_tma = getenv("PCB_NO_TMA") != nullptr;
+  const int use_tma = !no_tma && make_brick_tensor_map(&tmap, x, N, a.D, a.H, a.W, a.C, DT_Z + 2 * P, DT_Y + 2 * P, DT_X + 2 * P + 1);
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(dwconv_same_tiled_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -372,7 +394,7 @@ static bool launch_dw_tiled(cudaStream_t st, const uint4* x, const float* w, con
   }
   const int tz = (a.D + DT_Z - 1) / DT_Z, ty = (a.H + DT_Y - 1) / DT_Y, tx = (a.W + DT_X - 1) / DT_X;
   dim3 grid((unsigned)(tz * ty * tx), (unsigned)(a.C / 32), (unsigned)N);
-  dwconv_same_tiled_kernel<K><<<grid, 256, smem, st>>>(x, w, b, y, stats, add, a, ty, tx);
+  dwconv_same_tiled_kernel<K><<<grid, 256, smem, st>>>(x, w, b, y, stats, add, a, ty, tx, tmap, use_tma);
   return true;
 }
 
