@@ -118,6 +118,18 @@ int pcb_mlp_bwd(const void* y, const double* stats, const float* gamma, const fl
                 const float* b2, const void* w3t, const void* w2t, const void* dout, void* hact, void* dh,
                 void* dyhat, double* gstats, int64_t N, const int64_t y_size[3], int64_t C, int64_t H,
                 int64_t Co, int mode, void* stream);
+/* Deep levels (C >= 128): conv2 -> GELU -> conv3 as two launches of one warp-specialised tcgen05 GEMM
+ * (csrc/deep_mlp.cu) — the expanded activation goes through `hact` ([N][Vout][H] bf16, caller-owned, kept for
+ * the backward pass) instead of shared memory, so the work splits over output columns as well as rows.
+ * Same argument meaning as pcb_mlp_fwd.  pcb_mlp_fwd_deep_workspace returns the bytes `hact` needs, or 0 when
+ * the shape is not served by this path (use pcb_mlp_fwd).  Replaces the same reference modules as pcb_mlp_fwd
+ * (MedNeXtBlock.conv2/act/conv3 + res_conv, built at mednext_models.py:374-380). */
+int64_t pcb_mlp_fwd_deep_workspace(int64_t N, const int64_t out_size[3], int64_t C, int64_t H, int64_t Co, int64_t Cr);
+int pcb_mlp_fwd_deep(const void* y, const double* stats, const float* gamma, const float* beta, const void* w2,
+                     const float* b2, const void* w3, const float* b3, const void* res, const void* xs,
+                     const void* wr, const float* br, void* out, void* hact, int64_t N, const int64_t out_size[3],
+                     const int64_t xs_size[3], int64_t C, int64_t H, int64_t Co, int64_t Cr, int mode, void* stream);
+
 /* levels 0/1 (3H+C+Co <= 512): persistent kernel doing pcb_mlp_bwd AND both pointwise weight gradients with
  * Hact/dh kept on chip (TMEM-resident wgrad accumulators, bias grads via an all-ones MN-major row).
  * dW3 [Co,H], db3 [Co], dW2 [H,C], db2 [H] fp32 are overwritten; workspace from ..._workspace_floats. */

@@ -19,7 +19,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libpcb200.so")
-SOURCES = ["pcb_api.cu", "sw_kernels.cu", "mednext_fwd.cu", "mednext_bwd.cu", "dense_conv.cu"]
+SOURCES = ["pcb_api.cu", "sw_kernels.cu", "mednext_fwd.cu", "mednext_bwd.cu", "dense_conv.cu", "deep_mlp.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -63,6 +63,7 @@ def lib() -> ctypes.CDLL:
         _lib.pcb_launch_count.restype = ctypes.c_int64
         _lib.pcb_tn_workspace_floats.restype = ctypes.c_int64
         _lib.pcb_mlp_bwd_fused_workspace_floats.restype = ctypes.c_int64
+        _lib.pcb_mlp_fwd_deep_workspace.restype = ctypes.c_int64
     return _lib
 
 

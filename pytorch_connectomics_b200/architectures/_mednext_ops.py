@@ -147,6 +147,18 @@ def block_forward(x: torch.Tensor, skip: Optional[torch.Tensor], params: List[to
         br = packed(params[9], "f32")
         cr = c
     vo = osize[0] * osize[1] * osize[2]
+    ws = int(lib.pcb_mlp_fwd_deep_workspace(ctypes.c_int64(n), L.i64x(osize), ctypes.c_int64(c), ctypes.c_int64(h),
+                                            ctypes.c_int64(co), ctypes.c_int64(cr)))
+    if ws > 0:      # deep levels: two column-split GEMM launches through an HBM/L2-resident expanded activation
+        hact = torch.empty((n, *osize, h), device=dev, dtype=_BF16)
+        with L.prof(f"mlp_fwd_deep:m{mode}C{c}H{h}Co{co}V{vo}"):
+            L.check(lib.pcb_mlp_fwd_deep(L.ptr(y), L.ptr(stats), L.ptr(packed(gamma, "f32")), L.ptr(packed(beta, "f32")),
+                                         L.ptr(packed(w2, "pw")), L.ptr(packed(b2, "f32")), L.ptr(packed(w3, "pw")),
+                                         L.ptr(packed(b3, "f32")), L.ptr(res), L.ptr(x if has_rc else None), L.ptr(wr),
+                                         L.ptr(br), L.ptr(out), L.ptr(hact), ctypes.c_int64(n), L.i64x(osize), L.i64x(size),
+                                         ctypes.c_int64(c), ctypes.c_int64(h), ctypes.c_int64(co), ctypes.c_int64(cr),
+                                         ctypes.c_int(mode), st), "pcb_mlp_fwd_deep")
+        return _mark(out), y, stats
     with L.prof(f"mlp_fwd:m{mode}C{c}H{h}Co{co}V{vo}"):
         L.check(lib.pcb_mlp_fwd(L.ptr(y), L.ptr(stats), L.ptr(packed(gamma, "f32")), L.ptr(packed(beta, "f32")),
                                 L.ptr(packed(w2, "pw")), L.ptr(packed(b2, "f32")), L.ptr(packed(w3, "pw")),

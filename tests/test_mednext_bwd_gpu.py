@@ -80,6 +80,10 @@ def _mk_pair(kind, cin, cout, r, k):
     ("up", 64, 32, 2, 3, (8, 8, 8)),
     ("up", 32, 16, 4, 3, (5, 6, 7)),
     ("up", 512, 256, 2, 3, (2, 2, 2)),
+    ("same", 128, 128, 2, 3, (10, 12, 14)),    # deep path: 14 ragged row tiles x column tiles
+    ("down", 128, 256, 2, 3, (10, 12, 14)),    # deep path + strided res-conv K segment
+    ("up", 128, 64, 2, 3, (6, 6, 6)),          # deep path: padded rows, sparse res-conv rows, BN = 64
+    ("same", 256, 256, 4, 3, (6, 8, 10)),      # deep path: H = 1024, 4 column tiles, K = 256
 ])
 def test_block_backward(kind, cin, cout, r, k, size):
     o, p = _mk_pair(kind, cin, cout, r, k)
