@@ -41,6 +41,12 @@ struct GemmArgs {
   int ntn;                               // column tiles
   int64_t ntiles;                        // N * tps * ntn
   uint32_t dm2, dm1; int ds2, ds1;       // exact division by o2 / o1 (see mf_fdiv in mednext_fwd.cu)
+  // ---- backward (data-gradient) variants
+  int dual;                              // segment 2 feeds a SECOND accumulator: out = GELU(acc1 + bias), out2 = acc2 * GELU'(acc1 + bias)
+  uint4* out2;                           // [N][Vout][Nout] bf16 (dual)
+  int map2;                              // segment-2 row source: 0 per `mode`, 1 output row, 2 output row + 1 on every axis (o1, o2 = box dims)
+  double* gst;                           // GroupNorm-backward sums [N][2][Nout] f64 (+=): S1 = sum g, S2 = sum g * xhat with xhat from
+                                         // `res` (= y) and `stats`; the bf16-rounded g is what gets stored and summed
 };
 
 constexpr int GW_LOAD = 4, GW_EPI = 8, GW_THREADS = 32 * (GW_LOAD + GW_EPI + 1);
@@ -52,6 +58,14 @@ __device__ __forceinline__ int gw_fdiv(int n, uint32_t m, int sh) {
 __device__ __forceinline__ void gw_row_sources(const GemmArgs& a, int ov, int& ry, int& rx) {
   ry = -1; rx = -1;
   if (ov >= (int)a.Vout) return;
+  if (a.map2 == 1) { ry = ov; rx = ov; return; }
+  if (a.map2 == 2) {
+    const int t = gw_fdiv(ov, a.dm2, a.ds2), ox = ov - t * a.o2;
+    const int oz = gw_fdiv(t, a.dm1, a.ds1), oy = t - oz * a.o1;
+    ry = ov;
+    rx = ((oz + 1) * (a.o1 + 1) + (oy + 1)) * (a.o2 + 1) + (ox + 1);
+    return;
+  }
   if (a.mode == PCB_DW_SAME) { ry = ov; return; }
   const int t = gw_fdiv(ov, a.dm2, a.ds2), ox = ov - t * a.o2;
   const int oz = gw_fdiv(t, a.dm1, a.ds1), oy = t - oz * a.o1;
@@ -125,13 +139,16 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gemm_ws_kernel(GemmArgs a) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = a.S, BN = a.BN;
   const int kch1 = a.K1 >> 6, kch = kch1 + (a.K2 >> 6);
-  const bool norm = a.stats != nullptr;
+  const bool gstat = a.gst != nullptr;
+  const bool norm = a.stats != nullptr && !gstat;
+  const int nsc = norm ? a.N * a.K1 : (gstat ? a.N * a.Nout : 0);   // per-(sample, channel) GroupNorm constants
+  const int accw = a.dual ? 2 * BN : BN;                             // TMEM columns per accumulator buffer
   uint8_t* sA = smem;                                        // S x [128 x 64]
   const int bstage = (BN > 128 ? BN : 128) * 128;            // a loader call always writes 128 rows
   uint8_t* sB = sA + S * 16384;                              // S x [max(BN,128) x 64]
   float* sScale = reinterpret_cast<float*>(sB + S * bstage); // [N][K1]
-  float* sShift = sScale + (norm ? a.N * a.K1 : 0);
-  int* sRow = reinterpret_cast<int*>(sShift + (norm ? a.N * a.K1 : 0));   // [4 loader warps][2][128]
+  float* sShift = sScale + nsc;
+  int* sRow = reinterpret_cast<int*>(sShift + nsc);   // [4 loader warps][2][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sRow + GW_LOAD * 2 * 128);
   uint64_t* full = bars;             // [S]  loaders -> MMA
   uint64_t* empty = bars + 4;        // [S]  MMA -> loaders
@@ -139,7 +156,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gemm_ws_kernel(GemmArgs a) {
   uint64_t* acc_empty = bars + 10;   // [2]  epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
-  const uint32_t tmem_cols = tmem_cols_pow2(2 * BN);
+  const uint32_t tmem_cols = tmem_cols_pow2(2 * accw);
   if (warp == GW_LOAD + GW_EPI) tmem_alloc(tmem_slot, tmem_cols);
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) { mbar_init(&full[i], 32); mbar_init(&empty[i], 1); }
@@ -156,6 +173,17 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gemm_ws_kernel(GemmArgs a) {
       const float g = a.gamma[c] * (float)(1.0 / sqrt(var + 1e-5));
       sScale[i] = g;
       sShift[i] = a.beta[c] - (float)mean * g;
+    }
+  } else if (gstat) {   // xhat = y * rstd - mean * rstd
+    for (int i = tid; i < nsc; i += GW_THREADS) {
+      const int n = i / a.Nout, c = i - n * a.Nout;
+      const double sm = a.stats[(int64_t)n * 2 * a.Nout + c], q = a.stats[(int64_t)n * 2 * a.Nout + a.Nout + c];
+      const double mean = sm * (double)a.inv_count;
+      double var = q * (double)a.inv_count - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const float rstd = (float)(1.0 / sqrt(var + 1e-5));
+      sScale[i] = rstd;
+      sShift[i] = (float)mean * rstd;
     }
   }
   fence_proxy_async_smem();
@@ -237,8 +265,11 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gemm_ws_kernel(GemmArgs a) {
         const int g = (int)(i & 1);
         if (i >= 2) mbar_wait(&acc_empty[g], (uint32_t)(((i >> 1) - 1) & 1));
         tc_fence_after();
-        const uint32_t acc = tmem_base + g * BN;
+        const uint32_t acc0 = tmem_base + g * accw;
         for (int kc = 0; kc < kch; ++kc, ++q) {
+          const bool second = a.dual && kc >= kch1;
+          const uint32_t acc = second ? acc0 + BN : acc0;
+          const int kfirst = second ? kch1 : 0;
           const int s = (int)(q % S);
           mbar_wait(&full[s], (uint32_t)((q / S) & 1));
           tc_fence_after();
@@ -246,7 +277,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gemm_ws_kernel(GemmArgs a) {
           const uint64_t dB = umma_desc(smem_u32(sB + s * bstage), 128, 1024);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(acc, dA + (uint64_t)(k * 16), dB + (uint64_t)(k * 16), idesc, (kc > 0 || k > 0) ? 1u : 0u);
+            umma_bf16(acc, dA + (uint64_t)(k * 16), dB + (uint64_t)(k * 16), idesc, (kc > kfirst || k > 0) ? 1u : 0u);
           tc_commit(&empty[s]);
         }
         tc_commit(&acc_full[g]);
@@ -276,7 +307,71 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gemm_ws_kernel(GemmArgs a) {
       const int col0 = nt * BN;
       mbar_wait(&acc_full[eg], (uint32_t)((i >> 1) & 1));
       tc_fence_after();
-      const uint32_t trow = tmem_base + eg * BN + lane_off;
+      const uint32_t trow = tmem_base + eg * accw + lane_off;
+      if (a.dual) {
+        // Hact = GELU(h), dh = dG * GELU'(h) with h = acc1 + bias (both bf16 to HBM for the weight-gradient GEMMs)
+#pragma unroll 1
+        for (int c16 = 0; c16 < BN / 16; ++c16) {
+          uint32_t v1[16], v2[16];
+          tmem_ld16(trow + c16 * 16, v1);
+          tmem_ld16(trow + BN + c16 * 16, v2);
+          tmem_ld_wait();
+          if (!in_range) continue;
+          const float4* bp = reinterpret_cast<const float4*>(a.bias + col0 + c16 * 16);
+          float ha[16], dv[16];
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 b = __ldg(bp + j4);
+            uint64_t val, grad;
+            gelu_fast_vg2(add2(pk2(__uint_as_float(v1[4 * j4]), __uint_as_float(v1[4 * j4 + 1])), pk2(b.x, b.y)), val, grad);
+            upk2(val, ha[4 * j4], ha[4 * j4 + 1]);
+            upk2(mul2(grad, pk2(__uint_as_float(v2[4 * j4]), __uint_as_float(v2[4 * j4 + 1]))), dv[4 * j4], dv[4 * j4 + 1]);
+            gelu_fast_vg2(add2(pk2(__uint_as_float(v1[4 * j4 + 2]), __uint_as_float(v1[4 * j4 + 3])), pk2(b.z, b.w)), val, grad);
+            upk2(val, ha[4 * j4 + 2], ha[4 * j4 + 3]);
+            upk2(mul2(grad, pk2(__uint_as_float(v2[4 * j4 + 2]), __uint_as_float(v2[4 * j4 + 3]))), dv[4 * j4 + 2], dv[4 * j4 + 3]);
+          }
+          a.out[orow + c16 * 2] = pack8(ha);
+          a.out[orow + c16 * 2 + 1] = pack8(ha + 8);
+          a.out2[orow + c16 * 2] = pack8(dv);
+          a.out2[orow + c16 * 2 + 1] = pack8(dv + 8);
+        }
+      } else if (gstat) {
+        // g = bf16(acc) -> HBM; S1 += g, S2 += g * xhat (column sums over the tile rows, f64 atomics per warp)
+        const float* rs = sScale + n * a.Nout + col0;
+        const float* mr = sShift + n * a.Nout + col0;
+        double* gs = a.gst + (int64_t)n * 2 * a.Nout + col0;
+#pragma unroll 1
+        for (int c16 = 0; c16 < BN / 16; ++c16) {
+          uint32_t v[16];
+          tmem_ld16(trow + c16 * 16, v);
+          uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0, 0, 0);
+          if (in_range) { r0 = __ldg(a.res + orow + c16 * 2); r1 = __ldg(a.res + orow + c16 * 2 + 1); }
+          tmem_ld_wait();
+          float g[16], gx[16];
+          if (in_range) {
+            float yv[16];
+            unpack8(r0, yv);
+            unpack8(r1, yv + 8);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              g[j] = round_bf16(__uint_as_float(v[j]));
+              gx[j] = g[j] * fmaf(yv[j], rs[c16 * 16 + j], -mr[c16 * 16 + j]);
+            }
+            a.out[orow + c16 * 2] = pack8(g);
+            a.out[orow + c16 * 2 + 1] = pack8(g + 8);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { g[j] = 0.f; gx[j] = 0.f; }
+          }
+          warp_colsum16(g, lane);
+          warp_colsum16(gx, lane);
+          if (!(lane & 1)) {
+            const int col = c16 * 16 + colsum16_col(lane);
+            atomicAdd(gs + col, (double)g[0]);
+            atomicAdd(gs + a.Nout + col, (double)gx[0]);
+          }
+        }
+      } else
 #pragma unroll 1
       for (int c16 = 0; c16 < BN / 16; ++c16) {
         uint32_t v[16];
@@ -343,13 +438,13 @@ static bool gw_launch(GemmArgs a, cudaStream_t st) {
   a.tps = (a.Vout + 127) / 128;
   const int64_t mtiles = a.tps * a.N;
   // widest column tile that still yields >= 2 tiles per SM, else the narrowest legal one
-  int bn = 256;
+  int bn = a.dual ? 128 : 256;   // dual: two accumulators x two buffers must fit the 512 TMEM columns
   while (bn > 64 && (a.Nout % bn != 0 || mtiles * (a.Nout / bn) < 2 * 148)) bn >>= 1;
   if (a.Nout % bn != 0) return false;
   a.BN = bn;
   a.ntn = a.Nout / bn;
   a.ntiles = mtiles * a.ntn;
-  const size_t fixed = (a.stats ? (size_t)2 * a.N * a.K1 * 4 : 0) + GW_LOAD * 2 * 128 * 4 + 12 * 8 + 16 + 128;
+  const size_t fixed = (a.stats ? (size_t)2 * a.N * (a.gst ? a.Nout : a.K1) * 4 : 0) + GW_LOAD * 2 * 128 * 4 + 12 * 8 + 16 + 128;
   const size_t stage = 16384 + (size_t)(bn > 128 ? bn : 128) * 128;
   int S = 4;
   while (S > 2 && fixed + S * stage > 227 * 1024) --S;
@@ -370,6 +465,41 @@ static bool gw_launch(GemmArgs a, cudaStream_t st) {
   if (a.ntiles < ctas) ctas = (int)a.ntiles;
   gemm_ws_kernel<<<ctas, GW_THREADS, fixed + S * stage, st>>>(a);
   return true;
+}
+
+// Data gradient of conv2 -> GELU -> conv3 for the deep levels (what autograd does for MedNeXtBlock under
+// connectomics/training/lightning/model.py:863-910), rows in y space:
+//   launch 1 (dual accumulators):  Hpre = GN(y) W2^T,  dG = dOut[row map] W3   ->  Hact = GELU(Hpre + b2),  dh = dG * GELU'(Hpre + b2)
+//   launch 2 (stats epilogue)   :  dYhat = dh W2  ->  bf16 + GroupNorm-backward sums
+int mlp_bwd_deep(const void* y, const double* stats, const float* gamma, const float* beta, const void* w2, const float* b2,
+                 const void* w3t, const void* w2t, const void* dout, void* hact, void* dh, void* dyhat, double* gstats,
+                 int64_t N, const int64_t y_size[3], int64_t C, int64_t H, int64_t Co, int mode, void* stream) {
+  if (getenv("PCB_NO_DEEP_BWD") != nullptr || getenv("PCB_NO_DEEP") != nullptr) return 0;
+  if (C < 128 || C % 64 != 0 || H % 64 != 0 || Co % 64 != 0 || N < 1 || N > 8) return 0;
+  const int64_t Vy = y_size[0] * y_size[1] * y_size[2];
+  if (Vy <= 0 || (y_size[0] + 1) * (y_size[1] + 1) * (y_size[2] + 1) >= (1ll << 30)) return 0;
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.o1 = (int)y_size[1]; g.o2 = (int)y_size[2];
+  g.Vout = Vy; g.mode = PCB_DW_SAME; g.N = (int)N;
+  g.inv_count = (float)(1.0 / (double)Vy);
+  GemmArgs g1 = g;
+  g1.a = (const uint4*)y; g1.K1 = (int)C; g1.Va = Vy; g1.b = (const uint4*)w2; g1.Nout = (int)H;
+  g1.stats = stats; g1.gamma = gamma; g1.beta = beta; g1.bias = b2;
+  g1.a2 = (const uint4*)dout; g1.K2 = (int)Co; g1.b2 = (const uint4*)w3t;
+  g1.Va2 = mode == PCB_DW_UP ? (y_size[0] + 1) * (y_size[1] + 1) * (y_size[2] + 1) : Vy;
+  g1.map2 = mode == PCB_DW_UP ? 2 : 1;
+  g1.dual = 1; g1.out = (uint4*)hact; g1.out2 = (uint4*)dh;
+  if (!gw_launch(g1, (cudaStream_t)stream)) return 0;
+  count_launch();
+  GemmArgs g2 = g;
+  g2.a = (const uint4*)dh; g2.K1 = (int)H; g2.Va = Vy; g2.b = (const uint4*)w2t; g2.Nout = (int)C;
+  g2.stats = stats; g2.res = (const uint4*)y; g2.out = (uint4*)dyhat; g2.gst = gstats;
+  if (!gw_launch(g2, (cudaStream_t)stream)) { set_error("pcb_mlp_bwd(deep): launch 2 rejected the shape"); return PCB_ERR_INVALID; }
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("pcb_mlp_bwd(deep): %s", cudaGetErrorString(e)); return PCB_ERR_CUDA; }
+  return 1;
 }
 
 }  // namespace pcb

@@ -35,34 +35,6 @@ __device__ __forceinline__ int64_t map_row(int kind, int64_t v, int d1, int d2, 
   return ((int64_t)(2 * z + 1) * s1 + (2 * y + 1)) * s2 + (2 * x + 1);
 }
 
-// 16 per-lane values -> column totals over the 32 lanes with 16 shuffles (recursive halving).
-// Afterwards lane l holds the total of column  8*b4 + 4*b3 + 2*b2 + b1  (bits of l) in v[0].
-__device__ __forceinline__ void warp_colsum16(float* v, int lane) {
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const float send = (lane & 16) ? v[k] : v[k + 8], keep = (lane & 16) ? v[k + 8] : v[k];
-    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-  }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const float send = (lane & 8) ? v[k] : v[k + 4], keep = (lane & 8) ? v[k + 4] : v[k];
-    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-  }
-#pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const float send = (lane & 4) ? v[k] : v[k + 2], keep = (lane & 4) ? v[k + 2] : v[k];
-    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-  {
-    const float send = (lane & 2) ? v[0] : v[1], keep = (lane & 2) ? v[1] : v[0];
-    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  }
-  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
-}
-__device__ __forceinline__ int colsum16_col(int lane) {
-  return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-}
-
 __device__ __forceinline__ void stage_rows_k(uint8_t* dst, const uint4* __restrict__ src, int rows, int kc8,
                                              int64_t pitch8, int tid, int nthreads = 128) {
   const uint32_t sbo = kc8 * 128;
@@ -1293,6 +1265,11 @@ extern "C" int pcb_mlp_bwd(const void* y, const double* stats, const float* gamm
                 "pcb_mlp_bwd: null argument");
   PCB_CHECK_ARG(C % 16 == 0 && H % 16 == 0 && Co % 16 == 0, "pcb_mlp_bwd: channel counts must be multiples of 16");
   PCB_CHECK_ARG(N > 0 && N <= 65535, "pcb_mlp_bwd: bad batch");
+  PCB_CHECK_ARG(mode >= PCB_DW_SAME && mode <= PCB_DW_UP, "pcb_mlp_bwd: bad mode %d", mode);
+  {
+    const int r = mlp_bwd_deep(y, stats, gamma, beta, w2, b2, w3t, w2t, dout, hact, dh, dyhat, gstats, N, y_size, C, H, Co, mode, stream);
+    if (r != 0) return r > 0 ? PCB_OK : r;
+  }
   MlpBwdArgs a;
   a.y = (const uint4*)y; a.stats = stats; a.gamma = gamma; a.beta = beta; a.w2 = (const uint4*)w2; a.b2 = b2;
   a.w3t = (const uint4*)w3t; a.w2t = (const uint4*)w2t; a.dout = (const uint4*)dout; a.hact = (uint4*)hact;

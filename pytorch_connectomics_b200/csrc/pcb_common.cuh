@@ -172,6 +172,34 @@ __device__ __forceinline__ void staged_copy(int total, int tid, int nthreads, Lo
   }
 }
 
+// 16 per-lane values -> column totals over the 32 lanes with 16 shuffles (recursive halving).
+// Afterwards lane l holds the total of column  8*b4 + 4*b3 + 2*b2 + b1  (bits of l) in v[0].
+__device__ __forceinline__ void warp_colsum16(float* v, int lane) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float send = (lane & 16) ? v[k] : v[k + 8], keep = (lane & 16) ? v[k + 8] : v[k];
+    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float send = (lane & 8) ? v[k] : v[k + 4], keep = (lane & 8) ? v[k + 4] : v[k];
+    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const float send = (lane & 4) ? v[k] : v[k + 2], keep = (lane & 4) ? v[k + 2] : v[k];
+    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  {
+    const float send = (lane & 2) ? v[0] : v[1], keep = (lane & 2) ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+__device__ __forceinline__ int colsum16_col(int lane) {
+  return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+}
+
 // ----------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -305,5 +333,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_ma
 __host__ __device__ constexpr uint32_t tmem_cols_pow2(uint32_t n) {
   return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512;
 }
+
+// deep-level (C >= 128) MLP data gradient as two launches of the column-split GEMM (csrc/deep_mlp.cu);
+// returns 1 when it ran, 0 when the shape is not served (caller uses mlp_bwd_kernel), <0 on error.
+int mlp_bwd_deep(const void* y, const double* stats, const float* gamma, const float* beta, const void* w2, const float* b2,
+                 const void* w3t, const void* w2t, const void* dout, void* hact, void* dh, void* dyhat, double* gstats,
+                 int64_t N, const int64_t y_size[3], int64_t C, int64_t H, int64_t Co, int mode, void* stream);
 
 }  // namespace pcb
