@@ -165,8 +165,9 @@ def workload_config(a, world):
         return {"workload": f"MedNeXt-S k3 train step, {a.batch}x1x{SIDE}^3 crops per GPU, BCE+Dice, AdamW (BASELINE configs[1])",
                 "global_batch": world * a.batch, "crop": [SIDE] * 3, "parallelism": f"dp{world}",
                 "l2": "inputs+activations >> 126 MB L2 per step (no explicit flush)"}
-    return {"workload": f"MedNeXt-S sliding-window inference, {a.volume}^3 volume per GPU, {SIDE}^3 tiles, 50% overlap, bump",
-            "volume": [a.volume] * 3, "tile": [SIDE] * 3, "overlap": 0.5, "parallelism": f"volume-shard x{world}",
+    return {"workload": f"MedNeXt-S sliding-window inference, {a.volume * world}x{a.volume}x{a.volume} volume ({a.volume}^3 per GPU), {SIDE}^3 tiles, 50% overlap, bump",
+            "volume": [a.volume * world, a.volume, a.volume], "tile": [SIDE] * 3, "overlap": 0.5,
+            "parallelism": "single GPU" if world == 1 else f"one volume, z-slab shards x{world} + neighbour overlap exchange (NCCL send/recv)",
             "l2": "volume+accumulators >> 126 MB L2 (no explicit flush)"}
 
 
@@ -393,12 +394,25 @@ def main():
         from pytorch_connectomics_b200.inference.window import EagerSlidingWindowEngine
         eng = EagerSlidingWindowEngine(roi_size=(SIDE,) * 3, sw_batch_size=2, overlap=0.5, mode="bump",
                                        padding_mode="constant", cval=0.0)
-        vol = torch.rand(1, 1, a.volume, a.volume, a.volume, device=dev).half()
         net = lambda t: model(t)  # noqa: E731
+        if world > 1:
+            # ONE volume of world x `volume` planes, z-slab sharded with a neighbour exchange of the overlap planes
+            # (inference/sharded.py); every rank holds the same synthetic volume and stages only its slab
+            from pytorch_connectomics_b200.inference.sharded import ZSlabShardedEngine
+            torch.manual_seed(99)
+            vol = torch.rand(1, 1, a.volume * world, a.volume, a.volume, device=dev).half()
+            sh = ZSlabShardedEngine(roi_size=(SIDE,) * 3, sw_batch_size=2, overlap=0.5, mode="bump",
+                                    padding_mode="constant", cval=0.0, device=dev)
 
-        def step():
-            with torch.no_grad():
-                return eng(inputs=vol, network=net)
+            def step():
+                with torch.no_grad():
+                    return sh(vol, net)
+        else:
+            vol = torch.rand(1, 1, a.volume, a.volume, a.volume, device=dev).half()
+
+            def step():
+                with torch.no_grad():
+                    return eng(inputs=vol, network=net)
 
         for _ in range(max(1, a.warmup // 3)):
             step()
@@ -417,19 +431,28 @@ def main():
         prof = L.prof_stop()
         ms = max_over_ranks(e0.elapsed_time(e1))
         value = world * a.steps * a.volume ** 3 / (ms / 1e3) / 1e6
-        hv = torch.rand(1, 1, a.volume, a.volume, a.volume).half().pin_memory()
+        if world > 1:
+            hv = torch.rand(1, 1, a.volume * world, a.volume, a.volume).half().pin_memory()
+        else:
+            hv = torch.rand(1, 1, a.volume, a.volume, a.volume).half().pin_memory()
         eng_cpu = EagerSlidingWindowEngine(roi_size=(SIDE,) * 3, sw_batch_size=2, overlap=0.5, mode="bump",
                                            padding_mode="constant", cval=0.0, sw_device=dev, output_device="cpu")
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
         with torch.no_grad():
-            out = eng_cpu(inputs=hv, network=net)
+            if world > 1:      # host volume -> this rank's slab H2D -> windows -> exchange -> own planes D2H
+                part, own = sh(hv, net)
+                out = part.cpu() if part is not None else torch.empty(0)
+                h2d_bytes = 0 if part is None else (own[1] - own[0] + SIDE // 2) * a.volume * a.volume * 2
+            else:
+                out = eng_cpu(inputs=hv, network=net)
+                h2d_bytes = hv.numel() * 2
         f1.record()
         barrier()
         ms_e2e = max_over_ranks(f0.elapsed_time(f1))
         e2e = {"value": world * a.volume ** 3 / (ms_e2e / 1e3) / 1e6, "unit": "Mvox/s",
-               "h2d_bytes_per_step": hv.numel() * 2, "d2h_bytes_per_step": out.numel() * out.element_size()}
+               "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": out.numel() * out.element_size()}
         metric, unit = METRIC_INFER, "Mvox/s"
 
     if rank != 0:

@@ -15,6 +15,7 @@ for f in $O/bench_*.json; do echo "$f: $(python -c "import json,sys; d=json.load
 (timeout 120 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --profile-ops) > $O/bench_ops.json 2> $O/bench_ops.err
 (timeout 100 python tools/profile_blocks.py --time) > $O/blocks_time.log 2>&1
 (timeout 100 python tools/time_fwd.py --split) > $O/time_fwd.log 2>&1
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:'dwconv|dw_wgrad|mlp_bwd_fused|mlp_fused|gn_dy|head_bwd' \
+timeout 400 ncu --set full --clock-control none -c 80 -k regex:'dwconv|dw_wgrad|mlp_bwd_fused|mlp_fused|gn_dy|head_bwd' \
   -o $O/blocks python tools/profile_blocks.py > $O/ncu_blocks.log 2>&1
+ncu -i $O/blocks.ncu-rep --page raw --csv > $O/blocks_raw.csv 2>/dev/null
 ls -la $O
