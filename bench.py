@@ -337,11 +337,12 @@ def main():
         graphed = None
         run = step
         dbg(f"eager pass done: {ms_eager:.2f} ms/step")
-        # NCCL collectives inside a captured graph are left for a later round: data-parallel runs time eager steps
-        if not (a.no_graph or a.profile_ops or (world > 1 and not os.environ.get("PCB_GRAPH_DDP"))):
+        # data-parallel runs: two graphs around an eagerly launched NCCL all-reduce (PCB_GRAPH_DDP=1: one graph, NCCL captured)
+        if not (a.no_graph or a.profile_ops):
             try:
                 from pytorch_connectomics_b200.training import GraphedTrainStep
-                graphed = GraphedTrainStep(model, bce_dice_loss, opt, arena, pool[0][0], pool[0][1], warmup=1)
+                graphed = GraphedTrainStep(model, bce_dice_loss, opt, arena, pool[0][0], pool[0][1], warmup=1,
+                                           split_collective=world > 1 and not os.environ.get("PCB_GRAPH_DDP"))
                 run = graphed
             except Exception as exc:   # keep the bench alive; say so in the JSON line
                 print(f"[bench] CUDA-graph capture failed, timing eager steps: {exc!r}", file=sys.stderr)
@@ -478,7 +479,7 @@ def main():
            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "bf16", "data": "synthetic", "config": workload_config(a, world), "e2e": e2e,
            "gpu_launches": int(launches), "roofline": roof,
-           "execution": ({"timed_region": "cuda_graph_replay" if graphed is not None else "eager",
+           "execution": ({"timed_region": ("cuda_graph_replay" if graphed.graph_opt is None else "cuda_graph_replay x2 around eager NCCL all-reduce") if graphed is not None else "eager",
                           "eager_ms_per_step": ms_eager, "roofline_timed_in": f"instrumented eager pass of {nprof} steps"}
                          if a.mode == "train" else {"timed_region": "eager"}),
            "clocks": clocks.window(w0, w1) if clocks else None}

@@ -350,6 +350,95 @@ __global__ void __launch_bounds__(256, 2) dwconv_up3_kernel(const uint4* __restr
 // one voxel (64 B) so a quarter-warp's LDS.128 touches 8 distinct 16 B bank groups.
 constexpr int DT_Z = 4, DT_Y = 8, DT_X = 16, DT_XB = 8;
 
+// One 4x8x16 output brick x 32 channels from the staged input brick: every thread owns 8 consecutive outputs along W
+// for 8 channels (64 fp32 accumulators as 32 packed pairs); adds bias (+ fused `add`), rounds to bf16, stores, and
+// returns the thread's partial GroupNorm sums of the rounded outputs.
+template <int K>
+__device__ __forceinline__ void dw_same_brick(const uint4* __restrict__ s_in, const float* __restrict__ s_w,
+                                              const float* __restrict__ bias, const uint4* __restrict__ add,
+                                              uint4* __restrict__ y, const DwArgs& a, int tid, int n, int cg, int z0, int y0,
+                                              int x0, float* ssum, float* ssq) {
+  constexpr int P = K / 2;
+  constexpr int BY = DT_Y + 2 * P, BX = DT_X + 2 * P, PITCH = BX + 1;
+  const int CH = a.C >> 3;
+  const int cc = tid & 3, ly = (tid >> 2) & 7, xb = (tid >> 5) & 1, lz = tid >> 6;
+  uint64_t acc[DT_XB][4];
+#pragma unroll
+  for (int j = 0; j < DT_XB; ++j)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[j][c] = 0ull;
+#pragma unroll 1
+  for (int dz = 0; dz < K; ++dz) {
+#pragma unroll 1
+    for (int dy = 0; dy < K; ++dy) {
+      uint64_t wv[K][4];
+#pragma unroll
+      for (int dx = 0; dx < K; ++dx) {
+        const float4* wp = reinterpret_cast<const float4*>(s_w + ((dz * K + dy) * K + dx) * 32 + cc * 8);
+        const float4 w0 = wp[0], w1 = wp[1];
+        wv[dx][0] = pk2(w0.x, w0.y); wv[dx][1] = pk2(w0.z, w0.w); wv[dx][2] = pk2(w1.x, w1.y); wv[dx][3] = pk2(w1.z, w1.w);
+      }
+      const uint4* row = s_in + (((lz + dz) * BY + (ly + dy)) * PITCH + xb * DT_XB) * 4 + cc;
+#pragma unroll
+      for (int i = 0; i < DT_XB + K - 1; ++i) {
+        const uint4 v4 = row[i * 4];
+        uint64_t f[4];
+        f[0] = pk2(bf16_lo(v4.x), bf16_hi(v4.x)); f[1] = pk2(bf16_lo(v4.y), bf16_hi(v4.y));
+        f[2] = pk2(bf16_lo(v4.z), bf16_hi(v4.z)); f[3] = pk2(bf16_lo(v4.w), bf16_hi(v4.w));
+#pragma unroll
+        for (int dx = 0; dx < K; ++dx) {
+          const int j = i - dx;
+          if (j >= 0 && j < DT_XB) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[j][c] = fma2(f[c], wv[dx][c], acc[j][c]);
+          }
+        }
+      }
+    }
+  }
+  float bv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (bias != nullptr) {
+    const float4* bp = reinterpret_cast<const float4*>(bias + cg * 32 + cc * 8);
+    const float4 b0 = __ldg(bp), b1 = __ldg(bp + 1);
+    bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) { ssum[c] = 0.f; ssq[c] = 0.f; }
+  const int oz = z0 + lz, oy = y0 + ly;
+  if (oz < a.D && oy < a.H) {
+    const int64_t rowoff = ((((int64_t)n * a.D + oz) * a.H + oy) * a.W) * CH + cg * 4 + cc;
+    uint4 addv[DT_XB];
+    if (add != nullptr) {
+#pragma unroll
+      for (int j = 0; j < DT_XB; ++j) {
+        const int ox = x0 + xb * DT_XB + j;
+        addv[j] = ox < a.W ? __ldg(add + rowoff + (int64_t)ox * CH) : make_uint4(0, 0, 0, 0);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < DT_XB; ++j) {
+      const int ox = x0 + xb * DT_XB + j;
+      if (ox >= a.W) continue;
+      float o[8];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) upk2(acc[j][c], o[2 * c], o[2 * c + 1]);
+      if (add != nullptr) {
+        float f[8];
+        unpack8(addv[j], f);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) o[c] += f[c];
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        o[c] = round_bf16(o[c] + bv[c]);
+        ssum[c] += o[c];
+        ssq[c] = fmaf(o[c], o[c], ssq[c]);
+      }
+      y[rowoff + (int64_t)ox * CH] = pack8(o);
+    }
+  }
+}
+
 template <int K>
 __global__ void __launch_bounds__(256, 2) dwconv_same_tiled_kernel(const uint4* __restrict__ x, const float* __restrict__ w,
                                                                 const float* __restrict__ bias, uint4* __restrict__ y,
@@ -406,83 +495,9 @@ __global__ void __launch_bounds__(256, 2) dwconv_same_tiled_kernel(const uint4* 
       });
   __syncthreads();
 
-  const int cc = tid & 3, ly = (tid >> 2) & 7, xb = (tid >> 5) & 1, lz = tid >> 6;
-  uint64_t acc[DT_XB][4];
-#pragma unroll
-  for (int j = 0; j < DT_XB; ++j)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) acc[j][c] = 0ull;
-#pragma unroll 1
-  for (int dz = 0; dz < K; ++dz) {
-#pragma unroll 1
-    for (int dy = 0; dy < K; ++dy) {
-      uint64_t wv[K][4];
-#pragma unroll
-      for (int dx = 0; dx < K; ++dx) {
-        const float4* wp = reinterpret_cast<const float4*>(s_w + ((dz * K + dy) * K + dx) * 32 + cc * 8);
-        const float4 w0 = wp[0], w1 = wp[1];
-        wv[dx][0] = pk2(w0.x, w0.y); wv[dx][1] = pk2(w0.z, w0.w); wv[dx][2] = pk2(w1.x, w1.y); wv[dx][3] = pk2(w1.z, w1.w);
-      }
-      const uint4* row = s_in + (((lz + dz) * BY + (ly + dy)) * PITCH + xb * DT_XB) * 4 + cc;
-#pragma unroll
-      for (int i = 0; i < DT_XB + K - 1; ++i) {
-        const uint4 v4 = row[i * 4];
-        uint64_t f[4];
-        f[0] = pk2(bf16_lo(v4.x), bf16_hi(v4.x)); f[1] = pk2(bf16_lo(v4.y), bf16_hi(v4.y));
-        f[2] = pk2(bf16_lo(v4.z), bf16_hi(v4.z)); f[3] = pk2(bf16_lo(v4.w), bf16_hi(v4.w));
-#pragma unroll
-        for (int dx = 0; dx < K; ++dx) {
-          const int j = i - dx;
-          if (j >= 0 && j < DT_XB) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) acc[j][c] = fma2(f[c], wv[dx][c], acc[j][c]);
-          }
-        }
-      }
-    }
-  }
-  float bv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  if (bias != nullptr) {
-    const float4* bp = reinterpret_cast<const float4*>(bias + cg * 32 + cc * 8);
-    const float4 b0 = __ldg(bp), b1 = __ldg(bp + 1);
-    bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
-  }
+  const int cc = tid & 3;
   float ssum[8], ssq[8];
-#pragma unroll
-  for (int c = 0; c < 8; ++c) { ssum[c] = 0.f; ssq[c] = 0.f; }
-  const int oz = z0 + lz, oy = y0 + ly;
-  if (oz < a.D && oy < a.H) {
-    const int64_t rowoff = ((((int64_t)n * a.D + oz) * a.H + oy) * a.W) * CH + cg * 4 + cc;
-    uint4 addv[DT_XB];
-    if (add != nullptr) {
-#pragma unroll
-      for (int j = 0; j < DT_XB; ++j) {
-        const int ox = x0 + xb * DT_XB + j;
-        addv[j] = ox < a.W ? __ldg(add + rowoff + (int64_t)ox * CH) : make_uint4(0, 0, 0, 0);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < DT_XB; ++j) {
-      const int ox = x0 + xb * DT_XB + j;
-      if (ox >= a.W) continue;
-      float o[8];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) upk2(acc[j][c], o[2 * c], o[2 * c + 1]);
-      if (add != nullptr) {
-        float f[8];
-        unpack8(addv[j], f);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) o[c] += f[c];
-      }
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        o[c] = round_bf16(o[c] + bv[c]);
-        ssum[c] += o[c];
-        ssq[c] = fmaf(o[c], o[c], ssq[c]);
-      }
-      y[rowoff + (int64_t)ox * CH] = pack8(o);
-    }
-  }
+  dw_same_brick<K>(s_in, s_w, bias, add, y, a, tid, n, cg, z0, y0, x0, ssum, ssq);
   if (stats == nullptr) return;
   // lanes sharing a channel chunk differ in bits 2..4 (ly low bits) -> butterfly, then shared/global f64 atomics
 #pragma unroll
@@ -502,6 +517,81 @@ __global__ void __launch_bounds__(256, 2) dwconv_same_tiled_kernel(const uint4* 
   }
   __syncthreads();
   if (tid < 64) {
+    const int which = tid >> 5, c = tid & 31;
+    atomicAdd(&stats[(int64_t)n * 2 * a.C + which * a.C + cg * 32 + c], s_stats[tid]);
+  }
+}
+
+// Persistent variant (TMA only): one CTA per SM loops over the bricks of one (sample, 32-channel group) with TWO input
+// stages — the bulk tensor copy of brick i+1 is in flight while brick i is computed, weights are staged once, and the
+// GroupNorm partial sums leave the CTA once (64 f64 atomics per CTA instead of per brick).
+template <int K>
+__global__ void __launch_bounds__(256, 1) dwconv_same_persist_kernel(const float* __restrict__ w, const float* __restrict__ bias,
+                                                                     uint4* __restrict__ y, double* __restrict__ stats,
+                                                                     const uint4* __restrict__ add, DwArgs a, int tiles_y,
+                                                                     int tiles_x, int nbricks,
+                                                                     const __grid_constant__ CUtensorMap tmap) {
+  constexpr int P = K / 2;
+  constexpr int BZ = DT_Z + 2 * P, BY = DT_Y + 2 * P, BX = DT_X + 2 * P, PITCH = BX + 1;   // voxels
+  constexpr int STAGE = BZ * BY * PITCH * 4;                                                // uint4 per stage
+  extern __shared__ __align__(128) uint8_t dsm[];
+  uint4* s_in = reinterpret_cast<uint4*>(dsm);                       // [2][BZ][BY][PITCH][4 chunks]
+  float* s_w = reinterpret_cast<float*>(s_in + 2 * STAGE);           // [K^3][32]
+  double* s_stats = reinterpret_cast<double*>(s_w + K * K * K * 32); // [64]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stats + 64);       // [2] TMA completion barriers
+  const int tid = threadIdx.x;
+  const int cg = blockIdx.y, n = blockIdx.z;
+  auto issue = [&](int b, int stage) {
+    int t = b;
+    const int tx = t % tiles_x; t /= tiles_x;
+    const int ty = t % tiles_y, tz = t / tiles_y;
+    mbar_arrive_expect_tx(&s_bar[stage], (uint32_t)(STAGE * 16));
+    tma_load_5d(s_in + stage * STAGE, &tmap, cg * 32, tx * DT_X - P, ty * DT_Y - P, tz * DT_Z - P, n, &s_bar[stage]);
+  };
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    fence_mbar_init();
+    fence_proxy_async_smem();
+    if ((int)blockIdx.x < nbricks) issue(blockIdx.x, 0);
+  }
+  for (int i = tid; i < K * K * K * 32; i += 256) s_w[i] = w[(i >> 5) * a.C + cg * 32 + (i & 31)];
+  if (tid < 64) s_stats[tid] = 0.0;
+  __syncthreads();
+  const int cc = tid & 3;
+  uint32_t phase0 = 0, phase1 = 0;
+  int stage = 0;
+  for (int b = blockIdx.x; b < nbricks; b += gridDim.x) {
+    // stage^1 was fully consumed before the __syncthreads that ended the previous iteration
+    if (tid == 0 && b + (int)gridDim.x < nbricks) issue(b + gridDim.x, stage ^ 1);
+    if (stage == 0) { mbar_wait(&s_bar[0], phase0); phase0 ^= 1; }
+    else { mbar_wait(&s_bar[1], phase1); phase1 ^= 1; }
+    int t = b;
+    const int tx = t % tiles_x; t /= tiles_x;
+    const int ty = t % tiles_y, tz = t / tiles_y;
+    float ssum[8], ssq[8];
+    dw_same_brick<K>(s_in + stage * STAGE, s_w, bias, add, y, a, tid, n, cg, tz * DT_Z, ty * DT_Y, tx * DT_X, ssum, ssq);
+    if (stats != nullptr) {
+#pragma unroll
+      for (int off = 4; off <= 16; off <<= 1) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          ssum[c] += __shfl_xor_sync(0xffffffffu, ssum[c], off);
+          ssq[c] += __shfl_xor_sync(0xffffffffu, ssq[c], off);
+        }
+      }
+      if ((tid & 31) < 4) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          atomicAdd(&s_stats[cc * 8 + c], (double)ssum[c]);
+          atomicAdd(&s_stats[32 + cc * 8 + c], (double)ssq[c]);
+        }
+      }
+    }
+    __syncthreads();
+    stage ^= 1;
+  }
+  if (stats != nullptr && tid < 64) {
     const int which = tid >> 5, c = tid & 31;
     atomicAdd(&stats[(int64_t)n * 2 * a.C + which * a.C + cg * 32 + c], s_stats[tid]);
   }
@@ -527,6 +617,26 @@ static bool launch_dw_tiled(cudaStream_t st, const uint4* x, const float* w, con
     configured = true;
   }
   const int tz = (a.D + DT_Z - 1) / DT_Z, ty = (a.H + DT_Y - 1) / DT_Y, tx = (a.W + DT_X - 1) / DT_X;
+  static const bool no_persist = getenv("PCB_NO_DW_PERSIST") != nullptr;
+  const size_t smem_p = (size_t)2 * (DT_Z + 2 * P) * (DT_Y + 2 * P) * (DT_X + 2 * P + 1) * 64 + (size_t)K * K * K * 32 * 4 + 64 * 8 + 32;
+  if (use_tma && !no_persist && smem_p <= 227 * 1024) {
+    static bool configured_p = false;
+    if (!configured_p) {
+      cudaFuncSetAttribute(dwconv_same_persist_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      configured_p = cudaFuncSetAttribute(dwconv_same_persist_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess;
+      if (!configured_p) cudaGetLastError();
+    }
+    if (configured_p) {
+      const int nbricks = tz * ty * tx;
+      const int64_t groups = (int64_t)(a.C / 32) * N;
+      int ctas = (int)(148 / groups);                 // one resident CTA per SM, whole grid in a single wave
+      if (ctas < 1) ctas = 1;
+      if (ctas > nbricks) ctas = nbricks;
+      dim3 grid((unsigned)ctas, (unsigned)(a.C / 32), (unsigned)N);
+      dwconv_same_persist_kernel<K><<<grid, 256, smem_p, st>>>(w, b, y, stats, add, a, ty, tx, nbricks, tmap);
+      return true;
+    }
+  }
   dim3 grid((unsigned)(tz * ty * tx), (unsigned)(a.C / 32), (unsigned)N);
   dwconv_same_tiled_kernel<K><<<grid, 256, smem, st>>>(x, w, b, y, stats, add, a, ty, tx, tmap, use_tma);
   return true;

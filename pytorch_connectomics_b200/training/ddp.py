@@ -46,10 +46,22 @@ class FlatGradArena:
                 p.grad = view
             off += p.numel()
 
-    def allreduce(self, group: Optional[dist.ProcessGroup] = None) -> None:
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+    @staticmethod
+    def _world(group) -> int:
+        return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+    def allreduce_sum(self, group: Optional[dist.ProcessGroup] = None) -> None:
+        """The exchange step alone (NCCL all-reduce SUM over NVLink); pair with :meth:`scale_mean`."""
+        if self._world(group) > 1:
             dist.all_reduce(self.buffer, op=dist.ReduceOp.SUM, group=group)
-            self.buffer.mul_(1.0 / dist.get_world_size(group))
+
+    def scale_mean(self, group: Optional[dist.ProcessGroup] = None) -> None:
+        if self._world(group) > 1:
+            self.buffer.mul_(1.0 / self._world(group))
+
+    def allreduce(self, group: Optional[dist.ProcessGroup] = None) -> None:
+        self.allreduce_sum(group)
+        self.scale_mean(group)
 
 
 def allreduce_gradients(arena: FlatGradArena, group: Optional[dist.ProcessGroup] = None) -> None:

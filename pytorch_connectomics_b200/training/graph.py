@@ -17,9 +17,17 @@ from .ddp import FlatGradArena
 
 
 class GraphedTrainStep:
+    """``split_collective=False``: the whole step (gradient all-reduce included) is ONE graph.
+    ``split_collective=True`` (data-parallel default): two graphs around an eagerly launched all-reduce —
+    graph A = zero grads + forward + loss + backward, then ``dist.all_reduce`` over the flat arena on the same
+    stream, then graph B = 1/world scale + optimizer step — three host launches per step instead of ~1 400, and
+    no NCCL call inside a capture."""
+
     def __init__(self, model: torch.nn.Module, loss_fn: Callable, optimizer: torch.optim.Optimizer,
-                 arena: FlatGradArena, example_input: torch.Tensor, example_target: torch.Tensor, warmup: int = 3):
+                 arena: FlatGradArena, example_input: torch.Tensor, example_target: torch.Tensor, warmup: int = 3,
+                 split_collective: bool = False, group=None):
         self.model, self.loss_fn, self.opt, self.arena = model, loss_fn, optimizer, arena
+        self.split, self.group = bool(split_collective), group
         self.x = example_input.clone()
         self.t = example_target.clone()
         side = torch.cuda.Stream()
@@ -30,8 +38,24 @@ class GraphedTrainStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
+        self.graph_opt = None
+        if not self.split:
+            with torch.cuda.graph(self.graph):
+                self.loss = self._step()
+            return
         with torch.cuda.graph(self.graph):
-            self.loss = self._step()
+            self.loss = self._fwd_bwd()
+        self.arena.allreduce_sum(self.group)
+        self.graph_opt = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_opt, pool=self.graph.pool()):
+            self.arena.scale_mean(self.group)
+            self.opt.step()
+
+    def _fwd_bwd(self) -> torch.Tensor:
+        self.arena.zero()
+        loss = self.loss_fn(self.model(self.x), self.t)
+        loss.backward()
+        return loss
 
     def _step(self) -> torch.Tensor:
         self.arena.zero()
@@ -45,4 +69,7 @@ class GraphedTrainStep:
         self.x.copy_(x, non_blocking=True)
         self.t.copy_(t, non_blocking=True)
         self.graph.replay()
+        if self.graph_opt is not None:
+            self.arena.allreduce_sum(self.group)
+            self.graph_opt.replay()
         return self.loss

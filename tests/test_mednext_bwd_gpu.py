@@ -227,3 +227,48 @@ def test_pointwise_projection_matches_conv():
         assert rel(ncdhw(out), conv(x)) < 5e-3
     out.backward(cl(gout))
     assert rel(ncdhw(xc.grad), xr.grad) < 6e-3 and rel(w.grad, conv.weight.grad) < 5e-3 and rel(b.grad, conv.bias.grad) < 1e-4
+
+
+@pytest.mark.parametrize("split", [False, True])
+def test_graphed_train_step_matches_eager(split):
+    """training/graph.py: the captured step (one graph, or two graphs around the eager all-reduce) must update the
+    parameters exactly like the eager step it replaces (training/lightning/model.py:863-910 semantics)."""
+    from pytorch_connectomics_b200.training import FlatGradArena, GraphedTrainStep
+
+    def make():
+        torch.manual_seed(11)
+        net = PM.MedNeXt(1, 16, 1, exp_r=2, kernel_size=3, deep_supervision=False, do_res=True, do_res_up_down=True,
+                         block_counts=[1] * 9).to(DEV).train()
+        arena = FlatGradArena(net.parameters())
+        opt = torch.optim.AdamW(net.parameters(), lr=1e-3, weight_decay=0.01, fused=True, capturable=True)
+        return net, arena, opt
+
+    def loss_fn(out, t):
+        return torch.nn.functional.binary_cross_entropy_with_logits(out.float(), t)
+
+    torch.manual_seed(3)
+    xs = [torch.rand(1, 1, 32, 32, 32, device=DEV).half() for _ in range(3)]
+    ts = [(torch.rand(1, 1, 32, 32, 32, device=DEV) > 0.8).float() for _ in range(3)]
+    net_e, arena_e, opt_e = make()
+    net_g, arena_g, opt_g = make()
+    g = GraphedTrainStep(net_g, loss_fn, opt_g, arena_g, xs[0], ts[0], warmup=1, split_collective=split)
+    assert (g.graph_opt is not None) == split
+    # the graphed object already ran warm-up + capture steps on (xs[0], ts[0]); replay the same history eagerly
+    n_pre = 1          # one eager warm-up step ran inside GraphedTrainStep; captures record, they do not execute
+    for _ in range(n_pre):
+        arena_e.zero()
+        loss_fn(net_e(xs[0]), ts[0]).backward()
+        arena_e.allreduce()
+        opt_e.step()
+    for x, t in zip(xs, ts):
+        arena_e.zero()
+        le = loss_fn(net_e(x), t)
+        le.backward()
+        arena_e.allreduce()
+        opt_e.step()
+        lg = g(x, t)
+    torch.cuda.synchronize()
+    # GroupNorm statistics use f64 atomics (order-dependent in the last bits) -> compare tightly, not bitwise
+    assert abs(float(le) - float(lg)) < 5e-3 * max(1.0, abs(float(le)))
+    for pe, pg in zip(net_e.parameters(), net_g.parameters()):
+        assert torch.allclose(pe, pg, rtol=0, atol=5e-3), (pe - pg).abs().max()
