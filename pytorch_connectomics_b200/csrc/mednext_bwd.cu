@@ -918,7 +918,7 @@ struct DwWgArgs {
 };
 
 template <int K>
-__global__ void __launch_bounds__(256) dw_wgrad_kernel(const uint4* __restrict__ center, const uint4* __restrict__ neigh,
+__global__ void __launch_bounds__(256, K == 3 ? 3 : 1) dw_wgrad_kernel(const uint4* __restrict__ center, const uint4* __restrict__ neigh,
                                                        double* __restrict__ dW, DwWgArgs a) {
   extern __shared__ double s_acc[];   // [K][C]
   constexpr int P = K / 2;
@@ -954,20 +954,50 @@ __global__ void __launch_bounds__(256) dw_wgrad_kernel(const uint4* __restrict__
     if (iz < 0 || iz >= a.n0 || iy < 0 || iy >= a.n1) continue;
     const uint4* crow = cn + ((int64_t)cz * a.c1 + cy) * a.c2 * CH + cc;
     const uint4* nrow = nn + ((int64_t)iz * a.n1 + iy) * a.n2 * CH + cc;
+    // every load of the strip is issued before the first FMA (branch-free, zero fill outside the rows): the kernel is
+    // latency-bound otherwise (ncu: long_scoreboard 17 warps per issue at 48 % occupancy)
+    constexpr int NIN = 2 * (DW_XB_WG - 1) + K;          // neighbour vectors a strip can touch at stride 2
+    const int cx0 = xs * DW_XB_WG;
+    const int nin = a.S * (DW_XB_WG - 1) + K;
+    const int ix0 = cx0 * a.S - P;
+    uint4 cv4[DW_XB_WG], nv4[NIN];
 #pragma unroll
-    for (int j = 0; j < DW_XB_WG; ++j) {
-      const int cx = xs * DW_XB_WG + j;
-      if (cx >= a.c2) break;
-      float cv[8];
-      unpack8(__ldg(crow + (int64_t)cx * CH), cv);
+    for (int j = 0; j < DW_XB_WG; ++j)
+      cv4[j] = (cx0 + j < a.c2) ? __ldg(crow + (int64_t)(cx0 + j) * CH) : make_uint4(0, 0, 0, 0);
 #pragma unroll
-      for (int k = 0; k < K; ++k) {
-        const int ix = cx * a.S - P + k;
-        if (ix < 0 || ix >= a.n2) continue;
-        float nv[8];
-        unpack8(__ldg(nrow + (int64_t)ix * CH), nv);
+    for (int i = 0; i < NIN; ++i) {
+      const int ix = ix0 + i;
+      nv4[i] = (i < nin && ix >= 0 && ix < a.n2) ? __ldg(nrow + (int64_t)ix * CH) : make_uint4(0, 0, 0, 0);
+    }
+    if (a.S == 1) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[k][c] = fmaf(cv[c], nv[c], acc[k][c]);
+      for (int j = 0; j < DW_XB_WG; ++j) {
+        float cv[8];
+        unpack8(cv4[j], cv);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          if (j + k < NIN) {
+            float nv[8];
+            unpack8(nv4[j + k], nv);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[k][c] = fmaf(cv[c], nv[c], acc[k][c]);
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < DW_XB_WG; ++j) {
+        float cv[8];
+        unpack8(cv4[j], cv);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          if (2 * j + k < NIN) {
+            float nv[8];
+            unpack8(nv4[2 * j + k], nv);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[k][c] = fmaf(cv[c], nv[c], acc[k][c]);
+          }
+        }
       }
     }
   }
@@ -1204,6 +1234,74 @@ __global__ void __launch_bounds__(128) head_bwd_kernel(const TO* __restrict__ dO
     if (pr < npair) atomicAdd(&dW[pr], (double)wacc[u]);
   }
   if (tid < ncls) atomicAdd(&db[tid], (double)bacc);
+}
+
+// Streaming variant for the full-resolution head (few classes, C/8 a power of two <= 32): thread = (voxel, 8-channel chunk)
+// with the chunk fixed per thread, so its weight rows and its dW partials live in registers; x is read and dX written
+// exactly once with fully coalesced 128-bit accesses; one warp-shuffle + shared f64 reduction per CTA at the end.
+template <typename TO, int NCLS>
+__global__ void __launch_bounds__(256) head_bwd_stream_kernel(const TO* __restrict__ dO, const uint4* __restrict__ x,
+                                                              const float* __restrict__ w, uint4* __restrict__ dX,
+                                                              double* __restrict__ dW, double* __restrict__ db,
+                                                              int C, int64_t V) {
+  extern __shared__ double s_red[];      // [C*NCLS + NCLS]
+  const int CH = C >> 3, n = blockIdx.y, tid = threadIdx.x;
+  for (int i = tid; i < C * NCLS + NCLS; i += 256) s_red[i] = 0.0;
+  __syncthreads();
+  const int64_t T = (int64_t)gridDim.x * 256;            // multiple of CH (host guarantees) -> fixed chunk per thread
+  const int64_t first = (int64_t)blockIdx.x * 256 + tid;
+  const int cc = (int)(first % CH);
+  float wr[8][NCLS], wacc[8][NCLS], bacc[NCLS];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int k = 0; k < NCLS; ++k) { wr[j][k] = __ldg(w + (cc * 8 + j) * NCLS + k); wacc[j][k] = 0.f; }
+#pragma unroll
+  for (int k = 0; k < NCLS; ++k) bacc[k] = 0.f;
+  const uint4* xn = x + (int64_t)n * V * CH;
+  uint4* dxn = dX + (int64_t)n * V * CH;
+  const TO* don = dO + (int64_t)n * NCLS * V;
+  for (int64_t it = first; it < V * CH; it += T) {
+    const int64_t v = it / CH;
+    float g[NCLS], f[8], o[8];
+#pragma unroll
+    for (int k = 0; k < NCLS; ++k) g[k] = (float)don[(int64_t)k * V + v];
+    unpack8(ldg_nc(xn + it), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float sacc = 0.f;
+#pragma unroll
+      for (int k = 0; k < NCLS; ++k) { sacc = fmaf(g[k], wr[j][k], sacc); wacc[j][k] = fmaf(f[j], g[k], wacc[j][k]); }
+      o[j] = sacc;
+    }
+    dxn[it] = pack8(o);
+    if (cc == 0) {
+#pragma unroll
+      for (int k = 0; k < NCLS; ++k) bacc[k] += g[k];
+    }
+  }
+  // lanes with equal (lane % CH) share the chunk: butterfly over the higher lane bits
+  for (int off = 16; off >= CH; off >>= 1) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int k = 0; k < NCLS; ++k) wacc[j][k] += __shfl_xor_sync(0xffffffffu, wacc[j][k], off);
+#pragma unroll
+    for (int k = 0; k < NCLS; ++k) bacc[k] += __shfl_xor_sync(0xffffffffu, bacc[k], off);
+  }
+  if ((tid & 31) < CH) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int k = 0; k < NCLS; ++k) atomicAdd(&s_red[(cc * 8 + j) * NCLS + k], (double)wacc[j][k]);
+    if (cc == 0) {
+#pragma unroll
+      for (int k = 0; k < NCLS; ++k) atomicAdd(&s_red[C * NCLS + k], (double)bacc[k]);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < C * NCLS; i += 256) atomicAdd(&dW[i], s_red[i]);
+  if (tid < NCLS) atomicAdd(&db[tid], s_red[C * NCLS + tid]);
 }
 
 // stem: out[v,c] = sum_ci x[ci,v] w[c,ci] + b[c].  dW[c,ci] += sum_v g[v,c] x[ci,v]; db[c] += sum_v g[v,c]
@@ -1539,13 +1637,38 @@ extern "C" int pcb_head_bwd(const void* dout, int dtype, const void* x, const fl
                             int64_t N, int64_t C, int64_t ncls, int64_t nvox, void* stream) {
   PCB_CHECK_ARG(dout && x && w && dx && dW && db, "pcb_head_bwd: null argument");
   PCB_CHECK_ARG(C % 8 == 0 && C > 0 && ncls > 0 && C * ncls <= 1024 && ncls <= 128, "pcb_head_bwd: C*ncls must be <= 1024");
+  cudaStream_t st = (cudaStream_t)stream;
+  {
+    // streaming kernel: few classes, C/8 a power of two that divides the warp; the grid keeps each thread's chunk fixed
+    const int ch = (int)(C >> 3);
+    static const bool no_stream = getenv("PCB_NO_HEAD_STREAM") != nullptr;
+    if (!no_stream && ncls <= 4 && ch <= 32 && (ch & (ch - 1)) == 0 && nvox * ch >= 256) {
+      int64_t nb = (nvox * ch + 255) / 256;
+      if (nb > 148 * 8) nb = 148 * 8;
+      dim3 grid_s((unsigned)nb, (unsigned)N);
+      const size_t smem_s = (size_t)(C * ncls + ncls) * sizeof(double);
+#define PCB_HEAD_STREAM(T, K) head_bwd_stream_kernel<T, K><<<grid_s, 256, smem_s, st>>>((const T*)dout, (const uint4*)x, w, (uint4*)dx, dW, db, (int)C, nvox)
+#define PCB_HEAD_STREAM_T(T)                                                             \
+      do {                                                                               \
+        if (ncls == 1) PCB_HEAD_STREAM(T, 1); else if (ncls == 2) PCB_HEAD_STREAM(T, 2); \
+        else if (ncls == 3) PCB_HEAD_STREAM(T, 3); else PCB_HEAD_STREAM(T, 4);           \
+      } while (0)
+      if (dtype == PCB_F32) PCB_HEAD_STREAM_T(float);
+      else if (dtype == PCB_F16) PCB_HEAD_STREAM_T(__half);
+      else if (dtype == PCB_BF16) PCB_HEAD_STREAM_T(__nv_bfloat16);
+      else { set_error("pcb_head_bwd: bad dtype %d", dtype); return PCB_ERR_INVALID; }
+#undef PCB_HEAD_STREAM_T
+#undef PCB_HEAD_STREAM
+      PCB_CHECK_LAUNCH("pcb_head_bwd");
+      return PCB_OK;
+    }
+  }
   const int TV = C <= 128 ? 128 : 32;
   const size_t smem = (size_t)(C * ncls + ncls * TV + TV * (C + 1)) * sizeof(float);
   PCB_CHECK_ARG(smem <= 200 * 1024, "pcb_head_bwd: shared memory");
   int blocks = (int)((nvox + TV - 1) / TV);
   if (blocks > 148 * 4) blocks = 148 * 4;
   dim3 grid((unsigned)blocks, (unsigned)N);
-  cudaStream_t st = (cudaStream_t)stream;
 #define PCB_HEAD_BWD(T)                                                                                                    \
   do {                                                                                                                     \
     cudaFuncSetAttribute(head_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);                     \

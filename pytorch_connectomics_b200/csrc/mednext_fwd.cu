@@ -597,6 +597,155 @@ __global__ void __launch_bounds__(256, 1) dwconv_same_persist_kernel(const float
   }
 }
 
+// ---------------------------------------------------------------------------- tiled stride-2 stencil, k = 3
+// Conv3d(k=3, stride 2, padding 1, groups=C) (MedNeXtDownBlock.conv1; also the data gradient of the transposed conv of
+// MedNeXtUpBlock).  One CTA = a 2x4x16 output tile x 32 channels; its 5x9x33 input brick (origin 2*o0-1, zero-filled
+// outside the volume) arrives as ONE bulk tensor copy, so 95 KB per CTA are in flight instead of a few dependent
+// 128-bit loads per thread (the untiled kernel is latency-bound: ncu long_scoreboard 12 warps/issue, 14 % of DRAM peak).
+// Thread = (8-channel chunk, ox, oy) and both oz of the tile: 45 LDS.128 feed 54 taps x 8 channels.
+constexpr int DN_Z = 2, DN_Y = 4, DN_X = 16;
+constexpr int DN_BZ = 2 * DN_Z + 1, DN_BY = 2 * DN_Y + 1, DN_BX = 2 * DN_X + 1;
+
+__global__ void __launch_bounds__(256, 2) dwconv_down3_tiled_kernel(const float* __restrict__ w, const float* __restrict__ bias,
+                                                                    uint4* __restrict__ y, double* __restrict__ stats,
+                                                                    const uint4* __restrict__ add, DwArgs a, int tiles_y,
+                                                                    int tiles_x, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(128) uint8_t dsm[];
+  uint4* s_in = reinterpret_cast<uint4*>(dsm);                               // [BZ][BY][BX][4 chunks]
+  float* s_w = reinterpret_cast<float*>(s_in + DN_BZ * DN_BY * DN_BX * 4);   // [27][32]
+  double* s_stats = reinterpret_cast<double*>(s_w + 27 * 32);                // [64]
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stats + 64);
+  const int tid = threadIdx.x, CH = a.C >> 3;
+  const int cg = blockIdx.y, n = blockIdx.z;
+  int t = blockIdx.x;
+  const int tx = t % tiles_x; t /= tiles_x;
+  const int ty = t % tiles_y, tz = t / tiles_y;
+  const int z0 = tz * DN_Z, y0 = ty * DN_Y, x0 = tx * DN_X;
+  if (tid == 0) {
+    mbar_init(s_bar, 1);
+    fence_mbar_init();
+    fence_proxy_async_smem();
+    mbar_arrive_expect_tx(s_bar, (uint32_t)(DN_BZ * DN_BY * DN_BX * 64));
+    tma_load_5d(s_in, &tmap, cg * 32, 2 * x0 - 1, 2 * y0 - 1, 2 * z0 - 1, n, s_bar);
+  }
+  for (int i = tid; i < 27 * 32; i += 256) s_w[i] = w[(i >> 5) * a.C + cg * 32 + (i & 31)];
+  if (tid < 64) s_stats[tid] = 0.0;
+  __syncthreads();
+  mbar_wait(s_bar, 0);
+
+  const int cc = tid & 3, lx = (tid >> 2) & 15, ly = tid >> 6;
+  uint64_t acc[DN_Z][4];
+#pragma unroll
+  for (int z = 0; z < DN_Z; ++z)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[z][c] = 0ull;
+#pragma unroll 1
+  for (int pz = 0; pz < DN_BZ; ++pz) {        // input plane pz serves output lz with tap dz = pz - 2 lz in [0, 3)
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const uint4* row = s_in + ((pz * DN_BY + 2 * ly + dy) * DN_BX + 2 * lx) * 4 + cc;
+      uint64_t f[3][4];
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const uint4 v4 = row[dx * 4];
+        f[dx][0] = pk2(bf16_lo(v4.x), bf16_hi(v4.x)); f[dx][1] = pk2(bf16_lo(v4.y), bf16_hi(v4.y));
+        f[dx][2] = pk2(bf16_lo(v4.z), bf16_hi(v4.z)); f[dx][3] = pk2(bf16_lo(v4.w), bf16_hi(v4.w));
+      }
+#pragma unroll
+      for (int lz = 0; lz < DN_Z; ++lz) {
+        const int dz = pz - 2 * lz;
+        if (dz < 0 || dz > 2) continue;
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const float4* wp = reinterpret_cast<const float4*>(s_w + ((dz * 3 + dy) * 3 + dx) * 32 + cc * 8);
+          const float4 w0 = wp[0], w1 = wp[1];
+          acc[lz][0] = fma2(f[dx][0], pk2(w0.x, w0.y), acc[lz][0]);
+          acc[lz][1] = fma2(f[dx][1], pk2(w0.z, w0.w), acc[lz][1]);
+          acc[lz][2] = fma2(f[dx][2], pk2(w1.x, w1.y), acc[lz][2]);
+          acc[lz][3] = fma2(f[dx][3], pk2(w1.z, w1.w), acc[lz][3]);
+        }
+      }
+    }
+  }
+  float bv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (bias != nullptr) {
+    const float4* bp = reinterpret_cast<const float4*>(bias + cg * 32 + cc * 8);
+    const float4 b0 = __ldg(bp), b1 = __ldg(bp + 1);
+    bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+  }
+  float ssum[8], ssq[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) { ssum[c] = 0.f; ssq[c] = 0.f; }
+  const int oy = y0 + ly, ox = x0 + lx;
+#pragma unroll
+  for (int lz = 0; lz < DN_Z; ++lz) {
+    const int oz = z0 + lz;
+    if (oz >= a.Do || oy >= a.Ho || ox >= a.Wo) continue;
+    const int64_t off = ((((int64_t)n * a.Do + oz) * a.Ho + oy) * a.Wo + ox) * CH + cg * 4 + cc;
+    float o[8];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) upk2(acc[lz][c], o[2 * c], o[2 * c + 1]);
+    if (add != nullptr) {
+      float f[8];
+      unpack8(__ldg(add + off), f);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) o[c] += f[c];
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      o[c] = round_bf16(o[c] + bv[c]);
+      ssum[c] += o[c];
+      ssq[c] = fmaf(o[c], o[c], ssq[c]);
+    }
+    y[off] = pack8(o);
+  }
+  if (stats == nullptr) return;
+#pragma unroll
+  for (int off = 4; off <= 16; off <<= 1) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      ssum[c] += __shfl_xor_sync(0xffffffffu, ssum[c], off);
+      ssq[c] += __shfl_xor_sync(0xffffffffu, ssq[c], off);
+    }
+  }
+  if ((tid & 31) < 4) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      atomicAdd(&s_stats[cc * 8 + c], (double)ssum[c]);
+      atomicAdd(&s_stats[32 + cc * 8 + c], (double)ssq[c]);
+    }
+  }
+  __syncthreads();
+  if (tid < 64) {
+    const int which = tid >> 5, c = tid & 31;
+    atomicAdd(&stats[(int64_t)n * 2 * a.C + which * a.C + cg * 32 + c], s_stats[tid]);
+  }
+}
+
+static bool launch_dw_down3_tiled(cudaStream_t st, const uint4* x, const float* w, const float* b, uint4* y, double* stats,
+                                  const uint4* add, DwArgs a, int64_t N) {
+  static const bool off = getenv("PCB_NO_DOWN3") != nullptr || getenv("PCB_NO_TMA") != nullptr;
+  if (off) return false;
+  const size_t smem = (size_t)DN_BZ * DN_BY * DN_BX * 64 + 27 * 32 * 4 + 64 * 8 + 16;
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  if (!make_brick_tensor_map(&tmap, x, N, a.D, a.H, a.W, a.C, DN_BZ, DN_BY, DN_BX)) return false;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(dwconv_down3_tiled_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (cudaFuncSetAttribute(dwconv_down3_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    configured = true;
+  }
+  const int tz = (a.Do + DN_Z - 1) / DN_Z, ty = (a.Ho + DN_Y - 1) / DN_Y, tx = (a.Wo + DN_X - 1) / DN_X;
+  if ((int64_t)tz * ty * tx >= (1ll << 31) || N > 65535 || a.C / 32 > 65535) return false;
+  dim3 grid((unsigned)(tz * ty * tx), (unsigned)(a.C / 32), (unsigned)N);
+  dwconv_down3_tiled_kernel<<<grid, 256, smem, st>>>(w, b, y, stats, add, a, ty, tx, tmap);
+  return true;
+}
+
 template <int K>
 static bool launch_dw_tiled(cudaStream_t st, const uint4* x, const float* w, const float* b, uint4* y, double* stats,
                             const uint4* add, DwArgs a, int64_t N) {
@@ -1460,6 +1609,13 @@ static int dwconv_launch(const void* x, const float* w, const float* b, void* y,
     else if (k == 5) ok = launch_dw_tiled<5>(st, (const uint4*)x, w, b, (uint4*)y, stats, (const uint4*)add, a, N);
     else ok = launch_dw_tiled<7>(st, (const uint4*)x, w, b, (uint4*)y, stats, (const uint4*)add, a, N);
     if (ok) { PCB_CHECK_LAUNCH(what); return PCB_OK; }
+  }
+  if (mode == PCB_DW_DOWN && k == 3 && C % 32 == 0 && a.add_mode != 2 && a.Do == (a.D - 1) / 2 + 1 && a.Ho == (a.H - 1) / 2 + 1 &&
+      a.Wo == (a.W - 1) / 2 + 1) {
+    if (launch_dw_down3_tiled(st, (const uint4*)x, w, b, (uint4*)y, stats, (const uint4*)add, a, N)) {
+      PCB_CHECK_LAUNCH(what);
+      return PCB_OK;
+    }
   }
   const size_t smem = 2 * C * sizeof(double);
   static const bool no_up3 = getenv("PCB_NO_UP3") != nullptr;

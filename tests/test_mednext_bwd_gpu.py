@@ -117,7 +117,7 @@ def test_up_block_backward_with_skip():
     assert torch.equal(ncdhw(sc.grad), gout)   # d(skip) is the incoming gradient, untouched
 
 
-@pytest.mark.parametrize("c,ncls", [(32, 1), (32, 3), (16, 12), (512, 2)])
+@pytest.mark.parametrize("c,ncls", [(32, 1), (32, 3), (16, 12), (512, 2), (64, 4), (8, 2), (256, 1)])
 def test_head_backward(c, ncls):
     torch.manual_seed(5)
     o = OM.OutBlock(c, ncls)

@@ -62,7 +62,8 @@ def test_stem(cin, c):
         assert rel(ncdhw(got), want) < (4e-3 if dt == torch.float32 else 8e-3)
 
 
-@pytest.mark.parametrize("c,k,size", [(32, 3, (10, 12, 14)), (16, 5, (9, 8, 11)), (64, 7, (8, 8, 8)), (32, 3, (7, 9, 13))])
+@pytest.mark.parametrize("c,k,size", [(32, 3, (10, 12, 14)), (16, 5, (9, 8, 11)), (64, 7, (8, 8, 8)), (32, 3, (7, 9, 13)),
+                                      (64, 3, (11, 18, 41))])
 @pytest.mark.parametrize("mode", ["same", "down", "up"])
 def test_dwconv_and_stats(c, k, size, mode):
     torch.manual_seed(1)
