@@ -249,6 +249,7 @@ def main():
     ap.add_argument("--mode", default="train", choices=["train", "infer"])
     ap.add_argument("--batch", type=int, default=4, help="sub-volumes per GPU per step (tutorials/mito_lucchi++ trains with 4)")
     ap.add_argument("--volume", type=int, default=480)
+    ap.add_argument("--sw-batch", type=int, default=2, help="windows per network call in --mode infer")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-ops", action="store_true", help="time every pcb200 op with CUDA events (stderr table)")
     ap.add_argument("--no-graph", action="store_true", help="run the timed steps eagerly instead of as one CUDA graph")
@@ -393,7 +394,7 @@ def main():
     else:
         model.eval()
         from pytorch_connectomics_b200.inference.window import EagerSlidingWindowEngine
-        eng = EagerSlidingWindowEngine(roi_size=(SIDE,) * 3, sw_batch_size=2, overlap=0.5, mode="bump",
+        eng = EagerSlidingWindowEngine(roi_size=(SIDE,) * 3, sw_batch_size=a.sw_batch, overlap=0.5, mode="bump",
                                        padding_mode="constant", cval=0.0)
         net = lambda t: model(t)  # noqa: E731
         if world > 1:
@@ -402,7 +403,7 @@ def main():
             from pytorch_connectomics_b200.inference.sharded import ZSlabShardedEngine
             torch.manual_seed(99)
             vol = torch.rand(1, 1, a.volume * world, a.volume, a.volume, device=dev).half()
-            sh = ZSlabShardedEngine(roi_size=(SIDE,) * 3, sw_batch_size=2, overlap=0.5, mode="bump",
+            sh = ZSlabShardedEngine(roi_size=(SIDE,) * 3, sw_batch_size=a.sw_batch, overlap=0.5, mode="bump",
                                     padding_mode="constant", cval=0.0, device=dev)
 
             def step():
@@ -436,7 +437,7 @@ def main():
             hv = torch.rand(1, 1, a.volume * world, a.volume, a.volume).half().pin_memory()
         else:
             hv = torch.rand(1, 1, a.volume, a.volume, a.volume).half().pin_memory()
-        eng_cpu = EagerSlidingWindowEngine(roi_size=(SIDE,) * 3, sw_batch_size=2, overlap=0.5, mode="bump",
+        eng_cpu = EagerSlidingWindowEngine(roi_size=(SIDE,) * 3, sw_batch_size=a.sw_batch, overlap=0.5, mode="bump",
                                            padding_mode="constant", cval=0.0, sw_device=dev, output_device="cpu")
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
