@@ -249,7 +249,7 @@ def main():
     ap.add_argument("--mode", default="train", choices=["train", "infer"])
     ap.add_argument("--batch", type=int, default=4, help="sub-volumes per GPU per step (tutorials/mito_lucchi++ trains with 4)")
     ap.add_argument("--volume", type=int, default=480)
-    ap.add_argument("--sw-batch", type=int, default=2, help="windows per network call in --mode infer")
+    ap.add_argument("--sw-batch", type=int, default=4, help="windows per network call in --mode infer")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-ops", action="store_true", help="time every pcb200 op with CUDA events (stderr table)")
     ap.add_argument("--no-graph", action="store_true", help="run the timed steps eagerly instead of as one CUDA graph")

@@ -166,6 +166,17 @@ int pcb_head_bwd(const void* dout, int dtype, const void* x, const float* w, voi
 int pcb_stem_bwd(const void* g, const void* x, int in_dtype, double* dW, double* db, int64_t N, int64_t Cin,
                  int64_t C, int64_t nvox, void* stream);
 
+/* channels-first LayerNorm of the MedNeXt blocks, cfg.model.mednext.norm = "layer" (upstream nnunet_mednext
+ * blocks.py::LayerNorm(data_format="channels_first"), selected at mednext_models.py:449-476): per row (voxel) of a
+ * channels-last bf16 [rows, C] tensor, out = (y - mean_c) / sqrt(var_c + 1e-5) * weight + bias.  C/8 must be a power of
+ * two (PCB_ERR_UNSUPPORTED otherwise).  The normalised tensor feeds pcb_mlp_fwd with identity GroupNorm constants. */
+int pcb_layernorm_fwd(const void* y, const float* weight, const float* bias, void* out, int64_t C, int64_t rows,
+                      void* stream);
+/* its backward: dy = rstd*(g*w - mean_c(g*w) - xhat*mean_c(g*w*xhat)) (bf16); dweight[c] += sum g*xhat, dbias[c] += sum g
+ * (f64, caller zeroes). */
+int pcb_layernorm_bwd(const void* g, const void* y, const float* weight, void* dy, double* dweight, double* dbias,
+                      int64_t C, int64_t rows, void* stream);
+
 /* ------------------------------------------------------------------ dense conv path (MONAI UNet, `monai_unet`)
  * (monai.networks.blocks.{Convolution,ResidualUnit,ADN} as built by
  *  connectomics/models/architectures/monai_models.py:235-248)

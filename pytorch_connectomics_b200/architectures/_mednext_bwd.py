@@ -107,15 +107,16 @@ def _tn(A, B, stats, gamma, beta, dW, ldm, ldn, db, n, box, map_a, a_size, a_col
 
 class BlockFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, skip, mode, k, do_res, has_rc, *params):
-        out, y, stats = ops.block_forward(x, skip, list(params), mode, k, do_res, has_rc)
+    def forward(ctx, x, skip, mode, k, do_res, has_rc, norm, *params):
+        out, y, stats = ops.block_forward(x, skip, list(params), mode, k, do_res, has_rc, norm)
         ctx.save_for_backward(x, y, stats, *params)
-        ctx.cfg = (mode, k, do_res, has_rc, skip is not None)
+        ctx.cfg = (mode, k, do_res, has_rc, skip is not None, norm)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        mode, k, do_res, has_rc, has_skip = ctx.cfg
+        mode, k, do_res, has_rc, has_skip, norm = ctx.cfg
+        layer = norm == "layer"
         x, y, stats, *params = ctx.saved_tensors
         w1, b1, gamma, beta, w2, b2, w3, b3 = params[:8]
         dout = _cl_grad(dout)
@@ -129,6 +130,12 @@ class BlockFn(torch.autograd.Function):
         vy = ysize[0] * ysize[1] * ysize[2]
         g_f32, b_f32 = ops.packed(gamma, "f32"), ops.packed(beta, "f32")
         side = _Side(dev)
+        y_raw = y
+        if layer:
+            # channels-first LayerNorm: re-normalise y (one streaming kernel) and run the MLP gradient kernels with
+            # identity GroupNorm constants; the norm's own backward is pcb_layernorm_bwd below
+            y = ops.layernorm_forward(y_raw, gamma, beta)
+            stats, g_f32, b_f32 = ops.identity_groupnorm(n, c, vy, dev)
 
         dyhat = torch.empty((n, *ysize, c), device=dev, dtype=_BF16)
         gstats = torch.zeros((n, 2, c), device=dev, dtype=torch.float64)
@@ -161,16 +168,33 @@ class BlockFn(torch.autograd.Function):
                 sst = L.stream_ptr(dev)
                 _tn(dout, hact, None, None, None, dw3, h, 1, db3, n, ysize, MAP_PLUS1 if mode == L.DW_UP else MAP_IDENT,
                     osize, co, co, MAP_IDENT, ysize, h, sst)
-                _tn(dh, y, stats, g_f32, b_f32, dw2, c, 1, db2, n, ysize, MAP_IDENT, ysize, h, h, MAP_IDENT, ysize, c, sst)
+                if layer:
+                    _tn(dh, y, None, None, None, dw2, c, 1, db2, n, ysize, MAP_IDENT, ysize, h, h, MAP_IDENT, ysize, c, sst)
+                else:
+                    _tn(dh, y, stats, g_f32, b_f32, dw2, c, 1, db2, n, ysize, MAP_IDENT, ysize, h, h, MAP_IDENT, ysize, c, sst)
             del hact, dh
-        # ---- GroupNorm backward
+        # ---- norm backward
         dy = torch.empty_like(y)
-        db1 = torch.zeros((c,), device=dev, dtype=torch.float64)
-        with L.prof(f"gn_bwd:C{c}V{vy}"):
-          L.check(lib.pcb_gn_bwd(L.ptr(dyhat), L.ptr(y), L.ptr(stats), L.ptr(gstats), L.ptr(g_f32), L.ptr(dy), L.ptr(db1),
-                                 ctypes.c_int64(n), ctypes.c_int64(c), ctypes.c_int64(vy), st), "pcb_gn_bwd")
-        dgamma = gstats[:, 1].sum(0).float()
-        dbeta = gstats[:, 0].sum(0).float()
+        if layer:
+            dg64 = torch.zeros((c,), device=dev, dtype=torch.float64)
+            db64 = torch.zeros((c,), device=dev, dtype=torch.float64)
+            with L.prof(f"layernorm_bwd:C{c}V{vy}"):
+                L.check(lib.pcb_layernorm_bwd(L.ptr(dyhat), L.ptr(y_raw), L.ptr(ops.packed(gamma, "f32")), L.ptr(dy),
+                                              L.ptr(dg64), L.ptr(db64), ctypes.c_int64(c), ctypes.c_int64(n * vy), st),
+                        "pcb_layernorm_bwd")
+            dgamma, dbeta = dg64.float(), db64.float()
+            cs = torch.zeros((2, c), device=dev, dtype=torch.float64)     # conv1 bias gradient = per-channel sum of dy
+            L.check(lib.pcb_channel_stats(L.ptr(dy), L.ptr(cs), ctypes.c_int64(c), ctypes.c_int64(n * vy), st),
+                    "pcb_channel_stats")
+            db1 = cs[0]
+            y = y_raw
+        else:
+            db1 = torch.zeros((c,), device=dev, dtype=torch.float64)
+            with L.prof(f"gn_bwd:C{c}V{vy}"):
+                L.check(lib.pcb_gn_bwd(L.ptr(dyhat), L.ptr(y), L.ptr(stats), L.ptr(gstats), L.ptr(g_f32), L.ptr(dy), L.ptr(db1),
+                                       ctypes.c_int64(n), ctypes.c_int64(c), ctypes.c_int64(vy), st), "pcb_gn_bwd")
+            dgamma = gstats[:, 1].sum(0).float()
+            dbeta = gstats[:, 0].sum(0).float()
         del dyhat
         # ---- depthwise weight gradient (side stream: only needs dy and x)
         dw1 = torch.zeros((k * k * k, c), device=dev, dtype=torch.float64)
@@ -226,7 +250,7 @@ class BlockFn(torch.autograd.Function):
             grads_rc = [dwr.reshape(params[8].shape), db3.clone()]
         grads = [dw1.t().reshape(w1.shape).float(), db1.float(), dgamma, dbeta,
                  dw2.reshape(w2.shape), db2, dw3.reshape(w3.shape), db3] + grads_rc
-        return (dx, dskip, None, None, None, None, *grads)
+        return (dx, dskip, None, None, None, None, None, *grads)
 
 
 class StemFn(torch.autograd.Function):

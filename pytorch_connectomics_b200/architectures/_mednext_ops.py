@@ -115,8 +115,40 @@ def stem_forward(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Ten
     return _mark(out)
 
 
+_IDENT: Dict[tuple, tuple] = {}
+
+
+def identity_groupnorm(n: int, c: int, vy: int, device) -> tuple:
+    """(stats [n,2,c] f64, ones [c] f32, zeros [c] f32) that make the kernels' GroupNorm-apply the identity
+    (sum 0, sum of squares V*(1-eps) -> mean 0, rstd 1): used when the block's norm is the channels-first
+    LayerNorm, which runs as its own kernel in front of the fused MLP."""
+    key = (str(device), n, c, vy)
+    ent = _IDENT.get(key)
+    if ent is None:
+        stats = torch.zeros((n, 2, c), device=device, dtype=torch.float64)
+        stats[:, 1] = float(vy) * (1.0 - 1e-5)
+        ent = (stats, torch.ones(c, device=device, dtype=torch.float32), torch.zeros(c, device=device, dtype=torch.float32))
+        if len(_IDENT) > 256:
+            _IDENT.clear()
+        _IDENT[key] = ent
+    return ent
+
+
+def layernorm_forward(y: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """upstream blocks.py::LayerNorm(channels_first) on a channels-last bf16 tensor (``pcb_layernorm_fwd``)."""
+    c = int(y.shape[-1])
+    rows = y.numel() // c
+    out = torch.empty_like(y)
+    st = L.lib().pcb_layernorm_fwd(L.ptr(y), L.ptr(packed(weight, "f32")), L.ptr(packed(bias, "f32")), L.ptr(out),
+                                   ctypes.c_int64(c), ctypes.c_int64(rows), L.stream_ptr(y.device))
+    if st == -3:
+        raise NotImplementedError(L.lib().pcb_last_error().decode())
+    L.check(st, "pcb_layernorm_fwd")
+    return out
+
+
 def block_forward(x: torch.Tensor, skip: Optional[torch.Tensor], params: List[torch.Tensor], mode: int, k: int,
-                  do_res: bool, has_rc: bool):
+                  do_res: bool, has_rc: bool, norm: str = "group"):
     """Returns (out, y, stats).  x: [N,D,H,W,C] bf16."""
     w1, b1, gamma, beta, w2, b2, w3, b3 = params[:8]
     n, size, c = int(x.shape[0]), [int(s) for s in x.shape[1:4]], int(x.shape[4])
@@ -132,6 +164,13 @@ def block_forward(x: torch.Tensor, skip: Optional[torch.Tensor], params: List[to
         L.check(lib.pcb_dwconv_fwd(L.ptr(x), L.ptr(packed(w1, "dw")), L.ptr(packed(b1, "f32")), L.ptr(y), L.ptr(stats),
                                    ctypes.c_int64(n), L.i64x(size), ctypes.c_int64(c), ctypes.c_int(k),
                                    ctypes.c_int(mode), st), "pcb_dwconv_fwd")
+    y_in, gam_t, bet_t = y, packed(gamma, "f32"), packed(beta, "f32")
+    if norm == "layer":
+        with L.prof(f"layernorm_fwd:C{c}V{vy}"):
+            y_in = layernorm_forward(y, gamma, beta)
+        stats_in, gam_t, bet_t = identity_groupnorm(n, c, vy, dev)
+    else:
+        stats_in = stats
     out = torch.empty((n, *osize, co), device=dev, dtype=_BF16)
     res = None
     if mode == L.DW_SAME and do_res:
@@ -152,7 +191,7 @@ def block_forward(x: torch.Tensor, skip: Optional[torch.Tensor], params: List[to
     if ws > 0:      # deep levels: two column-split GEMM launches through an HBM/L2-resident expanded activation
         hact = torch.empty((n, *osize, h), device=dev, dtype=_BF16)
         with L.prof(f"mlp_fwd_deep:m{mode}C{c}H{h}Co{co}V{vo}"):
-            L.check(lib.pcb_mlp_fwd_deep(L.ptr(y), L.ptr(stats), L.ptr(packed(gamma, "f32")), L.ptr(packed(beta, "f32")),
+            L.check(lib.pcb_mlp_fwd_deep(L.ptr(y_in), L.ptr(stats_in), L.ptr(gam_t), L.ptr(bet_t),
                                          L.ptr(packed(w2, "pw")), L.ptr(packed(b2, "f32")), L.ptr(packed(w3, "pw")),
                                          L.ptr(packed(b3, "f32")), L.ptr(res), L.ptr(x if has_rc else None), L.ptr(wr),
                                          L.ptr(br), L.ptr(out), L.ptr(hact), ctypes.c_int64(n), L.i64x(osize), L.i64x(size),
@@ -160,7 +199,7 @@ def block_forward(x: torch.Tensor, skip: Optional[torch.Tensor], params: List[to
                                          ctypes.c_int(mode), st), "pcb_mlp_fwd_deep")
         return _mark(out), y, stats
     with L.prof(f"mlp_fwd:m{mode}C{c}H{h}Co{co}V{vo}"):
-        L.check(lib.pcb_mlp_fwd(L.ptr(y), L.ptr(stats), L.ptr(packed(gamma, "f32")), L.ptr(packed(beta, "f32")),
+        L.check(lib.pcb_mlp_fwd(L.ptr(y_in), L.ptr(stats_in), L.ptr(gam_t), L.ptr(bet_t),
                                 L.ptr(packed(w2, "pw")), L.ptr(packed(b2, "f32")), L.ptr(packed(w3, "pw")),
                                 L.ptr(packed(b3, "f32")), L.ptr(res), L.ptr(x if has_rc else None), L.ptr(wr), L.ptr(br),
                                 L.ptr(out), ctypes.c_int64(n), L.i64x(osize), L.i64x(size), ctypes.c_int64(c),
@@ -195,14 +234,14 @@ def stem_apply(x, w, b):
     return stem_forward(x, w, b)
 
 
-def block_apply(x, skip, params, mode, k, do_res, has_rc):
+def block_apply(x, skip, params, mode, k, do_res, has_rc, norm="group"):
     x = as_channels_last(x)
     if skip is not None:
         skip = as_channels_last(skip)
     if _needs_grad(x, skip, *params):
         from . import _mednext_bwd as B
-        return _mark(B.BlockFn.apply(x, skip, mode, k, do_res, has_rc, *params))
-    return block_forward(x, skip, params, mode, k, do_res, has_rc)[0]
+        return _mark(B.BlockFn.apply(x, skip, mode, k, do_res, has_rc, norm, *params))
+    return block_forward(x, skip, params, mode, k, do_res, has_rc, norm)[0]
 
 
 def head_apply(x, w, b, out_dtype, conv_layout=False):

@@ -32,6 +32,21 @@ def _unsupported(what: str):
         f"pcb200 MedNeXt: {what} is not implemented in the B200 engine yet (3-D, GroupNorm, no GRN only).")
 
 
+class LayerNorm(nn.Module):
+    """upstream blocks.py::LayerNorm(data_format="channels_first"), eps 1e-5 — parameter container (``weight``,
+    ``bias``; same ``state_dict`` keys as the GroupNorm variant); the arithmetic is ``csrc/layernorm.cu``."""
+
+    def __init__(self, normalized_shape: int, eps: float = 1e-5, data_format: str = "channels_first"):
+        super().__init__()
+        if abs(eps - 1e-5) > 1e-12:
+            _unsupported("LayerNorm eps != 1e-5")
+        self.weight = nn.Parameter(torch.ones(normalized_shape))
+        self.bias = nn.Parameter(torch.zeros(normalized_shape))
+        self.eps = eps
+        self.data_format = data_format
+        self.normalized_shape = (normalized_shape,)
+
+
 class MedNeXtBlock(nn.Module):
     """upstream blocks.py::MedNeXtBlock — conv1 (depthwise k^3) -> GroupNorm(C groups) -> conv2 (1x1,
     C->rC) -> GELU -> conv3 (1x1, rC->Cout) [+ x].  ``forward`` takes/returns channels-last bf16."""
@@ -44,8 +59,8 @@ class MedNeXtBlock(nn.Module):
         super().__init__()
         if dim != "3d":
             _unsupported("dim='2d'")
-        if norm_type != "group":
-            _unsupported("norm_type='layer'")
+        if norm_type not in ("group", "layer"):
+            raise ValueError(f"norm_type must be 'group' or 'layer', got {norm_type!r}")
         if grn:
             _unsupported("grn=True")
         if n_groups is not None and n_groups != in_channels:
@@ -54,7 +69,9 @@ class MedNeXtBlock(nn.Module):
         self.dim = dim
         self.grn = grn
         self.conv1 = nn.Conv3d(in_channels, in_channels, kernel_size, 1, kernel_size // 2, groups=in_channels)
-        self.norm = nn.GroupNorm(num_groups=in_channels, num_channels=in_channels)
+        self.norm_type = norm_type
+        self.norm = (nn.GroupNorm(num_groups=in_channels, num_channels=in_channels) if norm_type == "group"
+                     else LayerNorm(in_channels))
         self.conv2 = nn.Conv3d(in_channels, exp_r * in_channels, 1)
         self.act = nn.GELU()
         self.conv3 = nn.Conv3d(exp_r * in_channels, out_channels, 1)
@@ -70,7 +87,7 @@ class MedNeXtBlock(nn.Module):
     def forward(self, x: torch.Tensor, skip: Optional[torch.Tensor] = None) -> torch.Tensor:
         has_rc = getattr(self, "res_conv", None) is not None
         return ops.block_apply(x, skip, self._params(), self._dw_mode, self.conv1.kernel_size[0],
-                               bool(self.do_res), has_rc)
+                               bool(self.do_res), has_rc, self.norm_type)
 
 
 class MedNeXtDownBlock(MedNeXtBlock):

@@ -42,6 +42,7 @@ struct GemmArgs {
   int64_t ntiles;                        // N * tps * ntn
   uint32_t dm2, dm1; int ds2, ds1;       // exact division by o2 / o1 (see mf_fdiv in mednext_fwd.cu)
   // ---- backward (data-gradient) variants
+  int bres;                              // weights resident: the CTA keeps ONE column tile, all K chunks of B staged once
   int dual;                              // segment 2 feeds a SECOND accumulator: out = GELU(acc1 + bias), out2 = acc2 * GELU'(acc1 + bias)
   uint4* out2;                           // [N][Vout][Nout] bf16 (dual)
   int map2;                              // segment-2 row source: 0 per `mode`, 1 output row, 2 output row + 1 on every axis (o1, o2 = box dims)
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gemm_ws_kernel(GemmArgs a) {
   uint8_t* sA = smem;                                        // S x [128 x 64]
   const int bstage = (BN > 128 ? BN : 128) * 128;            // a loader call always writes 128 rows
   uint8_t* sB = sA + S * 16384;                              // S x [max(BN,128) x 64]
-  float* sScale = reinterpret_cast<float*>(sB + S * bstage); // [N][K1]
+  float* sScale = reinterpret_cast<float*>(sB + (a.bres ? kch : S) * bstage); // [N][K1]
   float* sShift = sScale + nsc;
   int* sRow = reinterpret_cast<int*>(sShift + nsc);   // [4 loader warps][2][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sRow + GW_LOAD * 2 * 128);
@@ -154,13 +155,15 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gemm_ws_kernel(GemmArgs a) {
   uint64_t* empty = bars + 4;        // [S]  MMA -> loaders
   uint64_t* acc_full = bars + 8;     // [2]  MMA -> epilogue
   uint64_t* acc_empty = bars + 10;   // [2]  epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* b_full = bars + 12;      // resident weights staged (4 loader warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const uint32_t tmem_cols = tmem_cols_pow2(2 * accw);
   if (warp == GW_LOAD + GW_EPI) tmem_alloc(tmem_slot, tmem_cols);
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) { mbar_init(&full[i], 32); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+    mbar_init(b_full, GW_LOAD);
     fence_mbar_init();
   }
   if (norm) {
@@ -193,7 +196,12 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gemm_ws_kernel(GemmArgs a) {
   const uint32_t tmem_base = *tmem_slot;
   // this CTA's tiles: t = blockIdx.x + i * gridDim.x;  column tile fastest so that CTAs running side by side
   // share the A rows through L2
-  const int64_t ntl = (int64_t)blockIdx.x < a.ntiles ? (a.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  // resident weights: column tile = blockIdx.x % ntn for the CTA's whole life, row tiles strided by gridDim.x / ntn
+  const int64_t mtiles = a.tps * a.N;
+  const int nrc = a.bres ? (int)(gridDim.x / a.ntn) : 0;
+  const int rowcta = a.bres ? (int)(blockIdx.x / a.ntn) : 0, nt_fixed = a.bres ? (int)(blockIdx.x % a.ntn) : 0;
+  const int64_t ntl = a.bres ? (rowcta < mtiles ? (mtiles - rowcta + nrc - 1) / nrc : 0)
+                             : ((int64_t)blockIdx.x < a.ntiles ? (a.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
 
   if (warp < GW_LOAD) {
     // ===================================================================== loaders
@@ -202,12 +210,27 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gemm_ws_kernel(GemmArgs a) {
     int64_t cached_mt = -1;
     const bool need_tab = (a.map1 && a.mode == PCB_DW_UP) || a.K2 > 0;
     const int64_t nchunks = ntl * kch;
+    if (a.bres) {   // the CTA's weight column tile, every K chunk, once
+      if (ntl > 0) {
+        for (int kc = warp; kc < kch; kc += GW_LOAD) {
+          const bool seg1 = kc < kch1;
+          const int64_t bp8 = (seg1 ? a.K1 : a.K2) >> 3;
+          const uint4* bsrc = (seg1 ? a.b : a.b2) + (int64_t)nt_fixed * BN * bp8 + (seg1 ? kc : kc - kch1) * 8;
+          for (int h = 0; h < BN; h += 128)
+            gw_stage_k64<false, false>(sB + kc * bstage + h * 128, bsrc + (int64_t)h * bp8, bp8, nullptr, 0, min(128, BN - h),
+                                       nullptr, nullptr, lane);
+        }
+        fence_proxy_async_smem();
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(b_full);
+    }
     for (int64_t q = warp; q < nchunks; q += GW_LOAD) {
       const int64_t i = q / kch;
       const int kc = (int)(q - i * kch);
       const int64_t t = blockIdx.x + i * gridDim.x;
-      const int64_t mt = t / a.ntn;
-      const int nt = (int)(t - mt * a.ntn);
+      const int64_t mt = a.bres ? rowcta + i * nrc : t / a.ntn;
+      const int nt = a.bres ? nt_fixed : (int)(t - mt * a.ntn);
       const int n = (int)(mt / a.tps);
       const int tile0 = (int)((mt - (int64_t)n * a.tps) * 128);
       const int s = (int)(q % S);
@@ -251,8 +274,9 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gemm_ws_kernel(GemmArgs a) {
         bp8 = p8;
         bsrc = a.b2 + (int64_t)nt * BN * p8 + (kc - kch1) * 8;
       }
-      for (int h = 0; h < BN; h += 128)
-        gw_stage_k64<false, false>(dB + h * 128, bsrc + (int64_t)h * bp8, bp8, nullptr, 0, min(128, BN - h), nullptr, nullptr, lane);
+      if (!a.bres)
+        for (int h = 0; h < BN; h += 128)
+          gw_stage_k64<false, false>(dB + h * 128, bsrc + (int64_t)h * bp8, bp8, nullptr, 0, min(128, BN - h), nullptr, nullptr, lane);
       fence_proxy_async_smem();
       mbar_arrive(&full[s]);
     }
@@ -261,6 +285,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gemm_ws_kernel(GemmArgs a) {
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
       int64_t q = 0;
+      if (a.bres && ntl > 0) { mbar_wait(b_full, 0); tc_fence_after(); }
       for (int64_t i = 0; i < ntl; ++i) {
         const int g = (int)(i & 1);
         if (i >= 2) mbar_wait(&acc_empty[g], (uint32_t)(((i >> 1) - 1) & 1));
@@ -274,7 +299,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gemm_ws_kernel(GemmArgs a) {
           mbar_wait(&full[s], (uint32_t)((q / S) & 1));
           tc_fence_after();
           const uint64_t dA = umma_desc(smem_u32(sA + s * 16384), 128, 1024);
-          const uint64_t dB = umma_desc(smem_u32(sB + s * bstage), 128, 1024);
+          const uint64_t dB = umma_desc(smem_u32(sB + (a.bres ? kc : s) * bstage), 128, 1024);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_bf16(acc, dA + (uint64_t)(k * 16), dB + (uint64_t)(k * 16), idesc, (kc > kfirst || k > 0) ? 1u : 0u);
@@ -292,8 +317,8 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gemm_ws_kernel(GemmArgs a) {
     const int n8 = a.Nout >> 3;
     for (int64_t i = eg; i < ntl; i += 2) {
       const int64_t t = blockIdx.x + i * gridDim.x;
-      const int64_t mt = t / a.ntn;
-      const int nt = (int)(t - mt * a.ntn);
+      const int64_t mt = a.bres ? rowcta + i * nrc : t / a.ntn;
+      const int nt = a.bres ? nt_fixed : (int)(t - mt * a.ntn);
       const int n = (int)(mt / a.tps);
       const int ovi = (int)((mt - (int64_t)n * a.tps) * 128) + row;
       const bool in_range = ovi < (int)a.Vout;
@@ -444,11 +469,24 @@ static bool gw_launch(GemmArgs a, cudaStream_t st) {
   a.BN = bn;
   a.ntn = a.Nout / bn;
   a.ntiles = mtiles * a.ntn;
-  const size_t fixed = (a.stats ? (size_t)2 * a.N * (a.gst ? a.Nout : a.K1) * 4 : 0) + GW_LOAD * 2 * 128 * 4 + 12 * 8 + 16 + 128;
-  const size_t stage = 16384 + (size_t)(bn > 128 ? bn : 128) * 128;
+  const size_t fixed = (a.stats ? (size_t)2 * a.N * (a.gst ? a.Nout : a.K1) * 4 : 0) + GW_LOAD * 2 * 128 * 4 + 13 * 8 + 16 + 128;
+  const size_t bstage = (size_t)(bn > 128 ? bn : 128) * 128;
+  const int kch = (a.K1 + a.K2) >> 6;
+  // resident weights when every K chunk of the column tile fits next to >= 3 A stages and each CTA sees >= 3 row tiles
+  static const bool no_bres = getenv("PCB_NO_BRES") != nullptr;
   int S = 4;
-  while (S > 2 && fixed + S * stage > 227 * 1024) --S;
-  if (fixed + S * stage > 227 * 1024) return false;
+  size_t dyn = 0;
+  a.bres = 0;
+  if (!no_bres && a.ntn <= 148 && mtiles >= 3 * (148 / a.ntn) && fixed + kch * bstage + 3 * 16384 <= 227 * 1024) {
+    a.bres = 1;
+    while (S > 3 && fixed + kch * bstage + (size_t)S * 16384 > 227 * 1024) --S;
+    dyn = fixed + kch * bstage + (size_t)S * 16384;
+  } else {
+    const size_t stage = 16384 + bstage;
+    while (S > 2 && fixed + S * stage > 227 * 1024) --S;
+    if (fixed + S * stage > 227 * 1024) return false;
+    dyn = fixed + S * stage;
+  }
   a.S = S;
   gw_magic((uint32_t)(a.o2 > 0 ? a.o2 : 1), a.dm2, a.ds2);
   gw_magic((uint32_t)(a.o1 > 0 ? a.o1 : 1), a.dm1, a.ds1);
@@ -463,7 +501,8 @@ static bool gw_launch(GemmArgs a, cudaStream_t st) {
   }
   int ctas = 148;
   if (a.ntiles < ctas) ctas = (int)a.ntiles;
-  gemm_ws_kernel<<<ctas, GW_THREADS, fixed + S * stage, st>>>(a);
+  if (a.bres) ctas = (148 / a.ntn) * a.ntn;     // every CTA owns one column tile; mtiles >= 3 row tiles per CTA (checked above)
+  gemm_ws_kernel<<<ctas, GW_THREADS, dyn, st>>>(a);
   return true;
 }
 

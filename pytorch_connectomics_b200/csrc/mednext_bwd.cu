@@ -663,7 +663,8 @@ __global__ void __launch_bounds__(128) tn_gemm_kernel(TnArgs a) {
     cur_n = n;
     const uint4* An = a.A + (int64_t)n * a.a_sample8;
     const uint4* Bn = a.B + (int64_t)n * a.b_sample8;
-    staged_copy<8>(128 * m8n, tid, 128,
+    staged_copy<16>(128 * m8n, tid, 128,   // 16 loads in flight per thread: the kernel is latency-bound at 2 CTAs/SM
+       
         [&](int q) {
           const int v = m8pow2 ? (q >> m8sh) : (q / m8n), g8 = q - v * m8n;
           if (v0 + v >= a.V) return make_uint4(0, 0, 0, 0);
@@ -674,7 +675,7 @@ __global__ void __launch_bounds__(128) tn_gemm_kernel(TnArgs a) {
           const int v = m8pow2 ? (q >> m8sh) : (q / m8n), g8 = q - v * m8n;
           *reinterpret_cast<uint4*>(sA + g8 * sboA + v * 16) = val;
         });
-    staged_copy<8>(128 * nb8, tid, 128,
+    staged_copy<16>(128 * nb8, tid, 128,
         [&](int q) {
           const int v = n8pow2 ? (q >> n8sh) : (q / nb8), g8 = q - v * nb8;
           if (v0 + v >= a.V) return make_uint4(0, 0, 0, 0);
@@ -863,8 +864,11 @@ __global__ void __launch_bounds__(256) gn_dy_kernel(const uint4* __restrict__ g,
                                                     const double* __restrict__ stats, const double* __restrict__ gstats,
                                                     const float* __restrict__ gamma, uint4* __restrict__ dy,
                                                     double* __restrict__ dsum, int C, int64_t V, float inv_count) {
-  extern __shared__ double s_sum[];   // [C] doubles, then 5*[C] floats
-  float* s_k = reinterpret_cast<float*>(s_sum + C);   // mean, rstd, gamma*rstd, S1/V, S2/V
+  // dy = A*g + B*y + D per channel with A = gamma*rstd, B = -A*rstd*S2/V, D = A*(mean*rstd*S2/V - S1/V): the three
+  // coefficients are formed once per CTA in f64 and (power-of-two C/8) held in registers by the thread that owns the
+  // 8-channel chunk, so the streaming loop is 2 loads, 16 FMAs and 1 store per 8 elements.
+  extern __shared__ double s_sum[];   // [C] doubles, then 3*[C] floats
+  float* s_k = reinterpret_cast<float*>(s_sum + C);
   const int CH = C >> 3, n = blockIdx.y;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     s_sum[c] = 0.0;
@@ -872,38 +876,54 @@ __global__ void __launch_bounds__(256) gn_dy_kernel(const uint4* __restrict__ g,
     const double mean = sm * (double)inv_count;
     double var = q * (double)inv_count - mean * mean;
     if (var < 0.0) var = 0.0;
-    const float rstd = (float)(1.0 / sqrt(var + 1e-5));
-    s_k[c] = (float)mean; s_k[C + c] = rstd; s_k[2 * C + c] = gamma[c] * rstd;
-    s_k[3 * C + c] = (float)(gstats[(int64_t)n * 2 * C + c] * (double)inv_count);
-    s_k[4 * C + c] = (float)(gstats[(int64_t)n * 2 * C + C + c] * (double)inv_count);
+    const double rstd = (double)(float)(1.0 / sqrt(var + 1e-5));
+    const double A = (double)gamma[c] * rstd;
+    const double k1 = gstats[(int64_t)n * 2 * C + c] * (double)inv_count;
+    const double k2 = gstats[(int64_t)n * 2 * C + C + c] * (double)inv_count;
+    s_k[c] = (float)A; s_k[C + c] = (float)(-A * rstd * k2); s_k[2 * C + c] = (float)(A * (mean * rstd * k2 - k1));
   }
   __syncthreads();
   const int64_t items = V * CH;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;   // multiple of CH when CH | 256
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t first = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const uint4* gn = g + (int64_t)n * items;
+  const uint4* yn = y + (int64_t)n * items;
+  uint4* dn = dy + (int64_t)n * items;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  int cc_fixed = -1;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < items; i += stride) {
-    const int cc = (int)(i % CH);
-    if (cc_fixed >= 0 && cc != cc_fixed) {   // non power-of-two CH: flush and restart
+  if (stride % CH == 0) {            // the thread's channel chunk never changes
+    const int cc = (int)(first % CH);
+    float ka[8], kb[8], kd[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { atomicAdd(&s_sum[cc_fixed * 8 + j], (double)acc[j]); acc[j] = 0.f; }
+    for (int j = 0; j < 8; ++j) { ka[j] = s_k[cc * 8 + j]; kb[j] = s_k[C + cc * 8 + j]; kd[j] = s_k[2 * C + cc * 8 + j]; }
+    for (int64_t i = first; i < items; i += stride) {
+      float gv[8], yv[8], o[8];
+      unpack8(ldg_nc(gn + i), gv);
+      unpack8(ldg_nc(yn + i), yv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        o[j] = round_bf16(fmaf(ka[j], gv[j], fmaf(kb[j], yv[j], kd[j])));
+        acc[j] += o[j];
+      }
+      dn[i] = pack8(o);
     }
-    cc_fixed = cc;
-    float gv[8], yv[8], o[8];
-    unpack8(__ldg(g + (int64_t)n * items + i), gv);
-    unpack8(__ldg(y + (int64_t)n * items + i), yv);
+    if (first < items) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = cc * 8 + j;
-      const float xh = (yv[j] - s_k[c]) * s_k[C + c];
-      o[j] = round_bf16(s_k[2 * C + c] * (gv[j] - s_k[3 * C + c] - xh * s_k[4 * C + c]));
-      acc[j] += o[j];
+      for (int j = 0; j < 8; ++j) atomicAdd(&s_sum[cc * 8 + j], (double)acc[j]);
     }
-    dy[(int64_t)n * items + i] = pack8(o);
-  }
-  if (cc_fixed >= 0) {
+  } else {
+    for (int64_t i = first; i < items; i += stride) {
+      const int cc = (int)(i % CH);
+      float gv[8], yv[8], o[8];
+      unpack8(ldg_nc(gn + i), gv);
+      unpack8(ldg_nc(yn + i), yv);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(&s_sum[cc_fixed * 8 + j], (double)acc[j]);
+      for (int j = 0; j < 8; ++j) {
+        const int c = cc * 8 + j;
+        o[j] = round_bf16(fmaf(s_k[c], gv[j], fmaf(s_k[C + c], yv[j], s_k[2 * C + c])));
+        atomicAdd(&s_sum[c], (double)o[j]);
+      }
+      dn[i] = pack8(o);
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&dsum[i], s_sum[i]);
@@ -1596,10 +1616,11 @@ static int gn_bwd_impl(const void* g, const void* y, const double* stats, const 
   PCB_CHECK_ARG(g && y && stats && gstats && gamma && dy && dsum, "pcb_gn_bwd: null argument");
   PCB_CHECK_ARG(C % 8 == 0 && C > 0 && V > 0 && N > 0 && N <= 65535, "pcb_gn_bwd: bad shape");
   const int64_t items = V * (C / 8);
-  int blocks = (int)((items + 255) / 256);
+  int64_t blocks = (items + 256 * 4 - 1) / (256 * 4);      // >= 4 chunks per thread amortise the per-CTA coefficient setup
   if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
   dim3 grid((unsigned)blocks, (unsigned)N);
-  gn_dy_kernel<<<grid, 256, C * sizeof(double) + 5 * C * sizeof(float), (cudaStream_t)stream>>>((const uint4*)g, (const uint4*)y, stats, gstats, gamma,
+  gn_dy_kernel<<<grid, 256, C * sizeof(double) + 3 * C * sizeof(float), (cudaStream_t)stream>>>((const uint4*)g, (const uint4*)y, stats, gstats, gamma,
                                                                      (uint4*)dy, dsum, (int)C, V, (float)(1.0 / count));
   PCB_CHECK_LAUNCH("pcb_gn_bwd");
   return PCB_OK;

@@ -766,7 +766,9 @@ static bool launch_dw_tiled(cudaStream_t st, const uint4* x, const float* w, con
     configured = true;
   }
   const int tz = (a.D + DT_Z - 1) / DT_Z, ty = (a.H + DT_Y - 1) / DT_Y, tx = (a.W + DT_X - 1) / DT_X;
-  static const bool no_persist = getenv("PCB_NO_DW_PERSIST") != nullptr;
+  // measured on B200 (level 0, batch 4): the persistent double-buffered variant runs 8 warps/SM and loses to two
+  // resident non-persistent CTAs (374 vs 335 us per launch, the brick compute is ALU/FMA-issue bound) -> opt-in only
+  static const bool no_persist = getenv("PCB_DW_PERSIST") == nullptr;
   const size_t smem_p = (size_t)2 * (DT_Z + 2 * P) * (DT_Y + 2 * P) * (DT_X + 2 * P + 1) * 64 + (size_t)K * K * K * 32 * 4 + 64 * 8 + 32;
   if (use_tma && !no_persist && smem_p <= 227 * 1024) {
     static bool configured_p = false;

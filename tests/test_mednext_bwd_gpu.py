@@ -272,3 +272,42 @@ def test_graphed_train_step_matches_eager(split):
     assert abs(float(le) - float(lg)) < 5e-3 * max(1.0, abs(float(le)))
     for pe, pg in zip(net_e.parameters(), net_g.parameters()):
         assert torch.allclose(pe, pg, rtol=0, atol=5e-3), (pe - pg).abs().max()
+
+
+@pytest.mark.parametrize("kind,cin,cout,r,size", [
+    ("same", 32, 32, 2, (12, 10, 14)), ("down", 32, 64, 2, (12, 12, 12)), ("up", 64, 32, 2, (6, 6, 6)),
+    ("same", 128, 128, 2, (6, 8, 10)), ("same", 512, 512, 2, (4, 4, 4)), ("same", 16, 16, 4, (8, 8, 8)),
+])
+def test_block_layernorm_forward_backward(kind, cin, cout, r, size):
+    """norm_type='layer' (upstream blocks.py::LayerNorm channels_first; cfg.model.mednext.norm, mednext_models.py:449-476):
+    csrc/layernorm.cu in front of the fused MLP kernels, forward and every gradient against the oracle."""
+    torch.manual_seed(2)
+    cls_o = {"same": OM.MedNeXtBlock, "down": OM.MedNeXtDownBlock, "up": OM.MedNeXtUpBlock}[kind]
+    cls_p = {"same": PM.MedNeXtBlock, "down": PM.MedNeXtDownBlock, "up": PM.MedNeXtUpBlock}[kind]
+    o = cls_o(cin, cout, r, 3, do_res=True, norm_type="layer")
+    with torch.no_grad():
+        o.norm.weight.uniform_(0.5, 1.5)
+        o.norm.bias.uniform_(-0.5, 0.5)
+    p = cls_p(cin, cout, r, 3, do_res=True, norm_type="layer")
+    assert list(p.state_dict().keys()) == list(o.state_dict().keys())
+    p.load_state_dict(o.state_dict(), strict=True)
+    p = p.to(DEV)
+    torch.manual_seed(3)
+    x = torch.randn(2, cin, *size).bfloat16().float()
+    with torch.no_grad():
+        want = o(x)
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            want_bf = o(x).float()
+        got = ncdhw(p(cl(x)))
+    e, eb = rel(got, want), rel(want_bf, want)
+    print(f"layernorm {kind} C{cin}: fwd engine {e:.3e} vs bf16-path {eb:.3e}")
+    assert e <= 1.5 * eb + 1e-3
+    gout = torch.randn_like(want)
+    ref32 = _grads_oracle(o, x, gout, autocast=False)
+    refbf = _grads_oracle(o, x, gout, autocast=True)
+    xc = cl(x).requires_grad_(True)
+    p.zero_grad()
+    out = p(xc)
+    out.backward(cl(gout))
+    got_p = {k: v.grad.detach() for k, v in p.named_parameters() if v.grad is not None}
+    _compare(f"layernorm {kind} C{cin}", ncdhw(xc.grad), got_p, ref32, refbf)
