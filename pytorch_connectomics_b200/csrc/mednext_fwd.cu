@@ -42,6 +42,42 @@ __global__ void __launch_bounds__(256) stem_kernel(const TIn* __restrict__ x, co
   }
 }
 
+// Streaming variant (C/8 a power of two, Cin <= 4): the thread's 8-channel chunk is fixed for the whole grid-stride
+// loop, so its weight rows and bias sit in registers and the voxel index is a shift — one coalesced 128-bit store per
+// item and no 64-bit divisions (the generic kernel above spends most of its instructions on index math and weight loads).
+template <typename TIn, int CIN>
+__global__ void __launch_bounds__(256) stem_stream_kernel(const TIn* __restrict__ x, const float* __restrict__ w,
+                                                          const float* __restrict__ b, uint4* __restrict__ out,
+                                                          int C, int64_t V, int ch_shift) {
+  const int CH = C >> 3, n = blockIdx.y;
+  const int64_t stride = (int64_t)gridDim.x * 256;          // multiple of CH
+  const int64_t first = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int cc = (int)(first & (CH - 1));
+  float wr[CIN][8], br[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    br[j] = __ldg(b + cc * 8 + j);
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) wr[ci][j] = __ldg(w + (cc * 8 + j) * CIN + ci);
+  }
+  const TIn* xn = x + (int64_t)n * CIN * V;
+  uint4* on = out + (int64_t)n * V * CH;
+  const int64_t items = V * CH;
+  for (int64_t i = first; i < items; i += stride) {
+    const int64_t v = i >> ch_shift;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = br[j];
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) {
+      const float xv = (float)xn[(int64_t)ci * V + v];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv, wr[ci][j], acc[j]);
+    }
+    on[i] = pack8(acc);
+  }
+}
+
 // ============================================================================ depthwise conv
 constexpr int DW_XB = 4;  // outputs per thread along W
 
@@ -1569,6 +1605,31 @@ extern "C" int pcb_stem_fwd(const void* x, int in_dtype, const float* w, const f
   const int64_t total = N * nvox * (C / 8);
   const int grid = (int)((total + 255) / 256 > 148 * 32 ? 148 * 32 : (total + 255) / 256);
   uint4* o = (uint4*)out;
+  {
+    const int ch = (int)(C >> 3);
+    static const bool no_stream = getenv("PCB_NO_STEM_STREAM") != nullptr;
+    if (!no_stream && Cin <= 4 && ch <= 256 && (ch & (ch - 1)) == 0 && N <= 65535 && in_dtype >= PCB_F32 && in_dtype <= PCB_BF16) {
+      int sh = 0;
+      while ((1 << sh) < ch) ++sh;
+      int64_t nb = (nvox * ch + 256 * 4 - 1) / (256 * 4);
+      if (nb > 148 * 8) nb = 148 * 8;
+      if (nb < 1) nb = 1;
+      dim3 g2((unsigned)nb, (unsigned)N);
+#define PCB_STEM(T, K) stem_stream_kernel<T, K><<<g2, 256, 0, st>>>((const T*)x, w, b, o, (int)C, nvox, sh)
+#define PCB_STEM_T(T)                                                                     \
+      do {                                                                                \
+        if (Cin == 1) PCB_STEM(T, 1); else if (Cin == 2) PCB_STEM(T, 2);                  \
+        else if (Cin == 3) PCB_STEM(T, 3); else PCB_STEM(T, 4);                           \
+      } while (0)
+      if (in_dtype == PCB_F32) PCB_STEM_T(float);
+      else if (in_dtype == PCB_F16) PCB_STEM_T(__half);
+      else PCB_STEM_T(__nv_bfloat16);
+#undef PCB_STEM_T
+#undef PCB_STEM
+      PCB_CHECK_LAUNCH("pcb_stem_fwd");
+      return PCB_OK;
+    }
+  }
   if (in_dtype == PCB_F32) stem_kernel<float><<<grid, 256, 0, st>>>((const float*)x, w, b, o, N, (int)Cin, (int)C, nvox);
   else if (in_dtype == PCB_F16) stem_kernel<__half><<<grid, 256, 0, st>>>((const __half*)x, w, b, o, N, (int)Cin, (int)C, nvox);
   else if (in_dtype == PCB_BF16) stem_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, w, b, o, N, (int)Cin, (int)C, nvox);
