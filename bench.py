@@ -184,10 +184,16 @@ KERNELS = {
     "tn_gemm": "pcb::tn_gemm_kernel (split-K wgrad GEMM, tcgen05 MN-major)",
     "gn_bwd": "pcb::gn_dy_kernel (GroupNorm backward)",
 }
-NCU_TRAFFIC = {  # dram__bytes_read.sum + dram__bytes_write.sum PER SAMPLE (captures at batch 1, profiles/*.ncu-rep)
-    "mlp_fwd:m0C32H64Co32V4096000": 524441344 + 234754048,     # r01_mlp_fused_l0_final.ncu-rep
-    "mlp_fwd:m2C64H128Co32V4096000": 843630080 + 245193984,    # r01_mlp_fused_up0.ncu-rep
-    "mlp_bwd_fused:m2C64H128Co32V4019679": 773626624 + 480401664,   # r01_mlp_bwd_fused_up0.ncu-rep
+NCU_TRAFFIC = {  # DRAM bytes (read + write) PER SAMPLE of one launch: dram__bytes.sum.per_second x gpu__time_duration from the
+    # batch-1 block capture profiles/r01_blocks_final.ncu-rep (raw page: profiles/r01_blocks_final_raw.csv)
+    "mlp_bwd_fused:m0C32H64Co32V4096000": 759.3e6,
+    "mlp_bwd_fused:m2C64H128Co32V4019679": 1253.9e6,
+    "mlp_fwd:m0C32H64Co32V4096000": 758.6e6,
+    "mlp_fwd:m2C64H128Co32V4096000": 1084.8e6,
+    "dwconv_fwd:m0C32V4096000": 487.3e6,
+    "dw_bwd_data:m0C32V4096000": 763.4e6,
+    "dw_wgrad:m0C32V4096000": 604.8e6,
+    "gn_bwd:C32V4096000": 733.1e6,
 }
 
 
@@ -232,7 +238,7 @@ def build_roofline(prof, a, peak_gbs, measured, step_ms, nsteps):
                      "op_ms_per_step": g["ms"], "share_of_step": g["ms"] / step_ms})
     roof = dict(rows[0])
     roof["peak_source"] = "MEASURED_PEAKS.json (of measured)" if measured else "fallback 6650 GB/s (of fallback)"
-    roof["traffic_source"] = "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/); null = not captured"
+    roof["traffic_source"] = "ncu DRAM bytes (read + write) per launch from the batch-1 capture in profiles/ x batch; null = not captured"
     roof["others"] = rows[1:]
     return roof
 
@@ -274,6 +280,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout (one JSON line contract)
         dist.init_process_group("nccl", device_id=dev)
         dbg("process group up")
     if not os.path.exists(L.LIB_PATH):
