@@ -206,6 +206,8 @@ def _op_bytes(op: str, key: str, batch: int):
         return batch * v * 2 * (c + 2 * co)            # read y, read residual/skip, write out
     if op in ("mlp_bwd_fused", "mlp_bwd"):
         return batch * v * 2 * (2 * c + co)            # read y, read dOut, write dYhat
+    if op == "dw_bwd_data" and ":m0" in key:
+        return batch * v * 2 * 3 * c                   # read dy + fused residual gradient, write dx
     if op in ("dwconv_fwd", "dw_bwd_data", "dw_wgrad"):
         return batch * v * 2 * 2 * c                   # read + write (or read two tensors)
     if op == "gn_bwd":

@@ -24,3 +24,11 @@ def window_goldens():
 def mednext_tiny_golden():
     import numpy as np
     return np.load(os.path.join(GOLDEN, "mednext_tiny.npz"))
+
+
+def free_port() -> int:
+    """A TCP port the kernel reports as free right now (gloo rendezvous of the multi-process CPU tests)."""
+    import socket
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as sk:
+        sk.bind(("127.0.0.1", 0))
+        return int(sk.getsockname()[1])

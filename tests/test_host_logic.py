@@ -208,11 +208,12 @@ def test_flat_arena_allreduce_gloo_world2():
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000)
+    from conftest import free_port
+    port = free_port()
     procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = dict(q.get(timeout=120) for _ in range(2))
+    res = dict(q.get(timeout=300) for _ in range(2))
     for p in procs:
         p.join(timeout=60)
     assert torch.equal(res[0], res[1])                      # identical averaged gradients on both ranks
@@ -253,11 +254,12 @@ def test_accumulator_reduce_to_root_gloo_world2():
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 31500 + (os.getpid() % 2000)
+    from conftest import free_port
+    port = free_port()
     procs = [ctx.Process(target=_reduce_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got = [q.get(timeout=120) for _ in range(4)]
+    got = [q.get(timeout=300) for _ in range(4)]
     for p in procs:
         p.join(timeout=60)
     first = {r: v for r, v in got if not isinstance(v, (bool, str))}

@@ -103,11 +103,12 @@ def test_exchange_overlaps_gloo(world):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 33500 + (os.getpid() % 2000) + world
+    from conftest import free_port
+    port = free_port()
     procs = [ctx.Process(target=_shard_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = sorted((q.get(timeout=180) for _ in range(world)), key=lambda t: t[0])
+    res = sorted((q.get(timeout=300) for _ in range(world)), key=lambda t: t[0])
     for p in procs:
         p.join(timeout=60)
     torch.manual_seed(5)
