@@ -67,6 +67,21 @@ int pcb_sw_accumulate(const void* pred, const void* map, void* value, void* weig
 /* window.py:275-294 normalize_weighted_accumulator: value /= clamp_min(weight, 1e-4) (in place). */
 int pcb_sw_normalize(void* value, const void* weight, int dtype, int64_t Cout, int64_t nvox, void* stream);
 
+/* ------------------------------------------------------------------ test-time augmentation (fully valid channels)
+ * connectomics/inference/tta.py:706-714: out = rot90(flip(x, flip axes), k, (rot_a, rot_b)) for x [planes, in_size],
+ * spatial axes 0..2, flip_mask bit a = flip axis a, rot_a < 0 = no rotation; odd k swaps the plane's dims in `out`. */
+int pcb_tta_view(const void* x, void* out, int dtype, int64_t planes, const int64_t in_size[3], int flip_mask,
+                 int rot_a, int rot_b, int k, void* stream);
+/* One view folded into the ensemble accumulator acc [N, Cacc, acc_size]: the view is inverted by index map
+ * (tta_affinity.py:364-369 invert_view: rot90(-k) then flip), channel c reads prediction channel src_channel[c]
+ * (tta.py:404-413 select_channel), the activation act[c] (0 none, 1 sigmoid, 2 sigmoid(act_scale*x), 3 tanh; tta.py:312-402)
+ * is applied in the prediction dtype, the value is cast to the accumulator dtype and folded with mode[c] (0 mean:
+ * cur += (inc - cur) / (n_prev + 1), 1 min, 2 max; n_prev == 0 copies) — tta_ensemble.py:94-110.  pred is
+ * [N, Cpred, view-frame size]; the arrays are HOST arrays of Cacc entries (Cacc <= 64). */
+int pcb_tta_fold(const void* pred, int pred_dtype, void* acc, int acc_dtype, int64_t N, int64_t Cpred, int64_t Cacc,
+                 const int64_t acc_size[3], int flip_mask, int rot_a, int rot_b, int k, const int* src_channel,
+                 const int* mode, const int* act, const float* act_scale, int n_prev, void* stream);
+
 /* ------------------------------------------------------------------ MedNeXt forward ops
  * (upstream nnunet_mednext blocks.py / MedNextV1.py as built by
  *  connectomics/models/architectures/mednext_models.py:374-380,479)

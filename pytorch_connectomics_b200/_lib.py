@@ -19,7 +19,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libpcb200.so")
-SOURCES = ["pcb_api.cu", "sw_kernels.cu", "mednext_fwd.cu", "mednext_bwd.cu", "dense_conv.cu", "deep_mlp.cu", "layernorm.cu"]
+SOURCES = ["pcb_api.cu", "sw_kernels.cu", "mednext_fwd.cu", "mednext_bwd.cu", "dense_conv.cu", "deep_mlp.cu", "layernorm.cu", "tta_kernels.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

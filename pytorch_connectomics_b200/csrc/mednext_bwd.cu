@@ -288,13 +288,17 @@ struct MlpBwdFusedArgs {
 };
 
 constexpr int BF_PF = 8;          // prefetch depth: (C/8 + Co/8) * 128 / 256 <= 8 chunks per thread
-constexpr int BF_THREADS = 256;   // two warpgroups: same TMEM lane quarters, each takes half of the columns
+// NT threads = NT/128 warpgroups: every warpgroup covers all 128 TMEM lanes (warp w reads lane quarter w%4), the
+// warpgroups split the columns.  NT = 256 where TMEM lets two CTAs share an SM (<= 256 columns), NT = 512 where only
+// one fits (up_0, down_0, level 1: 16 warps instead of 8 on the SM; measured IPC of the 8-warp CTA: 1.1).
 
-__global__ void __launch_bounds__(BF_THREADS, 2) mlp_bwd_fused_kernel(MlpBwdFusedArgs fa) {
+template <int NT>
+__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) mlp_bwd_fused_kernel(MlpBwdFusedArgs fa) {
+  constexpr int BF_THREADS = NT, NPART = NT / 128;
   const MlpBwdArgs& a = fa.m;
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int row = tid & 127, half = tid >> 7, wq = warp & 3;   // tile row, column half, TMEM lane quarter
+  const int row = tid & 127, part = tid >> 7, wq = warp & 3;   // tile row, column part (warpgroup), TMEM lane quarter
   const int c8n = a.C >> 3, h8n = a.H >> 3, o8n = a.Co >> 3;
   const uint32_t pitchA = (c8n + 1) * 128, pitchH = h8n * 128, pitchD = o8n * 128, pitchDh = h8n * 128;
   uint8_t* sW2 = smem;                                 // [H x C]   K-major (B of G1)
@@ -442,12 +446,12 @@ __global__ void __launch_bounds__(BF_THREADS, 2) mlp_bwd_fused_kernel(MlpBwdFuse
     }
     mbar_wait(&bar[0], ph0); ph0 ^= 1;
     tc_fence_after();
-    // ---- E1: Hact -> sH, dh -> sDh   (warpgroup `half` handles its half of the hidden columns)
+    // ---- E1: Hact -> sH, dh -> sDh   (warpgroup `part` handles its share of the hidden columns)
     {
       const uint32_t t1 = acc1 + ((uint32_t)(wq * 32) << 16), tg = accG + ((uint32_t)(wq * 32) << 16);
       uint8_t* dH = sH + (row >> 3) * pitchH + (row & 7) * 16;
       uint8_t* dDh = sDh + (row >> 3) * pitchDh + (row & 7) * 16;
-      const int nch = a.H / 16, c_lo = half * ((nch + 1) >> 1), c_hi = half ? nch : ((nch + 1) >> 1);
+      const int nch = a.H / 16, c_lo = (part * nch) / NPART, c_hi = ((part + 1) * nch) / NPART;
       for (int c16 = c_lo; c16 < c_hi; ++c16) {
         uint32_t v1[16], vg[16];
         tmem_ld16(t1 + c16 * 16, v1);
@@ -501,7 +505,7 @@ __global__ void __launch_bounds__(BF_THREADS, 2) mlp_bwd_fused_kernel(MlpBwdFuse
       const int prow = tile0 + row;
       const bool row_ok = prow < (int)a.Vy;
       const uint32_t td = accD + ((uint32_t)(wq * 32) << 16);
-      const int ncd = a.C / 16, d_lo = half * ((ncd + 1) >> 1), d_hi = half ? ncd : ((ncd + 1) >> 1);
+      const int ncd = a.C / 16, d_lo = (part * ncd) / NPART, d_hi = ((part + 1) * ncd) / NPART;
       const int64_t yrow = ((int64_t)n * a.Vy + prow) * c8n;
       const float* rs = sRstd + n * a.C; const float* mr = sMR + n * a.C;
       for (int c16 = d_lo; c16 < d_hi; ++c16) {
@@ -551,7 +555,7 @@ __global__ void __launch_bounds__(BF_THREADS, 2) mlp_bwd_fused_kernel(MlpBwdFuse
     const uint32_t lo = (uint32_t)(wq * 32) << 16;
     float* p3 = fa.part3 + ((int64_t)blockIdx.x * 129 + row) * a.Co;
     if (tid < a.Co) fa.part3[((int64_t)blockIdx.x * 129 + 128) * a.Co + tid] = db3acc;
-    for (int c16 = half; c16 < a.Co / 16; c16 += 2) {
+    for (int c16 = part; c16 < a.Co / 16; c16 += NPART) {
       uint32_t v[16];
       tmem_ld16(accW3 + lo + c16 * 16, v);
       tmem_ld_wait();
@@ -561,7 +565,7 @@ __global__ void __launch_bounds__(BF_THREADS, 2) mlp_bwd_fused_kernel(MlpBwdFuse
       }
     }
     float* p2 = fa.part2 + ((int64_t)blockIdx.x * 128 + row) * a.H;
-    for (int c16 = half; c16 < a.H / 16; c16 += 2) {
+    for (int c16 = part; c16 < a.H / 16; c16 += NPART) {
       uint32_t v[16];
       tmem_ld16(accW2 + lo + c16 * 16, v);
       tmem_ld_wait();
@@ -1373,6 +1377,61 @@ __global__ void __launch_bounds__(256) stem_bwd_kernel(const uint4* __restrict__
   }
 }
 
+// Streaming variant (C/8 a power of two, Cin <= 4): ONE pass over g with the thread's 8-channel chunk fixed, all Cin+1
+// partial columns (weights + bias) in registers; the generic kernel above walks g once per input channel and bias.
+template <typename TIn, int CIN>
+__global__ void __launch_bounds__(256) stem_bwd_stream_kernel(const uint4* __restrict__ g, const TIn* __restrict__ x,
+                                                              double* __restrict__ dW, double* __restrict__ db, int C,
+                                                              int64_t V, int ch_shift) {
+  extern __shared__ double s_acc[];   // [C*(CIN+1)]
+  const int CH = C >> 3, n = blockIdx.y, tid = threadIdx.x;
+  for (int i = tid; i < C * (CIN + 1); i += 256) s_acc[i] = 0.0;
+  __syncthreads();
+  const int64_t items = V * CH;
+  const int64_t stride = (int64_t)gridDim.x * 256;          // multiple of CH
+  const int64_t first = (int64_t)blockIdx.x * 256 + tid;
+  const int cc = (int)(first & (CH - 1));
+  float acc[CIN + 1][8];
+#pragma unroll
+  for (int ci = 0; ci <= CIN; ++ci)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[ci][j] = 0.f;
+  const uint4* gn = g + (int64_t)n * items;
+  const TIn* xn = x + (int64_t)n * CIN * V;
+  for (int64_t i = first; i < items; i += stride) {
+    const int64_t v = i >> ch_shift;
+    float gv[8];
+    unpack8(ldg_nc(gn + i), gv);
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) {
+      const float xv = (float)xn[(int64_t)ci * V + v];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[ci][j] = fmaf(gv[j], xv, acc[ci][j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[CIN][j] += gv[j];
+  }
+  // lanes with equal (lane % CH) own the same chunk
+  for (int off = 16; off >= CH; off >>= 1) {
+#pragma unroll
+    for (int ci = 0; ci <= CIN; ++ci)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[ci][j] += __shfl_xor_sync(0xffffffffu, acc[ci][j], off);
+  }
+  if ((tid & 31) < CH || CH > 32) {
+#pragma unroll
+    for (int ci = 0; ci <= CIN; ++ci)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&s_acc[(cc * 8 + j) * (CIN + 1) + ci], (double)acc[ci][j]);
+  }
+  __syncthreads();
+  for (int i = tid; i < C * (CIN + 1); i += 256) {
+    const int c = i / (CIN + 1), ci = i - c * (CIN + 1);
+    if (ci < CIN) atomicAdd(&dW[c * CIN + ci], s_acc[i]);
+    else atomicAdd(&db[c], s_acc[i]);
+  }
+}
+
 static inline int pick_chunk_b(int64_t n, int cap) {
   for (int c = cap; c >= 16; c >>= 1)
     if (n % c == 0) return c;
@@ -1479,14 +1538,20 @@ extern "C" int pcb_mlp_bwd_fused(const void* y, const double* stats, const float
   const size_t smem = mlp_bwd_fused_smem((int)C, (int)H, (int)Co, (int)N);
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(mlp_bwd_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (cudaFuncSetAttribute(mlp_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+    cudaFuncSetAttribute(mlp_bwd_fused_kernel<256>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(mlp_bwd_fused_kernel<512>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (cudaFuncSetAttribute(mlp_bwd_fused_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(mlp_bwd_fused_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
       set_error("pcb_mlp_bwd_fused: cudaFuncSetAttribute failed"); return PCB_ERR_CUDA;
     }
     configured = true;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  mlp_bwd_fused_kernel<<<P, BF_THREADS, smem, st>>>(fa);
+  // one CTA per SM (TMEM > 256 columns): four warpgroups; H >= 64 and C >= 64 keep every warpgroup busy in E1 / E2
+  const char* nt_env = getenv("PCB_BWD_NT512");
+  const bool wide = tcols > 256 && H / 16 >= 4 && !(nt_env && nt_env[0] == '0');
+  if (wide) mlp_bwd_fused_kernel<512><<<P, 512, smem, st>>>(fa);
+  else mlp_bwd_fused_kernel<256><<<P, 256, smem, st>>>(fa);
   PCB_CHECK_LAUNCH("pcb_mlp_bwd_fused");
   // second stage: dW3[co,h] = sum_p part3[p][h][co] ; db3[co] = sum_p part3[p][H][co]   (and the same for W2)
   reduce_partials_kernel<<<(unsigned)((H * Co + 31) / 32), 256, 0, st>>>(fa.part3, P, (int)H, 129, (int)Co, (int)Co, dW3, 1, H, nullptr);
@@ -1722,6 +1787,31 @@ extern "C" int pcb_stem_bwd(const void* g, const void* x, int in_dtype, double* 
   dim3 grid((unsigned)blocks, (unsigned)N);
   const size_t smem = (size_t)C * (Cin + 1) * sizeof(double);
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    const int ch = (int)(C >> 3);
+    static const bool no_stream = getenv("PCB_NO_STEM_STREAM") != nullptr;
+    if (!no_stream && Cin <= 4 && ch <= 32 && (ch & (ch - 1)) == 0 && N <= 65535 && in_dtype >= PCB_F32 && in_dtype <= PCB_BF16) {
+      int sh = 0;
+      while ((1 << sh) < ch) ++sh;
+      int64_t nb = (items + 256 * 8 - 1) / (256 * 8);
+      if (nb > 148 * 6) nb = 148 * 6;
+      if (nb < 1) nb = 1;
+      dim3 g2((unsigned)nb, (unsigned)N);
+#define PCB_STEMB(T, K) stem_bwd_stream_kernel<T, K><<<g2, 256, (size_t)C * (K + 1) * sizeof(double), st>>>((const uint4*)g, (const T*)x, dW, db, (int)C, nvox, sh)
+#define PCB_STEMB_T(T)                                                                        \
+      do {                                                                                    \
+        if (Cin == 1) PCB_STEMB(T, 1); else if (Cin == 2) PCB_STEMB(T, 2);                    \
+        else if (Cin == 3) PCB_STEMB(T, 3); else PCB_STEMB(T, 4);                             \
+      } while (0)
+      if (in_dtype == PCB_F32) PCB_STEMB_T(float);
+      else if (in_dtype == PCB_F16) PCB_STEMB_T(__half);
+      else PCB_STEMB_T(__nv_bfloat16);
+#undef PCB_STEMB_T
+#undef PCB_STEMB
+      PCB_CHECK_LAUNCH("pcb_stem_bwd");
+      return PCB_OK;
+    }
+  }
   if (in_dtype == PCB_F32) stem_bwd_kernel<float><<<grid, 256, smem, st>>>((const uint4*)g, (const float*)x, dW, db, (int)Cin, (int)C, nvox);
   else if (in_dtype == PCB_F16) stem_bwd_kernel<__half><<<grid, 256, smem, st>>>((const uint4*)g, (const __half*)x, dW, db, (int)Cin, (int)C, nvox);
   else if (in_dtype == PCB_BF16) stem_bwd_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>((const uint4*)g, (const __nv_bfloat16*)x, dW, db, (int)Cin, (int)C, nvox);

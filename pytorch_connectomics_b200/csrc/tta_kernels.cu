@@ -1,0 +1,203 @@
+// pcb200 — test-time-augmentation views and the streaming ensemble.
+//
+// Replaces, for fully valid channels (no affinity channel moves), the per-view tensor ops of
+// connectomics/inference/tta.py:691-771 (_run_ensemble: torch.flip + torch.rot90 on the input, the network,
+// tta_affinity.py:364-369 invert_view: rot90(-k) then flip), tta.py:312-402 (apply_preprocessing: per-channel
+// sigmoid / scale_sigmoid / tanh, channel selection, cast to the output dtype) and
+// tta_ensemble.py:94-110 (_add_full_channels: first view copies, "mean" is the running average
+// cur += (inc - cur) / (n + 1), "min" / "max" elementwise).  Two kernels:
+//   tta_view_kernel  out = rot90(flip(x, axes), k, plane)            (gather; the view handed to the network)
+//   tta_fold_kernel  acc <- fold(acc, act(inverse_view(pred))[selected channels])   — the inverse view is only an
+//                    index map, so un-rotating, un-flipping, the activation, the channel select, the dtype cast and the
+//                    ensemble update are ONE pass over the accumulator instead of six tensor ops per view.
+// Arithmetic follows torch's elementwise kernels (compute in fp32, round to the tensor dtype after every op), so the
+// fp32 path is bit-identical to the reference expression and the half paths round exactly where torch rounds.
+#include "../../include/pcb200.h"
+#include <stdlib.h>
+#include <string.h>
+
+#include "pcb_common.cuh"
+
+namespace pcb {
+
+struct TtaGeom {
+  int s[3];        // spatial size of the tensor being WRITTEN (output of the kernel's index space)
+  int in[3];       // spatial size of the tensor being READ
+  int flip[3];     // flip flags per spatial axis
+  int ra, rb, k;   // rotation plane (spatial axes, ra < 0: none) and number of quarter turns (0..3)
+};
+
+// source coordinate of torch.rot90(x, k, (ra, rb))[o] in x (sizes `in`): k=1: x.flip(rb).transpose; k=2: both flips;
+// k=3: x.flip(ra).transpose
+__device__ __forceinline__ void rot_src(const TtaGeom& g, int k, const int* in_size, int* c) {
+  if (g.ra < 0 || k == 0) return;
+  const int oa = c[g.ra], ob = c[g.rb];
+  if (k == 1) { c[g.ra] = ob; c[g.rb] = in_size[g.rb] - 1 - oa; }
+  else if (k == 2) { c[g.ra] = in_size[g.ra] - 1 - oa; c[g.rb] = in_size[g.rb] - 1 - ob; }
+  else { c[g.ra] = in_size[g.ra] - 1 - ob; c[g.rb] = oa; }
+}
+
+template <typename T> struct TtaNum;
+template <> struct TtaNum<float> {
+  static __device__ __forceinline__ float ld(const float* p) { return *p; }
+  static __device__ __forceinline__ float rnd(float v) { return v; }
+  static __device__ __forceinline__ void st(float* p, float v) { *p = v; }
+};
+template <> struct TtaNum<__half> {
+  static __device__ __forceinline__ float ld(const __half* p) { return __half2float(*p); }
+  static __device__ __forceinline__ float rnd(float v) { return __half2float(__float2half_rn(v)); }
+  static __device__ __forceinline__ void st(__half* p, float v) { *p = __float2half_rn(v); }
+};
+template <> struct TtaNum<__nv_bfloat16> {
+  static __device__ __forceinline__ float ld(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+  static __device__ __forceinline__ float rnd(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+
+// out[plane, o] = x[plane, flip(rot_src(o))]   — planes = N*C
+template <typename T>
+__global__ void __launch_bounds__(256) tta_view_kernel(const T* __restrict__ x, T* __restrict__ out, TtaGeom g, int64_t planes) {
+  const int64_t vol = (int64_t)g.s[0] * g.s[1] * g.s[2];
+  const int64_t total = planes * vol;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i / vol;
+    int64_t r = i - p * vol;
+    int c[3];
+    c[2] = (int)(r % g.s[2]); r /= g.s[2];
+    c[1] = (int)(r % g.s[1]);
+    c[0] = (int)(r / g.s[1]);
+    rot_src(g, g.k, g.in, c);                       // coordinate in flip(x): same sizes as x
+#pragma unroll
+    for (int a = 0; a < 3; ++a) if (g.flip[a]) c[a] = g.in[a] - 1 - c[a];
+    out[i] = x[p * vol + ((int64_t)c[0] * g.in[1] + c[1]) * g.in[2] + c[2]];
+  }
+}
+
+constexpr int TTA_MAXC = 64;
+struct TtaFold {
+  TtaGeom g;               // g.s = canonical (accumulator) size, g.in = prediction (view frame) size, g.k = inverse turns
+  int N, Cacc, Cpred;
+  int n_prev;              // views folded so far
+  int src[TTA_MAXC];       // prediction channel feeding accumulator channel c (channel selection)
+  int mode[TTA_MAXC];      // 0 mean, 1 min, 2 max
+  int act[TTA_MAXC];       // 0 none, 1 sigmoid, 2 scale_sigmoid, 3 tanh
+  float scale[TTA_MAXC];
+};
+
+// TP: prediction dtype, TA: accumulator (output) dtype
+template <typename TP, typename TA>
+__global__ void __launch_bounds__(256) tta_fold_kernel(const TP* __restrict__ pred, TA* __restrict__ acc, TtaFold f) {
+  const TtaGeom& g = f.g;
+  const int64_t vol = (int64_t)g.s[0] * g.s[1] * g.s[2];
+  const int64_t pvol = (int64_t)g.in[0] * g.in[1] * g.in[2];
+  const int64_t total = (int64_t)f.N * f.Cacc * vol;
+  const float inv_n = 1.0f;   // division is done explicitly below (torch: delta / (n + 1))
+  (void)inv_n;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pc = i / vol;
+    int64_t r = i - pc * vol;
+    const int ch = (int)(pc % f.Cacc);
+    const int64_t n = pc / f.Cacc;
+    int c[3];
+    c[2] = (int)(r % g.s[2]); r /= g.s[2];
+    c[1] = (int)(r % g.s[1]);
+    c[0] = (int)(r / g.s[1]);
+    // canonical = flip(rot90(pred, -k)): undo the flip (sizes of the canonical frame), then the rotation
+#pragma unroll
+    for (int a = 0; a < 3; ++a) if (g.flip[a]) c[a] = g.s[a] - 1 - c[a];
+    rot_src(g, g.k, g.in, c);
+    float v = TtaNum<TP>::ld(pred + (n * f.Cpred + f.src[ch]) * pvol + ((int64_t)c[0] * g.in[1] + c[1]) * g.in[2] + c[2]);
+    // activation in the prediction dtype (torch in-place ops on the network output), then the cast to the output dtype
+    const int act = f.act[ch];
+    if (act == 1) v = TtaNum<TP>::rnd(1.0f / (1.0f + expf(-v)));
+    else if (act == 2) { v = TtaNum<TP>::rnd(v * f.scale[ch]); v = TtaNum<TP>::rnd(1.0f / (1.0f + expf(-v))); }
+    else if (act == 3) v = TtaNum<TP>::rnd(tanhf(v));
+    v = TtaNum<TA>::rnd(v);
+    if (f.n_prev > 0) {
+      const float cur = TtaNum<TA>::ld(acc + i);
+      const int mode = f.mode[ch];
+      if (mode == 0) {
+        const float delta = TtaNum<TA>::rnd(v - cur);
+        const float q = TtaNum<TA>::rnd(__fdiv_rn(delta, (float)(f.n_prev + 1)));
+        v = __fadd_rn(cur, q);
+      } else if (mode == 1) v = fminf(cur, v);
+      else v = fmaxf(cur, v);
+    }
+    TtaNum<TA>::st(acc + i, v);
+  }
+}
+
+static bool geom_ok(const int64_t s[3]) { return s && s[0] > 0 && s[1] > 0 && s[2] > 0 && s[0] * s[1] * s[2] < (1ll << 40); }
+
+}  // namespace pcb
+
+using namespace pcb;
+
+static int tta_grid(int64_t total) {
+  int64_t b = (total + 255) / 256;
+  if (b > 148 * 16) b = 148 * 16;
+  return (int)(b < 1 ? 1 : b);
+}
+
+extern "C" int pcb_tta_view(const void* x, void* out, int dtype, int64_t planes, const int64_t in_size[3], int flip_mask,
+                            int rot_a, int rot_b, int k, void* stream) {
+  PCB_CHECK_ARG(x && out && geom_ok(in_size) && planes > 0, "pcb_tta_view: bad argument");
+  PCB_CHECK_ARG(k >= 0 && k <= 3, "pcb_tta_view: k must be in 0..3 (got %d)", k);
+  PCB_CHECK_ARG((rot_a < 0 && rot_b < 0) || (rot_a >= 0 && rot_a < 3 && rot_b >= 0 && rot_b < 3 && rot_a != rot_b),
+                "pcb_tta_view: bad rotation plane (%d, %d)", rot_a, rot_b);
+  TtaGeom g;
+  for (int a = 0; a < 3; ++a) { g.in[a] = (int)in_size[a]; g.s[a] = (int)in_size[a]; g.flip[a] = (flip_mask >> a) & 1; }
+  g.ra = rot_a; g.rb = rot_b; g.k = rot_a < 0 ? 0 : k;
+  if (g.ra >= 0 && (g.k & 1)) { g.s[g.ra] = g.in[g.rb]; g.s[g.rb] = g.in[g.ra]; }
+  const int64_t total = planes * in_size[0] * in_size[1] * in_size[2];
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == PCB_F32) tta_view_kernel<float><<<tta_grid(total), 256, 0, st>>>((const float*)x, (float*)out, g, planes);
+  else if (dtype == PCB_F16) tta_view_kernel<__half><<<tta_grid(total), 256, 0, st>>>((const __half*)x, (__half*)out, g, planes);
+  else if (dtype == PCB_BF16) tta_view_kernel<__nv_bfloat16><<<tta_grid(total), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, g, planes);
+  else { set_error("pcb_tta_view: bad dtype %d", dtype); return PCB_ERR_INVALID; }
+  PCB_CHECK_LAUNCH("pcb_tta_view");
+  return PCB_OK;
+}
+
+extern "C" int pcb_tta_fold(const void* pred, int pred_dtype, void* acc, int acc_dtype, int64_t N, int64_t Cpred, int64_t Cacc,
+                            const int64_t acc_size[3], int flip_mask, int rot_a, int rot_b, int k, const int* src_channel,
+                            const int* mode, const int* act, const float* act_scale, int n_prev, void* stream) {
+  PCB_CHECK_ARG(pred && acc && geom_ok(acc_size) && N > 0 && src_channel && mode && act && act_scale, "pcb_tta_fold: bad argument");
+  PCB_CHECK_ARG(Cacc > 0 && Cacc <= TTA_MAXC && Cpred > 0, "pcb_tta_fold: at most %d output channels (got %lld)", TTA_MAXC, (long long)Cacc);
+  PCB_CHECK_ARG(k >= 0 && k <= 3 && n_prev >= 0, "pcb_tta_fold: bad k / n_prev");
+  PCB_CHECK_ARG((rot_a < 0 && rot_b < 0) || (rot_a >= 0 && rot_a < 3 && rot_b >= 0 && rot_b < 3 && rot_a != rot_b),
+                "pcb_tta_fold: bad rotation plane (%d, %d)", rot_a, rot_b);
+  TtaFold f;
+  memset(&f, 0, sizeof(f));
+  TtaGeom& g = f.g;
+  for (int a = 0; a < 3; ++a) { g.s[a] = (int)acc_size[a]; g.in[a] = (int)acc_size[a]; g.flip[a] = (flip_mask >> a) & 1; }
+  g.ra = rot_a; g.rb = rot_b;
+  const int kf = rot_a < 0 ? 0 : k;
+  g.k = (4 - kf) & 3;                                   // invert_view rotates by -k
+  if (g.ra >= 0 && (kf & 1)) { g.in[g.ra] = g.s[g.rb]; g.in[g.rb] = g.s[g.ra]; }   // the view frame has the plane dims swapped
+  f.N = (int)N; f.Cacc = (int)Cacc; f.Cpred = (int)Cpred; f.n_prev = n_prev;
+  for (int c = 0; c < Cacc; ++c) {
+    PCB_CHECK_ARG(src_channel[c] >= 0 && src_channel[c] < Cpred, "pcb_tta_fold: source channel %d out of range", src_channel[c]);
+    PCB_CHECK_ARG(mode[c] >= 0 && mode[c] <= 2 && act[c] >= 0 && act[c] <= 3, "pcb_tta_fold: bad mode / activation code");
+    f.src[c] = src_channel[c]; f.mode[c] = mode[c]; f.act[c] = act[c]; f.scale[c] = act_scale[c];
+  }
+  const int64_t total = N * Cacc * acc_size[0] * acc_size[1] * acc_size[2];
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = tta_grid(total);
+#define PCB_FOLD(TP, TA) tta_fold_kernel<TP, TA><<<grid, 256, 0, st>>>((const TP*)pred, (TA*)acc, f)
+#define PCB_FOLD_P(TP)                                                          \
+  do {                                                                          \
+    if (acc_dtype == PCB_F32) PCB_FOLD(TP, float);                              \
+    else if (acc_dtype == PCB_F16) PCB_FOLD(TP, __half);                        \
+    else if (acc_dtype == PCB_BF16) PCB_FOLD(TP, __nv_bfloat16);                \
+    else { set_error("pcb_tta_fold: bad dtype %d", acc_dtype); return PCB_ERR_INVALID; } \
+  } while (0)
+  if (pred_dtype == PCB_F32) PCB_FOLD_P(float);
+  else if (pred_dtype == PCB_F16) PCB_FOLD_P(__half);
+  else if (pred_dtype == PCB_BF16) PCB_FOLD_P(__nv_bfloat16);
+  else { set_error("pcb_tta_fold: bad dtype %d", pred_dtype); return PCB_ERR_INVALID; }
+#undef PCB_FOLD_P
+#undef PCB_FOLD
+  PCB_CHECK_LAUNCH("pcb_tta_fold");
+  return PCB_OK;
+}

@@ -11,8 +11,9 @@ from .chunked import (ChunkRef, build_chunk_grid, chunks_for_rank, resolve_chunk
                       resolve_halo_region, run_chunked_prediction, stitch_chunks)
 
 from .sharded import SlabPlan, ZSlabShardedEngine, exchange_overlaps, plan_z_slabs
+from .tta import TTAEnsemble, apply_view, resolve_tta_augmentation_combinations
 
-__all__ = ["SlabPlan", "ZSlabShardedEngine", "exchange_overlaps", "plan_z_slabs", "lazy_predict_region", "lazy_predict_volume", "lazy_sliding_window", "lazy_window_records", "ChunkRef",
+__all__ = ["TTAEnsemble", "apply_view", "resolve_tta_augmentation_combinations", "SlabPlan", "ZSlabShardedEngine", "exchange_overlaps", "plan_z_slabs", "lazy_predict_region", "lazy_predict_volume", "lazy_sliding_window", "lazy_window_records", "ChunkRef",
            "build_chunk_grid", "chunks_for_rank", "resolve_chunk_shape", "resolve_external_chunk_shard",
            "resolve_halo_region", "run_chunked_prediction", "stitch_chunks",
            "EagerSlidingWindowEngine", "apply_border_mask", "build_sliding_accumulator_weight_maps",
