@@ -200,7 +200,7 @@ def _ddp_worker(rank, world, port, q):
     arena.zero()
     net[2](net[1](net[0](x))).sum().backward()
     arena.allreduce()
-    q.put((rank, arena.buffer.clone()))
+    q.put((rank, arena.buffer.clone().numpy()))   # by value: torch tensors travel as fds that die with the worker
     dist.destroy_process_group()
 
 
@@ -213,7 +213,7 @@ def test_flat_arena_allreduce_gloo_world2():
     procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = dict(q.get(timeout=300) for _ in range(2))
+    res = {r: torch.from_numpy(v) for r, v in (q.get(timeout=300) for _ in range(2))}
     for p in procs:
         p.join(timeout=60)
     assert torch.equal(res[0], res[1])                      # identical averaged gradients on both ranks
@@ -240,7 +240,7 @@ def _reduce_worker(rank, world, port, q):
     v = torch.full((1, 2, 3, 3, 3), float(rank + 1))
     w = torch.full((1, 1, 3, 3, 3), 0.5)
     out = make_accumulator_reducer()(v, w)
-    q.put((rank, None if out is None else (out[0].clone(), out[1].clone())))
+    q.put((rank, None if out is None else (out[0].clone().numpy(), out[1].clone().numpy())))
     try:
         validate_patch_shard(0 if rank == 1 else 2, 2, "cpu")
         q.put((rank, "no error"))
@@ -264,7 +264,8 @@ def test_accumulator_reduce_to_root_gloo_world2():
         p.join(timeout=60)
     first = {r: v for r, v in got if not isinstance(v, (bool, str))}
     assert first[1] is None
-    assert torch.equal(first[0][0], torch.full((1, 2, 3, 3, 3), 3.0)) and torch.equal(first[0][1], torch.full((1, 1, 3, 3, 3), 1.0))
+    assert torch.equal(torch.from_numpy(first[0][0]), torch.full((1, 2, 3, 3, 3), 3.0))
+    assert torch.equal(torch.from_numpy(first[0][1]), torch.full((1, 1, 3, 3, 3), 1.0))
     assert all(v is True for r, v in got if isinstance(v, (bool, str)))
 
 

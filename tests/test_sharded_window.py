@@ -94,7 +94,7 @@ def _shard_worker(rank, world, port, q):
     z0 = plan.slab[0]
     own = O.normalize_accumulator(val[:, :, plan.own[0] - z0:plan.own[1] - z0].clone(),
                                   wacc[:, :, plan.own[0] - z0:plan.own[1] - z0].clone())
-    q.put((rank, plan.own, own))
+    q.put((rank, plan.own, own.numpy()))     # by value: torch tensors travel as fds that die with the worker
     dist.destroy_process_group()
 
 
@@ -114,7 +114,7 @@ def test_exchange_overlaps_gloo(world):
     torch.manual_seed(5)
     vol = torch.rand(1, 1, 44, 24, 20)
     want = O.eager_sliding_window(vol, _net, (16, 16, 16), overlap=0.5, mode="bump")
-    got = torch.cat([r[2] for r in res], dim=2)
+    got = torch.cat([torch.from_numpy(r[2]) for r in res], dim=2)
     assert got.shape == want.shape
     assert [r[1] for r in res][0][0] == 0 and res[-1][1][1] == 44
     assert torch.allclose(got, want, rtol=2e-6, atol=1e-6)
