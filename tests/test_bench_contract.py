@@ -1,0 +1,67 @@
+"""bench.py contract pieces that do not need a GPU: workload naming, algorithmic bytes per launch class and the
+roofline object assembled from per-op CUDA-event times (keys the driver reads)."""
+import argparse
+import importlib.util
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+spec = importlib.util.spec_from_file_location("pcb_bench", os.path.join(ROOT, "bench.py"))
+bench = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(bench)
+
+
+def _args(**kw):
+    d = dict(mode="train", batch=4, volume=480, steps=10, warmup=3, gpus=1, sw_batch=4)
+    d.update(kw)
+    return argparse.Namespace(**d)
+
+
+def test_algorithmic_bytes_per_launch_class():
+    v, c = 4096000, 32
+    assert bench._op_bytes("mlp_fwd", f"mlp_fwd:m0C{c}H64Co32V{v}", 4) == 4 * v * 2 * (c + 2 * 32)       # y + residual in, out
+    assert bench._op_bytes("mlp_bwd_fused", f"mlp_bwd_fused:m0C{c}H64Co32V{v}", 4) == 4 * v * 2 * (2 * c + 32)
+    assert bench._op_bytes("dwconv_fwd", f"dwconv_fwd:m0C{c}V{v}", 1) == v * 2 * 2 * c
+    assert bench._op_bytes("dw_bwd_data", f"dw_bwd_data:m0C{c}V{v}", 1) == v * 2 * 3 * c                 # + fused residual gradient
+    assert bench._op_bytes("dw_bwd_data", f"dw_bwd_data:m2C64V{v}", 1) == v * 2 * 2 * 64
+    assert bench._op_bytes("gn_bwd", f"gn_bwd:C{c}V{v}", 2) == 2 * v * 2 * 3 * c
+    assert bench._op_bytes("tn_gemm", "tn_gemm:M32N64V512000", 1) is None
+
+
+def test_roofline_object_has_the_contract_keys():
+    a = _args()
+    key = "mlp_bwd_fused:m0C32H64Co32V4096000"
+    prof = {key: [3.0] * 12, "dwconv_fwd:m0C32V4096000": [1.4] * 12, "tn_gemm:M32N64V512000": [1.0] * 3,
+            "gn_bwd:C32V4096000": [0.6] * 12}
+    roof = bench.build_roofline(prof, a, 6554.9, True, 100.0, 3)
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "kernel", "launch_class", "others", "peak_source"):
+        assert k in roof
+    assert roof["launch_class"] == key and roof["bound"] == "hbm" and roof["unit"] == "GB/s"
+    nbytes = 4 * 4096000 * 2 * (2 * 32 + 32)
+    assert abs(roof["achieved"] - nbytes / 3.0e-3 / 1e9) < 1e-6 and abs(roof["frac"] - roof["achieved"] / 6554.9) < 1e-12
+    assert roof["traffic"] == bench.NCU_TRAFFIC[key] * 4                      # per-sample ncu capture x batch
+    assert [r["launch_class"].split(":")[0] for r in roof["others"]] == ["dwconv_fwd", "gn_bwd", "tn_gemm"]
+    assert bench.build_roofline({}, a, 6554.9, True, 100.0, 3) is None
+
+
+def test_workload_config_names_the_workload():
+    c = bench.workload_config(_args(), 2)
+    assert c["global_batch"] == 8 and c["parallelism"] == "dp2" and "BASELINE configs[1]" in c["workload"]
+    ci = bench.workload_config(_args(mode="infer"), 2)
+    assert ci["volume"] == [960, 480, 480] and "z-slab" in ci["parallelism"]
+    assert "model" not in c and "model" not in ci
+
+
+def test_reference_arm_prints_one_json_line():
+    # the reference arm runs on host cores only; keep it tiny here (1 step, no warm-up)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == bench.METRIC_TRAIN and d["unit"] == "sub-volumes/s"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["value"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

@@ -287,3 +287,19 @@ def test_monai_unet_builder_and_state_dict_keys():
     cfg.model.monai.norm = "group"
     with pytest.raises(NotImplementedError):
         A.build_model(cfg)
+
+
+def test_apply_border_mask_matches_reference():
+    # window.py:297-319: zero the outer k voxels per axis; too-large masks raise
+    from oracle import ref_loader
+    m = W.apply_border_mask(torch.ones(6, 8, 10), [1, 2, 0])
+    assert m.sum() == (6 - 2) * (8 - 4) * 10 and m[0].sum() == 0 and m[:, :2].sum() == 0 and m[:, :, 0].sum() > 0
+    assert torch.equal(W.apply_border_mask(torch.ones(4, 4), []), torch.ones(4, 4))
+    with pytest.raises(ValueError, match="too large"):
+        W.apply_border_mask(torch.ones(4, 4, 4), [2, 0, 0])
+    if ref_loader.available():      # build container: the real reference file, executed in place
+        R = ref_loader.ref_window()
+        for shape, mask in [((6, 8, 10), [1, 2, 0]), ((5, 5, 5), [2, 1, 1]), ((2, 7, 9), [0, 3, 4])]:
+            torch.manual_seed(0)
+            a = torch.rand(*shape)
+            assert torch.equal(W.apply_border_mask(a.clone(), mask), R.apply_border_mask(a.clone(), mask))
