@@ -132,6 +132,32 @@ def test_no_cpu_fallback():
         eng(inputs=torch.zeros(2, 1, 8, 8, 8), network=lambda t: t)
     with pytest.raises(ValueError):
         eng(inputs=torch.zeros(1, 8, 8), network=lambda t: t)
+    # the newer seams fail just as loudly: TTA views / folds, the z-slab engine, LayerNorm blocks
+    from pytorch_connectomics_b200.inference import TTAEnsemble, ZSlabShardedEngine, apply_view
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        apply_view(torch.zeros(1, 1, 4, 4, 4), [0], None, 0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        TTAEnsemble(NS(enabled=True, flip_axes="all")).predict(torch.zeros(1, 1, 4, 4, 4), lambda t: t)
+    with pytest.raises(ValueError, match=r"\[N,C,D,H,W\]"):
+        TTAEnsemble(None).predict(torch.zeros(1, 4, 4, 4), lambda t: t)
+    sh = ZSlabShardedEngine(roi_size=(8, 8, 8), sw_batch_size=1, overlap=0.5, mode="bump", rank=0, world=1)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        sh(torch.zeros(1, 1, 16, 16, 16), lambda t: t)
+    with pytest.raises(ValueError, match="smaller than the window"):
+        sh(torch.zeros(1, 1, 4, 16, 16), lambda t: t)
+    with pytest.raises(ValueError, match="batch size 1"):
+        sh(torch.zeros(2, 1, 16, 16, 16), lambda t: t)
+    with pytest.raises(ValueError, match="3-D roi_size"):
+        ZSlabShardedEngine(roi_size=(8, 8), sw_batch_size=1, overlap=0.5, mode="bump")
+    from pytorch_connectomics_b200.architectures.mednext import MedNeXtBlock
+    blk = MedNeXtBlock(16, 16, 2, 3, norm_type="layer")
+    assert type(blk.norm).__name__ == "LayerNorm" and list(blk.state_dict()) == list(MedNeXtBlock(16, 16, 2, 3).state_dict())
+    with pytest.raises(ValueError, match="norm_type"):
+        MedNeXtBlock(16, 16, 2, 3, norm_type="batch")
+    with pytest.raises(NotImplementedError):
+        MedNeXtBlock(16, 16, 2, 3, grn=True)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        blk(torch.zeros(1, 4, 4, 4, 16, dtype=torch.bfloat16))
 
 
 def test_config_resolvers():
