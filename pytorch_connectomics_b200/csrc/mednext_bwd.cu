@@ -580,6 +580,351 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) mlp_bwd_fused_kernel(Ml
   if (warp == 0) tmem_dealloc(tmem_base, tmem_cols);
 }
 
+// ============================================================================ warp-specialised fused MLP backward
+// OPT-IN (PCB_BWD_WS=1): same math, operands and partial-sum layout as mlp_bwd_fused_kernel, reorganised the way the forward
+// kernel is so that no role ever waits on a block-wide barrier (the 256-thread kernel spends its time in `wait` / `barrier`
+// stalls: five __syncthreads per tile and every MMA latency exposed).  One CTA per SM, 13 warps:
+//   4 loader warps   warp w owns stage w and the tiles it == w (mod 4): y -> GroupNorm-apply -> sA[w] (K-major, + the
+//                    all-ones core matrix per row group), dOut -> sD[w]
+//   1 MMA thread     G1 Hpre -> acc1[it&1], G2 dG -> accG[it&1]; one tile behind: G3 dYhat -> accD, G4 / G5 weight gradients
+//   2 x 4 epilogue   group eg owns the tiles it == eg (mod 2): E1 (GELU / GELU' -> sH[eg], sDh[eg]) and E2 (dYhat -> HBM,
+//                    GroupNorm-backward sums) of its tile; while it waits for G3 the other group runs its E1
+// TMEM: 2 x (acc1 + accG) + 2 x accD + accW3 + accW2 = 4H + 2C + Co + H columns (416 at level 0).  Level-0 shape only
+// (C = 32, Co = 32, H = 64, SAME / DOWN rows): the level-1 and up_0 shapes do not fit double-buffered accumulators.
+constexpr int WS_LOAD = 4, WS_EPI = 8, WS_THREADS = 32 * (WS_LOAD + WS_EPI + 1);
+
+// One warp stages a [128 x 32] bf16 tile (4 chunks of 16 B per row) into the K-major canonical layout with row-group
+// pitch `pitch` (same lane mapping as mf_stage_tile in mednext_fwd.cu): 8 loads in flight per lane, conflict-free stores.
+template <bool NORM>
+__device__ __forceinline__ void ws_stage_tile32(uint8_t* __restrict__ dst, uint32_t pitch, const uint4* __restrict__ src,
+                                                int row0, int nvalid, const float* __restrict__ sc,
+                                                const float* __restrict__ sh, int lane) {
+  const int rl = lane & 7, cs = lane >> 3;      // row inside the core matrix, chunk
+  uint64_t ps[4], pt[4];
+  if (NORM) {
+    const float4* sp = reinterpret_cast<const float4*>(sc + cs * 8);
+    const float4* tp = reinterpret_cast<const float4*>(sh + cs * 8);
+    const float4 s0 = sp[0], s1 = sp[1], t0 = tp[0], t1 = tp[1];
+    ps[0] = pk2(s0.x, s0.y); ps[1] = pk2(s0.z, s0.w); ps[2] = pk2(s1.x, s1.y); ps[3] = pk2(s1.z, s1.w);
+    pt[0] = pk2(t0.x, t0.y); pt[1] = pk2(t0.z, t0.w); pt[2] = pk2(t1.x, t1.y); pt[3] = pk2(t1.z, t1.w);
+  }
+  uint8_t* dl = dst + cs * 128 + rl * 16;
+#pragma unroll 1
+  for (int b = 0; b < 2; ++b) {
+    uint4 v[8];
+    uint32_t ok = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int r = (b * 8 + k) * 8 + rl;
+      v[k] = make_uint4(0, 0, 0, 0);
+      if (r < nvalid) { v[k] = __ldg(src + (int64_t)(row0 + r) * 4 + cs); ok |= 1u << k; }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      uint4 o = v[k];
+      if (NORM) {
+        const bool live = (ok >> k) & 1u;
+        float a0, a1, a2, a3, a4, a5, a6, a7;
+        upk2(fma2(pk2(bf16_lo(o.x), bf16_hi(o.x)), ps[0], pt[0]), a0, a1);
+        upk2(fma2(pk2(bf16_lo(o.y), bf16_hi(o.y)), ps[1], pt[1]), a2, a3);
+        upk2(fma2(pk2(bf16_lo(o.z), bf16_hi(o.z)), ps[2], pt[2]), a4, a5);
+        upk2(fma2(pk2(bf16_lo(o.w), bf16_hi(o.w)), ps[3], pt[3]), a6, a7);
+        o.x = live ? pack_bf16(a0, a1) : 0u; o.y = live ? pack_bf16(a2, a3) : 0u;
+        o.z = live ? pack_bf16(a4, a5) : 0u; o.w = live ? pack_bf16(a6, a7) : 0u;
+      }
+      *reinterpret_cast<uint4*>(dl + (b * 8 + k) * pitch) = o;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(WS_THREADS, 1) mlp_bwd_ws_kernel(MlpBwdFusedArgs fa) {
+  const MlpBwdArgs& a = fa.m;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int c8n = a.C >> 3, h8n = a.H >> 3, o8n = a.Co >> 3;      // 4, 8, 4
+  const uint32_t pitchA = (c8n + 1) * 128, pitchD = o8n * 128, pitchH = h8n * 128;
+  const uint32_t stageA = 16 * pitchA, stageD = 16 * pitchD, stageH = 16 * pitchH;
+  uint8_t* sW2 = smem;                                 // [H x C]   K-major (B of G1)
+  uint8_t* sW3t = sW2 + a.H * a.C * 2;                 // [H x Co]  K-major (B of G2)
+  uint8_t* sW2t = sW3t + a.H * a.Co * 2;               // [C x H]   K-major (B of G3)
+  uint8_t* sA = sW2t + a.C * a.H * 2;                  // 4 x [128 x C] + ones core matrix per row group
+  uint8_t* sD = sA + 4 * stageA;                       // 4 x [128 x Co]
+  uint8_t* sH = sD + 4 * stageD;                       // 2 x [128 x H]
+  uint8_t* sDh = sH + 2 * stageH;                      // 2 x [128 x H]
+  uint8_t* sTail = sDh + 2 * stageH;                   // 2 KB finite padding behind the last MN-major operand
+  float* sScale = reinterpret_cast<float*>(sTail + 2048);   // [N][C] gamma*rstd
+  float* sShift = sScale + fa.N * a.C;                 // [N][C]
+  float* sRstd = sShift + fa.N * a.C;                  // [N][C]
+  float* sMR = sRstd + fa.N * a.C;                     // [N][C] mean*rstd
+  float* sB2 = sMR + fa.N * a.C;                       // [H]
+  float* sDb3 = sB2 + a.H;                             // [2][Co] per-group conv3 bias-gradient partials
+  double* sG = reinterpret_cast<double*>(sDb3 + 2 * a.Co);  // [N][2C] S1, S2 per sample
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sG + fa.N * 2 * a.C);
+  uint64_t* a_full = bars;          // [4] loaders -> MMA / epilogue
+  uint64_t* a_empty = bars + 4;     // [4] MMA (G4/G5 retired) -> loaders
+  uint64_t* hp_full = bars + 8;     // [2] MMA (G1/G2) -> E1
+  uint64_t* e1_done = bars + 10;    // [2] E1 -> MMA
+  uint64_t* d_full = bars + 12;     // [2] MMA (G3) -> E2
+  uint64_t* d_empty = bars + 14;    // [2] E2 -> MMA
+  uint64_t* h_free = bars + 16;     // [2] MMA (G3/G4/G5 retired) -> E1
+  uint64_t* w_done = bars + 18;     // every MMA of the CTA retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+
+  const uint32_t tmem_cols = tmem_cols_pow2((uint32_t)(5 * a.H + 2 * a.C + a.Co));
+  if (warp == WS_LOAD + WS_EPI) tmem_alloc(tmem_slot, tmem_cols);
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) { mbar_init(&a_full[i], 32); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&hp_full[i], 1); mbar_init(&e1_done[i], 128); mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 128);
+      mbar_init(&h_free[i], 1);
+    }
+    mbar_init(w_done, 1);
+    fence_mbar_init();
+  }
+  stage_rows_k(sW2, a.w2, a.H, c8n, c8n, tid, WS_THREADS);
+  stage_rows_k(sW3t, a.w3t, a.H, o8n, o8n, tid, WS_THREADS);
+  stage_rows_k(sW2t, a.w2t, a.C, h8n, h8n, tid, WS_THREADS);
+  for (int i = tid; i < a.H; i += WS_THREADS) sB2[i] = a.b2[i];
+  for (int i = tid; i < fa.N * a.C; i += WS_THREADS) {
+    const int n = i / a.C, c = i - n * a.C;
+    const double sm = a.stats[(int64_t)n * 2 * a.C + c], q = a.stats[(int64_t)n * 2 * a.C + a.C + c];
+    const double mean = sm * (double)a.inv_count;
+    double var = q * (double)a.inv_count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + 1e-5));
+    const float g = a.gamma[c] * rstd;
+    sScale[i] = g; sShift[i] = a.beta[c] - (float)mean * g; sRstd[i] = rstd; sMR[i] = (float)mean * rstd;
+  }
+  for (int i = tid; i < fa.N * 2 * a.C; i += WS_THREADS) sG[i] = 0.0;
+  for (int i = tid; i < 2 * a.Co; i += WS_THREADS) sDb3[i] = 0.f;
+  // all-ones core matrix (chunk index c8n) of every row group of every A stage; finite tail
+  for (int i = tid; i < 4 * 128; i += WS_THREADS) {
+    const int st = i >> 7, r = i & 127;
+    *reinterpret_cast<uint4*>(sA + st * stageA + (r >> 3) * pitchA + c8n * 128 + (r & 7) * 16) = make_uint4(0x3F80u, 0, 0, 0);
+  }
+  for (int i = tid; i < 128; i += WS_THREADS) *reinterpret_cast<uint4*>(sTail + i * 16) = make_uint4(0, 0, 0, 0);
+  // the MN-major operand reads run past the valid channel groups: keep every operand byte finite from the start
+  for (uint32_t i = tid * 16; i < 4 * stageD + 4 * stageH; i += WS_THREADS * 16) *reinterpret_cast<uint4*>(sD + i) = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // TMEM columns: acc1[g] g*H | accG[g] 2H + g*H | accD[g] 4H + g*C | accW3 4H+2C | accW2 4H+2C+Co
+  const uint32_t colD = 4 * a.H, colW3 = colD + 2 * a.C, colW2 = colW3 + a.Co;
+
+  if (warp < WS_LOAD) {
+    // ===================================================================== loaders
+    int uses = 0;
+    for (int64_t g = blockIdx.x + (int64_t)warp * gridDim.x; g < fa.ntiles; g += 4ll * gridDim.x, ++uses) {
+      if (uses >= 1) mbar_wait(&a_empty[warp], (uint32_t)((uses - 1) & 1));
+      const int n = (int)(g / fa.tps);
+      const int tile0 = (int)((g - (int64_t)n * fa.tps) * 128);
+      const int nvalid = min(128, (int)a.Vy - tile0);
+      ws_stage_tile32<true>(sA + warp * stageA, pitchA, a.y + (int64_t)n * a.Vy * c8n, tile0, nvalid, sScale + n * a.C,
+                            sShift + n * a.C, lane);
+      ws_stage_tile32<false>(sD + warp * stageD, pitchD, a.dout + (int64_t)n * a.Vout * o8n, tile0, nvalid, nullptr, nullptr, lane);
+      fence_proxy_async_smem();
+      mbar_arrive(&a_full[warp]);
+    }
+  } else if (warp == WS_LOAD + WS_EPI) {
+    // ===================================================================== MMA issuer (one thread)
+    if (lane == 0) {
+      const uint32_t idescH = umma_idesc_bf16(128, a.H, 0, 0), idescD = umma_idesc_bf16(128, a.C, 0, 0);
+      const uint32_t idescW3 = umma_idesc_bf16(128, a.Co, 1, 1), idescW2 = umma_idesc_bf16(128, a.H, 1, 1);
+      const uint64_t dW2 = umma_desc(smem_u32(sW2), 128, c8n * 128), dW3 = umma_desc(smem_u32(sW3t), 128, o8n * 128);
+      const uint64_t dW2t = umma_desc(smem_u32(sW2t), 128, h8n * 128);
+      auto second_half = [&](int64_t j) {     // G3 + weight-gradient GEMMs of local tile j
+        const int gj = (int)(j & 1), sj = (int)(j & 3);
+        const int64_t u = j >> 1;
+        mbar_wait(&e1_done[gj], (uint32_t)(u & 1));
+        if (j >= 2) mbar_wait(&d_empty[gj], (uint32_t)((u - 1) & 1));
+        tc_fence_after();
+        const uint64_t dDhK = umma_desc(smem_u32(sDh + gj * stageH), 128, pitchH);
+        for (int k = 0; k < a.H / 16; ++k)
+          umma_bf16(tmem_base + colD + gj * a.C, dDhK + (uint64_t)(k * 16), dW2t + (uint64_t)(k * 16), idescD, k > 0 ? 1u : 0u);
+        tc_commit(&d_full[gj]);
+        const uint64_t aH = umma_desc(smem_u32(sH + gj * stageH), pitchH, 128), bD = umma_desc(smem_u32(sD + sj * stageD), pitchD, 128);
+        const uint64_t aA = umma_desc(smem_u32(sA + sj * stageA), pitchA, 128), bDh = umma_desc(smem_u32(sDh + gj * stageH), pitchH, 128);
+        for (int k = 0; k < 8; ++k)
+          umma_bf16(tmem_base + colW3, aH + (uint64_t)(k * 2 * (pitchH >> 4)), bD + (uint64_t)(k * 2 * (pitchD >> 4)), idescW3,
+                    (j > 0 || k > 0) ? 1u : 0u);
+        for (int k = 0; k < 8; ++k)
+          umma_bf16(tmem_base + colW2, aA + (uint64_t)(k * 2 * (pitchA >> 4)), bDh + (uint64_t)(k * 2 * (pitchH >> 4)), idescW2,
+                    (j > 0 || k > 0) ? 1u : 0u);
+        tc_commit(&a_empty[sj]);
+        tc_commit(&h_free[gj]);
+      };
+      int64_t it = 0;
+      for (int64_t g = blockIdx.x; g < fa.ntiles; g += gridDim.x, ++it) {
+        const int s = (int)(it & 3), gacc = (int)(it & 1);
+        mbar_wait(&a_full[s], (uint32_t)((it >> 2) & 1));
+        tc_fence_after();
+        const uint64_t dA = umma_desc(smem_u32(sA + s * stageA), 128, pitchA), dD = umma_desc(smem_u32(sD + s * stageD), 128, pitchD);
+        for (int k = 0; k < a.C / 16; ++k)
+          umma_bf16(tmem_base + gacc * a.H, dA + (uint64_t)(k * 16), dW2 + (uint64_t)(k * 16), idescH, k > 0 ? 1u : 0u);
+        for (int k = 0; k < a.Co / 16; ++k)
+          umma_bf16(tmem_base + 2 * a.H + gacc * a.H, dD + (uint64_t)(k * 16), dW3 + (uint64_t)(k * 16), idescH, k > 0 ? 1u : 0u);
+        tc_commit(&hp_full[gacc]);
+        if (it >= 1) second_half(it - 1);
+      }
+      if (it >= 1) second_half(it - 1);
+      tc_commit(w_done);
+    }
+  } else {
+    // ===================================================================== epilogue groups
+    const int eg = (warp - WS_LOAD) >> 2;
+    const int wq = warp & 3, row = wq * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
+    float db3acc = 0.f;        // wq == 0: running sum_v dOut[v, lane] over this group's tiles
+    int64_t it = eg;
+    for (int64_t g = blockIdx.x + (int64_t)eg * gridDim.x; g < fa.ntiles; g += 2ll * gridDim.x, it += 2) {
+      const int64_t u = it >> 1;
+      const uint32_t par = (uint32_t)(u & 1);
+      const int s = (int)(it & 3);
+      const int n = (int)(g / fa.tps);
+      const int tile0 = (int)((g - (int64_t)n * fa.tps) * 128);
+      const int prow = tile0 + row;
+      const bool row_ok = prow < (int)a.Vy;
+      mbar_wait(&a_full[s], (uint32_t)((it >> 2) & 1));      // this group reads sD[s] itself (conv3 bias gradient)
+      if (wq == 0 && lane < a.Co) {
+        const uint8_t* col = sD + s * stageD + (lane >> 3) * 128 + (lane & 7) * 2;
+        float sacc = 0.f;
+#pragma unroll 8
+        for (int r = 0; r < 128; ++r)
+          sacc += __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(col + (r >> 3) * pitchD + (r & 7) * 16)) << 16);
+        db3acc += sacc;
+      }
+      mbar_wait(&hp_full[eg], par);
+      if (u >= 1) mbar_wait(&h_free[eg], (uint32_t)((u - 1) & 1));
+      tc_fence_after();
+      // ---- E1: Hact -> sH[eg], dh -> sDh[eg]
+      {
+        const uint32_t t1 = tmem_base + eg * a.H + lane_off, tg = tmem_base + 2 * a.H + eg * a.H + lane_off;
+        uint8_t* dH = sH + eg * stageH + (row >> 3) * pitchH + (row & 7) * 16;
+        uint8_t* dDh = sDh + eg * stageH + (row >> 3) * pitchH + (row & 7) * 16;
+#pragma unroll 1
+        for (int c16 = 0; c16 < a.H / 16; ++c16) {
+          uint32_t v1[16], vg[16];
+          tmem_ld16(t1 + c16 * 16, v1);
+          tmem_ld16(tg + c16 * 16, vg);
+          tmem_ld_wait();
+          uint32_t hw[8], dw[8];
+          const float4* bp = reinterpret_cast<const float4*>(sB2 + c16 * 16);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 b = bp[j4];
+            uint64_t va, ga, vb, gb;
+            gelu_fast_vg2(add2(pk2(__uint_as_float(v1[4 * j4]), __uint_as_float(v1[4 * j4 + 1])), pk2(b.x, b.y)), va, ga);
+            gelu_fast_vg2(add2(pk2(__uint_as_float(v1[4 * j4 + 2]), __uint_as_float(v1[4 * j4 + 3])), pk2(b.z, b.w)), vb, gb);
+            ga = mul2(ga, pk2(__uint_as_float(vg[4 * j4]), __uint_as_float(vg[4 * j4 + 1])));
+            gb = mul2(gb, pk2(__uint_as_float(vg[4 * j4 + 2]), __uint_as_float(vg[4 * j4 + 3])));
+            float e0, e1;
+            upk2(va, e0, e1); hw[2 * j4] = pack_bf16(e0, e1);
+            upk2(vb, e0, e1); hw[2 * j4 + 1] = pack_bf16(e0, e1);
+            upk2(ga, e0, e1); dw[2 * j4] = pack_bf16(e0, e1);
+            upk2(gb, e0, e1); dw[2 * j4 + 1] = pack_bf16(e0, e1);
+          }
+          *reinterpret_cast<uint4*>(dH + (c16 * 2) * 128) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          *reinterpret_cast<uint4*>(dH + (c16 * 2 + 1) * 128) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+          *reinterpret_cast<uint4*>(dDh + (c16 * 2) * 128) = make_uint4(dw[0], dw[1], dw[2], dw[3]);
+          *reinterpret_cast<uint4*>(dDh + (c16 * 2 + 1) * 128) = make_uint4(dw[4], dw[5], dw[6], dw[7]);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(&e1_done[eg]);
+      // ---- E2: g = dYhat -> bf16 -> HBM ; S1 += g ; S2 += g * xhat
+      const int64_t yrow = ((int64_t)n * a.Vy + prow) * c8n;
+      uint4 ypre[4];                                       // the row's y (L2-resident: the loaders just read it)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) ypre[c] = row_ok ? __ldg(a.y + yrow + c) : make_uint4(0, 0, 0, 0);
+      mbar_wait(&d_full[eg], par);
+      tc_fence_after();
+      {
+        const uint32_t td = tmem_base + colD + eg * a.C + lane_off;
+        const float* rs = sRstd + n * a.C; const float* mr = sMR + n * a.C;
+        double* sGn = sG + n * 2 * a.C;
+#pragma unroll
+        for (int c16 = 0; c16 < 2; ++c16) {
+          uint32_t v[16];
+          tmem_ld16(td + c16 * 16, v);
+          tmem_ld_wait();
+          float gq[16], gx[16];
+          if (row_ok) {
+            float yv[16];
+            unpack8(ypre[2 * c16], yv);
+            unpack8(ypre[2 * c16 + 1], yv + 8);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              gq[j] = round_bf16(__uint_as_float(v[j]));
+              gx[j] = gq[j] * fmaf(yv[j], rs[c16 * 16 + j], -mr[c16 * 16 + j]);
+            }
+            a.dyhat[yrow + c16 * 2] = pack8(gq);
+            a.dyhat[yrow + c16 * 2 + 1] = pack8(gq + 8);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { gq[j] = 0.f; gx[j] = 0.f; }
+          }
+          warp_colsum16(gq, lane);
+          warp_colsum16(gx, lane);
+          if (!(lane & 1)) {
+            const int col = c16 * 16 + colsum16_col(lane);
+            atomicAdd(&sGn[col], (double)gq[0]);
+            atomicAdd(&sGn[a.C + col], (double)gx[0]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&d_empty[eg]);
+    }
+    if (wq == 0 && lane < a.Co) sDb3[eg * a.Co + lane] = db3acc;
+  }
+  tc_fence_before();
+  __syncthreads();
+  // ---- weight-gradient partials of this CTA (every CTA owns >= 1 tile: the grid never exceeds the tile count)
+  if (warp >= WS_LOAD && warp < WS_LOAD + 4) {
+    mbar_wait(w_done, 0);
+    tc_fence_after();
+    const int wq = warp & 3, row = wq * 32 + lane;
+    const uint32_t lo = (uint32_t)(wq * 32) << 16;
+    float* p3 = fa.part3 + ((int64_t)blockIdx.x * 129 + row) * a.Co;
+    if (row < a.Co) fa.part3[((int64_t)blockIdx.x * 129 + 128) * a.Co + row] = sDb3[row] + sDb3[a.Co + row];
+    for (int c16 = 0; c16 < a.Co / 16; ++c16) {
+      uint32_t v[16];
+      tmem_ld16(tmem_base + colW3 + lo + c16 * 16, v);
+      tmem_ld_wait();
+      if (row < a.H) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) p3[c16 * 16 + j] = __uint_as_float(v[j]);
+      }
+    }
+    float* p2 = fa.part2 + ((int64_t)blockIdx.x * 128 + row) * a.H;
+    for (int c16 = 0; c16 < a.H / 16; ++c16) {
+      uint32_t v[16];
+      tmem_ld16(tmem_base + colW2 + lo + c16 * 16, v);
+      tmem_ld_wait();
+      if (row <= a.C) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) p2[c16 * 16 + j] = __uint_as_float(v[j]);
+      }
+    }
+  }
+  for (int i = tid; i < fa.N * 2 * a.C; i += WS_THREADS) {
+    const double v = sG[i];
+    if (v != 0.0) atomicAdd(&a.gstats[i], v);       // sG is [N][2C] exactly like gstats
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == WS_LOAD + WS_EPI) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+static size_t mlp_bwd_ws_smem(int C, int H, int Co, int N) {
+  return (size_t)H * C * 2 + (size_t)H * Co * 2 + (size_t)C * H * 2 + (size_t)4 * 16 * (C / 8 + 1) * 128 + (size_t)4 * 16 * (Co / 8) * 128 +
+         (size_t)4 * 16 * (H / 8) * 128 + 2048 + (size_t)4 * N * C * 4 + (size_t)H * 4 + (size_t)2 * Co * 4 + (size_t)N * 2 * C * 8 +
+         19 * 8 + 16 + 128;
+}
+
 static size_t mlp_bwd_fused_smem(int C, int H, int Co, int N) {
   return (size_t)H * C * 2 + (size_t)H * Co * 2 + (size_t)C * H * 2 + (size_t)16 * (C / 8 + 1) * 128 + (size_t)16 * (Co / 8) * 128 +
          (size_t)16 * (H / 8) * 128 + (size_t)16 * (H / 8) * 128 + (size_t)128 * (C * 2 + 16) + 2048 + (size_t)4 * N * C * 4 + (size_t)H * 4 +
@@ -1547,6 +1892,31 @@ extern "C" int pcb_mlp_bwd_fused(const void* y, const double* stats, const float
     configured = true;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  // opt-in warp-specialised variant for the level-0 shape (see mlp_bwd_ws_kernel); same workspace layout, P = grid size
+  {
+    const char* ws_env = getenv("PCB_BWD_WS");
+    if (ws_env && ws_env[0] == '1' && C == 32 && Co == 32 && H == 64 && mode != PCB_DW_UP && N <= 8 &&
+        mlp_bwd_ws_smem((int)C, (int)H, (int)Co, (int)N) <= 227 * 1024) {
+      static bool conf_ws = false;
+      if (!conf_ws) {
+        cudaFuncSetAttribute(mlp_bwd_ws_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        conf_ws = cudaFuncSetAttribute(mlp_bwd_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess;
+        if (!conf_ws) cudaGetLastError();
+      }
+      if (conf_ws) {
+        const int Pw = (int)(fa.ntiles < 148 ? fa.ntiles : 148);     // <= P: the caller's workspace is large enough
+        fa.part3 = workspace; fa.part2 = workspace + (int64_t)Pw * 129 * Co;
+        mlp_bwd_ws_kernel<<<Pw, WS_THREADS, mlp_bwd_ws_smem((int)C, (int)H, (int)Co, (int)N), st>>>(fa);
+        PCB_CHECK_LAUNCH("pcb_mlp_bwd_fused(ws)");
+        reduce_partials_kernel<<<(unsigned)((H * Co + 31) / 32), 256, 0, st>>>(fa.part3, Pw, (int)H, 129, (int)Co, (int)Co, dW3, 1, H, nullptr);
+        reduce_partials_kernel<<<(unsigned)((Co + 31) / 32), 256, 0, st>>>(fa.part3 + 128 * Co, Pw, 1, 129, (int)Co, (int)Co, db3, 0, 1, nullptr);
+        reduce_partials_kernel<<<(unsigned)((C * H + 31) / 32), 256, 0, st>>>(fa.part2, Pw, (int)C, 128, (int)H, (int)H, dW2, 1, C, nullptr);
+        reduce_partials_kernel<<<(unsigned)((H + 31) / 32), 256, 0, st>>>(fa.part2 + C * H, Pw, 1, 128, (int)H, (int)H, db2, 0, 1, nullptr);
+        PCB_CHECK_LAUNCH("pcb_mlp_bwd_fused(ws reduce)");
+        return PCB_OK;
+      }
+    }
+  }
   // one CTA per SM (TMEM > 256 columns): four warpgroups; H >= 64 and C >= 64 keep every warpgroup busy in E1 / E2
   const char* nt_env = getenv("PCB_BWD_NT512");
   const bool wide = tcols > 256 && H / 16 >= 4 && !(nt_env && nt_env[0] == '0');

@@ -3,6 +3,8 @@
 Same tolerance statement as tests/test_mednext_gpu.py: errors are relative L2 against the fp32
 oracle gradients, compared with the error of the oracle run under torch.autocast(bfloat16) (the
 reference's own bf16 training path); the engine may be at most 1.5x that + a small slack."""
+import os
+
 import pytest
 import torch
 
@@ -311,3 +313,12 @@ def test_block_layernorm_forward_backward(kind, cin, cout, r, size):
     out.backward(cl(gout))
     got_p = {k: v.grad.detach() for k, v in p.named_parameters() if v.grad is not None}
     _compare(f"layernorm {kind} C{cin}", ncdhw(xc.grad), got_p, ref32, refbf)
+
+
+@pytest.mark.skipif(os.environ.get("PCB_TEST_OPTIN") != "1", reason="opt-in kernels: set PCB_TEST_OPTIN=1")
+@pytest.mark.parametrize("size", [(16, 16, 16), (9, 10, 11), (24, 20, 18)])
+def test_block_backward_warp_specialised(size, monkeypatch):
+    """mlp_bwd_ws_kernel (PCB_BWD_WS=1, level-0 shape): same parity bar as the default fused backward; 2 samples,
+    ragged last tiles, more tiles than one wave of loader stages (24*20*18 = 68 tiles per sample)."""
+    monkeypatch.setenv("PCB_BWD_WS", "1")
+    test_block_backward("same", 32, 32, 2, 3, size)
