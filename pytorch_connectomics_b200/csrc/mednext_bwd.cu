@@ -285,6 +285,7 @@ struct MlpBwdFusedArgs {
   float* part2;      // [P][128][H]   partial dW2^T (+ row C = db2)
   int N;
   int64_t tps, ntiles;
+  uint32_t dm2, dm1; int ds2, ds1;   // exact division by y2 / y1 (mlp_bwd_ws2_kernel, UP-mode dOut row map)
 };
 
 constexpr int BF_PF = 8;          // prefetch depth: (C/8 + Co/8) * 128 / 256 <= 8 chunks per thread
@@ -917,6 +918,397 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_bwd_ws_kernel(MlpBwdFusedAr
   tc_fence_before();
   __syncthreads();
   if (warp == WS_LOAD + WS_EPI) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ---------------------------------------------------------------------------- generalised warp-specialised backward
+// OPT-IN (PCB_BWD_WS=2): the role split of mlp_bwd_ws_kernel for every shape the fused backward serves.
+//   C8N = C/8 in {4, 8};  NB = accumulator / Hact / dh buffers: 2 where 2(2H + C) + Co + H <= 512 TMEM columns (level 0),
+//   else 1 (level 1, up_0, down_0: 2H + C + Co + H <= 512) — with one buffer G1/G2 of tile i+1 still overlap G3/E2 of tile i
+//   (the MMA thread issues them as soon as E1 of tile i has drained the accumulators).
+//   Operand stages: 4 (NB = 2) or 2 (NB = 1; shared memory), one loader warp per tile either way.
+//   UP mode: dOut rows through a per-tile table (p -> p + 1 on every axis, divisions by multiplication).
+template <int C8N, bool NORM, bool TAB>
+__device__ __forceinline__ void ws2_stage_tile(uint8_t* __restrict__ dst, uint32_t pitch, const uint4* __restrict__ src,
+                                               const int* __restrict__ tab, int row0, int nvalid, const float* __restrict__ sc,
+                                               const float* __restrict__ sh, int lane) {
+  static_assert(C8N == 4 || C8N == 8, "C8N");
+  constexpr int J = C8N / 4;      // chunks per lane per row group
+  constexpr int RGB = 8 / J;      // row groups per batch of 8 loads
+  const int rl = lane & 7, cs = lane >> 3;
+  uint64_t ps[J][4], pt[J][4];
+  if (NORM) {
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const float4* sp = reinterpret_cast<const float4*>(sc + (cs + 4 * j) * 8);
+      const float4* tp = reinterpret_cast<const float4*>(sh + (cs + 4 * j) * 8);
+      const float4 s0 = sp[0], s1 = sp[1], t0 = tp[0], t1 = tp[1];
+      ps[j][0] = pk2(s0.x, s0.y); ps[j][1] = pk2(s0.z, s0.w); ps[j][2] = pk2(s1.x, s1.y); ps[j][3] = pk2(s1.z, s1.w);
+      pt[j][0] = pk2(t0.x, t0.y); pt[j][1] = pk2(t0.z, t0.w); pt[j][2] = pk2(t1.x, t1.y); pt[j][3] = pk2(t1.z, t1.w);
+    }
+  }
+  uint8_t* dl = dst + cs * 128 + rl * 16;
+#pragma unroll 1
+  for (int b = 0; b < 16 / RGB; ++b) {
+    uint4 v[8];
+    uint32_t ok = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int rg = b * RGB + k / J, j = k % J;
+      const int r = rg * 8 + rl;
+      int ry;
+      if (TAB) ry = tab[r]; else ry = r < nvalid ? row0 + r : -1;
+      v[k] = make_uint4(0, 0, 0, 0);
+      if (ry >= 0) { v[k] = __ldg(src + (int64_t)ry * C8N + (cs + 4 * j)); ok |= 1u << k; }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int rg = b * RGB + k / J, j = k % J;
+      uint4 o = v[k];
+      if (NORM) {
+        const bool live = (ok >> k) & 1u;
+        float a0, a1, a2, a3, a4, a5, a6, a7;
+        upk2(fma2(pk2(bf16_lo(o.x), bf16_hi(o.x)), ps[j][0], pt[j][0]), a0, a1);
+        upk2(fma2(pk2(bf16_lo(o.y), bf16_hi(o.y)), ps[j][1], pt[j][1]), a2, a3);
+        upk2(fma2(pk2(bf16_lo(o.z), bf16_hi(o.z)), ps[j][2], pt[j][2]), a4, a5);
+        upk2(fma2(pk2(bf16_lo(o.w), bf16_hi(o.w)), ps[j][3], pt[j][3]), a6, a7);
+        o.x = live ? pack_bf16(a0, a1) : 0u; o.y = live ? pack_bf16(a2, a3) : 0u;
+        o.z = live ? pack_bf16(a4, a5) : 0u; o.w = live ? pack_bf16(a6, a7) : 0u;
+      }
+      *reinterpret_cast<uint4*>(dl + rg * pitch + j * 512) = o;
+    }
+  }
+}
+
+__device__ __forceinline__ int ws2_fdiv(int n, uint32_t m, int sh) { return (int)(((uint64_t)(uint32_t)n * (uint64_t)m) >> sh); }
+
+template <int C8N, int NB>
+__global__ void __launch_bounds__(WS_THREADS, 1) mlp_bwd_ws2_kernel(MlpBwdFusedArgs fa) {
+  constexpr int NST = NB == 2 ? 4 : 2;
+  const MlpBwdArgs& a = fa.m;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int c8n = C8N, h8n = a.H >> 3, o8n = a.Co >> 3;
+  const uint32_t pitchA = (c8n + 1) * 128, pitchD = o8n * 128, pitchH = h8n * 128;
+  const uint32_t stageA = 16 * pitchA, stageD = 16 * pitchD, stageH = 16 * pitchH;
+  uint8_t* sW2 = smem;                                 // [H x C]   K-major (B of G1)
+  uint8_t* sW3t = sW2 + a.H * a.C * 2;                 // [H x Co]  K-major (B of G2)
+  uint8_t* sW2t = sW3t + a.H * a.Co * 2;               // [C x H]   K-major (B of G3)
+  uint8_t* sA = sW2t + a.C * a.H * 2;                  // NST x ([128 x C] + ones core matrix per row group)
+  uint8_t* sD = sA + NST * stageA;                     // NST x [128 x Co]
+  uint8_t* sH = sD + NST * stageD;                     // NB x [128 x H]
+  uint8_t* sDh = sH + NB * stageH;                     // NB x [128 x H]
+  uint8_t* sTail = sDh + NB * stageH;                  // 2 KB finite padding behind the last MN-major operand
+  float* sScale = reinterpret_cast<float*>(sTail + 2048);   // [N][C] gamma*rstd
+  float* sShift = sScale + fa.N * a.C;                 // [N][C]
+  float* sRstd = sShift + fa.N * a.C;                  // [N][C]
+  float* sMR = sRstd + fa.N * a.C;                     // [N][C] mean*rstd
+  float* sB2 = sMR + fa.N * a.C;                       // [H]
+  float* sDb3 = sB2 + a.H;                             // [2][Co]
+  int* sRow = reinterpret_cast<int*>(sDb3 + 2 * a.Co); // [4 loader warps][128] dOut row of the tile in flight (UP mode)
+  double* sG = reinterpret_cast<double*>(sRow + WS_LOAD * 128);   // [N][2C]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sG + fa.N * 2 * a.C);
+  // Barriers are indexed by the TILE (it & 3 for the loader hand-offs, it & 1 for the accumulator hand-offs) and the DATA
+  // by it % NST / it % NB: every barrier then has exactly one waiting role that sees each of its completions, whatever
+  // NST / NB are (a waiter that skipped a completion would mis-read the phase parity).
+  uint64_t* a_full = bars;          // [4] loader warp (it & 3) -> MMA / epilogue
+  uint64_t* a_empty = bars + 4;     // [4] MMA (G4/G5 of tile it retired) -> the loader of tile it + NST
+  uint64_t* hp_full = bars + 8;     // [2] MMA (G1/G2) -> E1
+  uint64_t* e1_done = bars + 10;    // [2] E1 -> MMA
+  uint64_t* d_full = bars + 12;     // [2] MMA (G3) -> E2
+  uint64_t* d_empty = bars + 14;    // [2] E2 -> MMA
+  uint64_t* h_free = bars + 16;     // [2] MMA (G3/G4/G5 retired) -> E1 of tile it + NB
+  uint64_t* w_done = bars + 18;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+
+  const uint32_t tmem_cols = tmem_cols_pow2((uint32_t)(NB * (2 * a.H + a.C) + a.Co + a.H));
+  if (warp == WS_LOAD + WS_EPI) tmem_alloc(tmem_slot, tmem_cols);
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) { mbar_init(&a_full[i], 32); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&hp_full[i], 1); mbar_init(&e1_done[i], 128); mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 128);
+      mbar_init(&h_free[i], 1);
+    }
+    mbar_init(w_done, 1);
+    fence_mbar_init();
+  }
+  stage_rows_k(sW2, a.w2, a.H, c8n, c8n, tid, WS_THREADS);
+  stage_rows_k(sW3t, a.w3t, a.H, o8n, o8n, tid, WS_THREADS);
+  stage_rows_k(sW2t, a.w2t, a.C, h8n, h8n, tid, WS_THREADS);
+  for (int i = tid; i < a.H; i += WS_THREADS) sB2[i] = a.b2[i];
+  for (int i = tid; i < fa.N * a.C; i += WS_THREADS) {
+    const int n = i / a.C, c = i - n * a.C;
+    const double sm = a.stats[(int64_t)n * 2 * a.C + c], q = a.stats[(int64_t)n * 2 * a.C + a.C + c];
+    const double mean = sm * (double)a.inv_count;
+    double var = q * (double)a.inv_count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + 1e-5));
+    const float g = a.gamma[c] * rstd;
+    sScale[i] = g; sShift[i] = a.beta[c] - (float)mean * g; sRstd[i] = rstd; sMR[i] = (float)mean * rstd;
+  }
+  for (int i = tid; i < fa.N * 2 * a.C; i += WS_THREADS) sG[i] = 0.0;
+  for (int i = tid; i < 2 * a.Co; i += WS_THREADS) sDb3[i] = 0.f;
+  // every operand byte finite from the start (MN-major reads run past the valid channel groups), then the ones matrices
+  for (uint32_t i = tid * 16; i < NST * (stageA + stageD) + 2 * NB * stageH + 2048; i += WS_THREADS * 16)
+    *reinterpret_cast<uint4*>(sA + i) = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  for (int i = tid; i < NST * 128; i += WS_THREADS) {
+    const int st = i >> 7, r = i & 127;
+    *reinterpret_cast<uint4*>(sA + st * stageA + (r >> 3) * pitchA + c8n * 128 + (r & 7) * 16) = make_uint4(0x3F80u, 0, 0, 0);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // TMEM columns: acc1[b] b*H | accG[b] NB*H + b*H | accD[b] 2*NB*H + b*C | accW3 | accW2
+  const uint32_t colG = NB * a.H, colD = 2 * NB * a.H, colW3 = colD + NB * a.C, colW2 = colW3 + a.Co;
+  const bool up = a.mode == PCB_DW_UP;
+
+  if (warp < WS_LOAD) {
+    // ===================================================================== loaders: warp w owns the tiles it == w (mod 4)
+    int* rowO = sRow + warp * 128;
+    for (int64_t it = warp, g = blockIdx.x + (int64_t)warp * gridDim.x; g < fa.ntiles; g += 4ll * gridDim.x, it += 4) {
+      const int s = (int)(it % NST);
+      const int64_t prev = it - NST;                    // the tile that used this stage last
+      if (prev >= 0) mbar_wait(&a_empty[prev & 3], (uint32_t)((prev >> 2) & 1));
+      const int n = (int)(g / fa.tps);
+      const int tile0 = (int)((g - (int64_t)n * fa.tps) * 128);
+      const int nvalid = min(128, (int)a.Vy - tile0);
+      ws2_stage_tile<C8N, true, false>(sA + s * stageA, pitchA, a.y + (int64_t)n * a.Vy * c8n, nullptr, tile0, nvalid,
+                                       sScale + n * a.C, sShift + n * a.C, lane);
+      const uint4* dn = a.dout + (int64_t)n * a.Vout * o8n;
+      if (up) {
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int r = lane + 32 * k, p = tile0 + r;
+          int ro = -1;
+          if (r < nvalid) {
+            const int t = ws2_fdiv(p, fa.dm2, fa.ds2), x = p - t * a.y2;
+            const int z = ws2_fdiv(t, fa.dm1, fa.ds1), y = t - z * a.y1;
+            ro = ((z + 1) * a.o1 + (y + 1)) * a.o2 + (x + 1);
+          }
+          rowO[r] = ro;
+        }
+        __syncwarp();
+        if (o8n == 8) ws2_stage_tile<8, false, true>(sD + s * stageD, pitchD, dn, rowO, 0, 0, nullptr, nullptr, lane);
+        else ws2_stage_tile<4, false, true>(sD + s * stageD, pitchD, dn, rowO, 0, 0, nullptr, nullptr, lane);
+      } else {
+        if (o8n == 8) ws2_stage_tile<8, false, false>(sD + s * stageD, pitchD, dn, nullptr, tile0, nvalid, nullptr, nullptr, lane);
+        else ws2_stage_tile<4, false, false>(sD + s * stageD, pitchD, dn, nullptr, tile0, nvalid, nullptr, nullptr, lane);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&a_full[warp]);                        // warp == it & 3
+    }
+  } else if (warp == WS_LOAD + WS_EPI) {
+    // ===================================================================== MMA issuer (one thread)
+    if (lane == 0) {
+      const uint32_t idescH = umma_idesc_bf16(128, a.H, 0, 0), idescD = umma_idesc_bf16(128, a.C, 0, 0);
+      const uint32_t idescW3 = umma_idesc_bf16(128, a.Co, 1, 1), idescW2 = umma_idesc_bf16(128, a.H, 1, 1);
+      const uint64_t dW2 = umma_desc(smem_u32(sW2), 128, c8n * 128), dW3 = umma_desc(smem_u32(sW3t), 128, o8n * 128);
+      const uint64_t dW2t = umma_desc(smem_u32(sW2t), 128, h8n * 128);
+      auto second_half = [&](int64_t j) {     // G3 + weight-gradient GEMMs of local tile j
+        const int bj = (int)(j % NB), sj = (int)(j % NST), qj = (int)(j & 1);
+        mbar_wait(&e1_done[qj], (uint32_t)((j >> 1) & 1));
+        const int64_t jj = j - NB;                      // the tile whose dYhat sat in accD[bj] before
+        if (jj >= 0) mbar_wait(&d_empty[jj & 1], (uint32_t)((jj >> 1) & 1));
+        tc_fence_after();
+        const uint64_t dDhK = umma_desc(smem_u32(sDh + bj * stageH), 128, pitchH);
+        for (int k = 0; k < a.H / 16; ++k)
+          umma_bf16(tmem_base + colD + bj * a.C, dDhK + (uint64_t)(k * 16), dW2t + (uint64_t)(k * 16), idescD, k > 0 ? 1u : 0u);
+        tc_commit(&d_full[qj]);
+        const uint64_t aH = umma_desc(smem_u32(sH + bj * stageH), pitchH, 128), bD = umma_desc(smem_u32(sD + sj * stageD), pitchD, 128);
+        const uint64_t aA = umma_desc(smem_u32(sA + sj * stageA), pitchA, 128), bDh = umma_desc(smem_u32(sDh + bj * stageH), pitchH, 128);
+        for (int k = 0; k < 8; ++k)
+          umma_bf16(tmem_base + colW3, aH + (uint64_t)(k * 2 * (pitchH >> 4)), bD + (uint64_t)(k * 2 * (pitchD >> 4)), idescW3,
+                    (j > 0 || k > 0) ? 1u : 0u);
+        for (int k = 0; k < 8; ++k)
+          umma_bf16(tmem_base + colW2, aA + (uint64_t)(k * 2 * (pitchA >> 4)), bDh + (uint64_t)(k * 2 * (pitchH >> 4)), idescW2,
+                    (j > 0 || k > 0) ? 1u : 0u);
+        tc_commit(&a_empty[j & 3]);
+        tc_commit(&h_free[qj]);
+      };
+      int64_t it = 0;
+      for (int64_t g = blockIdx.x; g < fa.ntiles; g += gridDim.x, ++it) {
+        const int s = (int)(it % NST), b = (int)(it % NB);
+        mbar_wait(&a_full[it & 3], (uint32_t)((it >> 2) & 1));
+        // one accumulator buffer: E1 of the previous tile must have drained acc1 / accG before they are overwritten,
+        // so its second half (which waits for exactly that) is issued first; with two buffers it trails by one tile
+        if (NB == 1 && it >= 1) second_half(it - 1);
+        tc_fence_after();
+        const uint64_t dA = umma_desc(smem_u32(sA + s * stageA), 128, pitchA), dD = umma_desc(smem_u32(sD + s * stageD), 128, pitchD);
+        for (int k = 0; k < a.C / 16; ++k)
+          umma_bf16(tmem_base + b * a.H, dA + (uint64_t)(k * 16), dW2 + (uint64_t)(k * 16), idescH, k > 0 ? 1u : 0u);
+        for (int k = 0; k < a.Co / 16; ++k)
+          umma_bf16(tmem_base + colG + b * a.H, dD + (uint64_t)(k * 16), dW3 + (uint64_t)(k * 16), idescH, k > 0 ? 1u : 0u);
+        tc_commit(&hp_full[it & 1]);
+        if (NB == 2 && it >= 1) second_half(it - 1);
+      }
+      if (it >= 1) second_half(it - 1);
+      tc_commit(w_done);
+    }
+  } else {
+    // ===================================================================== epilogue groups (tiles it == eg mod 2)
+    const int eg = (warp - WS_LOAD) >> 2;
+    const int wq = warp & 3, row = wq * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
+    float db3acc = 0.f;        // row < Co: running sum_v dOut[v, row] over this group's tiles
+    int64_t it = eg;
+    for (int64_t g = blockIdx.x + (int64_t)eg * gridDim.x; g < fa.ntiles; g += 2ll * gridDim.x, it += 2) {
+      const int b = (int)(it % NB), s = (int)(it % NST);
+      const uint32_t par = (uint32_t)((it >> 1) & 1);      // (it & 1) == eg: this group sees every completion of its barriers
+      const int n = (int)(g / fa.tps);
+      const int tile0 = (int)((g - (int64_t)n * fa.tps) * 128);
+      const int prow = tile0 + row;
+      const bool row_ok = prow < (int)a.Vy;
+      mbar_wait(&a_full[it & 3], (uint32_t)((it >> 2) & 1)); // this group reads sD[s] itself (conv3 bias gradient)
+      if (row < a.Co) {
+        const uint8_t* col = sD + s * stageD + (row >> 3) * 128 + (row & 7) * 2;
+        float sacc = 0.f;
+#pragma unroll 8
+        for (int r = 0; r < 128; ++r)
+          sacc += __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(col + (r >> 3) * pitchD + (r & 7) * 16)) << 16);
+        db3acc += sacc;
+      }
+      mbar_wait(&hp_full[eg], par);
+      {
+        const int64_t pj = it - NB;                       // the tile whose Hact / dh sat in sH[b] / sDh[b] before
+        if (pj >= 0) mbar_wait(&h_free[pj & 1], (uint32_t)((pj >> 1) & 1));
+      }
+      tc_fence_after();
+      // ---- E1: Hact -> sH[b], dh -> sDh[b]
+      {
+        const uint32_t t1 = tmem_base + b * a.H + lane_off, tg = tmem_base + colG + b * a.H + lane_off;
+        uint8_t* dH = sH + b * stageH + (row >> 3) * pitchH + (row & 7) * 16;
+        uint8_t* dDh = sDh + b * stageH + (row >> 3) * pitchH + (row & 7) * 16;
+#pragma unroll 1
+        for (int c16 = 0; c16 < a.H / 16; ++c16) {
+          uint32_t v1[16], vg[16];
+          tmem_ld16(t1 + c16 * 16, v1);
+          tmem_ld16(tg + c16 * 16, vg);
+          tmem_ld_wait();
+          uint32_t hw[8], dw[8];
+          const float4* bp = reinterpret_cast<const float4*>(sB2 + c16 * 16);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 bb = bp[j4];
+            uint64_t va, ga, vb, gb;
+            gelu_fast_vg2(add2(pk2(__uint_as_float(v1[4 * j4]), __uint_as_float(v1[4 * j4 + 1])), pk2(bb.x, bb.y)), va, ga);
+            gelu_fast_vg2(add2(pk2(__uint_as_float(v1[4 * j4 + 2]), __uint_as_float(v1[4 * j4 + 3])), pk2(bb.z, bb.w)), vb, gb);
+            ga = mul2(ga, pk2(__uint_as_float(vg[4 * j4]), __uint_as_float(vg[4 * j4 + 1])));
+            gb = mul2(gb, pk2(__uint_as_float(vg[4 * j4 + 2]), __uint_as_float(vg[4 * j4 + 3])));
+            float e0, e1;
+            upk2(va, e0, e1); hw[2 * j4] = pack_bf16(e0, e1);
+            upk2(vb, e0, e1); hw[2 * j4 + 1] = pack_bf16(e0, e1);
+            upk2(ga, e0, e1); dw[2 * j4] = pack_bf16(e0, e1);
+            upk2(gb, e0, e1); dw[2 * j4 + 1] = pack_bf16(e0, e1);
+          }
+          *reinterpret_cast<uint4*>(dH + (c16 * 2) * 128) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          *reinterpret_cast<uint4*>(dH + (c16 * 2 + 1) * 128) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+          *reinterpret_cast<uint4*>(dDh + (c16 * 2) * 128) = make_uint4(dw[0], dw[1], dw[2], dw[3]);
+          *reinterpret_cast<uint4*>(dDh + (c16 * 2 + 1) * 128) = make_uint4(dw[4], dw[5], dw[6], dw[7]);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(&e1_done[eg]);
+      // ---- E2: g = dYhat -> bf16 -> HBM ; S1 += g ; S2 += g * xhat
+      const int64_t yrow = ((int64_t)n * a.Vy + prow) * c8n;
+      mbar_wait(&d_full[eg], par);
+      tc_fence_after();
+      {
+        const uint32_t td = tmem_base + colD + b * a.C + lane_off;
+        const float* rs = sRstd + n * a.C; const float* mr = sMR + n * a.C;
+        double* sGn = sG + n * 2 * a.C;
+#pragma unroll 1
+        for (int c16 = 0; c16 < C8N / 2; ++c16) {
+          uint32_t v[16];
+          tmem_ld16(td + c16 * 16, v);
+          uint4 y0 = make_uint4(0, 0, 0, 0), y1 = make_uint4(0, 0, 0, 0);
+          if (row_ok) { y0 = __ldg(a.y + yrow + c16 * 2); y1 = __ldg(a.y + yrow + c16 * 2 + 1); }   // L2-resident
+          tmem_ld_wait();
+          float gq[16], gx[16];
+          if (row_ok) {
+            float yv[16];
+            unpack8(y0, yv);
+            unpack8(y1, yv + 8);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              gq[j] = round_bf16(__uint_as_float(v[j]));
+              gx[j] = gq[j] * fmaf(yv[j], rs[c16 * 16 + j], -mr[c16 * 16 + j]);
+            }
+            a.dyhat[yrow + c16 * 2] = pack8(gq);
+            a.dyhat[yrow + c16 * 2 + 1] = pack8(gq + 8);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { gq[j] = 0.f; gx[j] = 0.f; }
+          }
+          warp_colsum16(gq, lane);
+          warp_colsum16(gx, lane);
+          if (!(lane & 1)) {
+            const int col = c16 * 16 + colsum16_col(lane);
+            atomicAdd(&sGn[col], (double)gq[0]);
+            atomicAdd(&sGn[a.C + col], (double)gx[0]);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&d_empty[eg]);
+    }
+    if (row < a.Co) sDb3[eg * a.Co + row] = db3acc;
+  }
+  tc_fence_before();
+  __syncthreads();
+  // ---- weight-gradient partials of this CTA (every CTA owns >= 1 tile: the grid never exceeds the tile count)
+  if (warp >= WS_LOAD && warp < WS_LOAD + 4) {
+    mbar_wait(w_done, 0);
+    tc_fence_after();
+    const int wq = warp & 3, row = wq * 32 + lane;
+    const uint32_t lo = (uint32_t)(wq * 32) << 16;
+    float* p3 = fa.part3 + ((int64_t)blockIdx.x * 129 + row) * a.Co;
+    if (row < a.Co) fa.part3[((int64_t)blockIdx.x * 129 + 128) * a.Co + row] = sDb3[row] + sDb3[a.Co + row];
+    for (int c16 = 0; c16 < a.Co / 16; ++c16) {
+      uint32_t v[16];
+      tmem_ld16(tmem_base + colW3 + lo + c16 * 16, v);
+      tmem_ld_wait();
+      if (row < a.H) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) p3[c16 * 16 + j] = __uint_as_float(v[j]);
+      }
+    }
+    float* p2 = fa.part2 + ((int64_t)blockIdx.x * 128 + row) * a.H;
+    for (int c16 = 0; c16 < a.H / 16; ++c16) {
+      uint32_t v[16];
+      tmem_ld16(tmem_base + colW2 + lo + c16 * 16, v);
+      tmem_ld_wait();
+      if (row <= a.C) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) p2[c16 * 16 + j] = __uint_as_float(v[j]);
+      }
+    }
+  }
+  for (int i = tid; i < fa.N * 2 * a.C; i += WS_THREADS) {
+    const double v = sG[i];
+    if (v != 0.0) atomicAdd(&a.gstats[i], v);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == WS_LOAD + WS_EPI) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+static size_t mlp_bwd_ws2_smem(int C, int H, int Co, int N, int NB) {
+  const int NST = NB == 2 ? 4 : 2;
+  return (size_t)H * C * 2 + (size_t)H * Co * 2 + (size_t)C * H * 2 + (size_t)NST * 16 * (C / 8 + 1) * 128 +
+         (size_t)NST * 16 * (Co / 8) * 128 + (size_t)2 * NB * 16 * (H / 8) * 128 + 2048 + (size_t)4 * N * C * 4 + (size_t)H * 4 +
+         (size_t)2 * Co * 4 + (size_t)WS_LOAD * 128 * 4 + (size_t)N * 2 * C * 8 + 19 * 8 + 16 + 128;
+}
+
+static void ws2_magic(uint32_t d, uint32_t& m, int& sh) {
+  int l = 0;
+  while ((1ull << l) < d) ++l;
+  const unsigned __int128 p = (unsigned __int128)1 << (31 + l);
+  m = (uint32_t)((p + d - 1) / d);
+  sh = 31 + l;
 }
 
 static size_t mlp_bwd_ws_smem(int C, int H, int Co, int N) {
@@ -1892,6 +2284,38 @@ extern "C" int pcb_mlp_bwd_fused(const void* y, const double* stats, const float
     configured = true;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  // opt-in generalised warp-specialised variant (PCB_BWD_WS=2): C in {32, 64}, Co in {32, 64}, every mode
+  {
+    const char* ws_env = getenv("PCB_BWD_WS");
+    if (ws_env && ws_env[0] == '2' && (C == 32 || C == 64) && (Co == 32 || Co == 64) && H % 16 == 0 && H <= 128 && N <= 8) {
+      const int NB = (2 * (2 * H + C) + Co + H <= 512) ? 2 : 1;
+      const size_t smem_ws = mlp_bwd_ws2_smem((int)C, (int)H, (int)Co, (int)N, NB);
+      if ((int64_t)NB * (2 * H + C) + Co + H <= 512 && smem_ws <= 227 * 1024) {
+        auto conf = [&](const void* fn) {
+          cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+          if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) { cudaGetLastError(); return false; }
+          return true;
+        };
+        const int Pw = (int)(fa.ntiles < 148 ? fa.ntiles : 148);     // <= P: the caller's workspace is large enough
+        fa.part3 = workspace; fa.part2 = workspace + (int64_t)Pw * 129 * Co;
+        ws2_magic((uint32_t)a.y2, fa.dm2, fa.ds2);
+        ws2_magic((uint32_t)a.y1, fa.dm1, fa.ds1);
+        bool launched = false;
+        if (C == 32 && NB == 2 && conf((const void*)mlp_bwd_ws2_kernel<4, 2>)) { mlp_bwd_ws2_kernel<4, 2><<<Pw, WS_THREADS, smem_ws, st>>>(fa); launched = true; }
+        else if (C == 32 && NB == 1 && conf((const void*)mlp_bwd_ws2_kernel<4, 1>)) { mlp_bwd_ws2_kernel<4, 1><<<Pw, WS_THREADS, smem_ws, st>>>(fa); launched = true; }
+        else if (C == 64 && NB == 1 && conf((const void*)mlp_bwd_ws2_kernel<8, 1>)) { mlp_bwd_ws2_kernel<8, 1><<<Pw, WS_THREADS, smem_ws, st>>>(fa); launched = true; }
+        if (launched) {
+          PCB_CHECK_LAUNCH("pcb_mlp_bwd_fused(ws2)");
+          reduce_partials_kernel<<<(unsigned)((H * Co + 31) / 32), 256, 0, st>>>(fa.part3, Pw, (int)H, 129, (int)Co, (int)Co, dW3, 1, H, nullptr);
+          reduce_partials_kernel<<<(unsigned)((Co + 31) / 32), 256, 0, st>>>(fa.part3 + 128 * Co, Pw, 1, 129, (int)Co, (int)Co, db3, 0, 1, nullptr);
+          reduce_partials_kernel<<<(unsigned)((C * H + 31) / 32), 256, 0, st>>>(fa.part2, Pw, (int)C, 128, (int)H, (int)H, dW2, 1, C, nullptr);
+          reduce_partials_kernel<<<(unsigned)((H + 31) / 32), 256, 0, st>>>(fa.part2 + C * H, Pw, 1, 128, (int)H, (int)H, db2, 0, 1, nullptr);
+          PCB_CHECK_LAUNCH("pcb_mlp_bwd_fused(ws2 reduce)");
+          return PCB_OK;
+        }
+      }
+    }
+  }
   // opt-in warp-specialised variant for the level-0 shape (see mlp_bwd_ws_kernel); same workspace layout, P = grid size
   {
     const char* ws_env = getenv("PCB_BWD_WS");

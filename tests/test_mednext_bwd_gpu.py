@@ -322,3 +322,16 @@ def test_block_backward_warp_specialised(size, monkeypatch):
     ragged last tiles, more tiles than one wave of loader stages (24*20*18 = 68 tiles per sample)."""
     monkeypatch.setenv("PCB_BWD_WS", "1")
     test_block_backward("same", 32, 32, 2, 3, size)
+
+
+@pytest.mark.skipif(os.environ.get("PCB_TEST_OPTIN") != "1", reason="opt-in kernels: set PCB_TEST_OPTIN=1")
+@pytest.mark.parametrize("kind,cin,cout,size", [
+    ("same", 32, 32, (16, 16, 16)), ("same", 32, 32, (9, 10, 11)),      # level 0: two accumulator buffers, 4 stages
+    ("same", 64, 64, (16, 16, 16)), ("same", 64, 64, (9, 10, 11)),      # level 1: one buffer, 2 stages
+    ("down", 32, 64, (16, 16, 16)),                                      # down_0: C=32 -> Co=64
+    ("up", 64, 32, (8, 8, 8)), ("up", 64, 32, (5, 6, 7)),               # up_0: dOut rows through the +1 table
+])
+def test_block_backward_warp_specialised_general(kind, cin, cout, size, monkeypatch):
+    """mlp_bwd_ws2_kernel (PCB_BWD_WS=2): every shape the fused backward serves, same parity bar."""
+    monkeypatch.setenv("PCB_BWD_WS", "2")
+    test_block_backward(kind, cin, cout, 2, 3, size)
