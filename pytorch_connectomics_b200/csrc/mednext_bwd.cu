@@ -2313,6 +2313,7 @@ extern "C" int pcb_mlp_bwd_fused(const void* y, const double* stats, const float
           PCB_CHECK_LAUNCH("pcb_mlp_bwd_fused(ws2 reduce)");
           return PCB_OK;
         }
+        fa.part3 = workspace; fa.part2 = workspace + (int64_t)P * 129 * Co;   // not launched: back to the default layout
       }
     }
   }
