@@ -335,3 +335,13 @@ def test_block_backward_warp_specialised_general(kind, cin, cout, size, monkeypa
     """mlp_bwd_ws2_kernel (PCB_BWD_WS=2): every shape the fused backward serves, same parity bar."""
     monkeypatch.setenv("PCB_BWD_WS", "2")
     test_block_backward(kind, cin, cout, 2, 3, size)
+
+
+@pytest.mark.skipif(os.environ.get("PCB_TEST_OPTIN") != "1", reason="opt-in: set PCB_TEST_OPTIN=1 (long CPU oracle run)")
+@pytest.mark.parametrize("ws", ["0", "1", "2"])
+def test_block_backward_many_tiles_per_cta(ws, monkeypatch):
+    """Persistent kernels with MANY tiles per CTA (stage reuse, accumulator double buffering, barrier phase flips): the
+    parametrised shapes above give every CTA a single tile.  2 x 64x64x48 voxels = 3 072 tiles over <= 296 CTAs.
+    ws = 0: default fused backward; 1 / 2: the opt-in warp-specialised kernels."""
+    monkeypatch.setenv("PCB_BWD_WS", ws)
+    test_block_backward("same", 32, 32, 2, 3, (64, 64, 48))
