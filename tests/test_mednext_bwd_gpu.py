@@ -345,3 +345,52 @@ def test_block_backward_many_tiles_per_cta(ws, monkeypatch):
     ws = 0: default fused backward; 1 / 2: the opt-in warp-specialised kernels."""
     monkeypatch.setenv("PCB_BWD_WS", ws)
     test_block_backward("same", 32, 32, 2, 3, (64, 64, 48))
+
+
+@pytest.mark.skipif(os.environ.get("PCB_TEST_OPTIN") != "1", reason="opt-in: set PCB_TEST_OPTIN=1 (long CPU oracle run)")
+def test_deep_block_backward_many_tiles_per_cta():
+    """gemm_ws_kernel backward modes (dual accumulators, stats epilogue, resident weights) with several tiles per CTA:
+    2 x 32x32x24 voxels at C=128 -> 384 row tiles x 2 column tiles over 148 CTAs."""
+    test_block_backward("same", 128, 128, 2, 3, (32, 32, 24))
+
+
+@pytest.mark.skipif(os.environ.get("PCB_TEST_OPTIN") != "1", reason="opt-in: set PCB_TEST_OPTIN=1 (long CPU oracle run)")
+@pytest.mark.parametrize("ws", ["0", "2"])
+def test_mednext_s_training_step_64_matches_oracle(ws, monkeypatch):
+    """Whole MedNeXt-S (the bench model) forward + BCE + backward on 2 x 64^3 against the oracle: every persistent
+    kernel sees many tiles per CTA at the real channel counts (level 0: 2 x 2048 tiles).  Same acceptance rule as the tiny
+    network: all-parameter gradient error <= 1.5 x the reference's own bf16-autocast error + slack."""
+    monkeypatch.setenv("PCB_BWD_WS", ws)
+    torch.manual_seed(0)
+    o = OM.create_mednext_v1(1, 1, "S", 3, False)
+    p = PM.create_mednext_v1(1, 1, "S", 3, False)
+    p.load_state_dict(o.state_dict(), strict=True)
+    p.to(DEV)
+    torch.manual_seed(1)
+    x = torch.rand(2, 1, 64, 64, 64)
+    tgt = (torch.rand(2, 1, 64, 64, 64) > 0.85).float()
+    bce = torch.nn.functional.binary_cross_entropy_with_logits
+    l32 = bce(o(x).float(), tgt)
+    l32.backward()
+    g32 = {k: q.grad.clone() for k, q in o.named_parameters() if q.grad is not None}
+    o.zero_grad()
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        out = o(x)
+    lbf = bce(out.float(), tgt)
+    lbf.backward()
+    gbf = {k: q.grad.clone() for k, q in o.named_parameters() if q.grad is not None}
+    lg = bce(p(x.to(DEV)).float(), tgt.to(DEV))
+    lg.backward()
+    torch.cuda.synchronize()
+    print(f"loss fp32 {l32.item():.6f}  bf16-path {lbf.item():.6f}  engine {lg.item():.6f}")
+    assert abs(lg.item() - l32.item()) <= 1.5 * abs(lbf.item() - l32.item()) + 2e-3
+    gg = {k: q.grad for k, q in p.named_parameters() if q.grad is not None}
+    assert set(gg) == set(g32)
+    num = den = numb = 0.0
+    for k in g32:
+        num += float((gg[k].cpu() - g32[k]).norm() ** 2)
+        numb += float((gbf[k] - g32[k]).norm() ** 2)
+        den += float(g32[k].norm() ** 2)
+    e, eb = (num / den) ** 0.5, (numb / den) ** 0.5
+    print(f"all-parameter gradient rel-L2: engine {e:.3e}  reference-bf16-path {eb:.3e}")
+    assert e <= 1.5 * eb + 5e-3
