@@ -1098,6 +1098,7 @@ struct MlpFusedArgs {
   int64_t tps;       // tiles per sample
   int64_t ntiles;    // N * tps
   int fast;          // warp-per-tile register loader (C, Cr in {32, 64}; nst == 4)
+  int ld16;          // opt-in (PCB_FWD_LD16=1): 16 instead of 8 loads in flight per loader lane
   uint32_t dm2, dm1; // magic multipliers of the exact division by o2 / o1 (n < 2^31):  n / d == (n * dm) >> ds
   int ds2, ds1;
 };
@@ -1153,13 +1154,17 @@ __device__ __forceinline__ void mf_row_sources_fast(const MlpFusedArgs& fa, int 
 // (conflict-free) and every global request covers whole 32-byte sectors.  The lane's channels are fixed, so the
 // GroupNorm affine (NORM) stays in registers for the tile.  TAB: row sources come from `tab` (-1 = zero row),
 // otherwise rows row0 .. row0+nvalid-1 are read in order.  8 loads are in flight per lane before the first store.
-template <int C8N, bool NORM, bool TAB>
+// LD = loads in flight per lane before the first store.  With 4 loader warps x 32 lanes x 8 x 16 B = 16 KB in flight per SM
+// the level-0 kernel sits exactly at the latency-bandwidth product it was measured at (2.4 TB/s ~ 148 SMs x 16 KB / 1 us);
+// LD = 16 doubles the bytes in flight (opt-in until measured).
+template <int C8N, bool NORM, bool TAB, int LD = 8>
 __device__ __forceinline__ void mf_stage_tile(uint8_t* __restrict__ dst, const uint4* __restrict__ src,
                                               const int* __restrict__ tab, int row0, int nvalid,
                                               const float* __restrict__ sc, const float* __restrict__ sh, int lane) {
   static_assert(C8N == 4 || C8N == 8, "C8N");
+  static_assert(LD == 8 || LD == 16, "LD");
   constexpr int J = C8N / 4;      // chunks per lane per row group
-  constexpr int RGB = 8 / J;      // row groups per batch of 8 loads
+  constexpr int RGB = LD / J;     // row groups per batch of LD loads
   const int rl = lane & 7, cs = lane >> 3;
   uint64_t ps[J][4], pt[J][4];
   if (NORM) {
@@ -1175,10 +1180,10 @@ __device__ __forceinline__ void mf_stage_tile(uint8_t* __restrict__ dst, const u
   uint8_t* dl = dst + cs * 128 + rl * 16;
 #pragma unroll 1
   for (int b = 0; b < 16 / RGB; ++b) {
-    uint4 v[8];
+    uint4 v[LD];
     uint32_t ok = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < LD; ++k) {
       const int rg = b * RGB + k / J, j = k % J;
       const int r = rg * 8 + rl;
       int ry;
@@ -1187,7 +1192,7 @@ __device__ __forceinline__ void mf_stage_tile(uint8_t* __restrict__ dst, const u
       if (ry >= 0) { v[k] = __ldg(src + (int64_t)ry * C8N + (cs + 4 * j)); ok |= 1u << k; }
     }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < LD; ++k) {
       const int rg = b * RGB + k / J, j = k % J;
       uint4 o = v[k];
       if (NORM) {
@@ -1205,6 +1210,7 @@ __device__ __forceinline__ void mf_stage_tile(uint8_t* __restrict__ dst, const u
   }
 }
 
+template <bool LD16>   // LD16: opt-in loader depth (separate instantiation: the default kernel's code is unchanged)
 __global__ void __launch_bounds__(MF_THREADS, 1) mlp_fused_kernel(MlpFusedArgs fa) {
   const MlpArgs& a = fa.m;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -1321,9 +1327,11 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_fused_kernel(MlpFusedArgs f
         uint8_t* dA = sA + warp * 128 * a.C * 2;
         if (c8n == 8) {
           if (tabY) mf_stage_tile<8, true, true>(dA, yn, rowY, tile0, nvalid, sc, sh, lane);
+          else if (LD16) mf_stage_tile<8, true, false, 16>(dA, yn, rowY, tile0, nvalid, sc, sh, lane);
           else mf_stage_tile<8, true, false>(dA, yn, rowY, tile0, nvalid, sc, sh, lane);
         } else {
           if (tabY) mf_stage_tile<4, true, true>(dA, yn, rowY, tile0, nvalid, sc, sh, lane);
+          else if (LD16) mf_stage_tile<4, true, false, 16>(dA, yn, rowY, tile0, nvalid, sc, sh, lane);
           else mf_stage_tile<4, true, false>(dA, yn, rowY, tile0, nvalid, sc, sh, lane);
         }
         if (has_rc) {
@@ -1782,8 +1790,10 @@ extern "C" int pcb_mlp_fwd(const void* y, const double* stats, const float* gamm
         N <= 8 && fsm <= 227 * 1024 && pow2 && a.Vout < (1ll << 30) && a.Vin < (1ll << 30)) {
       static bool fconf = false;
       if (!fconf) {
-        cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if (cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+        cudaFuncSetAttribute(mlp_fused_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(mlp_fused_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (cudaFuncSetAttribute(mlp_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(mlp_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
           set_error("pcb_mlp_fwd: cudaFuncSetAttribute(fused) failed"); return PCB_ERR_CUDA;
         }
         fconf = true;
@@ -1791,11 +1801,13 @@ extern "C" int pcb_mlp_fwd(const void* y, const double* stats, const float* gamm
       MlpFusedArgs fa;
       fa.m = a; fa.N = (int)N; fa.nst = nst; fa.nsx = nsx; fa.tps = (a.Vout + 127) / 128; fa.ntiles = fa.tps * N;
       fa.fast = nst == 4 && (C == 32 || C == 64) && (!wr || Cr == 32 || Cr == 64) && getenv("PCB_OLD_LOADER") == nullptr;
+      { const char* e16 = getenv("PCB_FWD_LD16"); fa.ld16 = (e16 && e16[0] == '1') ? 1 : 0; }
       mf_magic((uint32_t)(a.o2 > 0 ? a.o2 : 1), fa.dm2, fa.ds2);
       mf_magic((uint32_t)(a.o1 > 0 ? a.o1 : 1), fa.dm1, fa.ds1);
       int ctas = 148;
       if (fa.ntiles < ctas) ctas = (int)fa.ntiles;
-      mlp_fused_kernel<<<ctas, MF_THREADS, fsm, (cudaStream_t)stream>>>(fa);
+      if (fa.ld16 && fa.fast) mlp_fused_kernel<true><<<ctas, MF_THREADS, fsm, (cudaStream_t)stream>>>(fa);
+      else mlp_fused_kernel<false><<<ctas, MF_THREADS, fsm, (cudaStream_t)stream>>>(fa);
       PCB_CHECK_LAUNCH("pcb_mlp_fwd(fused)");
       return PCB_OK;
     }

@@ -7,6 +7,8 @@ reference under `precision: bf16-mixed` — and bf16 storage alone rounds every 
 fp32 oracle, and the same error for the oracle run under torch.autocast(bfloat16) (= the reference's
 own bf16 path); the engine must not be further from fp32 than 1.5x the reference's bf16 path
 (+1e-3 absolute slack)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -245,3 +247,14 @@ def test_full_size_config2_forward_parity():
     j_ref = binary_jaccard(mask(want_bf), mask(want), 0.5)
     print(f"Jaccard vs fp32-oracle mask at 160^3: engine {j:.5f}   reference-bf16-path {j_ref:.5f}")
     assert j >= j_ref - 0.01
+
+
+@pytest.mark.skipif(os.environ.get("PCB_TEST_OPTIN") != "1", reason="opt-in kernels: set PCB_TEST_OPTIN=1")
+def test_forward_loader_depth_16(monkeypatch):
+    """mlp_fused_kernel<LD16> (PCB_FWD_LD16=1: 16 loads in flight per loader lane): block parity at C=32 / C=64 and the
+    full-size MedNeXt-S forward (many tiles per CTA)."""
+    monkeypatch.setenv("PCB_FWD_LD16", "1")
+    test_block_forward("same", 32, 32, 2, 3, (16, 16, 16))
+    test_block_forward("same", 64, 64, 3, 5, (8, 8, 8))
+    test_block_forward("down", 32, 64, 2, 3, (16, 16, 16))
+    test_full_size_config2_forward_parity()
