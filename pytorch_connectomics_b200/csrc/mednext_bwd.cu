@@ -286,6 +286,7 @@ struct MlpBwdFusedArgs {
   int N;
   int64_t tps, ntiles;
   uint32_t dm2, dm1; int ds2, ds1;   // exact division by y2 / y1 (mlp_bwd_ws2_kernel, UP-mode dOut row map)
+  int ld16;                          // mlp_bwd_ws2_kernel: 16 loads in flight per loader lane (PCB_BWD_LD16=1)
 };
 
 constexpr int BF_PF = 8;          // prefetch depth: (C/8 + Co/8) * 128 / 256 <= 8 chunks per thread
@@ -927,13 +928,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_bwd_ws_kernel(MlpBwdFusedAr
 //   (the MMA thread issues them as soon as E1 of tile i has drained the accumulators).
 //   Operand stages: 4 (NB = 2) or 2 (NB = 1; shared memory), one loader warp per tile either way.
 //   UP mode: dOut rows through a per-tile table (p -> p + 1 on every axis, divisions by multiplication).
-template <int C8N, bool NORM, bool TAB>
+template <int C8N, bool NORM, bool TAB, int LD = 8>
 __device__ __forceinline__ void ws2_stage_tile(uint8_t* __restrict__ dst, uint32_t pitch, const uint4* __restrict__ src,
                                                const int* __restrict__ tab, int row0, int nvalid, const float* __restrict__ sc,
                                                const float* __restrict__ sh, int lane) {
   static_assert(C8N == 4 || C8N == 8, "C8N");
   constexpr int J = C8N / 4;      // chunks per lane per row group
-  constexpr int RGB = 8 / J;      // row groups per batch of 8 loads
+  constexpr int RGB = LD / J;     // row groups per batch of LD loads
   const int rl = lane & 7, cs = lane >> 3;
   uint64_t ps[J][4], pt[J][4];
   if (NORM) {
@@ -949,10 +950,10 @@ __device__ __forceinline__ void ws2_stage_tile(uint8_t* __restrict__ dst, uint32
   uint8_t* dl = dst + cs * 128 + rl * 16;
 #pragma unroll 1
   for (int b = 0; b < 16 / RGB; ++b) {
-    uint4 v[8];
+    uint4 v[LD];
     uint32_t ok = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < LD; ++k) {
       const int rg = b * RGB + k / J, j = k % J;
       const int r = rg * 8 + rl;
       int ry;
@@ -961,7 +962,7 @@ __device__ __forceinline__ void ws2_stage_tile(uint8_t* __restrict__ dst, uint32
       if (ry >= 0) { v[k] = __ldg(src + (int64_t)ry * C8N + (cs + 4 * j)); ok |= 1u << k; }
     }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < LD; ++k) {
       const int rg = b * RGB + k / J, j = k % J;
       uint4 o = v[k];
       if (NORM) {
@@ -1074,8 +1075,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_bwd_ws2_kernel(MlpBwdFusedA
       const int n = (int)(g / fa.tps);
       const int tile0 = (int)((g - (int64_t)n * fa.tps) * 128);
       const int nvalid = min(128, (int)a.Vy - tile0);
-      ws2_stage_tile<C8N, true, false>(sA + s * stageA, pitchA, a.y + (int64_t)n * a.Vy * c8n, nullptr, tile0, nvalid,
-                                       sScale + n * a.C, sShift + n * a.C, lane);
+      if (fa.ld16)
+        ws2_stage_tile<C8N, true, false, 16>(sA + s * stageA, pitchA, a.y + (int64_t)n * a.Vy * c8n, nullptr, tile0, nvalid,
+                                             sScale + n * a.C, sShift + n * a.C, lane);
+      else
+        ws2_stage_tile<C8N, true, false>(sA + s * stageA, pitchA, a.y + (int64_t)n * a.Vy * c8n, nullptr, tile0, nvalid,
+                                         sScale + n * a.C, sShift + n * a.C, lane);
       const uint4* dn = a.dout + (int64_t)n * a.Vout * o8n;
       if (up) {
         __syncwarp();
@@ -2256,6 +2261,7 @@ extern "C" int pcb_mlp_bwd_fused(const void* y, const double* stats, const float
   PCB_CHECK_ARG(y && stats && gamma && beta && w2 && b2 && w3t && w2t && dout && dyhat && gstats && workspace && dW3 && db3 &&
                 dW2 && db2 && y_size, "pcb_mlp_bwd_fused: null argument");
   MlpBwdFusedArgs fa;
+  memset(&fa, 0, sizeof(fa));
   MlpBwdArgs& a = fa.m;
   a.y = (const uint4*)y; a.stats = stats; a.gamma = gamma; a.beta = beta; a.w2 = (const uint4*)w2; a.b2 = b2;
   a.w3t = (const uint4*)w3t; a.w2t = (const uint4*)w2t; a.dout = (const uint4*)dout; a.hact = nullptr; a.dh = nullptr;
@@ -2300,6 +2306,7 @@ extern "C" int pcb_mlp_bwd_fused(const void* y, const double* stats, const float
         fa.part3 = workspace; fa.part2 = workspace + (int64_t)Pw * 129 * Co;
         ws2_magic((uint32_t)a.y2, fa.dm2, fa.ds2);
         ws2_magic((uint32_t)a.y1, fa.dm1, fa.ds1);
+        { const char* e16 = getenv("PCB_BWD_LD16"); fa.ld16 = (e16 && e16[0] == '1') ? 1 : 0; }
         bool launched = false;
         if (C == 32 && NB == 2 && conf((const void*)mlp_bwd_ws2_kernel<4, 2>)) { mlp_bwd_ws2_kernel<4, 2><<<Pw, WS_THREADS, smem_ws, st>>>(fa); launched = true; }
         else if (C == 32 && NB == 1 && conf((const void*)mlp_bwd_ws2_kernel<4, 1>)) { mlp_bwd_ws2_kernel<4, 1><<<Pw, WS_THREADS, smem_ws, st>>>(fa); launched = true; }
