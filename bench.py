@@ -244,6 +244,19 @@ def build_roofline(prof, a, peak_gbs, measured, step_ms, nsteps):
     roof["others"] = rows[1:]
     return roof
 
+def step_roofline(mode: str, units_per_step: float, ms_per_step: float, hbm_gbs: float, bf16_tflops: float):
+    """Whole-step roofline (BASELINE.md §2 / SURVEY §8d): MedNeXt-S k3 at 160^3 needs 522 GFLOP and, with fused blocks,
+    5.49 GB of HBM traffic per forward; a training step is 3x that.  Time per unit = max(bytes / HBM, FLOPs / tensor peak)
+    with the MEASURED peaks; `frac` = roofline time / achieved time of the whole step (not of one kernel)."""
+    passes = 3.0 if mode == "train" else 1.0
+    t_unit = max(passes * 5.49e9 / (hbm_gbs * 1e9), passes * 522e9 / (bf16_tflops * 1e12))      # s per 160^3 sub-volume / tile
+    roof_ms = units_per_step * t_unit * 1e3
+    return {"unit": "160^3 sub-volume (train: fwd+bwd = 3 x fwd)" if mode == "train" else "160^3 tile forward",
+            "bytes_per_unit": passes * 5.49e9, "flops_per_unit": passes * 522e9, "units_per_step": units_per_step,
+            "roofline_ms_per_step": roof_ms, "frac": roof_ms / ms_per_step if ms_per_step > 0 else None,
+            "bound": "hbm" if passes * 5.49e9 / (hbm_gbs * 1e9) >= passes * 522e9 / (bf16_tflops * 1e12) else "tensor"}
+
+
 # ----------------------------------------------------------------------------- our arm
 T0 = time.time()
 
@@ -496,6 +509,15 @@ def main():
            "clocks": clocks.window(w0, w1) if clocks else None}
     if clocks:
         clocks.stop()
+    try:        # whole-step roofline beside the dominant-kernel one (never allowed to cost the JSON line)
+        tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1366.0)))
+        if a.mode == "train":
+            out["step_roofline"] = step_roofline("train", a.batch, ms / a.steps, peak_gbs, tf)      # per GPU
+        elif world == 1:
+            ntile = (max(a.volume, SIDE) - SIDE + SIDE // 2 - 1) // (SIDE // 2) + 1
+            out["step_roofline"] = step_roofline("infer", ntile ** 3, ms / a.steps, peak_gbs, tf)
+    except Exception as exc:
+        out["step_roofline"] = {"error": repr(exc)}
     if world == 1 and not a.no_cpu_baseline:
         r = cpu_train_rate(1, 0) if a.mode == "train" else cpu_infer_rate(1, 0)
         out["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}

@@ -65,3 +65,12 @@ def test_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["metric"] == bench.METRIC_TRAIN and d["unit"] == "sub-volumes/s"
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["value"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_step_roofline_arithmetic():
+    # 4 sub-volumes per step at the measured peaks of this pod: 3 x 5.49 GB / 6554.9 GB/s = 2.51 ms each (HBM-bound)
+    r = bench.step_roofline("train", 4, 91.4, 6554.9, 1366.2)
+    assert r["bound"] == "hbm" and abs(r["roofline_ms_per_step"] - 4 * 3 * 5.49e9 / 6554.9e9 * 1e3) < 1e-9
+    assert abs(r["frac"] - r["roofline_ms_per_step"] / 91.4) < 1e-12 and 0.10 < r["frac"] < 0.12
+    ri = bench.step_roofline("infer", 125, 750.0, 6554.9, 1366.2)       # 480^3 volume: 5^3 tiles
+    assert abs(ri["roofline_ms_per_step"] - 125 * 5.49e9 / 6554.9e9 * 1e3) < 1e-9
