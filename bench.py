@@ -1,16 +1,21 @@
 #!/usr/bin/env python
 """pcb200 benchmark — prints ONE JSON line (see DESIGN.md "Measurement").
 
-    python bench.py --gpus N --steps K --warmup W            # our arm (training step, config 2)
-    python bench.py --impl reference --steps K --warmup W    # reference CPU arm (oracle port)
-    python bench.py --mode infer ...                         # sliding-window inference workload
+    python bench.py --gpus N --steps K --warmup W               # our arm: C2 training step + C5-geometry inference record
+    python bench.py --config c2|c3|c4|c5 ...                    # one BASELINE.json config on its own
+    python bench.py --impl reference --steps K --warmup W       # reference CPU arm (oracle port, real 160^3 crops)
 
-Workload (BASELINE.json configs[1]): MedNeXt-S, 1-channel 160^3 crops, bf16 compute, per-GPU batch 4 (--batch),
-BCE-with-logits + Dice loss, AdamW(lr 1e-3, wd 0.01) — one "step" = forward + loss + backward + gradient
-all-reduce (N>1) + optimizer step on one synthetic batch per GPU.  `value` = sub-volumes/s over all
-ranks with inputs resident in HBM; `e2e` = the same step through the public API with the batch copied from
-pinned host memory every step and the loss read back.  Inputs are regenerated (different tensors) each step
-and each step touches >1 GB of activations, far beyond the 126 MB L2, so no explicit L2 flush is needed.
+BASELINE.json's metric has two halves — training sub-volumes/s and inference Mvoxels/s — so the default line carries
+both: the top-level `metric/value/roofline/e2e/cpu_baseline` are the TRAINING step of configs[1] (MedNeXt-S, 1-channel
+160^3 crops, bf16 compute, per-GPU batch 4, BCE+Dice, AdamW; timed over exactly K steps), and `infer` is a second record
+of the same shape (metric, value, unit, ms_per_step, steps, config, roofline, e2e, cpu_baseline) for sliding-window
+inference with configs[4]'s geometry (160^3 tiles, 50 % overlap, bump blending) on the largest cubic volume per GPU that
+keeps the whole run within a few minutes (--volume, default 640; N GPUs: ONE (N*volume) x volume x volume volume,
+z-slab sharded).  `--config c5` runs the full 2048^3 volume; `--config c3` / `c4` the 3-channel and MedNeXt-L training
+configs.  `value` = whole-job throughput with inputs resident in HBM; `e2e` = the same work through the public API with
+the inputs in pinned host memory and the result read back, copies inside the timed region.  Every step streams far more
+than the 126 MB L2 (activations > 1 GB), inputs rotate over a pool of distinct tensors: no explicit L2 flush (said in
+`config.l2`).
 """
 
 from __future__ import annotations
@@ -32,6 +37,19 @@ import torch  # noqa: E402
 SIDE = 160
 METRIC_TRAIN = "training sub-volumes/sec"
 METRIC_INFER = "inference Mvoxels/sec"
+
+# BASELINE.json configs[1..4] (configs[0] is the CPU plumbing case, a parity test — tests/test_monai_unet_gpu.py)
+TRAIN_CONFIGS = {
+    "c2": dict(size="S", out_channels=1, crop=160, batch=4,
+               name="MedNeXt-S k3 train step, {b}x1x160^3 crops per GPU, BCE+Dice, AdamW (BASELINE configs[1])"),
+    "c3": dict(size="S", out_channels=3, crop=160, batch=4,
+               name="MedNeXt-S k3 3-channel affinity train step, {b}x1x160^3 crops per GPU -> 3x160^3, BCE+Dice, AdamW, DDP "
+                    "(BASELINE configs[2])"),
+    "c4": dict(size="L", out_channels=1, crop=224, batch=1,
+               name="MedNeXt-L k3 train step, {b}x1x224^3 crops per GPU, BCE+Dice, AdamW, DDP (BASELINE configs[3])"),
+}
+# algorithmic work per forward of one crop/tile (fused blocks, bf16 activations)
+FWD_WORK = {("S", 160): (5.49e9, 522e9), ("L", 224): (23.6e9, 5416e9), ("L", 160): (8.6e9, 1974e9)}
 
 
 def cfg_mednext(size="S", out_channels=1):
@@ -92,20 +110,26 @@ class Clocks:
 
 
 # ----------------------------------------------------------------------------- reference / CPU arm
-def cpu_train_rate(steps: int, warmup: int, side: int = 64):
-    """The reference's own path on host cores: the oracle MedNeXt-S (pure-torch restatement of the
-    un-vendored nnunet_mednext modules the reference builds) — fp32 forward + loss + backward + AdamW
-    on a bounded sample (one `side`^3 crop per step), scaled to 160^3 sub-volumes by voxel count."""
+def _cpu_threads() -> int:
+    return min(os.cpu_count() or 1, 32)   # oneDNN stops scaling (and regresses) beyond ~32 threads at this size
+
+
+def cpu_train_rate(steps: int, warmup: int, cfg_key: str = "c2", side: int = 0):
+    """The reference's own path on host cores: the oracle MedNeXt (pure-torch restatement of the un-vendored
+    nnunet_mednext modules the reference builds) — fp32 forward + loss + backward + AdamW on ONE real crop of the
+    config's size per step (B=1; a bounded sample of the per-GPU batch, nothing is extrapolated)."""
     from oracle.mednext_oracle import create_mednext_v1
-    cores = min(os.cpu_count() or 1, 32)   # oneDNN stops scaling (and regresses) beyond ~32 threads at this size
+    spec = TRAIN_CONFIGS[cfg_key]
+    side = side or spec["crop"]
+    cores = _cpu_threads()
     torch.set_num_threads(cores)
     torch.manual_seed(0)
-    net = create_mednext_v1(1, 1, "S", 3, False)
+    net = create_mednext_v1(1, spec["out_channels"], spec["size"], 3, False)
     opt = torch.optim.AdamW(net.parameters(), lr=1e-3, weight_decay=0.01)
     ts = []
     for i in range(warmup + steps):
         x = torch.rand(1, 1, side, side, side)
-        t = (torch.rand(1, 1, side, side, side) > 0.85).float()
+        t = (torch.rand(1, spec["out_channels"], side, side, side) > 0.85).float()
         t0 = time.perf_counter()
         opt.zero_grad(set_to_none=True)
         loss = bce_dice_loss(net(x), t)
@@ -115,15 +139,18 @@ def cpu_train_rate(steps: int, warmup: int, side: int = 64):
         if i >= warmup:
             ts.append(dt)
     sec = sum(ts) / len(ts)
-    scale = (side / SIDE) ** 3
-    return {"value": scale / sec, "unit": "sub-volumes/s", "cores": cores, "kind": "port",
-            "sample": f"oracle MedNeXt-S fp32 train step on one {side}^3 crop per step ({sec:.2f} s/step), "
-                      f"scaled by ({side}/{SIDE})^3 to 160^3 sub-volumes", "sec_per_step": sec}
+    return {"value": 1.0 / sec, "unit": "sub-volumes/s", "cores": cores, "kind": "port",
+            "sample": f"oracle MedNeXt-{spec['size']} fp32 train step (forward + BCE/Dice + backward + AdamW) on one real "
+                      f"1x{side}^3 crop per step ({sec:.2f} s/step, {len(ts)} timed); no size extrapolation",
+            "sec_per_step": sec}
 
 
-def cpu_infer_rate(steps: int, warmup: int, side: int = 64):
+def cpu_infer_rate(steps: int, warmup: int, side: int = SIDE):
+    """Reference sliding-window inference cost per output voxel on host cores: one real 160^3 tile forward of the oracle
+    MedNeXt-S per step; Mvox/s = tile voxels / (forward time x tile coverage), coverage 8 at 50 % overlap (the blend
+    itself runs at ~20 Mvox-out/s on 8 cores, BASELINE.md §3, and is not the bound)."""
     from oracle.mednext_oracle import create_mednext_v1
-    cores = min(os.cpu_count() or 1, 32)
+    cores = _cpu_threads()
     torch.set_num_threads(cores)
     torch.manual_seed(0)
     net = create_mednext_v1(1, 1, "S", 3, False).eval()
@@ -136,48 +163,83 @@ def cpu_infer_rate(steps: int, warmup: int, side: int = 64):
             if i >= warmup:
                 ts.append(time.perf_counter() - t0)
     sec = sum(ts) / len(ts)
-    # 50 % overlap => every output voxel is covered by 8 tiles in the interior
     return {"value": side ** 3 / sec / 8.0 / 1e6, "unit": "Mvox/s", "cores": cores, "kind": "port",
-            "sample": f"oracle MedNeXt-S fp32 forward on one {side}^3 tile per step ({sec:.2f} s), /8 tile coverage",
+            "sample": f"oracle MedNeXt-S fp32 forward on one real {side}^3 tile per step ({sec:.2f} s, {len(ts)} timed), "
+                      "/8 tile coverage at 50 % overlap",
             "sec_per_step": sec}
 
 
 def run_reference(a):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """`--impl reference`: the reference's CPU path (oracle port — nnunet_mednext / monai are not installable offline) on
+    all host threads, same metric / unit / config as our arm; rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    steps, warm = max(1, min(a.steps, 3)), max(0, min(a.warmup, 1))
-    train = a.mode == "train"
-    r = cpu_train_rate(steps, warm) if train else cpu_infer_rate(steps, warm)
-    out = {"impl": "reference", "metric": METRIC_TRAIN if train else METRIC_INFER, "value": r["value"],
-           "unit": r["unit"], "n_gpus": a.gpus, "steps": steps, "warmup": warm, "ms_per_step": r["sec_per_step"] * 1e3,
-           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": workload_config(a, 1),
-           "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
-           "e2e": {"value": r["value"], "unit": r["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-           "note": "reference third-party nets (nnunet_mednext) are not installable offline; this is the oracle port "
-                   "of the reference's PyTorch CPU path on all host threads"}
+    steps, warm = max(1, min(a.steps, 2)), max(0, min(a.warmup, 1))
+    world = int(os.environ.get("WORLD_SIZE", str(a.gpus)))
+    note = ("reference third-party nets (nnunet_mednext) are not installable offline; this is the oracle port of the "
+            "reference's PyTorch CPU path on all host threads; every step is ONE real crop (B=1) of the config's size — a "
+            "bounded sample of the per-GPU batch, value = crops/s")
+
+    def line(metric, r, config):
+        return {"impl": "reference", "metric": metric, "value": r["value"], "unit": r["unit"], "n_gpus": a.gpus,
+                "steps": steps, "warmup": warm, "ms_per_step": r["sec_per_step"] * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": r["value"], "unit": r["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+    if a.config == "c5":
+        r = cpu_infer_rate(steps, warm)
+        out = line(METRIC_INFER, r, infer_config(a, world))
+    else:
+        key = a.config if a.config in TRAIN_CONFIGS else "c2"
+        r = cpu_train_rate(steps, warm, key)
+        out = line(METRIC_TRAIN, r, train_config(a, key, world))
+        if a.config == "default":
+            ri = cpu_infer_rate(1, 0)
+            out["infer"] = line(METRIC_INFER, ri, infer_config(a, world))
+            out["infer"]["steps"], out["infer"]["warmup"] = 1, 0
+    out["note"] = note
     print(json.dumps(out))
 
 
-def workload_config(a, world):
-    if a.mode == "train":
-        return {"workload": f"MedNeXt-S k3 train step, {a.batch}x1x{SIDE}^3 crops per GPU, BCE+Dice, AdamW (BASELINE configs[1])",
-                "global_batch": world * a.batch, "crop": [SIDE] * 3, "parallelism": f"dp{world}",
-                "l2": "inputs+activations >> 126 MB L2 per step (no explicit flush)"}
-    return {"workload": f"MedNeXt-S sliding-window inference, {a.volume * world}x{a.volume}x{a.volume} volume ({a.volume}^3 per GPU), {SIDE}^3 tiles, 50% overlap, bump",
-            "volume": [a.volume * world, a.volume, a.volume], "tile": [SIDE] * 3, "overlap": 0.5,
-            "parallelism": "single GPU" if world == 1 else f"one volume, z-slab shards x{world} + neighbour overlap exchange (NCCL send/recv)",
+def train_batch(a, key):
+    return a.batch if a.batch > 0 else TRAIN_CONFIGS[key]["batch"]
+
+
+def train_config(a, key, world):
+    spec = TRAIN_CONFIGS[key]
+    b = train_batch(a, key)
+    return {"workload": spec["name"].format(b=b), "baseline_config": key, "global_batch": world * b,
+            "crop": [spec["crop"]] * 3, "parallelism": f"dp{world}",
+            "l2": "inputs+activations >> 126 MB L2 per step (no explicit flush)"}
+
+
+def infer_volume(a, world):
+    if a.config == "c5":
+        v = a.volume or 2048
+        return [v, v, v]                       # ONE 2048^3 volume over all ranks (strong: the volume is fixed)
+    v = a.volume or 640
+    return [v * world, v, v]                   # weak: `volume`^3 per GPU
+
+
+def infer_config(a, world):
+    vol = infer_volume(a, world)
+    tag = "BASELINE configs[4]" if a.config == "c5" else "BASELINE configs[4] geometry"
+    return {"workload": f"MedNeXt-S sliding-window inference, {vol[0]}x{vol[1]}x{vol[2]} fp16 volume, {SIDE}^3 tiles, "
+                        f"50% overlap, bump blending, sw_batch {a.sw_batch} ({tag})",
+            "baseline_config": "c5", "volume": vol, "tile": [SIDE] * 3, "overlap": 0.5, "sw_batch": a.sw_batch,
+            "parallelism": "single GPU" if world == 1 else
+            f"one volume, z-slab shards x{world} + neighbour overlap exchange (NCCL send/recv)",
             "l2": "volume+accumulators >> 126 MB L2 (no explicit flush)"}
 
 
-
 # ----------------------------------------------------------------------------- roofline leg
-# op-name prefix (pytorch_connectomics_b200 profiler hooks) -> kernel symbol, algorithmic bytes per voxel-channel
+# op-name prefix (pytorch_connectomics_b200 profiler hooks) -> kernel symbol
 KERNELS = {
     "mlp_fwd": "pcb::mlp_fused_kernel / pcb::mlp_kernel (GN-apply -> GEMM -> GELU -> GEMM + residual, tcgen05)",
-    "mlp_bwd_fused": "pcb::mlp_bwd_fused_kernel (dgrad + both pointwise wgrads in TMEM, tcgen05)",
-    "mlp_bwd": "pcb::mlp_bwd_kernel (dgrad, tcgen05)",
+    "mlp_fwd_deep": "pcb::gemm_ws_kernel x2 (deep levels: conv2+GELU, conv3+residual, tcgen05)",
+    "mlp_bwd_fused": "pcb::mlp_bwd_ws_kernel / mlp_bwd_ws2_kernel (dgrad + both pointwise wgrads in TMEM, tcgen05, warp-specialised)",
+    "mlp_bwd": "pcb::mlp_bwd_kernel / gemm_ws_kernel (dgrad, tcgen05)",
     "dwconv_fwd": "pcb::dwconv_same_tiled_kernel<3> / dwconv_kernel (depthwise stencil + GN statistics)",
     "dw_bwd_data": "pcb::dwconv_same_tiled_kernel<3> / dwconv_kernel (stencil data gradient)",
     "dw_wgrad": "pcb::dw_wgrad_same_tiled_kernel<3> / dw_wgrad_kernel (depthwise weight gradient)",
@@ -215,9 +277,10 @@ def _op_bytes(op: str, key: str, batch: int):
     return None
 
 
-def build_roofline(prof, a, peak_gbs, measured, step_ms, nsteps):
+def build_roofline(prof, batch, peak_gbs, measured, step_ms, nsteps):
     """Dominant kernel = op type with the largest share of the (eager, event-instrumented) step; its roofline
-    numbers are quoted on its biggest launch class (level 0) with the live CUDA-event launch durations."""
+    numbers are quoted on its biggest launch class (level 0) with the live CUDA-event launch durations.
+    `batch` = samples (crops or windows) per launch — the training batch or the engine's sw_batch."""
     if not prof:
         return None
     groups = {}
@@ -227,7 +290,6 @@ def build_roofline(prof, a, peak_gbs, measured, step_ms, nsteps):
         g["ms"] += sum(dts) / nsteps
         g["classes"][key] = dts
     ranked = sorted(groups.items(), key=lambda kv: -kv[1]["ms"])
-    batch = a.batch if a.mode == "train" else 2
     rows = []
     for op, g in ranked[:4]:
         key, dts = max(g["classes"].items(), key=lambda kv: sum(kv[1]))
@@ -235,30 +297,324 @@ def build_roofline(prof, a, peak_gbs, measured, step_ms, nsteps):
         nbytes = _op_bytes(op, key, batch)
         ach = nbytes / (avg_ms / 1e3) / 1e9 if nbytes else None
         rows.append({"kernel": KERNELS.get(op, op), "launch_class": key, "bound": "hbm", "achieved": ach, "peak": peak_gbs,
-                     "unit": "GB/s", "frac": (ach / peak_gbs) if ach else None, "traffic": (NCU_TRAFFIC[key] * batch) if key in NCU_TRAFFIC else None,
-                     "avg_launch_ms": avg_ms, "launches_timed": len(dts), "algorithmic_bytes": nbytes,
-                     "op_ms_per_step": g["ms"], "share_of_step": g["ms"] / step_ms})
+                     "unit": "GB/s", "frac": (ach / peak_gbs) if ach else None,
+                     "traffic": (NCU_TRAFFIC[key] * batch) if key in NCU_TRAFFIC else None,
+                     "avg_launch_ms": avg_ms, "launches_timed": len(dts), "samples_per_launch": batch,
+                     "algorithmic_bytes": nbytes, "op_ms_per_step": g["ms"], "share_of_step": g["ms"] / step_ms})
     roof = dict(rows[0])
     roof["peak_source"] = "MEASURED_PEAKS.json (of measured)" if measured else "fallback 6650 GB/s (of fallback)"
-    roof["traffic_source"] = "ncu DRAM bytes (read + write) per launch from the batch-1 capture in profiles/ x batch; null = not captured"
+    roof["traffic_source"] = "ncu DRAM bytes (read + write) per launch from the batch-1 capture in profiles/ x samples per launch; null = not captured"
     roof["others"] = rows[1:]
     return roof
 
-def step_roofline(mode: str, units_per_step: float, ms_per_step: float, hbm_gbs: float, bf16_tflops: float):
-    """Whole-step roofline (BASELINE.md §2 / SURVEY §8d): MedNeXt-S k3 at 160^3 needs 522 GFLOP and, with fused blocks,
-    5.49 GB of HBM traffic per forward; a training step is 3x that.  Time per unit = max(bytes / HBM, FLOPs / tensor peak)
-    with the MEASURED peaks; `frac` = roofline time / achieved time of the whole step (not of one kernel)."""
+
+def step_roofline(mode: str, units_per_step: float, ms_per_step: float, hbm_gbs: float, bf16_tflops: float,
+                  work=FWD_WORK[("S", 160)], unit_name: str = "160^3"):
+    """Whole-step roofline (BASELINE.md §2 / SURVEY §8d): one forward of the unit needs `work` = (min HBM bytes with fused
+    blocks, FLOPs); a training step is 3x that.  Time per unit = max(bytes / HBM, FLOPs / tensor peak) with the MEASURED
+    peaks; `frac` = roofline time / achieved time of the whole step (not of one kernel)."""
     passes = 3.0 if mode == "train" else 1.0
-    t_unit = max(passes * 5.49e9 / (hbm_gbs * 1e9), passes * 522e9 / (bf16_tflops * 1e12))      # s per 160^3 sub-volume / tile
+    nbytes, flops = passes * work[0], passes * work[1]
+    t_unit = max(nbytes / (hbm_gbs * 1e9), flops / (bf16_tflops * 1e12))      # s per sub-volume / tile
     roof_ms = units_per_step * t_unit * 1e3
-    return {"unit": "160^3 sub-volume (train: fwd+bwd = 3 x fwd)" if mode == "train" else "160^3 tile forward",
-            "bytes_per_unit": passes * 5.49e9, "flops_per_unit": passes * 522e9, "units_per_step": units_per_step,
+    return {"unit": f"{unit_name} sub-volume (train: fwd+bwd = 3 x fwd)" if mode == "train" else f"{unit_name} tile forward",
+            "bytes_per_unit": nbytes, "flops_per_unit": flops, "units_per_step": units_per_step,
             "roofline_ms_per_step": roof_ms, "frac": roof_ms / ms_per_step if ms_per_step > 0 else None,
-            "bound": "hbm" if passes * 5.49e9 / (hbm_gbs * 1e9) >= passes * 522e9 / (bf16_tflops * 1e12) else "tensor"}
+            "bound": "hbm" if nbytes / (hbm_gbs * 1e9) >= flops / (bf16_tflops * 1e12) else "tensor"}
+
+
+def tiles_per_axis(n: int, roi: int = SIDE) -> int:
+    """eager grid (window.py:92-134) at 50 % overlap: starts 0, 80, ... plus the snapped last one."""
+    if n <= roi:
+        return 1
+    st = roi // 2
+    k = (n - roi) // st + 1
+    return k + (1 if (n - roi) % st else 0)
 
 
 # ----------------------------------------------------------------------------- our arm
 T0 = time.time()
+
+
+def dbg(msg):
+    if os.environ.get("PCB_BENCH_DEBUG"):
+        print(f"[bench r{os.environ.get('RANK', '0')} +{time.time() - T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
+class Ctx:
+    """process-group plumbing shared by the two legs"""
+
+    def __init__(self):
+        import torch.distributed as dist
+        self.dist = dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+                os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout (one JSON line contract)
+            dist.init_process_group("nccl", device_id=self.dev)
+            dbg("process group up")
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, ms: float) -> float:
+        if self.world == 1:
+            return ms
+        t = torch.tensor([ms], device=self.dev, dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def run_train(cx: Ctx, a, key: str, clocks):
+    """One BASELINE training config: K timed steps (CUDA-graph replay), instrumented eager pass for the roofline, e2e."""
+    from pytorch_connectomics_b200 import _lib as L
+    from pytorch_connectomics_b200.architectures import build_model
+    from pytorch_connectomics_b200.training import FlatGradArena, broadcast_parameters
+
+    spec = TRAIN_CONFIGS[key]
+    world, rank, dev = cx.world, cx.rank, cx.dev
+    nb, side, oc = train_batch(a, key), spec["crop"], spec["out_channels"]
+    torch.manual_seed(1234)                         # identical initial weights on every rank ...
+    model = build_model(cfg_mednext(spec["size"], oc)).to(dev)
+    model.train()
+    broadcast_parameters(model, src=0)              # ... and, like DDP at construction, rank 0's copy wins
+    torch.manual_seed(4321 + rank)                  # data differs per rank
+    arena = FlatGradArena(model.parameters())
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.01, fused=True, capturable=True)
+    shape, tshape = (nb, 1, side, side, side), (nb, oc, side, side, side)
+    npool = 4 if side <= 160 else 2
+    # a small pool of distinct resident inputs (fp16 volumes, as the data pipeline delivers them)
+    pool = [(torch.rand(shape, device=dev).half(), (torch.rand(tshape, device=dev) > 0.85).float()) for _ in range(npool)]
+
+    def step(x, t):
+        arena.zero()
+        loss = bce_dice_loss(model(x), t)
+        loss.backward()
+        arena.allreduce()
+        opt.step()
+        return loss
+
+    for i in range(a.warmup):
+        step(*pool[i % npool])
+    cx.barrier()
+    dbg("warmup done")
+    # (1) instrumented eager pass: per-launch CUDA events around every pcb200 op (roofline leg)
+    nprof = a.steps if (a.no_graph or a.profile_ops) else min(3, a.steps)
+    L.prof_start([])
+    l0 = L.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(nprof):
+        step(*pool[i % npool])
+    e1.record()
+    cx.barrier()
+    launches_per_step = (L.launch_count() - l0) // max(1, nprof)
+    prof = L.prof_stop()
+    ms_eager = cx.max_over_ranks(e0.elapsed_time(e1)) / nprof
+    dbg(f"eager pass done: {ms_eager:.2f} ms/step")
+    # (2) timed region: the same step captured once as a CUDA graph and replayed K times
+    graphed, run, capture_error = None, step, None
+    if not (a.no_graph or a.profile_ops):
+        try:
+            from pytorch_connectomics_b200.training import GraphedTrainStep
+            graphed = GraphedTrainStep(model, bce_dice_loss, opt, arena, pool[0][0], pool[0][1], warmup=1,
+                                       split_collective=world > 1 and not os.environ.get("PCB_GRAPH_DDP"))
+            run = graphed
+        except Exception as exc:   # keep the bench alive; say so in the JSON line
+            capture_error = repr(exc)
+            print(f"[bench] CUDA-graph capture failed, timing eager steps: {exc!r}", file=sys.stderr)
+            graphed = None
+            arena.rebind()
+    for i in range(2):
+        run(*pool[i % npool])
+    cx.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.time()
+    e0.record()
+    for i in range(a.steps):
+        run(*pool[i % npool])
+    e1.record()
+    cx.barrier()
+    w1 = time.time()
+    ms = cx.max_over_ranks(e0.elapsed_time(e1))
+    value = world * nb * a.steps / (ms / 1e3)
+    dbg(f"timed region done: {ms / a.steps:.2f} ms/step")
+
+    # ---- end to end: pinned host batch -> H2D -> step -> loss D2H, every step
+    hx = [torch.rand(shape).half().pin_memory() for _ in range(2)]
+    ht = [(torch.rand(tshape) > 0.85).float().pin_memory() for _ in range(2)]
+    h2d = hx[0].numel() * 2 + ht[0].numel() * 4
+
+    def e2e_step(i):
+        if graphed is not None:      # pinned host -> static device buffers -> graph replay -> loss D2H
+            return float(graphed(hx[i % 2], ht[i % 2]).item())
+        x = hx[i % 2].to(dev, non_blocking=True)
+        t = ht[i % 2].to(dev, non_blocking=True)
+        return float(step(x, t).item())
+
+    for i in range(2):
+        e2e_step(i)
+    cx.barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(a.steps):
+        e2e_step(i)
+    f1.record()
+    cx.barrier()
+    ms_e2e = cx.max_over_ranks(f0.elapsed_time(f1))
+    dbg("e2e done")
+    peaks = load_peaks()
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1366.0)))
+    rec = {"metric": METRIC_TRAIN, "value": value, "unit": "sub-volumes/s", "n_gpus": world, "steps": a.steps,
+           "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": train_config(a, key, world),
+           "e2e": {"value": world * nb * a.steps / (ms_e2e / 1e3), "unit": "sub-volumes/s", "h2d_bytes_per_step": h2d,
+                   "d2h_bytes_per_step": 4},
+           "gpu_launches": int(launches_per_step * a.steps),
+           "roofline": build_roofline(prof, nb, peak_gbs, bool(peaks), ms_eager, nprof),
+           "execution": {"timed_region": ("cuda_graph_replay" if graphed.graph_opt is None else
+                                          "cuda_graph_replay x2 around eager NCCL all-reduce") if graphed is not None else "eager",
+                         "eager_ms_per_step": ms_eager, "roofline_timed_in": f"instrumented eager pass of {nprof} steps",
+                         "graph_capture_error": capture_error},
+           "clocks": clocks.window(w0, w1) if clocks else None}
+    try:
+        rec["step_roofline"] = step_roofline("train", nb, ms / a.steps, peak_gbs, tf, FWD_WORK[(spec["size"], side)],
+                                             f"{side}^3")
+    except Exception as exc:
+        rec["step_roofline"] = {"error": repr(exc)}
+    if a.profile_ops and rank == 0:
+        _print_ops(prof, nprof, ms_eager)
+    del graphed, run, pool, opt, arena, model
+    torch.cuda.empty_cache()
+    return rec
+
+
+def _print_ops(prof, nsteps, step_ms):
+    tot = sum(sum(v) for v in prof.values())
+    for k, v in sorted(prof.items(), key=lambda kv: -sum(kv[1])):
+        print(f"{k:44s} n={len(v) // nsteps:3d}/step  {sum(v) / nsteps:8.3f} ms/step  avg {sum(v) / len(v):7.3f} ms",
+              file=sys.stderr)
+    print(f"{'sum of timed ops':44s} {tot / nsteps:8.3f} ms/step of {step_ms:.3f}", file=sys.stderr)
+
+
+def run_infer(cx: Ctx, a, clocks, steps: int, warmup: int):
+    """Sliding-window inference (configs[4] geometry).  world == 1: one volume on one GPU through
+    EagerSlidingWindowEngine; world > 1: ONE volume z-slab sharded over the ranks (inference/sharded.py)."""
+    from pytorch_connectomics_b200 import _lib as L
+    from pytorch_connectomics_b200.architectures import build_model
+    from pytorch_connectomics_b200.inference.window import EagerSlidingWindowEngine
+
+    world, rank, dev = cx.world, cx.rank, cx.dev
+    vol_size = infer_volume(a, world)
+    nvox = vol_size[0] * vol_size[1] * vol_size[2]
+    torch.manual_seed(1234)
+    model = build_model(cfg_mednext("S", 1)).to(dev)
+    model.eval()
+    kw = dict(roi_size=(SIDE,) * 3, sw_batch_size=a.sw_batch, overlap=0.5, mode="bump", padding_mode="constant", cval=0.0)
+    net = lambda t: model(t)  # noqa: E731
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(99)                      # every rank generates the same synthetic volume, slab by slab, on the device
+    if world > 1:
+        from pytorch_connectomics_b200.inference.sharded import ZSlabShardedEngine, plan_z_slabs
+        sh = ZSlabShardedEngine(device=dev, **kw)
+        plan = plan_z_slabs(vol_size, (SIDE,) * 3, 0.5, world)[rank]
+        z0, z1 = plan.slab if plan.windows else (0, 0)
+        # only this rank's slab is materialised (C5: 2048^3 fp16 = 17 GB whole, ~3 GB per rank)
+        slab = torch.rand((1, 1, max(z1 - z0, 1), vol_size[1], vol_size[2]), device=dev, generator=gen).half()
+        my_tiles = len(plan.windows)
+
+        def step():
+            with torch.no_grad():
+                return sh.run_slab(slab, net, plan)
+    else:
+        eng = EagerSlidingWindowEngine(**kw)
+        vol = torch.empty((1, 1, *vol_size), device=dev, dtype=torch.float16)
+        for z in range(0, vol_size[0], 64):
+            vol[:, :, z:z + 64] = torch.rand((1, 1, min(64, vol_size[0] - z), vol_size[1], vol_size[2]), device=dev,
+                                             generator=gen).half()
+        my_tiles = tiles_per_axis(vol_size[0]) * tiles_per_axis(vol_size[1]) * tiles_per_axis(vol_size[2])
+
+        def step():
+            with torch.no_grad():
+                return eng(inputs=vol, network=net)
+
+    for _ in range(max(1, warmup)):
+        step()
+    cx.barrier()
+    L.prof_start([])
+    l0 = L.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.time()
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    cx.barrier()
+    w1 = time.time()
+    launches = L.launch_count() - l0
+    prof = L.prof_stop()
+    ms = cx.max_over_ranks(e0.elapsed_time(e1))
+    value = steps * nvox / (ms / 1e3) / 1e6
+    dbg(f"infer timed region done: {ms / steps:.1f} ms/volume")
+    # ---- end to end: pinned host volume -> H2D (this rank's slab) -> windows -> exchange -> own planes D2H
+    e2e = None
+    if not a.no_e2e:
+        if world > 1:
+            hv = torch.rand((1, 1, max(z1 - z0, 1), vol_size[1], vol_size[2])).half().pin_memory()
+        else:
+            hv = torch.rand((1, 1, *vol_size)).half().pin_memory()
+            eng_cpu = EagerSlidingWindowEngine(sw_device=dev, output_device="cpu", **kw)
+        cx.barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        with torch.no_grad():
+            if world > 1:
+                part = sh.run_slab(hv, net, plan)
+                out = part.cpu() if part is not None else torch.empty(0)
+            else:
+                out = eng_cpu(inputs=hv, network=net)
+        f1.record()
+        cx.barrier()
+        ms_e2e = cx.max_over_ranks(f0.elapsed_time(f1))
+        e2e = {"value": nvox / (ms_e2e / 1e3) / 1e6, "unit": "Mvox/s", "h2d_bytes_per_step": hv.numel() * 2,
+               "d2h_bytes_per_step": out.numel() * out.element_size(), "steps": 1}
+        del hv, out
+    peaks = load_peaks()
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1366.0)))
+    rec = {"metric": METRIC_INFER, "value": value, "unit": "Mvox/s", "n_gpus": world, "steps": steps, "warmup": max(1, warmup),
+           "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong" if a.config == "c5" else "weak",
+           "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": infer_config(a, world), "e2e": e2e,
+           "gpu_launches": int(launches), "tiles_per_rank_per_step": my_tiles,
+           "roofline": build_roofline(prof, a.sw_batch, peak_gbs, bool(peaks), ms / steps, steps),
+           "execution": {"timed_region": "eager tile loop"}, "clocks": clocks.window(w0, w1) if clocks else None}
+    try:      # the slowest rank's tile count bounds the step
+        rec["step_roofline"] = step_roofline("infer", my_tiles, ms / steps, peak_gbs, tf)
+    except Exception as exc:
+        rec["step_roofline"] = {"error": repr(exc)}
+    if a.profile_ops and rank == 0:
+        _print_ops(prof, steps, ms / steps)
+    del model
+    torch.cuda.empty_cache()
+    return rec
 
 
 def main():
@@ -267,263 +623,58 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="pcb200", choices=["pcb200", "reference"])
-    ap.add_argument("--mode", default="train", choices=["train", "infer"])
-    ap.add_argument("--batch", type=int, default=4, help="sub-volumes per GPU per step (tutorials/mito_lucchi++ trains with 4)")
-    ap.add_argument("--volume", type=int, default=480)
-    ap.add_argument("--sw-batch", type=int, default=4, help="windows per network call in --mode infer")
+    ap.add_argument("--config", default="default", choices=["default", "c2", "c3", "c4", "c5"],
+                    help="BASELINE.json config; default = c2 training (top-level record) + c5-geometry inference (`infer`)")
+    ap.add_argument("--mode", default=None, choices=["train", "infer"], help="legacy alias: train = --config c2, infer = c5 geometry only")
+    ap.add_argument("--batch", type=int, default=0, help="sub-volumes per GPU per step (0 = the config's own: 4 for c2/c3, 1 for c4)")
+    ap.add_argument("--volume", type=int, default=0, help="inference volume side per GPU (default 640; --config c5: 2048 total)")
+    ap.add_argument("--sw-batch", type=int, default=4, help="windows per network call in the inference leg")
+    ap.add_argument("--infer-steps", type=int, default=0, help="timed volumes of the `infer` record (default min(steps, 3))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-volume e2e pass of the inference leg")
     ap.add_argument("--profile-ops", action="store_true", help="time every pcb200 op with CUDA events (stderr table)")
     ap.add_argument("--no-graph", action="store_true", help="run the timed steps eagerly instead of as one CUDA graph")
     a = ap.parse_args()
+    if a.mode == "train":
+        a.config = "c2"
+    a.infer_only = a.mode == "infer"
     a.warmup = max(3, a.warmup) if a.impl == "pcb200" else a.warmup
     if a.impl == "reference":
+        if a.infer_only:
+            a.config = "c5"
         return run_reference(a)
 
-    import torch.distributed as dist
     from pytorch_connectomics_b200 import _lib as L
-
-    def dbg(msg):
-        if os.environ.get("PCB_BENCH_DEBUG"):
-            print(f"[bench r{os.environ.get('RANK', '0')} +{time.time() - T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
-
-    from pytorch_connectomics_b200.architectures import build_model
-    from pytorch_connectomics_b200.training import FlatGradArena
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout (one JSON line contract)
-        dist.init_process_group("nccl", device_id=dev)
-        dbg("process group up")
+    cx = Ctx()
     if not os.path.exists(L.LIB_PATH):
         L.build()
     if L.lib().pcb_device_ok() != 1:
         raise RuntimeError(L.lib().pcb_last_error().decode())
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(ms: float) -> float:
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    torch.manual_seed(1234 + rank)
-    model = build_model(cfg_mednext("S", 1)).to(dev)
-    clocks = Clocks(local) if rank == 0 else None
-
-    if a.mode == "train":
-        model.train()
-        arena = FlatGradArena(model.parameters())
-        opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.01, fused=True, capturable=True)
-        nb = a.batch
-        shape = (nb, 1, SIDE, SIDE, SIDE)
-        # a small pool of distinct resident inputs (fp16 volumes, as the data pipeline delivers them)
-        pool = [(torch.rand(shape, device=dev).half(), (torch.rand(shape, device=dev) > 0.85).float()) for _ in range(4)]
-
-        def step(x, t):
-            arena.zero()
-            loss = bce_dice_loss(model(x), t)
-            loss.backward()
-            arena.allreduce()
-            opt.step()
-            return loss
-
-        for i in range(a.warmup):
-            step(*pool[i % 4])
-            dbg(f"warmup step {i} enqueued")
-        barrier()
-        dbg("warmup done")
-        # (1) instrumented eager pass: per-launch CUDA events around the dominant kernel (roofline leg)
-        nprof = a.steps if (a.no_graph or a.profile_ops) else min(3, a.steps)
-        L.prof_start([])   # every pcb200 op gets a CUDA-event pair
-        l0 = L.launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        w0 = time.time()
-        e0.record()
-        for i in range(nprof):
-            step(*pool[i % 4])
-        e1.record()
-        barrier()
-        w1 = time.time()
-        launches_per_step = (L.launch_count() - l0) // max(1, nprof)
-        prof = L.prof_stop()
-        ms_eager = max_over_ranks(e0.elapsed_time(e1)) / nprof
-        # (2) timed region: the same step captured once as a CUDA graph and replayed K times
-        graphed = None
-        run = step
-        dbg(f"eager pass done: {ms_eager:.2f} ms/step")
-        # data-parallel runs: two graphs around an eagerly launched NCCL all-reduce (PCB_GRAPH_DDP=1: one graph, NCCL captured)
-        if not (a.no_graph or a.profile_ops):
-            try:
-                from pytorch_connectomics_b200.training import GraphedTrainStep
-                graphed = GraphedTrainStep(model, bce_dice_loss, opt, arena, pool[0][0], pool[0][1], warmup=1,
-                                           split_collective=world > 1 and not os.environ.get("PCB_GRAPH_DDP"))
-                run = graphed
-            except Exception as exc:   # keep the bench alive; say so in the JSON line
-                print(f"[bench] CUDA-graph capture failed, timing eager steps: {exc!r}", file=sys.stderr)
-                graphed = None
-                arena.rebind()
-        for i in range(2):
-            run(*pool[i % 4])
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        w0 = time.time()
-        e0.record()
-        for i in range(a.steps):
-            run(*pool[i % 4])
-        e1.record()
-        barrier()
-        w1 = time.time()
-        launches = launches_per_step * a.steps
-        ms = max_over_ranks(e0.elapsed_time(e1))
-        value = world * nb * a.steps / (ms / 1e3)
-        dbg(f"timed region done: {ms / a.steps:.2f} ms/step")
-
-        # ---- end to end: pinned host batch -> H2D -> step -> loss D2H, every step
-        hx = [torch.rand(shape).half().pin_memory() for _ in range(2)]
-        ht = [(torch.rand(shape) > 0.85).float().pin_memory() for _ in range(2)]
-        h2d = hx[0].numel() * 2 + ht[0].numel() * 4
-
-        def e2e_step(i):
-            if graphed is not None:      # pinned host -> static device buffers -> graph replay -> loss D2H
-                return float(graphed(hx[i % 2], ht[i % 2]).item())
-            x = hx[i % 2].to(dev, non_blocking=True)
-            t = ht[i % 2].to(dev, non_blocking=True)
-            return float(step(x, t).item())
-
-        for i in range(2):
-            e2e_step(i)
-        barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        for i in range(a.steps):
-            e2e_step(i)
-        f1.record()
-        barrier()
-        ms_e2e = max_over_ranks(f0.elapsed_time(f1))
-        dbg("e2e done")
-        e2e = {"value": world * nb * a.steps / (ms_e2e / 1e3), "unit": "sub-volumes/s",
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
-        metric, unit = METRIC_TRAIN, "sub-volumes/s"
+    clocks = Clocks(cx.local) if cx.rank == 0 else None
+    infer_steps = a.infer_steps or max(1, min(a.steps, 3))
+    out = None
+    if a.config == "c5" or a.infer_only:
+        out = run_infer(cx, a, clocks, a.steps if a.config == "c5" and not a.infer_steps else infer_steps,
+                        1 if a.config == "c5" else a.warmup // 3)
     else:
-        model.eval()
-        from pytorch_connectomics_b200.inference.window import EagerSlidingWindowEngine
-        eng = EagerSlidingWindowEngine(roi_size=(SIDE,) * 3, sw_batch_size=a.sw_batch, overlap=0.5, mode="bump",
-                                       padding_mode="constant", cval=0.0)
-        net = lambda t: model(t)  # noqa: E731
-        if world > 1:
-            # ONE volume of world x `volume` planes, z-slab sharded with a neighbour exchange of the overlap planes
-            # (inference/sharded.py); every rank holds the same synthetic volume and stages only its slab
-            from pytorch_connectomics_b200.inference.sharded import ZSlabShardedEngine
-            torch.manual_seed(99)
-            vol = torch.rand(1, 1, a.volume * world, a.volume, a.volume, device=dev).half()
-            sh = ZSlabShardedEngine(roi_size=(SIDE,) * 3, sw_batch_size=a.sw_batch, overlap=0.5, mode="bump",
-                                    padding_mode="constant", cval=0.0, device=dev)
-
-            def step():
-                with torch.no_grad():
-                    return sh(vol, net)
-        else:
-            vol = torch.rand(1, 1, a.volume, a.volume, a.volume, device=dev).half()
-
-            def step():
-                with torch.no_grad():
-                    return eng(inputs=vol, network=net)
-
-        for _ in range(max(1, a.warmup // 3)):
-            step()
-        barrier()
-        L.prof_start([])
-        l0 = L.launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        w0 = time.time()
-        e0.record()
-        for _ in range(a.steps):
-            step()
-        e1.record()
-        barrier()
-        w1 = time.time()
-        launches = L.launch_count() - l0
-        prof = L.prof_stop()
-        ms = max_over_ranks(e0.elapsed_time(e1))
-        value = world * a.steps * a.volume ** 3 / (ms / 1e3) / 1e6
-        if world > 1:
-            hv = torch.rand(1, 1, a.volume * world, a.volume, a.volume).half().pin_memory()
-        else:
-            hv = torch.rand(1, 1, a.volume, a.volume, a.volume).half().pin_memory()
-        eng_cpu = EagerSlidingWindowEngine(roi_size=(SIDE,) * 3, sw_batch_size=a.sw_batch, overlap=0.5, mode="bump",
-                                           padding_mode="constant", cval=0.0, sw_device=dev, output_device="cpu")
-        barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        with torch.no_grad():
-            if world > 1:      # host volume -> this rank's slab H2D -> windows -> exchange -> own planes D2H
-                part, own = sh(hv, net)
-                out = part.cpu() if part is not None else torch.empty(0)
-                h2d_bytes = 0 if part is None else (own[1] - own[0] + SIDE // 2) * a.volume * a.volume * 2
-            else:
-                out = eng_cpu(inputs=hv, network=net)
-                h2d_bytes = hv.numel() * 2
-        f1.record()
-        barrier()
-        ms_e2e = max_over_ranks(f0.elapsed_time(f1))
-        e2e = {"value": world * a.volume ** 3 / (ms_e2e / 1e3) / 1e6, "unit": "Mvox/s",
-               "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": out.numel() * out.element_size()}
-        metric, unit = METRIC_INFER, "Mvox/s"
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    if a.profile_ops:
-        tot = sum(sum(v) for v in prof.values())
-        for k, v in sorted(prof.items(), key=lambda kv: -sum(kv[1])):
-            print(f"{k:40s} n={len(v) // a.steps:3d}/step  {sum(v) / a.steps:8.3f} ms/step  avg {sum(v) / len(v):7.3f} ms",
-                  file=sys.stderr)
-        print(f"{'sum of timed ops':40s} {tot / a.steps:8.3f} ms/step of {ms / a.steps:.3f}", file=sys.stderr)
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
-    roof = build_roofline(prof, a, peak_gbs, bool(peaks), ms_eager if a.mode == "train" else ms / a.steps,
-                          nprof if a.mode == "train" else a.steps)
-    out = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-           "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "bf16", "data": "synthetic", "config": workload_config(a, world), "e2e": e2e,
-           "gpu_launches": int(launches), "roofline": roof,
-           "execution": ({"timed_region": ("cuda_graph_replay" if graphed.graph_opt is None else "cuda_graph_replay x2 around eager NCCL all-reduce") if graphed is not None else "eager",
-                          "eager_ms_per_step": ms_eager, "roofline_timed_in": f"instrumented eager pass of {nprof} steps"}
-                         if a.mode == "train" else {"timed_region": "eager"}),
-           "clocks": clocks.window(w0, w1) if clocks else None}
+        out = run_train(cx, a, a.config if a.config != "default" else "c2", clocks)
+        if a.config == "default":
+            out["infer"] = run_infer(cx, a, clocks, infer_steps, 1)
     if clocks:
         clocks.stop()
-    try:        # whole-step roofline beside the dominant-kernel one (never allowed to cost the JSON line)
-        tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1366.0)))
-        if a.mode == "train":
-            out["step_roofline"] = step_roofline("train", a.batch, ms / a.steps, peak_gbs, tf)      # per GPU
-        elif world == 1:
-            ntile = (max(a.volume, SIDE) - SIDE + SIDE // 2 - 1) // (SIDE // 2) + 1
-            out["step_roofline"] = step_roofline("infer", ntile ** 3, ms / a.steps, peak_gbs, tf)
-    except Exception as exc:
-        out["step_roofline"] = {"error": repr(exc)}
-    if world == 1 and not a.no_cpu_baseline:
-        r = cpu_train_rate(1, 0) if a.mode == "train" else cpu_infer_rate(1, 0)
-        out["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
-    print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    if cx.rank == 0:
+        if cx.world == 1 and not a.no_cpu_baseline:
+            if out["metric"] == METRIC_TRAIN:
+                r = cpu_train_rate(1, 0, out["config"]["baseline_config"])
+                out["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+                if "infer" in out:
+                    ri = cpu_infer_rate(1, 0)
+                    out["infer"]["cpu_baseline"] = {k: ri[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            else:
+                ri = cpu_infer_rate(1, 0)
+                out["cpu_baseline"] = {k: ri[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(out))
+    cx.close()
 
 
 if __name__ == "__main__":

@@ -54,7 +54,8 @@ int pcb_sw_plan(int grid_kind, const int64_t image[3], const int64_t roi[3], con
 int pcb_sw_importance_map(int blend, const int64_t roi[3], int ndim, int dtype, double min_value,
                           void* map_out, void* stream);
 /* window.py:464-527 _extract_padded_patch_batch: gather n windows [n,C,roi] from vol [1,C,D,H,W];
- * `starts` is a HOST array of n (z,y,x) triples; pad per window relative to the in-image crop. */
+ * `starts` is a HOST array of n (z,y,x) triples (passed to the kernel as launch parameters: no device allocation, copy
+ * or synchronisation — the call is CUDA-graph capturable); pad per window relative to the in-image crop. */
 int pcb_sw_extract(const void* vol, int dtype, int64_t C, const int64_t image[3], const int64_t roi[3],
                    const int64_t* starts, int64_t n, int pad_mode, double cval, void* out, void* stream);
 /* window.py:648-655 _accumulate for ONE window: value[:, lo:hi] += pred[plo:phi]*map ; weight += map
@@ -64,6 +65,13 @@ int pcb_sw_accumulate(const void* pred, const void* map, void* value, void* weig
                       int64_t Cout, const int64_t roi[3], const int64_t out_size[3],
                       const int64_t pred_lo[3], const int64_t out_lo[3], const int64_t box[3],
                       void* stream);
+/* window.py:641-655: the `for idx ...: _accumulate(...)` loop over one network batch — n FULL windows (pred [n,Cout,roi],
+ * `starts` = HOST array of n (z,y,x) triples inside the accumulator) in ONE launch per 16 windows, bit-identical to
+ * calling pcb_sw_accumulate once per window in list order (each output voxel is owned by one thread, which applies the
+ * covering windows in order). */
+int pcb_sw_accumulate_batch(const void* pred, const void* map, void* value, void* weight, int dtype, int64_t Cout,
+                            const int64_t roi[3], const int64_t out_size[3], const int64_t* starts, int64_t n,
+                            void* stream);
 /* window.py:275-294 normalize_weighted_accumulator: value /= clamp_min(weight, 1e-4) (in place). */
 int pcb_sw_normalize(void* value, const void* weight, int dtype, int64_t Cout, int64_t nvox, void* stream);
 
@@ -218,6 +226,22 @@ int pcb_bn_act_bwd(const void* dy, const void* x, const float* scale, const floa
 /* BatchNorm backward with batch statistics (pooled sums replicated per sample in stats/gstats [N,2,C]). */
 int pcb_bn_bwd(const void* g, const void* x, const double* stats, const double* gstats, const float* gamma,
                void* dx, double* dsum, int64_t N, int64_t C, int64_t V, void* stream);
+
+/* ------------------------------------------------------------------ optimizer-side fusion over the flat arenas
+ * sum of squares of a gradient arena (f64 device scalar, caller zeroes) — torch.nn.utils.clip_grad_norm_'s total norm
+ * (Lightning gradient_clip_val, tutorials: 1.0). */
+int pcb_grad_sumsq(const float* grad, int64_t n, double* out, void* stream);
+/* ONE pass: [clip by global norm] + AdamW + [EMA] over flat fp32 arenas of n elements.  Segment i covers elements
+ * [seg_end[i-1], seg_end[i]) with its own lr / weight decay (training/optimization/build.py:88-113: norm layers and
+ * biases form their own groups); seg_* are DEVICE arrays.  grad is used as grad*grad_scale (1/world: the all-reduced SUM
+ * becomes the mean) * clip coefficient min(1, max_norm / (sqrt(*grad_sumsq)*grad_scale + 1e-6)) when grad_sumsq != NULL
+ * and max_norm > 0.  `step` is a device float holding the number of steps taken so far; it is incremented on the stream
+ * (CUDA-graph capturable, like torch's capturable=True).  ema (or NULL): ema = ema*decay + param*(1-decay) after the
+ * update (training/lightning/callbacks.py:869-907).  Update formula = torch.optim.AdamW, op for op. */
+int pcb_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* ema, int64_t n,
+                   const int64_t* seg_end, const float* seg_lr, const float* seg_wd, int nseg, float beta1, float beta2,
+                   float eps, float* step, const double* grad_sumsq, float max_norm, float grad_scale, float ema_decay,
+                   void* stream);
 
 #ifdef __cplusplus
 }

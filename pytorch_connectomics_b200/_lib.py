@@ -19,7 +19,8 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libpcb200.so")
-SOURCES = ["pcb_api.cu", "sw_kernels.cu", "mednext_fwd.cu", "mednext_bwd.cu", "dense_conv.cu", "deep_mlp.cu", "layernorm.cu", "tta_kernels.cu"]
+SOURCES = ["pcb_api.cu", "sw_kernels.cu", "mednext_fwd.cu", "mednext_bwd.cu", "dense_conv.cu", "deep_mlp.cu", "layernorm.cu", "tta_kernels.cu",
+           "optim_kernels.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -33,20 +34,48 @@ _DTYPES = {torch.float32: PCB_F32, torch.float16: PCB_F16, torch.bfloat16: PCB_B
 
 _lib: Optional[ctypes.CDLL] = None
 
+# Bumped by anything that rewrites parameter storage behind autograd's back (the fused optimizer kernel updates the flat
+# parameter arena through a raw pointer, so ``Parameter._version`` does not move): kernel-layout weight caches
+# (``architectures/_mednext_ops.packed``) compare it and repack.
+PARAM_EPOCH = [0]
+
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile the CUDA sources into ``csrc/libpcb200.so`` with nvcc for sm_100a (in-tree)."""
+    """Compile the CUDA sources into ``csrc/libpcb200.so`` with nvcc for sm_100a (in-tree): one object per source,
+    compiled in parallel and only when stale, then one link step."""
+    from concurrent.futures import ThreadPoolExecutor
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    deps = srcs + [os.path.join(CSRC, "pcb_common.cuh"), os.path.join(_HERE, "..", "include", "pcb200.h")]
-    if not force and os.path.exists(LIB_PATH):
-        t = os.path.getmtime(LIB_PATH)
-        if all(os.path.getmtime(d) <= t for d in deps if os.path.exists(d)):
-            return LIB_PATH
+    hdrs = [os.path.join(CSRC, "pcb_common.cuh"), os.path.join(_HERE, "..", "include", "pcb200.h")]
+    hdr_t = max(os.path.getmtime(h) for h in hdrs if os.path.exists(h))
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + srcs
-    if verbose:
-        print(" ".join(cmd), file=sys.stderr)
-    subprocess.run(cmd, check=True, cwd=CSRC)
+    objdir = os.path.join(CSRC, "build")
+    os.makedirs(objdir, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def obj_of(src):
+        return os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+
+    def stale(src):
+        o = obj_of(src)
+        return force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(src), hdr_t)
+
+    todo = [s for s in srcs if stale(s)]
+
+    def compile_one(src):
+        cmd = [nvcc] + flags + ["-c", "-o", obj_of(src), src]
+        if verbose:
+            print(" ".join(cmd), file=sys.stderr)
+        subprocess.run(cmd, check=True, cwd=CSRC)
+
+    if todo:
+        with ThreadPoolExecutor(max_workers=min(len(todo), os.cpu_count() or 1)) as ex:
+            list(ex.map(compile_one, todo))
+    objs = [obj_of(s) for s in srcs]
+    if todo or not os.path.exists(LIB_PATH) or any(os.path.getmtime(o) > os.path.getmtime(LIB_PATH) for o in objs):
+        cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH] + objs
+        if verbose:
+            print(" ".join(cmd), file=sys.stderr)
+        subprocess.run(cmd, check=True, cwd=CSRC)
     return LIB_PATH
 
 

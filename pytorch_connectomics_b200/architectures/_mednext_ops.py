@@ -58,14 +58,15 @@ def packed(p: torch.Tensor, kind: str) -> torch.Tensor:
     load_state_dict, .to(device))."""
     key = (id(p), kind)
     ent = _CACHE.get(key)
-    if ent is not None and ent[0] == p._version and ent[1]() is p and ent[2] == p.data_ptr():
+    ver = (p._version, L.PARAM_EPOCH[0])
+    if ent is not None and ent[0] == ver and ent[1]() is p and ent[2] == p.data_ptr():
         return ent[3]
     with torch.no_grad():
         t = _PACKERS[kind](p.detach())
     if len(_CACHE) > 8192:
         for k in [k for k, e in _CACHE.items() if e[1]() is None]:
             del _CACHE[k]
-    _CACHE[key] = (p._version, weakref.ref(p), p.data_ptr(), t)
+    _CACHE[key] = (ver, weakref.ref(p), p.data_ptr(), t)
     return t
 
 

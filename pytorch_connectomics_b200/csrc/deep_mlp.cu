@@ -490,7 +490,7 @@ static bool gw_launch(GemmArgs a, cudaStream_t st) {
   a.S = S;
   gw_magic((uint32_t)(a.o2 > 0 ? a.o2 : 1), a.dm2, a.ds2);
   gw_magic((uint32_t)(a.o1 > 0 ? a.o1 : 1), a.dm1, a.ds1);
-  static bool conf = false;
+  static DevFlag conf;
   if (!conf) {
     cudaFuncSetAttribute(gemm_ws_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (cudaFuncSetAttribute(gemm_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {

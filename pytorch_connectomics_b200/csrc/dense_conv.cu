@@ -268,7 +268,7 @@ extern "C" int pcb_conv_fwd(const void* x, const void* w, const float* bias, voi
   a.Vout = (int64_t)a.Do * a.Ho * a.Wo; a.Vin = (int64_t)a.D * a.H * a.W;
   PCB_CHECK_ARG(a.Vout < (1ll << 30) && a.Vin < (1ll << 30), "pcb_conv_fwd: volume too large");
   const size_t smem = (size_t)128 * a.KC * 2 + (size_t)a.NT * a.KC * 2 + 4 * 128 * sizeof(int) + 32;
-  static bool configured = false;
+  static DevFlag configured;
   if (!configured) {
     if (cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
       set_error("pcb_conv_fwd: cudaFuncSetAttribute failed"); return PCB_ERR_CUDA;

@@ -1921,7 +1921,7 @@ static bool launch_dw_wgrad_tiled(cudaStream_t st, const uint4* dy, const uint4*
   static const bool no_tma = getenv("PCB_NO_TMA") != nullptr;
   const int use_tma = !no_tma && make_brick_tensor_map(&tmx, x, N, D, H, W, C, WT_Z + 2 * P, WT_Y + 2 * P, WT_X + 2 * P + 1) &&
                       make_brick_tensor_map(&tmd, dy, N, D, H, W, C, WT_Z, WT_Y, WT_X);
-  static bool configured = false;
+  static DevFlag configured;
   if (!configured) {
     cudaFuncSetAttribute(dw_wgrad_same_tiled_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (cudaFuncSetAttribute(dw_wgrad_same_tiled_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
@@ -2214,7 +2214,7 @@ extern "C" int pcb_mlp_bwd(const void* y, const double* stats, const float* gamm
                       (size_t)128 * a.N1 * 2 + (size_t)a.Ct * a.N1 * 2 + (size_t)4 * C * sizeof(float) +
                       (size_t)2 * a.Ct * sizeof(double) + 128 * sizeof(int64_t) + 16;
   PCB_CHECK_ARG(smem <= 227 * 1024, "pcb_mlp_bwd: tile needs %zu B shared memory", smem);
-  static bool configured = false;
+  static DevFlag configured;
   if (!configured) {
     cudaFuncSetAttribute(mlp_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (cudaFuncSetAttribute(mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
@@ -2279,7 +2279,7 @@ extern "C" int pcb_mlp_bwd_fused(const void* y, const double* stats, const float
   const int P = mlp_bwd_fused_ctas(fa.ntiles, tcols);
   fa.part3 = workspace; fa.part2 = workspace + (int64_t)P * 129 * Co;
   const size_t smem = mlp_bwd_fused_smem((int)C, (int)H, (int)Co, (int)N);
-  static bool configured = false;
+  static DevFlag configured;
   if (!configured) {
     cudaFuncSetAttribute(mlp_bwd_fused_kernel<256>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(mlp_bwd_fused_kernel<512>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -2290,10 +2290,15 @@ extern "C" int pcb_mlp_bwd_fused(const void* y, const double* stats, const float
     configured = true;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  // opt-in generalised warp-specialised variant (PCB_BWD_WS=2): C in {32, 64}, Co in {32, 64}, every mode
+  // generalised warp-specialised variant: C in {32, 64}, Co in {32, 64}, every mode
   {
+    // default policy (measured round 2, 2 x 160^3: level-0 SAME 1.226 ms ws vs 1.334 ws2 vs 1.536 fused; down_0 0.231 ws2 vs
+    // 0.367; up_0 3.14 ws2 vs 3.60; level 1 0.506 ws2 vs 0.518): the level-0 SAME shape runs mlp_bwd_ws_kernel, every other
+    // fused-backward shape mlp_bwd_ws2_kernel.  PCB_BWD_WS=0 forces the non-specialised kernel, =1 / =2 one variant.
     const char* ws_env = getenv("PCB_BWD_WS");
-    if (ws_env && ws_env[0] == '2' && (C == 32 || C == 64) && (Co == 32 || Co == 64) && H % 16 == 0 && H <= 128 && N <= 8) {
+    const bool l0_same = C == 32 && Co == 32 && H == 64 && mode != PCB_DW_UP;
+    const bool want_ws2 = ws_env ? ws_env[0] == '2' : !l0_same;
+    if (want_ws2 && (C == 32 || C == 64) && (Co == 32 || Co == 64) && H % 16 == 0 && H <= 128 && N <= 8) {
       const int NB = (2 * (2 * H + C) + Co + H <= 512) ? 2 : 1;
       const size_t smem_ws = mlp_bwd_ws2_smem((int)C, (int)H, (int)Co, (int)N, NB);
       if ((int64_t)NB * (2 * H + C) + Co + H <= 512 && smem_ws <= 227 * 1024) {
@@ -2324,12 +2329,12 @@ extern "C" int pcb_mlp_bwd_fused(const void* y, const double* stats, const float
       }
     }
   }
-  // opt-in warp-specialised variant for the level-0 shape (see mlp_bwd_ws_kernel); same workspace layout, P = grid size
+  // warp-specialised variant for the level-0 shape (see mlp_bwd_ws_kernel); same workspace layout, P = grid size
   {
     const char* ws_env = getenv("PCB_BWD_WS");
-    if (ws_env && ws_env[0] == '1' && C == 32 && Co == 32 && H == 64 && mode != PCB_DW_UP && N <= 8 &&
+    if ((ws_env ? ws_env[0] == '1' : true) && C == 32 && Co == 32 && H == 64 && mode != PCB_DW_UP && N <= 8 &&
         mlp_bwd_ws_smem((int)C, (int)H, (int)Co, (int)N) <= 227 * 1024) {
-      static bool conf_ws = false;
+      static DevFlag conf_ws;
       if (!conf_ws) {
         cudaFuncSetAttribute(mlp_bwd_ws_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         conf_ws = cudaFuncSetAttribute(mlp_bwd_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess;
@@ -2428,7 +2433,7 @@ static int tn_gemm_impl(const void* A, const void* B, const double* stats, const
   const int mt = a.Mtot / 128, ncn = (int)((Nb + TN_NCHUNK - 1) / TN_NCHUNK);
   const size_t smem = (size_t)16 * (2048 + 64) + (size_t)((TN_NCHUNK >> 3) + 2) * (2048 + 64) +
                       2 * TN_NCHUNK * sizeof(float) + 64;
-  static bool configured = false;
+  static DevFlag configured;
   if (!configured) {
     cudaFuncSetAttribute(tn_gemm_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (cudaFuncSetAttribute(tn_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
@@ -2458,7 +2463,7 @@ extern "C" int pcb_pw_fwd(const void* A, const void* W, const float* bias, void*
   a.map = map; a.d1 = (int)out_box[1]; a.d2 = (int)out_box[2]; a.s1 = (int)a_size[1]; a.s2 = (int)a_size[2];
   a.Vout = out_box[0] * out_box[1] * out_box[2]; a.Vin = a_size[0] * a_size[1] * a_size[2];
   const size_t smem = (size_t)128 * a.KC * 2 + (size_t)a.NT * a.KC * 2 + 32;
-  static bool configured = false;
+  static DevFlag configured;
   if (!configured) {
     if (cudaFuncSetAttribute(pw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
       set_error("pcb_pw_fwd: cudaFuncSetAttribute failed"); return PCB_ERR_CUDA;

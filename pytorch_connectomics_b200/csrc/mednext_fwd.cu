@@ -768,7 +768,7 @@ static bool launch_dw_down3_tiled(cudaStream_t st, const uint4* x, const float* 
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
   if (!make_brick_tensor_map(&tmap, x, N, a.D, a.H, a.W, a.C, DN_BZ, DN_BY, DN_BX)) return false;
-  static bool configured = false;
+  static DevFlag configured;
   if (!configured) {
     cudaFuncSetAttribute(dwconv_down3_tiled_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (cudaFuncSetAttribute(dwconv_down3_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
@@ -794,7 +794,7 @@ static bool launch_dw_tiled(cudaStream_t st, const uint4* x, const float* w, con
   memset(&tmap, 0, sizeof(tmap));
   static const bool no_tma = getenv("PCB_NO_TMA") != nullptr;
   const int use_tma = !no_tma && make_brick_tensor_map(&tmap, x, N, a.D, a.H, a.W, a.C, DT_Z + 2 * P, DT_Y + 2 * P, DT_X + 2 * P + 1);
-  static bool configured = false;
+  static DevFlag configured;
   if (!configured) {
     cudaFuncSetAttribute(dwconv_same_tiled_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (cudaFuncSetAttribute(dwconv_same_tiled_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
@@ -809,7 +809,7 @@ static bool launch_dw_tiled(cudaStream_t st, const uint4* x, const float* w, con
   static const bool no_persist = getenv("PCB_DW_PERSIST") == nullptr;
   const size_t smem_p = (size_t)2 * (DT_Z + 2 * P) * (DT_Y + 2 * P) * (DT_X + 2 * P + 1) * 64 + (size_t)K * K * K * 32 * 4 + 64 * 8 + 32;
   if (use_tma && !no_persist && smem_p <= 227 * 1024) {
-    static bool configured_p = false;
+    static DevFlag configured_p;
     if (!configured_p) {
       cudaFuncSetAttribute(dwconv_same_persist_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
       configured_p = cudaFuncSetAttribute(dwconv_same_persist_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess;
@@ -1788,7 +1788,7 @@ extern "C" int pcb_mlp_fwd(const void* y, const double* stats, const float* gamm
     const bool pow2 = ((C & (C - 1)) == 0) && ((H & (H - 1)) == 0 || true);
     if (getenv("PCB_NO_FUSED") == nullptr && C <= 64 && H <= 256 && Co <= 128 && (!wr || Cr <= 64) && 2 * (H + Co) <= 512 &&
         N <= 8 && fsm <= 227 * 1024 && pow2 && a.Vout < (1ll << 30) && a.Vin < (1ll << 30)) {
-      static bool fconf = false;
+      static DevFlag fconf;
       if (!fconf) {
         cudaFuncSetAttribute(mlp_fused_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(mlp_fused_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);

@@ -8,7 +8,21 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 namespace pcb {
+
+// Kernel function attributes (dynamic shared-memory opt-in, carveout) are PER DEVICE: a process-wide `static bool`
+// would configure only the first GPU a process launches on, and >48 KB launches on a second GPU would fail with
+// invalid-argument.  DevFlag is a drop-in for such a flag with one atomic slot per device ordinal (configuring twice
+// from two threads is idempotent and harmless).
+struct DevFlag {
+  std::atomic<unsigned char> f[64];
+  DevFlag() { for (auto& x : f) x.store(0); }
+  static int dev() { int d = 0; if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); d = 0; } return (d >= 0 && d < 64) ? d : 0; }
+  operator bool() const { return f[dev()].load(std::memory_order_acquire) != 0; }
+  DevFlag& operator=(bool v) { f[dev()].store(v ? 1 : 0, std::memory_order_release); return *this; }
+};
 
 // ----------------------------------------------------------------------------- error plumbing
 void set_error(const char* fmt, ...);

@@ -5,6 +5,7 @@
 // x-rows, one pass per tensor, no atomics (windows are accumulated in launch order, so fp sums
 // associate exactly like the reference's sequential `+=`).
 #include <math.h>
+#include <string.h>
 #include <vector>
 
 #include "../../include/pcb200.h"
@@ -111,15 +112,46 @@ __device__ __forceinline__ int64_t pad_index(int64_t p, int64_t lo, int64_t hi, 
   return -1;
 }
 
+// Up to SW_MAXB windows per launch.  Window starts come either from the kernel parameters (host-known batch) or from a
+// device-resident table indexed through a device cursor (CUDA-graph replay: the same graph serves every batch; the
+// cursor is advanced by advance_cursor_kernel at the end of the captured body).  A start with z <= SW_SKIP marks a
+// padding slot of the last, partial batch.
+constexpr int SW_MAXB = 16;
+constexpr int64_t SW_SKIP = -(1ll << 40);
+struct WinList {
+  int64_t s[SW_MAXB][3];
+  const int64_t* table;      // device table of (z,y,x) starts, or nullptr
+  const int64_t* cursor;     // device scalar: index of the batch's first window in `table`
+  int64_t total;             // windows in `table`
+  int n;
+};
+__device__ __forceinline__ bool win_start(const WinList& wl, int w, int64_t& z, int64_t& y, int64_t& x) {
+  if (wl.table == nullptr) { z = wl.s[w][0]; y = wl.s[w][1]; x = wl.s[w][2]; return z > SW_SKIP; }
+  const int64_t i = wl.cursor[0] + w;
+  if (i >= wl.total) return false;
+  z = wl.table[3 * i]; y = wl.table[3 * i + 1]; x = wl.table[3 * i + 2];
+  return z > SW_SKIP;
+}
+
 template <typename T>
-__global__ void extract_kernel(const T* __restrict__ vol, T* __restrict__ out, const int64_t* __restrict__ starts,
-                               const int* __restrict__ modes, ExtractArgs a) {
+__global__ void extract_kernel(const T* __restrict__ vol, T* __restrict__ out, WinList wl, ExtractArgs a) {
   const int64_t w = blockIdx.y;  // window in batch
-  const int64_t s0 = starts[3 * w], s1 = starts[3 * w + 1], s2 = starts[3 * w + 2];
-  const int mode = modes[w];
+  int64_t s0, s1, s2;
+  if (!win_start(wl, (int)w, s0, s1, s2)) return;
   const int64_t lo0 = max((int64_t)0, s0), hi0 = min(a.D, s0 + a.r0);
   const int64_t lo1 = max((int64_t)0, s1), hi1 = min(a.H, s1 + a.r1);
   const int64_t lo2 = max((int64_t)0, s2), hi2 = min(a.W, s2 + a.r2);
+  // per-window fallback to constant when a reflect/circular pad >= the cropped dim (window.py:509-518)
+  int mode = a.mode;
+  if (mode == PCB_PAD_REFLECT || mode == PCB_PAD_CIRCULAR) {
+    const int64_t st[3] = {s0, s1, s2}, rr[3] = {a.r0, a.r1, a.r2}, im[3] = {a.D, a.H, a.W};
+    const int64_t lo[3] = {lo0, lo1, lo2}, hi[3] = {hi0, hi1, hi2};
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) {
+      const int64_t before = st[ax] < 0 ? -st[ax] : 0, e = st[ax] + rr[ax], after = e > im[ax] ? e - im[ax] : 0;
+      if (before >= hi[ax] - lo[ax] || after >= hi[ax] - lo[ax]) mode = PCB_PAD_CONSTANT;
+    }
+  }
   const int64_t per = a.C * a.r0 * a.r1 * a.r2;
   const T cv = DT<T>::st(a.cval);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < per; i += (int64_t)gridDim.x * blockDim.x) {
@@ -130,6 +162,10 @@ __global__ void extract_kernel(const T* __restrict__ vol, T* __restrict__ out, c
     if (pz >= 0 && py >= 0 && px >= 0) v = vol[((c * a.D + pz) * a.H + py) * a.W + px];
     out[w * per + i] = v;
   }
+}
+
+__global__ void advance_cursor_kernel(int64_t* cursor, int64_t by) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) cursor[0] += by;
 }
 
 struct AccArgs {
@@ -151,6 +187,58 @@ __global__ void accumulate_kernel(const T* __restrict__ pred, const T* __restric
       const float prod = rnd<T>(__fmul_rn(DT<T>::ld(pred[c * pstride + pi]), w));
       value[c * ostride + oi] = DT<T>::st(__fadd_rn(DT<T>::ld(value[c * ostride + oi]), prod));
     }
+  }
+}
+
+// A batch of FULL windows in one launch, bit-identical to accumulating them one after the other in list order: the
+// thread of (window w, voxel i) owns output voxel o = start_w + i for the WHOLE batch iff w is the first window of the
+// batch that covers o; it then applies every covering window w' >= w in order (value += pred*map, weight += map; mul then
+// add, no FMA).  Each output voxel is touched by exactly one thread: no atomics, no race, the reference's association.
+struct AccBatchArgs {
+  int64_t Cout, r0, r1, r2, o0, o1, o2;
+};
+template <typename T>
+__global__ void accumulate_batch_kernel(const T* __restrict__ pred, const T* __restrict__ map, T* __restrict__ value,
+                                        T* __restrict__ weight, WinList wl, AccBatchArgs a) {
+  __shared__ int64_t sst[SW_MAXB][3];
+  __shared__ int sok[SW_MAXB];
+  if (threadIdx.x < wl.n) {
+    int64_t z, y, x;
+    const bool ok = win_start(wl, threadIdx.x, z, y, x);
+    sok[threadIdx.x] = ok ? 1 : 0;
+    sst[threadIdx.x][0] = z; sst[threadIdx.x][1] = y; sst[threadIdx.x][2] = x;
+  }
+  __syncthreads();
+  const int w = blockIdx.y;
+  if (!sok[w]) return;
+  const int64_t per = a.r0 * a.r1 * a.r2, ostride = a.o0 * a.o1 * a.o2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < per; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t x = i % a.r2, y = (i / a.r2) % a.r1, z = i / (a.r2 * a.r1);
+    const int64_t oz = sst[w][0] + z, oy = sst[w][1] + y, ox = sst[w][2] + x;
+    if (oz < 0 || oz >= a.o0 || oy < 0 || oy >= a.o1 || ox < 0 || ox >= a.o2) continue;
+    bool first = true;
+    for (int u = 0; u < w; ++u) {
+      if (!sok[u]) continue;
+      const int64_t dz = oz - sst[u][0], dy = oy - sst[u][1], dx = ox - sst[u][2];
+      if (dz >= 0 && dz < a.r0 && dy >= 0 && dy < a.r1 && dx >= 0 && dx < a.r2) { first = false; break; }
+    }
+    if (!first) continue;
+    const int64_t oi = (oz * a.o1 + oy) * a.o2 + ox;
+    float wacc = DT<T>::ld(weight[oi]);
+    for (int u = w; u < wl.n; ++u) {
+      if (!sok[u]) continue;
+      const int64_t dz = oz - sst[u][0], dy = oy - sst[u][1], dx = ox - sst[u][2];
+      if (dz < 0 || dz >= a.r0 || dy < 0 || dy >= a.r1 || dx < 0 || dx >= a.r2) continue;
+      const int64_t pi = (dz * a.r1 + dy) * a.r2 + dx;
+      const float m = DT<T>::ld(map[pi]);
+      wacc = rnd<T>(__fadd_rn(wacc, m));
+      const T* pw = pred + (int64_t)u * a.Cout * per + pi;
+      for (int64_t c = 0; c < a.Cout; ++c) {
+        const float prod = rnd<T>(__fmul_rn(DT<T>::ld(pw[c * per]), m));
+        value[c * ostride + oi] = DT<T>::st(__fadd_rn(DT<T>::ld(value[c * ostride + oi]), prod));
+      }
+    }
+    weight[oi] = DT<T>::st(wacc);
   }
 }
 
@@ -242,10 +330,14 @@ static int imap_impl(int blend, const int64_t roi[3], int ndim, double min_value
   float* dk = nullptr;
   const int64_t tot = roi[0] + roi[1] + roi[2];
   if (cudaMallocAsync(&dk, tot * sizeof(float), st) != cudaSuccess) { set_error("imap: cudaMallocAsync failed"); return PCB_ERR_CUDA; }
-  cudaMemcpyAsync(dk, k[0].data(), roi[0] * 4, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(dk + roi[0], k[1].data(), roi[1] * 4, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(dk + roi[0] + roi[1], k[2].data(), roi[2] * 4, cudaMemcpyHostToDevice, st);
-  cudaStreamSynchronize(st);  // host staging vectors die at return (one-off setup call, not the tile loop)
+  if (cudaMemcpyAsync(dk, k[0].data(), roi[0] * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+      cudaMemcpyAsync(dk + roi[0], k[1].data(), roi[1] * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+      cudaMemcpyAsync(dk + roi[0] + roi[1], k[2].data(), roi[2] * 4, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+      cudaStreamSynchronize(st) != cudaSuccess) {  // host staging vectors die at return (one-off setup call, not the tile loop)
+    set_error("imap: staging the axis kernels failed: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFreeAsync(dk, st);
+    return PCB_ERR_CUDA;
+  }
   const int64_t n = roi[0] * roi[1] * roi[2];
   const float mv = min_value > 0 ? rnd<T>((float)min_value) : 0.f;
   imap_kernel<T><<<grid_for(n), 256, 0, st>>>((T*)out, dk, dk + roi[0], dk + roi[0] + roi[1], roi[0], roi[1], roi[2],
@@ -269,39 +361,40 @@ extern "C" int pcb_sw_importance_map(int blend, const int64_t roi[3], int ndim, 
   return PCB_ERR_INVALID;
 }
 
+static int extract_launch(const void* vol, int dtype, int64_t C, const int64_t image[3], const int64_t roi[3],
+                          const WinList& wl, int pad_mode, double cval, void* out, cudaStream_t st) {
+  ExtractArgs a{C, image[0], image[1], image[2], roi[0], roi[1], roi[2], (float)cval, pad_mode};
+  const int64_t per = C * roi[0] * roi[1] * roi[2];
+  dim3 grid(grid_for(per), (unsigned)wl.n);
+  if (dtype == PCB_F32) extract_kernel<float><<<grid, 256, 0, st>>>((const float*)vol, (float*)out, wl, a);
+  else if (dtype == PCB_F16) extract_kernel<__half><<<grid, 256, 0, st>>>((const __half*)vol, (__half*)out, wl, a);
+  else if (dtype == PCB_BF16) extract_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)vol, (__nv_bfloat16*)out, wl, a);
+  else { set_error("pcb_sw_extract: bad dtype %d", dtype); return PCB_ERR_INVALID; }
+  PCB_CHECK_LAUNCH("pcb_sw_extract");
+  return PCB_OK;
+}
+
+static inline size_t dtype_size(int dtype) { return dtype == PCB_F32 ? 4 : 2; }
+
 extern "C" int pcb_sw_extract(const void* vol, int dtype, int64_t C, const int64_t image[3], const int64_t roi[3],
                               const int64_t* starts, int64_t n, int pad_mode, double cval, void* out, void* stream) {
   PCB_CHECK_ARG(vol && image && roi && starts && out, "pcb_sw_extract: null argument");
   PCB_CHECK_ARG(n > 0 && n <= 65535, "pcb_sw_extract: batch of %lld windows unsupported", (long long)n);
   PCB_CHECK_ARG(pad_mode >= 0 && pad_mode <= 3, "pcb_sw_extract: bad padding mode %d", pad_mode);
-  cudaStream_t st = (cudaStream_t)stream;
-  // per-window fallback to constant when a reflect/circular pad >= the cropped dim (window.py:509-518)
-  std::vector<int> modes(n, pad_mode);
-  for (int64_t w = 0; w < n; ++w) {
-    if (pad_mode != PCB_PAD_REFLECT && pad_mode != PCB_PAD_CIRCULAR) break;
-    for (int a = 0; a < 3; ++a) {
-      const int64_t s = starts[3 * w + a], e = s + roi[a];
-      const int64_t lo = s > 0 ? s : 0, hi = e < image[a] ? e : image[a];
-      const int64_t before = s < 0 ? -s : 0, after = e > image[a] ? e - image[a] : 0;
-      if (before >= hi - lo || after >= hi - lo) modes[w] = PCB_PAD_CONSTANT;
-    }
-  }
-  int64_t* dstarts = nullptr;
-  const size_t sb = n * 3 * sizeof(int64_t), mb = n * sizeof(int);
-  if (cudaMallocAsync(&dstarts, sb + mb, st) != cudaSuccess) { set_error("extract: cudaMallocAsync failed"); return PCB_ERR_CUDA; }
-  int* dmodes = (int*)((char*)dstarts + sb);
-  cudaMemcpyAsync(dstarts, starts, sb, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(dmodes, modes.data(), mb, cudaMemcpyHostToDevice, st);
-  cudaStreamSynchronize(st);  // `modes` is a host temporary
-  ExtractArgs a{C, image[0], image[1], image[2], roi[0], roi[1], roi[2], (float)cval, pad_mode};
+  PCB_CHECK_ARG(dtype >= PCB_F32 && dtype <= PCB_BF16, "pcb_sw_extract: bad dtype %d", dtype);
+  // window starts travel as kernel parameters (SW_MAXB per launch): no device allocation, no host->device copy and no
+  // synchronisation in the tile loop — the host can enqueue ahead and the call is CUDA-graph capturable
   const int64_t per = C * roi[0] * roi[1] * roi[2];
-  dim3 grid(grid_for(per), (unsigned)n);
-  if (dtype == PCB_F32) extract_kernel<float><<<grid, 256, 0, st>>>((const float*)vol, (float*)out, dstarts, dmodes, a);
-  else if (dtype == PCB_F16) extract_kernel<__half><<<grid, 256, 0, st>>>((const __half*)vol, (__half*)out, dstarts, dmodes, a);
-  else if (dtype == PCB_BF16) extract_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)vol, (__nv_bfloat16*)out, dstarts, dmodes, a);
-  else { cudaFreeAsync(dstarts, st); set_error("pcb_sw_extract: bad dtype %d", dtype); return PCB_ERR_INVALID; }
-  cudaFreeAsync(dstarts, st);
-  PCB_CHECK_LAUNCH("pcb_sw_extract");
+  for (int64_t b0 = 0; b0 < n; b0 += SW_MAXB) {
+    WinList wl;
+    memset(&wl, 0, sizeof(wl));
+    wl.n = (int)(n - b0 < SW_MAXB ? n - b0 : SW_MAXB);
+    for (int w = 0; w < wl.n; ++w)
+      for (int ax = 0; ax < 3; ++ax) wl.s[w][ax] = starts[3 * (b0 + w) + ax];
+    int rc = extract_launch(vol, dtype, C, image, roi, wl, pad_mode, cval, (char*)out + (size_t)b0 * per * dtype_size(dtype),
+                            (cudaStream_t)stream);
+    if (rc) return rc;
+  }
   return PCB_OK;
 }
 
@@ -323,6 +416,42 @@ extern "C" int pcb_sw_accumulate(const void* pred, const void* map, void* value,
   else if (dtype == PCB_BF16) accumulate_kernel<__nv_bfloat16><<<grid_for(nbox), 256, 0, st>>>((const __nv_bfloat16*)pred, (const __nv_bfloat16*)map, (__nv_bfloat16*)value, (__nv_bfloat16*)weight, a);
   else { set_error("pcb_sw_accumulate: bad dtype %d", dtype); return PCB_ERR_INVALID; }
   PCB_CHECK_LAUNCH("pcb_sw_accumulate");
+  return PCB_OK;
+}
+
+static int accumulate_batch_launch(const void* pred, const void* map, void* value, void* weight, int dtype, int64_t Cout,
+                                   const int64_t roi[3], const int64_t out_size[3], const WinList& wl, cudaStream_t st) {
+  AccBatchArgs a{Cout, roi[0], roi[1], roi[2], out_size[0], out_size[1], out_size[2]};
+  dim3 grid(grid_for(roi[0] * roi[1] * roi[2]), (unsigned)wl.n);
+  if (dtype == PCB_F32) accumulate_batch_kernel<float><<<grid, 256, 0, st>>>((const float*)pred, (const float*)map, (float*)value, (float*)weight, wl, a);
+  else if (dtype == PCB_F16) accumulate_batch_kernel<__half><<<grid, 256, 0, st>>>((const __half*)pred, (const __half*)map, (__half*)value, (__half*)weight, wl, a);
+  else if (dtype == PCB_BF16) accumulate_batch_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)pred, (const __nv_bfloat16*)map, (__nv_bfloat16*)value, (__nv_bfloat16*)weight, wl, a);
+  else { set_error("pcb_sw_accumulate_batch: bad dtype %d", dtype); return PCB_ERR_INVALID; }
+  PCB_CHECK_LAUNCH("pcb_sw_accumulate_batch");
+  return PCB_OK;
+}
+
+extern "C" int pcb_sw_accumulate_batch(const void* pred, const void* map, void* value, void* weight, int dtype, int64_t Cout,
+                                       const int64_t roi[3], const int64_t out_size[3], const int64_t* starts, int64_t n,
+                                       void* stream) {
+  PCB_CHECK_ARG(pred && map && value && weight && roi && out_size && starts, "pcb_sw_accumulate_batch: null argument");
+  PCB_CHECK_ARG(n > 0 && Cout > 0, "pcb_sw_accumulate_batch: empty batch");
+  PCB_CHECK_ARG(dtype >= PCB_F32 && dtype <= PCB_BF16, "pcb_sw_accumulate_batch: bad dtype %d", dtype);
+  for (int64_t w = 0; w < n; ++w)
+    for (int a = 0; a < 3; ++a)
+      PCB_CHECK_ARG(starts[3 * w + a] >= 0 && starts[3 * w + a] + roi[a] <= out_size[a],
+                    "pcb_sw_accumulate_batch: window %lld outside the accumulator", (long long)w);
+  const int64_t per = Cout * roi[0] * roi[1] * roi[2];
+  for (int64_t b0 = 0; b0 < n; b0 += SW_MAXB) {       // launches run in stream order, so list order is preserved
+    WinList wl;
+    memset(&wl, 0, sizeof(wl));
+    wl.n = (int)(n - b0 < SW_MAXB ? n - b0 : SW_MAXB);
+    for (int w = 0; w < wl.n; ++w)
+      for (int ax = 0; ax < 3; ++ax) wl.s[w][ax] = starts[3 * (b0 + w) + ax];
+    int rc = accumulate_batch_launch((const char*)pred + (size_t)b0 * per * dtype_size(dtype), map, value, weight, dtype, Cout,
+                                     roi, out_size, wl, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
   return PCB_OK;
 }
 

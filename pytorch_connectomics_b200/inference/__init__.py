@@ -6,7 +6,10 @@ from .window import (EagerSlidingWindowEngine, apply_border_mask, build_sliding_
                      normalize_weighted_accumulator, resolve_border_mask, resolve_inferer_overlap,
                      resolve_inferer_roi_size, resolve_model_output_dtype)
 
-from .lazy import lazy_predict_region, lazy_predict_volume, lazy_sliding_window, lazy_window_records
+from .lazy import (ArrayVolumeAccessor, build_accessor, lazy_predict_region, lazy_predict_volume, lazy_sliding_window,
+                   lazy_window_records, register_accessor_factory)
+from .artifact import (PredictionArtifactMetadata, build_prediction_artifact_metadata, read_prediction_artifact,
+                       write_prediction_artifact)
 from .chunked import (ChunkRef, build_chunk_grid, chunks_for_rank, resolve_chunk_shape, resolve_external_chunk_shard,
                       resolve_halo_region, run_chunked_prediction, stitch_chunks)
 

@@ -17,7 +17,13 @@ from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch
 
-from .lazy import lazy_predict_region
+import json
+import logging
+from pathlib import Path
+
+from .lazy import lazy_predict_region, lazy_sliding_window
+
+logger = logging.getLogger(__name__)
 
 
 @dataclass(frozen=True)
@@ -105,7 +111,7 @@ def run_chunked_prediction(volume: torch.Tensor, network: Callable, *, chunk_sha
     for _, ch in chunks_for_rank(chunks, rank, world_size):
         if ch.key in out:
             continue
-        out[ch.key] = lazy_predict_region(volume, network, region_start=ch.start, region_stop=ch.stop,
+        out[ch.key] = lazy_sliding_window(volume, network, region_start=ch.start, region_stop=ch.stop,
                                           roi_size=roi_size, overlap=overlap, mode=mode, padding_mode=padding_mode,
                                           cval=cval, sw_batch_size=sw_batch_size, output_dtype=output_dtype,
                                           device=device)
@@ -126,5 +132,108 @@ def stitch_chunks(volume_shape, chunk_shape, parts: Dict[str, torch.Tensor]) -> 
     return out
 
 
-__all__ = ["ChunkRef", "build_chunk_grid", "resolve_halo_region", "resolve_chunk_shape",
+# ----------------------------------------------------------------------------- the reference's per-rank runner
+def _per_chunk_dir(output_path: Path) -> Path:
+    """``chunked.py:50-52``"""
+    return output_path.with_suffix(output_path.suffix + ".chunks")
+
+
+def _chunk_file_path(chunks_dir: Path, chunk: ChunkRef) -> Path:
+    """``chunked.py:55-56``"""
+    return chunks_dir / f"chunk_{chunk.key}.h5"
+
+
+def _write_chunk_index(*, output_path: Path, chunks_dir: Path, chunks, input_shape, final_shape, crop_pad, chunk_shape,
+                       halo, checkpoint_path, world_size) -> Path:
+    """``chunked.py:279-315`` — same keys."""
+    from .artifact import artifact_path
+    index = {
+        "input_shape": list(input_shape), "final_shape": list(final_shape), "chunk_shape": list(chunk_shape),
+        "halo": list(halo), "crop_pad": [list(p) for p in crop_pad],
+        "checkpoint_path": str(checkpoint_path) if checkpoint_path is not None else None, "world_size": world_size,
+        "chunks": [{"key": c.key, "index_zyx": list(c.index), "start_zyx": list(c.start), "stop_zyx": list(c.stop),
+                    "path": str(artifact_path(_chunk_file_path(chunks_dir, c)).relative_to(output_path.parent))}
+                   for c in chunks],
+    }
+    index_path = output_path.with_suffix(output_path.suffix + ".index.json")
+    with open(index_path, "w") as fh:
+        json.dump(index, fh, indent=2)
+    return index_path
+
+
+def _run_chunked_prediction_per_rank(*, cfg, forward_fn, image_path, output_path, checkpoint_path=None, mask_path=None,
+                                     mask_align_to_image: bool = False, requested_head=None, device="cuda", chunks,
+                                     input_shape, final_shape, crop_pad=((0, 0), (0, 0), (0, 0)), crop_before=(0, 0, 0),
+                                     chunk_shape, halo=(0, 0, 0), compression="gzip", h5_spatial_chunks=(64, 64, 64),
+                                     rank: int = 0, world_size: int = 1, qc_streaming_callback=None,
+                                     stitch_output: bool = True, use_distributed_barrier: bool = True) -> Path:
+    """``chunked.py:437-723`` with the same keyword contract: each rank predicts the chunks ``idx % world_size == rank``
+    (halo-extended read box through :func:`lazy_predict_region`, core cropped back out), writes one artifact per chunk
+    under ``<output_path>.chunks/`` (finished chunks are skipped on re-run), ranks meet in a barrier, rank 0 writes
+    ``<output_path>.index.json`` and, with ``stitch_output``, assembles the ``CZYX`` volume at ``output_path``.
+    The CloudVolume ``precomputed`` sink and the prediction/storage-dtype transforms are I/O-side options outside this
+    path (``NotImplementedError`` when configured)."""
+    from .artifact import (artifact_path, build_prediction_artifact_metadata, read_prediction_artifact,
+                           write_prediction_artifact)
+    del qc_streaming_callback
+    output_path = Path(output_path)
+    chunks_dir = _per_chunk_dir(output_path)
+    chunks_dir.mkdir(parents=True, exist_ok=True)
+    if bool(getattr(getattr(getattr(cfg, "inference", None), "chunking", None), "precomputed", False)):
+        raise NotImplementedError("pcb200: the CloudVolume precomputed sink of chunked inference is not implemented")
+    my_chunks = chunks_for_rank(chunks, rank, world_size)
+    logger.info("Per-rank chunked raw prediction: rank=%d/%d, total_chunks=%d, my_chunks=%d, chunk_shape=%s, halo=%s",
+                rank, world_size, len(chunks), len(my_chunks), chunk_shape, halo)
+    for _, chunk in my_chunks:
+        chunk_path = _chunk_file_path(chunks_dir, chunk)
+        if artifact_path(chunk_path).exists():
+            logger.info("[rank %d] chunk %s: already exists, skipping", rank, chunk.key)
+            continue
+        read_lo, read_hi, core = resolve_halo_region(chunk, input_shape, halo=halo, crop_before=crop_before)
+        pred = lazy_predict_region(cfg, forward_fn, image_path, region_start=read_lo, region_stop=read_hi,
+                                   mask_path=mask_path, mask_align_to_image=mask_align_to_image, device=device,
+                                   requested_head=requested_head)
+        core_pred = pred.detach().cpu().numpy()[0][(slice(None), *core)]
+        core_shape = tuple(int(v) for v in core_pred.shape[1:])
+        write_prediction_artifact(
+            chunk_path, core_pred,
+            metadata=build_prediction_artifact_metadata(
+                cfg, image_path=str(image_path) if isinstance(image_path, (str, Path)) else None,
+                checkpoint_path=checkpoint_path, output_head=requested_head,
+                input_shape=tuple(h - l for l, h in zip(read_lo, read_hi)), final_shape=core_shape, chunk_shape=core_shape,
+                halo=halo, intensity_dtype=str(core_pred.dtype),
+                extra={"compression": str(compression), "chunk_key": chunk.key, "chunk_index_zyx": list(chunk.index),
+                       "chunk_start_zyx": list(chunk.start), "chunk_stop_zyx": list(chunk.stop),
+                       "chunk_read_start_zyx": list(read_lo), "chunk_read_stop_zyx": list(read_hi),
+                       "chunk_read_shape_zyx": [h - l for l, h in zip(read_lo, read_hi)]}),
+            compression=compression,
+            chunks=(int(core_pred.shape[0]), *[max(1, min(int(h5_spatial_chunks[a]), core_shape[a])) for a in range(3)]))
+        del pred, core_pred
+    if use_distributed_barrier and torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.barrier()
+    if rank != 0:
+        return chunks_dir
+    _write_chunk_index(output_path=output_path, chunks_dir=chunks_dir, chunks=chunks, input_shape=input_shape,
+                       final_shape=final_shape, crop_pad=crop_pad, chunk_shape=chunk_shape, halo=halo,
+                       checkpoint_path=checkpoint_path, world_size=world_size)
+    if not stitch_output:
+        return chunks_dir
+    first = read_prediction_artifact(_chunk_file_path(chunks_dir, chunks[0]))
+    nch, dt = int(first.shape[0]), first.dtype
+
+    def fill(dset):
+        for c in chunks:
+            dset[(slice(None), *c.slices)] = read_prediction_artifact(_chunk_file_path(chunks_dir, c))
+
+    write_prediction_artifact(output_path, None, shape=(nch, *[int(v) for v in final_shape]), dtype=dt, writer=fill,
+                              metadata=build_prediction_artifact_metadata(
+                                  cfg, image_path=str(image_path) if isinstance(image_path, (str, Path)) else None,
+                                  checkpoint_path=checkpoint_path, output_head=requested_head, input_shape=input_shape,
+                                  final_shape=final_shape, crop_pad=crop_pad, chunk_shape=chunk_shape, halo=halo,
+                                  intensity_dtype=str(dt)),
+                              compression=compression)
+    return output_path
+
+
+__all__ = ["ChunkRef", "_run_chunked_prediction_per_rank", "build_chunk_grid", "resolve_halo_region", "resolve_chunk_shape",
            "resolve_external_chunk_shard", "chunks_for_rank", "run_chunked_prediction", "stitch_chunks"]

@@ -1,32 +1,218 @@
-"""Lazy-grid sliding-window inference over a bounded region — the tile loop of
-``connectomics/inference/lazy.py:986-1258`` (``_lazy_sliding_window`` / ``lazy_predict_region`` /
-``lazy_predict_volume``) on the B200 engine.
+"""Lazy-grid sliding-window inference over a bounded region — ``connectomics/inference/lazy.py`` on the B200 engine.
 
-The reference's lazy path reads windows from disk (h5/zarr/tiff accessors — out of scope, they need
-h5py/zarr) and blends on the CPU.  Here the volume is a tensor (resident in HBM, or pinned host memory
-staged to the GPU once); the grid, the clipped boxes, rank sharding and the accumulate/normalise
-arithmetic follow the reference exactly:
+Two layers:
 
-  * window offsets with face-centred boundary windows (``lazy.py:269-334``, negative starts) from
-    ``pcb_sw_plan(PCB_GRID_LAZY | PCB_GRID_LAZY_SNAP)``, filtered to the windows that intersect the
-    requested region (``:337-365``);
-  * patches are read with the outer padding mode, cast to fp32, run through ``network`` and cast to
-    the output dtype (``:1184-1206``); only the part of each window inside the region is accumulated
-    (``:1077-1102,1216-1227``);
-  * ``rank``/``world_size`` shard the records as ``records[rank::world_size]`` (``:1104``) and
-    ``accumulator_reduce`` sees the un-normalised accumulators (``:1241-1249``).
+* the reference's own seam, callable unchanged by its callers (``inference/chunked.py:541-551``,
+  ``tests/unit/test_lazy_inference.py``): ``lazy_predict_region(cfg, forward_fn, image_path, *, region_start,
+  region_stop, mask_path, mask_align_to_image, device, requested_head)`` and ``lazy_predict_volume(cfg, forward_fn,
+  image_path, *, mask_path, ...)`` (``lazy.py:1261-1334``), driven by ``cfg.inference.sliding_window`` exactly like
+  ``_lazy_sliding_window`` (``:986-1258``): roi / overlap / sw_batch_size / blending / padding_mode / cval /
+  snap_to_edge / ``target_context`` (``:368-419``) / border_mask / ``inference.model.output_dtype``.
+  ``image_path`` is anything :func:`build_accessor` understands: a path to a ``.npy`` volume (memory-mapped; h5/zarr only
+  if those packages import), a ``torch.Tensor`` / ``numpy`` array, or any object with the accessor protocol of
+  ``LazyVolumeAccessor`` (``padded_spatial_shape``, ``channel_count``, ``read_patch(location, patch_size, *,
+  outer_pad_mode, outer_pad_value)``, ``lazy.py:456-918``).  The reference's test-time transforms (resize, transpose,
+  normalisation, tile mosaics) are data-pipeline work outside this path: accessors here serve the stored
+  voxels.
+
+* ``lazy_sliding_window(volume, network, ...)`` — the tile loop itself on a tensor: window offsets with face-centred
+  boundary windows (``lazy.py:269-334``, negative starts) from ``pcb_sw_plan(PCB_GRID_LAZY | PCB_GRID_LAZY_SNAP)``,
+  filtered to the windows that intersect the region (``:337-365``); patches cast to fp32, run through ``network``, cast
+  to the output dtype (``:1184-1206``); only the part of each window inside the region is accumulated
+  (``:1077-1102,1216-1227``); ``rank``/``world_size`` shard the records as ``records[rank::world_size]`` (``:1104``)
+  and ``accumulator_reduce`` sees the un-normalised accumulators (``:1241-1249``).
 """
 
 from __future__ import annotations
 
-from typing import Callable, List, Optional, Sequence, Tuple
+import os
+from typing import Any, Callable, List, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 
 from .. import _lib as L
 from . import window as W
 
 
+# ----------------------------------------------------------------------------- accessors (lazy.py:456-918 protocol)
+def _pad_channel_first(array: np.ndarray, pads, *, mode: str, constant_value: float = 0.0) -> np.ndarray:
+    """``lazy.py:237-256``: numpy padding of a [C, z, y, x] crop (``replicate`` -> ``edge``; reflect on a size-1 axis ->
+    edge)."""
+    if not any(b > 0 or a > 0 for b, a in pads):
+        return array
+    np_mode = "edge" if str(mode).lower() == "replicate" else str(mode).lower()
+    width = [(0, 0)] + [(int(b), int(a)) for b, a in pads]
+    if np_mode == "constant":
+        return np.pad(array, width, mode="constant", constant_values=constant_value)
+    if np_mode == "circular":
+        np_mode = "wrap"
+    if np_mode == "reflect" and any(s <= 1 for s in array.shape[1:]):
+        np_mode = "edge"
+    return np.pad(array, width, mode=np_mode)
+
+
+class ArrayVolumeAccessor:
+    """Accessor over an in-memory or memory-mapped ``[C, D, H, W]`` / ``[D, H, W]`` array (numpy or torch).
+    Same surface the tile loop uses on ``LazyVolumeAccessor``: context manager, ``padded_spatial_shape``,
+    ``channel_count``, ``read_patch`` (fp32 ``[C, *patch_size]``, outer padding as ``lazy.py:852-904``), ``load_full``."""
+
+    def __init__(self, data, *, kind: str = "image", binarize: bool = False, threshold: float = 0.0):
+        if isinstance(data, torch.Tensor):
+            if data.dim() == 5:
+                if data.shape[0] != 1:
+                    raise ValueError(f"expected a [1, C, D, H, W] volume, got {tuple(data.shape)}")
+                data = data[0]
+            if data.dim() == 3:
+                data = data.unsqueeze(0)
+            self._tensor: Optional[torch.Tensor] = data
+            self._array = None
+        else:
+            arr = data
+            if arr.ndim == 5 and arr.shape[0] == 1:
+                arr = arr[0]
+            if arr.ndim == 3:
+                arr = arr[None]
+            self._tensor = None
+            self._array = arr
+        ref = self._tensor if self._tensor is not None else self._array
+        if len(ref.shape) != 4:
+            raise ValueError(f"volume must be [C, D, H, W] or [D, H, W]; got shape {tuple(ref.shape)}")
+        self.kind = kind
+        self.binarize = bool(binarize)
+        self.threshold = float(threshold)
+        self.channel_count = int(ref.shape[0])
+        self.padded_spatial_shape = tuple(int(v) for v in ref.shape[1:])
+        self.transformed_spatial_shape = self.padded_spatial_shape
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+    def close(self) -> None:
+        pass
+
+    def as_tensor(self) -> Optional[torch.Tensor]:
+        """``[1, C, D, H, W]`` view when the whole volume is a tensor (device-resident fast path), else ``None``."""
+        if self._tensor is not None and not self.binarize:
+            return self._tensor.unsqueeze(0)
+        return None
+
+    def _crop(self, lo, hi) -> np.ndarray:
+        sl = (slice(None),) + tuple(slice(int(a), int(b)) for a, b in zip(lo, hi))
+        if self._tensor is not None:
+            return self._tensor[sl].detach().to("cpu", torch.float32).numpy()
+        return np.asarray(self._array[sl], dtype=np.float32)
+
+    def read_patch(self, location, patch_size, *, outer_pad_mode: str, outer_pad_value: float) -> np.ndarray:
+        start = tuple(int(v) for v in location)
+        size = tuple(int(v) for v in patch_size)
+        end = tuple(start[i] + size[i] for i in range(3))
+        lo = tuple(max(0, start[i]) for i in range(3))
+        hi = tuple(min(self.padded_spatial_shape[i], end[i]) for i in range(3))
+        if any(hi[i] <= lo[i] for i in range(3)):
+            inner = np.zeros((self.channel_count, 0, 0, 0), dtype=np.float32)
+            return np.full((self.channel_count, *size), outer_pad_value, dtype=np.float32) if str(outer_pad_mode) == "constant" \
+                else np.zeros((self.channel_count, *size), dtype=np.float32)
+        inner = self._crop(lo, hi)
+        pads = [(max(0, -start[i]), max(0, end[i] - self.padded_spatial_shape[i])) for i in range(3)]
+        patch = _pad_channel_first(inner, pads, mode=outer_pad_mode, constant_value=outer_pad_value)
+        if self.binarize:
+            patch = (patch > self.threshold).astype(np.float32, copy=False)
+        return patch.astype(np.float32, copy=False)
+
+    def load_full(self) -> np.ndarray:
+        return self._crop((0, 0, 0), self.padded_spatial_shape)
+
+
+_ACCESSOR_FACTORIES: List[Callable[..., Any]] = []
+
+
+def register_accessor_factory(factory: Callable[..., Any]) -> None:
+    """``factory(cfg, source, kind=..., mode=...) -> accessor | None``; consulted before the built-in sources (the place a
+    deployment plugs the reference's h5/zarr/tiff ``LazyVolumeAccessor`` in)."""
+    _ACCESSOR_FACTORIES.insert(0, factory)
+
+
+def build_accessor(cfg, source, *, kind: str = "image", mode: str = "test"):
+    """``lazy.py:920-959`` seam: image/mask source -> accessor."""
+    for factory in _ACCESSOR_FACTORIES:
+        acc = factory(cfg, source, kind=kind, mode=mode)
+        if acc is not None:
+            return acc
+    binarize, threshold = False, 0.0
+    if kind == "mask":
+        data_cfg = getattr(cfg, "data", None)
+        mask_cfg = getattr(data_cfg, "mask_transform", None) or getattr(data_cfg, "data_transform", None)
+        binarize = bool(getattr(mask_cfg, "binarize", False))
+        threshold = float(getattr(mask_cfg, "threshold", 0.0))
+    if hasattr(source, "read_patch") and hasattr(source, "padded_spatial_shape"):
+        return source
+    if isinstance(source, (torch.Tensor, np.ndarray)):
+        return ArrayVolumeAccessor(source, kind=kind, binarize=binarize, threshold=threshold)
+    path = os.fspath(source)
+    ext = os.path.splitext(path)[1].lower()
+    if ext == ".npy":
+        return ArrayVolumeAccessor(np.load(path, mmap_mode="r"), kind=kind, binarize=binarize, threshold=threshold)
+    if ext in (".h5", ".hdf5"):
+        try:
+            import h5py  # noqa: F401
+        except ImportError as exc:
+            raise RuntimeError(f"pcb200 lazy inference: reading {path} needs h5py, which is not installed; pass a .npy "
+                               "volume, an array, or register_accessor_factory(...)") from exc
+        f = h5py.File(path, "r")
+        return ArrayVolumeAccessor(f[next(iter(f.keys()))], kind=kind, binarize=binarize, threshold=threshold)
+    raise ValueError(f"pcb200 lazy inference: unsupported volume source {source!r}; expected a .npy path, a tensor/array "
+                     "or an accessor object (register_accessor_factory adds formats).")
+
+
+def get_lazy_image_reference_shape(cfg, image_path, *, mode: str = "test") -> Tuple[int, ...]:
+    """``lazy.py:962-978``."""
+    with build_accessor(cfg, image_path, kind="image", mode=mode) as acc:
+        return (1, int(acc.channel_count), *tuple(int(v) for v in acc.padded_spatial_shape))
+
+
+# ----------------------------------------------------------------------------- target context (lazy.py:368-419)
+def _resolve_target_context(sliding_cfg, roi_size: Sequence[int]) -> Tuple[int, int, int]:
+    context_cfg = list(getattr(sliding_cfg, "target_context", []) or [])
+    if not context_cfg:
+        return (0, 0, 0)
+    if len(context_cfg) == 1:
+        context_cfg = context_cfg * 3
+    if len(context_cfg) != 3:
+        raise ValueError("inference.sliding_window.target_context must have length 1 or 3, "
+                         f"got {context_cfg}.")
+    context = tuple(int(v) for v in context_cfg)
+    if any(v < 0 for v in context):
+        raise ValueError(f"inference.sliding_window.target_context values must be non-negative, got {context}.")
+    if len(tuple(roi_size)) != 3:
+        raise ValueError("Lazy sliding-window target_context currently supports 3D only.")
+    return context
+
+
+def _crop_prediction_to_roi(prediction: torch.Tensor, *, roi_size: Sequence[int], target_context: Sequence[int],
+                            scope: str) -> torch.Tensor:
+    spatial = tuple(int(v) for v in prediction.shape[2:])
+    roi = tuple(int(v) for v in roi_size)
+    context = tuple(int(v) for v in target_context)
+    if not any(context):
+        if spatial != roi:
+            raise RuntimeError(f"{scope} requires model predictions to have the same spatial shape as the "
+                               f"sliding-window ROI. Got prediction.shape={tuple(prediction.shape)} and "
+                               f"roi_size={roi}.")
+        return prediction
+    expected = tuple(roi[a] + 2 * context[a] for a in range(3))
+    if spatial != expected:
+        raise RuntimeError(f"{scope} with target_context={context} expected prediction spatial shape "
+                           f"{expected}, got {spatial}.")
+    sl = [slice(None), slice(None)] + [slice(context[a], context[a] + roi[a]) for a in range(3)]
+    return prediction[tuple(sl)]
+
+
+# ----------------------------------------------------------------------------- grid records
 def lazy_window_records(image_size, roi_size, overlap, region_start, region_stop, snap_to_edge: bool):
     """(patch_start, pred_lo, box, out_lo) per window intersecting the region, in grid order."""
     kind = L.GRID_LAZY_SNAP if snap_to_edge else L.GRID_LAZY
@@ -42,26 +228,15 @@ def lazy_window_records(image_size, roi_size, overlap, region_start, region_stop
     return recs
 
 
-def lazy_sliding_window(volume: torch.Tensor, network: Callable[[torch.Tensor], torch.Tensor], *, roi_size,
-                        overlap=0.5, mode: str = "bump", padding_mode: str = "constant", cval: float = 0.0,
-                        region_start: Optional[Sequence[int]] = None, region_stop: Optional[Sequence[int]] = None,
-                        snap_to_edge: bool = False, sw_batch_size: int = 1, output_dtype: torch.dtype = torch.float32,
-                        border_mask: Sequence[int] = (), rank: int = 0, world_size: int = 1,
-                        accumulator_reduce=None, device=None, normalize: bool = True):
-    """Returns the blended prediction of the region ``[1, Cout, *region]`` on the compute device
-    (or ``(value, weight)`` un-normalised when ``normalize=False``)."""
-    roi = tuple(int(v) for v in roi_size)
-    if len(roi) != 3:
-        raise ValueError(f"Lazy sliding-window inference currently supports 3D only, got {roi}.")
-    if volume.dim() != 5 or volume.shape[0] != 1:
-        raise ValueError(f"expected a [1, C, D, H, W] volume, got {tuple(volume.shape)}")
-    dev = torch.device(device) if device is not None else volume.device
-    W._device_or_raise(dev)
-    vol = volume.to(dev, non_blocking=True)
-    img = tuple(int(v) for v in vol.shape[-3:])
+# ----------------------------------------------------------------------------- the tile loop
+def _lazy_tile_loop(read_batch: Callable[[list], torch.Tensor], predict: Callable[[torch.Tensor, list], torch.Tensor],
+                    *, image_size, roi, overlap, mode, region_start, region_stop, snap_to_edge, sw_batch_size,
+                    output_dtype, border_mask, rank, world_size, accumulator_reduce, dev, normalize, target_context,
+                    what: str = ""):
+    img = tuple(int(v) for v in image_size)
     if any(img[a] < roi[a] for a in range(3)):
-        raise ValueError("Lazy sliding-window inference requires the volume to be at least as large as the ROI "
-                         f"in every axis. Got bounds_shape={img}, roi_size={roi}.")
+        raise ValueError("Lazy sliding-window inference requires the transformed test volume to be at least as large "
+                         f"as the ROI in every axis. Got bounds_shape={img}, roi_size={roi}.")
     start = (0, 0, 0) if region_start is None else tuple(max(0, int(v)) for v in region_start)
     stop = img if region_stop is None else tuple(min(img[a], int(region_stop[a])) for a in range(3))
     if any(stop[a] <= start[a] for a in range(3)):
@@ -70,16 +245,24 @@ def lazy_sliding_window(volume: torch.Tensor, network: Callable[[torch.Tensor], 
     ov = tuple(float(v) for v in overlap) if isinstance(overlap, (list, tuple)) else (float(overlap),) * 3
     recs = lazy_window_records(img, roi, ov, start, stop, snap_to_edge)[rank::world_size]
     if not recs:
-        raise RuntimeError("No lazy sliding-window patches were generated" + (f" on rank {rank}" if world_size > 1 else "."))
+        raise RuntimeError(f"No lazy sliding-window patches were generated{what}" +
+                           (f" on rank {rank}" if world_size > 1 else "."))
     wmap = W.build_sliding_importance_map(roi, mode=mode, device=dev, dtype=output_dtype)
     wmap = W.apply_border_mask(wmap, list(border_mask))
     value = None
     weight = torch.zeros((1, 1, *osz), device=dev, dtype=output_dtype)
-    for b0 in range(0, len(recs), max(1, int(sw_batch_size))):
-        chunk = recs[b0:b0 + sw_batch_size]
-        batch = W._extract_starts(vol, [r[0] for r in chunk], roi, padding_mode, cval)
+    bs = max(1, int(sw_batch_size))
+    for b0 in range(0, len(recs), bs):
+        chunk = recs[b0:b0 + bs]
+        batch = read_batch([r[0] for r in chunk])
         with torch.no_grad():
-            pred = network(batch.float())
+            pred = predict(batch, chunk)
+        if not isinstance(pred, torch.Tensor):
+            raise ValueError(f"lazy sliding-window: `network` must return a torch.Tensor; got {type(pred).__name__}.")
+        pred = _crop_prediction_to_roi(pred, roi_size=roi, target_context=target_context,
+                                       scope="Lazy sliding-window inference")
+        W.check_network_output(pred, len(chunk), None if value is None else int(value.shape[1]), roi,
+                               "lazy sliding-window")
         pred = pred.detach().to(device=dev, dtype=output_dtype).contiguous()
         if value is None:
             value = torch.zeros((1, int(pred.shape[1]), *osz), device=dev, dtype=output_dtype)
@@ -95,14 +278,162 @@ def lazy_sliding_window(volume: torch.Tensor, network: Callable[[torch.Tensor], 
     return W.normalize_weighted_accumulator(value, weight)
 
 
-def lazy_predict_region(volume, network, *, region_start, region_stop, **kw):
-    """``lazy.py:1261-1293`` on an in-memory volume."""
-    return lazy_sliding_window(volume, network, region_start=region_start, region_stop=region_stop, **kw)
+def lazy_sliding_window(volume: torch.Tensor, network: Callable[[torch.Tensor], torch.Tensor], *, roi_size,
+                        overlap=0.5, mode: str = "bump", padding_mode: str = "constant", cval: float = 0.0,
+                        region_start: Optional[Sequence[int]] = None, region_stop: Optional[Sequence[int]] = None,
+                        snap_to_edge: bool = False, sw_batch_size: int = 1, output_dtype: torch.dtype = torch.float32,
+                        border_mask: Sequence[int] = (), rank: int = 0, world_size: int = 1,
+                        accumulator_reduce=None, device=None, normalize: bool = True,
+                        target_context: Sequence[int] = (0, 0, 0)):
+    """Returns the blended prediction of the region ``[1, Cout, *region]`` on the compute device
+    (or ``(value, weight)`` un-normalised when ``normalize=False``)."""
+    roi = tuple(int(v) for v in roi_size)
+    if len(roi) != 3:
+        raise ValueError(f"Lazy sliding-window inference currently supports 3D only, got {roi}.")
+    if volume.dim() != 5 or volume.shape[0] != 1:
+        raise ValueError(f"expected a [1, C, D, H, W] volume, got {tuple(volume.shape)}")
+    dev = torch.device(device) if device is not None else volume.device
+    W._device_or_raise(dev)
+    vol = volume.to(dev, non_blocking=True)
+    ctx = tuple(int(v) for v in target_context)
+    read_size = tuple(roi[a] + 2 * ctx[a] for a in range(3))
+
+    def read_batch(starts):
+        shifted = [tuple(s[a] - ctx[a] for a in range(3)) for s in starts]
+        return W._extract_starts(vol, shifted, read_size, padding_mode, cval)
+
+    return _lazy_tile_loop(read_batch, lambda b, _c: network(b.float()), image_size=vol.shape[-3:], roi=roi,
+                           overlap=overlap, mode=mode, region_start=region_start, region_stop=region_stop,
+                           snap_to_edge=snap_to_edge, sw_batch_size=sw_batch_size, output_dtype=output_dtype,
+                           border_mask=border_mask, rank=rank, world_size=world_size,
+                           accumulator_reduce=accumulator_reduce, dev=dev, normalize=normalize, target_context=ctx)
 
 
-def lazy_predict_volume(volume, network, **kw):
-    """``lazy.py:1295-1334`` on an in-memory volume."""
-    return lazy_sliding_window(volume, network, region_start=None, region_stop=None, **kw)
+# ----------------------------------------------------------------------------- the reference's seam
+def _select_head(pred, requested_head: Optional[str]):
+    """``forward_fn`` may return a tensor, ``{"output": tensor | {head: tensor}, ...}`` or ``{head: tensor}``
+    (``mednext_models.py:54-89,253-273``); ``requested_head`` picks a named head (comma-separated = channel concat)."""
+    if isinstance(pred, torch.Tensor):
+        return pred
+    if isinstance(pred, dict) and "output" in pred:
+        pred = pred["output"]
+        if isinstance(pred, torch.Tensor):
+            return pred
+    if isinstance(pred, dict):
+        if requested_head:
+            names = [n.strip() for n in str(requested_head).split(",") if n.strip()]
+            missing = [n for n in names if n not in pred]
+            if missing:
+                raise ValueError(f"requested_head {missing} not in model outputs {sorted(pred.keys())}")
+            outs = [pred[n] for n in names]
+            return outs[0] if len(outs) == 1 else torch.cat(outs, dim=1)
+        return next(iter(pred.values()))
+    raise ValueError(f"forward_fn must return a tensor or a dict of tensors; got {type(pred).__name__}.")
 
 
-__all__ = ["lazy_window_records", "lazy_sliding_window", "lazy_predict_region", "lazy_predict_volume"]
+def _dist_context():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return True, dist.get_rank(), dist.get_world_size()
+    return False, 0, 1
+
+
+def _lazy_sliding_window_cfg(cfg, forward_fn, image_path, *, region_start, region_stop, mask_path, mask_align_to_image,
+                             device, requested_head, enable_distributed_window_sharding: bool, accumulator_reduce=None):
+    """``lazy.py:986-1258`` with the B200 kernels for map / accumulate / normalise.  Accumulators live on ``device``
+    (the reference keeps them on the CPU); the result is returned on the CPU as the reference does."""
+    del mask_align_to_image          # masks are read on the image grid here (no resize transform in this path)
+    roi_size = W.resolve_inferer_roi_size(cfg)
+    if roi_size is None:
+        raise ValueError("Lazy sliding-window inference requires inference.sliding_window.window_size "
+                         "or model.output_size to be configured.")
+    if len(roi_size) != 3:
+        raise ValueError(f"Lazy sliding-window inference currently supports 3D only, got {roi_size}.")
+    roi = tuple(int(v) for v in roi_size)
+    overlap = W.resolve_inferer_overlap(cfg, roi)
+    sc = getattr(getattr(cfg, "inference", None), "sliding_window", None)
+    loader = getattr(getattr(cfg, "data", None), "dataloader", None)
+    sw_batch_size = max(1, int(getattr(sc, "sw_batch_size", None) or getattr(loader, "batch_size", 1) or 1))
+    mode = str(getattr(sc, "blending", "bump")).strip().lower()
+    pad_mode = getattr(sc, "padding_mode", "constant")
+    cval = float(getattr(sc, "cval", 0.0))
+    snap = bool(getattr(sc, "snap_to_edge", False))
+    ctx = _resolve_target_context(sc, roi)
+    read_size = tuple(roi[a] + 2 * ctx[a] for a in range(3))
+    dev = torch.device(device)
+    if dev.type == "cuda" and dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    W._device_or_raise(dev)
+    _, rank, world = _dist_context()
+    if not enable_distributed_window_sharding:
+        rank, world = 0, 1
+    border_mask = W.resolve_border_mask(cfg, 3)
+    output_dtype = W.resolve_model_output_dtype(cfg)
+
+    with build_accessor(cfg, image_path, kind="image", mode="test") as image_acc:
+        mask_acc = build_accessor(cfg, mask_path, kind="mask", mode="test") if mask_path is not None else None
+        try:
+            resident = image_acc.as_tensor() if hasattr(image_acc, "as_tensor") else None
+            if resident is not None and str(pad_mode) == "constant":
+                vol = resident.to(dev, non_blocking=True)       # whole volume resident in HBM: gather windows on the GPU
+
+                def read_batch(starts):
+                    shifted = [tuple(s[a] - ctx[a] for a in range(3)) for s in starts]
+                    return W._extract_starts(vol, shifted, read_size, "constant", cval).float()
+            else:
+                def read_batch(starts):                          # disk / host -> pinned -> H2D, one batch at a time
+                    patches = [image_acc.read_patch(tuple(s[a] - ctx[a] for a in range(3)), read_size,
+                                                    outer_pad_mode=pad_mode, outer_pad_value=cval) for s in starts]
+                    host = torch.from_numpy(np.stack(patches, axis=0)).pin_memory()
+                    return host.to(dev, non_blocking=True)
+
+            def predict(batch, chunk):
+                pred = _select_head(forward_fn(batch), requested_head)
+                if mask_acc is not None:
+                    masks = [mask_acc.read_patch(tuple(r[0][a] - ctx[a] for a in range(3)), read_size,
+                                                 outer_pad_mode="constant", outer_pad_value=0.0) for r in chunk]
+                    m = torch.from_numpy(np.stack(masks, axis=0)).to(dev, non_blocking=True)
+                    if m.shape[1] not in (1, pred.shape[1]):
+                        raise ValueError(f"Mask channels {m.shape[1]} incompatible with prediction channels "
+                                         f"{pred.shape[1]}")
+                    pred = pred * (m > 0).to(pred.dtype)
+                return pred
+
+            out = _lazy_tile_loop(read_batch, predict, image_size=image_acc.padded_spatial_shape, roi=roi, overlap=overlap,
+                                  mode=mode, region_start=region_start, region_stop=region_stop, snap_to_edge=snap,
+                                  sw_batch_size=sw_batch_size, output_dtype=output_dtype, border_mask=border_mask,
+                                  rank=rank, world_size=world, accumulator_reduce=accumulator_reduce, dev=dev,
+                                  normalize=True, target_context=ctx, what=f" for {image_path!r}" if isinstance(image_path, (str, os.PathLike)) else "")
+        finally:
+            if mask_acc is not None:
+                mask_acc.close()
+    return out.cpu() if out.numel() else out
+
+
+def lazy_predict_region(cfg, forward_fn, image_path, *, region_start: Sequence[int], region_stop: Sequence[int],
+                        mask_path=None, mask_align_to_image: bool = False, device="cuda",
+                        requested_head: Optional[str] = None) -> torch.Tensor:
+    """``lazy.py:1261-1293`` — one bounded region (transformed/padded ZYX coordinates); windows come from the full-volume
+    grid, so region boundaries see real neighbouring data."""
+    return _lazy_sliding_window_cfg(cfg, forward_fn, image_path, region_start=region_start, region_stop=region_stop,
+                                    mask_path=mask_path, mask_align_to_image=mask_align_to_image, device=device,
+                                    requested_head=requested_head, enable_distributed_window_sharding=False)
+
+
+def lazy_predict_volume(cfg, forward_fn, image_path, *, mask_path=None, mask_align_to_image: bool = False,
+                        device="cuda", requested_head: Optional[str] = None) -> torch.Tensor:
+    """``lazy.py:1295-1334`` — the whole volume; with ``inference.sliding_window.distributed_sharding`` inside an
+    initialised process group the windows are sharded ``[rank::world]`` and the accumulators reduced onto rank 0
+    (non-root ranks get an empty tensor back)."""
+    from .lazy_distributed import make_accumulator_reducer, should_shard_windows
+    sc = getattr(getattr(cfg, "inference", None), "sliding_window", None)
+    distributed = should_shard_windows(bool(getattr(sc, "distributed_sharding", False)))
+    reducer = make_accumulator_reducer() if distributed else None
+    return _lazy_sliding_window_cfg(cfg, forward_fn, image_path, region_start=None, region_stop=None,
+                                    mask_path=mask_path, mask_align_to_image=mask_align_to_image, device=device,
+                                    requested_head=requested_head, enable_distributed_window_sharding=distributed,
+                                    accumulator_reduce=reducer)
+
+
+__all__ = ["ArrayVolumeAccessor", "build_accessor", "register_accessor_factory", "get_lazy_image_reference_shape",
+           "lazy_window_records", "lazy_sliding_window", "lazy_predict_region", "lazy_predict_volume"]

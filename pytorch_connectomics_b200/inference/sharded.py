@@ -152,11 +152,19 @@ class ZSlabShardedEngine:
         self.world = world if world is not None else (dist.get_world_size(group) if use_dist else 1)
 
     # ---- phase 1: my windows -> local slab accumulators
-    def accumulate_local(self, inputs: torch.Tensor, network: Callable[[torch.Tensor], torch.Tensor], plan: SlabPlan):
+    def accumulate_local(self, inputs: torch.Tensor, network: Callable[[torch.Tensor], torch.Tensor], plan: SlabPlan,
+                         presliced: bool = False):
+        """``inputs`` is the whole volume (only this rank's z-range is copied to the GPU) or, with ``presliced``, the
+        slab ``[1, C, plan.slab extent, H, W]`` itself (host or device)."""
         roi = self.roi
         dev = W._device_or_raise(self.device if self.device is not None else inputs.device)
         z0, z1 = plan.slab
-        vol = inputs[:, :, z0:z1].to(dev, non_blocking=True)
+        if presliced:
+            if int(inputs.shape[2]) != z1 - z0:
+                raise ValueError(f"ZSlabShardedEngine: slab has {int(inputs.shape[2])} planes, the plan needs {z1 - z0}")
+            vol = inputs.to(dev, non_blocking=True)
+        else:
+            vol = inputs[:, :, z0:z1].to(dev, non_blocking=True)
         local_image = (z1 - z0, plan.image[1], plan.image[2])
         starts = [(s[0] - z0, s[1], s[2]) for s in plan.windows]
         value = weight = wmap = None
@@ -165,18 +173,28 @@ class ZSlabShardedEngine:
             batch = W._extract_starts(vol, chunk, roi, self.padding_mode, self.cval)
             with torch.no_grad():
                 out = network(batch)
-            if not isinstance(out, torch.Tensor):
-                raise ValueError("ZSlabShardedEngine: `network` must return a torch.Tensor; "
-                                 f"got {type(out).__name__}.")
+            W.check_network_output(out, len(chunk), None if value is None else int(value.shape[1]), roi,
+                                   "ZSlabShardedEngine")
             if value is None:
                 cout, odt = int(out.shape[1]), out.dtype
                 wmap = W.build_sliding_importance_map(roi, mode=self.mode, device=dev, dtype=odt)
                 value = torch.zeros((1, cout, *local_image), device=dev, dtype=odt)
                 weight = torch.zeros((1, 1, *local_image), device=dev, dtype=odt)
             out = out.to(device=dev, dtype=value.dtype).contiguous()
-            for i, st in enumerate(chunk):
-                W._accumulate_window(out[i], wmap, value, weight, roi, local_image, (0, 0, 0), st, roi)
+            W._accumulate_batch(out, wmap, value, weight, roi, local_image, chunk)
         return value, weight
+
+    def run_slab(self, slab: torch.Tensor, network: Callable[[torch.Tensor], torch.Tensor], plan: SlabPlan):
+        """One rank's share given only ITS slab of the volume (what a loader that reads per-rank z-ranges hands over):
+        windows -> neighbour exchange -> normalised own planes (``None`` for a rank without windows)."""
+        if not plan.windows:
+            if self.world > 1:
+                exchange_overlaps(torch.empty(0), torch.empty(0), plan, self.group)
+            return None
+        value, weight = self.accumulate_local(slab, network, plan, presliced=True)
+        if self.world > 1:
+            exchange_overlaps(value, weight, plan, self.group)
+        return self.finalize(value, weight, plan)
 
     # ---- phase 3: normalise my own planes
     @staticmethod

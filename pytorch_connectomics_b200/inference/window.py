@@ -337,11 +337,49 @@ def _accumulate_window(pred: torch.Tensor, wmap: torch.Tensor, value: torch.Tens
                 "pcb_sw_accumulate")
 
 
+def _accumulate_batch(pred: torch.Tensor, wmap: torch.Tensor, value: torch.Tensor, weight: torch.Tensor,
+                      roi, out_size, starts) -> None:
+    """``window.py:641-655`` for one network batch: every full window of ``pred`` [n,Cout,*roi] in ONE launch per 16
+    windows, bit-identical to the per-window loop in list order (``pcb_sw_accumulate_batch``)."""
+    flat = []
+    for s in starts:
+        flat += _pad3(s, 0)
+    with torch.cuda.device(value.device):
+        L.check(L.lib().pcb_sw_accumulate_batch(L.ptr(pred), L.ptr(wmap), L.ptr(value), L.ptr(weight),
+                                                L.dtype_code(value.dtype), ctypes.c_int64(int(value.shape[1])),
+                                                L.i64x(_pad3(roi, 1)), L.i64x(_pad3(out_size, 1)), L.i64x(flat),
+                                                ctypes.c_int64(len(starts)), L.stream_ptr(value.device)),
+                "pcb_sw_accumulate_batch")
+
+
+def check_network_output(out, n: int, cout: Optional[int], roi, who: str) -> torch.Tensor:
+    """The kernels read ``out`` through raw pointers as [n, cout, *roi]; the reference would fail with a broadcast error
+    for anything else (``window.py:648-655``), so refuse it here instead of reading out of bounds."""
+    if not isinstance(out, torch.Tensor):
+        raise ValueError(f"{who}: `network` must return a torch.Tensor; got {type(out).__name__}.")
+    want_tail = tuple(int(v) for v in roi)
+    ok = out.dim() == len(want_tail) + 2 and int(out.shape[0]) == n and tuple(int(v) for v in out.shape[2:]) == want_tail
+    if ok and cout is not None:
+        ok = int(out.shape[1]) == cout
+    if not ok:
+        want = (n, cout if cout is not None else "Cout") + want_tail
+        raise ValueError(f"{who}: `network` returned shape {tuple(out.shape)} for a batch of {n} windows; expected "
+                         f"{want} (window-sized outputs with a fixed channel count).")
+    return out
+
+
 class EagerSlidingWindowEngine:
-    """``window.py:530-683`` — ``engine(inputs=[1,C,*spatial], network=fn) -> [1,Cout,*spatial]``."""
+    """``window.py:530-683`` — ``engine(inputs=[1,C,*spatial], network=fn) -> [1,Cout,*spatial]``.
+
+    Device-resident volumes run as one pass over the eager grid.  HOST volumes (``keep_input_on_cpu`` /
+    ``output_device='cpu'``, ``window.py:413-461``) are STREAMED: the z-starts of the grid are processed in groups, the
+    input planes of the next group travel host -> pinned staging -> HBM on a side stream while the current group computes,
+    finished output planes are normalised and sent back through pinned memory, and the partial planes shared with the
+    next group are carried over in place — HBM holds two input slabs and one accumulator slab instead of the volume and
+    both accumulators, and the fp sums still associate in grid order (bit-identical to the one-pass result)."""
 
     def __init__(self, *, roi_size, sw_batch_size: int, overlap, mode: str, padding_mode: str, cval: float,
-                 sw_device=None, output_device=None, progress: bool = False) -> None:
+                 sw_device=None, output_device=None, progress: bool = False, stream_z_starts: int = 0) -> None:
         self.roi_size = tuple(int(v) for v in roi_size)
         self.sw_batch_size = max(1, int(sw_batch_size))
         self.overlap = overlap
@@ -351,6 +389,41 @@ class EagerSlidingWindowEngine:
         self.sw_device = sw_device
         self.output_device = output_device
         self.progress = bool(progress)
+        self.stream_z_starts = int(stream_z_starts)     # z-starts per streamed group (0 = auto: 4)
+
+    # ---- one pass over `starts` on a device-resident volume, into given (or new) accumulators
+    def _run_windows(self, vol, network, starts, image, sw_device, work_device, value=None, weight=None, wmap=None,
+                     probe_first=True):
+        roi = self.roi_size
+        state = {"value": value, "weight": weight, "wmap": wmap}
+
+        def run(batch_starts):
+            batch = _extract_starts(vol, batch_starts, roi, self.padding_mode, self.cval)
+            if batch.device != sw_device:
+                batch = batch.to(sw_device, non_blocking=True)
+            with torch.no_grad():
+                return network(batch)
+
+        def blend(out, batch_starts) -> None:
+            if state["value"] is None:
+                check_network_output(out, len(batch_starts), None, roi, "EagerSlidingWindowEngine")
+                cout, odt = int(out.shape[1]), out.dtype
+                state["wmap"] = build_sliding_importance_map(roi, mode=self.mode, device=work_device, dtype=odt)
+                state["value"] = torch.zeros((1, cout, *image), device=work_device, dtype=odt)
+                state["weight"] = torch.zeros((1, 1, *image), device=work_device, dtype=odt)
+            v = state["value"]
+            check_network_output(out, len(batch_starts), int(v.shape[1]), roi, "EagerSlidingWindowEngine")
+            out = out.to(device=work_device, dtype=v.dtype).contiguous()
+            _accumulate_batch(out, state["wmap"], v, state["weight"], roi, image, batch_starts)
+
+        rest = starts
+        if probe_first and starts:          # the reference probes with the first window alone (window.py:612-639)
+            blend(run(starts[:1]), starts[:1])
+            rest = starts[1:]
+        for b0 in range(0, len(rest), self.sw_batch_size):
+            chunk = rest[b0:b0 + self.sw_batch_size]
+            blend(run(chunk), chunk)
+        return state["value"], state["weight"], state["wmap"]
 
     def __call__(self, inputs: torch.Tensor, network: Callable[[torch.Tensor], torch.Tensor]) -> torch.Tensor:
         roi = self.roi_size
@@ -363,51 +436,116 @@ class EagerSlidingWindowEngine:
         original = tuple(int(v) for v in inputs.shape[-nd:])
         sw_device = torch.device(self.sw_device) if self.sw_device else inputs.device
         output_device = torch.device(self.output_device) if self.output_device else inputs.device
-        # the tile loop (crop, blend, normalise) always runs on the GPU; a CPU volume is staged there once
+        # the tile loop (crop, blend, normalise) always runs on the GPU
         work_device = sw_device if sw_device.type == "cuda" else (
             inputs.device if inputs.is_cuda else output_device)
         _device_or_raise(work_device)
-        vol = inputs.to(work_device, non_blocking=True)
-
         grow = [max(0, roi[a] - original[a]) for a in range(nd)]
+        if (not inputs.is_cuda) and nd == 3 and not any(grow) and original[0] > roi[0]:
+            return self._call_streamed(inputs, network, sw_device, work_device, output_device)
+        vol = inputs.to(work_device, non_blocking=True)
         if any(grow):  # constant pad up to the ROI (window.py:583-601): one padded-window gather
             grown = tuple(original[a] + grow[a] for a in range(nd))
             vol = _extract_starts(vol, [(0,) * nd], grown, "constant", self.cval)
         image = tuple(int(v) for v in vol.shape[-nd:])
         starts = _plan(L.GRID_EAGER, image, roi, self.overlap)
-
-        def run(batch_starts):
-            batch = _extract_starts(vol, batch_starts, roi, self.padding_mode, self.cval)
-            if batch.device != sw_device:
-                batch = batch.to(sw_device, non_blocking=True)
-            with torch.no_grad():
-                return network(batch)
-
-        probe = run(starts[:1])
-        if not isinstance(probe, torch.Tensor):
-            raise ValueError("EagerSlidingWindowEngine: `network` must return a torch.Tensor; "
-                             f"got {type(probe).__name__}.")
-        cout, odt = int(probe.shape[1]), probe.dtype
-        wmap = build_sliding_importance_map(roi, mode=self.mode, device=work_device, dtype=odt)
-        value = torch.zeros((1, cout, *image), device=work_device, dtype=odt)
-        weight = torch.zeros((1, 1, *image), device=work_device, dtype=odt)
-        zero, full = (0,) * nd, roi
-
-        def blend(out: torch.Tensor, batch_starts) -> None:
-            out = out.to(device=work_device, dtype=odt).contiguous()
-            for i, st in enumerate(batch_starts):
-                _accumulate_window(out[i], wmap, value, weight, roi, image, zero, st, full)
-
-        blend(probe[0:1], starts[:1])
-        rest = starts[1:]
-        for b0 in range(0, len(rest), self.sw_batch_size):
-            chunk = rest[b0:b0 + self.sw_batch_size]
-            blend(run(chunk), chunk)
-
+        value, weight, _ = self._run_windows(vol, network, starts, image, sw_device, work_device)
         out = normalize_weighted_accumulator(value, weight)
         if any(grow):
             out = out[(slice(None), slice(None)) + tuple(slice(0, original[a]) for a in range(nd))].contiguous()
         return out if out.device == output_device else out.to(output_device)
+
+    # ---- host volume: z-slab streaming with double-buffered H2D on a side stream
+    def _call_streamed(self, inputs, network, sw_device, work_device, output_device):
+        roi = self.roi_size
+        image = tuple(int(v) for v in inputs.shape[-3:])
+        cin = int(inputs.shape[1])
+        starts = _plan(L.GRID_EAGER, image, roi, self.overlap)
+        zs = sorted({s[0] for s in starts})
+        g = self.stream_z_starts if self.stream_z_starts > 0 else 4
+        groups = [zs[i:i + g] for i in range(0, len(zs), g)]
+        depth = max(gz[-1] + roi[0] - gz[0] for gz in groups)
+        main = torch.cuda.current_stream(work_device)
+        side = torch.cuda.Stream(device=work_device)
+        src = inputs if inputs.is_contiguous() else inputs.contiguous()
+        pinned_src = src.is_pinned()
+        stage = None if pinned_src else [torch.empty((1, cin, depth, image[1], image[2]), dtype=src.dtype).pin_memory()
+                                         for _ in range(2)]
+        dbuf = [torch.empty((1, cin, depth, image[1], image[2]), device=work_device, dtype=src.dtype) for _ in range(2)]
+        ready = [torch.cuda.Event(), torch.cuda.Event()]          # slab i is in HBM
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]       # the windows of the group reading dbuf[i] are enqueued+done
+        staged = [None, None]                                     # H2D out of stage[i] finished (host may refill it)
+
+        def upload(gi):
+            b = gi % 2
+            z0, z1 = groups[gi][0], groups[gi][-1] + roi[0]
+            if stage is not None:
+                if staged[b] is not None:
+                    staged[b].synchronize()
+                stage[b][:, :, :z1 - z0].copy_(src[:, :, z0:z1])              # pageable -> pinned (host memcpy)
+                host = stage[b][:, :, :z1 - z0]
+            else:
+                host = src[:, :, z0:z1]
+            with torch.cuda.stream(side):
+                side.wait_event(consumed[b])                                   # do not overwrite a slab still being read
+                dbuf[b][:, :, :z1 - z0].copy_(host, non_blocking=True)
+                ready[b].record(side)
+                if stage is not None:
+                    staged[b] = torch.cuda.Event()
+                    staged[b].record(side)
+
+        for ev in consumed:
+            ev.record(main)
+        upload(0)
+        out_host = None
+        value = weight = wmap = None
+        done_ev = None
+        out_lo = 0
+        for gi, gz in enumerate(groups):
+            b = gi % 2
+            if gi + 1 < len(groups):
+                upload(gi + 1)                 # next slab's H2D overlaps this group's windows
+            z0, z1 = gz[0], gz[-1] + roi[0]
+            local_image = (z1 - z0, image[1], image[2])
+            main.wait_event(ready[b])
+            vol = dbuf[b][:, :, :z1 - z0]
+            mine = [(s[0] - z0, s[1], s[2]) for s in starts if gz[0] <= s[0] <= gz[-1]]     # grid order preserved
+            carry = None
+            if value is not None:              # partial planes shared with the previous group go first (same fp order)
+                pz0 = groups[gi - 1][0]
+                keep = groups[gi - 1][-1] + roi[0] - z0
+                if keep > 0:
+                    carry = (value[:, :, z0 - pz0:z0 - pz0 + keep], weight[:, :, z0 - pz0:z0 - pz0 + keep], keep)
+            if value is not None:              # fresh accumulators for this group's z-extent (+ the carried head)
+                nv = torch.zeros((1, value.shape[1], *local_image), device=work_device, dtype=value.dtype)
+                nw = torch.zeros((1, 1, *local_image), device=work_device, dtype=value.dtype)
+                if carry is not None:
+                    nv[:, :, :carry[2]].copy_(carry[0])
+                    nw[:, :, :carry[2]].copy_(carry[1])
+                value, weight = nv, nw
+            value, weight, wmap = self._run_windows(vol, network, mine, local_image, sw_device, work_device, value, weight,
+                                                    wmap, probe_first=(gi == 0))
+            consumed[b].record(main)
+            # planes no later group touches are final: normalise and ship them
+            final_hi = image[0] if gi + 1 == len(groups) else groups[gi + 1][0]
+            lo, hi = out_lo - z0, final_hi - z0
+            if hi > lo:
+                part = normalize_weighted_accumulator(value[:, :, lo:hi].contiguous(), weight[:, :, lo:hi].contiguous())
+                if output_device.type == "cuda":
+                    if out_host is None:
+                        out_host = torch.empty((1, value.shape[1], *image), device=output_device, dtype=value.dtype)
+                    out_host[:, :, out_lo:final_hi].copy_(part, non_blocking=True)
+                else:
+                    if out_host is None:
+                        out_host = torch.empty((1, value.shape[1], *image), dtype=value.dtype).pin_memory()
+                    out_host[:, :, out_lo:final_hi].copy_(part, non_blocking=True)
+                    done_ev = torch.cuda.Event()
+                    done_ev.record(main)
+            out_lo = final_hi
+        if done_ev is not None:
+            done_ev.synchronize()
+        main.wait_stream(side)
+        return out_host
 
 
 def build_sliding_inferer(cfg) -> Optional[EagerSlidingWindowEngine]:

@@ -1,3 +1,4 @@
 """Data-parallel training step plumbing (DDP seam, ``training/lightning/trainer.py:231-256``)."""
-from .ddp import FlatGradArena, allreduce_gradients  # noqa: F401
+from .ddp import FlatGradArena, allreduce_gradients, broadcast_parameters  # noqa: F401
 from .graph import GraphedTrainStep  # noqa: F401
+from .optim import FusedAdamW, build_fused_adamw, reference_param_groups  # noqa: F401

@@ -37,6 +37,37 @@ class FlatGradArena:
         """Use instead of ``optimizer.zero_grad()`` (which would detach the views when set_to_none)."""
         self.buffer.zero_()
 
+    def zero_grad(self, set_to_none: bool = False) -> None:
+        """``optimizer.zero_grad`` / ``model.zero_grad`` shim: zeroes the arena and keeps every ``.grad`` a view of it
+        (``set_to_none`` is accepted and ignored — detaching the views is exactly what must not happen)."""
+        del set_to_none
+        self.rebind()
+        self.buffer.zero_()
+
+    def patch_zero_grad(self, optimizer: torch.optim.Optimizer) -> None:
+        """Route ``optimizer.zero_grad()`` (Lightning calls it every step with ``set_to_none=True``) to the arena."""
+        optimizer.zero_grad = self.zero_grad  # type: ignore[method-assign]
+
+    def gather_stray_grads(self) -> int:
+        """If something replaced a ``.grad`` view (``zero_grad(set_to_none=True)`` followed by a backward pass leaves
+        autograd-allocated tensors), copy those gradients into the arena and re-attach the views, so the exchange step
+        never reduces a stale buffer.  Returns the number of repaired parameters."""
+        off, fixed = 0, 0
+        for p in self.params:
+            n = p.numel()
+            view = self.buffer[off:off + n].view_as(p)
+            g = p.grad
+            if g is None:
+                view.zero_()
+                p.grad = view
+                fixed += 1
+            elif g.data_ptr() != view.data_ptr():
+                view.copy_(g)
+                p.grad = view
+                fixed += 1
+            off += n
+        return fixed
+
     def rebind(self) -> None:
         """Re-attach ``.grad`` views if something replaced them (e.g. ``zero_grad(set_to_none=True)``)."""
         off = 0
@@ -60,8 +91,21 @@ class FlatGradArena:
             self.buffer.mul_(1.0 / self._world(group))
 
     def allreduce(self, group: Optional[dist.ProcessGroup] = None) -> None:
+        self.gather_stray_grads()       # host-side pointer checks; copies only when a view was replaced
         self.allreduce_sum(group)
         self.scale_mean(group)
+
+
+def broadcast_parameters(module: torch.nn.Module, src: int = 0, group: Optional[dist.ProcessGroup] = None) -> None:
+    """What ``DistributedDataParallel`` does at construction (``trainer.py:231-256`` builds a ``DDPStrategy``): every
+    rank starts from rank ``src``'s parameters AND buffers (BatchNorm running statistics of ``monai_unet``), so replicas
+    that average gradients are replicas of the same model.  No-op without an initialised process group / world 1."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    with torch.no_grad():
+        for t in list(module.parameters()) + list(module.buffers()):
+            if t.is_floating_point() or t.dtype in (torch.int64, torch.int32):
+                dist.broadcast(t.data, src=src, group=group)
 
 
 def allreduce_gradients(arena: FlatGradArena, group: Optional[dist.ProcessGroup] = None) -> None:

@@ -216,17 +216,23 @@ def _ddp_worker(rank, world, port, q):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from pytorch_connectomics_b200.training import FlatGradArena
-    torch.manual_seed(0)
-    net = torch.nn.Sequential(torch.nn.Linear(4, 8), torch.nn.ReLU(), torch.nn.Linear(8, 2), torch.nn.Linear(2, 2))
-    for p in net[3].parameters():          # an unused head: never receives a gradient (find_unused_parameters)
-        pass
+    from pytorch_connectomics_b200.training import FlatGradArena, broadcast_parameters
+    torch.manual_seed(rank)                # ranks start from DIFFERENT weights ...
+    net = torch.nn.Sequential(torch.nn.Linear(4, 8), torch.nn.ReLU(), torch.nn.Linear(8, 2), torch.nn.Linear(2, 2),
+                              torch.nn.BatchNorm1d(2))
+    net[4].running_mean.fill_(float(rank))
+    broadcast_parameters(net, src=0)       # ... and rank 0's parameters AND buffers win (DDP construction semantics)
     arena = FlatGradArena(net.parameters())
     x = torch.full((3, 4), float(rank + 1))
-    arena.zero()
+    if rank == 1:                          # Lightning-style zero_grad detaches the views: the arena must repair them
+        net.zero_grad(set_to_none=True)
+    else:
+        arena.zero()
     net[2](net[1](net[0](x))).sum().backward()
     arena.allreduce()
-    q.put((rank, arena.buffer.clone().numpy()))   # by value: torch tensors travel as fds that die with the worker
+    assert all(p.grad is not None and p.grad.data_ptr() >= arena.buffer.data_ptr() for p in net.parameters())
+    q.put((rank, arena.buffer.clone().numpy(), torch.cat([p.detach().reshape(-1) for p in net.parameters()]).numpy(),
+           float(net[4].running_mean[0])))   # by value: torch tensors travel as fds that die with the worker
     dist.destroy_process_group()
 
 
@@ -239,20 +245,24 @@ def test_flat_arena_allreduce_gloo_world2():
     procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = {r: torch.from_numpy(v) for r, v in (q.get(timeout=300) for _ in range(2))}
+    got = [q.get(timeout=300) for _ in range(2)]
+    res = {r: torch.from_numpy(v) for r, v, _, _ in got}
+    par = {r: torch.from_numpy(w) for r, _, w, _ in got}
     for p in procs:
         p.join(timeout=60)
+    assert torch.equal(par[0], par[1]) and all(rm == 0.0 for _, _, _, rm in got)   # broadcast: params and buffers of rank 0
     assert torch.equal(res[0], res[1])                      # identical averaged gradients on both ranks
     # reference: mean of the two per-rank gradients computed in-process
     torch.manual_seed(0)
-    net = torch.nn.Sequential(torch.nn.Linear(4, 8), torch.nn.ReLU(), torch.nn.Linear(8, 2), torch.nn.Linear(2, 2))
+    net = torch.nn.Sequential(torch.nn.Linear(4, 8), torch.nn.ReLU(), torch.nn.Linear(8, 2), torch.nn.Linear(2, 2),
+                              torch.nn.BatchNorm1d(2))
     gs = []
     for r in range(2):
         net.zero_grad()
         net[2](net[1](net[0](torch.full((3, 4), float(r + 1))))).sum().backward()
         gs.append(torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in net.parameters()]))
     assert torch.allclose(res[0], (gs[0] + gs[1]) / 2, atol=1e-6)
-    assert res[0][-6:].abs().sum() == 0                     # the unused head stays zero (no hang, no None grads)
+    assert res[0][-10:].abs().sum() == 0                    # the unused head + norm stay zero (no hang, no None grads)
 
 
 def _reduce_worker(rank, world, port, q):

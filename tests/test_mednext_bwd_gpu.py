@@ -2,7 +2,11 @@
 
 Same tolerance statement as tests/test_mednext_gpu.py: errors are relative L2 against the fp32
 oracle gradients, compared with the error of the oracle run under torch.autocast(bfloat16) (the
-reference's own bf16 training path); the engine may be at most 1.5x that + a small slack."""
+reference's own bf16 training path); the engine may be at most 1.5x that + a small slack.
+
+On top of that every block / network gradient is compared with the ROUNDING-MATCHED oracle
+(`oracle.mednext_oracle.bf16_matched()`: bf16 rounding of the same activations AND the same gradients the engine stores
+as bf16 — dOut, dh, dYhat, dy, dx — fp32 everywhere else): rel-L2 <= MATCHED_GRAD (3e-3) per tensor."""
 import os
 
 import pytest
@@ -30,16 +34,36 @@ def ncdhw(x):
     return x.permute(0, 4, 1, 2, 3).float().cpu()
 
 
-def _grads_oracle(mod, x, gout, autocast, extra=None):
+MATCHED_GRAD = 3e-3
+
+
+def _grads_oracle(mod, x, gout, autocast, extra=None, matched=False):
     mod.zero_grad()
     x = x.clone().requires_grad_(True)
-    if autocast:
+    if matched:
+        with OM.bf16_matched():     # the block input is a bf16 tensor whose gradient the engine stores as bf16 too
+            xin = OM.q(x, fwd=False)
+            out = mod(xin) if extra is None else mod(xin, skip=extra)
+    elif autocast:
         with torch.autocast("cpu", dtype=torch.bfloat16):
             out = mod(x) if extra is None else extra + mod(x)
     else:
         out = mod(x) if extra is None else extra + mod(x)
     (out.float() * gout).sum().backward()
     return x.grad.clone(), {k: p.grad.clone() for k, p in mod.named_parameters() if p.grad is not None}
+
+
+def _compare_matched(label, got_dx, got_p, refm, bound=MATCHED_GRAD):
+    dxm, pm = refm
+    e = rel(got_dx, dxm)
+    print(f"{label}: dx vs rounding-matched oracle {e:.3e} (bound {bound:.0e})")
+    worst = [("dx", e)]
+    for k in pm:
+        ek = rel(got_p[k], pm[k])
+        print(f"   {k:18s} vs matched {ek:.3e}")
+        worst.append((k, ek))
+    bad = [(k, v) for k, v in worst if v > bound]
+    assert not bad, (label, "matched-oracle gradient bound", bad)
 
 
 def _compare(label, got_dx, got_p, ref32, refbf, slack=4e-3):
@@ -103,6 +127,7 @@ def test_block_backward(kind, cin, cout, r, k, size):
     got_p = {k_: q.grad for k_, q in p.named_parameters()}
     assert set(got_p) == set(ref32[1])
     _compare(f"{kind} C={cin}->{cout} r={r} k={k}", ncdhw(xc.grad), got_p, ref32, refbf)
+    _compare_matched(f"{kind} C={cin}->{cout} r={r} k={k}", ncdhw(xc.grad), got_p, _grads_oracle(o, x, gout, False, matched=True))
 
 
 def test_up_block_backward_with_skip():
@@ -116,6 +141,8 @@ def test_up_block_backward_with_skip():
     xc, sc = cl(x).requires_grad_(True), cl(skip).requires_grad_(True)
     p(xc, sc).backward(cl(gout))
     _compare("up+skip", ncdhw(xc.grad), {k: q.grad for k, q in p.named_parameters()}, ref32, refbf)
+    _compare_matched("up+skip", ncdhw(xc.grad), {k: q.grad for k, q in p.named_parameters()},
+                     _grads_oracle(o, x, gout, False, extra=skip, matched=True))
     assert torch.equal(ncdhw(sc.grad), gout)   # d(skip) is the incoming gradient, untouched
 
 
@@ -190,6 +217,32 @@ def test_tiny_network_training_step_matches_oracle():
     e, eb = (num / den) ** 0.5, (numb / den) ** 0.5
     print(f"all-parameter gradient rel-L2: engine {e:.3e}  reference-bf16-path {eb:.3e}")
     assert e <= 1.5 * eb + 5e-3
+    o.zero_grad()
+    with OM.bf16_matched():
+        lm = bce(o(x).float(), tgt)
+    lm.backward()
+    num = den = 0.0
+    for k in g32:
+        num += float((gg[k].cpu() - o.get_parameter(k).grad).norm() ** 2)
+        den += float(o.get_parameter(k).grad.norm() ** 2)
+    em = (num / den) ** 0.5
+    print(f"MedNeXt-{size_id} x{out_ch}: loss matched {lm.item():.6f} engine {lg.item():.6f}; all-parameter gradient vs "
+          f"rounding-matched oracle {em:.3e}")
+    assert abs(lg.item() - lm.item()) <= 1e-3 * max(1.0, abs(lm.item()))
+    assert em <= 8e-3
+    # rounding-matched oracle: the same step with bf16 rounding where the engine stores bf16 (both directions)
+    o.zero_grad()
+    with OM.bf16_matched():
+        lm = loss_of(o(x), "cpu")
+    lm.backward()
+    num = den = 0.0
+    for k in g32:
+        num += float((gg[k].cpu() - o.get_parameter(k).grad).norm() ** 2)
+        den += float(o.get_parameter(k).grad.norm() ** 2)
+    em = (num / den) ** 0.5
+    print(f"loss matched {lm.item():.6f} (engine {lg.item():.6f});  all-parameter gradient vs rounding-matched oracle {em:.3e}")
+    assert abs(lg.item() - lm.item()) <= 1e-3 * max(1.0, abs(lm.item()))
+    assert em <= 5e-3
 
 
 def test_multihead_wrapper_forward_backward():
@@ -315,60 +368,64 @@ def test_block_layernorm_forward_backward(kind, cin, cout, r, size):
     _compare(f"layernorm {kind} C{cin}", ncdhw(xc.grad), got_p, ref32, refbf)
 
 
-@pytest.mark.skipif(os.environ.get("PCB_TEST_OPTIN") != "1", reason="opt-in kernels: set PCB_TEST_OPTIN=1")
-@pytest.mark.parametrize("size", [(16, 16, 16), (9, 10, 11), (24, 20, 18)])
-def test_block_backward_warp_specialised(size, monkeypatch):
-    """mlp_bwd_ws_kernel (PCB_BWD_WS=1, level-0 shape): same parity bar as the default fused backward; 2 samples,
+@pytest.mark.parametrize("size", [(9, 10, 11), (24, 20, 18)])
+@pytest.mark.parametrize("ws", ["0", "1", "2"])
+def test_block_backward_kernel_variants_level0(ws, size, monkeypatch):
+    """The level-0 SAME shape on each of its three kernels — PCB_BWD_WS=1 mlp_bwd_ws_kernel (the DEFAULT for this shape
+    since round 2), =2 mlp_bwd_ws2_kernel, =0 the non-specialised mlp_bwd_fused_kernel: same parity bars; 2 samples,
     ragged last tiles, more tiles than one wave of loader stages (24*20*18 = 68 tiles per sample)."""
-    monkeypatch.setenv("PCB_BWD_WS", "1")
+    monkeypatch.setenv("PCB_BWD_WS", ws)
     test_block_backward("same", 32, 32, 2, 3, size)
 
 
-@pytest.mark.skipif(os.environ.get("PCB_TEST_OPTIN") != "1", reason="opt-in kernels: set PCB_TEST_OPTIN=1")
 @pytest.mark.parametrize("kind,cin,cout,size", [
-    ("same", 32, 32, (16, 16, 16)), ("same", 32, 32, (9, 10, 11)),      # level 0: two accumulator buffers, 4 stages
-    ("same", 64, 64, (16, 16, 16)), ("same", 64, 64, (9, 10, 11)),      # level 1: one buffer, 2 stages
+    ("same", 64, 64, (9, 10, 11)),                                       # level 1: one buffer, 2 stages
     ("down", 32, 64, (16, 16, 16)),                                      # down_0: C=32 -> Co=64
-    ("up", 64, 32, (8, 8, 8)), ("up", 64, 32, (5, 6, 7)),               # up_0: dOut rows through the +1 table
+    ("up", 64, 32, (5, 6, 7)),                                           # up_0: dOut rows through the +1 table
 ])
-def test_block_backward_warp_specialised_general(kind, cin, cout, size, monkeypatch):
-    """mlp_bwd_ws2_kernel (PCB_BWD_WS=2): every shape the fused backward serves, same parity bar."""
-    monkeypatch.setenv("PCB_BWD_WS", "2")
+@pytest.mark.parametrize("ws", ["0", "2"])
+def test_block_backward_kernel_variants_general(ws, kind, cin, cout, size, monkeypatch):
+    """mlp_bwd_ws2_kernel (the DEFAULT for every fused-backward shape but level-0 SAME since round 2; the parametrised
+    test_block_backward above runs it) against the non-specialised kernel it replaced (PCB_BWD_WS=0), same parity bars."""
+    monkeypatch.setenv("PCB_BWD_WS", ws)
     test_block_backward(kind, cin, cout, 2, 3, size)
 
 
-@pytest.mark.skipif(os.environ.get("PCB_TEST_OPTIN") != "1", reason="opt-in: set PCB_TEST_OPTIN=1 (long CPU oracle run)")
-@pytest.mark.parametrize("ws", ["0", "1", "2"])
-def test_block_backward_many_tiles_per_cta(ws, monkeypatch):
+@pytest.mark.parametrize("ws,kind,cin,cout,size", [
+    ("1", "same", 32, 32, (48, 48, 40)), ("2", "same", 32, 32, (48, 48, 40)), ("0", "same", 32, 32, (48, 48, 40)),
+    ("2", "same", 64, 64, (40, 40, 32)), ("2", "up", 64, 32, (20, 20, 20)), ("2", "down", 32, 64, (64, 64, 48)),
+])
+def test_block_backward_many_tiles_per_cta(ws, kind, cin, cout, size, monkeypatch):
     """Persistent kernels with MANY tiles per CTA (stage reuse, accumulator double buffering, barrier phase flips): the
-    parametrised shapes above give every CTA a single tile.  2 x 64x64x48 voxels = 3 072 tiles over <= 296 CTAs.
-    ws = 0: default fused backward; 1 / 2: the opt-in warp-specialised kernels."""
+    parametrised shapes above give every CTA a single tile.  2 x 48x48x40 voxels = 1 440 tiles over 148 CTAs (~10 each)
+    for the level-0 kernels; level 1 / up_0 / down_0 on the generalised kernel with 5-8 tiles per CTA."""
     monkeypatch.setenv("PCB_BWD_WS", ws)
-    test_block_backward("same", 32, 32, 2, 3, (64, 64, 48))
+    test_block_backward(kind, cin, cout, 2, 3, size)
 
 
-@pytest.mark.skipif(os.environ.get("PCB_TEST_OPTIN") != "1", reason="opt-in: set PCB_TEST_OPTIN=1 (long CPU oracle run)")
 def test_deep_block_backward_many_tiles_per_cta():
     """gemm_ws_kernel backward modes (dual accumulators, stats epilogue, resident weights) with several tiles per CTA:
     2 x 32x32x24 voxels at C=128 -> 384 row tiles x 2 column tiles over 148 CTAs."""
     test_block_backward("same", 128, 128, 2, 3, (32, 32, 24))
 
 
-@pytest.mark.skipif(os.environ.get("PCB_TEST_OPTIN") != "1", reason="opt-in: set PCB_TEST_OPTIN=1 (long CPU oracle run)")
-@pytest.mark.parametrize("ws", ["0", "2"])
-def test_mednext_s_training_step_64_matches_oracle(ws, monkeypatch):
-    """Whole MedNeXt-S (the bench model) forward + BCE + backward on 2 x 64^3 against the oracle: every persistent
-    kernel sees many tiles per CTA at the real channel counts (level 0: 2 x 2048 tiles).  Same acceptance rule as the tiny
-    network: all-parameter gradient error <= 1.5 x the reference's own bf16-autocast error + slack."""
-    monkeypatch.setenv("PCB_BWD_WS", ws)
+@pytest.mark.parametrize("size_id,out_ch,side", [("S", 1, 64), ("S", 3, 48), ("L", 1, 32)])
+def test_mednext_training_step_matches_oracle(size_id, out_ch, side):
+    """Whole networks of the BASELINE configs — MedNeXt-S (C2, the bench model: every persistent kernel sees many tiles per
+    CTA at the real channel counts, level 0: 2 x 2048 tiles), MedNeXt-S with 3 output channels (C3) and MedNeXt-L (C4:
+    exp_r 3/4/8, 3-4-8 blocks per stage — hidden widths 96 / 256 / 1024 leave the fused level-0/1 kernels for the general
+    ones) — forward + BCE + backward on 2 crops against the oracle.  Same acceptance rule as the tiny network:
+    all-parameter gradient error <= 1.5 x the reference's own bf16-autocast error + slack, plus the rounding-matched
+    bound."""
     torch.manual_seed(0)
-    o = OM.create_mednext_v1(1, 1, "S", 3, False)
-    p = PM.create_mednext_v1(1, 1, "S", 3, False)
+    o = OM.create_mednext_v1(1, out_ch, size_id, 3, False)
+    o.outside_block_checkpointing = False          # same arithmetic, no recompute: keeps the CPU oracle run short
+    p = PM.create_mednext_v1(1, out_ch, size_id, 3, False)
     p.load_state_dict(o.state_dict(), strict=True)
     p.to(DEV)
     torch.manual_seed(1)
-    x = torch.rand(2, 1, 64, 64, 64)
-    tgt = (torch.rand(2, 1, 64, 64, 64) > 0.85).float()
+    x = torch.rand(2, 1, side, side, side)
+    tgt = (torch.rand(2, out_ch, side, side, side) > 0.85).float()
     bce = torch.nn.functional.binary_cross_entropy_with_logits
     l32 = bce(o(x).float(), tgt)
     l32.backward()
@@ -394,3 +451,16 @@ def test_mednext_s_training_step_64_matches_oracle(ws, monkeypatch):
     e, eb = (num / den) ** 0.5, (numb / den) ** 0.5
     print(f"all-parameter gradient rel-L2: engine {e:.3e}  reference-bf16-path {eb:.3e}")
     assert e <= 1.5 * eb + 5e-3
+    o.zero_grad()
+    with OM.bf16_matched():
+        lm = bce(o(x).float(), tgt)
+    lm.backward()
+    num = den = 0.0
+    for k in g32:
+        num += float((gg[k].cpu() - o.get_parameter(k).grad).norm() ** 2)
+        den += float(o.get_parameter(k).grad.norm() ** 2)
+    em = (num / den) ** 0.5
+    print(f"MedNeXt-{size_id} x{out_ch}: loss matched {lm.item():.6f} engine {lg.item():.6f}; all-parameter gradient vs "
+          f"rounding-matched oracle {em:.3e}")
+    assert abs(lg.item() - lm.item()) <= 1e-3 * max(1.0, abs(lm.item()))
+    assert em <= 8e-3

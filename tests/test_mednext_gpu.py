@@ -6,7 +6,13 @@ reference under `precision: bf16-mixed` — and bf16 storage alone rounds every 
 = 2e-3 relative.  So each check states BOTH numbers: the engine's relative L2 error against the
 fp32 oracle, and the same error for the oracle run under torch.autocast(bfloat16) (= the reference's
 own bf16 path); the engine must not be further from fp32 than 1.5x the reference's bf16 path
-(+1e-3 absolute slack)."""
+(+1e-3 absolute slack).
+
+That bound alone is loose (it admits an engine error of ~1.7e-2 and hides a bug confined to a few rows inside an
+L2 norm), so every block / network check ALSO compares against the ROUNDING-MATCHED oracle
+(`oracle.mednext_oracle.bf16_matched()`: the same stock torch ops with bf16 rounding exactly where the engine stores
+bf16 and bf16 pointwise weights, fp32 in between): rel-L2 <= MATCHED_REL (2e-3 per block, 4e-3 through a whole
+network) AND max-abs <= MATCHED_ULPS bf16 ulps of the output range (a localised error cannot hide in a max)."""
 import os
 
 import numpy as np
@@ -40,10 +46,34 @@ def autocast_ref(mod, *a):
         return mod(*a).float()
 
 
-def check(got, want32, want_bf16, label, slack=1e-3):
+MATCHED_REL, MATCHED_REL_NET, MATCHED_ULPS = 2e-3, 4e-3, 8.0
+
+
+def matched_ref(mod, *a, **kw):
+    with torch.no_grad(), OM.bf16_matched():
+        out = mod(*a, **kw)
+    return [t.float() for t in out] if isinstance(out, (list, tuple)) else out.float()
+
+
+def check_matched(got, want_m, label, rel_bound=MATCHED_REL, ulps=MATCHED_ULPS):
+    g, w = got.float().cpu(), want_m.float().cpu()
+    e = float((g - w).norm() / w.norm().clamp_min(1e-12))
+    rng = float(w.abs().max())
+    mx = float((g - w).abs().max())
+    n_ulp = mx / (rng * 2.0 ** -8) if rng > 0 else 0.0
+    print(f"{label}: vs rounding-matched oracle rel-L2 {e:.3e} (bound {rel_bound:.0e}), max-abs {mx:.3e} = {n_ulp:.2f} "
+          f"bf16 ulps of range {rng:.3g} (bound {ulps})")
+    assert e <= rel_bound, (label, "matched rel-L2", e)
+    assert n_ulp <= ulps, (label, "matched max-abs ulps", n_ulp)
+    return e
+
+
+def check(got, want32, want_bf16, label, slack=1e-3, want_m=None, rel_bound=MATCHED_REL):
     e, e_ref = rel(got, want32), rel(want_bf16, want32)
     print(f"{label}: engine rel-L2 {e:.3e}   reference-bf16-path rel-L2 {e_ref:.3e}")
     assert e <= 1.5 * e_ref + slack, (label, e, e_ref)
+    if want_m is not None:
+        check_matched(got, want_m, label, rel_bound)
     return e
 
 
@@ -141,7 +171,7 @@ def test_block_forward(kind, cin, cout, r, k, size):
     want_bf = autocast_ref(o, xq)
     torch.cuda.synchronize()
     assert ncdhw(got).shape == want.shape
-    check(ncdhw(got), want, want_bf, f"{kind} block C={cin}->{cout} r={r} k={k}")
+    check(ncdhw(got), want, want_bf, f"{kind} block C={cin}->{cout} r={r} k={k}", want_m=matched_ref(o, xq))
 
 
 def test_up_block_with_fused_skip():
@@ -153,7 +183,7 @@ def test_up_block_with_fused_skip():
         want = sq + o(xq)
         got = p(cl(x), cl(skip))
     want_bf = sq + autocast_ref(o, xq)
-    check(ncdhw(got), want, want_bf, "up block + skip")
+    check(ncdhw(got), want, want_bf, "up block + skip", want_m=matched_ref(o, xq, skip=sq))
     # o = 0 planes carry the skip only (F.pad front zero, blocks.py MedNeXtUpBlock.forward)
     assert torch.equal(ncdhw(got)[:, :, 0], sq[:, :, 0])
     assert torch.equal(ncdhw(got)[:, :, :, :, 0], sq[:, :, :, :, 0])
@@ -188,11 +218,12 @@ def test_tiny_network_vs_golden_and_oracle(mednext_tiny_golden):
         want = o(x)
     with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
         want_bf = [t.float() for t in o(x)]
+    want_m = matched_ref(o, x)
     assert len(outs) == 5
     for i in range(5):
         assert outs[i].shape == want[i].shape and outs[i].dtype == torch.float32
         np.testing.assert_allclose(want[i].numpy(), g[f"out{i}"], rtol=1e-4, atol=1e-5)
-        check(outs[i], want[i], want_bf[i], f"tiny MedNeXt out{i}", slack=2e-3)
+        check(outs[i], want[i], want_bf[i], f"tiny MedNeXt out{i}", slack=2e-3, want_m=want_m[i], rel_bound=MATCHED_REL_NET)
     # forward_output(forward_features(x)) == model(x)  (reference tests/unit/test_mednext_features.py:26-39)
     with torch.no_grad():
         f = p.forward_features(x.to(DEV))
@@ -212,7 +243,7 @@ def test_mednext_s_shapes_and_parity():
         want = o(x.half().float())
     want_bf = autocast_ref(o, x.half().float())
     assert got.dtype == torch.float16 and got.shape == (1, 3, 32, 32, 32)
-    check(got, want, want_bf, "MedNeXt-S 32^3", slack=2e-3)
+    check(got, want, want_bf, "MedNeXt-S 32^3", slack=2e-3, want_m=matched_ref(o, x.half().float()), rel_bound=MATCHED_REL_NET)
     with pytest.raises(ValueError):
         p(torch.rand(1, 1, 20, 32, 32, device=DEV))
 
@@ -235,26 +266,63 @@ def test_full_size_config2_forward_parity():
         f2 = p.forward_features(x.to(DEV).half())
     want_bf = autocast_ref(o, x)
     assert got.shape == (1, 1, 160, 160, 160) and torch.isfinite(got).all()
-    check(got, want, want_bf, "MedNeXt-S 160^3 (config 2)", slack=2e-3)
+    check(got, want, want_bf, "MedNeXt-S 160^3 (config 2)", slack=2e-3, want_m=matched_ref(o, x), rel_bound=MATCHED_REL_NET)
     # run-to-run determinism of the whole trunk at full size (fp64 statistics, ordered blending of nothing else)
     assert (f1.float() - f2.float()).abs().max().item() <= 1e-2 * f1.float().abs().max().item()
-    # "matching reference Jaccard on synthetic replay": thresholded-sigmoid masks vs the fp32 oracle mask.  With
-    # random-init weights the logits sit near 0, so even the reference's own bf16 path flips ~3 % of the voxels;
-    # the engine must agree with the fp32 mask at least as well as that path does (minus 0.01).
+
+
+def _blob_volume(n, side, seed):
+    """learnable synthetic segmentation task: smooth random field -> image = field + noise, label = field > median"""
+    g = torch.Generator().manual_seed(seed)
+    f = torch.rand(n, 1, side, side, side, generator=g)
+    for _ in range(3):
+        f = torch.nn.functional.avg_pool3d(f, 5, 1, 2, count_include_pad=False)
+    f = (f - f.mean()) / f.std()
+    img = (f * 0.25 + 0.5 + 0.05 * torch.randn(f.shape, generator=g)).clamp(0, 1)
+    return img, (f > 0).float()
+
+
+def test_jaccard_replay_after_training():
+    """north_star: "matching reference Jaccard on Lucchi++ synthetic replay".  The HF checkpoint is not available
+    offline, so the replay is: train MedNeXt-S with THIS engine for 200 AdamW steps on a learnable synthetic task (logits
+    separate, unlike random-init weights whose logits sit at 0), load the trained weights into the fp32 CPU oracle
+    (strict), predict a held-out volume with both, threshold the sigmoid at 0.5 (evaluation/metric_execution.py:178-196)
+    and compare the Jaccard against the labels: |J_engine - J_oracle| <= 1e-3, and the two masks agree (J >= 0.995)."""
+    import os
     from oracle.window_oracle import binary_jaccard
-    mask = lambda t: (torch.sigmoid(t.float()).cpu() > 0.5).numpy().astype("float32")   # noqa: E731
-    j = binary_jaccard(mask(got), mask(want), 0.5)
-    j_ref = binary_jaccard(mask(want_bf), mask(want), 0.5)
-    print(f"Jaccard vs fp32-oracle mask at 160^3: engine {j:.5f}   reference-bf16-path {j_ref:.5f}")
-    assert j >= j_ref - 0.01
-
-
-@pytest.mark.skipif(os.environ.get("PCB_TEST_OPTIN") != "1", reason="opt-in kernels: set PCB_TEST_OPTIN=1")
-def test_forward_loader_depth_16(monkeypatch):
-    """mlp_fused_kernel<LD16> (PCB_FWD_LD16=1: 16 loads in flight per loader lane): block parity at C=32 / C=64 and the
-    full-size MedNeXt-S forward (many tiles per CTA)."""
-    monkeypatch.setenv("PCB_FWD_LD16", "1")
-    test_block_forward("same", 32, 32, 2, 3, (16, 16, 16))
-    test_block_forward("same", 64, 64, 3, 5, (8, 8, 8))
-    test_block_forward("down", 32, 64, 2, 3, (16, 16, 16))
-    test_full_size_config2_forward_parity()
+    torch.set_num_threads(min(os.cpu_count() or 1, 32))
+    torch.manual_seed(0)
+    p = PM.create_mednext_v1(1, 1, "S", 3, False).to(DEV).train()
+    opt = torch.optim.AdamW(p.parameters(), lr=1e-3, weight_decay=0.01)
+    imgs, labs = _blob_volume(8, 48, seed=1)
+    imgs, labs = imgs.to(DEV), labs.to(DEV)
+    bce = torch.nn.functional.binary_cross_entropy_with_logits
+    first = last = None
+    for it in range(200):
+        i = (2 * it) % 8
+        opt.zero_grad(set_to_none=True)
+        loss = bce(p(imgs[i:i + 2].half()).float(), labs[i:i + 2])
+        loss.backward()
+        opt.step()
+        if it == 0:
+            first = float(loss)
+        last = float(loss)
+    print(f"training loss {first:.4f} -> {last:.4f}")
+    assert last < 0.5 * first, (first, last)          # the task is learnable and the engine's gradients train it
+    p.eval()
+    o = OM.create_mednext_v1(1, 1, "S", 3, False).eval()
+    o.load_state_dict({k: v.detach().cpu() for k, v in p.state_dict().items()}, strict=True)
+    x, y = _blob_volume(1, 96, seed=2)
+    with torch.no_grad():
+        got = p(x.to(DEV).half()).float().cpu()
+        want = o(x.half().float())
+    mask = lambda t: (torch.sigmoid(t) > 0.5).numpy().astype("float32")   # noqa: E731
+    lab = y.numpy()
+    j_e, j_o = binary_jaccard(mask(got), lab, 0.5), binary_jaccard(mask(want), lab, 0.5)
+    j_eo = binary_jaccard(mask(got), mask(want), 0.5)
+    frac_sep = float((want.abs() > 1.0).float().mean())
+    print(f"Jaccard vs labels: engine {j_e:.5f}  fp32 oracle {j_o:.5f}  |delta| {abs(j_e - j_o):.2e};  engine-vs-oracle "
+          f"masks {j_eo:.5f};  |logit| > 1 on {100 * frac_sep:.1f}% of voxels")
+    assert j_o > 0.8                                   # the trained model actually segments the held-out volume
+    assert abs(j_e - j_o) <= 1e-3
+    assert j_eo >= 0.995

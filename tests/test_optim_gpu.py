@@ -1,0 +1,142 @@
+"""Fused AdamW + clip + EMA kernel (csrc/optim_kernels.cu) against torch.optim.AdamW + clip_grad_norm_ + the reference's
+EMA update (training/lightning/callbacks.py:869-907) on the CPU, same parameter groups (training/optimization/build.py:69-111).
+fp32 arithmetic, torch's op order: tolerance 2e-6 relative (documented in the kernel: (1 - lr*wd) and lr/bc1 are formed
+in fp32 instead of Python doubles)."""
+from types import SimpleNamespace as NS
+
+import pytest
+import torch
+
+from pytorch_connectomics_b200.training import FlatGradArena, FusedAdamW, build_fused_adamw, reference_param_groups
+
+DEV = "cuda:0"
+
+
+def _model():
+    torch.manual_seed(0)
+    return torch.nn.Sequential(torch.nn.Conv3d(2, 5, 3), torch.nn.GroupNorm(5, 5), torch.nn.Conv3d(5, 3, 1, bias=False),
+                               torch.nn.Linear(7, 3))
+
+
+def test_reference_param_groups_follow_build_optimizer():
+    m = _model()
+    groups = reference_param_groups(m, 1e-3, 0.01, weight_decay_norm=0.0, weight_decay_bias=0.002, bias_lr_factor=2.0)
+    by = {id(g["params"][0]): g for g in groups}
+    assert by[id(m[0].weight)]["weight_decay"] == 0.01 and by[id(m[0].bias)]["weight_decay"] == 0.002
+    assert by[id(m[0].bias)]["lr"] == 2e-3 and by[id(m[1].weight)]["weight_decay"] == 0.0 and by[id(m[1].bias)]["weight_decay"] == 0.0
+    assert len(groups) == len(list(m.parameters()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("clip,ema,world", [(0.0, None, 1), (0.5, 0.99, 1), (1.0, 0.999, 4)])
+def test_fused_adamw_matches_torch(clip, ema, world):
+    ref = _model()
+    net = _model().to(DEV)
+    lr, wd = 1e-2, 0.05
+    kw = dict(weight_decay_norm=0.0, weight_decay_bias=0.01, bias_lr_factor=2.0)
+    topt = torch.optim.AdamW(reference_param_groups(ref, lr, wd, **kw), lr=lr, betas=(0.9, 0.99), eps=1e-8, weight_decay=wd)
+    arena = FlatGradArena(net.parameters())
+    groups = reference_param_groups(net, lr, wd, **kw)
+    order = {id(p): i for i, p in enumerate(arena.params)}
+    groups.sort(key=lambda g: order[id(g["params"][0])])
+    fopt = FusedAdamW(groups, betas=(0.9, 0.99), eps=1e-8, max_grad_norm=clip, ema_decay=ema, arena=arena, world_size=world)
+    ema_ref = {k: v.detach().clone() for k, v in ref.named_parameters()} if ema is not None else None
+    g = torch.Generator().manual_seed(1)
+    for it in range(4):
+        grads = [torch.randn(p.shape, generator=g) * (3.0 if it == 2 else 0.3) for p in ref.parameters()]
+        for p, gr in zip(ref.parameters(), grads):
+            p.grad = gr.clone()
+        if clip > 0:
+            torch.nn.utils.clip_grad_norm_(ref.parameters(), clip)
+        topt.step()
+        if ema_ref is not None:
+            for k, p in ref.named_parameters():
+                ema_ref[k].mul_(ema).add_(p.detach(), alpha=1.0 - ema)
+        arena.zero()
+        for p, gr in zip(net.parameters(), grads):       # the all-reduced SUM over `world` identical ranks
+            p.grad.copy_((gr * world).to(DEV))
+        fopt.step(grads_are_summed=True)
+    torch.cuda.synchronize()
+    for (k, a), b in zip(ref.named_parameters(), net.parameters()):
+        assert torch.allclose(b.cpu(), a.detach(), rtol=2e-6, atol=2e-7), (k, (b.cpu() - a).abs().max())
+    if ema is not None:
+        views = fopt.ema_tensors()
+        for (k, _), b in zip(ref.named_parameters(), net.parameters()):
+            assert torch.allclose(views[id(b)].cpu(), ema_ref[k], rtol=2e-6, atol=2e-7), k
+        before = [p.detach().clone() for p in net.parameters()]
+        fopt.swap_ema()
+        for (k, _), b in zip(ref.named_parameters(), net.parameters()):
+            assert torch.allclose(b.cpu(), ema_ref[k], rtol=2e-6, atol=2e-7)
+        fopt.swap_ema()
+        assert all(torch.equal(a, b.detach()) for a, b in zip(before, net.parameters()))
+    assert float(fopt.step_count) == 4.0
+    # the modules still see the flat storage: a forward pass works and parameters are views of ONE arena
+    assert net(torch.zeros(1, 2, 5, 5, 9, device=DEV)).shape == (1, 3, 3, 3, 3)
+    assert all(p.data_ptr() >= fopt.flat.data_ptr() and p.data_ptr() < fopt.flat.data_ptr() + 4 * fopt.n for p in net.parameters())
+
+
+@pytest.mark.gpu
+def test_build_fused_adamw_from_cfg_and_graph_capture():
+    net = _model().to(DEV)
+    cfg = NS(optimization=NS(optimizer=NS(name="adamw", lr=1e-3, weight_decay=0.01, betas=[0.9, 0.999], eps=1e-8),
+                             gradient_clip_val=1.0))
+    arena = FlatGradArena(net.parameters())
+    opt = build_fused_adamw(cfg, net, arena=arena, ema_decay=0.99)
+    assert opt.max_grad_norm == 1.0 and float(opt.seg_wd[2]) == 0.0        # GroupNorm weight: weight_decay_norm default 0
+    arena.buffer.normal_()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        opt.step()
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        opt.step()
+    p0 = opt.flat.clone()
+    g.replay(); g.replay()
+    torch.cuda.synchronize()
+    assert float(opt.step_count) == 3.0 and not torch.equal(p0, opt.flat)
+    with pytest.raises(NotImplementedError):
+        build_fused_adamw(NS(optimization=NS(optimizer=NS(name="sgd"))), net)
+
+
+@pytest.mark.gpu
+def test_fused_adamw_trains_mednext_like_torch_adamw():
+    """Whole loop on the engine: two identical tiny MedNeXts, one stepped by torch.optim.AdamW (same param groups), one by
+    the fused kernel — after 3 steps the weights agree and the fused model's forward uses the UPDATED weights (the
+    kernel-layout weight cache is invalidated by the parameter epoch)."""
+    from pytorch_connectomics_b200.architectures import mednext as PM
+
+    def make():
+        torch.manual_seed(3)
+        return PM.MedNeXt(1, 16, 1, exp_r=2, kernel_size=3, deep_supervision=False, do_res=True, do_res_up_down=True,
+                          block_counts=[1] * 9).to(DEV).train()
+
+    a, b = make(), make()
+    lr, wd = 1e-3, 0.01
+    topt = torch.optim.AdamW(reference_param_groups(a, lr, wd), lr=lr, weight_decay=wd)
+    arena = FlatGradArena(b.parameters())
+    groups = reference_param_groups(b, lr, wd)
+    order = {id(p): i for i, p in enumerate(arena.params)}
+    groups.sort(key=lambda g: order[id(g["params"][0])])
+    fopt = FusedAdamW(groups, arena=arena)
+    torch.manual_seed(4)
+    xs = [torch.rand(1, 1, 32, 32, 32, device=DEV).half() for _ in range(3)]
+    ts = [(torch.rand(1, 1, 32, 32, 32, device=DEV) > 0.8).float() for _ in range(3)]
+    bce = torch.nn.functional.binary_cross_entropy_with_logits
+    with torch.no_grad():
+        out0 = b(xs[0]).clone()
+    for x, t in zip(xs, ts):
+        topt.zero_grad(set_to_none=True)
+        bce(a(x).float(), t).backward()
+        topt.step()
+        fopt.zero_grad()
+        bce(b(x).float(), t).backward()
+        fopt.step()
+    torch.cuda.synchronize()
+    for (k, pa), pb in zip(a.named_parameters(), b.parameters()):
+        assert torch.allclose(pa, pb, rtol=0, atol=2e-5), (k, (pa - pb).abs().max())
+    with torch.no_grad():
+        out_a, out_b = a(xs[0]), b(xs[0])
+    assert not torch.equal(out_b, out0)                      # the forward sees the stepped weights
+    assert torch.allclose(out_a.float(), out_b.float(), atol=5e-3)

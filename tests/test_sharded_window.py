@@ -152,3 +152,50 @@ def test_sharded_engine_matches_eager_gpu(world, overlap):
             exchanged[lo:hi] = True
     keep = (~exchanged).nonzero().flatten().to(dev)
     assert torch.equal(got.index_select(2, keep), want.index_select(2, keep))   # untouched planes are bit-exact
+
+
+def _nccl_worker(rank, world, port, q):
+    """one process per GPU over NCCL: the product path of ZSlabShardedEngine (send/recv of the overlap planes)"""
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    torch.manual_seed(7)
+    vol = torch.rand(1, 1, 52, 40, 36)
+    kw = dict(roi_size=(16, 16, 16), sw_batch_size=3, overlap=0.5, mode="bump", padding_mode="constant", cval=0.0)
+    eng = S.ZSlabShardedEngine(device=dev, **kw)
+    part, own = eng(vol, _net)                                  # host volume: only this rank's slab goes to its GPU
+    plan = S.plan_z_slabs(vol.shape[2:], (16, 16, 16), 0.5, world)[rank]
+    part2 = eng.run_slab(vol[:, :, plan.slab[0]:plan.slab[1]].to(dev), _net, plan)     # pre-sliced device slab
+    assert torch.equal(part, part2)
+    q.put((rank, own, part.cpu().numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_sharded_engine_two_ranks_nccl():
+    """2 GPUs, 2 processes, NCCL: the exchanged result equals the single-GPU eager engine (bit-exact away from the
+    exchanged planes).  Skipped on a single-GPU box (run with `gpurun --gpus 2`)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from pytorch_connectomics_b200.inference.window import EagerSlidingWindowEngine
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    from conftest import free_port
+    port = free_port()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=600) for _ in range(2)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=120)
+    torch.manual_seed(7)
+    vol = torch.rand(1, 1, 52, 40, 36)
+    kw = dict(roi_size=(16, 16, 16), sw_batch_size=3, overlap=0.5, mode="bump", padding_mode="constant", cval=0.0)
+    want = EagerSlidingWindowEngine(**kw)(inputs=vol.to("cuda:0"), network=_net).cpu()
+    got = torch.cat([torch.from_numpy(r[2]) for r in res], dim=2)
+    assert got.shape == want.shape and res[0][1][0] == 0 and res[1][1][1] == 52
+    assert torch.allclose(got, want, rtol=2e-6, atol=1e-6)

@@ -124,3 +124,62 @@ def test_engine_cpu_input_and_output_device():
     assert out.device.type == "cpu" and torch.allclose(out, x * 2, atol=1e-6)
     with pytest.raises(ValueError):
         eng(inputs=x.to(DEV), network=lambda t: [t])
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float16, torch.bfloat16])
+def test_accumulate_batch_bit_exact_vs_per_window(dt):
+    """pcb_sw_accumulate_batch == pcb_sw_accumulate called once per window in list order, bit for bit: heavily
+    overlapping windows, duplicates, 21 windows (two launches of <= 16), 3 channels."""
+    torch.manual_seed(11)
+    roi, image, n, cout = (6, 7, 5), (14, 16, 12), 21, 3
+    g = torch.Generator().manual_seed(3)
+    starts = [tuple(int(torch.randint(0, image[a] - roi[a] + 1, (1,), generator=g)) for a in range(3)) for _ in range(n)]
+    starts[5] = starts[4]                                       # a duplicate window inside one launch
+    pred = torch.randn(n, cout, *roi, device=DEV).to(dt)
+    wmap = W.build_sliding_importance_map(roi, mode="bump", device=DEV, dtype=dt)
+    v1 = torch.randn(1, cout, *image, device=DEV).to(dt)
+    w1 = torch.rand(1, 1, *image, device=DEV).to(dt)
+    v2, w2 = v1.clone(), w1.clone()
+    for i, st in enumerate(starts):
+        W._accumulate_window(pred[i], wmap, v1, w1, roi, image, (0, 0, 0), st, roi)
+    W._accumulate_batch(pred, wmap, v2, w2, roi, image, starts)
+    assert torch.equal(v1, v2) and torch.equal(w1, w2)
+    with pytest.raises(ValueError):
+        W._accumulate_batch(pred, wmap, v2, w2, roi, image, [(10, 0, 0)])       # window outside the accumulator
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+@pytest.mark.parametrize("groups", [1, 2, 3])
+def test_engine_streams_host_volume_bit_exact(pinned, groups):
+    """HOST volumes are streamed z-slab by z-slab (double-buffered H2D on a side stream, carried partial planes, finished
+    planes shipped back): the result is bit-identical to the one-pass device-resident run, for pageable and pinned
+    inputs, with output on the host or on the device."""
+    torch.manual_seed(12)
+    x = torch.rand(1, 2, 45, 19, 26)
+    if pinned:
+        x = x.pin_memory()
+    net2 = lambda t: torch.cat([affine_net(t[:, :1]), t[:, 1:] * 2.0], 1)   # noqa: E731
+    kw = dict(roi_size=(8, 8, 8), sw_batch_size=3, overlap=0.5, mode="distance_transform", padding_mode="constant", cval=0.0)
+    want = W.EagerSlidingWindowEngine(**kw)(inputs=x.to(DEV), network=net2)
+    for outdev in ("cpu", DEV):
+        eng = W.EagerSlidingWindowEngine(sw_device=DEV, output_device=outdev, stream_z_starts=groups, **kw)
+        got = eng(inputs=x, network=net2)
+        assert got.device.type == torch.device(outdev).type and got.shape == want.shape
+        assert torch.equal(got.to(DEV), want), (pinned, groups, outdev)
+
+
+def test_engine_rejects_wrong_network_output_shape():
+    """the kernels read the network output through raw pointers — a cropped or re-channelled output must raise
+    (the reference fails with a broadcast error there, window.py:648-655), not read out of bounds."""
+    x = torch.rand(1, 1, 16, 16, 16, device=DEV)
+    eng = _eng((8, 8, 8), 0.5, "constant", "constant", bs=2)
+    with pytest.raises(ValueError, match="expected"):
+        eng(inputs=x, network=lambda t: t[..., 1:-1, 1:-1, 1:-1])           # valid-conv style crop
+    calls = []
+
+    def flaky(t):
+        calls.append(1)
+        return t if len(calls) == 1 else torch.cat([t, t], 1)                 # channel count changes on a later batch
+
+    with pytest.raises(ValueError, match="expected"):
+        eng(inputs=x, network=flaky)
