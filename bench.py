@@ -7,7 +7,7 @@
 
 BASELINE.json's metric has two halves — training sub-volumes/s and inference Mvoxels/s — so the default line carries
 both: the top-level `metric/value/roofline/e2e/cpu_baseline` are the TRAINING step of configs[1] (MedNeXt-S, 1-channel
-160^3 crops, bf16 compute, per-GPU batch 4, BCE+Dice, AdamW; timed over exactly K steps), and `infer` is a second record
+160^3 crops, bf16 compute, per-GPU batch 4, BCE+Dice, grad-norm clip 1.0 + AdamW; timed over exactly K steps), and `infer` is a second record
 of the same shape (metric, value, unit, ms_per_step, steps, config, roofline, e2e, cpu_baseline) for sliding-window
 inference with configs[4]'s geometry (160^3 tiles, 50 % overlap, bump blending) on the largest cubic volume per GPU that
 keeps the whole run within a few minutes (--volume, default 640; N GPUs: ONE (N*volume) x volume x volume volume,
@@ -134,6 +134,7 @@ def cpu_train_rate(steps: int, warmup: int, cfg_key: str = "c2", side: int = 0):
         opt.zero_grad(set_to_none=True)
         loss = bce_dice_loss(net(x), t)
         loss.backward()
+        torch.nn.utils.clip_grad_norm_(net.parameters(), 1.0)      # gradient_clip_val 1.0 (tutorials/mito_lucchi++)
         opt.step()
         dt = time.perf_counter() - t0
         if i >= warmup:
@@ -397,7 +398,13 @@ def run_train(cx: Ctx, a, key: str, clocks):
     broadcast_parameters(model, src=0)              # ... and, like DDP at construction, rank 0's copy wins
     torch.manual_seed(4321 + rank)                  # data differs per rank
     arena = FlatGradArena(model.parameters())
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.01, fused=True, capturable=True)
+    if os.environ.get("PCB_TORCH_ADAMW"):      # A/B switch: torch's multi-tensor AdamW instead of the fused arena kernel
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.01, fused=True, capturable=True)
+    else:
+        # the tutorial's optimizer section (mito_lucchi++.yaml: AdamW lr 1e-3, gradient_clip_val 1.0) with the reference's
+        # per-parameter groups (training/optimization/build.py:69-111), as ONE clip + AdamW pass over the flat arenas
+        from pytorch_connectomics_b200.training import FusedAdamW, reference_param_groups
+        opt = FusedAdamW(reference_param_groups(model, 1e-3, 0.01), max_grad_norm=1.0, arena=arena, world_size=world)
     shape, tshape = (nb, 1, side, side, side), (nb, oc, side, side, side)
     npool = 4 if side <= 160 else 2
     # a small pool of distinct resident inputs (fp16 volumes, as the data pipeline delivers them)
@@ -529,7 +536,7 @@ def run_infer(cx: Ctx, a, clocks, steps: int, warmup: int):
     model = build_model(cfg_mednext("S", 1)).to(dev)
     model.eval()
     kw = dict(roi_size=(SIDE,) * 3, sw_batch_size=a.sw_batch, overlap=0.5, mode="bump", padding_mode="constant", cval=0.0)
-    net = lambda t: model(t)  # noqa: E731
+    net = model          # a pcb200 MedNeXt: the engine runs the whole tile loop in the library (pcb_sw_run)
     gen = torch.Generator(device=dev)
     gen.manual_seed(99)                      # every rank generates the same synthetic volume, slab by slab, on the device
     if world > 1:
@@ -570,10 +577,23 @@ def run_infer(cx: Ctx, a, clocks, steps: int, warmup: int):
     cx.barrier()
     w1 = time.time()
     launches = L.launch_count() - l0
-    prof = L.prof_stop()
+    L.prof_stop()
     ms = cx.max_over_ranks(e0.elapsed_time(e1))
     value = steps * nvox / (ms / 1e3) / 1e6
     dbg(f"infer timed region done: {ms / steps:.1f} ms/volume")
+    # roofline leg: the native loop has no per-op hooks, so the per-kernel CUDA-event times come from ONE instrumented pass
+    # of the same volume through the module path (same kernels, launched from Python with an event pair around each op)
+    inner = getattr(model, "model", model)
+    inner.native_inference = False
+    L.prof_start([])
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    step()
+    p1.record()
+    cx.barrier()
+    prof = L.prof_stop()
+    ms_prof = p0.elapsed_time(p1)
+    inner.native_inference = True
     # ---- end to end: pinned host volume -> H2D (this rank's slab) -> windows -> exchange -> own planes D2H
     e2e = None
     if not a.no_e2e:
@@ -604,14 +624,17 @@ def run_infer(cx: Ctx, a, clocks, steps: int, warmup: int):
            "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong" if a.config == "c5" else "weak",
            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": infer_config(a, world), "e2e": e2e,
            "gpu_launches": int(launches), "tiles_per_rank_per_step": my_tiles,
-           "roofline": build_roofline(prof, a.sw_batch, peak_gbs, bool(peaks), ms / steps, steps),
-           "execution": {"timed_region": "eager tile loop"}, "clocks": clocks.window(w0, w1) if clocks else None}
+           "roofline": build_roofline(prof, min(a.sw_batch, 8), peak_gbs, bool(peaks), ms_prof, 1),
+           "execution": {"timed_region": "pcb_sw_run: crop -> pcb_net_forward -> blend enqueued by the library, one CUDA-graph "
+                                         "replay per window batch", "module_path_ms_per_step": ms_prof,
+                         "roofline_timed_in": "one instrumented pass of the same volume through the module path"},
+           "clocks": clocks.window(w0, w1) if clocks else None}
     try:      # the slowest rank's tile count bounds the step
         rec["step_roofline"] = step_roofline("infer", my_tiles, ms / steps, peak_gbs, tf)
     except Exception as exc:
         rec["step_roofline"] = {"error": repr(exc)}
     if a.profile_ops and rank == 0:
-        _print_ops(prof, steps, ms / steps)
+        _print_ops(prof, 1, ms_prof)
     del model
     torch.cuda.empty_cache()
     return rec

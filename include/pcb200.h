@@ -227,6 +227,64 @@ int pcb_bn_act_bwd(const void* dy, const void* x, const float* scale, const floa
 int pcb_bn_bwd(const void* g, const void* x, const double* stats, const double* gstats, const float* gamma,
                void* dx, double* dsum, int64_t N, int64_t C, int64_t V, void* stream);
 
+/* ------------------------------------------------------------------ network- and plan-level entry points (inference)
+ * A pcb_net is the forward plan of a MedNeXt — nnunet_mednext MedNextV1.py::MedNeXt.forward as built by
+ * connectomics/models/architectures/mednext_models.py:374-380: stem -> blocks (SAME / DOWN / UP with encoder skips) ->
+ * OutBlock heads.  The library owns the plan; the CALLER owns the weights (device pointers in kernel layout, below) and
+ * the activation arena, and keeps both alive while the plan is used.  One pcb_net_forward call enqueues the whole
+ * network on the caller's stream (no host work between kernels, CUDA-graph capturable). */
+typedef struct pcb_net pcb_net;
+typedef struct {
+  int32_t kind;       /* pcb_dw_mode of conv1 */
+  int32_t C, H, Co;   /* channels in, hidden (exp_r*C), out */
+  int32_t k;          /* depthwise kernel size 3/5/7 */
+  int32_t do_res;     /* SAME blocks: out += x */
+  int32_t norm;       /* 0 = GroupNorm(num_groups=C) (the only kind the native plan runs) */
+  int32_t skip_from;  /* UP blocks: index of the block whose OUTPUT is added as the encoder skip, -1 = none */
+  const float* w1;    /* conv1.weight as [k^3, C] f32 (tap-major) */
+  const float* b1;    /* conv1.bias [C] */
+  const float* gamma; /* norm.weight [C] */
+  const float* beta;  /* norm.bias [C] */
+  const void* w2;     /* conv2.weight as bf16 [H, C] */
+  const float* b2;    /* [H] */
+  const void* w3;     /* conv3.weight as bf16 [Co, H] */
+  const float* b3;    /* [Co] */
+  const void* wr;     /* res_conv.weight as bf16 [Co, C] (DOWN / UP with do_res_up_down) or NULL */
+  const float* br;    /* res_conv.bias [Co] or NULL */
+} pcb_block_desc;
+typedef struct {
+  int32_t from_block; /* index of the block whose output feeds this OutBlock; -1 = the stem output */
+  int32_t ncls;
+  const float* w;     /* conv_out.weight as [C, ncls] f32 (ConvTranspose layout) */
+  const float* b;     /* [ncls] */
+} pcb_head_desc;
+int pcb_net_create(int32_t in_channels, int32_t n_channels, const float* stem_w, const float* stem_b,
+                   const pcb_block_desc* blocks, int32_t nblocks, const pcb_head_desc* heads, int32_t nheads, pcb_net** out);
+void pcb_net_destroy(pcb_net* net);
+int32_t pcb_net_in_channels(const pcb_net* net);
+int32_t pcb_net_num_heads(const pcb_net* net);
+int32_t pcb_net_head_channels(const pcb_net* net, int32_t head);
+/* bytes of activation arena one forward of N samples of spatial `size` needs (liveness-planned: the peak of the live
+ * set, not the sum over layers); -1 on error. */
+int64_t pcb_net_workspace_bytes(const pcb_net* net, int64_t N, const int64_t size[3]);
+/* x NCDHW [N, Cin, size] in `in_dtype` -> outs[h] NCDHW [N, ncls_h, size_h] in `out_dtype` for every head whose
+ * outs[h] != NULL (deep-supervision heads read coarser levels: size_h = size / 2^level).  workspace: 256-byte aligned. */
+int pcb_net_forward(pcb_net* net, const void* x, int in_dtype, int64_t N, const int64_t size[3], void* const* outs,
+                    int out_dtype, void* workspace, int64_t ws_bytes, void* stream);
+/* The sliding-window tile loop of connectomics/inference/window.py:563-683 for a pcb_net, entirely in the library:
+ * for each batch of `sw_batch` (<= 16) windows of the HOST list `starts` (n (z,y,x) triples, all inside acc_size):
+ * crop + pad from vol [1, Cin, image] -> pcb_net_forward -> value[:, box] += pred*map, weight[box] += map in list order
+ * (pcb_sw_accumulate_batch semantics: bit-identical to the sequential loop).  value [ncls, acc_size] / weight [acc_size]
+ * in `acc_dtype` are NOT zeroed and NOT normalised here (callers carry partial planes across slabs / ranks and call
+ * pcb_sw_normalize).  use_graph: the batch body is captured once into a CUDA graph (window starts come from a device
+ * table through a device cursor) and replayed — one graph launch per batch.  map: pcb_sw_importance_map in acc_dtype. */
+int64_t pcb_sw_run_workspace_bytes(const pcb_net* net, int head, const int64_t roi[3], int sw_batch, int64_t nstarts,
+                                   int vol_dtype, int acc_dtype);
+int pcb_sw_run(pcb_net* net, int head, const void* vol, int vol_dtype, const int64_t image[3], const int64_t roi[3],
+               int pad_mode, double cval, int sw_batch, const int64_t* starts, int64_t nstarts, const void* map,
+               void* value, void* weight, int acc_dtype, const int64_t acc_size[3], void* workspace, int64_t ws_bytes,
+               int use_graph, void* stream);
+
 /* ------------------------------------------------------------------ optimizer-side fusion over the flat arenas
  * sum of squares of a gradient arena (f64 device scalar, caller zeroes) — torch.nn.utils.clip_grad_norm_'s total norm
  * (Lightning gradient_clip_val, tutorials: 1.0). */
@@ -237,11 +295,13 @@ int pcb_grad_sumsq(const float* grad, int64_t n, double* out, void* stream);
  * becomes the mean) * clip coefficient min(1, max_norm / (sqrt(*grad_sumsq)*grad_scale + 1e-6)) when grad_sumsq != NULL
  * and max_norm > 0.  `step` is a device float holding the number of steps taken so far; it is incremented on the stream
  * (CUDA-graph capturable, like torch's capturable=True).  ema (or NULL): ema = ema*decay + param*(1-decay) after the
- * update (training/lightning/callbacks.py:869-907).  Update formula = torch.optim.AdamW, op for op. */
+ * update (training/lightning/callbacks.py:869-907).  seg_active (device scratch, nseg int32, or NULL): segments whose
+ * gradient slice is entirely zero are skipped, as torch.optim skips parameters whose .grad is None (what DDP with
+ * find_unused_parameters leaves for unused heads).  Update formula = torch.optim.AdamW, op for op. */
 int pcb_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* ema, int64_t n,
                    const int64_t* seg_end, const float* seg_lr, const float* seg_wd, int nseg, float beta1, float beta2,
                    float eps, float* step, const double* grad_sumsq, float max_norm, float grad_scale, float ema_decay,
-                   void* stream);
+                   int32_t* seg_active, void* stream);
 
 #ifdef __cplusplus
 }

@@ -20,7 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libpcb200.so")
 SOURCES = ["pcb_api.cu", "sw_kernels.cu", "mednext_fwd.cu", "mednext_bwd.cu", "dense_conv.cu", "deep_mlp.cu", "layernorm.cu", "tta_kernels.cu",
-           "optim_kernels.cu"]
+           "optim_kernels.cu", "net_runtime.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -93,6 +93,10 @@ def lib() -> ctypes.CDLL:
         _lib.pcb_tn_workspace_floats.restype = ctypes.c_int64
         _lib.pcb_mlp_bwd_fused_workspace_floats.restype = ctypes.c_int64
         _lib.pcb_mlp_fwd_deep_workspace.restype = ctypes.c_int64
+        _lib.pcb_net_workspace_bytes.restype = ctypes.c_int64
+        _lib.pcb_sw_run_workspace_bytes.restype = ctypes.c_int64
+        _lib.pcb_net_destroy.restype = None
+        _lib.pcb_net_destroy.argtypes = [ctypes.c_void_p]
     return _lib
 
 

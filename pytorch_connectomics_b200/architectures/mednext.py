@@ -233,11 +233,40 @@ class MedNeXt(nn.Module):
 
     def forward(self, x: torch.Tensor):
         odt = self._odt(x)
+        if self._use_native(x):
+            outs = self.native_plan().forward(x, odt)
+            return outs if self.do_ds else outs[0]
         f = self._trunk(x)
         y = self.out_0(f[0], odt)
         if self.do_ds:
             return [y, self.out_1(f[1], odt), self.out_2(f[2], odt), self.out_3(f[3], odt), self.out_4(f[4], odt)]
         return y
+
+    # ---- native inference plan (include/pcb200.h pcb_net_*): no autograd, whole network enqueued by the library
+    native_inference: bool = True
+
+    def native_plan(self):
+        """The ``pcb_net`` of this module (built lazily, rebuilt when a weight changed); ``None`` when the architecture
+        is not served by the native plan (LayerNorm / GRN blocks)."""
+        from .native import NativeMedNeXt, native_eligible
+        plan = self.__dict__.get("_native_plan")
+        if plan is not None and not plan.stale() and plan.device == self.stem.weight.device:
+            return plan
+        self.__dict__["_native_plan"] = None
+        if native_eligible(self) is not None or not self.stem.weight.is_cuda:
+            return None
+        plan = NativeMedNeXt(self)
+        self.__dict__["_native_plan"] = plan
+        return plan
+
+    def _use_native(self, x: torch.Tensor) -> bool:
+        if not self.native_inference or self.training or not x.is_cuda or x.dim() != 5:
+            return False
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            return False              # someone may call backward: keep the autograd path
+        if int(x.shape[0]) > 8 or int(x.shape[1]) != self.stem.in_channels or any(int(s) % 16 for s in x.shape[2:]):
+            return False
+        return self.native_plan() is not None
 
 
 _V1 = {
@@ -273,6 +302,13 @@ class MedNeXtWrapper(ConnectomicsModel):
         if self.supports_deep_supervision and isinstance(out, list):
             return {"output": out[0], "ds_1": out[1], "ds_2": out[2], "ds_3": out[3], "ds_4": out[4]}
         return out
+
+    def native_plan(self):
+        """``pcb_net`` of the trunk when this wrapper returns a plain tensor (the sliding-window engine then runs its
+        whole tile loop in the library, ``pcb_sw_run``); ``None`` otherwise."""
+        if self.supports_deep_supervision or self.training or not getattr(self.model, "native_inference", False):
+            return None
+        return self.model.native_plan() if hasattr(self.model, "native_plan") else None
 
 
 def _cfg_value(cfg: Any, key: str, default: Any = None) -> Any:

@@ -1770,14 +1770,14 @@ extern "C" int pcb_mlp_fwd(const void* y, const double* stats, const float* gamm
   const size_t smem = (size_t)128 * KA * 2 + (size_t)a.N1 * a.KC * 2 + (size_t)128 * a.N1 * 2 + (size_t)a.CoT * KW3 * 2 +
                       (size_t)2 * C * sizeof(float) + 256 * sizeof(int64_t) + 16;
   PCB_CHECK_ARG(smem <= 227 * 1024, "pcb_mlp_fwd: tile needs %zu B shared memory", smem);
-  static size_t configured = 0;
-  if (smem > configured) {
+  static DevFlag configured;
+  if (!configured) {
     cudaFuncSetAttribute(mlp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (cudaFuncSetAttribute(mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)) != cudaSuccess) {
       set_error("pcb_mlp_fwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
       return PCB_ERR_CUDA;
     }
-    configured = 227 * 1024;
+    configured = true;
   }
   // top levels: persistent warp-specialised kernel (weights resident, single K / hidden chunk)
   {

@@ -30,8 +30,24 @@ __global__ void __launch_bounds__(256) grad_sumsq_kernel(const float* __restrict
   }
 }
 
+// seg_active[i] = 1 iff segment i's gradient has a non-zero element.  A parameter that received no gradient at all (unused
+// deep-supervision heads, MedNeXt's dummy_tensor: its slice of the arena stays exactly zero) is SKIPPED — torch.optim
+// skips parameters whose .grad is None, which is what DDP(find_unused_parameters=True) leaves for them: no weight
+// decay, no moment decay, no EMA drift relative to the reference.
+__global__ void __launch_bounds__(256) seg_active_kernel(const float* __restrict__ g, const int64_t* __restrict__ seg_end,
+                                                         int nseg, int* __restrict__ active) {
+  const int seg = blockIdx.x;
+  if (seg >= nseg) return;
+  const int64_t lo = seg == 0 ? 0 : seg_end[seg - 1], hi = seg_end[seg];
+  int any = 0;
+  for (int64_t i = lo + threadIdx.x; i < hi && !any; i += blockDim.x) any |= (g[i] != 0.f);
+  any = __syncthreads_or(any);
+  if (threadIdx.x == 0) active[seg] = any;
+}
+
 struct AdamArgs {
   float* p; const float* g; float* m; float* v; float* ema;
+  const int* active;
   int64_t n;
   const int64_t* seg_end; const float* seg_lr; const float* seg_wd; int nseg;
   float beta1, beta2, eps, max_norm, grad_scale, ema_decay;
@@ -51,10 +67,13 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
 }
 
 __global__ void __launch_bounds__(256) adamw_kernel(AdamArgs a) {
-  extern __shared__ int64_t s_end[];                      // [nseg] ends, then lr / wd floats
+  extern __shared__ int64_t s_end[];                      // [nseg] ends, then lr / wd floats, then active flags
   float* s_lr = reinterpret_cast<float*>(s_end + a.nseg);
   float* s_wd = s_lr + a.nseg;
-  for (int i = threadIdx.x; i < a.nseg; i += blockDim.x) { s_end[i] = a.seg_end[i]; s_lr[i] = a.seg_lr[i]; s_wd[i] = a.seg_wd[i]; }
+  int* s_act = reinterpret_cast<int*>(s_wd + a.nseg);
+  for (int i = threadIdx.x; i < a.nseg; i += blockDim.x) {
+    s_end[i] = a.seg_end[i]; s_lr[i] = a.seg_lr[i]; s_wd[i] = a.seg_wd[i]; s_act[i] = a.active ? a.active[i] : 1;
+  }
   __syncthreads();
   const float t = a.step[0] + 1.0f;                       // this step's index (the host-side wrapper bumps a.step afterwards)
   const float bc1 = 1.0f - (float)pow((double)a.beta1, (double)t);
@@ -72,6 +91,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(AdamArgs a) {
     while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_end[mid] > i0) hi = mid; else lo = mid + 1; }
     int seg = lo;
     if (i0 + 4 <= a.n && s_end[seg] >= i0 + 4) {           // fast path: 4 elements of one segment, 128-bit accesses
+      if (!s_act[seg]) continue;
       float4 p = reinterpret_cast<float4*>(a.p)[i4], m = reinterpret_cast<float4*>(a.m)[i4], v = reinterpret_cast<float4*>(a.v)[i4];
       const float4 g = __ldg(reinterpret_cast<const float4*>(a.g) + i4);
       float4 e = a.ema ? reinterpret_cast<float4*>(a.ema)[i4] : make_float4(0, 0, 0, 0);
@@ -85,6 +105,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(AdamArgs a) {
     } else {
       for (int64_t i = i0; i < i0 + 4 && i < a.n; ++i) {
         while (s_end[seg] <= i) ++seg;
+        if (!s_act[seg]) continue;
         adam_one(a.p[i], __fmul_rn(a.g[i], gs), a.m[i], a.v[i], a.ema ? a.ema + i : nullptr, s_lr[seg], s_wd[seg], a.beta1,
                  a.beta2, a.eps, bc1, bc2_sqrt, a.ema_decay);
       }
@@ -114,7 +135,7 @@ extern "C" int pcb_grad_sumsq(const float* grad, int64_t n, double* out, void* s
 extern "C" int pcb_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* ema, int64_t n,
                               const int64_t* seg_end, const float* seg_lr, const float* seg_wd, int nseg, float beta1,
                               float beta2, float eps, float* step, const double* grad_sumsq, float max_norm,
-                              float grad_scale, float ema_decay, void* stream) {
+                              float grad_scale, float ema_decay, int32_t* seg_active, void* stream) {
   PCB_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && seg_end && seg_lr && seg_wd && step && n > 0 && nseg > 0,
                 "pcb_adamw_step: null argument");
   PCB_CHECK_ARG(nseg <= 4096, "pcb_adamw_step: at most 4096 parameter segments (got %d)", nseg);
@@ -122,12 +143,16 @@ extern "C" int pcb_adamw_step(float* param, const float* grad, float* exp_avg, f
                        reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq) |
                        reinterpret_cast<uintptr_t>(ema);
   PCB_CHECK_ARG((al & 15) == 0, "pcb_adamw_step: the arenas must be 16-byte aligned");
-  AdamArgs a{param, grad, exp_avg, exp_avg_sq, ema, n, seg_end, seg_lr, seg_wd, nseg, beta1, beta2, eps, max_norm, grad_scale,
-             ema_decay, step, grad_sumsq};
+  AdamArgs a{param, grad, exp_avg, exp_avg_sq, ema, seg_active, n, seg_end, seg_lr, seg_wd, nseg, beta1, beta2, eps, max_norm,
+             grad_scale, ema_decay, step, grad_sumsq};
   int64_t blocks = ((n + 3) / 4 + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   cudaStream_t st = (cudaStream_t)stream;
-  adamw_kernel<<<(unsigned)blocks, 256, (size_t)nseg * (sizeof(int64_t) + 2 * sizeof(float)), st>>>(a);
+  if (seg_active != nullptr) {
+    seg_active_kernel<<<(unsigned)nseg, 256, 0, st>>>(grad, seg_end, nseg, seg_active);
+    PCB_CHECK_LAUNCH("pcb_adamw_step(active)");
+  }
+  adamw_kernel<<<(unsigned)blocks, 256, (size_t)nseg * (sizeof(int64_t) + 2 * sizeof(float) + sizeof(int)), st>>>(a);
   PCB_CHECK_LAUNCH("pcb_adamw_step");
   bump_step_kernel<<<1, 32, 0, st>>>(step);
   PCB_CHECK_LAUNCH("pcb_adamw_step(step)");

@@ -466,3 +466,147 @@ extern "C" int pcb_sw_normalize(void* value, const void* weight, int dtype, int6
   PCB_CHECK_LAUNCH("pcb_sw_normalize");
   return PCB_OK;
 }
+
+// ---------------------------------------------------------------------------- the native tile loop (pcb_sw_run)
+// window.py:563-683 for a pcb_net: for every batch of windows  crop+pad -> network -> overlap-add blend, all enqueued
+// by the library.  The batch body reads its window starts from a device table through a device cursor, so ONE captured
+// CUDA graph serves every batch (use_graph): per batch the host does a single cudaGraphLaunch instead of ~50 kernel
+// launches.  Windows are blended in list order (pcb_sw_accumulate_batch semantics) => same fp association as the
+// reference's sequential loop.
+extern "C" void** pcb_net_graph_slot(pcb_net* net, uint64_t** key_out);
+extern "C" int32_t pcb_net_in_channels(const pcb_net* net);
+extern "C" int32_t pcb_net_head_channels(const pcb_net* net, int32_t head);
+extern "C" int32_t pcb_net_num_heads(const pcb_net* net);
+
+namespace {
+struct SwRunLayout { int64_t table, cursor, batch, pred, net, total; int64_t padded; };
+SwRunLayout sw_run_layout(const pcb_net* net, int head, const int64_t roi[3], int sw_batch, int64_t nstarts, int vol_dtype,
+                          int acc_dtype) {
+  SwRunLayout l;
+  auto al = [](int64_t v) { return (v + 255) & ~(int64_t)255; };
+  const int64_t per = roi[0] * roi[1] * roi[2];
+  l.padded = (nstarts + sw_batch - 1) / sw_batch * sw_batch;
+  int64_t off = 0;
+  l.table = off; off += al(l.padded * 3 * (int64_t)sizeof(int64_t));
+  l.cursor = off; off += 256;
+  l.batch = off; off += al((int64_t)sw_batch * pcb_net_in_channels(net) * per * (int64_t)dtype_size(vol_dtype));
+  l.pred = off; off += al((int64_t)sw_batch * pcb_net_head_channels(net, head) * per * (int64_t)dtype_size(acc_dtype));
+  l.net = off;
+  const int64_t nw = pcb_net_workspace_bytes(net, sw_batch, roi);
+  l.total = nw < 0 ? -1 : off + nw;
+  return l;
+}
+}  // namespace
+
+extern "C" int64_t pcb_sw_run_workspace_bytes(const pcb_net* net, int head, const int64_t roi[3], int sw_batch, int64_t nstarts,
+                                              int vol_dtype, int acc_dtype) {
+  if (!net || !roi || sw_batch < 1 || sw_batch > SW_MAXB || nstarts < 1 || head < 0 || head >= pcb_net_num_heads(net)) return -1;
+  return sw_run_layout(net, head, roi, sw_batch, nstarts, vol_dtype, acc_dtype).total;
+}
+
+extern "C" int pcb_sw_run(pcb_net* net, int head, const void* vol, int vol_dtype, const int64_t image[3], const int64_t roi[3],
+                          int pad_mode, double cval, int sw_batch, const int64_t* starts, int64_t nstarts, const void* map,
+                          void* value, void* weight, int acc_dtype, const int64_t acc_size[3], void* workspace,
+                          int64_t ws_bytes, int use_graph, void* stream) {
+  PCB_CHECK_ARG(net && vol && image && roi && starts && map && value && weight && acc_size && workspace, "pcb_sw_run: null argument");
+  PCB_CHECK_ARG(head >= 0 && head < pcb_net_num_heads(net), "pcb_sw_run: bad head %d", head);
+  PCB_CHECK_ARG(sw_batch >= 1 && sw_batch <= SW_MAXB, "pcb_sw_run: sw_batch must be 1..%d (got %d)", SW_MAXB, sw_batch);
+  PCB_CHECK_ARG(nstarts >= 1, "pcb_sw_run: no windows");
+  PCB_CHECK_ARG(pad_mode >= 0 && pad_mode <= 3, "pcb_sw_run: bad padding mode %d", pad_mode);
+  PCB_CHECK_ARG(vol_dtype >= PCB_F32 && vol_dtype <= PCB_BF16 && acc_dtype >= PCB_F32 && acc_dtype <= PCB_BF16, "pcb_sw_run: bad dtype");
+  PCB_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "pcb_sw_run: workspace must be 256-byte aligned");
+  for (int64_t w = 0; w < nstarts; ++w)
+    for (int a = 0; a < 3; ++a)
+      PCB_CHECK_ARG(starts[3 * w + a] >= 0 && starts[3 * w + a] + roi[a] <= acc_size[a],
+                    "pcb_sw_run: window %lld outside the accumulator", (long long)w);
+  const SwRunLayout l = sw_run_layout(net, head, roi, sw_batch, nstarts, vol_dtype, acc_dtype);
+  PCB_CHECK_ARG(l.total > 0 && l.total <= ws_bytes, "pcb_sw_run: workspace of %lld bytes needed, %lld given", (long long)l.total,
+                (long long)ws_bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  int64_t* d_table = (int64_t*)(ws + l.table);
+  int64_t* d_cursor = (int64_t*)(ws + l.cursor);
+  void* d_batch = ws + l.batch;
+  void* d_pred = ws + l.pred;
+  const int Cin = pcb_net_in_channels(net), ncls = pcb_net_head_channels(net, head), nheads = pcb_net_num_heads(net);
+  // starts table (padded to whole batches with skip sentinels) + cursor = 0
+  std::vector<int64_t> table((size_t)l.padded * 3, SW_SKIP);
+  memcpy(table.data(), starts, (size_t)nstarts * 3 * sizeof(int64_t));
+  if (cudaMemcpyAsync(d_table, table.data(), table.size() * sizeof(int64_t), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+      cudaMemsetAsync(d_cursor, 0, 256, st) != cudaSuccess ||
+      cudaMemsetAsync(d_batch, 0, (size_t)(l.pred - l.batch), st) != cudaSuccess ||
+      cudaStreamSynchronize(st) != cudaSuccess) {      // `table` is a host temporary (once per call, not per batch)
+    set_error("pcb_sw_run: staging the window table failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return PCB_ERR_CUDA;
+  }
+  std::vector<void*> outs((size_t)nheads, nullptr);
+  outs[head] = d_pred;
+  WinList wl;
+  memset(&wl, 0, sizeof(wl));
+  wl.table = d_table; wl.cursor = d_cursor; wl.total = l.padded; wl.n = sw_batch;
+  auto body = [&](cudaStream_t s) -> int {
+    int rc = extract_launch(vol, vol_dtype, Cin, image, roi, wl, pad_mode, cval, d_batch, s);
+    if (rc) return rc;
+    rc = pcb_net_forward(net, d_batch, vol_dtype, sw_batch, roi, outs.data(), acc_dtype, ws + l.net, ws_bytes - l.net, s);
+    if (rc) return rc;
+    rc = accumulate_batch_launch(d_pred, map, value, weight, acc_dtype, ncls, roi, acc_size, wl, s);
+    if (rc) return rc;
+    advance_cursor_kernel<<<1, 32, 0, s>>>(d_cursor, (int64_t)sw_batch);
+    PCB_CHECK_LAUNCH("pcb_sw_run(cursor)");
+    return PCB_OK;
+  };
+  const int64_t nbatches = l.padded / sw_batch;
+  int rc = body(st);                                 // first batch eagerly: configures kernels, resolves driver entry points
+  if (rc) return rc;
+  int64_t done = 1;
+  if (use_graph && nbatches - done >= 2) {
+    uint64_t* key = nullptr;
+    void** slot = pcb_net_graph_slot(net, &key);
+    const uint64_t want[12] = {(uint64_t)vol, (uint64_t)value, (uint64_t)weight, (uint64_t)map, (uint64_t)workspace,
+                               (uint64_t)(image[0] * 1000003 + image[1] * 1009 + image[2]),
+                               (uint64_t)(roi[0] * 1000003 + roi[1] * 1009 + roi[2]),
+                               (uint64_t)(acc_size[0] * 1000003 + acc_size[1] * 1009 + acc_size[2]),
+                               (uint64_t)(vol_dtype * 16 + acc_dtype + 256 * pad_mode + 4096 * sw_batch + 65536 * head),
+                               (uint64_t)l.padded, (uint64_t)(int64_t)(cval * 1e6), (uint64_t)(uintptr_t)st};
+    cudaGraphExec_t exec = (cudaGraphExec_t)*slot;
+    if (exec != nullptr && memcmp(key, want, sizeof(want)) != 0) { cudaGraphExecDestroy(exec); exec = nullptr; *slot = nullptr; }
+    if (exec == nullptr) {
+      // the body is recorded on a private stream (the caller's may be the legacy default stream, which cannot capture);
+      // nothing executes during capture, and the instantiated graph is launched on the caller's stream
+      cudaGraph_t graph = nullptr;
+      cudaStream_t cs = nullptr;
+      if (cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+        if (cs) cudaStreamDestroy(cs);
+        set_error("pcb_sw_run: cudaStreamBeginCapture failed: %s", cudaGetErrorString(cudaGetLastError())); return PCB_ERR_CUDA;
+      }
+      rc = body(cs);
+      const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+      cudaStreamDestroy(cs);
+      if (rc || ce != cudaSuccess || graph == nullptr) {
+        if (graph) cudaGraphDestroy(graph);
+        if (!rc) { set_error("pcb_sw_run: graph capture failed: %s", cudaGetErrorString(ce)); rc = PCB_ERR_CUDA; }
+        cudaGetLastError();
+        return rc;
+      }
+      if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+        cudaGraphDestroy(graph);
+        set_error("pcb_sw_run: cudaGraphInstantiate failed: %s", cudaGetErrorString(cudaGetLastError())); return PCB_ERR_CUDA;
+      }
+      cudaGraphDestroy(graph);
+      *slot = exec;
+      memcpy(key, want, sizeof(want));
+    }
+    for (; done < nbatches; ++done) {
+      if (cudaGraphLaunch(exec, st) != cudaSuccess) {
+        set_error("pcb_sw_run: cudaGraphLaunch failed: %s", cudaGetErrorString(cudaGetLastError())); return PCB_ERR_CUDA;
+      }
+      count_launch();
+    }
+  }
+  for (; done < nbatches; ++done) {
+    rc = body(st);
+    if (rc) return rc;
+  }
+  return PCB_OK;
+}

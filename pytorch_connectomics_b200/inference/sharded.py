@@ -136,7 +136,7 @@ class ZSlabShardedEngine:
 
     def __init__(self, *, roi_size, sw_batch_size: int, overlap, mode: str, padding_mode: str = "constant",
                  cval: float = 0.0, device=None, group: Optional[dist.ProcessGroup] = None,
-                 rank: Optional[int] = None, world: Optional[int] = None) -> None:
+                 rank: Optional[int] = None, world: Optional[int] = None, cuda_graph: bool = True) -> None:
         self.roi = tuple(int(v) for v in roi_size)
         if len(self.roi) != 3:
             raise ValueError(f"ZSlabShardedEngine needs a 3-D roi_size, got {roi_size}")
@@ -147,6 +147,7 @@ class ZSlabShardedEngine:
         self.cval = float(cval)
         self.device = device
         self.group = group
+        self.cuda_graph = bool(cuda_graph)
         use_dist = dist.is_available() and dist.is_initialized()
         self.rank = rank if rank is not None else (dist.get_rank(group) if use_dist else 0)
         self.world = world if world is not None else (dist.get_world_size(group) if use_dist else 1)
@@ -167,21 +168,10 @@ class ZSlabShardedEngine:
             vol = inputs[:, :, z0:z1].to(dev, non_blocking=True)
         local_image = (z1 - z0, plan.image[1], plan.image[2])
         starts = [(s[0] - z0, s[1], s[2]) for s in plan.windows]
-        value = weight = wmap = None
-        for b0 in range(0, len(starts), self.sw_batch_size):
-            chunk = starts[b0:b0 + self.sw_batch_size]
-            batch = W._extract_starts(vol, chunk, roi, self.padding_mode, self.cval)
-            with torch.no_grad():
-                out = network(batch)
-            W.check_network_output(out, len(chunk), None if value is None else int(value.shape[1]), roi,
-                                   "ZSlabShardedEngine")
-            if value is None:
-                cout, odt = int(out.shape[1]), out.dtype
-                wmap = W.build_sliding_importance_map(roi, mode=self.mode, device=dev, dtype=odt)
-                value = torch.zeros((1, cout, *local_image), device=dev, dtype=odt)
-                weight = torch.zeros((1, 1, *local_image), device=dev, dtype=odt)
-            out = out.to(device=dev, dtype=value.dtype).contiguous()
-            W._accumulate_batch(out, wmap, value, weight, roi, local_image, chunk)
+        value, weight, _ = W.run_window_list(vol, network, starts, roi=roi, image=local_image,
+                                             sw_batch_size=self.sw_batch_size, padding_mode=self.padding_mode,
+                                             cval=self.cval, mode=self.mode, sw_device=dev, work_device=dev,
+                                             probe_first=False, cuda_graph=self.cuda_graph, who="ZSlabShardedEngine")
         return value, weight
 
     def run_slab(self, slab: torch.Tensor, network: Callable[[torch.Tensor], torch.Tensor], plan: SlabPlan):

@@ -368,6 +368,74 @@ def check_network_output(out, n: int, cout: Optional[int], roi, who: str) -> tor
     return out
 
 
+def native_plan_of(network):
+    """The ``pcb_net`` plan behind ``network`` when it is a pcb200 MedNeXt (module or wrapper) in inference mode, else
+    ``None``.  Arbitrary callables (lambdas, TTA closures, other frameworks' modules) run through the generic loop."""
+    getter = getattr(network, "native_plan", None)
+    if getter is None or not callable(getter):
+        return None
+    try:
+        return getter()
+    except Exception:          # building the plan is an optimisation, never a reason to fail the inference call
+        logger.debug("native plan unavailable", exc_info=True)
+        return None
+
+
+def run_window_list(vol: torch.Tensor, network, starts, *, roi, image, sw_batch_size: int, padding_mode: str, cval: float,
+                    mode: str, sw_device, work_device, value=None, weight=None, wmap=None, probe_first: bool = True,
+                    cuda_graph: bool = True, who: str = "sliding window"):
+    """The tile loop of ``window.py:603-655`` over ``starts`` (grid order) on a device-resident ``vol`` [1,C,*image]:
+    crop+pad -> network -> ``value += pred*map; weight += map`` into the given (or new, zeroed) accumulators.
+
+    * ``network`` is a pcb200 MedNeXt: ONE library call (``pcb_sw_run``) runs every batch — crop, the whole network and
+      the blend are enqueued natively, as a replayed CUDA graph per batch when ``cuda_graph``;
+    * any other callable: crop kernel -> ``network(batch)`` -> one blend launch per batch.
+    Both blend in list order with the same arithmetic, so the accumulators are bit-identical for identical predictions."""
+    roi = tuple(int(v) for v in roi)
+    state = {"value": value, "weight": weight, "wmap": wmap}
+    plan = native_plan_of(network) if (len(roi) == 3 and vol.is_cuda and vol.device == torch.device(work_device)
+                                       and torch.device(sw_device) == vol.device) else None
+    if plan is not None and starts and int(vol.shape[1]) == plan.in_channels and all(r % 16 == 0 for r in roi) \
+            and padding_mode in L.PAD and len(plan.head_channels) == 1 and plan.device == vol.device:
+        odt = plan.model._odt(vol)
+        if state["value"] is None:
+            state["wmap"] = build_sliding_importance_map(roi, mode=mode, device=work_device, dtype=odt)
+            state["value"] = torch.zeros((1, plan.head_channels[0], *image), device=work_device, dtype=odt)
+            state["weight"] = torch.zeros((1, 1, *image), device=work_device, dtype=odt)
+        if state["value"].dtype == odt and int(state["value"].shape[1]) == plan.head_channels[0]:
+            plan.sw_run(vol.contiguous(), roi, starts, state["wmap"], state["value"], state["weight"],
+                        padding_mode=padding_mode, cval=cval, sw_batch=sw_batch_size, use_graph=cuda_graph)
+            return state["value"], state["weight"], state["wmap"]
+
+    def run(batch_starts):
+        batch = _extract_starts(vol, batch_starts, roi, padding_mode, cval)
+        if batch.device != sw_device:
+            batch = batch.to(sw_device, non_blocking=True)
+        with torch.no_grad():
+            return network(batch)
+
+    def blend(out, batch_starts) -> None:
+        if state["value"] is None:
+            check_network_output(out, len(batch_starts), None, roi, who)
+            cout, odt = int(out.shape[1]), out.dtype
+            state["wmap"] = build_sliding_importance_map(roi, mode=mode, device=work_device, dtype=odt)
+            state["value"] = torch.zeros((1, cout, *image), device=work_device, dtype=odt)
+            state["weight"] = torch.zeros((1, 1, *image), device=work_device, dtype=odt)
+        v = state["value"]
+        check_network_output(out, len(batch_starts), int(v.shape[1]), roi, who)
+        out = out.to(device=work_device, dtype=v.dtype).contiguous()
+        _accumulate_batch(out, state["wmap"], v, state["weight"], roi, image, batch_starts)
+
+    rest = starts
+    if probe_first and starts:          # the reference probes with the first window alone (window.py:612-639)
+        blend(run(starts[:1]), starts[:1])
+        rest = starts[1:]
+    for b0 in range(0, len(rest), sw_batch_size):
+        chunk = rest[b0:b0 + sw_batch_size]
+        blend(run(chunk), chunk)
+    return state["value"], state["weight"], state["wmap"]
+
+
 class EagerSlidingWindowEngine:
     """``window.py:530-683`` — ``engine(inputs=[1,C,*spatial], network=fn) -> [1,Cout,*spatial]``.
 
@@ -379,7 +447,8 @@ class EagerSlidingWindowEngine:
     both accumulators, and the fp sums still associate in grid order (bit-identical to the one-pass result)."""
 
     def __init__(self, *, roi_size, sw_batch_size: int, overlap, mode: str, padding_mode: str, cval: float,
-                 sw_device=None, output_device=None, progress: bool = False, stream_z_starts: int = 0) -> None:
+                 sw_device=None, output_device=None, progress: bool = False, stream_z_starts: int = 0,
+                 cuda_graph: bool = True) -> None:
         self.roi_size = tuple(int(v) for v in roi_size)
         self.sw_batch_size = max(1, int(sw_batch_size))
         self.overlap = overlap
@@ -390,40 +459,15 @@ class EagerSlidingWindowEngine:
         self.output_device = output_device
         self.progress = bool(progress)
         self.stream_z_starts = int(stream_z_starts)     # z-starts per streamed group (0 = auto: 4)
+        self.cuda_graph = bool(cuda_graph)              # native tile loop: replay one captured graph per window batch
 
     # ---- one pass over `starts` on a device-resident volume, into given (or new) accumulators
     def _run_windows(self, vol, network, starts, image, sw_device, work_device, value=None, weight=None, wmap=None,
                      probe_first=True):
-        roi = self.roi_size
-        state = {"value": value, "weight": weight, "wmap": wmap}
-
-        def run(batch_starts):
-            batch = _extract_starts(vol, batch_starts, roi, self.padding_mode, self.cval)
-            if batch.device != sw_device:
-                batch = batch.to(sw_device, non_blocking=True)
-            with torch.no_grad():
-                return network(batch)
-
-        def blend(out, batch_starts) -> None:
-            if state["value"] is None:
-                check_network_output(out, len(batch_starts), None, roi, "EagerSlidingWindowEngine")
-                cout, odt = int(out.shape[1]), out.dtype
-                state["wmap"] = build_sliding_importance_map(roi, mode=self.mode, device=work_device, dtype=odt)
-                state["value"] = torch.zeros((1, cout, *image), device=work_device, dtype=odt)
-                state["weight"] = torch.zeros((1, 1, *image), device=work_device, dtype=odt)
-            v = state["value"]
-            check_network_output(out, len(batch_starts), int(v.shape[1]), roi, "EagerSlidingWindowEngine")
-            out = out.to(device=work_device, dtype=v.dtype).contiguous()
-            _accumulate_batch(out, state["wmap"], v, state["weight"], roi, image, batch_starts)
-
-        rest = starts
-        if probe_first and starts:          # the reference probes with the first window alone (window.py:612-639)
-            blend(run(starts[:1]), starts[:1])
-            rest = starts[1:]
-        for b0 in range(0, len(rest), self.sw_batch_size):
-            chunk = rest[b0:b0 + self.sw_batch_size]
-            blend(run(chunk), chunk)
-        return state["value"], state["weight"], state["wmap"]
+        return run_window_list(vol, network, starts, roi=self.roi_size, image=image, sw_batch_size=self.sw_batch_size,
+                               padding_mode=self.padding_mode, cval=self.cval, mode=self.mode, sw_device=sw_device,
+                               work_device=work_device, value=value, weight=weight, wmap=wmap, probe_first=probe_first,
+                               cuda_graph=self.cuda_graph, who="EagerSlidingWindowEngine")
 
     def __call__(self, inputs: torch.Tensor, network: Callable[[torch.Tensor], torch.Tensor]) -> torch.Tensor:
         roi = self.roi_size

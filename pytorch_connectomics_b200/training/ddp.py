@@ -19,19 +19,36 @@ import torch.distributed as dist
 
 
 class FlatGradArena:
-    def __init__(self, params: Iterable[torch.nn.Parameter]):
+    """``align``: every parameter's slice starts at a multiple of ``align`` elements (default 64 = 256 B), so slices of
+    the arena — and of the parameter / optimizer-state arenas laid out the same way (``training/optim.py``) — can be
+    handed to kernels that use 128-bit accesses; padding elements stay zero."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], align: int = 64):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("FlatGradArena: no trainable parameters")
         dev = self.params[0].device
-        total = sum(p.numel() for p in self.params)
-        self.buffer = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.align = max(1, int(align))
+        self.offsets: List[int] = []
         off = 0
         for p in self.params:
             if p.dtype != torch.float32 or p.device != dev:
                 raise ValueError("FlatGradArena expects fp32 parameters on one device")
-            p.grad = self.buffer[off:off + p.numel()].view_as(p)
-            off += p.numel()
+            self.offsets.append(off)
+            off += -(-p.numel() // self.align) * self.align
+        self.total = off
+        self.buffer = torch.zeros(self.total, device=dev, dtype=torch.float32)
+        for p, o in zip(self.params, self.offsets):
+            p.grad = self.buffer[o:o + p.numel()].view_as(p)
+
+    def view_of(self, index: int, flat: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """the slice of ``flat`` (default: the gradient arena) that belongs to parameter ``index``"""
+        p, o = self.params[index], self.offsets[index]
+        return (self.buffer if flat is None else flat)[o:o + p.numel()].view_as(p)
+
+    def packed(self) -> torch.Tensor:
+        """the gradients concatenated without padding (parameter order)"""
+        return torch.cat([self.view_of(i).reshape(-1) for i in range(len(self.params))])
 
     def zero(self) -> None:
         """Use instead of ``optimizer.zero_grad()`` (which would detach the views when set_to_none)."""
@@ -52,10 +69,9 @@ class FlatGradArena:
         """If something replaced a ``.grad`` view (``zero_grad(set_to_none=True)`` followed by a backward pass leaves
         autograd-allocated tensors), copy those gradients into the arena and re-attach the views, so the exchange step
         never reduces a stale buffer.  Returns the number of repaired parameters."""
-        off, fixed = 0, 0
-        for p in self.params:
-            n = p.numel()
-            view = self.buffer[off:off + n].view_as(p)
+        fixed = 0
+        for i, p in enumerate(self.params):
+            view = self.view_of(i)
             g = p.grad
             if g is None:
                 view.zero_()
@@ -65,17 +81,14 @@ class FlatGradArena:
                 view.copy_(g)
                 p.grad = view
                 fixed += 1
-            off += n
         return fixed
 
     def rebind(self) -> None:
         """Re-attach ``.grad`` views if something replaced them (e.g. ``zero_grad(set_to_none=True)``)."""
-        off = 0
-        for p in self.params:
-            view = self.buffer[off:off + p.numel()].view_as(p)
+        for i, p in enumerate(self.params):
+            view = self.view_of(i)
             if p.grad is None or p.grad.data_ptr() != view.data_ptr():
                 p.grad = view
-            off += p.numel()
 
     @staticmethod
     def _world(group) -> int:

@@ -61,22 +61,23 @@ class FusedAdamW:
         if any(p.dtype != torch.float32 or p.device != dev for p in params):
             raise ValueError("FusedAdamW expects fp32 parameters on one CUDA device")
         self.params = params
-        if arena is not None and [id(p) for p in arena.params] != [id(p) for p in params]:
-            raise ValueError("FusedAdamW: the gradient arena must cover the same parameters in the same order")
+        if arena is not None and sorted(id(p) for p in arena.params) != sorted(id(p) for p in params):
+            raise ValueError("FusedAdamW: the gradient arena must cover the same parameters")
         self.arena = arena if arena is not None else FlatGradArena(params)
-        n = sum(p.numel() for p in params)
+        if self.arena.align % 4:
+            raise ValueError("FusedAdamW needs a gradient arena with 16-byte aligned slices (align % 4 == 0)")
+        n = self.arena.total                        # padded layout of the gradient arena (16-byte aligned slices)
         self.n = n
-        self.flat = torch.empty(n, device=dev, dtype=torch.float32)
-        ends, lrs, wds, off = [], [], [], 0
-        for g in groups:
-            for p in g["params"]:
-                if not p.requires_grad:
-                    continue
-                k = p.numel()
-                self.flat[off:off + k].copy_(p.data.reshape(-1))
-                p.data = self.flat[off:off + k].view_as(p)
-                off += k
-                ends.append(off); lrs.append(float(g["lr"])); wds.append(float(g["weight_decay"]))
+        self.flat = torch.zeros(n, device=dev, dtype=torch.float32)
+        by_id = {id(p): (g["lr"], g["weight_decay"]) for g in groups for p in g["params"]}
+        ends, lrs, wds = [], [], []
+        for i, p in enumerate(self.arena.params):
+            view = self.arena.view_of(i, self.flat)
+            view.copy_(p.data)
+            p.data = view
+            nxt = self.arena.offsets[i + 1] if i + 1 < len(self.arena.params) else n
+            ends.append(nxt)                           # the padding behind a parameter belongs to its segment (stays 0)
+            lrs.append(float(by_id[id(p)][0])); wds.append(float(by_id[id(p)][1]))
         self.seg_end = torch.tensor(ends, device=dev, dtype=torch.int64)
         self.seg_lr = torch.tensor(lrs, device=dev, dtype=torch.float32)
         self.seg_wd = torch.tensor(wds, device=dev, dtype=torch.float32)
@@ -87,6 +88,7 @@ class FusedAdamW:
         self.ema_decay = float(ema_decay) if ema_decay is not None else 0.0
         self.step_count = torch.zeros(1, device=dev, dtype=torch.float32)
         self.sumsq = torch.zeros(1, device=dev, dtype=torch.float64)
+        self.seg_active = torch.ones(len(ends), device=dev, dtype=torch.int32)      # device scratch of the kernel
         self.betas, self.eps = (float(betas[0]), float(betas[1])), float(eps)
         self.max_grad_norm = float(max_grad_norm or 0.0)
         self.world_size = int(world_size)
@@ -113,7 +115,8 @@ class FusedAdamW:
                                    L.ptr(self.seg_wd), ctypes.c_int(int(self.seg_end.numel())), ctypes.c_float(self.betas[0]),
                                    ctypes.c_float(self.betas[1]), ctypes.c_float(self.eps), L.ptr(self.step_count),
                                    L.ptr(self.sumsq) if clip else None, ctypes.c_float(self.max_grad_norm),
-                                   ctypes.c_float(scale), ctypes.c_float(self.ema_decay), st), "pcb_adamw_step")
+                                   ctypes.c_float(scale), ctypes.c_float(self.ema_decay), L.ptr(self.seg_active), st),
+                "pcb_adamw_step")
         L.PARAM_EPOCH[0] += 1          # parameters changed behind autograd's back: kernel-layout weight caches repack
 
     def grad_norm(self) -> torch.Tensor:
@@ -124,11 +127,7 @@ class FusedAdamW:
         """``{id(param): ema view}`` (what the EMA callback swaps in for validation)"""
         if self.ema is None:
             return {}
-        out, off = {}, 0
-        for p in self.params:
-            out[id(p)] = self.ema[off:off + p.numel()].view_as(p)
-            off += p.numel()
-        return out
+        return {id(p): self.arena.view_of(i, self.ema) for i, p in enumerate(self.arena.params)}
 
     def swap_ema(self) -> None:
         """exchange live weights and EMA weights in place (``callbacks.py:909-944``: validate with EMA, then swap back)"""

@@ -231,7 +231,7 @@ def _ddp_worker(rank, world, port, q):
     net[2](net[1](net[0](x))).sum().backward()
     arena.allreduce()
     assert all(p.grad is not None and p.grad.data_ptr() >= arena.buffer.data_ptr() for p in net.parameters())
-    q.put((rank, arena.buffer.clone().numpy(), torch.cat([p.detach().reshape(-1) for p in net.parameters()]).numpy(),
+    q.put((rank, arena.packed().numpy(), torch.cat([p.detach().reshape(-1) for p in net.parameters()]).numpy(),
            float(net[4].running_mean[0])))   # by value: torch tensors travel as fds that die with the worker
     dist.destroy_process_group()
 
