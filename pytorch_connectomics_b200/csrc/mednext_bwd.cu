@@ -666,20 +666,18 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_bwd_ws_kernel(MlpBwdFusedAr
   uint64_t* a_empty = bars + 4;     // [4] MMA (G4/G5 retired) -> loaders
   uint64_t* hp_full = bars + 8;     // [2] MMA (G1/G2) -> E1
   uint64_t* e1_done = bars + 10;    // [2] E1 -> MMA
-  uint64_t* d_full = bars + 12;     // [2] MMA (G3) -> E2
-  uint64_t* d_empty = bars + 14;    // [2] E2 -> MMA
-  uint64_t* h_free = bars + 16;     // [2] MMA (G3/G4/G5 retired) -> E1
-  uint64_t* w_done = bars + 18;     // every MMA of the CTA retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+  uint64_t* d_full = bars + 12;     // [2 groups][2 buffers] MMA (G3) -> E2
+  uint64_t* d_empty = bars + 16;    // [2 groups][2 buffers] E2 -> MMA
+  uint64_t* h_free = bars + 20;     // [2] MMA (G3/G4/G5 retired) -> E1
+  uint64_t* w_done = bars + 22;     // every MMA of the CTA retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 23);
 
-  const uint32_t tmem_cols = tmem_cols_pow2((uint32_t)(5 * a.H + 2 * a.C + a.Co));
+  const uint32_t tmem_cols = tmem_cols_pow2((uint32_t)(5 * a.H + 4 * a.C + a.Co));
   if (warp == WS_LOAD + WS_EPI) tmem_alloc(tmem_slot, tmem_cols);
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) { mbar_init(&a_full[i], 32); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&hp_full[i], 1); mbar_init(&e1_done[i], 128); mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 128);
-      mbar_init(&h_free[i], 1);
-    }
+    for (int i = 0; i < 2; ++i) { mbar_init(&hp_full[i], 1); mbar_init(&e1_done[i], 128); mbar_init(&h_free[i], 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 128); }
     mbar_init(w_done, 1);
     fence_mbar_init();
   }
@@ -712,8 +710,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_bwd_ws_kernel(MlpBwdFusedAr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // TMEM columns: acc1[g] g*H | accG[g] 2H + g*H | accD[g] 4H + g*C | accW3 4H+2C | accW2 4H+2C+Co
-  const uint32_t colD = 4 * a.H, colW3 = colD + 2 * a.C, colW2 = colW3 + a.Co;
+  // TMEM columns: acc1[g] g*H | accG[g] 2H + g*H | accD[g][b] 4H + (2g+b)*C | accW3 4H+4C | accW2 4H+4C+Co
+  const uint32_t colD = 4 * a.H, colW3 = colD + 4 * a.C, colW2 = colW3 + a.Co;
 
   if (warp < WS_LOAD) {
     // ===================================================================== loaders
@@ -731,63 +729,126 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_bwd_ws_kernel(MlpBwdFusedAr
     }
   } else if (warp == WS_LOAD + WS_EPI) {
     // ===================================================================== MMA issuer (one thread)
+    // The two epilogue groups are independent pipelines (group g: tiles it == g mod 2, own acc1 / accG / accD[2] / sH / sDh).
+    // The issuer POLLS their barriers and issues whichever GEMM set has its operands ready, so neither group waits behind
+    // the other's hand-off.  Per group and local tile k (it = 2k + g, operand stage s = it & 3, accD buffer b = k & 1):
+    //   first half : a_full[s]                               -> G1 Hpre -> acc1[g], G2 dG -> accG[g]      (hp_full[g])
+    //   second half: e1_done[g](k), d_empty[g][b] of k - 2   -> G3 dYhat -> accD[g][b]                    (d_full[g][b])
+    //                                                           G4 dW3 +=, G5 dW2 += (shared accumulators)  (a_empty[s], h_free[g])
     if (lane == 0) {
       const uint32_t idescH = umma_idesc_bf16(128, a.H, 0, 0), idescD = umma_idesc_bf16(128, a.C, 0, 0);
       const uint32_t idescW3 = umma_idesc_bf16(128, a.Co, 1, 1), idescW2 = umma_idesc_bf16(128, a.H, 1, 1);
       const uint64_t dW2 = umma_desc(smem_u32(sW2), 128, c8n * 128), dW3 = umma_desc(smem_u32(sW3t), 128, o8n * 128);
       const uint64_t dW2t = umma_desc(smem_u32(sW2t), 128, h8n * 128);
-      auto second_half = [&](int64_t j) {     // G3 + weight-gradient GEMMs of local tile j
-        const int gj = (int)(j & 1), sj = (int)(j & 3);
-        const int64_t u = j >> 1;
-        mbar_wait(&e1_done[gj], (uint32_t)(u & 1));
-        if (j >= 2) mbar_wait(&d_empty[gj], (uint32_t)((u - 1) & 1));
-        tc_fence_after();
-        const uint64_t dDhK = umma_desc(smem_u32(sDh + gj * stageH), 128, pitchH);
-        for (int k = 0; k < a.H / 16; ++k)
-          umma_bf16(tmem_base + colD + gj * a.C, dDhK + (uint64_t)(k * 16), dW2t + (uint64_t)(k * 16), idescD, k > 0 ? 1u : 0u);
-        tc_commit(&d_full[gj]);
-        const uint64_t aH = umma_desc(smem_u32(sH + gj * stageH), pitchH, 128), bD = umma_desc(smem_u32(sD + sj * stageD), pitchD, 128);
-        const uint64_t aA = umma_desc(smem_u32(sA + sj * stageA), pitchA, 128), bDh = umma_desc(smem_u32(sDh + gj * stageH), pitchH, 128);
-        for (int k = 0; k < 8; ++k)
-          umma_bf16(tmem_base + colW3, aH + (uint64_t)(k * 2 * (pitchH >> 4)), bD + (uint64_t)(k * 2 * (pitchD >> 4)), idescW3,
-                    (j > 0 || k > 0) ? 1u : 0u);
-        for (int k = 0; k < 8; ++k)
-          umma_bf16(tmem_base + colW2, aA + (uint64_t)(k * 2 * (pitchA >> 4)), bDh + (uint64_t)(k * 2 * (pitchH >> 4)), idescW2,
-                    (j > 0 || k > 0) ? 1u : 0u);
-        tc_commit(&a_empty[sj]);
-        tc_commit(&h_free[gj]);
-      };
-      int64_t it = 0;
-      for (int64_t g = blockIdx.x; g < fa.ntiles; g += gridDim.x, ++it) {
-        const int s = (int)(it & 3), gacc = (int)(it & 1);
-        mbar_wait(&a_full[s], (uint32_t)((it >> 2) & 1));
-        tc_fence_after();
-        const uint64_t dA = umma_desc(smem_u32(sA + s * stageA), 128, pitchA), dD = umma_desc(smem_u32(sD + s * stageD), 128, pitchD);
-        for (int k = 0; k < a.C / 16; ++k)
-          umma_bf16(tmem_base + gacc * a.H, dA + (uint64_t)(k * 16), dW2 + (uint64_t)(k * 16), idescH, k > 0 ? 1u : 0u);
-        for (int k = 0; k < a.Co / 16; ++k)
-          umma_bf16(tmem_base + 2 * a.H + gacc * a.H, dD + (uint64_t)(k * 16), dW3 + (uint64_t)(k * 16), idescH, k > 0 ? 1u : 0u);
-        tc_commit(&hp_full[gacc]);
-        if (it >= 1) second_half(it - 1);
+      const int64_t T = (fa.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;      // tiles of this CTA (>= 1)
+      int64_t kk[2] = {0, 0};
+      const int64_t nk[2] = {(T + 1) >> 1, T >> 1};
+      int ph[2] = {0, 0};
+      uint32_t wacc = 0;                                   // 0 until the first weight-gradient MMA has initialised accW3 / accW2
+      while (kk[0] < nk[0] || kk[1] < nk[1]) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (kk[g] >= nk[g]) continue;
+          const int64_t k = kk[g], it = 2 * k + g;
+          const int s = (int)(it & 3);
+          if (ph[g] == 0) {
+            if (!mbar_test(&a_full[s], (uint32_t)((it >> 2) & 1))) continue;
+            tc_fence_after();
+            const uint64_t dA = umma_desc(smem_u32(sA + s * stageA), 128, pitchA), dD = umma_desc(smem_u32(sD + s * stageD), 128, pitchD);
+            for (int q = 0; q < a.C / 16; ++q)
+              umma_bf16(tmem_base + g * a.H, dA + (uint64_t)(q * 16), dW2 + (uint64_t)(q * 16), idescH, q > 0 ? 1u : 0u);
+            for (int q = 0; q < a.Co / 16; ++q)
+              umma_bf16(tmem_base + 2 * a.H + g * a.H, dD + (uint64_t)(q * 16), dW3 + (uint64_t)(q * 16), idescH, q > 0 ? 1u : 0u);
+            tc_commit(&hp_full[g]);
+            ph[g] = 1;
+          } else {
+            if (!mbar_test(&e1_done[g], (uint32_t)(k & 1))) continue;
+            const int b = (int)(k & 1);
+            if (k >= 2 && !mbar_test(&d_empty[g * 2 + b], (uint32_t)(((k >> 1) - 1) & 1))) continue;
+            tc_fence_after();
+            const uint64_t dDhK = umma_desc(smem_u32(sDh + g * stageH), 128, pitchH);
+            for (int q = 0; q < a.H / 16; ++q)
+              umma_bf16(tmem_base + colD + (2 * g + b) * a.C, dDhK + (uint64_t)(q * 16), dW2t + (uint64_t)(q * 16), idescD, q > 0 ? 1u : 0u);
+            tc_commit(&d_full[g * 2 + b]);
+            const uint64_t aH = umma_desc(smem_u32(sH + g * stageH), pitchH, 128), bD = umma_desc(smem_u32(sD + s * stageD), pitchD, 128);
+            const uint64_t aA = umma_desc(smem_u32(sA + s * stageA), pitchA, 128), bDh = umma_desc(smem_u32(sDh + g * stageH), pitchH, 128);
+            for (int q = 0; q < 8; ++q)
+              umma_bf16(tmem_base + colW3, aH + (uint64_t)(q * 2 * (pitchH >> 4)), bD + (uint64_t)(q * 2 * (pitchD >> 4)), idescW3,
+                        (wacc | (uint32_t)q) ? 1u : 0u);
+            for (int q = 0; q < 8; ++q)
+              umma_bf16(tmem_base + colW2, aA + (uint64_t)(q * 2 * (pitchA >> 4)), bDh + (uint64_t)(q * 2 * (pitchH >> 4)), idescW2,
+                        (wacc | (uint32_t)q) ? 1u : 0u);
+            wacc = 1;
+            tc_commit(&a_empty[s]);
+            tc_commit(&h_free[g]);
+            ph[g] = 0;
+            ++kk[g];
+          }
+        }
       }
-      if (it >= 1) second_half(it - 1);
       tc_commit(w_done);
     }
   } else {
     // ===================================================================== epilogue groups
+    // Order per local tile k:  E1(k) -> e1_done -> E2(k-1).  G3 of tile k (and G1/G2 of k+1 behind it) run while the group
+    // still has the dYhat pass of tile k-1 to do, so it never idles on d_full (ncu, round 2: 22 % of all samples sat there).
     const int eg = (warp - WS_LOAD) >> 2;
     const int wq = warp & 3, row = wq * 32 + lane;
     const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
     float db3acc = 0.f;        // wq == 0: running sum_v dOut[v, lane] over this group's tiles
-    int64_t it = eg;
-    for (int64_t g = blockIdx.x + (int64_t)eg * gridDim.x; g < fa.ntiles; g += 2ll * gridDim.x, it += 2) {
-      const int64_t u = it >> 1;
-      const uint32_t par = (uint32_t)(u & 1);
+    // ---- E2 of one tile: g = dYhat -> bf16 -> HBM ; S1 += g ; S2 += g * xhat
+    auto epi2 = [&](int b, int n, int prow, const uint4 (&ypre)[4]) {
+      const bool row_ok = prow < (int)a.Vy;
+      const int64_t yrow = ((int64_t)n * a.Vy + prow) * c8n;
+      const uint32_t td = tmem_base + colD + (2 * eg + b) * a.C + lane_off;
+      const float* rs = sRstd + n * a.C; const float* mr = sMR + n * a.C;
+      double* sGn = sG + n * 2 * a.C;
+#pragma unroll
+      for (int c16 = 0; c16 < 2; ++c16) {
+        uint32_t v[16];
+        tmem_ld16(td + c16 * 16, v);
+        tmem_ld_wait();
+        float gq[16], gx[16];
+        if (row_ok) {
+          float yv[16];
+          unpack8(ypre[2 * c16], yv);
+          unpack8(ypre[2 * c16 + 1], yv + 8);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            gq[j] = round_bf16(__uint_as_float(v[j]));
+            gx[j] = gq[j] * fmaf(yv[j], rs[c16 * 16 + j], -mr[c16 * 16 + j]);
+          }
+          a.dyhat[yrow + c16 * 2] = pack8(gq);
+          a.dyhat[yrow + c16 * 2 + 1] = pack8(gq + 8);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { gq[j] = 0.f; gx[j] = 0.f; }
+        }
+        warp_colsum16(gq, lane);
+        warp_colsum16(gx, lane);
+        if (!(lane & 1)) {
+          const int col = c16 * 16 + colsum16_col(lane);
+          atomicAdd(&sGn[col], (double)gq[0]);
+          atomicAdd(&sGn[a.C + col], (double)gx[0]);
+        }
+      }
+    };
+    auto load_y = [&](uint4 (&ypre)[4], int n, int prow) {   // the row's y (L2-resident: the loaders just read it)
+      const bool row_ok = prow < (int)a.Vy;
+      const int64_t yrow = ((int64_t)n * a.Vy + prow) * c8n;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) ypre[c] = row_ok ? __ldg(a.y + yrow + c) : make_uint4(0, 0, 0, 0);
+    };
+    int64_t k = 0;
+    int p_n = 0, p_prow = 0;                              // tile whose E2 is pending
+    for (int64_t g = blockIdx.x + (int64_t)eg * gridDim.x; g < fa.ntiles; g += 2ll * gridDim.x, ++k) {
+      const int64_t it = 2 * k + eg;
       const int s = (int)(it & 3);
       const int n = (int)(g / fa.tps);
       const int tile0 = (int)((g - (int64_t)n * fa.tps) * 128);
       const int prow = tile0 + row;
-      const bool row_ok = prow < (int)a.Vy;
+      uint4 ypre[4];
+      if (k >= 1) load_y(ypre, p_n, p_prow);              // in flight during E1
       mbar_wait(&a_full[s], (uint32_t)((it >> 2) & 1));      // this group reads sD[s] itself (conv3 bias gradient)
       if (wq == 0 && lane < a.Co) {
         const uint8_t* col = sD + s * stageD + (lane >> 3) * 128 + (lane & 7) * 2;
@@ -797,8 +858,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_bwd_ws_kernel(MlpBwdFusedAr
           sacc += __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(col + (r >> 3) * pitchD + (r & 7) * 16)) << 16);
         db3acc += sacc;
       }
-      mbar_wait(&hp_full[eg], par);
-      if (u >= 1) mbar_wait(&h_free[eg], (uint32_t)((u - 1) & 1));
+      mbar_wait(&hp_full[eg], (uint32_t)(k & 1));
+      // sH / sDh[eg] are read by G3 / G4 / G5 of tile k-1 (issued an E2 pass ago); their retirement also completes d_full(k-1)
+      if (k >= 1) mbar_wait(&h_free[eg], (uint32_t)((k - 1) & 1));
       tc_fence_after();
       // ---- E1: Hact -> sH[eg], dh -> sDh[eg]
       {
@@ -836,49 +898,23 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_bwd_ws_kernel(MlpBwdFusedAr
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&e1_done[eg]);
-      // ---- E2: g = dYhat -> bf16 -> HBM ; S1 += g ; S2 += g * xhat
-      const int64_t yrow = ((int64_t)n * a.Vy + prow) * c8n;
-      uint4 ypre[4];                                       // the row's y (L2-resident: the loaders just read it)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) ypre[c] = row_ok ? __ldg(a.y + yrow + c) : make_uint4(0, 0, 0, 0);
-      mbar_wait(&d_full[eg], par);
-      tc_fence_after();
-      {
-        const uint32_t td = tmem_base + colD + eg * a.C + lane_off;
-        const float* rs = sRstd + n * a.C; const float* mr = sMR + n * a.C;
-        double* sGn = sG + n * 2 * a.C;
-#pragma unroll
-        for (int c16 = 0; c16 < 2; ++c16) {
-          uint32_t v[16];
-          tmem_ld16(td + c16 * 16, v);
-          tmem_ld_wait();
-          float gq[16], gx[16];
-          if (row_ok) {
-            float yv[16];
-            unpack8(ypre[2 * c16], yv);
-            unpack8(ypre[2 * c16 + 1], yv + 8);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              gq[j] = round_bf16(__uint_as_float(v[j]));
-              gx[j] = gq[j] * fmaf(yv[j], rs[c16 * 16 + j], -mr[c16 * 16 + j]);
-            }
-            a.dyhat[yrow + c16 * 2] = pack8(gq);
-            a.dyhat[yrow + c16 * 2 + 1] = pack8(gq + 8);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) { gq[j] = 0.f; gx[j] = 0.f; }
-          }
-          warp_colsum16(gq, lane);
-          warp_colsum16(gx, lane);
-          if (!(lane & 1)) {
-            const int col = c16 * 16 + colsum16_col(lane);
-            atomicAdd(&sGn[col], (double)gq[0]);
-            atomicAdd(&sGn[a.C + col], (double)gx[0]);
-          }
-        }
+      if (k >= 1) {
+        const int b = (int)((k - 1) & 1);
+        mbar_wait(&d_full[eg * 2 + b], (uint32_t)(((k - 1) >> 1) & 1));   // already complete (h_free above); orders the TMEM read
+        tc_fence_after();
+        epi2(b, p_n, p_prow, ypre);
+        tc_fence_before();
+        mbar_arrive(&d_empty[eg * 2 + b]);
       }
-      tc_fence_before();
-      mbar_arrive(&d_empty[eg]);
+      p_n = n; p_prow = prow;
+    }
+    if (k >= 1) {                                           // drain: E2 of the group's last tile
+      uint4 ypre[4];
+      load_y(ypre, p_n, p_prow);
+      const int b = (int)((k - 1) & 1);
+      mbar_wait(&d_full[eg * 2 + b], (uint32_t)(((k - 1) >> 1) & 1));
+      tc_fence_after();
+      epi2(b, p_n, p_prow, ypre);
     }
     if (wq == 0 && lane < a.Co) sDb3[eg * a.Co + lane] = db3acc;
   }
@@ -1319,7 +1355,7 @@ static void ws2_magic(uint32_t d, uint32_t& m, int& sh) {
 static size_t mlp_bwd_ws_smem(int C, int H, int Co, int N) {
   return (size_t)H * C * 2 + (size_t)H * Co * 2 + (size_t)C * H * 2 + (size_t)4 * 16 * (C / 8 + 1) * 128 + (size_t)4 * 16 * (Co / 8) * 128 +
          (size_t)4 * 16 * (H / 8) * 128 + 2048 + (size_t)4 * N * C * 4 + (size_t)H * 4 + (size_t)2 * Co * 4 + (size_t)N * 2 * C * 8 +
-         19 * 8 + 16 + 128;
+         23 * 8 + 16 + 128;
 }
 
 static size_t mlp_bwd_fused_smem(int C, int H, int Co, int N) {

@@ -1101,6 +1101,9 @@ struct MlpFusedArgs {
   int ld16;          // opt-in (PCB_FWD_LD16=1): 16 instead of 8 loads in flight per loader lane
   uint32_t dm2, dm1; // magic multipliers of the exact division by o2 / o1 (n < 2^31):  n / d == (n * dm) >> ds
   int ds2, ds1;
+  uint32_t dmt;      // ... and by tps (tile -> sample)
+  int dst;
+  int nb2;           // acc2 TMEM buffers per epilogue group: 2 = epilogue 2 of tile k-1 runs after epilogue 1 of tile k
 };
 
 // exact n / d for 0 <= n < 2^31 with m = ceil(2^(31+l) / d), l = ceil(log2 d), shift = 31 + l (host: mf_magic)
@@ -1236,17 +1239,17 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_fused_kernel(MlpFusedArgs f
   uint64_t* a_empty = bars + 4;     // [4] MMA -> loaders
   uint64_t* acc1_full = bars + 8;   // [2] MMA -> epilogue
   uint64_t* h_full = bars + 10;     // [2] epilogue -> MMA
-  uint64_t* acc2_full = bars + 12;  // [2] MMA -> epilogue
-  uint64_t* acc2_empty = bars + 14; // [2] epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* acc2_full = bars + 12;  // [2 groups][2 buffers] MMA -> epilogue
+  uint64_t* acc2_empty = bars + 16; // [2 groups][2 buffers] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  const int NB2 = fa.nb2;           // acc2 buffers per epilogue group
 
-  const uint32_t tmem_cols = tmem_cols_pow2(2 * (a.H + a.Co));
+  const uint32_t tmem_cols = tmem_cols_pow2(2 * a.H + 2 * NB2 * a.Co);
   if (warp == MF_LOAD_WARPS + MF_EPI_WARPS) tmem_alloc(tmem_slot, tmem_cols);
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) { mbar_init(&a_full[i], 32 * (MF_LOAD_WARPS / NST)); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&acc1_full[i], 1); mbar_init(&h_full[i], 128); mbar_init(&acc2_full[i], 1); mbar_init(&acc2_empty[i], 128);
-    }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc1_full[i], 1); mbar_init(&h_full[i], 128); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&acc2_full[i], 1); mbar_init(&acc2_empty[i], 128); }
     fence_mbar_init();
   }
   // resident weights, biases, GroupNorm affine of every sample
@@ -1286,7 +1289,7 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_fused_kernel(MlpFusedArgs f
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // TMEM columns: acc1[g] at g*H, acc2[g] at 2H + g*Co
+  // TMEM columns: acc1[g] at g*H, acc2[g][b] at 2H + (g*NB2 + b)*Co
 
   if (warp < MF_LOAD_WARPS) {
     // ===================================================================== loaders
@@ -1412,42 +1415,62 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_fused_kernel(MlpFusedArgs f
     }
   } else if (warp == MF_LOAD_WARPS + MF_EPI_WARPS) {
     // ===================================================================== MMA issuer (one thread)
+    // The two epilogue groups are independent pipelines (group g owns the CTA's tiles it == g mod 2, its own acc1 / sH / acc2
+    // buffers and barriers).  The issuer serves them by POLLING (mbarrier.test_wait): whichever group's next GEMM has its
+    // operands ready is issued, so a group never waits behind a barrier of the other one.  Per group and local tile k:
+    //   GEMM1(k): a_full(tile)                                  -> acc1[g]        (acc1[g] is free: h_full(k-1) was seen)
+    //   GEMM2(k): h_full[g](k), acc2_empty[g][b] of tile k-NB2  -> acc2[g][b]     (b = k mod NB2)
     if (lane == 0) {
       const uint32_t idesc1 = umma_idesc_bf16(128, a.H, 0, 0), idesc2 = umma_idesc_bf16(128, a.Co, 0, 0);
       const uint64_t dW2 = umma_desc(smem_u32(sW2), 128, c8n * 128);
       const uint64_t dW3 = umma_desc(smem_u32(sW3), 128, h8n * 128);
       const uint64_t dWr = has_rc ? umma_desc(smem_u32(sWr), 128, r8n * 128) : 0;
-      auto second_half = [&](int64_t j) {   // GEMM2 (+ res-GEMM) of local tile j
-        const int gj = (int)(j & 1), sj = (int)(j % NST);
-        mbar_wait(&h_full[gj], (uint32_t)((j >> 1) & 1));
-        if (j >= 2) mbar_wait(&acc2_empty[gj], (uint32_t)(((j >> 1) - 1) & 1));
-        tc_fence_after();
-        const uint32_t acc2 = tmem_base + 2 * a.H + gj * a.Co;
-        const uint64_t dH = umma_desc(smem_u32(sH + gj * 128 * a.H * 2), 128, h8n * 128);
-        for (int k = 0; k < a.H / 16; ++k) umma_bf16(acc2, dH + (uint64_t)(k * 16), dW3 + (uint64_t)(k * 16), idesc2, k > 0 ? 1u : 0u);
-        if (has_rc) {
-          const uint64_t dX = umma_desc(smem_u32(sX + (int)(j % NSX) * 128 * a.Cr * 2), 128, r8n * 128);
-          for (int k = 0; k < a.Cr / 16; ++k) umma_bf16(acc2, dX + (uint64_t)(k * 16), dWr + (uint64_t)(k * 16), idesc2, 1u);
+      const int64_t T = blockIdx.x < fa.ntiles ? (fa.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;   // tiles of this CTA
+      int64_t kk[2] = {0, 0};
+      const int64_t nk[2] = {(T + 1) >> 1, T >> 1};
+      int ph[2] = {0, 0};
+      while (kk[0] < nk[0] || kk[1] < nk[1]) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (kk[g] >= nk[g]) continue;
+          const int64_t k = kk[g], it = 2 * k + g;
+          const int s = (int)(it % NST);
+          if (ph[g] == 0) {
+            if (!mbar_test(&a_full[s], (uint32_t)((it / NST) & 1))) continue;
+            tc_fence_after();
+            const uint32_t acc1 = tmem_base + g * a.H;
+            const uint64_t dA = umma_desc(smem_u32(sA + s * 128 * a.C * 2), 128, c8n * 128);
+            for (int q = 0; q < a.C / 16; ++q) umma_bf16(acc1, dA + (uint64_t)(q * 16), dW2 + (uint64_t)(q * 16), idesc1, q > 0 ? 1u : 0u);
+            tc_commit(&acc1_full[g]);
+            if (!has_rc) tc_commit(&a_empty[s]);
+            ph[g] = 1;
+          } else {
+            if (!mbar_test(&h_full[g], (uint32_t)(k & 1))) continue;
+            const int b = NB2 == 2 ? (int)(k & 1) : 0;
+            const int64_t prev = k - NB2;                 // the tile whose epilogue 2 last read acc2[g][b]
+            if (prev >= 0 && !mbar_test(&acc2_empty[g * 2 + b], (uint32_t)((prev / NB2) & 1))) continue;
+            tc_fence_after();
+            const uint32_t acc2 = tmem_base + 2 * a.H + (g * NB2 + b) * a.Co;
+            const uint64_t dH = umma_desc(smem_u32(sH + g * 128 * a.H * 2), 128, h8n * 128);
+            for (int q = 0; q < a.H / 16; ++q) umma_bf16(acc2, dH + (uint64_t)(q * 16), dW3 + (uint64_t)(q * 16), idesc2, q > 0 ? 1u : 0u);
+            if (has_rc) {
+              const uint64_t dX = umma_desc(smem_u32(sX + (int)(it % NSX) * 128 * a.Cr * 2), 128, r8n * 128);
+              for (int q = 0; q < a.Cr / 16; ++q) umma_bf16(acc2, dX + (uint64_t)(q * 16), dWr + (uint64_t)(q * 16), idesc2, 1u);
+            }
+            tc_commit(&acc2_full[g * 2 + b]);
+            if (has_rc) tc_commit(&a_empty[s]);
+            ph[g] = 0;
+            ++kk[g];
+          }
         }
-        tc_commit(&acc2_full[gj]);
-        if (has_rc) tc_commit(&a_empty[sj]);
-      };
-      int64_t it = 0;
-      for (int64_t g = blockIdx.x; g < fa.ntiles; g += gridDim.x, ++it) {
-        const int s = (int)(it % NST), gacc = (int)(it & 1);
-        mbar_wait(&a_full[s], (uint32_t)((it / NST) & 1));
-        tc_fence_after();
-        const uint32_t acc1 = tmem_base + gacc * a.H;
-        const uint64_t dA = umma_desc(smem_u32(sA + s * 128 * a.C * 2), 128, c8n * 128);
-        for (int k = 0; k < a.C / 16; ++k) umma_bf16(acc1, dA + (uint64_t)(k * 16), dW2 + (uint64_t)(k * 16), idesc1, k > 0 ? 1u : 0u);
-        tc_commit(&acc1_full[gacc]);
-        if (!has_rc) tc_commit(&a_empty[s]);
-        if (it >= 1) second_half(it - 1);
       }
-      if (it >= 1) second_half(it - 1);
     }
   } else {
     // ===================================================================== epilogue warpgroups
+    // Group eg owns the tiles it == eg (mod 2).  With two acc2 buffers (NB2 == 2) the order per local tile k is
+    //   epilogue 1 (k)  ->  h_full  ->  epilogue 2 (k-1)
+    // so the GEMM2 of tile k (and the GEMM1 of k+1 behind it) runs while this group still has the output pass of tile k-1 to
+    // do: the group never idles on acc2_full (ncu, round 2: 38 % of the epilogue warps' samples sat in that wait).
     const int eg = (warp - MF_LOAD_WARPS) >> 2;          // 0 / 1: which tiles (it & 1) this group owns
     const int wq = warp & 3;                             // TMEM lane quarter this warp may access
     const int row = wq * 32 + lane;
@@ -1455,87 +1478,113 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_fused_kernel(MlpFusedArgs f
     const uint32_t sboH = h8n * 128;
     const int co8 = a.Co >> 3;
     const bool prefetch = a.res != nullptr && co8 <= 8;
-    int64_t it = eg;
-    for (int64_t g = blockIdx.x + (int64_t)eg * gridDim.x; g < fa.ntiles; g += 2 * (int64_t)gridDim.x, it += 2) {
-      const uint32_t par = (uint32_t)((it >> 1) & 1);
-      const int n = (int)(g / fa.tps);
-      const int ovi = (int)((g - (int64_t)n * fa.tps) * 128) + row;
+    const bool pipe = NB2 == 2;
+    // ---- epilogue 1: acc1 -> +b2 -> GELU -> bf16 -> sH[eg]
+    auto epi1 = [&]() {
+      const uint32_t trow = tmem_base + eg * a.H + lane_off;
+      uint8_t* dst = sH + eg * 128 * a.H * 2 + (row >> 3) * sboH + (row & 7) * 16;
+      for (int c16 = 0; c16 < a.H / 16; ++c16) {
+        uint32_t v[16];
+        tmem_ld16(trow + c16 * 16, v);
+        tmem_ld_wait();
+        float gl[16];
+        const float4* bp = reinterpret_cast<const float4*>(sB2 + c16 * 16);
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 b = bp[j4];
+          gelu_fast2p(add2(pk2(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1])), pk2(b.x, b.y)), gl[4 * j4], gl[4 * j4 + 1]);
+          gelu_fast2p(add2(pk2(__uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3])), pk2(b.z, b.w)), gl[4 * j4 + 2], gl[4 * j4 + 3]);
+        }
+        *reinterpret_cast<uint4*>(dst + (c16 * 2) * 128) = pack8(gl);
+        *reinterpret_cast<uint4*>(dst + (c16 * 2 + 1) * 128) = pack8(gl + 8);
+      }
+    };
+    // ---- epilogue 2: acc2[eg][b] -> +b3 (+br) (+residual / skip) -> bf16 -> HBM
+    auto epi2 = [&](int b, int64_t orow, bool in_range, bool valid, const uint4 (&rpre)[8]) {
+      const uint32_t trow = tmem_base + 2 * a.H + (eg * NB2 + b) * a.Co + lane_off;
+#pragma unroll 1
+      for (int c16 = 0; c16 < a.Co / 16; ++c16) {
+        uint32_t v[16];
+        tmem_ld16(trow + c16 * 16, v);
+        uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0, 0, 0);
+        if (prefetch) {
+          // constant-index selection keeps rpre in registers
+#pragma unroll
+          for (int c = 0; c < 4; ++c) if (c == c16) { r0 = rpre[2 * c]; r1 = rpre[2 * c + 1]; }
+        } else if (a.res != nullptr && in_range) {
+          r0 = __ldg(a.res + orow + c16 * 2); r1 = __ldg(a.res + orow + c16 * 2 + 1);
+        }
+        tmem_ld_wait();
+        if (!in_range) continue;
+        const float4* b3p = reinterpret_cast<const float4*>(sB3 + c16 * 16);
+        const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+        uint32_t ow[8];
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 bb = b3p[j4];
+          uint64_t lo = pk2(bf16_lo(rw[2 * j4]), bf16_hi(rw[2 * j4])), hi = pk2(bf16_lo(rw[2 * j4 + 1]), bf16_hi(rw[2 * j4 + 1]));
+          if (valid) {
+            lo = add2(lo, add2(pk2(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1])), pk2(bb.x, bb.y)));
+            hi = add2(hi, add2(pk2(__uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3])), pk2(bb.z, bb.w)));
+          }
+          float e0, e1, e2, e3;
+          upk2(lo, e0, e1);
+          upk2(hi, e2, e3);
+          ow[2 * j4] = pack_bf16(e0, e1);
+          ow[2 * j4 + 1] = pack_bf16(e2, e3);
+        }
+        a.out[orow + c16 * 2] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        a.out[orow + c16 * 2 + 1] = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+      }
+    };
+    auto load_res = [&](uint4 (&rpre)[8], int64_t orow, bool in_range) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) rpre[c] = (c < co8 && in_range) ? __ldg(a.res + orow + c) : make_uint4(0, 0, 0, 0);
+    };
+    int64_t k = 0;
+    int64_t p_orow = 0;                                  // row of the tile whose epilogue 2 is pending (pipe)
+    bool p_in = false, p_valid = false;
+    for (int64_t g = blockIdx.x + (int64_t)eg * gridDim.x; g < fa.ntiles; g += 2 * (int64_t)gridDim.x, ++k) {
+      const int n = mf_fdiv((int)g, fa.dmt, fa.dst);
+      const int ovi = ((int)g - n * (int)fa.tps) * 128 + row;
       int ry, rx;
-      mf_row_sources(a, ovi, ry, rx);
+      mf_row_sources_fast(fa, ovi, ry, rx);
       const bool in_range = ovi < (int)a.Vout, valid = in_range && ry >= 0;
       const int64_t orow = ((int64_t)n * a.Vout + ovi) * co8;
       uint4 rpre[8];                                     // residual / skip row, in flight during epilogue 1
       if (prefetch) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) rpre[c] = (c < co8 && in_range) ? __ldg(a.res + orow + c) : make_uint4(0, 0, 0, 0);
+        if (!pipe) load_res(rpre, orow, in_range);
+        else if (k >= 1) load_res(rpre, p_orow, p_in);
       }
-      // ---- epilogue 1: acc1 -> +b2 -> GELU -> bf16 -> sH[eg]
-      mbar_wait(&acc1_full[eg], par);
+      mbar_wait(&acc1_full[eg], (uint32_t)(k & 1));
+      // sH[eg] is read by GEMM2(k-1): it has retired when acc2_full of tile k-1 completed (issued an epilogue-2 pass ago)
+      if (pipe && k >= 1) mbar_wait(&acc2_full[eg * 2 + (int)((k - 1) & 1)], (uint32_t)(((k - 1) >> 1) & 1));
       tc_fence_after();
-      {
-        const uint32_t trow = tmem_base + eg * a.H + lane_off;
-        uint8_t* dst = sH + eg * 128 * a.H * 2 + (row >> 3) * sboH + (row & 7) * 16;
-        for (int c16 = 0; c16 < a.H / 16; ++c16) {
-          uint32_t v[16];
-          tmem_ld16(trow + c16 * 16, v);
-          tmem_ld_wait();
-          float gl[16];
-          const float4* bp = reinterpret_cast<const float4*>(sB2 + c16 * 16);
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 b = bp[j4];
-            gelu_fast2p(add2(pk2(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1])), pk2(b.x, b.y)), gl[4 * j4], gl[4 * j4 + 1]);
-            gelu_fast2p(add2(pk2(__uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3])), pk2(b.z, b.w)), gl[4 * j4 + 2], gl[4 * j4 + 3]);
-          }
-          *reinterpret_cast<uint4*>(dst + (c16 * 2) * 128) = pack8(gl);
-          *reinterpret_cast<uint4*>(dst + (c16 * 2 + 1) * 128) = pack8(gl + 8);
-        }
-      }
+      epi1();
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&h_full[eg]);
-      // ---- epilogue 2: acc2 -> +b3 (+br) (+residual / skip) -> bf16 -> HBM
-      mbar_wait(&acc2_full[eg], par);
-      tc_fence_after();
-      {
-        const uint32_t trow = tmem_base + 2 * a.H + eg * a.Co + lane_off;
-#pragma unroll 1
-        for (int c16 = 0; c16 < a.Co / 16; ++c16) {
-          uint32_t v[16];
-          tmem_ld16(trow + c16 * 16, v);
-          uint4 r0 = make_uint4(0, 0, 0, 0), r1 = make_uint4(0, 0, 0, 0);
-          if (prefetch) {
-            // constant-index selection keeps rpre in registers
-#pragma unroll
-            for (int c = 0; c < 4; ++c) if (c == c16) { r0 = rpre[2 * c]; r1 = rpre[2 * c + 1]; }
-          } else if (a.res != nullptr && in_range) {
-            r0 = __ldg(a.res + orow + c16 * 2); r1 = __ldg(a.res + orow + c16 * 2 + 1);
-          }
-          tmem_ld_wait();
-          if (!in_range) continue;
-          const float4* b3p = reinterpret_cast<const float4*>(sB3 + c16 * 16);
-          const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-          uint32_t ow[8];
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 b = b3p[j4];
-            uint64_t lo = pk2(bf16_lo(rw[2 * j4]), bf16_hi(rw[2 * j4])), hi = pk2(bf16_lo(rw[2 * j4 + 1]), bf16_hi(rw[2 * j4 + 1]));
-            if (valid) {
-              lo = add2(lo, add2(pk2(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1])), pk2(b.x, b.y)));
-              hi = add2(hi, add2(pk2(__uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3])), pk2(b.z, b.w)));
-            }
-            float e0, e1, e2, e3;
-            upk2(lo, e0, e1);
-            upk2(hi, e2, e3);
-            ow[2 * j4] = pack_bf16(e0, e1);
-            ow[2 * j4 + 1] = pack_bf16(e2, e3);
-          }
-          a.out[orow + c16 * 2] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-          a.out[orow + c16 * 2 + 1] = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+      if (pipe) {
+        if (k >= 1) {
+          epi2((int)((k - 1) & 1), p_orow, p_in, p_valid, rpre);
+          tc_fence_before();
+          mbar_arrive(&acc2_empty[eg * 2 + (int)((k - 1) & 1)]);
         }
+        p_orow = orow; p_in = in_range; p_valid = valid;
+      } else {
+        mbar_wait(&acc2_full[eg * 2], (uint32_t)(k & 1));
+        tc_fence_after();
+        epi2(0, orow, in_range, valid, rpre);
+        tc_fence_before();
+        mbar_arrive(&acc2_empty[eg * 2]);
       }
-      tc_fence_before();
-      mbar_arrive(&acc2_empty[eg]);
+    }
+    if (pipe && k >= 1) {                                // drain: epilogue 2 of the group's last tile
+      uint4 rpre[8];
+      if (prefetch) load_res(rpre, p_orow, p_in);
+      mbar_wait(&acc2_full[eg * 2 + (int)((k - 1) & 1)], (uint32_t)(((k - 1) >> 1) & 1));
+      tc_fence_after();
+      epi2((int)((k - 1) & 1), p_orow, p_in, p_valid, rpre);
     }
   }
   tc_fence_before();
@@ -1556,7 +1605,7 @@ static size_t mlp_fused_smem(const MlpArgs& a, int N, int nst, int nsx) {
   const bool rc = a.wr != nullptr;
   return (size_t)a.H * a.C * 2 + (size_t)a.Co * a.H * 2 + (rc ? (size_t)a.Co * a.Cr * 2 : 0) + (size_t)nst * 128 * a.C * 2 +
          (rc ? (size_t)nsx * 128 * a.Cr * 2 : 0) + (size_t)2 * 128 * a.H * 2 + (size_t)2 * N * a.C * 4 + (size_t)(a.H + a.Co) * 4 +
-         4 * 2 * 128 * 4 + 16 * 8 + 16 + 128;
+         4 * 2 * 128 * 4 + 20 * 8 + 16 + 128;
 }
 
 // ============================================================================ head (OutBlock)
@@ -1804,6 +1853,8 @@ extern "C" int pcb_mlp_fwd(const void* y, const double* stats, const float* gamm
       { const char* e16 = getenv("PCB_FWD_LD16"); fa.ld16 = (e16 && e16[0] == '1') ? 1 : 0; }
       mf_magic((uint32_t)(a.o2 > 0 ? a.o2 : 1), fa.dm2, fa.ds2);
       mf_magic((uint32_t)(a.o1 > 0 ? a.o1 : 1), fa.dm1, fa.ds1);
+      mf_magic((uint32_t)fa.tps, fa.dmt, fa.dst);
+      { const char* np = getenv("PCB_FWD_NOPIPE"); fa.nb2 = (2 * H + 4 * Co <= 512 && !(np && np[0] == '1')) ? 2 : 1; }
       int ctas = 148;
       if (fa.ntiles < ctas) ctas = (int)fa.ntiles;
       if (fa.ld16 && fa.fast) mlp_fused_kernel<true><<<ctas, MF_THREADS, fsm, (cudaStream_t)stream>>>(fa);

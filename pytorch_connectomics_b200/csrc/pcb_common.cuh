@@ -235,6 +235,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(done) : "r"(addr), "r"(parity) : "memory");
   } while (!done);
 }
+// non-blocking probe of a phase parity (polling issuers that serve several independent pipelines)
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return done != 0;
+}
 // ----------------------------------------------------------------------------- TMA (cp.async.bulk.tensor)
 // One thread arms the mbarrier with the byte count of the box and issues the bulk tensor load; the copy
 // engine writes the box densely ([c4][c3][c2][c1][c0] order, innermost = channels) into shared memory,
