@@ -75,7 +75,7 @@ int pcb_sw_accumulate_batch(const void* pred, const void* map, void* value, void
 /* window.py:275-294 normalize_weighted_accumulator: value /= clamp_min(weight, 1e-4) (in place). */
 int pcb_sw_normalize(void* value, const void* weight, int dtype, int64_t Cout, int64_t nvox, void* stream);
 
-/* ------------------------------------------------------------------ test-time augmentation (fully valid channels)
+/* ------------------------------------------------------------------ test-time augmentation
  * connectomics/inference/tta.py:706-714: out = rot90(flip(x, flip axes), k, (rot_a, rot_b)) for x [planes, in_size],
  * spatial axes 0..2, flip_mask bit a = flip axis a, rot_a < 0 = no rotation; odd k swaps the plane's dims in `out`. */
 int pcb_tta_view(const void* x, void* out, int dtype, int64_t planes, const int64_t in_size[3], int flip_mask,
@@ -89,6 +89,34 @@ int pcb_tta_view(const void* x, void* out, int dtype, int64_t planes, const int6
 int pcb_tta_fold(const void* pred, int pred_dtype, void* acc, int acc_dtype, int64_t N, int64_t Cpred, int64_t Cacc,
                  const int64_t acc_size[3], int flip_mask, int rot_a, int rot_b, int k, const int* src_channel,
                  const int* mode, const int* act, const float* act_scale, int n_prev, void* stream);
+
+/* pcb_tta_fold with the rest of the reference's view inversion and aggregation (same arrays, plus):
+ *  - shift[Cacc*3] (or NULL): affinity-aware inversion, tta_affinity.py:376-391 — accumulator channel c reads
+ *    spatial[src_channel[c]] displaced by the roll shift, canonical[p] = spatial[p - shift]; voxels whose source falls
+ *    outside are zero and INVALID (tta_affinity.py:101-117 valid_slices_for_shift);
+ *  - act[c] == 4: softmax over the canonical channels listed in sm_src / sm_shift [sm_off[c], sm_off[c]+sm_len[c])
+ *    (prediction channel + shift of every member; tta.py:368-370);
+ *  - part[c] >= 0: channel c is a PARTIAL channel (tta_ensemble.py:121-162): its value goes to stats[N, Cpart, vol] (fp32:
+ *    sum / min / max per part_mode[c]) and counts[N, Cpart, vol] (count_dtype 0 = uint8, 1 = int16) only where it is valid
+ *    (inside the shift's box and, when valid_mask [Cpart, vol] is given, where the mask byte is non-zero); mode[c] is ignored;
+ *  - mean_as_sum: "mean" channels accumulate the plain sum (distributed view sharding, tta_ensemble.py:92-93). */
+int pcb_tta_fold_ex(const void* pred, int pred_dtype, void* acc, int acc_dtype, int64_t N, int64_t Cpred, int64_t Cacc,
+                    const int64_t acc_size[3], int flip_mask, int rot_a, int rot_b, int k, const int* src_channel,
+                    const int* mode, const int* act, const float* act_scale, const int* shift, const int* sm_off,
+                    const int* sm_len, const int* sm_src, const int* sm_shift, int n_members, const int* part,
+                    const int* part_mode, int64_t Cpart, float* stats, void* counts, int count_dtype, const void* valid_mask,
+                    int mean_as_sum, int n_prev, void* stream);
+/* tta_affinity.py:350-393 invert_view as one gather: out [N, Cout, out_size] (same dtype as pred) = rot90(-k) then flip of
+ * pred [N, Cpred, view frame], channel c taken from src_channel[c] (NULL: identity) and displaced by shift[c*3..] (NULL: none);
+ * wrapped faces are zero. */
+int pcb_tta_unview(const void* pred, void* out, int dtype, int64_t N, int64_t Cpred, int64_t Cout, const int64_t out_size[3],
+                   int flip_mask, int rot_a, int rot_b, int k, const int* src_channel, const int* shift, void* stream);
+/* tta_ensemble.py:187-211 finalize for the partial channels: acc[:, part_channel[j]] = stats[:, j] (/ counts for mode 0 = mean)
+ * cast to the accumulator dtype.  *first_zero (device uint64, initialised by the caller to UINT64_MAX) receives the smallest flat
+ * index of stats with zero coverage — the caller raises the reference's RuntimeError when it moved. */
+int pcb_tta_finalize_partial(const float* stats, const void* counts, int count_dtype, void* acc, int acc_dtype, int64_t N,
+                             int64_t Cacc, int64_t Cpart, const int* part_channel, const int* part_mode, int64_t nvox,
+                             void* first_zero, void* stream);
 
 /* ------------------------------------------------------------------ MedNeXt forward ops
  * (upstream nnunet_mednext blocks.py / MedNextV1.py as built by

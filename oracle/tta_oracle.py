@@ -76,3 +76,43 @@ def tta_predict(images: torch.Tensor, network_fn: Callable, combos, modes: List[
         pred = invert_view(pred, flip_axes, plane, k)
         acc = fold(acc, apply_preprocessing(pred, act_codes, act_scales, select, output_dtype), modes, n_prev)
     return acc
+
+
+# ----------------------------------------------------------------------------- affinity-aware path (round 2)
+def ramp_network(num_channels: int):
+    """Deterministic stand-in for the model in the TTA tests and goldens: ``out[:, c] = x[:, 0] * ramp_c + 0.1 c`` with a
+    position-dependent ramp built from the VIEW tensor's own shape, so that a wrong inverse view or channel move changes
+    the result.  Only fp32 multiplies and adds (no FMA in eager torch): bit-identical on CPU and CUDA."""
+
+    def fn(x: torch.Tensor) -> torch.Tensor:
+        d, h, w = (int(v) for v in x.shape[2:])
+        dev = x.device
+        z = torch.arange(d, device=dev, dtype=torch.float32).view(d, 1, 1)
+        y = torch.arange(h, device=dev, dtype=torch.float32).view(1, h, 1)
+        xx = torch.arange(w, device=dev, dtype=torch.float32).view(1, 1, w)
+        outs = []
+        for c in range(num_channels):
+            ramp = z * (0.03125 * (c + 1)) + y * 0.0625 - xx * (0.015625 * (c + 2)) + 0.5
+            outs.append(x[:, 0].float() * ramp + 0.125 * c)
+        return torch.stack(outs, dim=1)
+
+    return fn
+
+
+def preprocess_specs(t: torch.Tensor, specs, select, output_dtype: torch.dtype) -> torch.Tensor:
+    """tta.py:327-402 for ``specs = [(channel list, activation name), ...]`` applied one after the other in place."""
+    t = t.clone()
+    for chans, act in specs:
+        chans = list(chans)
+        if act == "sigmoid":
+            t[:, chans] = torch.sigmoid(t[:, chans])
+        elif act == "tanh":
+            t[:, chans] = torch.tanh(t[:, chans])
+        elif isinstance(act, str) and act.startswith("scale_sigmoid"):
+            scale = float(act.split(":", 1)[1]) if ":" in act else 0.2
+            t[:, chans] = torch.sigmoid(scale * t[:, chans])
+        elif act == "softmax" and len(chans) > 1:
+            t[:, chans] = torch.softmax(t[:, chans], dim=1)
+    if select is not None:
+        t = t[:, list(select)]
+    return t if t.dtype == output_dtype else t.to(output_dtype)

@@ -594,6 +594,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) mlp_bwd_fused_kernel(Ml
 // TMEM: 2 x (acc1 + accG) + 2 x accD + accW3 + accW2 = 4H + 2C + Co + H columns (416 at level 0).  Level-0 shape only
 // (C = 32, Co = 32, H = 64, SAME / DOWN rows): the level-1 and up_0 shapes do not fit double-buffered accumulators.
 constexpr int WS_LOAD = 4, WS_EPI = 8, WS_THREADS = 32 * (WS_LOAD + WS_EPI + 1);
+constexpr int WS0_THREADS = 32 * (WS_LOAD + WS_EPI + 3);   // level-0 kernel: three MMA issuer warps (two groups + weight gradients)
 
 // One warp stages a [128 x 32] bf16 tile (4 chunks of 16 B per row) into the K-major canonical layout with row-group
 // pitch `pitch` (same lane mapping as mf_stage_tile in mednext_fwd.cu): 8 loads in flight per lane, conflict-free stores.
@@ -639,7 +640,7 @@ __device__ __forceinline__ void ws_stage_tile32(uint8_t* __restrict__ dst, uint3
   }
 }
 
-__global__ void __launch_bounds__(WS_THREADS, 1) mlp_bwd_ws_kernel(MlpBwdFusedArgs fa) {
+__global__ void __launch_bounds__(WS0_THREADS, 1) mlp_bwd_ws_kernel(MlpBwdFusedArgs fa) {
   const MlpBwdArgs& a = fa.m;
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -681,11 +682,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_bwd_ws_kernel(MlpBwdFusedAr
     mbar_init(w_done, 1);
     fence_mbar_init();
   }
-  stage_rows_k(sW2, a.w2, a.H, c8n, c8n, tid, WS_THREADS);
-  stage_rows_k(sW3t, a.w3t, a.H, o8n, o8n, tid, WS_THREADS);
-  stage_rows_k(sW2t, a.w2t, a.C, h8n, h8n, tid, WS_THREADS);
-  for (int i = tid; i < a.H; i += WS_THREADS) sB2[i] = a.b2[i];
-  for (int i = tid; i < fa.N * a.C; i += WS_THREADS) {
+  stage_rows_k(sW2, a.w2, a.H, c8n, c8n, tid, WS0_THREADS);
+  stage_rows_k(sW3t, a.w3t, a.H, o8n, o8n, tid, WS0_THREADS);
+  stage_rows_k(sW2t, a.w2t, a.C, h8n, h8n, tid, WS0_THREADS);
+  for (int i = tid; i < a.H; i += WS0_THREADS) sB2[i] = a.b2[i];
+  for (int i = tid; i < fa.N * a.C; i += WS0_THREADS) {
     const int n = i / a.C, c = i - n * a.C;
     const double sm = a.stats[(int64_t)n * 2 * a.C + c], q = a.stats[(int64_t)n * 2 * a.C + a.C + c];
     const double mean = sm * (double)a.inv_count;
@@ -695,16 +696,16 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_bwd_ws_kernel(MlpBwdFusedAr
     const float g = a.gamma[c] * rstd;
     sScale[i] = g; sShift[i] = a.beta[c] - (float)mean * g; sRstd[i] = rstd; sMR[i] = (float)mean * rstd;
   }
-  for (int i = tid; i < fa.N * 2 * a.C; i += WS_THREADS) sG[i] = 0.0;
-  for (int i = tid; i < 2 * a.Co; i += WS_THREADS) sDb3[i] = 0.f;
+  for (int i = tid; i < fa.N * 2 * a.C; i += WS0_THREADS) sG[i] = 0.0;
+  for (int i = tid; i < 2 * a.Co; i += WS0_THREADS) sDb3[i] = 0.f;
   // all-ones core matrix (chunk index c8n) of every row group of every A stage; finite tail
-  for (int i = tid; i < 4 * 128; i += WS_THREADS) {
+  for (int i = tid; i < 4 * 128; i += WS0_THREADS) {
     const int st = i >> 7, r = i & 127;
     *reinterpret_cast<uint4*>(sA + st * stageA + (r >> 3) * pitchA + c8n * 128 + (r & 7) * 16) = make_uint4(0x3F80u, 0, 0, 0);
   }
-  for (int i = tid; i < 128; i += WS_THREADS) *reinterpret_cast<uint4*>(sTail + i * 16) = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < 128; i += WS0_THREADS) *reinterpret_cast<uint4*>(sTail + i * 16) = make_uint4(0, 0, 0, 0);
   // the MN-major operand reads run past the valid channel groups: keep every operand byte finite from the start
-  for (uint32_t i = tid * 16; i < 4 * stageD + 4 * stageH; i += WS_THREADS * 16) *reinterpret_cast<uint4*>(sD + i) = make_uint4(0, 0, 0, 0);
+  for (uint32_t i = tid * 16; i < 4 * stageD + 4 * stageH; i += WS0_THREADS * 16) *reinterpret_cast<uint4*>(sD + i) = make_uint4(0, 0, 0, 0);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -727,64 +728,60 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_bwd_ws_kernel(MlpBwdFusedAr
       fence_proxy_async_smem();
       mbar_arrive(&a_full[warp]);
     }
-  } else if (warp == WS_LOAD + WS_EPI) {
-    // ===================================================================== MMA issuer (one thread)
+  } else if (warp >= WS_LOAD + WS_EPI) {
+    // ===================================================================== MMA issuers: one thread per role, blocking waits
     // The two epilogue groups are independent pipelines (group g: tiles it == g mod 2, own acc1 / accG / accD[2] / sH / sDh).
-    // The issuer POLLS their barriers and issues whichever GEMM set has its operands ready, so neither group waits behind
-    // the other's hand-off.  Per group and local tile k (it = 2k + g, operand stage s = it & 3, accD buffer b = k & 1):
-    //   first half : a_full[s]                               -> G1 Hpre -> acc1[g], G2 dG -> accG[g]      (hp_full[g])
-    //   second half: e1_done[g](k), d_empty[g][b] of k - 2   -> G3 dYhat -> accD[g][b]                    (d_full[g][b])
-    //                                                           G4 dW3 +=, G5 dW2 += (shared accumulators)  (a_empty[s], h_free[g])
-    if (lane == 0) {
+    //   issuer g (warps 12, 13), local tile k (it = 2k + g, operand stage s = it & 3, accD buffer b = k & 1):
+    //     a_full[s]                              -> G1 Hpre -> acc1[g], G2 dG -> accG[g]     (hp_full[g])
+    //     e1_done[g](k), d_empty[g][b] of k - 2  -> G3 dYhat -> accD[g][b]                   (d_full[g][b])
+    //   weight-gradient issuer (warp 14), tiles in CTA order: e1_done[g](k) -> G4 dW3 +=, G5 dW2 += into the shared
+    //     accumulators (one issuing thread: the MMAs retire in order)                        (a_empty[s], h_free[g])
+    // (A single polling issuer — mbarrier.test_wait, ~150 cycles per probe — was measured slower than the in-order one.)
+    const int role = warp - (WS_LOAD + WS_EPI);
+    if (lane == 0 && role < 2) {
+      const int g = role;
       const uint32_t idescH = umma_idesc_bf16(128, a.H, 0, 0), idescD = umma_idesc_bf16(128, a.C, 0, 0);
-      const uint32_t idescW3 = umma_idesc_bf16(128, a.Co, 1, 1), idescW2 = umma_idesc_bf16(128, a.H, 1, 1);
       const uint64_t dW2 = umma_desc(smem_u32(sW2), 128, c8n * 128), dW3 = umma_desc(smem_u32(sW3t), 128, o8n * 128);
       const uint64_t dW2t = umma_desc(smem_u32(sW2t), 128, h8n * 128);
-      const int64_t T = (fa.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;      // tiles of this CTA (>= 1)
-      int64_t kk[2] = {0, 0};
-      const int64_t nk[2] = {(T + 1) >> 1, T >> 1};
-      int ph[2] = {0, 0};
-      uint32_t wacc = 0;                                   // 0 until the first weight-gradient MMA has initialised accW3 / accW2
-      while (kk[0] < nk[0] || kk[1] < nk[1]) {
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          if (kk[g] >= nk[g]) continue;
-          const int64_t k = kk[g], it = 2 * k + g;
-          const int s = (int)(it & 3);
-          if (ph[g] == 0) {
-            if (!mbar_test(&a_full[s], (uint32_t)((it >> 2) & 1))) continue;
-            tc_fence_after();
-            const uint64_t dA = umma_desc(smem_u32(sA + s * stageA), 128, pitchA), dD = umma_desc(smem_u32(sD + s * stageD), 128, pitchD);
-            for (int q = 0; q < a.C / 16; ++q)
-              umma_bf16(tmem_base + g * a.H, dA + (uint64_t)(q * 16), dW2 + (uint64_t)(q * 16), idescH, q > 0 ? 1u : 0u);
-            for (int q = 0; q < a.Co / 16; ++q)
-              umma_bf16(tmem_base + 2 * a.H + g * a.H, dD + (uint64_t)(q * 16), dW3 + (uint64_t)(q * 16), idescH, q > 0 ? 1u : 0u);
-            tc_commit(&hp_full[g]);
-            ph[g] = 1;
-          } else {
-            if (!mbar_test(&e1_done[g], (uint32_t)(k & 1))) continue;
-            const int b = (int)(k & 1);
-            if (k >= 2 && !mbar_test(&d_empty[g * 2 + b], (uint32_t)(((k >> 1) - 1) & 1))) continue;
-            tc_fence_after();
-            const uint64_t dDhK = umma_desc(smem_u32(sDh + g * stageH), 128, pitchH);
-            for (int q = 0; q < a.H / 16; ++q)
-              umma_bf16(tmem_base + colD + (2 * g + b) * a.C, dDhK + (uint64_t)(q * 16), dW2t + (uint64_t)(q * 16), idescD, q > 0 ? 1u : 0u);
-            tc_commit(&d_full[g * 2 + b]);
-            const uint64_t aH = umma_desc(smem_u32(sH + g * stageH), pitchH, 128), bD = umma_desc(smem_u32(sD + s * stageD), pitchD, 128);
-            const uint64_t aA = umma_desc(smem_u32(sA + s * stageA), pitchA, 128), bDh = umma_desc(smem_u32(sDh + g * stageH), pitchH, 128);
-            for (int q = 0; q < 8; ++q)
-              umma_bf16(tmem_base + colW3, aH + (uint64_t)(q * 2 * (pitchH >> 4)), bD + (uint64_t)(q * 2 * (pitchD >> 4)), idescW3,
-                        (wacc | (uint32_t)q) ? 1u : 0u);
-            for (int q = 0; q < 8; ++q)
-              umma_bf16(tmem_base + colW2, aA + (uint64_t)(q * 2 * (pitchA >> 4)), bDh + (uint64_t)(q * 2 * (pitchH >> 4)), idescW2,
-                        (wacc | (uint32_t)q) ? 1u : 0u);
-            wacc = 1;
-            tc_commit(&a_empty[s]);
-            tc_commit(&h_free[g]);
-            ph[g] = 0;
-            ++kk[g];
-          }
-        }
+      int64_t k = 0;
+      for (int64_t gt = blockIdx.x + (int64_t)g * gridDim.x; gt < fa.ntiles; gt += 2ll * gridDim.x, ++k) {
+        const int64_t it = 2 * k + g;
+        const int s = (int)(it & 3), b = (int)(k & 1);
+        mbar_wait(&a_full[s], (uint32_t)((it >> 2) & 1));
+        tc_fence_after();
+        const uint64_t dA = umma_desc(smem_u32(sA + s * stageA), 128, pitchA), dD = umma_desc(smem_u32(sD + s * stageD), 128, pitchD);
+        for (int q = 0; q < a.C / 16; ++q)
+          umma_bf16(tmem_base + g * a.H, dA + (uint64_t)(q * 16), dW2 + (uint64_t)(q * 16), idescH, q > 0 ? 1u : 0u);
+        for (int q = 0; q < a.Co / 16; ++q)
+          umma_bf16(tmem_base + 2 * a.H + g * a.H, dD + (uint64_t)(q * 16), dW3 + (uint64_t)(q * 16), idescH, q > 0 ? 1u : 0u);
+        tc_commit(&hp_full[g]);
+        mbar_wait(&e1_done[g], (uint32_t)(k & 1));
+        if (k >= 2) mbar_wait(&d_empty[g * 2 + b], (uint32_t)(((k >> 1) - 1) & 1));
+        tc_fence_after();
+        const uint64_t dDhK = umma_desc(smem_u32(sDh + g * stageH), 128, pitchH);
+        for (int q = 0; q < a.H / 16; ++q)
+          umma_bf16(tmem_base + colD + (2 * g + b) * a.C, dDhK + (uint64_t)(q * 16), dW2t + (uint64_t)(q * 16), idescD, q > 0 ? 1u : 0u);
+        tc_commit(&d_full[g * 2 + b]);
+      }
+    } else if (lane == 0 && role == 2) {
+      const uint32_t idescW3 = umma_idesc_bf16(128, a.Co, 1, 1), idescW2 = umma_idesc_bf16(128, a.H, 1, 1);
+      int64_t it = 0;
+      for (int64_t gt = blockIdx.x; gt < fa.ntiles; gt += gridDim.x, ++it) {
+        const int g = (int)(it & 1), s = (int)(it & 3);
+        const int64_t k = it >> 1;
+        mbar_wait(&a_full[s], (uint32_t)((it >> 2) & 1));      // the loader's sA / sD writes (G1 / G2 retired before E1 started)
+        mbar_wait(&e1_done[g], (uint32_t)(k & 1));             // sH / sDh of this tile
+        tc_fence_after();
+        const uint64_t aH = umma_desc(smem_u32(sH + g * stageH), pitchH, 128), bD = umma_desc(smem_u32(sD + s * stageD), pitchD, 128);
+        const uint64_t aA = umma_desc(smem_u32(sA + s * stageA), pitchA, 128), bDh = umma_desc(smem_u32(sDh + g * stageH), pitchH, 128);
+        for (int q = 0; q < 8; ++q)
+          umma_bf16(tmem_base + colW3, aH + (uint64_t)(q * 2 * (pitchH >> 4)), bD + (uint64_t)(q * 2 * (pitchD >> 4)), idescW3,
+                    (it > 0 || q > 0) ? 1u : 0u);
+        for (int q = 0; q < 8; ++q)
+          umma_bf16(tmem_base + colW2, aA + (uint64_t)(q * 2 * (pitchA >> 4)), bDh + (uint64_t)(q * 2 * (pitchH >> 4)), idescW2,
+                    (it > 0 || q > 0) ? 1u : 0u);
+        tc_commit(&a_empty[s]);
+        tc_commit(&h_free[g]);
       }
       tc_commit(w_done);
     }
@@ -859,8 +856,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_bwd_ws_kernel(MlpBwdFusedAr
         db3acc += sacc;
       }
       mbar_wait(&hp_full[eg], (uint32_t)(k & 1));
-      // sH / sDh[eg] are read by G3 / G4 / G5 of tile k-1 (issued an E2 pass ago); their retirement also completes d_full(k-1)
-      if (k >= 1) mbar_wait(&h_free[eg], (uint32_t)((k - 1) & 1));
+      // sH / sDh[eg] are read by G3 / G4 / G5 of tile k-1 (issued an E2 pass ago)
+      if (k >= 1) {
+        mbar_wait(&h_free[eg], (uint32_t)((k - 1) & 1));                                               // G4 / G5 of tile k-1
+        mbar_wait(&d_full[eg * 2 + (int)((k - 1) & 1)], (uint32_t)(((k - 1) >> 1) & 1));           // G3 of tile k-1 (another issuer)
+      }
       tc_fence_after();
       // ---- E1: Hact -> sH[eg], dh -> sDh[eg]
       {
@@ -900,7 +900,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_bwd_ws_kernel(MlpBwdFusedAr
       mbar_arrive(&e1_done[eg]);
       if (k >= 1) {
         const int b = (int)((k - 1) & 1);
-        mbar_wait(&d_full[eg * 2 + b], (uint32_t)(((k - 1) >> 1) & 1));   // already complete (h_free above); orders the TMEM read
+        mbar_wait(&d_full[eg * 2 + b], (uint32_t)(((k - 1) >> 1) & 1));   // already complete (waited before E1)
         tc_fence_after();
         epi2(b, p_n, p_prow, ypre);
         tc_fence_before();
@@ -948,7 +948,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_bwd_ws_kernel(MlpBwdFusedAr
       }
     }
   }
-  for (int i = tid; i < fa.N * 2 * a.C; i += WS_THREADS) {
+  for (int i = tid; i < fa.N * 2 * a.C; i += WS0_THREADS) {
     const double v = sG[i];
     if (v != 0.0) atomicAdd(&a.gstats[i], v);       // sG is [N][2C] exactly like gstats
   }
@@ -2379,7 +2379,7 @@ extern "C" int pcb_mlp_bwd_fused(const void* y, const double* stats, const float
       if (conf_ws) {
         const int Pw = (int)(fa.ntiles < 148 ? fa.ntiles : 148);     // <= P: the caller's workspace is large enough
         fa.part3 = workspace; fa.part2 = workspace + (int64_t)Pw * 129 * Co;
-        mlp_bwd_ws_kernel<<<Pw, WS_THREADS, mlp_bwd_ws_smem((int)C, (int)H, (int)Co, (int)N), st>>>(fa);
+        mlp_bwd_ws_kernel<<<Pw, WS0_THREADS, mlp_bwd_ws_smem((int)C, (int)H, (int)Co, (int)N), st>>>(fa);
         PCB_CHECK_LAUNCH("pcb_mlp_bwd_fused(ws)");
         reduce_partials_kernel<<<(unsigned)((H * Co + 31) / 32), 256, 0, st>>>(fa.part3, Pw, (int)H, 129, (int)Co, (int)Co, dW3, 1, H, nullptr);
         reduce_partials_kernel<<<(unsigned)((Co + 31) / 32), 256, 0, st>>>(fa.part3 + 128 * Co, Pw, 1, 129, (int)Co, (int)Co, db3, 0, 1, nullptr);

@@ -1111,7 +1111,7 @@ __device__ __forceinline__ int mf_fdiv(int n, uint32_t m, int sh) {
   return (int)(((uint64_t)(uint32_t)n * (uint64_t)m) >> sh);
 }
 
-constexpr int MF_LOAD_WARPS = 4, MF_EPI_WARPS = 8, MF_THREADS = 32 * (MF_LOAD_WARPS + MF_EPI_WARPS + 1);
+constexpr int MF_LOAD_WARPS = 4, MF_EPI_WARPS = 8, MF_MMA_WARPS = 2, MF_THREADS = 32 * (MF_LOAD_WARPS + MF_EPI_WARPS + MF_MMA_WARPS);
 
 __device__ __forceinline__ void mf_row_sources(const MlpArgs& a, int ov, int& ry, int& rx) {
   ry = -1; rx = -1;
@@ -1413,56 +1413,45 @@ __global__ void __launch_bounds__(MF_THREADS, 1) mlp_fused_kernel(MlpFusedArgs f
       fence_proxy_async_smem();
       mbar_arrive(&a_full[grp]);
     }
-  } else if (warp == MF_LOAD_WARPS + MF_EPI_WARPS) {
-    // ===================================================================== MMA issuer (one thread)
+  } else if (warp >= MF_LOAD_WARPS + MF_EPI_WARPS) {
+    // ===================================================================== MMA issuers (one thread per epilogue group)
     // The two epilogue groups are independent pipelines (group g owns the CTA's tiles it == g mod 2, its own acc1 / sH / acc2
-    // buffers and barriers).  The issuer serves them by POLLING (mbarrier.test_wait): whichever group's next GEMM has its
-    // operands ready is issued, so a group never waits behind a barrier of the other one.  Per group and local tile k:
+    // buffers and barriers), each served by its own issuing thread with blocking mbarrier waits, so a group never waits behind
+    // a hand-off of the other one.  (A single issuer that polls both groups with mbarrier.test_wait was measured 23 % slower
+    // than the in-order issuer it replaced: test_wait costs ~150 cycles per probe.)  Per group and local tile k:
     //   GEMM1(k): a_full(tile)                                  -> acc1[g]        (acc1[g] is free: h_full(k-1) was seen)
     //   GEMM2(k): h_full[g](k), acc2_empty[g][b] of tile k-NB2  -> acc2[g][b]     (b = k mod NB2)
+    const int g = warp - (MF_LOAD_WARPS + MF_EPI_WARPS);
     if (lane == 0) {
       const uint32_t idesc1 = umma_idesc_bf16(128, a.H, 0, 0), idesc2 = umma_idesc_bf16(128, a.Co, 0, 0);
       const uint64_t dW2 = umma_desc(smem_u32(sW2), 128, c8n * 128);
       const uint64_t dW3 = umma_desc(smem_u32(sW3), 128, h8n * 128);
       const uint64_t dWr = has_rc ? umma_desc(smem_u32(sWr), 128, r8n * 128) : 0;
-      const int64_t T = blockIdx.x < fa.ntiles ? (fa.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;   // tiles of this CTA
-      int64_t kk[2] = {0, 0};
-      const int64_t nk[2] = {(T + 1) >> 1, T >> 1};
-      int ph[2] = {0, 0};
-      while (kk[0] < nk[0] || kk[1] < nk[1]) {
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          if (kk[g] >= nk[g]) continue;
-          const int64_t k = kk[g], it = 2 * k + g;
-          const int s = (int)(it % NST);
-          if (ph[g] == 0) {
-            if (!mbar_test(&a_full[s], (uint32_t)((it / NST) & 1))) continue;
-            tc_fence_after();
-            const uint32_t acc1 = tmem_base + g * a.H;
-            const uint64_t dA = umma_desc(smem_u32(sA + s * 128 * a.C * 2), 128, c8n * 128);
-            for (int q = 0; q < a.C / 16; ++q) umma_bf16(acc1, dA + (uint64_t)(q * 16), dW2 + (uint64_t)(q * 16), idesc1, q > 0 ? 1u : 0u);
-            tc_commit(&acc1_full[g]);
-            if (!has_rc) tc_commit(&a_empty[s]);
-            ph[g] = 1;
-          } else {
-            if (!mbar_test(&h_full[g], (uint32_t)(k & 1))) continue;
-            const int b = NB2 == 2 ? (int)(k & 1) : 0;
-            const int64_t prev = k - NB2;                 // the tile whose epilogue 2 last read acc2[g][b]
-            if (prev >= 0 && !mbar_test(&acc2_empty[g * 2 + b], (uint32_t)((prev / NB2) & 1))) continue;
-            tc_fence_after();
-            const uint32_t acc2 = tmem_base + 2 * a.H + (g * NB2 + b) * a.Co;
-            const uint64_t dH = umma_desc(smem_u32(sH + g * 128 * a.H * 2), 128, h8n * 128);
-            for (int q = 0; q < a.H / 16; ++q) umma_bf16(acc2, dH + (uint64_t)(q * 16), dW3 + (uint64_t)(q * 16), idesc2, q > 0 ? 1u : 0u);
-            if (has_rc) {
-              const uint64_t dX = umma_desc(smem_u32(sX + (int)(it % NSX) * 128 * a.Cr * 2), 128, r8n * 128);
-              for (int q = 0; q < a.Cr / 16; ++q) umma_bf16(acc2, dX + (uint64_t)(q * 16), dWr + (uint64_t)(q * 16), idesc2, 1u);
-            }
-            tc_commit(&acc2_full[g * 2 + b]);
-            if (has_rc) tc_commit(&a_empty[s]);
-            ph[g] = 0;
-            ++kk[g];
-          }
+      int64_t k = 0;
+      for (int64_t gt = blockIdx.x + (int64_t)g * gridDim.x; gt < fa.ntiles; gt += 2 * (int64_t)gridDim.x, ++k) {
+        const int64_t it = 2 * k + g;
+        const int s = (int)(it % NST);
+        mbar_wait(&a_full[s], (uint32_t)((it / NST) & 1));
+        tc_fence_after();
+        const uint32_t acc1 = tmem_base + g * a.H;
+        const uint64_t dA = umma_desc(smem_u32(sA + s * 128 * a.C * 2), 128, c8n * 128);
+        for (int q = 0; q < a.C / 16; ++q) umma_bf16(acc1, dA + (uint64_t)(q * 16), dW2 + (uint64_t)(q * 16), idesc1, q > 0 ? 1u : 0u);
+        tc_commit(&acc1_full[g]);
+        if (!has_rc) tc_commit(&a_empty[s]);
+        mbar_wait(&h_full[g], (uint32_t)(k & 1));
+        const int b = NB2 == 2 ? (int)(k & 1) : 0;
+        const int64_t prev = k - NB2;                 // the tile whose epilogue 2 last read acc2[g][b]
+        if (prev >= 0) mbar_wait(&acc2_empty[g * 2 + b], (uint32_t)((prev / NB2) & 1));
+        tc_fence_after();
+        const uint32_t acc2 = tmem_base + 2 * a.H + (g * NB2 + b) * a.Co;
+        const uint64_t dH = umma_desc(smem_u32(sH + g * 128 * a.H * 2), 128, h8n * 128);
+        for (int q = 0; q < a.H / 16; ++q) umma_bf16(acc2, dH + (uint64_t)(q * 16), dW3 + (uint64_t)(q * 16), idesc2, q > 0 ? 1u : 0u);
+        if (has_rc) {
+          const uint64_t dX = umma_desc(smem_u32(sX + (int)(it % NSX) * 128 * a.Cr * 2), 128, r8n * 128);
+          for (int q = 0; q < a.Cr / 16; ++q) umma_bf16(acc2, dX + (uint64_t)(q * 16), dWr + (uint64_t)(q * 16), idesc2, 1u);
         }
+        tc_commit(&acc2_full[g * 2 + b]);
+        if (has_rc) tc_commit(&a_empty[s]);
       }
     }
   } else {

@@ -56,8 +56,8 @@ def test_channel_selectors():
                                                 {"channels": 2, "activation": "scale_sigmoid:0.5"},
                                                 {"channels": [3], "activation": "tanh"}], 5)
     assert codes == [1, 1, 2, 3, 0] and scales[2] == 0.5
-    with pytest.raises(NotImplementedError):
-        T.resolve_activation_codes([{"channels": ":", "activation": "softmax"}], 3)
+    codes, _scales, groups = T.resolve_activation_specs([{"channels": ":", "activation": "softmax"}], 3)
+    assert codes == [4, 4, 4] and groups[0] == [0, 1, 2]
     with pytest.raises(ValueError, match="Unknown activation"):
         T.resolve_activation_codes([{"channels": ":", "activation": "relu"}], 3)
 

@@ -1,0 +1,154 @@
+"""Affinity-aware TTA: plan host logic on the CPU, inversion / validity-aware ensemble / patch-first loop on the
+GPU — all against ``tests/golden/tta_affinity_goldens.npz``, which ``oracle/make_tta_affinity_goldens.py`` produced by running
+the REAL ``tta_affinity.py`` / ``tta_ensemble.py`` / ``tta_combinations.py`` / ``window.py`` of the reference."""
+import json
+import os
+from types import SimpleNamespace as NS
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import tta_oracle as TO
+from pytorch_connectomics_b200.inference import tta as T
+from pytorch_connectomics_b200.inference import tta_affinity as A
+
+G = np.load(os.path.join(GOLDEN, "tta_affinity_goldens.npz"))
+HAS_GPU = torch.cuda.is_available()
+
+
+def _cfg(offsets, mode, out_channels, extra=()):
+    targets = [dict(name=t) for t in extra] + [dict(name="affinity", kwargs=dict(offsets=offsets, affinity_mode=mode))]
+    return NS(data=NS(label_transform=NS(targets=targets, stack_outputs=True)), model=NS(out_channels=out_channels, heads={}))
+
+
+def test_affinity_plans_match_reference():
+    plans = json.loads(bytes(G["plans_json"]).decode())
+    assert len(plans) == 4
+    for rec in plans:
+        case = rec["case"]
+        nch = len(case["offsets"]) + len(case["extra"])
+        combos = T.resolve_tta_augmentation_combinations(NS(**case["tta"]), spatial_dims=3)
+        assert [[list(f), (list(p) if p is not None else None), int(k)] for f, p, k in combos] == rec["combos"]
+        plan = A.build_affinity_tta_plan(_cfg(case["offsets"], case["mode"], nch, case["extra"]), augmentation_combinations=combos,
+                                         num_raw=nch)
+        want = rec["plan"]
+        assert sorted(plan.partial_channels) == want["partial"] and sorted(list(s) for s in plan.shifts) == want["shifts"]
+        assert plan.num_channels == want["num_channels"] and plan.spatial_rank == want["rank"]
+        got = [[[m.src, m.dst, (list(m.shift) if m.shift is not None else None)] for m in v.moves] for v in plan.views]
+        assert got == want["views"]
+        # explicit groups give the same plan as the config walk
+        start = len(case["extra"])
+        plan2 = A.build_affinity_tta_plan(None, augmentation_combinations=combos, num_raw=nch, mode=case["mode"],
+                                          groups=[((start, nch), A.parse_affinity_offsets(case["offsets"]))])
+        assert plan2 == plan
+
+
+def test_affinity_plan_errors_and_geometry():
+    combos = [([], (1, 2), 1)]
+    with pytest.raises(ValueError, match="sign-reversed counterpart"):
+        A.build_affinity_tta_plan(None, augmentation_combinations=combos, num_raw=3, mode="deepem",
+                                  groups=[((0, 3), [(1, 0, 0), (0, 2, 0), (0, 0, 1)])])
+    with pytest.raises(ValueError, match="duplicate offsets"):
+        A.build_affinity_tta_plan(None, augmentation_combinations=combos, num_raw=2, mode="deepem", groups=[((0, 2), [(1, 0, 0), (1, 0, 0)])])
+    with pytest.raises(ValueError, match="Unsupported affinity_mode"):
+        A.build_affinity_tta_plan(None, augmentation_combinations=combos, num_raw=1, mode="nope", groups=[((0, 1), [(1, 0, 0)])])
+    with pytest.raises(ValueError, match="all three must match"):
+        A.build_affinity_tta_plan(_cfg(["1-0-0"], "deepem", 4), augmentation_combinations=combos, num_raw=1)
+    assert A.build_affinity_tta_plan(NS(data=None), augmentation_combinations=combos, num_raw=1) is None
+    assert A.transform_offset((1, 2, 3), flip_axes=[0], rotation_plane_spatial=(1, 2), k=1) == (-1, 3, -2)
+    assert A.valid_slices_for_shift((4, 5, 6), (1, -2, 0)) == (slice(1, 4), slice(0, 3), slice(0, 6))
+    assert A.valid_slices_for_shift((4, 5, 6), (9, 0, 0))[0] == slice(4, 4)
+    codes, scales, groups = T.resolve_activation_specs([dict(channels="1:3", activation="softmax"), dict(channels="0", activation="softmax")], 3)
+    assert codes == [0, 4, 4] and groups[1] == [1, 2] and groups[0] is None       # single-channel softmax is skipped
+    with pytest.raises(NotImplementedError):
+        T.resolve_activation_specs([dict(channels=":", activation="sigmoid"), dict(channels="0", activation="tanh")], 2)
+
+
+def _close(got, want, tol=2e-6):
+    got = got.float().cpu().numpy()
+    assert got.shape == want.shape
+    err = float(np.abs(got - want).max())
+    assert err <= tol, err
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["deepem", "banis"])
+def test_volume_first_affinity_ensemble_matches_reference(mode):
+    """6 affinity channels (unit + long range), 16 views: channel moves, roll shifts with invalid faces, per-channel
+    mean / min / max over partial channels — one fused fold kernel per view (exp differs by ulps: tolerance 2e-6)."""
+    x = torch.from_numpy(G["vf_x"]).cuda()
+    offs = ["1-0-0", "0-1-0", "0-0-1", "2-0-0", "0-3-0", "0-0-3"]
+    ens = T.TTAEnsemble(NS(flip_axes="all", rotation90_axes=[[1, 2]], rotate90_k=[0, 1],
+                           ensemble_mode=[["0:3", "mean"], ["3:5", "min"], ["5:", "max"]]),
+                        channel_activations=[dict(channels=":", activation="sigmoid")], cfg=_cfg(offs, mode, 6))
+    _close(ens.predict(x, TO.ramp_network(6)), G[f"vf_{mode}"])
+
+
+@pytest.mark.gpu
+def test_volume_first_selection_softmax_matches_reference():
+    x = torch.from_numpy(G["vf_x"]).cuda()
+    ens = T.TTAEnsemble(NS(flip_axes=[[1], [2]], rotation90_axes=[[1, 2]], rotate90_k=[0, 1, 2], ensemble_mode="mean"),
+                        channel_activations=[dict(channels=[1, 2], activation="softmax"), dict(channels=[0], activation="tanh")],
+                        select_channel=[2, 0, 1], cfg=_cfg(["0-1-0", "0-0-1"], "deepem", 3, ("binary",)))
+    _close(ens.predict(x, TO.ramp_network(3)), G["vf_select_softmax"])
+
+
+@pytest.mark.gpu
+def test_invert_view_and_accumulator_api_match_reference_semantics():
+    """The reference-shaped calls (invert_view -> preprocessing -> TTAEnsembleAccumulator.add) give the fused result."""
+    x = torch.from_numpy(G["vf_x"]).cuda()
+    offs = ["1-0-0", "0-1-0", "0-0-1", "2-0-0", "0-3-0", "0-0-3"]
+    tta_cfg = NS(flip_axes="all", rotation90_axes=[[1, 2]], rotate90_k=[0, 1])
+    combos = T.resolve_tta_augmentation_combinations(tta_cfg, spatial_dims=3)
+    plan = A.build_affinity_tta_plan(_cfg(offs, "deepem", 6), augmentation_combinations=combos, num_raw=6)
+    net = TO.ramp_network(6)
+    mode_map = T._resolve_ensemble_mode_map([["0:3", "mean"], ["3:5", "min"], ["5:", "max"]], 6)
+    acc = T.TTAEnsembleAccumulator((1, 6, 6, 8, 8), dtype=torch.float32, device=x.device, mode_map=mode_map,
+                                   partial_channels=sorted(plan.partial_channels), distributed_sharding=False, max_views=len(combos))
+    for vi, (f, p, k) in enumerate(combos):
+        pred = net(T.apply_view(x, f, p, k) if (f or (p is not None and k % 4)) else x)
+        inv, validity = A.invert_view(pred, flip_axes=f, rotation_plane_spatial=p, k=k, view_plan=plan.views[vi], tta_plan=plan)
+        ref_inv = TO.invert_view(pred.cpu(), f, p, k)
+        for mv in plan.views[vi].moves:                      # channels without a shift are pure moves of the un-viewed tensor
+            if mv.shift is None:
+                assert torch.equal(inv[:, mv.dst].cpu(), ref_inv[:, mv.src])
+            else:
+                box = validity.channels[mv.dst]
+                assert box == A.valid_slices_for_shift((6, 8, 8), mv.shift)
+        acc.add(torch.sigmoid(inv), validity)
+    _close(acc.finalize(), G["vf_deepem"])
+    with pytest.raises(ValueError, match="does not match accumulator"):
+        acc.add(torch.zeros(1, 6, 6, 8, 7, device=x.device), A.ViewValidity.all_valid(6))
+    # a partial channel that no view covers somewhere is an error, as in the reference
+    acc2 = T.TTAEnsembleAccumulator((1, 1, 2, 2, 2), dtype=torch.float32, device=x.device, mode_map=["mean"], partial_channels=[0],
+                                    distributed_sharding=False, max_views=2)
+    acc2.add(torch.ones(1, 1, 2, 2, 2, device=x.device), A.ViewValidity(((slice(0, 2), slice(0, 2), slice(1, 2)),)))
+    with pytest.raises(RuntimeError, match=r"zero valid contributions for channel 0 at voxel index \(0, 0, 0, 0\)"):
+        acc2.finalize()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,mode,blend", [("deepem_const", "deepem", "constant"), ("banis_bump", "banis", "bump")])
+def test_patch_first_local_tta_matches_reference(name, mode, blend):
+    """tta.py:880-1314 composed from the real reference functions vs the engine's loop: one slide over a 10x20x20 volume with
+    8x12x12 windows, 16 views per window batch, per-view overlap-add, per-shift weight volumes, coverage-masked ensemble."""
+    x = torch.from_numpy(G["pf_x"]).cuda()
+    ens = T.TTAEnsemble(NS(flip_axes="all", rotation90_axes=[[1, 2]], rotate90_k=[0, 1], ensemble_mode="mean"),
+                        channel_activations=[dict(channels=":", activation="sigmoid")], cfg=_cfg(["1-0-0", "0-2-0", "0-0-2"], mode, 3),
+                        output_dtype=torch.float32)
+    out = ens.predict_patch_first(x, TO.ramp_network(3), roi_size=(8, 12, 12), overlap=0.5, sw_batch_size=2, mode=blend)
+    _close(out, G[f"pf_{name}"], tol=5e-6)
+
+
+@pytest.mark.gpu
+def test_patch_first_full_channels_and_rotation_guard():
+    x = torch.from_numpy(G["pf_x"]).cuda()
+    ens = T.TTAEnsemble(NS(flip_axes="all", rotation90_axes=None, ensemble_mode=[["0", "mean"], ["1", "max"]]),
+                        channel_activations=[dict(channels=[0], activation="sigmoid")], output_dtype=torch.float32)
+    out = ens.predict_patch_first(x, TO.ramp_network(2), roi_size=(8, 12, 12), overlap=0.5, sw_batch_size=3, mode="bump")
+    _close(out, G["pf_full_only"], tol=5e-6)
+    bad = T.TTAEnsemble(NS(flip_axes="none", rotation90_axes=[[0, 1]], rotate90_k=[1]))
+    with pytest.raises(ValueError, match="only supports odd 90-degree rotations"):
+        bad.predict_patch_first(x, TO.ramp_network(1), roi_size=(8, 12, 12))
