@@ -1536,6 +1536,246 @@ __global__ void __launch_bounds__(128) tn_gemm_kernel(TnArgs a) {
   if (warp == 0) tmem_dealloc(acc, tmem_cols);
 }
 
+// ---------------------------------------------------------------------------- warp-specialised split-K wgrad GEMM
+// Same operands, row maps, GroupNorm-apply and partial layout as tn_gemm_kernel, restructured (round 2: the single-stage kernel ran
+// the up_1 weight gradients at 1.45 TB/s — ncu: 14 k SASS lines of unrolled row-map arithmetic with 64-bit divisions
+// (instruction-cache misses, `no_inst` 15 %), a third of the resident CTAs parked in tcgen05.alloc because only two fit in
+// TMEM, 10 warps per SM):
+//   * persistent, one CTA per SM; 4 loader warps -> NS-stage ring -> 1 MMA-issuing thread -> loaders write the partials;
+//   * operands go global -> shared with cp.async (16 B, zero-fill for rows outside the box): no register staging, every copy of
+//     a tile (64 KB) is in flight at once and the next tile's copies are issued before the previous tile is handed to the MMA
+//     thread; only a B operand that needs the GroupNorm affine passes through registers;
+//   * the source row of every tile voxel is computed ONCE per tile (one voxel per loader thread, 32-bit magic divisions) into a
+//     shared table instead of once per 16-byte chunk with 64-bit divisions;
+//   * MT (1 or 2) row tiles of dW per CTA share the staged B tile (M = 256: B is read once instead of twice).
+struct TnWsArgs {
+  TnArgs t;
+  int MT;                       // row tiles (128 rows of dW each) per CTA
+  int NS;                       // stages
+  uint32_t dm2, dm1;            // magic multipliers of the exact division by d2 / d1
+  int ds2, ds1;
+};
+constexpr int TNW_LOAD_WARPS = 4, TNW_THREADS = 32 * (TNW_LOAD_WARPS + 1);
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const uint32_t n = valid ? 16u : 0u;          // src-size 0: the 16 destination bytes are zero-filled, src is not read
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ int tnw_fdiv(int n, uint32_t m, int sh) { return (int)(((uint64_t)(uint32_t)n * (uint64_t)m) >> sh); }
+
+__global__ void __launch_bounds__(TNW_THREADS, 1) tn_gemm_ws_kernel(TnWsArgs w) {
+  const TnArgs& a = w.t;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int MT = w.MT, NS = w.NS;
+  const int m0 = blockIdx.y * MT * 128;
+  const int mrows = min(MT * 128, a.Ma - m0);            // valid rows of dW handled by this CTA
+  const int m8n = mrows >> 3;
+  const int n0 = blockIdx.z * TN_NCHUNK;
+  const int nb = min(TN_NCHUNK, a.Nb - n0), nb8 = nb >> 3;
+  const bool ones = a.ones && blockIdx.z == 0;
+  const int ncols = nb + (ones ? 16 : 0);
+  // MN-major canonical layout: 16 B chunk (8 channels of voxel v) of channel-group g at g*SBO + v*16; the SBO padding spreads
+  // the copies of one voxel's channel groups over distinct banks
+  const uint32_t sbo = 2048 + 16;
+  const uint32_t bytesA = (uint32_t)(MT * 16) * sbo, bytesB = (uint32_t)((TN_NCHUNK >> 3) + 2) * sbo;
+  const uint32_t stage = bytesA + bytesB;
+  uint8_t* sStage = smem;                                                      // NS x (A | B)
+  int* sRowA = reinterpret_cast<int*>(smem + (size_t)NS * stage);              // [NS][128] source row of A (-1: zero row)
+  int* sRowB = sRowA + NS * 128;                                               // [NS][128]
+  float* sScale = reinterpret_cast<float*>(sRowB + NS * 128);                  // [N][nb] GroupNorm affine of the B channels
+  float* sShift = sScale + (a.stats ? a.N * TN_NCHUNK : 0);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sShift + (a.stats ? a.N * TN_NCHUNK : 0));
+  uint64_t* empty = full + 4;
+  uint64_t* done = empty + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+  const uint32_t tmem_cols = tmem_cols_pow2((uint32_t)(MT * ncols));
+  if (warp == TNW_LOAD_WARPS) tmem_alloc(tmem_slot, tmem_cols);
+  if (tid == 0) {
+    for (int i = 0; i < NS; ++i) { mbar_init(&full[i], 32 * TNW_LOAD_WARPS); mbar_init(&empty[i], 1); }
+    mbar_init(done, 1);
+    fence_mbar_init();
+  }
+  // zero every stage once: channel groups beyond the valid ones stay zero for the whole kernel
+  for (uint32_t i = tid * 16; i < (uint32_t)NS * stage; i += TNW_THREADS * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
+  if (a.stats != nullptr) {
+    for (int i = tid; i < a.N * nb; i += TNW_THREADS) {
+      const int n = i / nb, c = i - n * nb, cg = n0 + c;
+      const double sm = a.stats[(int64_t)n * 2 * a.Nb + cg], q = a.stats[(int64_t)n * 2 * a.Nb + a.Nb + cg];
+      const double mean = sm * (double)a.inv_count;
+      double var = q * (double)a.inv_count - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const float gg = a.gamma[cg] * (float)(1.0 / sqrt(var + 1e-5));
+      sScale[n * TN_NCHUNK + c] = gg; sShift[n * TN_NCHUNK + c] = a.beta[cg] - (float)mean * gg;
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t acc = *tmem_slot;
+  const int tps = (int)((a.V + 127) / 128);           // tiles per sample
+  const int64_t ntiles = (int64_t)tps * a.N;
+
+  if (warp < TNW_LOAD_WARPS) {
+    // ===================================================================== loaders
+    const bool m8pow2 = (m8n & (m8n - 1)) == 0, n8pow2 = (nb8 & (nb8 - 1)) == 0;
+    const int m8sh = __ffs(m8n) - 1, n8sh = __ffs(nb8) - 1;
+    int64_t it = 0;
+    for (int64_t g = blockIdx.x; g < ntiles; g += gridDim.x, ++it) {
+      const int s = (int)(it % NS);
+      if (it >= NS) mbar_wait(&empty[s], (uint32_t)((it / NS - 1) & 1));
+      const int n = (int)(g / tps);
+      const int v0 = ((int)(g - (int64_t)n * tps)) * 128;
+      int* rowA = sRowA + s * 128;
+      int* rowB = sRowB + s * 128;
+      {   // source rows of voxel v0 + tid
+        const int v = v0 + tid;
+        int ra = -1, rb = -1;
+        if (v < (int)a.V) {
+          if (a.mapA == MAP_IDENT && a.mapB == MAP_IDENT) { ra = v; rb = v; }
+          else {
+            const int t = tnw_fdiv(v, w.dm2, w.ds2), x = v - t * a.d2;
+            const int z = tnw_fdiv(t, w.dm1, w.ds1), y = t - z * a.d1;
+            auto mapped = [&](int kind, int s1, int s2) -> int {
+              if (kind == MAP_IDENT) return v;
+              if (kind == MAP_PLUS1) return ((z + 1) * s1 + (y + 1)) * s2 + (x + 1);
+              if (kind == MAP_TIMES2) return ((2 * z) * s1 + 2 * y) * s2 + 2 * x;
+              return ((2 * z + 1) * s1 + (2 * y + 1)) * s2 + (2 * x + 1);
+            };
+            ra = mapped(a.mapA, a.as1, a.as2);
+            if (a.mapB >= 4) {   // dense-conv weight gradient: B row = input voxel feeding output voxel v through this tap
+              int iz, iy, ix;
+              bool ok = true;
+              if (a.mapB == 4) {
+                iz = z * a.tstride + a.tz - a.tpad; iy = y * a.tstride + a.ty - a.tpad; ix = x * a.tstride + a.tx - a.tpad;
+              } else {
+                const int qz = z + a.tpad - a.tz, qy = y + a.tpad - a.ty, qx = x + a.tpad - a.tx;
+                ok = qz >= 0 && qy >= 0 && qx >= 0 && (qz % a.tstride == 0) && (qy % a.tstride == 0) && (qx % a.tstride == 0);
+                iz = qz / a.tstride; iy = qy / a.tstride; ix = qx / a.tstride;
+              }
+              ok = ok && iz >= 0 && iz < a.bs0 && iy >= 0 && iy < a.bs1 && ix >= 0 && ix < a.bs2;
+              rb = ok ? (iz * a.bs1 + iy) * a.bs2 + ix : -1;
+            } else {
+              rb = mapped(a.mapB, a.bs1, a.bs2);
+            }
+          }
+        }
+        rowA[tid] = ra; rowB[tid] = rb;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");     // the row tables of this stage (loader warps only)
+      uint8_t* sA = sStage + (size_t)s * stage;
+      uint8_t* sB = sA + bytesA;
+      const uint4* An = a.A + (int64_t)n * a.a_sample8 + (m0 >> 3);
+      const uint4* Bn = a.B + (int64_t)n * a.b_sample8 + (n0 >> 3);
+      if (a.stats != nullptr) {
+        // B through registers: GroupNorm affine of this sample on the way in
+        const float* sc = sScale + n * TN_NCHUNK;
+        const float* sh = sShift + n * TN_NCHUNK;
+        staged_copy<8>(128 * nb8, tid, 128,
+            [&](int q) {
+              const int v = n8pow2 ? (q >> n8sh) : (q / nb8), g8 = q - v * nb8;
+              const int r = rowB[v];
+              return r >= 0 ? __ldg(Bn + (int64_t)r * a.b_pitch8 + g8) : make_uint4(0, 0, 0, 0);
+            },
+            [&](int q, const uint4& raw) {
+              const int v = n8pow2 ? (q >> n8sh) : (q / nb8), g8 = q - v * nb8;
+              uint4 val = raw;
+              if (rowB[v] >= 0) {
+                float f[8];
+                unpack8(raw, f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[g8 * 8 + j], sh[g8 * 8 + j]);
+                val = pack8(f);
+              }
+              *reinterpret_cast<uint4*>(sB + g8 * sbo + v * 16) = val;
+            });
+      } else {
+        const uint32_t sBu = smem_u32(sB);
+#pragma unroll 4
+        for (int q = tid; q < 128 * nb8; q += 128) {
+          const int v = n8pow2 ? (q >> n8sh) : (q / nb8), g8 = q - v * nb8;
+          const int r = rowB[v];
+          cp_async16(sBu + g8 * sbo + v * 16, Bn + (int64_t)(r >= 0 ? r : 0) * a.b_pitch8 + g8, r >= 0);
+        }
+      }
+      if (ones) *reinterpret_cast<uint4*>(sB + nb8 * sbo + tid * 16) = make_uint4((v0 + tid < (int)a.V) ? 0x3F80u : 0u, 0, 0, 0);
+      {
+        const uint32_t sAu = smem_u32(sA);
+#pragma unroll 4
+        for (int q = tid; q < 128 * m8n; q += 128) {
+          const int v = m8pow2 ? (q >> m8sh) : (q / m8n), g8 = q - v * m8n;
+          const int r = rowA[v];
+          cp_async16(sAu + g8 * sbo + v * 16, An + (int64_t)(r >= 0 ? r : 0) * a.a_pitch8 + g8, r >= 0);
+        }
+      }
+      // hand-off, one tile behind: the copies of tile it stay in flight while those of tile it-1 are drained; cp.async writes
+      // through the generic proxy, so the writer fences before it arrives (the MMA reads through the async proxy)
+      cp_async_commit();
+      if (it >= 1) {
+        cp_async_wait<1>();
+        fence_proxy_async_smem();
+        mbar_arrive(&full[(int)((it - 1) % NS)]);
+      }
+    }
+    if (it >= 1) {
+      cp_async_wait<0>();
+      fence_proxy_async_smem();
+      mbar_arrive(&full[(int)((it - 1) % NS)]);
+    }
+  } else if (tid == TNW_LOAD_WARPS * 32) {
+    // ===================================================================== MMA issuer (one thread)
+    const uint32_t idesc = umma_idesc_bf16(128, ncols, 1, 1);
+    int64_t it = 0;
+    for (int64_t g = blockIdx.x; g < ntiles; g += gridDim.x, ++it) {
+      const int s = (int)(it % NS);
+      mbar_wait(&full[s], (uint32_t)((it / NS) & 1));
+      tc_fence_after();
+      const uint32_t sA = smem_u32(sStage + (size_t)s * stage), sB = sA + bytesA;
+      const uint64_t bd = umma_desc(sB, 128, sbo);
+      for (int mt = 0; mt < MT; ++mt) {
+        if (mt * 128 >= mrows) break;
+        const uint64_t ad = umma_desc(sA + (uint32_t)(mt * 16) * sbo, 128, sbo);
+        for (int k = 0; k < 8; ++k)   // 128 voxels = 8 x K16; K-groups of 8 voxels are LBO = 128 B apart
+          umma_bf16(acc + mt * ncols, ad + (uint64_t)(k * 16), bd + (uint64_t)(k * 16), idesc, (it > 0 || k > 0) ? 1u : 0u);
+      }
+      tc_commit(&empty[s]);
+    }
+    tc_commit(done);
+  }
+  // ---- partial sums of this CTA
+  if (warp < TNW_LOAD_WARPS) {
+    mbar_wait(done, 0);
+    tc_fence_after();
+    for (int mt = 0; mt < MT; ++mt) {
+      const int row = mt * 128 + tid;
+      if (mt * 128 >= mrows) break;
+      const uint32_t trow = acc + mt * ncols + ((uint32_t)(warp * 32) << 16);
+      float* prow = a.part + ((int64_t)blockIdx.x * a.Mtot + m0 + row) * a.Ncols_tot;
+      for (int c16 = 0; c16 < ncols / 16; ++c16) {
+        uint32_t v[16];
+        tmem_ld16(trow + c16 * 16, v);
+        tmem_ld_wait();
+        if (row < mrows) {
+          const int col0 = (c16 * 16 < nb) ? (n0 + c16 * 16) : a.Nb;   // ones block lives after all Nb columns
+          float4* dst = reinterpret_cast<float4*>(prow + col0);
+          dst[0] = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
+          dst[1] = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
+          dst[2] = make_float4(__uint_as_float(v[8]), __uint_as_float(v[9]), __uint_as_float(v[10]), __uint_as_float(v[11]));
+          dst[3] = make_float4(__uint_as_float(v[12]), __uint_as_float(v[13]), __uint_as_float(v[14]), __uint_as_float(v[15]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TNW_LOAD_WARPS) tmem_dealloc(acc, tmem_cols);
+}
+
 // second stage: dW[m*ldm + n*ldn] = sum_p part[p][m][n] (n < Nw) ; db[m] = sum_p part[p][m][Nw]
 // 256 threads = 32 outputs x 8 partial-index lanes; fixed summation order -> run-to-run deterministic.
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ part, int P, int M, int Mtot,
@@ -2405,8 +2645,10 @@ extern "C" int pcb_mlp_bwd_fused(const void* y, const double* stats, const float
   return PCB_OK;
 }
 
+static inline bool tn_use_ws() { const char* e = getenv("PCB_TN_WS"); return !(e && e[0] == '0'); }
+
 static inline int tn_num_ctas(int64_t ntiles, int64_t Mtot, int64_t Nc) {
-  int64_t p = 148 * 3;                                  // three single-stage CTAs per SM
+  int64_t p = tn_use_ws() ? 148 : 148 * 3;              // persistent: one CTA per SM (the single-stage kernel: three)
   const int64_t cap = (int64_t)(96 << 20) / (Mtot * Nc * 4);   // keep the partial-sum workspace <= 96 MB
   if (p > cap) p = cap < 1 ? 1 : cap;
   if (p > ntiles) p = ntiles;
@@ -2478,9 +2720,38 @@ static int tn_gemm_impl(const void* A, const void* B, const double* stats, const
     configured = true;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  dim3 grid((unsigned)P, (unsigned)mt, (unsigned)ncn);
-  tn_gemm_kernel<<<grid, 128, smem, st>>>(a);
-  PCB_CHECK_LAUNCH("pcb_tn_gemm");
+  bool launched = false;
+  if (tn_use_ws() && a.V < (1ll << 30) && a.a_sample8 < (1ll << 40)) {
+    TnWsArgs w;
+    w.t = a;
+    const int ncols_max = (int)((Nb < TN_NCHUNK ? Nb : TN_NCHUNK) + (ones ? 16 : 0));
+    w.MT = (mt >= 2 && 2 * ncols_max <= 512 && ntiles >= 2 * P) ? 2 : 1;      // share the B tile between two row tiles of dW
+    const size_t stage = (size_t)(w.MT * 16 + (TN_NCHUNK >> 3) + 2) * (2048 + 16);
+    const size_t fixed = (size_t)(stats ? 2 * N * TN_NCHUNK * sizeof(float) : 0) + 9 * 8 + 16 + 128;
+    int ns = 4;
+    while (ns > 1 && (size_t)ns * (stage + 2 * 128 * sizeof(int)) + fixed > 227 * 1024) --ns;
+    w.NS = ns;
+    ws2_magic((uint32_t)(a.d2 > 0 ? a.d2 : 1), w.dm2, w.ds2);
+    ws2_magic((uint32_t)(a.d1 > 0 ? a.d1 : 1), w.dm1, w.ds1);
+    const size_t smem_ws = (size_t)ns * (stage + 2 * 128 * sizeof(int)) + fixed;
+    static DevFlag conf_ws;
+    if (!conf_ws) {
+      cudaFuncSetAttribute(tn_gemm_ws_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      conf_ws = cudaFuncSetAttribute(tn_gemm_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess;
+      if (!conf_ws) cudaGetLastError();
+    }
+    if (conf_ws && ns >= 2 && smem_ws <= 227 * 1024) {   // the hand-off trails by one tile: at least two stages
+      dim3 grid((unsigned)P, (unsigned)((mt + w.MT - 1) / w.MT), (unsigned)ncn);
+      tn_gemm_ws_kernel<<<grid, TNW_THREADS, smem_ws, st>>>(w);
+      PCB_CHECK_LAUNCH("pcb_tn_gemm(ws)");
+      launched = true;
+    }
+  }
+  if (!launched) {
+    dim3 grid((unsigned)P, (unsigned)mt, (unsigned)ncn);
+    tn_gemm_kernel<<<grid, 128, smem, st>>>(a);
+    PCB_CHECK_LAUNCH("pcb_tn_gemm");
+  }
   const int64_t total = Ma * (Nb + (db ? 1 : 0));
   reduce_partials_kernel<<<(unsigned)((total + 31) / 32), 256, 0, st>>>(workspace, P, (int)Ma, a.Mtot, a.Ncols_tot,
                                                                          (int)Nb, dW, ldm, ldn, db);

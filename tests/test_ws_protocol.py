@@ -16,6 +16,32 @@ def test_protocol_has_no_hazard(NB, NST, ntiles):
     M.check(ntiles, NB, NST, seeds=40)
 
 
+@pytest.mark.parametrize("ntiles", [1, 2, 3, 4, 5, 6, 8, 9, 13, 21])
+def test_level0_three_issuer_protocol_has_no_hazard(ntiles):
+    """mlp_bwd_ws_kernel (round 2): per-group issuers + weight-gradient issuer, deferred E2, accD double-buffered per group."""
+    M.check_l0(ntiles, seeds=40)
+
+
+def test_level0_model_flags_a_missing_g3_wait():
+    """E1(k) must see G3(k-1) retired (another issuer than the one that commits h_free): without that wait the model reports
+    sDh overwritten while G3 still reads it (or a wrong-tile read)."""
+
+    class _NoG3Wait(M.SimL0):
+        def epilogue(self, eg):
+            for op in super().epilogue(eg):
+                if op[0] == "wait" and op[1].name.startswith("d_full") and getattr(self, "_skip", True):
+                    continue
+                yield op
+
+    bad = 0
+    for seed in range(60):
+        try:
+            _NoG3Wait(9, seed).run()
+        except M.Hazard:
+            bad += 1
+    assert bad > 0
+
+
 class _BufferIndexed(M.Sim):
     """The first draft of the generalised kernel indexed the accumulator barriers by BUFFER (it % NB): with one buffer the
     two epilogue groups then share a barrier and each skips every other completion.  The model must flag it."""

@@ -250,6 +250,119 @@ class Sim:
             raise Hazard(f"{self.done_tiles_e2} of {self.ntiles} tiles finished")
 
 
+class SimL0(Sim):
+    """`mlp_bwd_ws_kernel` as of round 2: THREE MMA-issuing threads (one per epilogue group for G1/G2/G3, one for the weight
+    gradients G4/G5 of every tile in CTA order), accD double-buffered per group, and the epilogue order
+    E1(k) -> e1_done -> E2(k-1).  Same index / parity formulas as the CUDA code; resources per group g: acc[g], sH[g],
+    accD[g][b]."""
+
+    def __init__(self, ntiles: int, seed: int):
+        super().__init__(ntiles, 2, 4, seed)
+        self.bars["d_full"] = [Barrier(f"d_full[{i}]", 1) for i in range(4)]
+        self.bars["d_empty"] = [Barrier(f"d_empty[{i}]", 1) for i in range(4)]
+        self.accD = [Resource(f"accD[{i}]") for i in range(4)]
+
+    def issuer(self, g: int):
+        B = self.bars
+        k = 0
+        while 2 * k + g < self.ntiles:
+            it = 2 * k + g
+            s, b = it & 3, k & 1
+            yield ("wait", B["a_full"][s], (it >> 2) & 1)
+            self.mma(self.dur(0.05, 0.3), [self.sAD[s]], [self.acc[g]], {self.sAD[s]: it, self.acc[g]: it}, [B["hp_full"][g]])
+            yield ("wait", B["e1_done"][g], k & 1)
+            if k >= 2:
+                yield ("wait", B["d_empty"][g * 2 + b], ((k >> 1) - 1) & 1)
+            self.mma(self.dur(0.05, 0.3), [self.sH[g]], [self.accD[g * 2 + b]], {self.sH[g]: it, self.accD[g * 2 + b]: it},
+                     [B["d_full"][g * 2 + b]])
+            yield ("sleep", self.dur(0.0, 0.05))
+            k += 1
+
+    def wgrad_issuer(self):
+        B = self.bars
+        for it in range(self.ntiles):
+            g, s, k = it & 1, it & 3, it >> 1
+            yield ("wait", B["a_full"][s], (it >> 2) & 1)
+            yield ("wait", B["e1_done"][g], k & 1)
+            self.mma(self.dur(0.05, 0.4), [self.sH[g], self.sAD[s]], [], {self.sH[g]: it, self.sAD[s]: it}, [B["a_empty"][s], B["h_free"][g]])
+            yield ("sleep", self.dur(0.0, 0.05))
+
+    def loader(self, warp: int):
+        B = self.bars
+        it, uses = warp, 0
+        while it < self.ntiles:
+            if uses >= 1:
+                yield ("wait", B["a_empty"][warp], (uses - 1) & 1)
+            self.sAD[warp].begin_write(it)
+            yield ("sleep", self.dur(0.5, 3.0))
+            self.sAD[warp].end_write(it)
+            self.arrive(B["a_full"][warp])
+            it += 4
+            uses += 1
+
+    def epilogue(self, eg: int):
+        B = self.bars
+        k = 0
+        pending = None                                         # (tile, buffer) whose E2 is deferred
+
+        def e2(tile, b):
+            yield ("wait", B["d_full"][eg * 2 + b], ((tile >> 1) >> 1) & 1)
+            self.accD[eg * 2 + b].begin_read(tile, f"E{eg} E2")
+            yield ("sleep", self.dur(0.3, 1.5))
+            self.accD[eg * 2 + b].end_read(tile)
+            self.done_tiles_e2 += 1
+
+        while 2 * k + eg < self.ntiles:
+            it = 2 * k + eg
+            s = it & 3
+            yield ("wait", B["a_full"][s], (it >> 2) & 1)
+            self.sAD[s].begin_read(it, f"E{eg} db3")
+            yield ("sleep", self.dur(0.05, 0.3))
+            self.sAD[s].end_read(it)
+            yield ("wait", B["hp_full"][eg], k & 1)
+            if k >= 1:
+                yield ("wait", B["h_free"][eg], (k - 1) & 1)
+                yield ("wait", B["d_full"][eg * 2 + ((k - 1) & 1)], ((k - 1) >> 1) & 1)
+            self.acc[eg].begin_read(it, f"E{eg} E1")
+            self.sH[eg].begin_write(it)
+            yield ("sleep", self.dur(0.5, 2.5))
+            self.acc[eg].end_read(it)
+            self.sH[eg].end_write(it)
+            self.arrive(B["e1_done"][eg])
+            if pending is not None:
+                yield from e2(*pending)
+                self.arrive(B["d_empty"][eg * 2 + pending[1]])
+            pending = (it, k & 1)
+            k += 1
+        if pending is not None:
+            yield from e2(*pending)
+
+    def run(self):
+        roles = [self.loader(w) for w in range(4)] + [self.issuer(0), self.issuer(1), self.wgrad_issuer(), self.epilogue(0),
+                                                        self.epilogue(1)]
+        self.roles_alive = len(roles)
+        for g in roles:
+            self.at(0.0, lambda g=g: self.run_role(g))
+        steps = 0
+        while self.events:
+            t, _, fn = heapq.heappop(self.events)
+            self.now = t
+            fn()
+            steps += 1
+            if steps > 200000 + 400 * self.ntiles:
+                raise Hazard("runaway simulation")
+        if self.roles_alive or self.waiting:
+            stuck = [(b.name, p, b.phase) for _, b, p in self.waiting]
+            raise Hazard(f"deadlock: {self.roles_alive} role(s) alive, waiting on {stuck}")
+        if self.done_tiles_e2 != self.ntiles:
+            raise Hazard(f"{self.done_tiles_e2} of {self.ntiles} tiles finished")
+
+
+def check_l0(ntiles: int, seeds: int) -> None:
+    for seed in range(seeds):
+        SimL0(ntiles, seed).run()
+
+
 def check(ntiles: int, NB: int, NST: int, seeds: int) -> None:
     for seed in range(seeds):
         Sim(ntiles, NB, NST, seed).run()
