@@ -120,7 +120,11 @@ def cpu_train_rate(steps: int, warmup: int, cfg_key: str = "c2", side: int = 0):
     config's size per step (B=1; a bounded sample of the per-GPU batch, nothing is extrapolated)."""
     from oracle.mednext_oracle import create_mednext_v1
     spec = TRAIN_CONFIGS[cfg_key]
-    side = side or spec["crop"]
+    # MedNeXt-L at 224^3 costs ~5 minutes per fp32 CPU step: its sample is ONE real 96^3 crop, scaled by voxel count (the net is
+    # fully convolutional: cost per voxel is constant up to the border) — said in `sample`, never silently
+    full = spec["crop"]
+    side = side or (96 if (spec["size"] == "L" and full > 160) else full)
+    scale = (side / full) ** 3
     cores = _cpu_threads()
     torch.set_num_threads(cores)
     torch.manual_seed(0)
@@ -140,10 +144,12 @@ def cpu_train_rate(steps: int, warmup: int, cfg_key: str = "c2", side: int = 0):
         if i >= warmup:
             ts.append(dt)
     sec = sum(ts) / len(ts)
-    return {"value": 1.0 / sec, "unit": "sub-volumes/s", "cores": cores, "kind": "port",
+    how = "no size extrapolation" if side == full else (f"EXTRAPOLATED to {full}^3 by voxel count (x{1.0 / scale:.2f} time): a "
+                                                        f"{full}^3 fp32 CPU step of this net takes minutes")
+    return {"value": scale / sec, "unit": "sub-volumes/s", "cores": cores, "kind": "port",
             "sample": f"oracle MedNeXt-{spec['size']} fp32 train step (forward + BCE/Dice + backward + AdamW) on one real "
-                      f"1x{side}^3 crop per step ({sec:.2f} s/step, {len(ts)} timed); no size extrapolation",
-            "sec_per_step": sec}
+                      f"1x{side}^3 crop per step ({sec:.2f} s/step, {len(ts)} timed); {how}",
+            "sec_per_step": sec / scale}
 
 
 def cpu_infer_rate(steps: int, warmup: int, side: int = SIDE):

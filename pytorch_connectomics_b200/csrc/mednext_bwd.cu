@@ -280,6 +280,7 @@ __global__ void __launch_bounds__(128) mlp_bwd_kernel(MlpBwdArgs a) {
 // gradient comes out of the tensor cores for free; db3 = sum dOut is a column sum of the staged dOut tile.
 // Hact / dh never touch HBM, no split-K GEMM launches.
 struct MlpBwdFusedArgs {
+  int split;                    // ws2, one accumulator set: both epilogue groups share every tile (column split)
   MlpBwdArgs m;
   float* part3;      // [P][129][Co]  partial dW3^T rows 0..H-1, row 128 = partial db3
   float* part2;      // [P][128][H]   partial dW2^T (+ row C = db2)
@@ -1018,9 +1019,13 @@ __device__ __forceinline__ void ws2_stage_tile(uint8_t* __restrict__ dst, uint32
 
 __device__ __forceinline__ int ws2_fdiv(int n, uint32_t m, int sh) { return (int)(((uint64_t)(uint32_t)n * (uint64_t)m) >> sh); }
 
-template <int C8N, int NB>
+template <int C8N, int NB, int NST>   // NST operand stages (2..4): with 4 every loader warp has a tile in flight
 __global__ void __launch_bounds__(WS_THREADS, 1) mlp_bwd_ws2_kernel(MlpBwdFusedArgs fa) {
-  constexpr int NST = NB == 2 ? 4 : 2;
+  // One accumulator set (NB == 1): nothing of tile i+1 can overlap E1 of tile i, so BOTH epilogue groups work on the SAME tile
+  // — each takes half of the hidden columns in E1 and half of the channel columns in E2 (a warp reads its own TMEM lane
+  // quarter; columns are free) — instead of alternating tiles with one group idle: per-tile latency of E1 + E2 halves
+  // (opt-in, PCB_BWD_SPLIT=1: measured SLOWER than alternating groups once the operand ring has 4 stages — the shapes were loader-bound).
+  const bool SPLIT = NB == 1 && fa.split != 0;
   const MlpBwdArgs& a = fa.m;
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1062,7 +1067,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_bwd_ws2_kernel(MlpBwdFusedA
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) { mbar_init(&a_full[i], 32); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&hp_full[i], 1); mbar_init(&e1_done[i], 128); mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 128);
+      mbar_init(&hp_full[i], 1); mbar_init(&e1_done[i], SPLIT ? 256 : 128); mbar_init(&d_full[i], 1);
+      mbar_init(&d_empty[i], SPLIT ? 256 : 128);
       mbar_init(&h_free[i], 1);
     }
     mbar_init(w_done, 1);
@@ -1194,16 +1200,19 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_bwd_ws2_kernel(MlpBwdFusedA
     const int wq = warp & 3, row = wq * 32 + lane;
     const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
     float db3acc = 0.f;        // row < Co: running sum_v dOut[v, row] over this group's tiles
-    int64_t it = eg;
-    for (int64_t g = blockIdx.x + (int64_t)eg * gridDim.x; g < fa.ntiles; g += 2ll * gridDim.x, it += 2) {
+    // alternating: group eg owns the tiles it == eg (mod 2); SPLIT: both groups visit every tile, barriers indexed by it & 1
+    const int tstep = SPLIT ? 1 : 2;
+    int64_t it = SPLIT ? 0 : eg;
+    for (int64_t g = blockIdx.x + it * gridDim.x; g < fa.ntiles; g += (int64_t)tstep * gridDim.x, it += tstep) {
       const int b = (int)(it % NB), s = (int)(it % NST);
-      const uint32_t par = (uint32_t)((it >> 1) & 1);      // (it & 1) == eg: this group sees every completion of its barriers
+      const int q = (int)(it & 1);                         // barrier index of this tile (== eg when alternating)
+      const uint32_t par = (uint32_t)((it >> 1) & 1);      // every waiter sees every completion of the barriers it waits on
       const int n = (int)(g / fa.tps);
       const int tile0 = (int)((g - (int64_t)n * fa.tps) * 128);
       const int prow = tile0 + row;
       const bool row_ok = prow < (int)a.Vy;
       mbar_wait(&a_full[it & 3], (uint32_t)((it >> 2) & 1)); // this group reads sD[s] itself (conv3 bias gradient)
-      if (row < a.Co) {
+      if (row < a.Co && (!SPLIT || eg == 0)) {
         const uint8_t* col = sD + s * stageD + (row >> 3) * 128 + (row & 7) * 2;
         float sacc = 0.f;
 #pragma unroll 8
@@ -1211,7 +1220,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_bwd_ws2_kernel(MlpBwdFusedA
           sacc += __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(col + (r >> 3) * pitchD + (r & 7) * 16)) << 16);
         db3acc += sacc;
       }
-      mbar_wait(&hp_full[eg], par);
+      mbar_wait(&hp_full[q], par);
       {
         const int64_t pj = it - NB;                       // the tile whose Hact / dh sat in sH[b] / sDh[b] before
         if (pj >= 0) mbar_wait(&h_free[pj & 1], (uint32_t)((pj >> 1) & 1));
@@ -1222,8 +1231,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_bwd_ws2_kernel(MlpBwdFusedA
         const uint32_t t1 = tmem_base + b * a.H + lane_off, tg = tmem_base + colG + b * a.H + lane_off;
         uint8_t* dH = sH + b * stageH + (row >> 3) * pitchH + (row & 7) * 16;
         uint8_t* dDh = sDh + b * stageH + (row >> 3) * pitchH + (row & 7) * 16;
+        const int h16 = a.H / 16, e1_lo = SPLIT ? eg * (h16 >> 1) : 0, e1_hi = SPLIT ? (eg ? h16 : (h16 >> 1)) : h16;
 #pragma unroll 1
-        for (int c16 = 0; c16 < a.H / 16; ++c16) {
+        for (int c16 = e1_lo; c16 < e1_hi; ++c16) {
           uint32_t v1[16], vg[16];
           tmem_ld16(t1 + c16 * 16, v1);
           tmem_ld16(tg + c16 * 16, vg);
@@ -1252,17 +1262,19 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_bwd_ws2_kernel(MlpBwdFusedA
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(&e1_done[eg]);
+      mbar_arrive(&e1_done[q]);
       // ---- E2: g = dYhat -> bf16 -> HBM ; S1 += g ; S2 += g * xhat
       const int64_t yrow = ((int64_t)n * a.Vy + prow) * c8n;
-      mbar_wait(&d_full[eg], par);
+      mbar_wait(&d_full[q], par);
       tc_fence_after();
       {
         const uint32_t td = tmem_base + colD + b * a.C + lane_off;
         const float* rs = sRstd + n * a.C; const float* mr = sMR + n * a.C;
         double* sGn = sG + n * 2 * a.C;
+        constexpr int C16N = C8N / 2;
+        const int e2_lo = SPLIT ? eg * (C16N >> 1) : 0, e2_hi = SPLIT ? (eg ? C16N : (C16N >> 1)) : C16N;
 #pragma unroll 1
-        for (int c16 = 0; c16 < C8N / 2; ++c16) {
+        for (int c16 = e2_lo; c16 < e2_hi; ++c16) {
           uint32_t v[16];
           tmem_ld16(td + c16 * 16, v);
           uint4 y0 = make_uint4(0, 0, 0, 0), y1 = make_uint4(0, 0, 0, 0);
@@ -1294,7 +1306,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_bwd_ws2_kernel(MlpBwdFusedA
         }
       }
       tc_fence_before();
-      mbar_arrive(&d_empty[eg]);
+      mbar_arrive(&d_empty[q]);
     }
     if (row < a.Co) sDb3[eg * a.Co + row] = db3acc;
   }
@@ -1337,8 +1349,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_bwd_ws2_kernel(MlpBwdFusedA
   if (warp == WS_LOAD + WS_EPI) tmem_dealloc(tmem_base, tmem_cols);
 }
 
-static size_t mlp_bwd_ws2_smem(int C, int H, int Co, int N, int NB) {
-  const int NST = NB == 2 ? 4 : 2;
+static size_t mlp_bwd_ws2_smem(int C, int H, int Co, int N, int NB, int NST) {
   return (size_t)H * C * 2 + (size_t)H * Co * 2 + (size_t)C * H * 2 + (size_t)NST * 16 * (C / 8 + 1) * 128 +
          (size_t)NST * 16 * (Co / 8) * 128 + (size_t)2 * NB * 16 * (H / 8) * 128 + 2048 + (size_t)4 * N * C * 4 + (size_t)H * 4 +
          (size_t)2 * Co * 4 + (size_t)WS_LOAD * 128 * 4 + (size_t)N * 2 * C * 8 + 19 * 8 + 16 + 128;
@@ -1555,7 +1566,8 @@ struct TnWsArgs {
   uint32_t dm2, dm1;            // magic multipliers of the exact division by d2 / d1
   int ds2, ds1;
 };
-constexpr int TNW_LOAD_WARPS = 4, TNW_THREADS = 32 * (TNW_LOAD_WARPS + 1);
+constexpr int TNW_LOAD_WARPS = 8, TNW_LOADERS = 32 * TNW_LOAD_WARPS, TNW_THREADS = 32 * (TNW_LOAD_WARPS + 1);   // ncu (4 loader warps): the
+// loaders' own instruction issue bounded the kernel (13.5 k warp-instructions per tile on 4 warps, 8 % warps active)
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
   const uint32_t n = valid ? 16u : 0u;          // src-size 0: the 16 destination bytes are zero-filled, src is not read
@@ -1633,7 +1645,7 @@ __global__ void __launch_bounds__(TNW_THREADS, 1) tn_gemm_ws_kernel(TnWsArgs w) 
       const int v0 = ((int)(g - (int64_t)n * tps)) * 128;
       int* rowA = sRowA + s * 128;
       int* rowB = sRowB + s * 128;
-      {   // source rows of voxel v0 + tid
+      if (tid < 128) {   // source rows of voxel v0 + tid (element offsets of the row start, in uint4 units, fit 32 bits)
         const int v = v0 + tid;
         int ra = -1, rb = -1;
         if (v < (int)a.V) {
@@ -1665,9 +1677,10 @@ __global__ void __launch_bounds__(TNW_THREADS, 1) tn_gemm_ws_kernel(TnWsArgs w) 
             }
           }
         }
-        rowA[tid] = ra; rowB[tid] = rb;
+        rowA[tid] = ra < 0 ? -1 : ra * (int)a.a_pitch8;
+        rowB[tid] = rb < 0 ? -1 : rb * (int)a.b_pitch8;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");     // the row tables of this stage (loader warps only)
+      asm volatile("bar.sync 1, %0;" ::"n"(TNW_LOADERS) : "memory");     // the row tables of this stage (loader warps only)
       uint8_t* sA = sStage + (size_t)s * stage;
       uint8_t* sB = sA + bytesA;
       const uint4* An = a.A + (int64_t)n * a.a_sample8 + (m0 >> 3);
@@ -1676,11 +1689,11 @@ __global__ void __launch_bounds__(TNW_THREADS, 1) tn_gemm_ws_kernel(TnWsArgs w) 
         // B through registers: GroupNorm affine of this sample on the way in
         const float* sc = sScale + n * TN_NCHUNK;
         const float* sh = sShift + n * TN_NCHUNK;
-        staged_copy<8>(128 * nb8, tid, 128,
+        staged_copy<8>(128 * nb8, tid, TNW_LOADERS,
             [&](int q) {
               const int v = n8pow2 ? (q >> n8sh) : (q / nb8), g8 = q - v * nb8;
               const int r = rowB[v];
-              return r >= 0 ? __ldg(Bn + (int64_t)r * a.b_pitch8 + g8) : make_uint4(0, 0, 0, 0);
+              return r >= 0 ? __ldg(Bn + (r + g8)) : make_uint4(0, 0, 0, 0);
             },
             [&](int q, const uint4& raw) {
               const int v = n8pow2 ? (q >> n8sh) : (q / nb8), g8 = q - v * nb8;
@@ -1697,20 +1710,20 @@ __global__ void __launch_bounds__(TNW_THREADS, 1) tn_gemm_ws_kernel(TnWsArgs w) 
       } else {
         const uint32_t sBu = smem_u32(sB);
 #pragma unroll 4
-        for (int q = tid; q < 128 * nb8; q += 128) {
+        for (int q = tid; q < 128 * nb8; q += TNW_LOADERS) {
           const int v = n8pow2 ? (q >> n8sh) : (q / nb8), g8 = q - v * nb8;
           const int r = rowB[v];
-          cp_async16(sBu + g8 * sbo + v * 16, Bn + (int64_t)(r >= 0 ? r : 0) * a.b_pitch8 + g8, r >= 0);
+          cp_async16(sBu + g8 * sbo + v * 16, Bn + (max(r, 0) + g8), r >= 0);
         }
       }
-      if (ones) *reinterpret_cast<uint4*>(sB + nb8 * sbo + tid * 16) = make_uint4((v0 + tid < (int)a.V) ? 0x3F80u : 0u, 0, 0, 0);
+      if (ones && tid < 128) *reinterpret_cast<uint4*>(sB + nb8 * sbo + tid * 16) = make_uint4((v0 + tid < (int)a.V) ? 0x3F80u : 0u, 0, 0, 0);
       {
         const uint32_t sAu = smem_u32(sA);
 #pragma unroll 4
-        for (int q = tid; q < 128 * m8n; q += 128) {
+        for (int q = tid; q < 128 * m8n; q += TNW_LOADERS) {
           const int v = m8pow2 ? (q >> m8sh) : (q / m8n), g8 = q - v * m8n;
           const int r = rowA[v];
-          cp_async16(sAu + g8 * sbo + v * 16, An + (int64_t)(r >= 0 ? r : 0) * a.a_pitch8 + g8, r >= 0);
+          cp_async16(sAu + g8 * sbo + v * 16, An + (max(r, 0) + g8), r >= 0);
         }
       }
       // hand-off, one tile behind: the copies of tile it stay in flight while those of tile it-1 are drained; cp.async writes
@@ -1747,8 +1760,8 @@ __global__ void __launch_bounds__(TNW_THREADS, 1) tn_gemm_ws_kernel(TnWsArgs w) 
     }
     tc_commit(done);
   }
-  // ---- partial sums of this CTA
-  if (warp < TNW_LOAD_WARPS) {
+  // ---- partial sums of this CTA (warps 0-3: one TMEM lane quarter each)
+  if (warp < 4) {
     mbar_wait(done, 0);
     tc_fence_after();
     for (int mt = 0; mt < MT; ++mt) {
@@ -2576,7 +2589,14 @@ extern "C" int pcb_mlp_bwd_fused(const void* y, const double* stats, const float
     const bool want_ws2 = ws_env ? ws_env[0] == '2' : !l0_same;
     if (want_ws2 && (C == 32 || C == 64) && (Co == 32 || Co == 64) && H % 16 == 0 && H <= 128 && N <= 8) {
       const int NB = (2 * (2 * H + C) + Co + H <= 512) ? 2 : 1;
-      const size_t smem_ws = mlp_bwd_ws2_smem((int)C, (int)H, (int)Co, (int)N, NB);
+      // operand stages: 4 with double-buffered accumulators; with one accumulator set as many of 4 / 3 / 2 as shared memory
+      // allows (round 2: the NB = 1 shapes were bound by their loaders — two stages keep two of the four loader warps busy and
+      // 8 KB in flight per SM; splitting E1 / E2 over both epilogue groups alone changed nothing)
+      int nst = 4;
+      { const char* e = getenv("PCB_BWD_NST"); if (e && e[0] >= '2' && e[0] <= '4') nst = e[0] - '0'; }
+      if (NB == 2) nst = 4;
+      while (nst > 2 && mlp_bwd_ws2_smem((int)C, (int)H, (int)Co, (int)N, NB, nst) > 227 * 1024) --nst;
+      const size_t smem_ws = mlp_bwd_ws2_smem((int)C, (int)H, (int)Co, (int)N, NB, nst);
       if ((int64_t)NB * (2 * H + C) + Co + H <= 512 && smem_ws <= 227 * 1024) {
         auto conf = [&](const void* fn) {
           cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -2588,10 +2608,16 @@ extern "C" int pcb_mlp_bwd_fused(const void* y, const double* stats, const float
         ws2_magic((uint32_t)a.y2, fa.dm2, fa.ds2);
         ws2_magic((uint32_t)a.y1, fa.dm1, fa.ds1);
         { const char* e16 = getenv("PCB_BWD_LD16"); fa.ld16 = (e16 && e16[0] == '1') ? 1 : 0; }
+        // column split of E1 / E2 over both groups: opt-in — with 4 operand stages the alternating scheme is faster
+        // (up_0 2.34 vs 2.82 ms, level 1 0.385 vs 0.432 ms at 2 x 160^3)
+        { const char* sp = getenv("PCB_BWD_SPLIT"); fa.split = (sp && sp[0] == '1') ? 1 : 0; }
         bool launched = false;
-        if (C == 32 && NB == 2 && conf((const void*)mlp_bwd_ws2_kernel<4, 2>)) { mlp_bwd_ws2_kernel<4, 2><<<Pw, WS_THREADS, smem_ws, st>>>(fa); launched = true; }
-        else if (C == 32 && NB == 1 && conf((const void*)mlp_bwd_ws2_kernel<4, 1>)) { mlp_bwd_ws2_kernel<4, 1><<<Pw, WS_THREADS, smem_ws, st>>>(fa); launched = true; }
-        else if (C == 64 && NB == 1 && conf((const void*)mlp_bwd_ws2_kernel<8, 1>)) { mlp_bwd_ws2_kernel<8, 1><<<Pw, WS_THREADS, smem_ws, st>>>(fa); launched = true; }
+#define PCB_WS2(C8, NBV, NSV)                                                                                      \
+        if (!launched && C == 8 * C8 && NB == NBV && nst == NSV && conf((const void*)mlp_bwd_ws2_kernel<C8, NBV, NSV>)) {   \
+          mlp_bwd_ws2_kernel<C8, NBV, NSV><<<Pw, WS_THREADS, smem_ws, st>>>(fa); launched = true;                   \
+        }
+        PCB_WS2(4, 2, 4) PCB_WS2(4, 1, 4) PCB_WS2(4, 1, 3) PCB_WS2(4, 1, 2) PCB_WS2(8, 1, 4) PCB_WS2(8, 1, 3) PCB_WS2(8, 1, 2)
+#undef PCB_WS2
         if (launched) {
           PCB_CHECK_LAUNCH("pcb_mlp_bwd_fused(ws2)");
           reduce_partials_kernel<<<(unsigned)((H * Co + 31) / 32), 256, 0, st>>>(fa.part3, Pw, (int)H, 129, (int)Co, (int)Co, dW3, 1, H, nullptr);
@@ -2721,7 +2747,7 @@ static int tn_gemm_impl(const void* A, const void* B, const double* stats, const
   }
   cudaStream_t st = (cudaStream_t)stream;
   bool launched = false;
-  if (tn_use_ws() && a.V < (1ll << 30) && a.a_sample8 < (1ll << 40)) {
+  if (tn_use_ws() && a.V < (1ll << 30) && a.a_sample8 < (1ll << 31) && a.b_sample8 < (1ll << 31)) {
     TnWsArgs w;
     w.t = a;
     const int ncols_max = (int)((Nb < TN_NCHUNK ? Nb : TN_NCHUNK) + (ones ? 16 : 0));

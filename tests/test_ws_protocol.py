@@ -22,6 +22,12 @@ def test_level0_three_issuer_protocol_has_no_hazard(ntiles):
     M.check_l0(ntiles, seeds=40)
 
 
+@pytest.mark.parametrize("ntiles", [1, 2, 3, 4, 5, 8, 9, 21])
+def test_column_split_protocol_has_no_hazard(ntiles):
+    """mlp_bwd_ws2_kernel<*, 1> with both epilogue groups on every tile (e1_done / d_empty count both groups)."""
+    M.check_split(ntiles, seeds=40)
+
+
 def test_level0_model_flags_a_missing_g3_wait():
     """E1(k) must see G3(k-1) retired (another issuer than the one that commits h_free): without that wait the model reports
     sDh overwritten while G3 still reads it (or a wrong-tile read)."""

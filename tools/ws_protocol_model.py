@@ -363,12 +363,81 @@ def check_l0(ntiles: int, seeds: int) -> None:
         SimL0(ntiles, seed).run()
 
 
+class SimSplit(Sim):
+    """`mlp_bwd_ws2_kernel<*, 1>` in column-split mode (round 2): one accumulator set, BOTH epilogue groups visit every tile and
+    take half of the E1 / E2 columns each; e1_done / d_empty expect both groups, barriers are indexed by the tile parity."""
+
+    def __init__(self, ntiles: int, seed: int):
+        super().__init__(ntiles, 1, 2, seed)
+        for name in ("e1_done", "d_empty"):
+            self.bars[name] = [Barrier(f"{name}[{i}]", 2) for i in range(2)]
+        self.sHh = [Resource("sH/sDh[lo]"), Resource("sH/sDh[hi]")]
+
+    def mma_thread(self):
+        B = self.bars
+
+        def second_half(j):
+            sj, qj = j % 2, j & 1
+            yield ("wait", B["e1_done"][qj], (j >> 1) & 1)
+            jj = j - 1
+            if jj >= 0:
+                yield ("wait", B["d_empty"][jj & 1], (jj >> 1) & 1)
+            rd = {self.sHh[0]: j, self.sHh[1]: j, self.accD[0]: j}
+            self.mma(self.dur(0.05, 0.3), [self.sHh[0], self.sHh[1]], [self.accD[0]], rd, [B["d_full"][qj]])
+            rd2 = {self.sHh[0]: j, self.sHh[1]: j, self.sAD[sj]: j}
+            self.mma(self.dur(0.05, 0.4), [self.sHh[0], self.sHh[1], self.sAD[sj]], [], rd2, [B["a_empty"][j & 3], B["h_free"][qj]])
+
+        it = 0
+        while it < self.ntiles:
+            s = it % 2
+            yield ("wait", B["a_full"][it & 3], (it >> 2) & 1)
+            if it >= 1:
+                yield from second_half(it - 1)
+            self.mma(self.dur(0.05, 0.3), [self.sAD[s]], [self.acc[0]], {self.sAD[s]: it, self.acc[0]: it}, [B["hp_full"][it & 1]])
+            yield ("sleep", self.dur(0.0, 0.05))
+            it += 1
+        if it >= 1:
+            yield from second_half(it - 1)
+
+    def epilogue(self, eg: int):
+        B = self.bars
+        for it in range(self.ntiles):
+            s, q, par = it % 2, it & 1, (it >> 1) & 1
+            yield ("wait", B["a_full"][it & 3], (it >> 2) & 1)
+            if eg == 0:
+                self.sAD[s].begin_read(it, "E0 db3")
+                yield ("sleep", self.dur(0.05, 0.3))
+                self.sAD[s].end_read(it)
+            yield ("wait", B["hp_full"][q], par)
+            pj = it - 1
+            if pj >= 0:
+                yield ("wait", B["h_free"][pj & 1], (pj >> 1) & 1)
+            self.acc[0].begin_read(it, f"E{eg} E1")
+            self.sHh[eg].begin_write(it)
+            yield ("sleep", self.dur(0.3, 1.5))
+            self.acc[0].end_read(it)
+            self.sHh[eg].end_write(it)
+            self.arrive(B["e1_done"][q])
+            yield ("wait", B["d_full"][q], par)
+            self.accD[0].begin_read(it, f"E{eg} E2")
+            yield ("sleep", self.dur(0.2, 1.0))
+            self.accD[0].end_read(it)
+            if eg == 0:
+                self.done_tiles_e2 += 1
+            self.arrive(B["d_empty"][q])
+
+
+def check_split(ntiles: int, seeds: int) -> None:
+    for seed in range(seeds):
+        SimSplit(ntiles, seed).run()
+
+
 def check(ntiles: int, NB: int, NST: int, seeds: int) -> None:
     for seed in range(seeds):
         Sim(ntiles, NB, NST, seed).run()
 
 
-CONFIGS = [(2, 4), (1, 2)]      # (NB, NST): level-0 kernel / single-buffered shapes
+CONFIGS = [(2, 4), (1, 2), (1, 3), (1, 4)]      # (NB, NST): double-buffered / single-buffered accumulators with 2..4 operand stages
 
 
 def main(seeds: int = 200) -> int:
