@@ -46,6 +46,7 @@ struct GemmArgs {
   int dual;                              // segment 2 feeds a SECOND accumulator: out = GELU(acc1 + bias), out2 = acc2 * GELU'(acc1 + bias)
   uint4* out2;                           // [N][Vout][Nout] bf16 (dual)
   int map2;                              // segment-2 row source: 0 per `mode`, 1 output row, 2 output row + 1 on every axis (o1, o2 = box dims)
+  int async_ld;                          // operands without a GroupNorm affine go global -> shared by cp.async (PCB_GW_ASYNC=0: registers)
   double* gst;                           // GroupNorm-backward sums [N][2][Nout] f64 (+=): S1 = sum g, S2 = sum g * xhat with xhat from
                                          // `res` (= y) and `stats`; the bf16-rounded g is what gets stored and summed
 };
@@ -135,6 +136,31 @@ __device__ __forceinline__ void gw_stage_k64(uint8_t* __restrict__ dst, const ui
   }
 }
 
+// The same tile with cp.async (operands that need no GroupNorm affine: hidden activations, dOut, dh, weights): 32 copies of
+// 16 B per lane, the whole 16 KB chunk in flight at once instead of four 4 KB register batches (round 2: the deep GEMMs were
+// bound by the bytes their four loader warps kept in flight).  Rows without a source are zero-filled (src-size 0).  The caller
+// waits for the group and fences the async proxy before it arrives on the stage barrier.
+template <bool TAB>
+__device__ __forceinline__ void gw_stage_k64_async(uint8_t* __restrict__ dst, const uint4* __restrict__ src, int64_t pitch8,
+                                                   const int* __restrict__ tab, int row0, int nvalid, int lane) {
+  const int rl = lane & 7, cs = lane >> 3;
+  const uint32_t dl = smem_u32(dst) + cs * 128 + rl * 16;
+#pragma unroll 4
+  for (int rg = 0; rg < 16; ++rg) {
+    const int r = rg * 8 + rl;
+    int ry;
+    if (TAB) ry = tab[r]; else ry = r < nvalid ? row0 + r : -1;
+    const uint4* p = src + (int64_t)(ry >= 0 ? ry : 0) * pitch8 + cs;
+    const uint32_t n = ry >= 0 ? 16u : 0u;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dl + rg * 1024), "l"(p), "r"(n) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dl + rg * 1024 + 512), "l"(p + 4), "r"(n) : "memory");
+  }
+}
+__device__ __forceinline__ void gw_async_join() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(GW_THREADS, 1) gemm_ws_kernel(GemmArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -216,16 +242,22 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gemm_ws_kernel(GemmArgs a) {
           const bool seg1 = kc < kch1;
           const int64_t bp8 = (seg1 ? a.K1 : a.K2) >> 3;
           const uint4* bsrc = (seg1 ? a.b : a.b2) + (int64_t)nt_fixed * BN * bp8 + (seg1 ? kc : kc - kch1) * 8;
-          for (int h = 0; h < BN; h += 128)
-            gw_stage_k64<false, false>(sB + kc * bstage + h * 128, bsrc + (int64_t)h * bp8, bp8, nullptr, 0, min(128, BN - h),
-                                       nullptr, nullptr, lane);
+          for (int h = 0; h < BN; h += 128) {
+            if (a.async_ld) gw_stage_k64_async<false>(sB + kc * bstage + h * 128, bsrc + (int64_t)h * bp8, bp8, nullptr, 0, min(128, BN - h), lane);
+            else gw_stage_k64<false, false>(sB + kc * bstage + h * 128, bsrc + (int64_t)h * bp8, bp8, nullptr, 0, min(128, BN - h),
+                                            nullptr, nullptr, lane);
+          }
         }
+        if (a.async_ld) gw_async_join();
         fence_proxy_async_smem();
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(b_full);
     }
-    for (int64_t q = warp; q < nchunks; q += GW_LOAD) {
+    // A stage is filled by ONE warp for the whole kernel (warp w <-> stage w; warps >= S stay idle): a warp that skipped a
+    // completion of `empty[s]` would mis-read its phase parity and overwrite a stage the MMA has not consumed — with S = 3
+    // (MedNeXt-L up_1: ten resident weight chunks leave room for three A stages) the old q += 4 walk did exactly that and hung.
+    for (int64_t q = warp; warp < S && q < nchunks; q += S) {
       const int64_t i = q / kch;
       const int kc = (int)(q - i * kch);
       const int64_t t = blockIdx.x + i * gridDim.x;
@@ -261,6 +293,9 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gemm_ws_kernel(GemmArgs a) {
         if (norm) {
           if (tab) gw_stage_k64<true, true>(dA, src, p8, rowY, tile0, nvalid, sc, sh, lane);
           else gw_stage_k64<true, false>(dA, src, p8, rowY, tile0, nvalid, sc, sh, lane);
+        } else if (a.async_ld) {
+          if (tab) gw_stage_k64_async<true>(dA, src, p8, rowY, tile0, nvalid, lane);
+          else gw_stage_k64_async<false>(dA, src, p8, rowY, tile0, nvalid, lane);
         } else {
           if (tab) gw_stage_k64<false, true>(dA, src, p8, rowY, tile0, nvalid, sc, sh, lane);
           else gw_stage_k64<false, false>(dA, src, p8, rowY, tile0, nvalid, sc, sh, lane);
@@ -270,13 +305,17 @@ __global__ void __launch_bounds__(GW_THREADS, 1) gemm_ws_kernel(GemmArgs a) {
       } else {
         const int64_t p8 = a.K2 >> 3;
         const uint4* src = a.a2 + (int64_t)n * a.Va2 * p8 + (kc - kch1) * 8;
-        gw_stage_k64<false, true>(dA, src, p8, rowX, 0, 0, nullptr, nullptr, lane);
+        if (a.async_ld) gw_stage_k64_async<true>(dA, src, p8, rowX, 0, 0, lane);
+        else gw_stage_k64<false, true>(dA, src, p8, rowX, 0, 0, nullptr, nullptr, lane);
         bp8 = p8;
         bsrc = a.b2 + (int64_t)nt * BN * p8 + (kc - kch1) * 8;
       }
       if (!a.bres)
-        for (int h = 0; h < BN; h += 128)
-          gw_stage_k64<false, false>(dB + h * 128, bsrc + (int64_t)h * bp8, bp8, nullptr, 0, min(128, BN - h), nullptr, nullptr, lane);
+        for (int h = 0; h < BN; h += 128) {
+          if (a.async_ld) gw_stage_k64_async<false>(dB + h * 128, bsrc + (int64_t)h * bp8, bp8, nullptr, 0, min(128, BN - h), lane);
+          else gw_stage_k64<false, false>(dB + h * 128, bsrc + (int64_t)h * bp8, bp8, nullptr, 0, min(128, BN - h), nullptr, nullptr, lane);
+        }
+      if (a.async_ld) gw_async_join();             // no-op for a chunk that only went through registers
       fence_proxy_async_smem();
       mbar_arrive(&full[s]);
     }
@@ -488,6 +527,7 @@ static bool gw_launch(GemmArgs a, cudaStream_t st) {
     dyn = fixed + S * stage;
   }
   a.S = S;
+  { const char* e = getenv("PCB_GW_ASYNC"); a.async_ld = (e && e[0] == '0') ? 0 : 1; }
   gw_magic((uint32_t)(a.o2 > 0 ? a.o2 : 1), a.dm2, a.ds2);
   gw_magic((uint32_t)(a.o1 > 0 ? a.o1 : 1), a.dm1, a.ds1);
   static DevFlag conf;

@@ -17,6 +17,15 @@ if os.environ.get("PCB_DEBUG_HANG"):      # find a hung launch: blocking launche
     os.environ["CUDA_LAUNCH_BLOCKING"] = "1"
     faulthandler.dump_traceback_later(int(os.environ["PCB_DEBUG_HANG"]), exit=True)
 
+if os.environ.get("PCB_TRACE_OPS"):       # print every op scope as it starts (the last line names a hung launch)
+    _enter = L.prof.__enter__
+
+    def _traced(self):
+        print("op", self.name, flush=True)
+        return _enter(self)
+
+    L.prof.__enter__ = _traced
+
 ap = argparse.ArgumentParser()
 ap.add_argument("--size", default="L")
 ap.add_argument("--side", type=int, default=224)
