@@ -38,10 +38,12 @@ __device__ __forceinline__ int64_t map_row(int kind, int64_t v, int d1, int d2, 
 __device__ __forceinline__ void stage_rows_k(uint8_t* dst, const uint4* __restrict__ src, int rows, int kc8,
                                              int64_t pitch8, int tid, int nthreads = 128) {
   const uint32_t sbo = kc8 * 128;
+  const bool p2 = (kc8 & (kc8 - 1)) == 0;          // kc8 = 12 for H = 96 (MedNeXt-L level 0): plain division
+  const int sh = __ffs(kc8) - 1;
   staged_copy<8>(rows * kc8, tid, nthreads,
-      [&](int q) { const int r = q >> __ffs(kc8) - 1, c8 = q & (kc8 - 1); return __ldg(src + (int64_t)r * pitch8 + c8); },
+      [&](int q) { const int r = p2 ? (q >> sh) : (q / kc8), c8 = q - r * kc8; return __ldg(src + (int64_t)r * pitch8 + c8); },
       [&](int q, const uint4& v) {
-        const int r = q >> __ffs(kc8) - 1, c8 = q & (kc8 - 1);
+        const int r = p2 ? (q >> sh) : (q / kc8), c8 = q - r * kc8;
         *reinterpret_cast<uint4*>(dst + (r >> 3) * sbo + c8 * 128 + (r & 7) * 16) = v;
       });
 }
@@ -2520,7 +2522,9 @@ extern "C" int pcb_mlp_bwd(const void* y, const double* stats, const float* gamm
 
 static bool mlp_bwd_fused_ok(int64_t C, int64_t H, int64_t Co, int64_t N, int64_t Vy, int64_t Vout) {
   auto pow2 = [](int64_t v) { return v > 0 && (v & (v - 1)) == 0; };
-  return getenv("PCB_NO_FUSED_BWD") == nullptr && pow2(C) && pow2(Co) && pow2(H) && C <= 64 && Co <= 128 && H < 128 + 1 && H % 16 == 0 &&
+  // a hidden width that is not a power of two (MedNeXt-L level 0: H = 96) is served by mlp_bwd_ws2_kernel only
+  const bool ws2_shape = (C == 32 || C == 64) && (Co == 32 || Co == 64) && N <= 8;
+  return getenv("PCB_NO_FUSED_BWD") == nullptr && pow2(C) && pow2(Co) && (pow2(H) || ws2_shape) && C <= 64 && Co <= 128 && H < 128 + 1 && H % 16 == 0 &&
          3 * H + C + Co <= 512 && (C + Co) / 8 * 128 <= 8 * 256 && N <= 8 && Vy < (1ll << 30) && Vout < (1ll << 30) &&
          mlp_bwd_fused_smem((int)C, (int)H, (int)Co, (int)N) <= 227 * 1024;
 }
@@ -2631,6 +2635,7 @@ extern "C" int pcb_mlp_bwd_fused(const void* y, const double* stats, const float
       }
     }
   }
+  PCB_CHECK_ARG((H & (H - 1)) == 0, "pcb_mlp_bwd_fused: H=%lld needs the generalised warp-specialised kernel (PCB_BWD_WS must not be 0 / 1)", (long long)H);
   // warp-specialised variant for the level-0 shape (see mlp_bwd_ws_kernel); same workspace layout, P = grid size
   {
     const char* ws_env = getenv("PCB_BWD_WS");

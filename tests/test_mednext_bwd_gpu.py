@@ -117,6 +117,9 @@ def _mk_pair(kind, cin, cout, r, k):
     ("down", 128, 256, 2, 3, (10, 12, 14)),    # deep path + strided res-conv K segment
     ("up", 128, 64, 2, 3, (6, 6, 6)),          # deep path: padded rows, sparse res-conv rows, BN = 64
     ("same", 256, 256, 4, 3, (6, 8, 10)),      # deep path: H = 1024, 4 column tiles, K = 256
+    ("same", 32, 32, 3, 3, (20, 18, 22)),      # MedNeXt-L level 0: H = 96 (not a power of two) on the fused ws2 backward
+    ("up", 128, 64, 4, 3, (20, 20, 20)),       # MedNeXt-L up_1: 10 resident weight chunks leave THREE A stages (hung before
+                                               # round 2: a loader warp skipped a completion of the stage barrier), 500 row tiles
 ])
 def test_block_backward(kind, cin, cout, r, k, size):
     o, p = _mk_pair(kind, cin, cout, r, k)
@@ -370,6 +373,17 @@ def test_block_backward_kernel_variants_level0(ws, size, monkeypatch):
     ragged last tiles, more tiles than one wave of loader stages (24*20*18 = 68 tiles per sample)."""
     monkeypatch.setenv("PCB_BWD_WS", ws)
     test_block_backward("same", 32, 32, 2, 3, size)
+
+
+@pytest.mark.parametrize("nst", ["2", "3", "4"])
+def test_block_backward_ws2_operand_stages(nst, monkeypatch):
+    """mlp_bwd_ws2_kernel with one accumulator set on 2 / 3 / 4 operand stages (the default takes as many as shared memory
+    allows) and, on top, the opt-in column split of E1 / E2 over both epilogue groups: many tiles per CTA, ragged last tile."""
+    monkeypatch.setenv("PCB_BWD_NST", nst)
+    test_block_backward("same", 64, 64, 2, 3, (30, 28, 26))
+    test_block_backward("up", 64, 32, 2, 3, (14, 15, 16))
+    monkeypatch.setenv("PCB_BWD_SPLIT", "1")
+    test_block_backward("same", 64, 64, 2, 3, (30, 28, 26))
 
 
 @pytest.mark.parametrize("kind,cin,cout,size", [
