@@ -1048,8 +1048,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_bwd_ws2_kernel(MlpBwdFusedA
   float* sMR = sRstd + fa.N * a.C;                     // [N][C] mean*rstd
   float* sB2 = sMR + fa.N * a.C;                       // [H]
   float* sDb3 = sB2 + a.H;                             // [2][Co]
-  int* sRow = reinterpret_cast<int*>(sDb3 + 2 * a.Co); // [4 loader warps][128] dOut row of the tile in flight (UP mode)
-  double* sG = reinterpret_cast<double*>(sRow + WS_LOAD * 128);   // [N][2C]
+  int* sRow = reinterpret_cast<int*>(sDb3 + 2 * a.Co); // [4 loader warps][128] dOut row of the tile in flight (UP mode only)
+  double* sG = reinterpret_cast<double*>(sRow + (a.mode == PCB_DW_UP ? WS_LOAD * 128 : 0));   // [N][2C]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sG + fa.N * 2 * a.C);
   // Barriers are indexed by the TILE (it & 3 for the loader hand-offs, it & 1 for the accumulator hand-offs) and the DATA
   // by it % NST / it % NB: every barrier then has exactly one waiting role that sees each of its completions, whatever
@@ -1351,10 +1351,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) mlp_bwd_ws2_kernel(MlpBwdFusedA
   if (warp == WS_LOAD + WS_EPI) tmem_dealloc(tmem_base, tmem_cols);
 }
 
-static size_t mlp_bwd_ws2_smem(int C, int H, int Co, int N, int NB, int NST) {
+static size_t mlp_bwd_ws2_smem(int C, int H, int Co, int N, int NB, int NST, bool up = true) {
   return (size_t)H * C * 2 + (size_t)H * Co * 2 + (size_t)C * H * 2 + (size_t)NST * 16 * (C / 8 + 1) * 128 +
          (size_t)NST * 16 * (Co / 8) * 128 + (size_t)2 * NB * 16 * (H / 8) * 128 + 2048 + (size_t)4 * N * C * 4 + (size_t)H * 4 +
-         (size_t)2 * Co * 4 + (size_t)WS_LOAD * 128 * 4 + (size_t)N * 2 * C * 8 + 19 * 8 + 16 + 128;
+         (size_t)2 * Co * 4 + (up ? (size_t)WS_LOAD * 128 * 4 : 0) + (size_t)N * 2 * C * 8 + 19 * 8 + 16 + 128;
 }
 
 static void ws2_magic(uint32_t d, uint32_t& m, int& sh) {
@@ -2233,6 +2233,139 @@ static bool launch_dw_wgrad_tiled(cudaStream_t st, const uint4* dy, const uint4*
   return true;
 }
 
+// ---------------------------------------------------------------------------- tiled stride-2 depthwise weight gradient (k = 3)
+// dW[tap][c] += sum_v center[v, c] * fine[2 v - 1 + tap, c]: the weight gradient of the stride-2 conv (center = dY on the coarse
+// grid, fine = x) and of the transposed stride-2 conv (center = x on the coarse grid, fine = dY).  Same decomposition as
+// dw_wgrad_same_tiled_kernel: a 2x7x8 coarse tile and its 5x15x17 fine brick (x 32 channels) are staged once; thread = (tap row
+// (dz,dy), 8-channel chunk, row partition) walks the coarse rows along W with the three x-taps of the fine row in registers (two
+// new fine vectors per coarse voxel).  The untiled kernel launched one grid per (dz,dy) tap row, so both tensors were re-streamed
+// from L2 nine times (up_0: 21 GB of L2 traffic for 2.3 GB of operands, 1.26 ms per batch-4 step).
+constexpr int W2_Z = 2, W2_Y = 7, W2_X = 8;
+constexpr int W2_BZ = 2 * W2_Z + 1, W2_BY = 2 * W2_Y + 1, W2_BX = 2 * W2_X + 1;
+
+__global__ void __launch_bounds__(256, 2) dw_wgrad_s2_tiled_kernel(const uint4* __restrict__ center, const uint4* __restrict__ fine,
+                                                                double* __restrict__ dW, int c0, int c1, int c2, int f0, int f1,
+                                                                int f2, int C, int tiles_y, int tiles_x, int nbricks, int N) {
+  constexpr int K = 3, NPART = 7;
+  extern __shared__ __align__(128) uint8_t dsm[];
+  uint4* s_f = reinterpret_cast<uint4*>(dsm);                               // [BZ][BY][BX][4]
+  uint4* s_c = s_f + W2_BZ * W2_BY * W2_BX * 4;                             // [Z][Y][X][4]
+  double* s_red = reinterpret_cast<double*>(s_c + W2_Z * W2_Y * W2_X * 4);  // [27][32]
+  const int ncg = C >> 5, cg = blockIdx.x % ncg, bx0 = blockIdx.x / ncg, nbx = gridDim.x / ncg;
+  const int tid = threadIdx.x, CH = C >> 3;
+  const int cc = tid & 3, tr = (tid >> 2) % (K * K), part = (tid >> 2) / (K * K);
+  const int dz = tr / K, dyy = tr % K;
+  const bool worker = part < NPART;
+  uint64_t acc[K][4];
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[k][c] = 0ull;
+  for (int i = tid; i < K * K * K * 32; i += 256) s_red[i] = 0.0;
+  for (int b = bx0; b < nbricks * N; b += nbx) {
+    const int n = b / nbricks;
+    int t = b - n * nbricks;
+    const int tx = t % tiles_x; t /= tiles_x;
+    const int ty = t % tiles_y, tz = t / tiles_y;
+    const int z0 = tz * W2_Z, y0 = ty * W2_Y, x0 = tx * W2_X;
+    const uint4* fn = fine + (int64_t)n * f0 * f1 * f2 * CH + cg * 4;
+    const uint4* cn = center + (int64_t)n * c0 * c1 * c2 * CH + cg * 4;
+    __syncthreads();   // previous brick fully consumed
+    staged_copy<10>(W2_BZ * W2_BY * W2_BX * 4, tid, 256,
+        [&](int q) {
+          const int c4 = q & 3, v = q >> 2;
+          const int bx = v % W2_BX, by = (v / W2_BX) % W2_BY, bz = v / (W2_BX * W2_BY);
+          const int gz = 2 * z0 - 1 + bz, gy = 2 * y0 - 1 + by, gx = 2 * x0 - 1 + bx;
+          if (gz < 0 || gz >= f0 || gy < 0 || gy >= f1 || gx < 0 || gx >= f2) return make_uint4(0, 0, 0, 0);
+          return __ldg(fn + (((int64_t)gz * f1 + gy) * f2 + gx) * CH + c4);
+        },
+        [&](int q, const uint4& v4) { s_f[q] = v4; });
+    staged_copy<2>(W2_Z * W2_Y * W2_X * 4, tid, 256,
+        [&](int q) {
+          const int c4 = q & 3, v = q >> 2;
+          const int bx = v % W2_X, by = (v / W2_X) % W2_Y, bz = v / (W2_X * W2_Y);
+          const int gz = z0 + bz, gy = y0 + by, gx = x0 + bx;
+          if (gz >= c0 || gy >= c1 || gx >= c2) return make_uint4(0, 0, 0, 0);
+          return __ldg(cn + (((int64_t)gz * c1 + gy) * c2 + gx) * CH + c4);
+        },
+        [&](int q, const uint4& v4) { s_c[q] = v4; });
+    __syncthreads();
+    if (worker) {
+      for (int r = part; r < W2_Z * W2_Y; r += NPART) {     // coarse (z,y) rows owned by this partition
+        const int lz = r / W2_Y, ly = r % W2_Y;
+        const uint4* frow = s_f + (((2 * lz + dz) * W2_BY + (2 * ly + dyy)) * W2_BX) * 4 + cc;
+        const uint4* crow = s_c + ((lz * W2_Y + ly) * W2_X) * 4 + cc;
+        uint64_t w0[4], w1[4], w2[4];
+        {
+          const uint4 v4 = frow[0];
+          w2[0] = pk2(bf16_lo(v4.x), bf16_hi(v4.x)); w2[1] = pk2(bf16_lo(v4.y), bf16_hi(v4.y));
+          w2[2] = pk2(bf16_lo(v4.z), bf16_hi(v4.z)); w2[3] = pk2(bf16_lo(v4.w), bf16_hi(v4.w));
+        }
+#pragma unroll 2
+        for (int xx = 0; xx < W2_X; ++xx) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) w0[c] = w2[c];
+          const uint4 a4 = frow[(2 * xx + 1) * 4], b4 = frow[(2 * xx + 2) * 4];
+          w1[0] = pk2(bf16_lo(a4.x), bf16_hi(a4.x)); w1[1] = pk2(bf16_lo(a4.y), bf16_hi(a4.y));
+          w1[2] = pk2(bf16_lo(a4.z), bf16_hi(a4.z)); w1[3] = pk2(bf16_lo(a4.w), bf16_hi(a4.w));
+          w2[0] = pk2(bf16_lo(b4.x), bf16_hi(b4.x)); w2[1] = pk2(bf16_lo(b4.y), bf16_hi(b4.y));
+          w2[2] = pk2(bf16_lo(b4.z), bf16_hi(b4.z)); w2[3] = pk2(bf16_lo(b4.w), bf16_hi(b4.w));
+          const uint4 d4 = crow[xx * 4];
+          uint64_t d[4];
+          d[0] = pk2(bf16_lo(d4.x), bf16_hi(d4.x)); d[1] = pk2(bf16_lo(d4.y), bf16_hi(d4.y));
+          d[2] = pk2(bf16_lo(d4.z), bf16_hi(d4.z)); d[3] = pk2(bf16_lo(d4.w), bf16_hi(d4.w));
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            acc[0][c] = fma2(d[c], w0[c], acc[0][c]);
+            acc[1][c] = fma2(d[c], w1[c], acc[1][c]);
+            acc[2][c] = fma2(d[c], w2[c], acc[2][c]);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (worker) {
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float a0, a1;
+        upk2(acc[k][c], a0, a1);
+        atomicAdd(&s_red[((dz * K + dyy) * K + k) * 32 + cc * 8 + 2 * c], (double)a0);
+        atomicAdd(&s_red[((dz * K + dyy) * K + k) * 32 + cc * 8 + 2 * c + 1], (double)a1);
+      }
+  }
+  __syncthreads();
+  for (int i = tid; i < K * K * K * 32; i += 256) atomicAdd(&dW[(int64_t)(i >> 5) * C + cg * 32 + (i & 31)], s_red[i]);
+}
+
+static bool launch_dw_wgrad_s2_tiled(cudaStream_t st, const uint4* center, const uint4* fine, double* dW, const int64_t c_size[3],
+                                     const int64_t f_size[3], int C, int N) {
+  static const bool off = getenv("PCB_NO_WG2") != nullptr;
+  if (off) return false;
+  const size_t smem = (size_t)W2_BZ * W2_BY * W2_BX * 64 + (size_t)W2_Z * W2_Y * W2_X * 64 + (size_t)27 * 32 * 8 + 16;
+  static DevFlag configured;
+  if (!configured) {
+    cudaFuncSetAttribute(dw_wgrad_s2_tiled_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (cudaFuncSetAttribute(dw_wgrad_s2_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    configured = true;
+  }
+  const int tz = (int)((c_size[0] + W2_Z - 1) / W2_Z), ty = (int)((c_size[1] + W2_Y - 1) / W2_Y), tx = (int)((c_size[2] + W2_X - 1) / W2_X);
+  const int64_t nb = (int64_t)tz * ty * tx;
+  if (nb * N >= (1ll << 31)) return false;
+  const int ncg = C / 32;
+  int ctas = (148 * 2) / ncg;                 // two resident CTAs per SM over all channel groups
+  if (ctas < 1) ctas = 1;
+  if (nb * N < ctas) ctas = (int)(nb * N);
+  dw_wgrad_s2_tiled_kernel<<<(unsigned)(ctas * ncg), 256, smem, st>>>(center, fine, dW, (int)c_size[0], (int)c_size[1], (int)c_size[2],
+                                                                     (int)f_size[0], (int)f_size[1], (int)f_size[2], C, ty, tx, (int)nb, N);
+  return true;
+}
+
 // ============================================================================ head / stem backward
 // head: out[n,k,v] = sum_c x[v,c] w[c,k] + b[k].   dX[v,c] = sum_k dO[k,v] w[c,k];
 //       dW[c,k] += sum_v x[v,c] dO[k,v]; db[k] += sum_v dO[k,v]     (float64 accumulators)
@@ -2599,8 +2732,8 @@ extern "C" int pcb_mlp_bwd_fused(const void* y, const double* stats, const float
       int nst = 4;
       { const char* e = getenv("PCB_BWD_NST"); if (e && e[0] >= '2' && e[0] <= '4') nst = e[0] - '0'; }
       if (NB == 2) nst = 4;
-      while (nst > 2 && mlp_bwd_ws2_smem((int)C, (int)H, (int)Co, (int)N, NB, nst) > 227 * 1024) --nst;
-      const size_t smem_ws = mlp_bwd_ws2_smem((int)C, (int)H, (int)Co, (int)N, NB, nst);
+      while (nst > 2 && mlp_bwd_ws2_smem((int)C, (int)H, (int)Co, (int)N, NB, nst, mode == PCB_DW_UP) > 227 * 1024) --nst;
+      const size_t smem_ws = mlp_bwd_ws2_smem((int)C, (int)H, (int)Co, (int)N, NB, nst, mode == PCB_DW_UP);
       if ((int64_t)NB * (2 * H + C) + Co + H <= 512 && smem_ws <= 227 * 1024) {
         auto conf = [&](const void* fn) {
           cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -2856,6 +2989,11 @@ extern "C" int pcb_dwconv_wgrad(const void* center, const void* neigh, double* d
     else if (k == 5) ok = launch_dw_wgrad_tiled<5>(st0, (const uint4*)center, (const uint4*)neigh, dW, (int)c_size[0], (int)c_size[1], (int)c_size[2], (int)C, (int)N);
     else ok = launch_dw_wgrad_tiled<7>(st0, (const uint4*)center, (const uint4*)neigh, dW, (int)c_size[0], (int)c_size[1], (int)c_size[2], (int)C, (int)N);
     if (ok) { PCB_CHECK_LAUNCH("pcb_dwconv_wgrad(tiled)"); return PCB_OK; }
+  }
+  if (stride == 2 && k == 3 && C % 32 == 0 &&
+      launch_dw_wgrad_s2_tiled(st0, (const uint4*)center, (const uint4*)neigh, dW, c_size, n_size, (int)C, (int)N)) {
+    PCB_CHECK_LAUNCH("pcb_dwconv_wgrad(stride-2 tiled)");
+    return PCB_OK;
   }
   DwWgArgs a{(int)c_size[0], (int)c_size[1], (int)c_size[2], (int)n_size[0], (int)n_size[1], (int)n_size[2], (int)C, stride};
   const int64_t items = (int64_t)a.c0 * a.c1 * ((a.c2 + DW_XB_WG - 1) / DW_XB_WG) * (C / 8);
