@@ -123,7 +123,10 @@ def cpu_train_rate(steps: int, warmup: int, cfg_key: str = "c2", side: int = 0):
     # MedNeXt-L at 224^3 costs ~5 minutes per fp32 CPU step: its sample is ONE real 96^3 crop, scaled by voxel count (the net is
     # fully convolutional: cost per voxel is constant up to the border) — said in `sample`, never silently
     full = spec["crop"]
-    side = side or (96 if (spec["size"] == "L" and full > 160) else full)
+    auto_small = not side and spec["size"] == "L" and full > 160
+    side = side or (96 if auto_small else full)
+    if not auto_small:
+        full = side                 # an explicit side (tests) is its own unit: nothing is scaled
     scale = (side / full) ** 3
     cores = _cpu_threads()
     torch.set_num_threads(cores)
@@ -250,14 +253,16 @@ KERNELS = {
     "dwconv_fwd": "pcb::dwconv_same_tiled_kernel<3> / dwconv_kernel (depthwise stencil + GN statistics)",
     "dw_bwd_data": "pcb::dwconv_same_tiled_kernel<3> / dwconv_kernel (stencil data gradient)",
     "dw_wgrad": "pcb::dw_wgrad_same_tiled_kernel<3> / dw_wgrad_kernel (depthwise weight gradient)",
-    "tn_gemm": "pcb::tn_gemm_kernel (split-K wgrad GEMM, tcgen05 MN-major)",
+    "tn_gemm": "pcb::tn_gemm_ws_kernel (split-K wgrad GEMM, cp.async ring, tcgen05 MN-major)",
     "gn_bwd": "pcb::gn_dy_kernel (GroupNorm backward)",
 }
-NCU_TRAFFIC = {  # DRAM bytes (read + write) PER SAMPLE of one launch: dram__bytes.sum.per_second x gpu__time_duration from the
-    # batch-1 block capture profiles/r01_blocks_final.ncu-rep (raw page: profiles/r01_blocks_final_raw.csv)
-    "mlp_bwd_fused:m0C32H64Co32V4096000": 759.3e6,
-    "mlp_bwd_fused:m2C64H128Co32V4019679": 1253.9e6,
-    "mlp_fwd:m0C32H64Co32V4096000": 758.6e6,
+NCU_TRAFFIC = {  # DRAM bytes (read + write) PER SAMPLE of one launch (dram__bytes_read.sum + dram__bytes_write.sum of the
+    # `ncu --set full` captures, divided by the samples of the launch): round 2 kernels from profiles/r02_mlp_fwd_bwd_l0.ncu-rep and
+    # profiles/r02_mlp_bwd_ws2.ncu-rep (batch 2, table in profiles/r02_kernels_summary.md), the unchanged stencils / gn_dy from
+    # profiles/r01_blocks_final.ncu-rep (batch 1)
+    "mlp_bwd_fused:m0C32H64Co32V4096000": 772.5e6,
+    "mlp_bwd_fused:m2C64H128Co32V4019679": 1270.5e6,
+    "mlp_fwd:m0C32H64Co32V4096000": 771.7e6,
     "mlp_fwd:m2C64H128Co32V4096000": 1084.8e6,
     "dwconv_fwd:m0C32V4096000": 487.3e6,
     "dw_bwd_data:m0C32V4096000": 763.4e6,
@@ -310,7 +315,7 @@ def build_roofline(prof, batch, peak_gbs, measured, step_ms, nsteps):
                      "algorithmic_bytes": nbytes, "op_ms_per_step": g["ms"], "share_of_step": g["ms"] / step_ms})
     roof = dict(rows[0])
     roof["peak_source"] = "MEASURED_PEAKS.json (of measured)" if measured else "fallback 6650 GB/s (of fallback)"
-    roof["traffic_source"] = "ncu DRAM bytes (read + write) per launch from the batch-1 capture in profiles/ x samples per launch; null = not captured"
+    roof["traffic_source"] = "ncu DRAM bytes (read + write) per sample from the captures in profiles/ (r02_kernels_summary.md) x samples per launch; null = not captured"
     roof["others"] = rows[1:]
     return roof
 

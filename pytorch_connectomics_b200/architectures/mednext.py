@@ -483,6 +483,37 @@ def build_mednext_custom(cfg) -> ConnectomicsModel:
     return MedNeXtWrapper(model, deep_supervision=params["deep_supervision"])
 
 
-__all__ = ["MedNeXt", "MedNeXtBlock", "MedNeXtDownBlock", "MedNeXtUpBlock", "OutBlock", "MedNeXtWrapper",
+def upkern_load_weights(target_model, source_model):
+    """``mednext_models.py:487-537`` — initialise a large-kernel MedNeXt from a trained small-kernel one (UpKern).
+
+    The reference delegates to ``nnunet_mednext.run.load_weights.upkern_load_weights`` (un-vendored); its published algorithm is
+    restated here: every key present in both state dicts is copied when the spatial kernel dims agree and resized with
+    ``F.interpolate(..., mode="trilinear")`` when they do not (channel dims must agree); keys missing from the source keep the
+    target's initialisation.  Accepts the wrappers (``.model``) or bare ``MedNeXt`` modules and returns ``target_model``."""
+    import torch.nn.functional as F
+    tgt = getattr(target_model, "model", target_model)
+    src = getattr(source_model, "model", source_model)
+    src_sd, tgt_sd = src.state_dict(), tgt.state_dict()
+    for key, cur in tgt_sd.items():
+        if key not in src_sd:
+            continue
+        old = src_sd[key]
+        if tuple(old.shape) == tuple(cur.shape):
+            tgt_sd[key] = old.detach().clone().to(cur.device, cur.dtype)
+            continue
+        if old.dim() != cur.dim() or old.dim() < 3 or tuple(old.shape[:2]) != tuple(cur.shape[:2]):
+            raise ValueError(f"UpKern: {key} has shape {tuple(old.shape)} in the source and {tuple(cur.shape)} in the target; "
+                             "the models must have identical architecture except kernel size")
+        tgt_sd[key] = F.interpolate(old.detach().float(), size=tuple(cur.shape[2:]), mode="trilinear").to(cur.device, cur.dtype)
+    tgt.load_state_dict(tgt_sd)
+    _lib_epoch_bump()
+    return target_model
+
+
+def _lib_epoch_bump() -> None:
+    L.PARAM_EPOCH[0] += 1       # kernel-layout weight caches repack (parameter storage was rewritten wholesale)
+
+
+__all__ = ["upkern_load_weights", "MedNeXt", "MedNeXtBlock", "MedNeXtDownBlock", "MedNeXtUpBlock", "OutBlock", "MedNeXtWrapper",
            "MedNeXtTaskHead", "MedNeXtMultiHeadWrapper", "build_mednext", "build_mednext_custom",
            "create_mednext_v1"]

@@ -2,3 +2,4 @@
 from .ddp import FlatGradArena, allreduce_gradients, broadcast_parameters  # noqa: F401
 from .graph import GraphedTrainStep  # noqa: F401
 from .optim import FusedAdamW, build_fused_adamw, reference_param_groups  # noqa: F401
+from .step import ArenaTrainStep  # noqa: F401

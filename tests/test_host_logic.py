@@ -339,3 +339,31 @@ def test_apply_border_mask_matches_reference():
             torch.manual_seed(0)
             a = torch.rand(*shape)
             assert torch.equal(W.apply_border_mask(a.clone(), mask), R.apply_border_mask(a.clone(), mask))
+
+
+def test_upkern_load_weights_resizes_depthwise_kernels():
+    """mednext_models.py:487-537 (UpKern): equal-shaped tensors are copied, k=3 depthwise / transposed kernels are resized to
+    k=5 by trilinear interpolation — checked against F.interpolate on the same tensors, through wrappers and bare modules."""
+    import torch.nn.functional as F
+    from pytorch_connectomics_b200.architectures import mednext as PM
+    torch.manual_seed(0)
+    kw = dict(in_channels=1, n_channels=16, n_classes=2, exp_r=2, deep_supervision=False, do_res=True, do_res_up_down=True,
+              block_counts=[1] * 9)
+    small, big = PM.MedNeXt(kernel_size=3, **kw), PM.MedNeXt(kernel_size=5, **kw)
+    before = {k: v.clone() for k, v in big.state_dict().items()}
+    out = PM.upkern_load_weights(PM.MedNeXtWrapper(big, deep_supervision=False), PM.MedNeXtWrapper(small, deep_supervision=False))
+    assert out.model is big
+    ssd, bsd = small.state_dict(), big.state_dict()
+    resized = 0
+    for k, v in bsd.items():
+        if ssd[k].shape == v.shape:
+            assert torch.equal(v, ssd[k]), k
+        else:
+            assert v.shape[2:] == (5, 5, 5) and ssd[k].shape[2:] == (3, 3, 3)
+            assert torch.allclose(v, F.interpolate(ssd[k], size=(5, 5, 5), mode="trilinear")), k
+            assert not torch.equal(v, before[k])
+            resized += 1
+    assert resized == 9 + 4 + 4            # conv1 of 9 stages' blocks, 4 down and 4 up blocks
+    bad = PM.MedNeXt(kernel_size=5, **{**kw, "n_channels": 32})
+    with pytest.raises(ValueError, match="identical architecture"):
+        PM.upkern_load_weights(bad, small)

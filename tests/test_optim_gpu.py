@@ -146,3 +146,44 @@ def test_fused_adamw_trains_mednext_like_torch_adamw():
     # weights agree to 2e-5; the two forwards still round to bf16 at different places (|out| ~ 3: one bf16 ulp = 1.6e-2)
     rel = float((out_a.float() - out_b.float()).norm() / out_a.float().norm())
     assert rel < 1e-2, rel
+
+
+@pytest.mark.gpu
+def test_arena_train_step_accumulates_like_one_large_batch():
+    """trainer.py:314-334 `accumulate_grad_batches`: two micro-batches of 2 with the loss divided by 2 move the weights exactly
+    like one batch of 4 (mean loss; GroupNorm is per sample, so the per-sample arithmetic is identical — only the fp32 order of
+    the gradient sums differs), the optimizer runs once per window, and the grad-norm clip sees the accumulated gradient."""
+    from pytorch_connectomics_b200.architectures import mednext as PM
+    from pytorch_connectomics_b200.training import ArenaTrainStep
+
+    def make():
+        torch.manual_seed(5)
+        net = PM.MedNeXt(1, 16, 1, exp_r=2, kernel_size=3, deep_supervision=False, do_res=True, do_res_up_down=True,
+                         block_counts=[1] * 9).to(DEV).train()
+        arena = FlatGradArena(net.parameters())
+        opt = FusedAdamW(reference_param_groups(net, 1e-3, 0.01), arena=arena, max_grad_norm=1.0)
+        return net, opt
+
+    bce = torch.nn.functional.binary_cross_entropy_with_logits
+    loss_fn = lambda out, t: bce(out.float(), t)
+    torch.manual_seed(6)
+    x = torch.rand(4, 1, 32, 32, 32, device=DEV).half()
+    t = (torch.rand(4, 1, 32, 32, 32, device=DEV) > 0.8).float()
+    a, oa = make()
+    b, ob = make()
+    one = ArenaTrainStep(a, loss_fn, oa)
+    acc = ArenaTrainStep(b, loss_fn, ob, accumulate_grad_batches=2)
+    la = one(x, t)
+    assert not acc.will_step
+    l0 = acc(x[:2], t[:2])
+    assert acc.optimizer_steps == 0 and acc.will_step
+    l1 = acc(x[2:], t[2:])
+    assert acc.optimizer_steps == 1 and one.optimizer_steps == 1
+    torch.cuda.synchronize()
+    assert abs(float(la) - 0.5 * (float(l0) + float(l1))) < 1e-5
+    assert abs(float(oa.grad_norm()) - float(ob.grad_norm())) < 1e-4 * float(oa.grad_norm())
+    for (k, pa), pb in zip(a.named_parameters(), b.parameters()):
+        assert torch.allclose(pa, pb, rtol=0, atol=2e-6), (k, float((pa - pb).abs().max()))
+    assert acc.flush() is None and acc(x[:2], t[:2]) is not None and acc.flush() == 1 and acc.optimizer_steps == 2
+    with pytest.raises(ValueError):
+        ArenaTrainStep(a, loss_fn, oa, accumulate_grad_batches=0)
