@@ -421,7 +421,12 @@ __global__ void __launch_bounds__(256, 2) dwconv_up3_tiled_kernel(const uint4* _
 #pragma unroll 1
   for (int item = tid; item < 4 * 8 * 4 * 4; item += 256) {
     const int xseg = (item >> 2) & 3, row = item >> 4;              // 4 segments of 8 outputs; 32 output rows (loz, loy)
-    const int loz = row >> 3, loy = row & 7;
+    // rows are enumerated by (z, y) parity class so that the two rows of a warp run the same 1 / 2 / 4 tap-row loop (no
+    // divergence), and a thread's two items (row, row + 16) pair the classes (even,even)+(odd,odd) / (even,odd)+(odd,even):
+    // 1 + 4 and 2 + 2 tap rows — balanced across the CTA's warps
+    const int cls = row >> 3, kk = row & 7;
+    const int pz = cls >> 1, py = (cls ^ (cls >> 1)) & 1;           // class order 00, 01, 11, 10
+    const int loz = 2 * (kk >> 2) + pz, loy = 2 * (kk & 3) + py;
     const int oz = 2 * z0 + loz, oy = 2 * y0 + loy, ox0 = 2 * x0 + 8 * xseg;
     if (oz >= a.Do || oy >= a.Ho || ox0 >= a.Wo) continue;
     uint64_t acc[8][4];

@@ -676,6 +676,7 @@ class TTAEnsemble:
             w_full = None
             w_part = {}
             scratch_w = {}
+            value_map = value_map32 = pmap32 = ones_patch = None
             dev = sample.device
             for s0 in range(0, len(slices), int(sw_batch_size)):
                 cur = slices[s0:s0 + int(sw_batch_size)]
@@ -697,10 +698,10 @@ class TTAEnsemble:
                         raw_full = [c for c in range(n_raw) if c not in pset]
                         if odt is None:
                             odt = pred.dtype
-                        self._value_map, _ = W.build_sliding_accumulator_weight_maps(roi, mode=mode, device=dev, value_dtype=odt)
-                        self._value_map32 = self._value_map.float()
-                        self._pmap32, _ = W.build_sliding_accumulator_weight_maps(roi, mode=mode, device=dev, value_dtype=torch.float32)
-                        self._ones = torch.ones((1, 1, *roi), device=dev, dtype=torch.float32)
+                        value_map, _ = W.build_sliding_accumulator_weight_maps(roi, mode=mode, device=dev, value_dtype=odt)
+                        value_map32 = value_map.float()
+                        pmap32, _ = W.build_sliding_accumulator_weight_maps(roi, mode=mode, device=dev, value_dtype=torch.float32)
+                        ones_patch = torch.ones((1, 1, *roi), device=dev, dtype=torch.float32)
                         if raw_full:
                             w_full = torch.zeros((1, 1, *padded), device=dev, dtype=torch.float32)
                         if raw_part:
@@ -721,7 +722,7 @@ class TTAEnsemble:
                         if w_full is not None:
                             sw = scratch_w.setdefault("f", torch.zeros_like(w_full))
                             for loc in locs:
-                                W._accumulate_window(self._ones, self._value_map32, w_full, sw, roi, padded, (0, 0, 0), loc, roi)
+                                W._accumulate_window(ones_patch, value_map32, w_full, sw, roi, padded, (0, 0, 0), loc, roi)
                         for key, wacc in w_part.items():
                             box = tuple(slice(0, r) for r in roi) if not key else valid_slices_for_shift(roi, key)
                             lo = tuple(int(sl.start) for sl in box)
@@ -730,7 +731,7 @@ class TTAEnsemble:
                                 continue
                             sw = scratch_w.setdefault("p", torch.zeros_like(wacc))
                             for loc in locs:
-                                W._accumulate_window(self._ones, self._pmap32, wacc, sw, roi, padded, lo,
+                                W._accumulate_window(ones_patch, pmap32, wacc, sw, roi, padded, lo,
                                                      tuple(loc[a] + lo[a] for a in range(3)), ext)
                         weights_added = True
                     if raw_full:
@@ -739,13 +740,13 @@ class TTAEnsemble:
                         pf = pred if len(raw_full) == n_raw else pred[:, raw_full]
                         pf = pf.to(odt).contiguous()
                         sw = scratch_w.setdefault("fv", torch.zeros((1, 1, *padded), device=dev, dtype=odt))
-                        W._accumulate_batch(pf, self._value_map, full_acc[li], sw, roi, padded, locs)
+                        W._accumulate_batch(pf, value_map, full_acc[li], sw, roi, padded, locs)
                     if raw_part:
                         if part_acc[li] is None:
                             part_acc[li] = torch.zeros((1, len(raw_part), *padded), device=dev, dtype=torch.float32)
                         pp = pred[:, raw_part].float().contiguous()
                         sw = scratch_w.setdefault("pv", torch.zeros((1, 1, *padded), device=dev, dtype=torch.float32))
-                        W._accumulate_batch(pp, self._pmap32, part_acc[li], sw, roi, padded, locs)
+                        W._accumulate_batch(pp, pmap32, part_acc[li], sw, roi, padded, locs)
             if n_raw is None:
                 raise RuntimeError("Patch-first local TTA generated no predictions.")
             crop = tuple(slice(0, v) for v in original)

@@ -28,6 +28,15 @@ def test_column_split_protocol_has_no_hazard(ntiles):
     M.check_split(ntiles, seeds=40)
 
 
+@pytest.mark.parametrize("nb2", [1, 2])
+@pytest.mark.parametrize("has_rc", [False, True])
+@pytest.mark.parametrize("ntiles", [1, 2, 3, 5, 8, 9, 21])
+def test_forward_two_issuer_protocol_has_no_hazard(ntiles, nb2, has_rc):
+    """mlp_fused_kernel (round 2): one MMA issuer per epilogue group, acc2 double-buffered + deferred epilogue 2 (nb2 = 2) or the
+    round-1 order (nb2 = 1), with and without the res-conv GEMM holding the A stage until GEMM2 retires."""
+    M.check_fwd(ntiles, nb2, seeds=30, has_rc=has_rc)
+
+
 def test_level0_model_flags_a_missing_g3_wait():
     """E1(k) must see G3(k-1) retired (another issuer than the one that commits h_free): without that wait the model reports
     sDh overwritten while G3 still reads it (or a wrong-tile read)."""

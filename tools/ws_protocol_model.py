@@ -1,4 +1,5 @@
-"""Discrete-event model of the mbarrier protocol of `mlp_bwd_ws_kernel` / `mlp_bwd_ws2_kernel` (csrc/mednext_bwd.cu).
+"""Discrete-event model of the mbarrier protocols of `mlp_bwd_ws_kernel` / `mlp_bwd_ws2_kernel` (csrc/mednext_bwd.cu) and
+`mlp_fused_kernel` (csrc/mednext_fwd.cu).
 
 The warp-specialised backward kernels hand tiles between four loader warps, one MMA-issuing thread and two epilogue
 groups through mbarriers only.  A wrong phase parity or barrier index does not fail loudly on the GPU — it races or hangs —
@@ -430,6 +431,123 @@ class SimSplit(Sim):
 def check_split(ntiles: int, seeds: int) -> None:
     for seed in range(seeds):
         SimSplit(ntiles, seed).run()
+
+
+class SimFwd(Sim):
+    """`mlp_fused_kernel` (csrc/mednext_fwd.cu) as of round 2: four A stages (loader warp w <-> stage w, tiles it == w mod 4), one
+    MMA-issuing thread per epilogue group, acc2 with NB2 buffers per group; with NB2 == 2 a group runs epilogue 2 of tile k-1
+    after epilogue 1 of tile k.  Resources per group g: acc1[g], sH[g], acc2[g][b]."""
+
+    def __init__(self, ntiles: int, nb2: int, seed: int, has_rc: bool = False):
+        super().__init__(ntiles, 2, 4, seed)
+        self.nb2, self.has_rc = nb2, has_rc
+        self.bars = {
+            "a_full": [Barrier(f"a_full[{i}]", 1) for i in range(4)],
+            "a_empty": [Barrier(f"a_empty[{i}]", 1) for i in range(4)],
+            "acc1_full": [Barrier(f"acc1_full[{i}]", 1) for i in range(2)],
+            "h_full": [Barrier(f"h_full[{i}]", 1) for i in range(2)],
+            "acc2_full": [Barrier(f"acc2_full[{i}]", 1) for i in range(4)],
+            "acc2_empty": [Barrier(f"acc2_empty[{i}]", 1) for i in range(4)],
+        }
+        self.sA = [Resource(f"sA[{i}]") for i in range(4)]
+        self.acc1 = [Resource(f"acc1[{i}]") for i in range(2)]
+        self.sHf = [Resource(f"sH[{i}]") for i in range(2)]
+        self.acc2 = [Resource(f"acc2[{i}]") for i in range(4)]
+
+    def loader(self, warp: int):
+        B = self.bars
+        it, uses = warp, 0
+        while it < self.ntiles:
+            if uses >= 1:
+                yield ("wait", B["a_empty"][warp], (uses - 1) & 1)
+            self.sA[warp].begin_write(it)
+            yield ("sleep", self.dur(0.3, 2.0))
+            self.sA[warp].end_write(it)
+            self.arrive(B["a_full"][warp])
+            it += 4
+            uses += 1
+
+    def issuer(self, g: int):
+        B, NB2 = self.bars, self.nb2
+        k = 0
+        while 2 * k + g < self.ntiles:
+            it = 2 * k + g
+            s = it % 4
+            yield ("wait", B["a_full"][s], (it // 4) & 1)
+            commits = [B["acc1_full"][g]] + ([] if self.has_rc else [B["a_empty"][s]])
+            self.mma(self.dur(0.05, 0.3), [self.sA[s]], [self.acc1[g]], {self.sA[s]: it, self.acc1[g]: it}, commits)
+            yield ("wait", B["h_full"][g], k & 1)
+            b = (k & 1) if NB2 == 2 else 0
+            prev = k - NB2
+            if prev >= 0:
+                yield ("wait", B["acc2_empty"][g * 2 + b], (prev // NB2) & 1)
+            reads = [self.sHf[g]] + ([self.sA[s]] if self.has_rc else [])
+            tiles = {self.sHf[g]: it, self.acc2[g * 2 + b]: it}
+            if self.has_rc:
+                tiles[self.sA[s]] = it
+            commits = [B["acc2_full"][g * 2 + b]] + ([B["a_empty"][s]] if self.has_rc else [])
+            self.mma(self.dur(0.05, 0.3), reads, [self.acc2[g * 2 + b]], tiles, commits)
+            yield ("sleep", self.dur(0.0, 0.05))
+            k += 1
+
+    def epilogue(self, eg: int):
+        B, NB2 = self.bars, self.nb2
+        pipe = NB2 == 2
+        k, pending = 0, None
+
+        def e2(tile, b):
+            self.acc2[eg * 2 + b].begin_read(tile, f"E{eg} epi2")
+            yield ("sleep", self.dur(0.2, 1.0))
+            self.acc2[eg * 2 + b].end_read(tile)
+            self.done_tiles_e2 += 1
+            self.arrive(B["acc2_empty"][eg * 2 + b])
+
+        while 2 * k + eg < self.ntiles:
+            it = 2 * k + eg
+            yield ("wait", B["acc1_full"][eg], k & 1)
+            if pipe and k >= 1:
+                yield ("wait", B["acc2_full"][eg * 2 + ((k - 1) & 1)], ((k - 1) >> 1) & 1)
+            self.acc1[eg].begin_read(it, f"E{eg} epi1")
+            self.sHf[eg].begin_write(it)
+            yield ("sleep", self.dur(0.4, 2.0))
+            self.acc1[eg].end_read(it)
+            self.sHf[eg].end_write(it)
+            self.arrive(B["h_full"][eg])
+            if pipe:
+                if pending is not None:
+                    yield from e2(*pending)
+                pending = (it, k & 1)
+            else:
+                yield ("wait", B["acc2_full"][eg * 2], k & 1)
+                yield from e2(it, 0)
+            k += 1
+        if pipe and pending is not None:
+            yield ("wait", B["acc2_full"][eg * 2 + pending[1]], ((pending[0] >> 1) >> 1) & 1)
+            yield from e2(*pending)
+
+    def run(self):
+        roles = [self.loader(w) for w in range(4)] + [self.issuer(0), self.issuer(1), self.epilogue(0), self.epilogue(1)]
+        self.roles_alive = len(roles)
+        for g in roles:
+            self.at(0.0, lambda g=g: self.run_role(g))
+        steps = 0
+        while self.events:
+            t, _, fn = heapq.heappop(self.events)
+            self.now = t
+            fn()
+            steps += 1
+            if steps > 200000 + 400 * self.ntiles:
+                raise Hazard("runaway simulation")
+        if self.roles_alive or self.waiting:
+            stuck = [(b.name, p, b.phase) for _, b, p in self.waiting]
+            raise Hazard(f"deadlock: {self.roles_alive} role(s) alive, waiting on {stuck}")
+        if self.done_tiles_e2 != self.ntiles:
+            raise Hazard(f"{self.done_tiles_e2} of {self.ntiles} tiles finished")
+
+
+def check_fwd(ntiles: int, nb2: int, seeds: int, has_rc: bool = False) -> None:
+    for seed in range(seeds):
+        SimFwd(ntiles, nb2, seed, has_rc).run()
 
 
 def check(ntiles: int, NB: int, NST: int, seeds: int) -> None:
