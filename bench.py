@@ -612,19 +612,23 @@ def run_infer(cx: Ctx, a, clocks, steps: int, warmup: int):
     # it is slower than the instrumented module-path pass, it is re-measured ONCE with the same K steps and the faster region is
     # reported — both are kept in `execution.remeasured`.
     remeasured = None
-    if ms / steps > 1.02 * ms_prof:
-        cx.barrier()
-        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        r0.record()
-        for _ in range(steps):
-            step()
-        r1.record()
-        cx.barrier()
-        ms2 = cx.max_over_ranks(r0.elapsed_time(r1))
-        remeasured = {"first_ms_per_step": ms / steps, "second_ms_per_step": ms2 / steps}
-        if ms2 < ms:
-            ms = ms2
-            value = steps * nvox / (ms / 1e3) / 1e6
+    if ms / steps > 1.02 * ms_prof or os.environ.get("PCB_BENCH_REMEASURE") == "1":      # env: exercise the branch
+        try:
+            step()                         # untimed: the native plan is rebuilt after the module-path pass toggled it off
+            cx.barrier()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record()
+            for _ in range(steps):
+                step()
+            r1.record()
+            cx.barrier()
+            ms2 = cx.max_over_ranks(r0.elapsed_time(r1))
+            remeasured = {"first_ms_per_step": ms / steps, "second_ms_per_step": ms2 / steps}
+            if ms2 < ms:
+                ms = ms2
+                value = steps * nvox / (ms / 1e3) / 1e6
+        except Exception as exc:           # never lose the first measurement to the second
+            remeasured = {"first_ms_per_step": ms / steps, "error": repr(exc)}
     # ---- end to end: pinned host volume -> H2D (this rank's slab) -> windows -> exchange -> own planes D2H
     e2e = None
     if not a.no_e2e:
