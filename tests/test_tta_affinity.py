@@ -152,3 +152,44 @@ def test_patch_first_full_channels_and_rotation_guard():
     bad = T.TTAEnsemble(NS(flip_axes="none", rotation90_axes=[[0, 1]], rotate90_k=[1]))
     with pytest.raises(ValueError, match="only supports odd 90-degree rotations"):
         bad.predict_patch_first(x, TO.ramp_network(1), roi_size=(8, 12, 12))
+
+
+def _view_shard_worker(rank, world, port, q):
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        ens = T.TTAEnsemble(NS(flip_axes="all", rotation90_axes=None), distributed_sharding=True)
+        combos = ens.combinations(5)
+        mine = ens._local_indices(len(combos))
+        err = None
+        try:
+            T.TTAEnsemble(NS(flip_axes=[[0]], rotation90_axes=None), distributed_sharding=True)._local_indices(2 if world <= 2 else 1)
+        except RuntimeError as exc:
+            err = str(exc)
+        q.put((rank, len(combos), mine, err))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_view_sharding_covers_every_view_once_gloo(world):
+    """tta.py:771-804: rank r evaluates the views r::world — together every view exactly once; a rank left without a view is an
+    error (the reference's message).  Host logic only: runs on CPU over gloo."""
+    import torch.multiprocessing as mp
+    from conftest import free_port
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = free_port()
+    procs = [ctx.Process(target=_view_shard_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=300) for _ in range(world)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+    n = res[0][1]
+    assert n == 8 and all(r[1] == n for r in res)
+    got = sorted(i for r in res for i in r[2])
+    assert got == list(range(n))
+    assert all(r[2] == list(range(r[0], n, world)) for r in res)
+    if world == 3:      # one view over three ranks: ranks 1 and 2 have nothing to do
+        assert res[0][3] is None and "empty augmentation shard" in res[1][3] and "empty augmentation shard" in res[2][3]
