@@ -12,6 +12,7 @@ from typing import Callable, Optional
 
 import torch
 
+from .data_parallel import ArenaDataParallel
 from .ddp import FlatGradArena
 from .optim import FusedAdamW
 
@@ -20,7 +21,12 @@ class ArenaTrainStep:
     """``step(x, target) -> loss`` for one MICRO-batch; the optimizer runs every ``accumulate_grad_batches`` calls.
 
     ``loss_fn(model(x), target)`` is any differentiable scalar.  ``group``: the data-parallel process group (None = default;
-    without an initialised group the step is single-process)."""
+    without an initialised group the step is single-process).
+
+    ``model`` may be an :class:`~.data_parallel.ArenaDataParallel` built on the optimizer's arena: then the exchange is the
+    wrapper's (segments all-reduced while the last backward of the window still runs, nothing inside ``no_sync()`` on the
+    other micro-batches) and this class only steps; the wrapper's ``reduce_op`` decides whether the 1/world is already in the
+    gradients (``"mean"``) or rides in the optimizer kernel (``"sum"``)."""
 
     def __init__(self, model: torch.nn.Module, loss_fn: Callable, optimizer: FusedAdamW, *, accumulate_grad_batches: int = 1,
                  group=None) -> None:
@@ -30,6 +36,9 @@ class ArenaTrainStep:
             raise TypeError("ArenaTrainStep drives a FusedAdamW (build_fused_adamw); use GraphedTrainStep for torch optimizers")
         self.model, self.loss_fn, self.opt = model, loss_fn, optimizer
         self.arena: FlatGradArena = optimizer.arena
+        self.wrapper: Optional[ArenaDataParallel] = model if isinstance(model, ArenaDataParallel) else None
+        if self.wrapper is not None and self.wrapper.arena is not self.arena:
+            raise ValueError("ArenaTrainStep: build the ArenaDataParallel on the optimizer's gradient arena (arena=optimizer.arena)")
         self.k = int(accumulate_grad_batches)
         self.group = group
         self.micro = 0
@@ -43,16 +52,30 @@ class ArenaTrainStep:
     def __call__(self, x: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
         if self.micro == 0:
             self.arena.zero()
-        loss = self.loss_fn(self.model(x), target)
-        (loss / self.k if self.k > 1 else loss).backward()
+        boundary = self.micro == self.k - 1
+        if self.wrapper is not None and not boundary:
+            with self.wrapper.no_sync():
+                loss = self.loss_fn(self.model(x), target)
+                (loss / self.k if self.k > 1 else loss).backward()
+        else:
+            loss = self.loss_fn(self.model(x), target)
+            (loss / self.k if self.k > 1 else loss).backward()
         self.micro += 1
         if self.micro == self.k:
             self.micro = 0
+            self._exchange_and_step(exchanged=self.wrapper is not None)
+        return loss.detach()
+
+    def _exchange_and_step(self, exchanged: bool) -> None:
+        if self.wrapper is not None:
+            if not exchanged:
+                self.wrapper.reduce_now()
+            self.opt.step(grads_are_summed=self.wrapper.reduce_op == "sum")
+        else:
             self.arena.gather_stray_grads()
             self.arena.allreduce_sum(self.group)
             self.opt.step(grads_are_summed=True)
-            self.optimizer_steps += 1
-        return loss.detach()
+        self.optimizer_steps += 1
 
     def flush(self) -> Optional[int]:
         """Step on a partial window (end of an epoch whose length is not a multiple of the window, as Lightning does)."""
@@ -60,8 +83,5 @@ class ArenaTrainStep:
             return None
         done = self.micro
         self.micro = 0
-        self.arena.gather_stray_grads()
-        self.arena.allreduce_sum(self.group)
-        self.opt.step(grads_are_summed=True)
-        self.optimizer_steps += 1
+        self._exchange_and_step(exchanged=False)     # the window's micro-batches all ran under no_sync()
         return done
