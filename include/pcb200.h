@@ -331,6 +331,33 @@ int pcb_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_a
                    float eps, float* step, const double* grad_sumsq, float max_norm, float grad_scale, float ema_decay,
                    int32_t* seg_active, void* stream);
 
+/* ------------------------------------------------------------------ exchange steps
+ * The two places where the path exchanges data between ranks, for hosts that do not have torch.distributed:
+ *   - the gradient mean of the data-parallel step — Lightning DDPStrategy, connectomics/training/lightning/trainer.py:231-256
+ *     (the Python package does the same exchange through torch.distributed over the flat arena, training/ddp.py);
+ *   - the overlap planes between z-neighbours of the sharded sliding-window engine (inference/sharded.py), which replaces the
+ *     full-accumulator reduce-to-root of connectomics/inference/lazy_distributed.py:78-169.
+ * NCCL is bound with dlopen at the first call (the copy already loaded in the process wins); no NCCL -> PCB_ERR_UNSUPPORTED.
+ * A pcb_comm belongs to the CUDA device that was current in pcb_comm_init; one communicator per rank process. */
+#define PCB_COMM_ID_BYTES 128
+typedef struct pcb_comm pcb_comm;
+/* rank 0 creates the id and hands the 128 bytes to every rank (MPI, a file, torch.distributed.broadcast_object_list ...) */
+int pcb_comm_unique_id(void* id_out);
+int pcb_comm_init(const void* unique_id, int rank, int world, pcb_comm** out);   /* collective over all `world` ranks */
+void pcb_comm_destroy(pcb_comm* comm);
+int pcb_comm_rank(const pcb_comm* comm);
+int pcb_comm_world(const pcb_comm* comm);
+int pcb_comm_nccl_version(void);          /* NCCL_VERSION_CODE of the bound library, -1 when none */
+/* arena[0..numel) = scale * SUM over ranks (in place, on `stream`): scale = 1/world is DDP's gradient mean; scale = 1 leaves
+ * the SUM (pcb_adamw_step folds 1/world into its grad_scale).  world == 1: only the scale is applied. */
+int pcb_grad_allreduce(pcb_comm* comm, void* arena, int64_t numel, int dtype, float scale, void* stream);
+/* One grouped ncclSend/ncclRecv exchange: message i of the send list goes to rank send_peer[i], message j of the receive
+ * list comes from recv_peer[j] (a message = value planes followed by weight planes of one face, packed by the caller;
+ * the caller adds what it received: own + neighbour, the association documented in inference/sharded.py). */
+int pcb_sw_exchange_overlap(pcb_comm* comm, int nsend, const void* const* send_bufs, const int64_t* send_numel,
+                            const int* send_peer, int nrecv, void* const* recv_bufs, const int64_t* recv_numel,
+                            const int* recv_peer, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

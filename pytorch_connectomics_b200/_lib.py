@@ -20,7 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libpcb200.so")
 SOURCES = ["pcb_api.cu", "sw_kernels.cu", "mednext_fwd.cu", "mednext_bwd.cu", "dense_conv.cu", "deep_mlp.cu", "layernorm.cu", "tta_kernels.cu",
-           "optim_kernels.cu", "net_runtime.cu"]
+           "optim_kernels.cu", "net_runtime.cu", "comm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -72,7 +72,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             list(ex.map(compile_one, todo))
     objs = [obj_of(s) for s in srcs]
     if todo or not os.path.exists(LIB_PATH) or any(os.path.getmtime(o) > os.path.getmtime(LIB_PATH) for o in objs):
-        cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH] + objs
+        cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH] + objs + ["-ldl"]
         if verbose:
             print(" ".join(cmd), file=sys.stderr)
         subprocess.run(cmd, check=True, cwd=CSRC)
@@ -97,6 +97,10 @@ def lib() -> ctypes.CDLL:
         _lib.pcb_sw_run_workspace_bytes.restype = ctypes.c_int64
         _lib.pcb_net_destroy.restype = None
         _lib.pcb_net_destroy.argtypes = [ctypes.c_void_p]
+        _lib.pcb_comm_destroy.restype = None
+        _lib.pcb_comm_destroy.argtypes = [ctypes.c_void_p]
+        _lib.pcb_comm_rank.argtypes = [ctypes.c_void_p]
+        _lib.pcb_comm_world.argtypes = [ctypes.c_void_p]
     return _lib
 
 

@@ -107,22 +107,30 @@ def _pack(value: torch.Tensor, weight: torch.Tensor, lo: int, hi: int) -> torch.
 
 
 def exchange_overlaps(value: torch.Tensor, weight: torch.Tensor, plan: SlabPlan,
-                      group: Optional[dist.ProcessGroup] = None) -> None:
+                      group: Optional[dist.ProcessGroup] = None, comm=None) -> None:
     """Send the planes of my slab that another rank owns and add what others computed for my planes (in place).
-    Works on any backend (NCCL on GPUs, gloo in the CPU tests); every rank of ``group`` must call it."""
+    Works on any backend (NCCL on GPUs, gloo in the CPU tests); every rank of ``group`` must call it.  ``comm``: a
+    :class:`pytorch_connectomics_b200.comm.NativeComm` — the same messages as ONE grouped send/recv through the C ABI
+    (``pcb_sw_exchange_overlap``) instead of ``torch.distributed``; ranks in ``plan`` are ranks of that communicator."""
     if not plan.sends and not plan.recvs:
         return
     z0 = plan.slab[0]
     cout = int(value.shape[1])
     ops, inbox = [], []
-    for peer, lo, hi in plan.sends:
-        ops.append(dist.P2POp(dist.isend, _pack(value, weight, lo - z0, hi - z0), peer, group))
-    for peer, lo, hi in plan.recvs:
-        buf = torch.empty((cout + 1, hi - lo, *value.shape[3:]), device=value.device, dtype=value.dtype)
-        inbox.append((buf, lo, hi))
-        ops.append(dist.P2POp(dist.irecv, buf, peer, group))
-    for req in dist.batch_isend_irecv(ops):
-        req.wait()
+    if comm is not None:
+        outbox = [(_pack(value, weight, lo - z0, hi - z0), peer) for peer, lo, hi in plan.sends]
+        for peer, lo, hi in plan.recvs:
+            inbox.append((torch.empty((cout + 1, hi - lo, *value.shape[3:]), device=value.device, dtype=value.dtype), lo, hi))
+        comm.exchange(outbox, [(b, peer) for (b, _, _), (peer, _, _) in zip(inbox, plan.recvs)])
+    else:
+        for peer, lo, hi in plan.sends:
+            ops.append(dist.P2POp(dist.isend, _pack(value, weight, lo - z0, hi - z0), peer, group))
+        for peer, lo, hi in plan.recvs:
+            buf = torch.empty((cout + 1, hi - lo, *value.shape[3:]), device=value.device, dtype=value.dtype)
+            inbox.append((buf, lo, hi))
+            ops.append(dist.P2POp(dist.irecv, buf, peer, group))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
     for buf, lo, hi in inbox:      # fixed (rank-ordered) accumulation order -> deterministic
         value[0, :, lo - z0:hi - z0] += buf[:cout]
         weight[0, :, lo - z0:hi - z0] += buf[cout:]
@@ -136,7 +144,7 @@ class ZSlabShardedEngine:
 
     def __init__(self, *, roi_size, sw_batch_size: int, overlap, mode: str, padding_mode: str = "constant",
                  cval: float = 0.0, device=None, group: Optional[dist.ProcessGroup] = None,
-                 rank: Optional[int] = None, world: Optional[int] = None, cuda_graph: bool = True) -> None:
+                 rank: Optional[int] = None, world: Optional[int] = None, cuda_graph: bool = True, comm=None) -> None:
         self.roi = tuple(int(v) for v in roi_size)
         if len(self.roi) != 3:
             raise ValueError(f"ZSlabShardedEngine needs a 3-D roi_size, got {roi_size}")
@@ -147,7 +155,11 @@ class ZSlabShardedEngine:
         self.cval = float(cval)
         self.device = device
         self.group = group
+        self.comm = comm                      # NativeComm: exchange through the C ABI instead of torch.distributed
         self.cuda_graph = bool(cuda_graph)
+        if comm is not None:
+            rank = comm.rank if rank is None else rank
+            world = comm.world if world is None else world
         use_dist = dist.is_available() and dist.is_initialized()
         self.rank = rank if rank is not None else (dist.get_rank(group) if use_dist else 0)
         self.world = world if world is not None else (dist.get_world_size(group) if use_dist else 1)
@@ -179,11 +191,11 @@ class ZSlabShardedEngine:
         windows -> neighbour exchange -> normalised own planes (``None`` for a rank without windows)."""
         if not plan.windows:
             if self.world > 1:
-                exchange_overlaps(torch.empty(0), torch.empty(0), plan, self.group)
+                exchange_overlaps(torch.empty(0), torch.empty(0), plan, self.group, self.comm)
             return None
         value, weight = self.accumulate_local(slab, network, plan, presliced=True)
         if self.world > 1:
-            exchange_overlaps(value, weight, plan, self.group)
+            exchange_overlaps(value, weight, plan, self.group, self.comm)
         return self.finalize(value, weight, plan)
 
     # ---- phase 3: normalise my own planes
@@ -208,11 +220,11 @@ class ZSlabShardedEngine:
         plan = plan_z_slabs(image, self.roi, self.overlap, self.world)[self.rank]
         if not plan.windows:       # more ranks than z-starts: nothing to do here, but stay in the collective
             if self.world > 1:
-                exchange_overlaps(torch.empty(0), torch.empty(0), plan, self.group)
+                exchange_overlaps(torch.empty(0), torch.empty(0), plan, self.group, self.comm)
             return None, plan.own
         value, weight = self.accumulate_local(inputs, network, plan)
         if self.world > 1:
-            exchange_overlaps(value, weight, plan, self.group)
+            exchange_overlaps(value, weight, plan, self.group, self.comm)
         return self.finalize(value, weight, plan), plan.own
 
 

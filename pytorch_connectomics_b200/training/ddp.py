@@ -94,8 +94,14 @@ class FlatGradArena:
     def _world(group) -> int:
         return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
 
-    def allreduce_sum(self, group: Optional[dist.ProcessGroup] = None) -> None:
-        """The exchange step alone (NCCL all-reduce SUM over NVLink); pair with :meth:`scale_mean`."""
+    def allreduce_sum(self, group: Optional[dist.ProcessGroup] = None, comm=None) -> None:
+        """The exchange step alone (NCCL all-reduce SUM over NVLink); pair with :meth:`scale_mean`.  ``comm``: a
+        :class:`pytorch_connectomics_b200.comm.NativeComm` — the same exchange through the C ABI (``pcb_grad_allreduce``)
+        instead of ``torch.distributed``."""
+        if comm is not None:
+            if comm.world > 1:
+                comm.allreduce_(self.buffer, 1.0)
+            return
         if self._world(group) > 1:
             dist.all_reduce(self.buffer, op=dist.ReduceOp.SUM, group=group)
 
@@ -103,8 +109,11 @@ class FlatGradArena:
         if self._world(group) > 1:
             self.buffer.mul_(1.0 / self._world(group))
 
-    def allreduce(self, group: Optional[dist.ProcessGroup] = None) -> None:
+    def allreduce(self, group: Optional[dist.ProcessGroup] = None, comm=None) -> None:
         self.gather_stray_grads()       # host-side pointer checks; copies only when a view was replaced
+        if comm is not None:            # SUM and 1/world in one library call
+            comm.allreduce_(self.buffer, 1.0 / comm.world)
+            return
         self.allreduce_sum(group)
         self.scale_mean(group)
 

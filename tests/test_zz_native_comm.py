@@ -1,0 +1,133 @@
+"""The exchange steps behind the C ABI (``csrc/comm.cu``: ``pcb_comm_init`` / ``pcb_grad_allreduce`` /
+``pcb_sw_exchange_overlap``) — what replaces Lightning DDP's gradient mean (``training/lightning/trainer.py:
+231-256``) and the accumulator reduction of ``inference/lazy_distributed.py:78-169`` for a host without torch.distributed.
+
+CPU part: the library binds NCCL at run time and fails loudly without a device.  GPU part: a world-1 communicator on one GPU
+(scale kernel, every dtype, unaligned tail) and, when the box has two GPUs, two rank processes (all-reduce of the flat
+gradient arena; the z-slab overlap exchange against the torch.distributed-free expectation computed from both ranks' seeds)."""
+
+import ctypes
+import os
+
+import pytest
+import torch
+
+from pytorch_connectomics_b200 import _lib as L
+from pytorch_connectomics_b200 import comm as C
+
+
+def test_nccl_is_bound_at_run_time_and_no_device_is_loud():
+    assert C.nccl_version() >= 22000                 # torch's bundled NCCL is already in the process: RTLD_NOLOAD finds it
+    uid = C.unique_id()
+    assert len(uid) == C.ID_BYTES and uid != bytes(C.ID_BYTES)
+    lib = L.lib()
+    h = ctypes.c_void_p()
+    assert lib.pcb_comm_init(ctypes.c_char_p(uid), 2, 2, ctypes.byref(h)) == -1 and b"rank 2" in lib.pcb_last_error()
+    assert lib.pcb_grad_allreduce(None, None, ctypes.c_int64(0), 0, ctypes.c_float(1.0), None) == -1
+    assert lib.pcb_sw_exchange_overlap(None, 0, None, None, None, 0, None, None, None, 0, None) == -1
+    assert lib.pcb_comm_rank(None) == -1 and lib.pcb_comm_world(None) == -1
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="CUDA device"):
+            C.NativeComm(uid, 0, 1)
+        assert lib.pcb_comm_init(ctypes.c_char_p(uid), 0, 1, ctypes.byref(h)) == -2 and not h.value
+    with pytest.raises(ValueError):
+        C.NativeComm(b"short", 0, 1)
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(300)
+def test_world1_communicator_scales_in_place():
+    dev = torch.device("cuda:0")
+    torch.cuda.set_device(dev)
+    comm = C.NativeComm.from_process_group()          # no process group: a world-1 communicator
+    assert (comm.rank, comm.world) == (0, 1)
+    from pytorch_connectomics_b200.training import FlatGradArena
+    for dt, n in ((torch.float32, 4099), (torch.float16, 8 * 1000 + 5), (torch.bfloat16, 77), (torch.float32, 1 << 22)):
+        x = torch.randn(n, device=dev).to(dt)
+        want = (x.float() * 0.25).to(dt)
+        before = L.launch_count()
+        comm.allreduce_(x, 0.25)
+        assert torch.equal(x, want), dt
+        assert L.launch_count() == before + 1
+        y = x.clone()
+        comm.allreduce_(y, 1.0)                       # world 1, scale 1: nothing to do, nothing launched
+        assert torch.equal(x, y) and L.launch_count() == before + 1
+    net = torch.nn.Linear(5, 3).to(dev)
+    arena = FlatGradArena(net.parameters())
+    net(torch.ones(2, 5, device=dev)).sum().backward()
+    g = arena.buffer.clone()
+    arena.allreduce(comm=comm)
+    assert torch.equal(arena.buffer, g)
+    with pytest.raises(ValueError):
+        comm.allreduce_(torch.zeros(4, 4, device=dev).t(), 1.0)
+    with pytest.raises(RuntimeError):
+        comm.allreduce_(torch.zeros(4), 1.0)
+    comm.close()
+    with pytest.raises(RuntimeError, match="closed"):
+        comm.allreduce_(torch.zeros(4, device=dev), 1.0)
+
+
+def _rank_tensors(rank, plan, cout, hw):
+    g = torch.Generator().manual_seed(40 + rank)
+    planes = plan.slab[1] - plan.slab[0]
+    return (torch.rand(1, cout, planes, *hw, generator=g), torch.rand(1, 1, planes, *hw, generator=g))
+
+
+def _two_gpu_worker(rank, uid, q):
+    try:
+        dev = torch.device("cuda", rank)
+        torch.cuda.set_device(dev)
+        comm = C.NativeComm(uid, rank, 2)
+        out = {}
+        x = (torch.arange(1000, dtype=torch.float32, device=dev) + 1) * (rank + 1)
+        comm.allreduce_(x, 0.5)
+        out["mean"] = x.cpu().numpy()
+        from pytorch_connectomics_b200.inference.sharded import exchange_overlaps, plan_z_slabs
+        plans = plan_z_slabs((40, 16, 16), (16, 16, 16), 0.5, 2)
+        v, w = _rank_tensors(rank, plans[rank], 2, (16, 16))
+        v, w = v.to(dev), w.to(dev)
+        exchange_overlaps(v, w, plans[rank], comm=comm)
+        torch.cuda.synchronize()
+        out["value"], out["weight"] = v.cpu().numpy(), w.cpu().numpy()
+        comm.close()
+        q.put((rank, out))
+    except Exception as e:
+        import traceback
+        q.put((rank, {"error": f"{e!r}\n{traceback.format_exc()}"}))
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(600)
+def test_two_ranks_allreduce_and_overlap_exchange():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    from pytorch_connectomics_b200.inference.sharded import plan_z_slabs
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    uid = C.unique_id()
+    procs = [ctx.Process(target=_two_gpu_worker, args=(r, uid, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in range(2):
+        r, o = q.get(timeout=400)
+        if "error" in o:
+            for p in procs:
+                p.kill()
+            pytest.fail(f"rank {r}: {o['error']}")
+        got[r] = o
+    for p in procs:
+        p.join(timeout=60)
+    want = (torch.arange(1000, dtype=torch.float32) + 1) * 1.5
+    assert all(torch.equal(torch.from_numpy(got[r]["mean"]), want) for r in range(2))
+    plans = plan_z_slabs((40, 16, 16), (16, 16, 16), 0.5, 2)
+    local = {r: _rank_tensors(r, plans[r], 2, (16, 16)) for r in range(2)}
+    for r in range(2):
+        v, w = (t.clone() for t in local[r])
+        z0 = plans[r].slab[0]
+        for peer, lo, hi in plans[r].recvs:
+            pz = plans[peer].slab[0]
+            v[0, :, lo - z0:hi - z0] += local[peer][0][0, :, lo - pz:hi - pz]
+            w[0, :, lo - z0:hi - z0] += local[peer][1][0, :, lo - pz:hi - pz]
+        assert torch.equal(torch.from_numpy(got[r]["value"]), v) and torch.equal(torch.from_numpy(got[r]["weight"]), w)
