@@ -232,7 +232,7 @@ def lazy_window_records(image_size, roi_size, overlap, region_start, region_stop
 def _lazy_tile_loop(read_batch: Callable[[list], torch.Tensor], predict: Callable[[torch.Tensor, list], torch.Tensor],
                     *, image_size, roi, overlap, mode, region_start, region_stop, snap_to_edge, sw_batch_size,
                     output_dtype, border_mask, rank, world_size, accumulator_reduce, dev, normalize, target_context,
-                    what: str = ""):
+                    what: str = "", shard_validator=None):
     img = tuple(int(v) for v in image_size)
     if any(img[a] < roi[a] for a in range(3)):
         raise ValueError("Lazy sliding-window inference requires the transformed test volume to be at least as large "
@@ -243,7 +243,10 @@ def _lazy_tile_loop(read_batch: Callable[[list], torch.Tensor], predict: Callabl
         raise ValueError(f"Empty lazy inference region: start={start}, stop={stop}")
     osz = tuple(stop[a] - start[a] for a in range(3))
     ov = tuple(float(v) for v in overlap) if isinstance(overlap, (list, tuple)) else (float(overlap),) * 3
-    recs = lazy_window_records(img, roi, ov, start, stop, snap_to_edge)[rank::world_size]
+    every = lazy_window_records(img, roi, ov, start, stop, snap_to_edge)
+    recs = every[rank::world_size]
+    if shard_validator is not None and world_size > 1:     # collective: every rank raises when any shard is empty
+        shard_validator(len(recs), len(every))
     if not recs:
         raise RuntimeError(f"No lazy sliding-window patches were generated{what}" +
                            (f" on rank {rank}" if world_size > 1 else "."))
@@ -339,7 +342,8 @@ def _dist_context():
 
 
 def _lazy_sliding_window_cfg(cfg, forward_fn, image_path, *, region_start, region_stop, mask_path, mask_align_to_image,
-                             device, requested_head, enable_distributed_window_sharding: bool, accumulator_reduce=None):
+                             device, requested_head, enable_distributed_window_sharding: bool, accumulator_reduce=None,
+                             shard_validator=None):
     """``lazy.py:986-1258`` with the B200 kernels for map / accumulate / normalise.  Accumulators live on ``device``
     (the reference keeps them on the CPU); the result is returned on the CPU as the reference does."""
     del mask_align_to_image          # masks are read on the image grid here (no resize transform in this path)
@@ -403,7 +407,9 @@ def _lazy_sliding_window_cfg(cfg, forward_fn, image_path, *, region_start, regio
                                   mode=mode, region_start=region_start, region_stop=region_stop, snap_to_edge=snap,
                                   sw_batch_size=sw_batch_size, output_dtype=output_dtype, border_mask=border_mask,
                                   rank=rank, world_size=world, accumulator_reduce=accumulator_reduce, dev=dev,
-                                  normalize=True, target_context=ctx, what=f" for {image_path!r}" if isinstance(image_path, (str, os.PathLike)) else "")
+                                  normalize=True, target_context=ctx,
+                                  what=f" for {image_path!r}" if isinstance(image_path, (str, os.PathLike)) else "",
+                                  shard_validator=shard_validator)
         finally:
             if mask_acc is not None:
                 mask_acc.close()
@@ -425,14 +431,19 @@ def lazy_predict_volume(cfg, forward_fn, image_path, *, mask_path=None, mask_ali
     """``lazy.py:1295-1334`` — the whole volume; with ``inference.sliding_window.distributed_sharding`` inside an
     initialised process group the windows are sharded ``[rank::world]`` and the accumulators reduced onto rank 0
     (non-root ranks get an empty tensor back)."""
-    from .lazy_distributed import make_accumulator_reducer, should_shard_windows
+    from .lazy_distributed import (distributed_reduction_device, make_accumulator_reducer, should_shard_windows,
+                                   validate_distributed_patch_shard)
     sc = getattr(getattr(cfg, "inference", None), "sliding_window", None)
     distributed = should_shard_windows(bool(getattr(sc, "distributed_sharding", False)))
     reducer = make_accumulator_reducer() if distributed else None
+    red_dev = distributed_reduction_device(torch.device(device))
+
+    def validator(local_count, total_count):             # lazy.py:1104-1110 -> lazy_distributed.py:110-129
+        validate_distributed_patch_shard(local_count=local_count, total_count=total_count, reduction_device=red_dev)
     return _lazy_sliding_window_cfg(cfg, forward_fn, image_path, region_start=None, region_stop=None,
                                     mask_path=mask_path, mask_align_to_image=mask_align_to_image, device=device,
                                     requested_head=requested_head, enable_distributed_window_sharding=distributed,
-                                    accumulator_reduce=reducer)
+                                    accumulator_reduce=reducer, shard_validator=validator if distributed else None)
 
 
 __all__ = ["ArrayVolumeAccessor", "build_accessor", "register_accessor_factory", "get_lazy_image_reference_shape",

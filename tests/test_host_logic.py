@@ -282,6 +282,29 @@ def _reduce_worker(rank, world, port, q):
         q.put((rank, "no error"))
     except RuntimeError as e:
         q.put((rank, "empty" in str(e)))
+    # the reference's own names and signatures (lazy_distributed.py:10-169)
+    from types import SimpleNamespace as NS
+    from pytorch_connectomics_b200.inference import lazy_distributed as LD
+    assert LD.distributed_context() == (True, rank, world)
+    cfg = NS(inference=NS(sliding_window=NS(distributed_sharding=True)), data=NS(dataloader=NS(use_lazy_zarr=True)))
+    assert LD.is_distributed_window_sharding_enabled(cfg)
+    cfg.data.dataloader.use_lazy_zarr = False
+    assert not LD.is_distributed_window_sharding_enabled(cfg) and not LD.is_distributed_window_sharding_enabled(NS())
+    assert LD.distributed_reduction_device(torch.device("cpu")).type in ("cpu", "cuda")
+    cpu = torch.device("cpu")
+    LD.validate_distributed_tensor_shape(torch.zeros(2, 3), name="acc", reduction_device=cpu)
+    try:
+        LD.validate_distributed_tensor_shape(torch.zeros(2, 3 + rank), name="acc", reduction_device=cpu)
+        shape_err = "no error"
+    except RuntimeError as e:
+        shape_err = str(e)
+    # a strided 1.5 MB accumulator takes the staged route in two 1 MB pieces
+    big = torch.full((2, 200_000), float(rank + 1)).t()
+    red = LD.reduce_cpu_tensor_to_rank_zero(big, op=dist.ReduceOp.SUM, reduction_device=cpu, chunk_mb=1, name="value accumulator")
+    hook = LD.make_accumulator_reduce_hook(reduction_device=cpu, chunk_mb=1)
+    pair = hook(torch.full((4,), float(rank)), torch.ones(4))
+    q.put((rank, ("ref-names", shape_err, None if red is None else (tuple(red.shape), float(red.min()), float(red.max())),
+                  None if pair is None else (pair[0].tolist(), pair[1].tolist()))))
     dist.destroy_process_group()
 
 
@@ -295,9 +318,17 @@ def test_accumulator_reduce_to_root_gloo_world2():
     procs = [ctx.Process(target=_reduce_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got = [q.get(timeout=300) for _ in range(4)]
+    got = [q.get(timeout=300) for _ in range(6)]
     for p in procs:
         p.join(timeout=60)
+    is_named = lambda v: isinstance(v, tuple) and len(v) == 4 and isinstance(v[0], str) and v[0] == "ref-names"
+    named = {r: v for r, v in got if is_named(v)}
+    got = [(r, v) for r, v in got if not is_named(v)]
+    for r in range(2):
+        _, shape_err, red, pair = named[r]
+        assert "same shape" in shape_err and "rank 0: (2, 3)" in shape_err and "rank 1: (2, 4)" in shape_err
+        assert red == (((200_000, 2), 3.0, 3.0) if r == 0 else None)
+        assert pair == (([1.0] * 4, [2.0] * 4) if r == 0 else None)
     first = {r: v for r, v in got if not isinstance(v, (bool, str))}
     assert first[1] is None
     assert torch.equal(torch.from_numpy(first[0][0]), torch.full((1, 2, 3, 3, 3), 3.0))
