@@ -13,7 +13,7 @@ from __future__ import annotations
 
 from dataclasses import dataclass
 from itertools import product
-from typing import Callable, Dict, List, Optional, Sequence, Tuple
+from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch
 
@@ -235,5 +235,158 @@ def _run_chunked_prediction_per_rank(*, cfg, forward_fn, image_path, output_path
     return output_path
 
 
+# ----------------------------------------------------------------------------- the reference's top-level driver
+def is_chunked_inference_enabled(cfg: Any) -> bool:
+    """``chunked.py:34-40``"""
+    inf = getattr(cfg, "inference", None)
+    if inf is None:
+        return False
+    return str(getattr(inf, "strategy", "whole_volume")).lower() == "chunked" or \
+        bool(getattr(getattr(inf, "chunking", None), "enabled", False))
+
+
+def _resolve_distributed_rank() -> Tuple[int, int]:
+    """``chunked.py:43-47``"""
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        return int(torch.distributed.get_rank()), int(torch.distributed.get_world_size())
+    return 0, 1
+
+
+def _resolve_external_chunk_shard(cfg: Any) -> Optional[Tuple[int, int]]:
+    """``chunked.py:196-214`` — ``inference.chunking.shard_id`` / ``num_shards`` (scheduler-driven sharding without a
+    process group)."""
+    chunking = getattr(getattr(cfg, "inference", None), "chunking", None)
+    if chunking is None:
+        return None
+    return resolve_external_chunk_shard(getattr(chunking, "shard_id", None), getattr(chunking, "num_shards", None))
+
+
+def is_external_chunk_sharding_enabled(cfg: Any) -> bool:
+    """``chunked.py:275-276``"""
+    return _resolve_external_chunk_shard(cfg) is not None
+
+
+def _resolve_inference_roi(cfg: Any):
+    """``chunked.py:217-243`` — ``inference.chunking.roi`` in INPUT voxels: 3 ints (size from the origin) or 6 (start, stop)."""
+    chunking = getattr(getattr(cfg, "inference", None), "chunking", None)
+    roi = getattr(chunking, "roi", None) if chunking is not None else None
+    if roi is None:
+        return None
+    vals = [int(v) for v in roi]
+    if len(vals) == 3:
+        start, stop = (0, 0, 0), tuple(vals)
+    elif len(vals) == 6:
+        start, stop = tuple(vals[:3]), tuple(vals[3:])
+    else:
+        raise ValueError(f"inference.chunking.roi must have 3 (size) or 6 (start/stop) ints ZYX, got {roi!r}.")
+    if any(stop[a] <= start[a] for a in range(3)):
+        raise ValueError(f"inference.chunking.roi stop must exceed start on every axis, got {roi!r}.")
+    return start, stop
+
+
+def _filter_chunks_to_roi(chunks, roi, crop_before):
+    """``chunked.py:246-272`` — drop the chunks that miss the ROI, crop the ones that straddle its faces; ``index`` / ``key``
+    stay those of the full grid so file names do not change."""
+    from dataclasses import replace
+    lo_roi, hi_roi = roi
+    kept = []
+    for ch in chunks:
+        lo = tuple(ch.start[a] + crop_before[a] for a in range(3))
+        hi = tuple(ch.stop[a] + crop_before[a] for a in range(3))
+        if any(lo[a] >= hi_roi[a] or hi[a] <= lo_roi[a] for a in range(3)):
+            continue
+        start = tuple(max(lo[a], lo_roi[a]) - crop_before[a] for a in range(3))
+        stop = tuple(min(hi[a], hi_roi[a]) - crop_before[a] for a in range(3))
+        kept.append(ch if (start, stop) == (tuple(ch.start), tuple(ch.stop)) else replace(ch, start=start, stop=stop))
+    return kept
+
+
+def run_chunked_prediction_inference(cfg, forward_fn, image_path, *, output_path, device, checkpoint_path=None, mask_path=None,
+                                     mask_align_to_image: bool = False, requested_head=None, qc_streaming_callback=None) -> Path:
+    """``chunked.py:725-957`` — chunked lazy inference streamed into ONE ``CZYX`` artifact.  Geometry from the config
+    (global prediction crop, ``inference.chunking.{chunk_size, axes, halo, roi}``); with ``shard_id/num_shards`` or inside a
+    process group the work goes to :func:`_run_chunked_prediction_per_rank`; otherwise every chunk is predicted here
+    (halo-extended region through :func:`lazy_predict_region`, core cropped back out, prediction / storage dtype
+    transforms) and written straight into its box of the output dataset."""
+    from .artifact import build_prediction_artifact_metadata, write_prediction_artifact
+    from .chunk_grid import (resolve_chunk_shape as _cfg_chunk_shape, resolve_global_prediction_crop,
+                             resolve_h5_spatial_chunks, validate_chunked_output_format)
+    from .lazy import get_lazy_image_reference_shape
+    from .output import apply_prediction_transform, apply_storage_dtype_transform
+    validate_chunked_output_format(cfg)
+    chunking = cfg.inference.chunking
+    input_shape = tuple(int(v) for v in get_lazy_image_reference_shape(cfg, image_path, mode="test")[-3:])
+    crop_pad = resolve_global_prediction_crop(cfg)
+    crop_before = tuple(int(crop_pad[a][0]) for a in range(3))
+    final_shape = tuple(input_shape[a] - crop_before[a] - int(crop_pad[a][1]) for a in range(3))
+    if any(v <= 0 for v in final_shape):
+        raise ValueError(f"Chunked inference crop {crop_pad} is too large for input shape {input_shape}.")
+    chunk_shape = _cfg_chunk_shape(cfg, final_shape)
+    halo = tuple(int(v) for v in getattr(chunking, "halo", [0, 0, 0]))
+    chunks = build_chunk_grid(final_shape, chunk_shape)
+    roi = _resolve_inference_roi(cfg)
+    if roi is not None:
+        total = len(chunks)
+        chunks = _filter_chunks_to_roi(chunks, roi, crop_before)
+        if not chunks:
+            raise ValueError(f"inference.chunking.roi={roi} excludes every chunk (final_shape={final_shape}).")
+        logger.info("Inference ROI %s (input ZYX voxels): kept %d/%d chunks.", roi, len(chunks), total)
+    output_path = Path(output_path)
+    output_path.parent.mkdir(parents=True, exist_ok=True)
+    compression = getattr(cfg.inference, "save_compression", "gzip")
+    compression = None if compression in (None, "", "none") else compression
+    h5_chunks = resolve_h5_spatial_chunks(final_shape)
+    shared = dict(cfg=cfg, forward_fn=forward_fn, image_path=image_path, output_path=output_path, checkpoint_path=checkpoint_path,
+                  mask_path=mask_path, mask_align_to_image=mask_align_to_image, requested_head=requested_head, device=device,
+                  chunks=chunks, input_shape=input_shape, final_shape=final_shape, crop_pad=crop_pad, crop_before=crop_before,
+                  chunk_shape=chunk_shape, halo=halo, compression=compression, h5_spatial_chunks=h5_chunks)
+    shard = _resolve_external_chunk_shard(cfg)
+    if shard is not None:
+        return _run_chunked_prediction_per_rank(rank=shard[0], world_size=shard[1], qc_streaming_callback=None,
+                                                stitch_output=False, use_distributed_barrier=False, **shared)
+    rank, world = _resolve_distributed_rank()
+    if world > 1:
+        return _run_chunked_prediction_per_rank(rank=rank, world_size=world, qc_streaming_callback=qc_streaming_callback,
+                                                **shared)
+    logger.info("Chunked raw prediction inference: input_shape=%s, final_shape=%s, chunk_shape=%s, halo=%s, chunks=%d",
+                input_shape, final_shape, chunk_shape, halo, len(chunks))
+
+    def core_predictions():
+        for chunk in chunks:
+            read_lo, read_hi, core = resolve_halo_region(chunk, input_shape, halo=halo, crop_before=crop_before)
+            pred = lazy_predict_region(cfg, forward_fn, image_path, region_start=read_lo, region_stop=read_hi,
+                                       mask_path=mask_path, mask_align_to_image=mask_align_to_image, device=device,
+                                       requested_head=requested_head)
+            arr = pred.detach().cpu().numpy()[0][(slice(None), *core)]
+            yield chunk, apply_storage_dtype_transform(cfg, apply_prediction_transform(cfg, arr))
+
+    stream = core_predictions()
+    first_chunk, first = next(stream)
+
+    def write(dset):
+        dset[(slice(None), *first_chunk.slices)] = first
+        for chunk, arr in stream:
+            dset[(slice(None), *chunk.slices)] = arr
+            if qc_streaming_callback is not None:
+                qc_streaming_callback.update(arr, z_offset=int(chunk.slices[0].start), z_axis=1)
+
+    if qc_streaming_callback is not None:
+        qc_streaming_callback.update(first, z_offset=int(first_chunk.slices[0].start), z_axis=1)
+    tc = getattr(cfg.inference, "prediction_transform", None)
+    transformed = tc is not None and bool(getattr(tc, "enabled", False))
+    meta = build_prediction_artifact_metadata(
+        cfg, image_path=str(image_path) if isinstance(image_path, (str, Path)) else None,
+        checkpoint_path=str(checkpoint_path) if checkpoint_path is not None else None, output_head=requested_head,
+        input_shape=input_shape, final_shape=final_shape, crop_pad=crop_pad, chunk_shape=chunk_shape, halo=halo,
+        intensity_scale=float(getattr(tc, "intensity_scale", -1.0)) if transformed else None,
+        intensity_dtype=str(getattr(tc, "intensity_dtype", first.dtype)) if transformed else str(first.dtype),
+        extra={"compression": str(compression)})
+    write_prediction_artifact(output_path, None, metadata=meta, compression=compression,
+                              shape=(int(first.shape[0]), *final_shape), dtype=first.dtype,
+                              chunks=(int(first.shape[0]), *h5_chunks), writer=write)
+    return output_path
+
+
 __all__ = ["ChunkRef", "_run_chunked_prediction_per_rank", "build_chunk_grid", "resolve_halo_region", "resolve_chunk_shape",
-           "resolve_external_chunk_shard", "chunks_for_rank", "run_chunked_prediction", "stitch_chunks"]
+           "resolve_external_chunk_shard", "chunks_for_rank", "run_chunked_prediction", "stitch_chunks",
+           "is_chunked_inference_enabled", "is_external_chunk_sharding_enabled", "run_chunked_prediction_inference"]
