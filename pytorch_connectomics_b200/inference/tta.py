@@ -823,5 +823,12 @@ class TTAEnsemble:
                                  "`inference.test_time_augmentation.patch_first_local`.")
 
 
-__all__ = ["TTAEnsemble", "TTAEnsembleAccumulator", "apply_view", "resolve_activation_codes", "resolve_activation_specs", "resolve_channel_indices", "resolve_channel_range",
+def __getattr__(name):          # ``from ...inference.tta import TTAPredictor`` as in the reference, without an import cycle
+    if name == "TTAPredictor":
+        from .tta_predictor import TTAPredictor
+        return TTAPredictor
+    raise AttributeError(name)
+
+
+__all__ = ["TTAPredictor", "TTAEnsemble", "TTAEnsembleAccumulator", "apply_view", "resolve_activation_codes", "resolve_activation_specs", "resolve_channel_indices", "resolve_channel_range",
            "resolve_tta_augmentation_combinations", "_resolve_ensemble_mode_map"]
