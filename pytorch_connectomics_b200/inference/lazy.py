@@ -346,7 +346,16 @@ def _lazy_sliding_window_cfg(cfg, forward_fn, image_path, *, region_start, regio
                              shard_validator=None):
     """``lazy.py:986-1258`` with the B200 kernels for map / accumulate / normalise.  Accumulators live on ``device``
     (the reference keeps them on the CPU); the result is returned on the CPU as the reference does."""
-    del mask_align_to_image          # masks are read on the image grid here (no resize transform in this path)
+    # lazy.py:1038: the reference runs every patch batch through TTAPredictor(cfg, None, forward_fn).predict — views,
+    # activations, channel selection and the mask per PATCH.  The predictor is only built when the config asks for any of
+    # that; a plain forward keeps the direct route (head selection + mask product).
+    tta_cfg = getattr(getattr(cfg, "inference", None), "test_time_augmentation", None)
+    inf_model = getattr(getattr(cfg, "inference", None), "model", None)
+    predictor = None
+    if (tta_cfg is not None and getattr(tta_cfg, "enabled", False)) or getattr(inf_model, "channel_activations", None) \
+            or getattr(inf_model, "select_channel", None) is not None:
+        from .tta_predictor import TTAPredictor
+        predictor = TTAPredictor(cfg, None, forward_fn)
     roi_size = W.resolve_inferer_roi_size(cfg)
     if roi_size is None:
         raise ValueError("Lazy sliding-window inference requires inference.sliding_window.window_size "
@@ -392,11 +401,16 @@ def _lazy_sliding_window_cfg(cfg, forward_fn, image_path, *, region_start, regio
                     return host.to(dev, non_blocking=True)
 
             def predict(batch, chunk):
-                pred = _select_head(forward_fn(batch), requested_head)
+                m = None
                 if mask_acc is not None:
                     masks = [mask_acc.read_patch(tuple(r[0][a] - ctx[a] for a in range(3)), read_size,
                                                  outer_pad_mode="constant", outer_pad_value=0.0) for r in chunk]
                     m = torch.from_numpy(np.stack(masks, axis=0)).to(dev, non_blocking=True)
+                if predictor is not None:
+                    return predictor.predict(batch.float(), mask=m, mask_align_to_image=mask_align_to_image,
+                                             requested_head=requested_head)
+                pred = _select_head(forward_fn(batch), requested_head)
+                if m is not None:
                     if m.shape[1] not in (1, pred.shape[1]):
                         raise ValueError(f"Mask channels {m.shape[1]} incompatible with prediction channels "
                                          f"{pred.shape[1]}")

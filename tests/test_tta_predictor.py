@@ -136,3 +136,31 @@ def test_predict_matches_ensemble_and_applies_mask():
     tta.patch_first_local = True
     patch_first = TTAPredictor(cfg, eng, _net).predict(big)
     assert torch.allclose(vol_first, direct, atol=1e-5) and torch.allclose(patch_first, direct, atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_lazy_seam_runs_patches_through_the_predictor(tmp_path):
+    """lazy.py:1038,1187-1194: with TTA / activations / channel selection configured, the lazy engine sends every patch batch
+    through ``TTAPredictor(cfg, None, forward_fn).predict`` (views + activations + selection + mask per PATCH) before
+    blending.  With a pointwise forward and flip views every view of a patch gives the same values, so the result is
+    activation(net(volume))[selected] * mask up to blending round-off."""
+    from pytorch_connectomics_b200.inference import lazy as Z
+    dev = "cuda:0"
+    vol = np.random.RandomState(5).rand(24, 16, 40).astype(np.float32)
+    mask = (np.random.RandomState(6).rand(24, 16, 40) > 0.3).astype(np.float32)
+    np.save(tmp_path / "v.npy", vol)
+    np.save(tmp_path / "m.npy", mask)
+    sw = NS(window_size=[16, 16, 16], overlap=0.5, blending="constant", sw_batch_size=2, padding_mode="constant", cval=0.0,
+            snap_to_edge=False, target_context=[], border_mask=None, distributed_sharding=False)
+    acts = [dict(channels="0:2", activation="sigmoid"), dict(channels="2:3", activation="tanh")]
+    cfg = NS(model=NS(output_size=[16, 16, 16], arch=NS(type="mednext"), primary_head=None),
+             data=NS(dataloader=NS(batch_size=1, patch_size=[16, 16, 16]), data_transform=NS()),
+             inference=NS(sliding_window=sw, model=NS(output_dtype=None, channel_activations=acts, select_channel=[2, 0], head=None),
+                          test_time_augmentation=NS(enabled=True, flip_axes="all", rotation90_axes=None, rotate90_k=None,
+                                                    ensemble_mode="mean", apply_mask=True)))
+    got = Z.lazy_predict_volume(cfg, _net, str(tmp_path / "v.npy"), mask_path=str(tmp_path / "m.npy"), device=dev)
+    x = torch.from_numpy(vol)[None, None]
+    raw = _net(x)
+    m = torch.from_numpy(mask)[None, None]
+    want = torch.cat([torch.tanh(raw[:, 2:3]) * m + (1 - m) * -1.0, torch.sigmoid(raw[:, 0:1]) * m], 1)
+    assert got.shape == want.shape and torch.allclose(got, want, atol=2e-5)
