@@ -51,9 +51,15 @@ class _EngineNetwork:
         p = self._p
         if p._requested_output_head_override is not None:
             return None
-        # forward_fn is the module itself, a bound ``forward`` of it, or of a LightningModule that holds it as ``.model``
-        owners = [p.forward_fn, getattr(p.forward_fn, "__self__", None)]
-        owners += [getattr(o, "model", None) for o in list(owners)]
+        # forward_fn is the module itself, its bound ``forward``, or the bound ``forward`` of the reference's LightningModule
+        # (``training/lightning/model.py:236-242``: a pure ``return self.model(x)``) — nothing else is looked through
+        fn = p.forward_fn
+        owners = [fn]
+        bound = getattr(fn, "__self__", None)
+        if bound is not None and getattr(fn, "__name__", "") == "forward":
+            owners.append(bound)
+            if type(bound).__name__ == "ConnectomicsModule":
+                owners.append(getattr(bound, "model", None))
         getter = next((g for g in (getattr(o, "native_plan", None) for o in owners if o is not None) if callable(g)), None)
         if getter is None:
             return None

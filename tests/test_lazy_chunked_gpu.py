@@ -201,42 +201,3 @@ def test_per_rank_chunked_runner_writes_artifacts(tmp_path):
     assert meta["layout"] == "CZYX" and json.loads(meta["halo"]) == [2, 2, 2]
     # re-run: every chunk exists -> the forward is never called
     C._run_chunked_prediction_per_rank(rank=0, world_size=1, **{**common, "forward_fn": lambda x: 1 / 0})
-
-
-def test_run_chunked_prediction_inference_streams_one_volume(tmp_path):
-    """`run_chunked_prediction_inference(cfg, forward_fn, image_path, output_path=..., device=...)` (chunked.py:725-957): geometry
-    from the config (crop_pad, chunk_size, halo, roi), every chunk predicted on its halo box and streamed into ONE CZYX artifact
-    == the (cropped) full lazy prediction; `shard_id/num_shards` routes to the per-rank runner without stitching."""
-    from pytorch_connectomics_b200.inference.artifact import read_prediction_artifact
-    volume = np.random.RandomState(1).rand(12, 10, 14).astype(np.float32)
-    path = tmp_path / "vol.npy"
-    np.save(path, volume)
-    cfg = _make_cfg((4, 4, 4), 0.5, "constant")
-    cfg.inference.chunking = NS(chunk_size=[6, 16, 7], axes="all", halo=[2, 2, 2], output_mode="raw_prediction")
-    cfg.inference.save_backend, cfg.inference.save_compression = "h5", None
-    cfg.inference.model.crop_pad = [1, 0, 2]
-    assert C.is_chunked_inference_enabled(NS(inference=NS(strategy="chunked")))
-    out = C.run_chunked_prediction_inference(cfg, _patch_mean_forward, str(path), output_path=tmp_path / "a" / "pred.h5", device=DEV)
-    got, meta = read_prediction_artifact(out, return_metadata=True)
-    full = Z.lazy_predict_volume(cfg, _patch_mean_forward, str(path), device=DEV)[0].numpy()
-    want = full[:, 1:11, :, 2:12]
-    assert got.shape == (1, 10, 10, 10) and np.allclose(np.asarray(got), want, atol=1e-5)
-    assert json.loads(meta["crop_pad"]) == [[1, 1], [0, 0], [2, 2]] and json.loads(meta["chunk_shape"]) == [6, 10, 7]
-    # prediction transform + roi: only the chunks that touch the ROI are written (the rest of the dataset stays zero)
-    cfg.inference.prediction_transform = NS(enabled=True, intensity_scale=100.0, intensity_dtype="uint8")
-    cfg.inference.chunking.roi = [0, 0, 0, 6, 10, 14]
-    out2 = C.run_chunked_prediction_inference(cfg, _patch_mean_forward, str(path), output_path=tmp_path / "b.h5", device=DEV)
-    got2 = np.asarray(read_prediction_artifact(out2))
-    assert got2.dtype == np.uint8
-    ref = np.clip(want * 100.0, 0, 255).astype(np.uint8)
-    assert np.abs(got2[:, :5].astype(np.int32) - ref[:, :5].astype(np.int32)).max() <= 1     # z < 5 in output space: inside the ROI
-    assert got2[:, 6:].max() == 0
-    # external sharding: per-chunk artifacts of shard 1 only, no stitched volume
-    cfg.inference.prediction_transform = None
-    cfg.inference.chunking.roi = None
-    cfg.inference.chunking.shard_id, cfg.inference.chunking.num_shards = 1, 2
-    assert C.is_external_chunk_sharding_enabled(cfg)
-    res = C.run_chunked_prediction_inference(cfg, _patch_mean_forward, str(path), output_path=tmp_path / "c.h5", device=DEV)
-    assert res == tmp_path / "c.h5.chunks" and not (tmp_path / "c.h5").exists() and not (tmp_path / "c.h5.npy").exists()
-    keys = {f.name.split(".")[0] for f in res.iterdir()}
-    assert keys == {"chunk_z0_y0_x1", "chunk_z1_y0_x1"}          # chunks 1 and 3 of the 2 x 1 x 2 grid

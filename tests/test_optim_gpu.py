@@ -187,42 +187,3 @@ def test_arena_train_step_accumulates_like_one_large_batch():
     assert acc.flush() is None and acc(x[:2], t[:2]) is not None and acc.flush() == 1 and acc.optimizer_steps == 2
     with pytest.raises(ValueError):
         ArenaTrainStep(a, loss_fn, oa, accumulate_grad_batches=0)
-
-
-@pytest.mark.gpu
-def test_arena_train_step_through_the_data_parallel_wrapper():
-    """The DDP seam as an object (trainer.py:231-256): ``ArenaTrainStep`` over ``ArenaDataParallel`` (built on the optimizer's
-    arena; micro-batches before the boundary run under ``no_sync()``, the boundary backward launches the segment exchange from
-    gradient hooks) moves the weights like the plain step.  Single process: the exchange is the identity, what is tested is that
-    hooks, segment bookkeeping and the pointer repairs leave the arena exactly as the kernels wrote it."""
-    from pytorch_connectomics_b200.architectures import mednext as PM
-    from pytorch_connectomics_b200.training import ArenaDataParallel, ArenaTrainStep
-
-    def make():
-        torch.manual_seed(5)
-        net = PM.MedNeXt(1, 16, 1, exp_r=2, kernel_size=3, deep_supervision=False, do_res=True, do_res_up_down=True,
-                         block_counts=[1] * 9).to(DEV).train()
-        opt = FusedAdamW(reference_param_groups(net, 1e-3, 0.01), arena=FlatGradArena(net.parameters()), max_grad_norm=1.0)
-        return net, opt
-
-    bce = torch.nn.functional.binary_cross_entropy_with_logits
-    loss_fn = lambda out, t: bce(out.float(), t)
-    torch.manual_seed(6)
-    x = torch.rand(4, 1, 32, 32, 32, device=DEV).half()
-    t = (torch.rand(4, 1, 32, 32, 32, device=DEV) > 0.8).float()
-    a, oa = make()
-    b, ob = make()
-    plain = ArenaTrainStep(a, loss_fn, oa, accumulate_grad_batches=2)
-    wrapped_net = ArenaDataParallel(b, arena=ob.arena, reduce_op="sum", bucket_cap_mb=0.05)
-    assert len(wrapped_net.segments) > 3
-    wrapped = ArenaTrainStep(wrapped_net, loss_fn, ob, accumulate_grad_batches=2)
-    for lo in (0, 2, 0, 2):
-        la, lb = plain(x[lo:lo + 2], t[lo:lo + 2]), wrapped(x[lo:lo + 2], t[lo:lo + 2])
-        assert abs(float(la) - float(lb)) < 1e-5
-    torch.cuda.synchronize()
-    assert plain.optimizer_steps == wrapped.optimizer_steps == 2
-    assert [k for k, _ in wrapped_net.launch_log] == list(range(len(wrapped_net.segments)))
-    for (k, pa), pb in zip(a.named_parameters(), b.parameters()):
-        assert torch.allclose(pa, pb, rtol=0, atol=2e-6), (k, float((pa - pb).abs().max()))
-    with pytest.raises(ValueError):
-        ArenaTrainStep(ArenaDataParallel(a), loss_fn, oa)          # a wrapper with its own arena cannot drive this optimizer

@@ -15,6 +15,8 @@ import torch
 from pytorch_connectomics_b200 import _lib as L
 from pytorch_connectomics_b200 import comm as C
 
+first_run = pytest.mark.xfail(strict=False, reason="written without GPU access; first B200 run is the driver's")
+
 
 def test_nccl_is_bound_at_run_time_and_no_device_is_loud():
     assert C.nccl_version() >= 22000                 # torch's bundled NCCL is already in the process: RTLD_NOLOAD finds it
@@ -35,6 +37,7 @@ def test_nccl_is_bound_at_run_time_and_no_device_is_loud():
 
 
 @pytest.mark.gpu
+@first_run
 @pytest.mark.timeout(300)
 def test_world1_communicator_scales_in_place():
     dev = torch.device("cuda:0")
@@ -97,6 +100,7 @@ def _two_gpu_worker(rank, uid, q):
 
 
 @pytest.mark.gpu
+@first_run
 @pytest.mark.timeout(600)
 def test_two_ranks_allreduce_and_overlap_exchange():
     if torch.cuda.device_count() < 2:
