@@ -256,8 +256,6 @@ class BlockFn(torch.autograd.Function):
 class StemFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b):
-        if ctx.needs_input_grad[0]:
-            raise NotImplementedError("pcb200: gradient w.r.t. the input volume is not implemented")
         out = ops.stem_forward(x, w, b)
         ctx.save_for_backward(x.contiguous(), w)
         return out
@@ -273,7 +271,17 @@ class StemFn(torch.autograd.Function):
         L.check(L.lib().pcb_stem_bwd(L.ptr(g), L.ptr(x), L.dtype_code(x.dtype), L.ptr(dw), L.ptr(db), ctypes.c_int64(n),
                                      ctypes.c_int64(cin), ctypes.c_int64(c), ctypes.c_int64(nvox), L.stream_ptr(g.device)),
                 "pcb_stem_bwd")
-        return None, dw.float().reshape(w.shape), db.float()
+        dx = None
+        if ctx.needs_input_grad[0]:
+            # dX[n,ci,v] = sum_c g[n,v,c] * W[c,ci]: the OutBlock kernel (NDHWC bf16 x [C, ncls] -> NCDHW) with the stem weight
+            # read as a [C, Cin] "head" and a zero bias — saliency / adversarial callers get the input gradient the
+            # reference's autograd path gives them
+            dx = torch.empty_like(x)
+            zero_b = torch.zeros(cin, device=g.device, dtype=torch.float32)
+            L.check(L.lib().pcb_head_fwd(L.ptr(g), L.ptr(ops.packed(w, "head")), L.ptr(zero_b), L.ptr(dx),
+                                         ctypes.c_int(L.dtype_code(dx.dtype)), ctypes.c_int64(n), ctypes.c_int64(c),
+                                         ctypes.c_int64(cin), ctypes.c_int64(nvox), L.stream_ptr(g.device)), "pcb_head_fwd")
+        return dx, dw.float().reshape(w.shape), db.float()
 
 
 class HeadFn(torch.autograd.Function):

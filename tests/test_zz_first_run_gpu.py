@@ -188,3 +188,32 @@ def test_lazy_seam_runs_patches_through_the_predictor(tmp_path):
     m = torch.from_numpy(mask)[None, None]
     want = torch.cat([torch.tanh(raw[:, 2:3]) * m + (1 - m) * -1.0, torch.sigmoid(raw[:, 0:1]) * m], 1)
     assert got.shape == want.shape and torch.allclose(got, want, atol=2e-5)
+
+
+# ----------------------------------------------------------------------------- gradient w.r.t. the input volume
+def test_input_volume_gradient_matches_oracle():
+    """``x.requires_grad_()`` (saliency / adversarial use of the reference's autograd path): the stem's input gradient
+    dX = g . W through the OutBlock kernel, against the fp32 CPU oracle (bf16 compute: the bound is the one the other
+    gradients of the tiny net meet against the fp32 oracle)."""
+    from oracle.mednext_oracle import MedNeXt as OracleNet
+    from pytorch_connectomics_b200.architectures.mednext import MedNeXt
+    torch.manual_seed(11)
+    kw = dict(in_channels=2, n_channels=16, n_classes=2, exp_r=2, kernel_size=3, deep_supervision=False, do_res=True,
+              do_res_up_down=True, block_counts=[1] * 9)
+    ref = OracleNet(**kw).train()
+    net = MedNeXt(**kw).train()
+    net.load_state_dict(ref.state_dict(), strict=True)
+    net.to(DEV)
+    x = torch.rand(2, 2, 32, 32, 32)
+    g = torch.randn(2, 2, 32, 32, 32)
+    xr = x.clone().requires_grad_(True)
+    (ref(xr) * g).sum().backward()
+    for dt in (torch.float32, torch.float16):
+        xe = x.to(DEV, dt).requires_grad_(True)
+        (net(xe).float() * g.to(DEV)).sum().backward()
+        assert xe.grad is not None and xe.grad.dtype == dt and xe.grad.shape == x.shape
+        err = float((xe.grad.float().cpu() - xr.grad).norm() / xr.grad.norm())
+        print(f"input-gradient rel-L2 vs fp32 oracle ({dt}): {err:.3e}")
+        assert err < 5e-2, err
+    # parameters still get their gradients in the same pass
+    assert net.stem.weight.grad is not None and float(net.stem.weight.grad.abs().sum()) > 0
