@@ -182,7 +182,7 @@ class ArenaDataParallel(torch.nn.Module):
         self.arena = arena
         per_mb = (1 << 20) // 4
         plan = plan_segments([p.numel() for p in arena.params], arena.offsets, arena.total, int(bucket_cap_mb * per_mb),
-                             None if first_bucket_mb is None else int(first_bucket_mb * per_mb))
+                             None if first_bucket_mb is None else int(min(first_bucket_mb, bucket_cap_mb) * per_mb))
         self.segments: List[GradSegment] = [GradSegment(arena, k, a, b, lo, hi, k == len(plan) - 1)
                                             for k, (a, b, lo, hi) in enumerate(plan)]
         self._seg_of = [0] * len(arena.params)

@@ -249,3 +249,39 @@ def test_static_graph_caches_the_unused_set_and_detects_a_changed_graph():
     adp.zero_grad()
     with pytest.raises(RuntimeError, match="after its segment was exchanged"):
         _forward(adp, _data(0, 1), False).square().sum().backward()   # ... the second one uses it: loud, not silently stale
+
+
+def test_lightning_strategy_factory_against_a_stub_ddp_strategy(monkeypatch):
+    """Lightning is not in this image: the factory is exercised against a stub of the three ``DDPStrategy`` members it
+    overrides (``_setup_model``, ``_register_ddp_hooks``, ``block_backward_sync``) so that at least the class body, the
+    keyword routing and the no_sync plumbing run.  Without any Lightning the factory raises ImportError."""
+    import sys
+    import types
+    from pytorch_connectomics_b200.training import ArenaDataParallel, allreduce_sum_hook, make_arena_ddp_strategy
+    for name in ("lightning", "lightning.pytorch", "lightning.pytorch.strategies", "pytorch_lightning", "pytorch_lightning.strategies"):
+        monkeypatch.setitem(sys.modules, name, None)
+    with pytest.raises(ImportError):
+        make_arena_ddp_strategy()
+
+    class DDPStrategy:
+        def __init__(self, **kw):
+            self._ddp_kwargs = {"bucket_cap_mb": 0.001, "find_unused_parameters": True, "unknown": 1}
+            self.init_kw = kw
+            self.model = None
+
+    pl = types.ModuleType("pytorch_lightning")
+    st = types.ModuleType("pytorch_lightning.strategies")
+    st.DDPStrategy = DDPStrategy
+    pl.strategies = st
+    monkeypatch.setitem(sys.modules, "pytorch_lightning", pl)
+    monkeypatch.setitem(sys.modules, "pytorch_lightning.strategies", st)
+    strat = make_arena_ddp_strategy({"timeout": 5}, reduce_op="sum", init_sync=False)
+    assert isinstance(strat, DDPStrategy) and strat.init_kw == {"timeout": 5}
+    strat.model = strat._setup_model(_net())
+    assert isinstance(strat.model, ArenaDataParallel) and strat.model.reduce_op == "sum" and len(strat.model.segments) > 1
+    strat._ddp_comm_hook, strat._ddp_comm_state = allreduce_sum_hook, None
+    strat._register_ddp_hooks()
+    assert strat.model._hook is allreduce_sum_hook
+    with strat.block_backward_sync():
+        assert strat.model.require_backward_grad_sync is False
+    assert strat.model.require_backward_grad_sync is True
