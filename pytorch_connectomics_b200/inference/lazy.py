@@ -397,8 +397,8 @@ def _lazy_sliding_window_cfg(cfg, forward_fn, image_path, *, region_start, regio
                 def read_batch(starts):                          # disk / host -> pinned -> H2D, one batch at a time
                     patches = [image_acc.read_patch(tuple(s[a] - ctx[a] for a in range(3)), read_size,
                                                     outer_pad_mode=pad_mode, outer_pad_value=cval) for s in starts]
-                    host = torch.from_numpy(np.stack(patches, axis=0)).pin_memory()
-                    return host.to(dev, non_blocking=True)
+                    host = torch.from_numpy(np.stack(patches, axis=0))
+                    return host.pin_memory().to(dev, non_blocking=True) if dev.type == "cuda" else host
 
             def predict(batch, chunk):
                 m = None

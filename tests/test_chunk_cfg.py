@@ -175,3 +175,51 @@ def test_top_level_chunked_driver_geometry_with_a_stub_region_predictor(tmp_path
     cfg.inference.save_backend = "zarr"
     with pytest.raises(ValueError, match="single streamed HDF5"):
         C.run_chunked_prediction_inference(cfg, None, str(path), output_path=tmp_path / "none.h5", device="cpu")
+
+
+def test_chunked_driver_with_the_real_lazy_engine_on_cpu_doubles(tmp_path, monkeypatch):
+    """`run_chunked_prediction_inference` over the REAL `lazy_predict_region` / `_lazy_tile_loop` host logic, with only the
+    kernel-calling window helpers replaced by oracle stand-ins (`tests/cpu_doubles.py`): a context-dependent forward (patch
+    mean) makes the result sensitive to where windows are cut, so chunk == slice(full lazy prediction) is the reference's own
+    property (tests/unit/test_chunked_inference.py:177-218).  GPU run of the same call:
+    `test_zz_first_run_gpu.py::test_run_chunked_prediction_inference_streams_one_volume`."""
+    import numpy as np
+    import torch
+    from types import SimpleNamespace as NS
+    import cpu_doubles
+    from pytorch_connectomics_b200.inference import chunked as C
+    from pytorch_connectomics_b200.inference import lazy as Z
+    from pytorch_connectomics_b200.inference.artifact import read_prediction_artifact
+    cpu_doubles.install(monkeypatch)
+
+    def patch_mean(x):
+        return x.mean(dim=(2, 3, 4), keepdim=True).expand_as(x).contiguous()
+
+    volume = np.random.RandomState(1).rand(12, 10, 14).astype(np.float32)
+    path = tmp_path / "vol.npy"
+    np.save(path, volume)
+    sw = NS(window_size=[4, 4, 4], overlap=0.5, blending="constant", sw_batch_size=2, padding_mode="constant", cval=0.0,
+            snap_to_edge=False, target_context=[], border_mask=None, distributed_sharding=False)
+    cfg = NS(model=NS(output_size=[4, 4, 4], arch=NS(type="mednext")),
+             data=NS(dataloader=NS(batch_size=1, patch_size=[4, 4, 4]), data_transform=NS()),
+             inference=NS(sliding_window=sw, model=NS(output_dtype=None, crop_pad=[1, 0, 2]), save_backend="h5", save_compression=None,
+                          chunking=NS(chunk_size=[6, 16, 7], axes="all", halo=[2, 2, 2], output_mode="raw_prediction")))
+    full = Z.lazy_predict_volume(cfg, patch_mean, str(path), device="cpu")[0].numpy()
+    want = full[:, 1:11, :, 2:12]
+    out = C.run_chunked_prediction_inference(cfg, patch_mean, str(path), output_path=tmp_path / "a" / "pred.h5", device="cpu")
+    got, meta = read_prediction_artifact(out, return_metadata=True)
+    assert got.shape == (1, 10, 10, 10) and np.allclose(np.asarray(got), want, atol=1e-6)
+    assert json.loads(meta["crop_pad"]) == [[1, 1], [0, 0], [2, 2]] and json.loads(meta["chunk_shape"]) == [6, 10, 7]
+    # external shards: two scheduler jobs write disjoint per-chunk artifacts; a third call (world 1, nothing left to predict)
+    # stitches them — the stitched volume is the same prediction
+    cfg.inference.chunking.shard_id, cfg.inference.chunking.num_shards = 1, 2
+    res = C.run_chunked_prediction_inference(cfg, patch_mean, str(path), output_path=tmp_path / "c.h5", device="cpu")
+    assert res == tmp_path / "c.h5.chunks" and {f.name.split(".")[0] for f in res.iterdir()} == {"chunk_z0_y0_x1", "chunk_z1_y0_x1"}
+    cfg.inference.chunking.shard_id = 0
+    C.run_chunked_prediction_inference(cfg, patch_mean, str(path), output_path=tmp_path / "c.h5", device="cpu")
+    chunks = C.build_chunk_grid((10, 10, 10), (6, 10, 7))
+    stitched = C._run_chunked_prediction_per_rank(
+        cfg=cfg, forward_fn=lambda x: 1 / 0, image_path=str(path), output_path=tmp_path / "c.h5", device="cpu", chunks=chunks,
+        input_shape=(12, 10, 14), final_shape=(10, 10, 10), crop_pad=((1, 1), (0, 0), (2, 2)), crop_before=(1, 0, 2),
+        chunk_shape=(6, 10, 7), halo=(2, 2, 2), compression=None, h5_spatial_chunks=(4, 4, 4), use_distributed_barrier=False)
+    assert np.allclose(np.asarray(read_prediction_artifact(stitched)), want, atol=1e-6)

@@ -128,3 +128,92 @@ def test_native_plan_passthrough_only_for_known_pure_forwards():
     p = TTAPredictor(_cfg(), object(), Net())
     p._requested_output_head_override = "aff"
     assert p._engine_network.native_plan() is None
+
+
+# ----------------------------------------------------------------------------- predict() glue on the CPU, oracle ensemble
+from cpu_doubles import oracle_ensemble_predict as _oracle_ensemble_predict  # noqa: E402
+
+
+def test_predict_glue_against_the_oracle_chain(monkeypatch):
+    """``TTAPredictor.predict`` end to end on the CPU with the fold kernels replaced by the oracle chain: what is checked is
+    everything the predictor adds — config nodes -> ensemble arguments, input normalisation, routing through a sliding
+    inferer object, named heads, the disabled-TTA path, mask + tanh fill, output dtype."""
+    from oracle import tta_oracle as O
+    from pytorch_connectomics_b200.inference import tta as T
+    monkeypatch.setattr(T.TTAEnsemble, "predict", _oracle_ensemble_predict)
+    net = O.ramp_network(3)
+    torch.manual_seed(2)
+    x = torch.rand(1, 1, 6, 8, 8)
+    acts = [dict(channels="0:2", activation="sigmoid"), dict(channels="2:3", activation="tanh")]
+    tta = NS(enabled=True, flip_axes="all", rotation90_axes=[[1, 2]], rotate90_k=None,
+             ensemble_mode=[["0:1", "min"], ["1:2", "mean"]], apply_mask=True, patch_first_local=False, distributed_sharding=False)
+    cfg = _cfg(tta, acts=acts, select=[2, 0])
+    combos = T.resolve_tta_augmentation_combinations(tta, spatial_dims=3)
+    assert len(combos) > 8
+    want = O.tta_predict(x, net, combos, ["min", "mean"], [1, 1, 3], [1.0, 1.0, 1.0], [2, 0], torch.float32)
+    calls = []
+
+    def engine(inputs, network):                     # a sliding inferer as the predictor sees it: keyword call, callable network
+        calls.append(tuple(inputs.shape))
+        assert network.native_plan() is None         # a plain function has no native plan: generic loop
+        return network(inputs)
+
+    for inferer in (None, engine):
+        p = TTAPredictor(cfg, inferer, net)
+        got = p.predict(x[0, 0])                     # (D, H, W) in
+        assert got.shape == (1, 2, 6, 8, 8) and torch.equal(got, want)
+        assert p.channel_activation_types == ["tanh", "sigmoid"]
+    assert len(calls) == len(combos) + 1             # one engine call per view (+ the stand-in's channel probe)
+    mask = (torch.rand(6, 8, 8) > 0.4).float()
+    m = mask[None, None]
+    masked = TTAPredictor(cfg, None, net).predict(x, mask=[[mask.numpy()]])          # collated container around the mask
+    assert torch.equal(masked[:, :1], want[:, :1] * m + (1 - m) * -1.0) and torch.equal(masked[:, 1:], want[:, 1:] * m)
+    tta.apply_mask = False
+    assert torch.equal(TTAPredictor(cfg, None, net).predict(x, mask=mask), want)
+    # TTA disabled: one pass = apply_preprocessing; fp16 output dtype from inference.model.output_dtype
+    off = _cfg(NS(enabled=False), acts=acts, odt="float16")
+    plain = TTAPredictor(off, None, net).predict(x)
+    ref = O.preprocess_specs(net(x), [([0, 1], "sigmoid"), ([2], "tanh")], None, torch.float16)
+    assert plain.dtype == torch.float16 and torch.equal(plain, ref)
+    # named heads: {"output": {head: tensor}}; requested_head overrides model.primary_head for one call only
+    heads = lambda t: {"output": {"aff": net(t), "sdt": net(t)[:, :1] * 2.0}}
+    ph = TTAPredictor(_cfg(NS(enabled=False), primary_head="aff"), None, heads)
+    assert torch.equal(ph.predict(x), net(x)) and torch.equal(ph.predict(x, requested_head="sdt"), net(x)[:, :1] * 2.0)
+    assert ph._requested_output_head_override is None
+    with pytest.raises(ValueError, match="requested_head"):
+        ph.predict(x, requested_head="nope")
+
+
+def test_lazy_seam_through_the_predictor_on_cpu_doubles(tmp_path, monkeypatch):
+    """The cfg-driven lazy engine (lazy.py:986-1258) with TTA, activations, channel selection and a mask file configured:
+    every patch batch goes through ``TTAPredictor(cfg, None, forward_fn).predict`` (lazy.py:1038,1187-1194).  Kernel-calling
+    helpers are replaced by the oracle stand-ins (``tests/cpu_doubles.py``), so this is the CPU run of the host logic whose
+    GPU run is ``test_zz_first_run_gpu.py::test_lazy_seam_runs_patches_through_the_predictor``.  Pointwise forward + flip
+    views: every view of a patch gives the same values, so the blended result is activation(net(volume))[selected] * mask."""
+    import cpu_doubles
+    from pytorch_connectomics_b200.inference import lazy as Z
+    cpu_doubles.install(monkeypatch)
+    vol = np.random.RandomState(5).rand(12, 8, 20).astype(np.float32)
+    mask = (np.random.RandomState(6).rand(12, 8, 20) > 0.3).astype(np.float32)
+    np.save(tmp_path / "v.npy", vol)
+    np.save(tmp_path / "m.npy", mask)
+    sw = NS(window_size=[8, 8, 8], overlap=0.5, blending="constant", sw_batch_size=2, padding_mode="constant", cval=0.0,
+            snap_to_edge=False, target_context=[], border_mask=None, distributed_sharding=False)
+    acts = [dict(channels="0:2", activation="sigmoid"), dict(channels="2:3", activation="tanh")]
+    cfg = NS(model=NS(output_size=[8, 8, 8], arch=NS(type="mednext"), primary_head=None),
+             data=NS(dataloader=NS(batch_size=1, patch_size=[8, 8, 8]), data_transform=NS()),
+             inference=NS(sliding_window=sw, model=NS(output_dtype=None, channel_activations=acts, select_channel=[2, 0], head=None),
+                          test_time_augmentation=NS(enabled=True, flip_axes="all", rotation90_axes=None, rotate90_k=None,
+                                                    ensemble_mode="mean", apply_mask=True)))
+    net = lambda t: torch.cat([t * 0.5 + 0.25, 1.0 - t, t * t], 1)
+    got = Z.lazy_predict_volume(cfg, net, str(tmp_path / "v.npy"), mask_path=str(tmp_path / "m.npy"), device="cpu")
+    x = torch.from_numpy(vol)[None, None]
+    raw = net(x)
+    m = torch.from_numpy(mask)[None, None]
+    want = torch.cat([torch.tanh(raw[:, 2:3]) * m + (1 - m) * -1.0, torch.sigmoid(raw[:, 0:1]) * m], 1)
+    assert got.shape == want.shape and torch.allclose(got, want, atol=2e-6)
+    # without TTA / activations / selection the predictor is not built and the direct route gives net(volume) * mask
+    cfg.inference.test_time_augmentation.enabled = False
+    cfg.inference.model.channel_activations, cfg.inference.model.select_channel = None, None
+    plain = Z.lazy_predict_volume(cfg, net, str(tmp_path / "v.npy"), mask_path=str(tmp_path / "m.npy"), device="cpu")
+    assert torch.allclose(plain, raw * m, atol=2e-6)
