@@ -238,9 +238,22 @@ class ArenaDataParallel(torch.nn.Module):
                 self._static_unused = unused
         for i in unused:
             if not self._ready[i]:
+                self._attach_view(i)          # BEFORE the segment can be launched: a detached .grad means a stale slice
                 self._ready[i] = True
                 self._n_ready += 1
                 self._missing[self._seg_of[i]] -= 1
+
+    def _attach_view(self, i: int) -> None:
+        """Make ``params[i].grad`` the arena view again.  ``zero_grad(set_to_none=True)`` (Lightning's default) leaves
+        ``None`` — and does NOT clear the arena, so the slice still holds the previous step's gradient: zero it; a foreign
+        tensor (autograd allocated one because ``.grad`` was ``None``) is copied in."""
+        p, view = self.arena.params[i], self.arena.view_of(i)
+        if p.grad is None:
+            view.zero_()
+            p.grad = view
+        elif p.grad.data_ptr() != view.data_ptr():
+            view.copy_(p.grad)
+            p.grad = view
 
     @contextlib.contextmanager
     def no_sync(self):
@@ -289,10 +302,7 @@ class ArenaDataParallel(torch.nn.Module):
         def hook(p: torch.Tensor) -> None:
             if not self.require_backward_grad_sync:
                 return
-            view = self.arena.view_of(i)
-            if p.grad is not None and p.grad.data_ptr() != view.data_ptr():      # a detached view (zero_grad(set_to_none))
-                view.copy_(p.grad)
-                p.grad = view
+            self._attach_view(i)                                                 # a detached view (zero_grad(set_to_none))
             if not self._queued:
                 self._queued = True
                 self.launch_log = []
@@ -323,14 +333,11 @@ class ArenaDataParallel(torch.nn.Module):
 
     def _finalize(self) -> None:
         try:
-            for i, p in enumerate(self.arena.params):          # parameters autograd never reached keep their zero slice
-                view = self.arena.view_of(i)
-                if p.grad is None:
-                    view.zero_()
-                    p.grad = view
-                elif p.grad.data_ptr() != view.data_ptr():
-                    view.copy_(p.grad)
-                    p.grad = view
+            # parameters neither hooked nor marked unused belong to segments that are not launched yet (a segment goes out
+            # only when all of its parameters are ready): repair their views now, never those of an exchanged segment
+            for i in range(len(self.arena.params)):
+                if not self._ready[i]:
+                    self._attach_view(i)
             while self._next < len(self.segments):
                 self._launch(self.segments[self._next])
                 self._next += 1
@@ -346,6 +353,9 @@ class ArenaDataParallel(torch.nn.Module):
     def reduce_now(self) -> None:
         """Exchange outside of a backward pass (e.g. gradients written by a CUDA-graph replay, which runs no hooks)."""
         self.launch_log = []
+        for i in range(len(self.arena.params)):
+            if not (self._ready[i] and self._seg_of[i] < self._next):
+                self._attach_view(i)
         self._ready = [True] * len(self.arena.params)
         self._n_ready = len(self._ready)
         self._finalize()

@@ -135,6 +135,19 @@ def _worker_body(rank, world, port, q):
     out["reduce_now"] = _flat_grads(net).numpy()
     adp3.remove_hooks()
 
+    # 5b. stale arena: after a full step, Lightning's zero_grad(set_to_none=True) detaches every view WITHOUT clearing the
+    # arena; a parameter that gets no gradient in the next step (layer 2 on rank 1) must contribute zero, not the old slice,
+    # and the repair must not touch a segment that has already been exchanged
+    adp4 = ArenaDataParallel(net, arena=adp.arena, bucket_cap_mb=0.5 * kb, first_bucket_mb=0.01 * kb, init_sync=False)
+    adp4.zero_grad()
+    _forward(adp4, _data(rank, 7), False).square().sum().backward()
+    net.zero_grad(set_to_none=True)
+    _forward(adp4, _data(rank, 8), skip_mid=rank == 1).square().sum().backward()
+    out["stale"] = _flat_grads(net).numpy()
+    out["stale_views"] = all(p.grad is not None and p.grad.data_ptr() == adp.arena.view_of(i).data_ptr()
+                             for i, p in enumerate(adp.arena.params))
+    adp4.remove_hooks()
+
     # 6. the same sum hook under torch's own DistributedDataParallel (GradBucket protocol)
     torch.manual_seed(3)
     ddp_net = _net()
@@ -217,6 +230,10 @@ def test_arena_data_parallel_gloo_world2():
     # 5. reduce_now
     _, g5 = _local([(0, [5]), (1, [5])])
     assert torch.allclose(t(0, "reduce_now"), (g5[0] + g5[1]) / 2, rtol=1e-6, atol=1e-7)
+    # 5b. stale arena + detached views
+    _, g8 = _local([(0, [8]), (1, [8])], skip=lambda r: r == 1)
+    assert torch.equal(t(0, "stale"), t(1, "stale")) and got[0]["stale_views"] and got[1]["stale_views"]
+    assert torch.allclose(t(0, "stale"), (g8[0] + g8[1]) / 2, rtol=1e-6, atol=1e-7)
     # 6. torch DDP + our sum hook
     _, g6 = _local([(0, [6]), (1, [6])], seed=3, fwd=lambda net, x, _s: net(x, everything=True))
     assert torch.allclose(t(0, "ddp_sum"), g6[0] + g6[1], rtol=1e-5, atol=1e-6)
