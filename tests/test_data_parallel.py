@@ -302,3 +302,43 @@ def test_lightning_strategy_factory_against_a_stub_ddp_strategy(monkeypatch):
     with strat.block_backward_sync():
         assert strat.model.require_backward_grad_sync is False
     assert strat.model.require_backward_grad_sync is True
+
+
+def test_arena_train_step_drives_the_wrapper(monkeypatch):
+    """``ArenaTrainStep`` over ``ArenaDataParallel`` (host logic; the fused optimizer kernel is replaced by a recorder): the
+    micro-batches before the boundary run under ``no_sync()``, the boundary backward exchanges, ``flush()`` exchanges through
+    ``reduce_now()``, and the optimizer is told whether the gradients are sums (``reduce_op='sum'``) or already means."""
+    from pytorch_connectomics_b200.training import ArenaDataParallel, ArenaTrainStep, FlatGradArena, FusedAdamW
+    for reduce_op in ("sum", "mean"):
+        torch.manual_seed(0)
+        net = _net()
+        arena = FlatGradArena(net.parameters())
+        opt = FusedAdamW.__new__(FusedAdamW)             # no CUDA here: only the attributes the step touches
+        opt.arena = arena
+        steps = []
+        opt.step = lambda grads_are_summed=False, _s=steps, _a=arena: _s.append((grads_are_summed, _a.buffer.clone()))
+        ddp = ArenaDataParallel(net, arena=arena, reduce_op=reduce_op, bucket_cap_mb=1e-4, first_bucket_mb=None)
+        synced = []
+        orig = ddp._finalize
+        monkeypatch.setattr(ddp, "_finalize", lambda: (synced.append(len(steps)), orig())[1])
+        step = ArenaTrainStep(ddp, lambda out, t: (out["output"] - t).square().mean(), opt, accumulate_grad_batches=2)
+        xs = [_data(0, s) for s in range(3)]
+        t = torch.zeros(5, 3)
+        step(xs[0], t)
+        assert steps == [] and synced == []              # first micro-batch: no exchange, no optimizer step
+        step(xs[1], t)
+        assert len(steps) == 1 and synced == [0] and steps[0][0] == (reduce_op == "sum")
+        # the window's gradient is the sum of the two micro-batch gradients of loss / 2
+        ref = _net()
+        ref.load_state_dict(net.state_dict())
+        for x in xs[:2]:
+            ((ref(x)["output"] - t).square().mean() / 2).backward()
+        assert torch.allclose(steps[0][1][:arena.total], torch.cat([
+            torch.nn.functional.pad((p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1),
+                                    (0, (arena.offsets[i + 1] if i + 1 < len(arena.params) else arena.total) - arena.offsets[i] - p.numel()))
+            for i, p in enumerate(ref.parameters())]), atol=1e-6)
+        step(xs[2], t)                                   # a partial window ...
+        assert len(steps) == 1 and step.flush() == 1     # ... is stepped by flush(), through reduce_now()
+        assert len(steps) == 2 and synced == [0, 1] and step.flush() is None
+    with pytest.raises(ValueError, match="optimizer's gradient arena"):
+        ArenaTrainStep(ArenaDataParallel(_net()), lambda o, t: o, opt)
