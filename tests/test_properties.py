@@ -1,0 +1,114 @@
+"""Property tests (hypothesis) of the host-side INTEGER logic behind the C ABI, over random geometries instead of a handful of
+golden cases: scan interval, eager window grid, lazy window grid + region filter, chunk grid, halo boxes, z-slab plans.
+Compared bit for bit with the oracle restatement always, and with the REAL reference files executed in place
+(``connectomics/inference/window.py``, ``connectomics/chunked/{chunk_grid,halo}.py``) when ``/root/reference`` exists (build
+container).  SURVEY §8 rows a11-a13, a21, §8e."""
+
+import pytest
+import torch
+from hypothesis import HealthCheck, given, settings
+from hypothesis import strategies as st
+
+from oracle import ref_loader
+from oracle import window_oracle as O
+from pytorch_connectomics_b200 import _lib as L
+from pytorch_connectomics_b200.inference import chunked as C
+from pytorch_connectomics_b200.inference import window as W
+from pytorch_connectomics_b200.inference.lazy import lazy_window_records
+from pytorch_connectomics_b200.inference.sharded import plan_z_slabs
+
+CFG = dict(max_examples=80, derandomize=True, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+axis = st.integers(1, 61)
+overlap = st.one_of(st.sampled_from([0.0, 0.25, 0.5, 0.75, 0.9, 0.99, 1.0, -0.2]), st.floats(0.0, 0.99, allow_nan=False))
+
+
+def _real_window():
+    return ref_loader.ref_window() if ref_loader.available() else None
+
+
+@settings(**CFG)
+@given(img=st.tuples(axis, axis, axis), roi=st.tuples(axis, axis, axis), ov=st.tuples(overlap, overlap, overlap))
+def test_scan_interval_and_eager_grid(img, roi, ov):
+    grown = tuple(max(i, r) for i, r in zip(img, roi))             # the engine grows the image to the window first
+    got_int = W.compute_scan_interval(grown, roi, 3, ov)
+    assert got_int == tuple(O.scan_interval(grown, roi, ov))
+    got = W._plan(L.GRID_EAGER, grown, roi, ov)
+    assert got == [tuple(s) for s in O.dense_starts(grown, roi, got_int)]
+    assert got == W.dense_patch_slices(grown, roi, got_int, return_slice=False)
+    # grid properties the blend relies on: inside the image, z-major order, every voxel covered
+    assert all(0 <= s[a] <= grown[a] - roi[a] for s in got for a in range(3)) and got == sorted(got)
+    for a in range(3):
+        starts = sorted({s[a] for s in got})
+        assert starts[0] == 0 and starts[-1] == grown[a] - roi[a]
+        assert all(b - c <= roi[a] for c, b in zip(starts, starts[1:]))
+    R = _real_window()
+    if R is not None:
+        assert tuple(R.compute_scan_interval(grown, roi, 3, ov)) == got_int
+        ref = R.dense_patch_slices(grown, roi, got_int, return_slice=False)
+        assert [tuple(int(v) for v in s) for s in ref] == got
+
+
+@settings(**CFG)
+@given(img=st.tuples(axis, axis, axis), roi=st.tuples(st.integers(1, 40), st.integers(1, 40), st.integers(1, 40)),
+       ov=st.sampled_from([0.0, 0.25, 0.5, 0.75]), snap=st.booleans(), data=st.data())
+def test_lazy_grid_and_region_filter(img, roi, ov, snap, data):
+    img = tuple(max(i, r) for i, r in zip(img, roi))
+    lo = tuple(data.draw(st.integers(0, img[a] - 1)) for a in range(3))
+    hi = tuple(data.draw(st.integers(lo[a] + 1, img[a])) for a in range(3))
+    got = lazy_window_records(img, roi, (ov,) * 3, lo, hi, snap)
+    want = O.lazy_region_records(img, roi, (ov,) * 3, lo, hi, snap)
+    assert [(r[0], r[1], tuple(h - l for l, h in zip(r[1], r[2])), r[3]) for r in want] == got
+    # the clipped boxes of the kept windows cover the region exactly (every voxel of it at least once)
+    cover = torch.zeros(tuple(h - l for l, h in zip(lo, hi)), dtype=torch.int32)
+    for _start, _plo, box, olo in got:
+        cover[tuple(slice(olo[a], olo[a] + box[a]) for a in range(3))] += 1
+    assert int(cover.min()) >= 1
+
+
+@settings(**CFG)
+@given(vol=st.tuples(axis, axis, axis), chunk=st.tuples(axis, axis, axis), halo=st.tuples(st.integers(0, 9), st.integers(0, 9), st.integers(0, 9)),
+       crop=st.tuples(st.integers(0, 5), st.integers(0, 5), st.integers(0, 5)), world=st.integers(1, 5))
+def test_chunk_grid_halo_and_rank_assignment(vol, chunk, halo, crop, world):
+    chunks = C.build_chunk_grid(vol, chunk)
+    want = O.chunk_grid(vol, chunk)
+    assert [(c.index, c.key, c.start, c.stop) for c in chunks] == [(tuple(i), k, tuple(a), tuple(b)) for i, k, a, b in want]
+    # the chunks tile the volume exactly once; rank shards partition the chunk list
+    cover = torch.zeros(vol, dtype=torch.int32)
+    for c in chunks:
+        cover[c.slices] += 1
+    assert int(cover.min()) == 1 and int(cover.max()) == 1
+    owned = [i for r in range(world) for i, _ in C.chunks_for_rank(chunks, r, world)]
+    assert sorted(owned) == list(range(len(chunks)))
+    input_shape = tuple(v + 2 * c for v, c in zip(vol, crop))
+    if ref_loader.available():
+        RC, RH = ref_loader.ref_chunk_grid(), ref_loader.ref_halo()
+        ref_chunks = RC.build_chunk_grid(vol, chunk)
+        assert [(c.index, c.start, c.stop, c.key) for c in chunks] == [(tuple(c.index), tuple(c.start), tuple(c.stop), c.key) for c in ref_chunks]
+    for k, c in enumerate(chunks[:6]):
+        lo, hi, core = C.resolve_halo_region(c, input_shape, halo=halo, crop_before=crop)
+        assert all(0 <= lo[a] <= c.start[a] + crop[a] and c.stop[a] + crop[a] <= hi[a] <= input_shape[a] for a in range(3))
+        assert tuple(s.stop - s.start for s in core) == c.shape
+        assert tuple(lo[a] + core[a].start for a in range(3)) == tuple(c.start[a] + crop[a] for a in range(3))
+        if ref_loader.available():
+            r = RH.resolve_halo_region(ref_chunks[k], input_shape, halo=halo, crop_before=crop)
+            assert (tuple(lo), tuple(hi), tuple(core)) == (tuple(r[0]), tuple(r[1]), tuple(r[2]))
+
+
+@settings(**{**CFG, "max_examples": 40})
+@given(img=st.tuples(st.integers(8, 200), st.integers(8, 40), st.integers(8, 40)), roi=st.tuples(st.integers(2, 32), st.integers(2, 8), st.integers(2, 8)),
+       ov=st.sampled_from([0.0, 0.25, 0.5, 0.75]), world=st.integers(1, 9))
+def test_z_slab_plans_partition_the_eager_grid(img, roi, ov, world):
+    img = tuple(max(i, r) for i, r in zip(img, roi))
+    plans = plan_z_slabs(img, roi, ov, world)
+    grid = W._plan(L.GRID_EAGER, img, roi, ov)
+    assert sorted(w for p in plans for w in p.windows) == sorted(grid)            # every window exactly once
+    live = [p for p in plans if p.windows]
+    own = sorted(p.own for p in live)
+    assert own[0][0] == 0 and own[-1][1] == img[0] and all(a[1] == b[0] for a, b in zip(own, own[1:]))
+    for p in live:                                                               # every plane I computed but do not own is sent
+        sent = sorted((lo, hi) for _, lo, hi in p.sends)
+        mine = set(range(p.slab[0], p.slab[1])) - set(range(p.own[0], p.own[1]))
+        assert set(z for lo, hi in sent for z in range(lo, hi)) == mine
+    sends = sorted((p.rank, peer, lo, hi) for p in plans for peer, lo, hi in p.sends)
+    recvs = sorted((peer, p.rank, lo, hi) for p in plans for peer, lo, hi in p.recvs)
+    assert sends == recvs                                                         # matched messages: no rank waits forever
