@@ -112,3 +112,64 @@ def test_z_slab_plans_partition_the_eager_grid(img, roi, ov, world):
     sends = sorted((p.rank, peer, lo, hi) for p in plans for peer, lo, hi in p.sends)
     recvs = sorted((peer, p.rank, lo, hi) for p in plans for peer, lo, hi in p.recvs)
     assert sends == recvs                                                         # matched messages: no rank waits forever
+
+
+# ----------------------------------------------------------------------------- TTA host logic vs the real reference files
+_flip_sets = st.one_of(st.just("all"), st.just(None), st.lists(st.lists(st.integers(0, 2), min_size=1, max_size=3, unique=True), min_size=0, max_size=4))
+_planes = st.one_of(st.just(None), st.lists(st.sampled_from([[0, 1], [1, 2], [0, 2], [2, 1]]), min_size=1, max_size=2, unique_by=tuple))
+_ks = st.one_of(st.just(None), st.lists(st.integers(0, 3), min_size=1, max_size=4, unique=True))
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference is only present in the build container")
+@settings(max_examples=120, derandomize=True, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(flips=_flip_sets, planes=_planes, ks=_ks, mode=st.sampled_from(["deepem", "banis"]), extra=st.integers(0, 2),
+       offs=st.lists(st.tuples(st.integers(0, 1), st.integers(1, 9)), min_size=0, max_size=3, unique=True))
+def test_tta_views_and_affinity_plans_against_the_real_reference(flips, planes, ks, mode, extra, offs):
+    """`resolve_tta_augmentation_combinations` (tta_combinations.py:161-193) and `build_affinity_tta_plan`
+    (tta_affinity.py:230-347) for random flip sets / rotation planes / quarter turns and random in-plane offset families
+    (each offset comes with its yx-swapped partner, which is what rotations in the yx plane need) — same views, same channel
+    moves and roll shifts, same partial channels, and the same ValueError when the reference refuses a combination."""
+    from types import SimpleNamespace as NS
+    from oracle.make_tta_affinity_goldens import load, plan_json
+    from pytorch_connectomics_b200.inference import tta as T
+    from pytorch_connectomics_b200.inference import tta_affinity as A
+    tc, ta, _te, _w = load()
+    tta = NS(flip_axes=flips, rotation90_axes=planes, rotate90_k=ks)
+
+    def both(fn_ref, fn_got):
+        try:
+            want = ("ok", fn_ref())
+        except ValueError as e:
+            want = ("error", str(e))
+        try:
+            got = ("ok", fn_got())
+        except ValueError as e:
+            got = ("error", str(e))
+        return want, got
+
+    want, got = both(lambda: tc.resolve_tta_augmentation_combinations(tta, spatial_dims=3),
+                     lambda: T.resolve_tta_augmentation_combinations(tta, spatial_dims=3))
+    assert want[0] == got[0]
+    if want[0] == "error":
+        assert want[1] == got[1]
+        return
+    norm = lambda combos: [(list(f), None if p is None else tuple(int(a) for a in p), int(k)) for f, p, k in combos]
+    assert norm(want[1]) == norm(got[1])
+    combos = got[1]
+    # offsets: unit z plus, per drawn (axis, distance), the offset along y or x AND its yx-swapped partner
+    offsets = ["1-0-0"]
+    for axis_id, d in offs:
+        for o in ((0, d, 0), (0, 0, d)):
+            s = "-".join(str(v) for v in o)
+            if s not in offsets:
+                offsets.append(s)
+    nch = extra + len(offsets)
+    targets = [dict(name="binary") for _ in range(extra)] + [dict(name="affinity", kwargs=dict(offsets=offsets, affinity_mode=mode))]
+    cfg = NS(data=NS(label_transform=NS(targets=targets, stack_outputs=True)), model=NS(out_channels=nch, heads={}))
+    want, got = both(lambda: ta.build_affinity_tta_plan(cfg, augmentation_combinations=want[1], num_raw=nch, requested_head=None),
+                     lambda: A.build_affinity_tta_plan(cfg, augmentation_combinations=combos, num_raw=nch))
+    assert want[0] == got[0], (want, got)
+    if want[0] == "error":
+        assert want[1] == got[1]
+    else:
+        assert plan_json(want[1]) == plan_json(got[1])
