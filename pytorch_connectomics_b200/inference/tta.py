@@ -56,53 +56,70 @@ def _parse_selector_string(value: str, *, context: str):
     return slice(start, stop)
 
 
+def _canonical_range_selector(selector, *, context: str):
+    """``normalize_channel_range_selector`` (channel_slices.py:55-81): None | int | the selector string re-rendered as
+    ``"start:stop"`` without blanks (error messages quote THIS form, not the raw string)."""
+    if selector is None:
+        return None
+    if isinstance(selector, int):
+        return int(selector)
+    if isinstance(selector, str):
+        parsed = _parse_selector_string(selector, context=context)
+        if isinstance(parsed, int):
+            return parsed
+        return f"{'' if parsed.start is None else parsed.start}:{'' if parsed.stop is None else parsed.stop}"
+    raise TypeError(f"{context} must be an int or a Python-style slice string, got {type(selector).__name__}.")
+
+
 def resolve_channel_index(index: int, *, num_channels: int, context: str = "channel selector") -> int:
+    """``channel_slices.py:130-145`` — Python indexing rules for one (possibly negative) channel index."""
     idx = int(index)
     if idx < 0:
         idx += num_channels
-    if idx < 0 or idx >= num_channels:
-        raise ValueError(f"Invalid {context} {index!r} for tensor with {num_channels} channels.")
+    if not 0 <= idx < num_channels:
+        raise ValueError(f"Invalid {context} {index!r} for tensor with {num_channels} channels: "
+                         f"resolved index {idx} is out of bounds.")
     return idx
 
 
 def resolve_channel_range(selector, *, num_channels: int, context: str = "channel selector") -> Tuple[int, int]:
-    """``channel_slices.py::resolve_channel_range`` — contiguous selector -> absolute half-open bounds."""
+    """``channel_slices.py:148-193`` — contiguous selector -> absolute half-open bounds."""
     if num_channels <= 0:
         raise ValueError(f"{context} requires num_channels > 0, got {num_channels}.")
-    if selector is None:
+    canon = _canonical_range_selector(selector, context=context)
+    if canon is None:
         return (0, num_channels)
-    if isinstance(selector, bool) or not isinstance(selector, (int, str)):
-        raise TypeError(f"{context} must be an int or a Python-style slice string, got {type(selector).__name__}.")
-    parsed = selector if isinstance(selector, int) else _parse_selector_string(selector, context=context)
-    if isinstance(parsed, int):
-        i = resolve_channel_index(parsed, num_channels=num_channels, context=context)
+    if isinstance(canon, int):
+        i = resolve_channel_index(canon, num_channels=num_channels, context=context)
         return (i, i + 1)
-    start = 0 if parsed.start is None else int(parsed.start)
-    stop = num_channels if parsed.stop is None else int(parsed.stop)
+    lo_text, hi_text = canon.split(":", 1)
+    start = int(lo_text) if lo_text else 0
+    stop = int(hi_text) if hi_text else num_channels
     if start < 0:
         start += num_channels
     if stop < 0:
         stop += num_channels
-    if start < 0 or start >= num_channels:
-        raise ValueError(f"Invalid {context} {selector!r} for tensor with {num_channels} channels: "
-                         f"resolved start index {start} is out of bounds.")
-    if stop < 0 or stop > num_channels:
-        raise ValueError(f"Invalid {context} {selector!r} for tensor with {num_channels} channels: "
-                         f"resolved stop index {stop} is out of bounds.")
+    where = f"Invalid {context} {canon!r} for tensor with {num_channels} channels: "
+    if not 0 <= start < num_channels:
+        raise ValueError(where + f"resolved start index {start} is out of bounds.")
+    if not 0 <= stop <= num_channels:
+        raise ValueError(where + f"resolved stop index {stop} is out of bounds.")
     if stop <= start:
-        raise ValueError(f"Invalid {context} {selector!r} for tensor with {num_channels} channels: "
-                         f"resolved range [{start}, {stop}) is empty or inverted.")
+        raise ValueError(where + f"resolved range [{start}, {stop}) is empty or inverted.")
     return (start, stop)
 
 
-def resolve_channel_indices(selector, *, num_channels: int, context: str = "channel selector") -> Optional[List[int]]:
-    """General selector (``None`` | int | slice string | list of ints) -> explicit channel list."""
+def resolve_channel_indices(selector, *, num_channels: int, context: str = "channel selector") -> List[int]:
+    """``channel_slices.py:196-224`` — general selector (``None`` = every channel | int | slice string | list of ints) ->
+    explicit channel list."""
+    if num_channels <= 0:
+        raise ValueError(f"{context} requires num_channels > 0, got {num_channels}.")
     if selector is None:
-        return None
-    if isinstance(selector, (int, str)) and not isinstance(selector, bool):
+        return list(range(num_channels))
+    if isinstance(selector, (int, str)):
         a, b = resolve_channel_range(selector, num_channels=num_channels, context=context)
         return list(range(a, b))
-    if isinstance(selector, Sequence):
+    if isinstance(selector, Sequence) and not isinstance(selector, bytes):
         if len(selector) == 0:
             raise ValueError(f"{context} must not be an empty channel list.")
         out = []
@@ -114,9 +131,10 @@ def resolve_channel_indices(selector, *, num_channels: int, context: str = "chan
                     raise ValueError(f"{context} channel lists must contain only integer indices, got {raw!r}.") from exc
             elif not isinstance(raw, int):
                 raise TypeError(f"{context} channel lists must contain only integers, got {type(raw).__name__}.")
-            out.append(resolve_channel_index(raw, num_channels=num_channels, context=context))
-        return out
-    raise TypeError(f"{context} must be an int, a slice string or a list of ints, got {type(selector).__name__}.")
+            out.append(raw)
+        return [resolve_channel_index(v, num_channels=num_channels, context=context) for v in out]
+    raise TypeError(f"{context} must be an int, a Python-style slice string, or an explicit list of ints; "
+                    f"got {type(selector).__name__}.")
 
 
 # ----------------------------------------------------------------------------- augmentation combinations (tta_combinations.py)

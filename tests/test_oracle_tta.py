@@ -48,7 +48,7 @@ def test_channel_selectors():
     assert T.resolve_channel_range("1:-1", num_channels=4) == (1, 3)
     assert T.resolve_channel_range(-1, num_channels=4) == (3, 4)
     assert T.resolve_channel_indices([0, "2", -1], num_channels=4) == [0, 2, 3]
-    assert T.resolve_channel_indices(None, num_channels=4) is None
+    assert T.resolve_channel_indices(None, num_channels=4) == [0, 1, 2, 3]     # utils/channel_slices.py:207-208: None = every channel
     for bad in ("4:", "2:1", "1:2:3", ""):
         with pytest.raises(ValueError):
             T.resolve_channel_range(bad, num_channels=4)

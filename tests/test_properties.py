@@ -173,3 +173,78 @@ def test_tta_views_and_affinity_plans_against_the_real_reference(flips, planes, 
         assert want[1] == got[1]
     else:
         assert plan_json(want[1]) == plan_json(got[1])
+
+
+# ----------------------------------------------------------------------------- selectors and config resolvers vs the real files
+_sel_str = st.one_of(st.integers(-6, 6).map(str), st.tuples(st.one_of(st.just(""), st.integers(-6, 6).map(str)),
+                                                            st.one_of(st.just(""), st.integers(-6, 6).map(str))).map(":".join),
+                     st.sampled_from([":", "", "a", "1:2:3", "0:", ":-1", " 1 : 3 "]))
+_selector = st.one_of(st.none(), st.integers(-6, 6), _sel_str, st.lists(st.integers(-6, 6), min_size=0, max_size=4))
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference is only present in the build container")
+@settings(max_examples=250, derandomize=True, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(selector=_selector, n=st.integers(1, 6), mode_cfg=st.one_of(st.sampled_from(["mean", "min", "max", "median"]),
+       st.lists(st.tuples(_sel_str, st.sampled_from(["mean", "min", "max", "avg"])).map(list), min_size=0, max_size=3)))
+def test_channel_selectors_and_ensemble_modes_against_the_real_reference(selector, n, mode_cfg):
+    """`resolve_channel_indices` / `resolve_channel_range` (utils/channel_slices.py:130-224) and
+    `_resolve_ensemble_mode_map` (tta_combinations.py:196-241): same result or the same ValueError text."""
+    import sys
+    from oracle.make_tta_affinity_goldens import load
+    from pytorch_connectomics_b200.inference import tta as T
+    tc, _ta, _te, _w = load()
+    cs = sys.modules["connectomics.utils.channel_slices"]
+
+    def outcome(fn):
+        try:
+            return ("ok", fn())
+        except (ValueError, TypeError) as e:
+            return (type(e).__name__, str(e))
+
+    for name in ("resolve_channel_indices", "resolve_channel_range"):
+        if name == "resolve_channel_range" and not isinstance(selector, str):
+            continue
+        want = outcome(lambda: getattr(cs, name)(selector, num_channels=n, context="sel"))
+        got = outcome(lambda: getattr(T, name)(selector, num_channels=n, context="sel"))
+        assert want == got, (name, selector, n, want, got)
+    want = outcome(lambda: tc._resolve_ensemble_mode_map(mode_cfg, n))
+    got = outcome(lambda: T._resolve_ensemble_mode_map(mode_cfg, n))
+    assert want == got, (mode_cfg, n, want, got)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference is only present in the build container")
+@settings(max_examples=250, derandomize=True, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(window=st.one_of(st.none(), st.lists(st.integers(1, 64), min_size=2, max_size=3)),
+       out_size=st.one_of(st.none(), st.lists(st.integers(1, 64), min_size=2, max_size=3)),
+       patch=st.one_of(st.none(), st.lists(st.integers(1, 64), min_size=3, max_size=3)),
+       ov=st.one_of(st.none(), st.floats(-0.5, 1.5, allow_nan=False), st.lists(st.floats(-0.5, 1.5, allow_nan=False), min_size=3, max_size=3)),
+       bs=st.one_of(st.none(), st.integers(0, 5)), loader_bs=st.integers(1, 4), blending=st.sampled_from(["bump", "constant", "gaussian", "Distance_Transform", "dt"]),
+       keep=st.booleans(), swdev=st.sampled_from([None, "", "none", "cpu"]), outdev=st.sampled_from([None, "null", "cpu"]),
+       odt=st.sampled_from([None, "float32", "float16", "bfloat16", "fp16", "half", "double"]),
+       border=st.one_of(st.none(), st.integers(0, 3), st.lists(st.integers(0, 3), min_size=1, max_size=3)))
+def test_config_resolvers_against_the_real_window_py(window, out_size, patch, ov, bs, loader_bs, blending, keep, swdev, outdev, odt, border):
+    """`resolve_inferer_roi_size` / `resolve_inferer_overlap` / `_resolve_sliding_window_runtime` / `resolve_model_output_dtype`
+    / `resolve_border_mask` (window.py:333-461) on random config trees: same values or the same error."""
+    from types import SimpleNamespace as NS
+    R = ref_loader.ref_window()
+    sw = NS(window_size=window, overlap=ov, sw_batch_size=bs, blending=blending, padding_mode="reflect", cval=0.5, keep_input_on_cpu=keep,
+            sw_device=swdev, output_device=outdev, border_mask=border)
+    cfg = NS(model=NS(output_size=out_size), data=NS(dataloader=NS(batch_size=loader_bs), data_transform=NS(patch_size=patch)),
+             inference=NS(sliding_window=sw, model=NS(output_dtype=odt)))
+
+    def outcome(fn):
+        try:
+            return ("ok", fn())
+        except (ValueError, TypeError) as e:
+            return (type(e).__name__, str(e))
+
+    roi_w, roi_g = outcome(lambda: R.resolve_inferer_roi_size(cfg)), outcome(lambda: W.resolve_inferer_roi_size(cfg))
+    assert roi_w == roi_g
+    assert outcome(lambda: R.resolve_model_output_dtype(cfg)) == outcome(lambda: W.resolve_model_output_dtype(cfg))
+    assert outcome(lambda: R.resolve_border_mask(cfg, 3)) == outcome(lambda: W.resolve_border_mask(cfg, 3))
+    if roi_w[0] == "ok" and roi_w[1] is not None:
+        roi = roi_w[1]
+        assert outcome(lambda: R.resolve_inferer_overlap(cfg, roi)) == outcome(lambda: W.resolve_inferer_overlap(cfg, roi))
+        want = outcome(lambda: R._resolve_sliding_window_runtime(cfg, roi))
+        got = outcome(lambda: W._resolve_sliding_window_runtime(cfg, roi))
+        assert want == got, (want, got)
