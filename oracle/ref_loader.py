@@ -80,3 +80,13 @@ def ref_chunk_grid():
 def ref_halo():
     ref_chunk_grid()
     return _load("connectomics.chunked.halo", "connectomics/chunked/halo.py")
+
+
+def ref_optimizer_build():
+    """``connectomics/training/optimization/build.py`` (torch + its sibling ``lr_scheduler.py`` only)"""
+    _base_stubs()
+    c = os.path.join(REF_ROOT, "connectomics")
+    _stub("connectomics.training", os.path.join(c, "training"))
+    _stub("connectomics.training.optimization", os.path.join(c, "training", "optimization"))
+    _load("connectomics.training.optimization.lr_scheduler", "connectomics/training/optimization/lr_scheduler.py")
+    return _load("connectomics.training.optimization.build", "connectomics/training/optimization/build.py")

@@ -30,7 +30,10 @@ def reference_param_groups(model: torch.nn.Module, lr: float, weight_decay: floa
     wdb = weight_decay if weight_decay_bias is None else weight_decay_bias
     groups, memo = [], set()
     for module in model.modules():
-        norm = isinstance(module, _NORM_TYPES) or type(module).__name__ == "LayerNorm"
+        # exactly the reference's test: torch's own norm classes.  The channels-first ``LayerNorm`` of MedNeXt's
+        # ``norm_type="layer"`` is a plain ``nn.Module`` upstream, so its weight is decayed like any other weight and its bias
+        # takes the bias rule — reproduced here, checked against the real ``build_optimizer`` in tests/test_host_logic.py
+        norm = isinstance(module, _NORM_TYPES)
         for key, value in module.named_parameters(recurse=False):
             if not value.requires_grad or value in memo:
                 continue

@@ -398,3 +398,39 @@ def test_upkern_load_weights_resizes_depthwise_kernels():
     bad = PM.MedNeXt(kernel_size=5, **{**kw, "n_channels": 32})
     with pytest.raises(ValueError, match="identical architecture"):
         PM.upkern_load_weights(bad, small)
+
+
+def test_param_groups_equal_the_real_build_optimizer():
+    """`reference_param_groups` / `build_fused_adamw`'s grouping against the REAL `training/optimization/build.py::build_optimizer`
+    (executed in place) on this package's own module trees: same parameter order, same lr / weight_decay per parameter —
+    MedNeXt with GroupNorm and with the channels-first LayerNorm (a plain nn.Module upstream: NOT a norm layer for the
+    reference's rule), the multi-head wrapper, the MONAI U-Net (BatchNorm + PReLU), shared parameters counted once."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("/root/reference is only present in the build container")
+    from pytorch_connectomics_b200.architectures import mednext as PM
+    from pytorch_connectomics_b200.architectures import monai_unet as MU
+    from pytorch_connectomics_b200.training.optim import reference_param_groups
+    B = ref_loader.ref_optimizer_build()
+    kw = dict(exp_r=2, kernel_size=3, deep_supervision=True, do_res=True, do_res_up_down=True, block_counts=[1] * 9)
+    shared = torch.nn.Sequential(torch.nn.Linear(3, 3), torch.nn.Linear(3, 3))
+    shared[1].weight = shared[0].weight
+    nets = [PM.MedNeXt(1, 16, 2, **kw), PM.MedNeXt(1, 16, 2, norm_type="layer", **kw),
+            MU.UNet(3, 1, 2, [16, 32, 64], [2, 2], num_res_units=1), shared,
+            A.build_model(NS(model=NS(arch=NS(type="mednext"), in_channels=1, out_channels=2, heads=None,
+                                      mednext=NS(size="S", kernel_size=3), loss=NS(deep_supervision=False))))]
+    nets[0].stem.bias.requires_grad_(False)                         # frozen parameters are left out by both
+    for oc in (NS(name="adamw", lr=1e-3, weight_decay=0.01),
+               NS(name="AdamW", lr=3e-4, weight_decay=0.05, weight_decay_norm=0.001, weight_decay_bias=0.0, bias_lr_factor=2.0)):
+        cfg = NS(optimization=NS(optimizer=oc))
+        for net in nets:
+            real = B.build_optimizer(cfg, net).param_groups
+            ours = reference_param_groups(net, oc.lr, oc.weight_decay, getattr(oc, "weight_decay_norm", 0.0),
+                                          getattr(oc, "weight_decay_bias", None), getattr(oc, "bias_lr_factor", 1.0))
+            assert len(real) == len(ours) > 0
+            for a, b in zip(real, ours):
+                assert a["params"][0] is b["params"][0] and a["lr"] == b["lr"] and a["weight_decay"] == b["weight_decay"]
+    layer_net = nets[1]
+    g = {id(x["params"][0]): x for x in reference_param_groups(layer_net, 1e-3, 0.01, 0.0, 0.002, 1.0)}
+    blk = layer_net.enc_block_0[0]
+    assert g[id(blk.norm.weight)]["weight_decay"] == 0.01 and g[id(blk.norm.bias)]["weight_decay"] == 0.002
