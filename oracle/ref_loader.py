@@ -90,3 +90,12 @@ def ref_optimizer_build():
     _stub("connectomics.training.optimization", os.path.join(c, "training", "optimization"))
     _load("connectomics.training.optimization.lr_scheduler", "connectomics/training/optimization/lr_scheduler.py")
     return _load("connectomics.training.optimization.build", "connectomics/training/optimization/build.py")
+
+
+def ref_artifact():
+    """``connectomics/inference/artifact.py`` (json / numpy + ``utils/model_outputs.py``; h5py is imported lazily there)"""
+    _base_stubs()
+    c = os.path.join(REF_ROOT, "connectomics")
+    _stub("connectomics.utils", os.path.join(c, "utils"))
+    _load("connectomics.utils.model_outputs", "connectomics/utils/model_outputs.py")
+    return _load("connectomics.inference.artifact", "connectomics/inference/artifact.py")

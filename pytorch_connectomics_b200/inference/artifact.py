@@ -68,7 +68,7 @@ def build_prediction_artifact_metadata(cfg: Any, *, image_path=None, checkpoint_
         ident.append(f"head={output_head}")
     elif _cfg_get(cfg, "model.primary_head"):
         ident.append(f"primary_head={_cfg_get(cfg, 'model.primary_head')}")
-    sel = _cfg_get(cfg, "inference.select_channel")
+    sel = _cfg_get(cfg, "inference.model.select_channel")      # utils/model_outputs.py:37-39 get_inference_select_channel
     if sel is not None:
         ident.append(f"select_channel={sel}")
     return PredictionArtifactMetadata(

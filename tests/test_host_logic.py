@@ -434,3 +434,36 @@ def test_param_groups_equal_the_real_build_optimizer():
     g = {id(x["params"][0]): x for x in reference_param_groups(layer_net, 1e-3, 0.01, 0.0, 0.002, 1.0)}
     blk = layer_net.enc_block_0[0]
     assert g[id(blk.norm.weight)]["weight_decay"] == 0.01 and g[id(blk.norm.bias)]["weight_decay"] == 0.002
+
+
+def test_artifact_metadata_equals_the_real_artifact_module():
+    """`build_prediction_artifact_metadata` and the attrs encoding (`inference/artifact.py:75-138`) against the REAL module
+    executed in place: same dataclass fields and the same JSON / scalar attrs on the dataset."""
+    from dataclasses import asdict
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("/root/reference is only present in the build container")
+    from pytorch_connectomics_b200.inference import artifact as PA
+    RA = ref_loader.ref_artifact()
+    cfgs = [NS(),
+            NS(model=NS(arch=NS(type="mednext"), primary_head="aff"), data=NS(data_transform=NS(val_transpose=[2, 1, 0])),
+               decoding=NS(enabled=False), inference=NS(model=NS(select_channel="0:3"),
+                                                       prediction_transform=NS(enabled=True, intensity_scale=255, intensity_dtype="uint8"))),
+            NS(model=NS(arch=NS(type="monai_unet"), primary_head=None), data=NS(data_transform=NS(val_transpose=[])),
+               inference=NS(model=NS(select_channel=[2, 0]), prediction_transform=NS(enabled=False, intensity_scale=3.0)))]
+    calls = [dict(),
+             dict(image_path="/d/img.h5", checkpoint_path="/c/last.ckpt", output_head="sdt", input_shape=[12, 10, 14], final_shape=(10, 10, 10),
+                  crop_pad=((1, 1), (0, 0), [2, 2]), chunk_shape=[6, 10, 7], halo=(2, 2, 2), extra={"compression": "gzip", "chunk_index_zyx": [0, 0, 1]}),
+             dict(input_shape=[], intensity_scale=0.5, intensity_dtype="float16", extra=None)]
+
+    class Dset:
+        def __init__(self):
+            self.attrs = {}
+
+    for cfg in cfgs:
+        for kw in calls:
+            want, got = RA.build_prediction_artifact_metadata(cfg, **kw), PA.build_prediction_artifact_metadata(cfg, **kw)
+            assert asdict(want) == asdict(got), (kw, asdict(want), asdict(got))
+            d = Dset()
+            RA.write_prediction_artifact_attrs(d, want)
+            assert d.attrs == PA.metadata_attrs(got)
