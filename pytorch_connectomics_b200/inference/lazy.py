@@ -313,25 +313,7 @@ def lazy_sliding_window(volume: torch.Tensor, network: Callable[[torch.Tensor], 
 
 
 # ----------------------------------------------------------------------------- the reference's seam
-def _select_head(pred, requested_head: Optional[str]):
-    """``forward_fn`` may return a tensor, ``{"output": tensor | {head: tensor}, ...}`` or ``{head: tensor}``
-    (``mednext_models.py:54-89,253-273``); ``requested_head`` picks a named head (comma-separated = channel concat)."""
-    if isinstance(pred, torch.Tensor):
-        return pred
-    if isinstance(pred, dict) and "output" in pred:
-        pred = pred["output"]
-        if isinstance(pred, torch.Tensor):
-            return pred
-    if isinstance(pred, dict):
-        if requested_head:
-            names = [n.strip() for n in str(requested_head).split(",") if n.strip()]
-            missing = [n for n in names if n not in pred]
-            if missing:
-                raise ValueError(f"requested_head {missing} not in model outputs {sorted(pred.keys())}")
-            outs = [pred[n] for n in names]
-            return outs[0] if len(outs) == 1 else torch.cat(outs, dim=1)
-        return next(iter(pred.values()))
-    raise ValueError(f"forward_fn must return a tensor or a dict of tensors; got {type(pred).__name__}.")
+from .model_outputs import pick_inference_output  # noqa: E402
 
 
 def _dist_context():
@@ -409,7 +391,8 @@ def _lazy_sliding_window_cfg(cfg, forward_fn, image_path, *, region_start, regio
                 if predictor is not None:
                     return predictor.predict(batch.float(), mask=m, mask_align_to_image=mask_align_to_image,
                                              requested_head=requested_head)
-                pred = _select_head(forward_fn(batch), requested_head)
+                # the reference's selection rules (utils/model_outputs.py:61-123,245-305), as its TTAPredictor applies them
+                pred = pick_inference_output(cfg, forward_fn(batch), requested_head)
                 if m is not None:
                     if m.shape[1] not in (1, pred.shape[1]):
                         raise ValueError(f"Mask channels {m.shape[1]} incompatible with prediction channels "

@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from . import window as W
-from .lazy import _select_head
+from .model_outputs import pick_inference_output, resolve_output_head
 from .tta import TTAEnsemble, resolve_activation_specs, resolve_channel_indices
 
 logger = logging.getLogger(__name__)
@@ -137,15 +137,7 @@ class TTAPredictor:
         """``tta.py:449-463`` — one forward, then the requested / primary head's tensor."""
         with torch.no_grad():
             out = self.forward_fn(inputs)
-        head = self._requested_output_head_override or _node(self.cfg, "inference", "model", "head")
-        if head is None and isinstance(out, dict):
-            head = _node(self.cfg, "model", "primary_head")
-            inner = out.get("output", out)
-            if isinstance(inner, dict) and head is not None and head not in inner:
-                head = None
-        pred = _select_head(out, head)
-        if not isinstance(pred, torch.Tensor):
-            raise ValueError(f"forward_fn must produce a tensor for the selected head; got {type(pred).__name__}.")
+        pred = pick_inference_output(self.cfg, out, self._requested_output_head_override)
         num_raw = int(pred.shape[1])
         if self._seen_raw != num_raw:
             self._seen_raw = num_raw
@@ -266,6 +258,8 @@ class TTAPredictor:
                 requested_head: Optional[str] = None) -> torch.Tensor:
         """``tta.py:1619-1666``"""
         previous = self._requested_output_head_override
+        if requested_head is not None:               # tta.py:1640-1646: an explicit request must name a configured head
+            resolve_output_head(self.cfg, requested_head=requested_head, purpose="inference output selection", allow_none=False)
         self._requested_output_head_override = requested_head
         self._seen_raw = None
         try:

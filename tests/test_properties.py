@@ -248,3 +248,52 @@ def test_config_resolvers_against_the_real_window_py(window, out_size, patch, ov
         want = outcome(lambda: R._resolve_sliding_window_runtime(cfg, roi))
         got = outcome(lambda: W._resolve_sliding_window_runtime(cfg, roi))
         assert want == got, (want, got)
+
+
+_head_name = st.sampled_from(["aff", "sdt", "bin", " aff ", "", "aff,sdt", "nope", "sdt, bin"])
+_maybe_head = st.one_of(st.none(), _head_name, st.just(3))
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference is only present in the build container")
+@settings(max_examples=400, derandomize=True, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(heads=st.one_of(st.none(), st.just({}), st.dictionaries(st.sampled_from(["aff", "sdt", "bin"]), st.integers(1, 6), min_size=1, max_size=3)),
+       requested=_maybe_head, configured=_maybe_head, primary=_maybe_head, out_channels=st.one_of(st.none(), st.integers(1, 4)),
+       allow=st.booleans(), shape=st.sampled_from(["tensor", "ds", "heads", "bare_heads", "empty", "list", "bad_head"]))
+def test_output_head_selection_against_the_real_model_outputs(heads, requested, configured, primary, out_channels, allow, shape):
+    """`resolve_output_head(s)` / `resolve_output_channels` / `select_output_tensor` (utils/model_outputs.py:61-305) on random
+    head configurations and output containers: same selection or the same error (type and text)."""
+    import sys
+    from types import SimpleNamespace as NS
+    from oracle.make_chunk_cfg_goldens import load
+    from pytorch_connectomics_b200.inference import model_outputs as MO
+    load()
+    R = sys.modules["connectomics.utils.model_outputs"]
+    head_cfg = None if heads is None else {k: NS(out_channels=v) for k, v in heads.items()}
+    cfg = NS(model=NS(heads=head_cfg, primary_head=primary, out_channels=out_channels), inference=NS(model=NS(head=configured)))
+
+    def outcome(fn):
+        try:
+            return ("ok", fn())
+        except (ValueError, TypeError) as e:
+            return (type(e).__name__, str(e))
+
+    for mod_fn in ("resolve_output_head", "resolve_output_heads", "resolve_output_channels"):
+        kw = {}
+        if mod_fn == "resolve_output_head":
+            kw = dict(requested_head=requested, allow_none=allow, purpose="p")
+        elif mod_fn == "resolve_output_channels":
+            kw = dict(requested_head=requested, allow_ambiguous=allow, purpose="p")
+        else:
+            kw = dict(purpose="p")
+        assert outcome(lambda: getattr(R, mod_fn)(cfg, **kw)) == outcome(lambda: getattr(MO, mod_fn)(cfg, **kw)), (mod_fn, kw)
+    t = {k: torch.full((1, 1, 1, 1, 1), float(i)) for i, k in enumerate(["aff", "sdt", "bin"])}
+    outputs = {"tensor": t["aff"], "ds": {"output": t["aff"], "ds_1": t["sdt"]}, "heads": {"output": {"aff": t["aff"], "sdt": t["sdt"]}},
+               "bare_heads": {"sdt": t["sdt"]}, "empty": {"output": {}}, "list": [t["aff"]], "bad_head": {"output": {"aff": [1], "sdt": t["sdt"]}}}[shape]
+    req = requested if isinstance(requested, str) or requested is None else None
+    prim = primary if isinstance(primary, str) or primary is None else None
+
+    def pick(mod):
+        tensor, name = mod.select_output_tensor(outputs, requested_head=req, primary_head=prim, purpose="p")
+        return float(tensor.flatten()[0]), name
+
+    assert outcome(lambda: pick(R)) == outcome(lambda: pick(MO))

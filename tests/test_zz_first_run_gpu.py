@@ -169,7 +169,6 @@ def test_lazy_seam_runs_patches_through_the_predictor(tmp_path):
     blending.  With a pointwise forward and flip views every view of a patch gives the same values, so the result is
     activation(net(volume))[selected] * mask up to blending round-off."""
     from pytorch_connectomics_b200.inference import lazy as Z
-    dev = "cuda:0"
     vol = np.random.RandomState(5).rand(24, 16, 40).astype(np.float32)
     mask = (np.random.RandomState(6).rand(24, 16, 40) > 0.3).astype(np.float32)
     np.save(tmp_path / "v.npy", vol)
@@ -182,7 +181,7 @@ def test_lazy_seam_runs_patches_through_the_predictor(tmp_path):
              inference=NS(sliding_window=sw, model=NS(output_dtype=None, channel_activations=acts, select_channel=[2, 0], head=None),
                           test_time_augmentation=NS(enabled=True, flip_axes="all", rotation90_axes=None, rotate90_k=None,
                                                     ensemble_mode="mean", apply_mask=True)))
-    got = Z.lazy_predict_volume(cfg, _net, str(tmp_path / "v.npy"), mask_path=str(tmp_path / "m.npy"), device=dev)
+    got = Z.lazy_predict_volume(cfg, _net, str(tmp_path / "v.npy"), mask_path=str(tmp_path / "m.npy"), device=DEV)
     x = torch.from_numpy(vol)[None, None]
     raw = _net(x)
     m = torch.from_numpy(mask)[None, None]
