@@ -297,3 +297,58 @@ def test_output_head_selection_against_the_real_model_outputs(heads, requested, 
         return float(tensor.flatten()[0]), name
 
     assert outcome(lambda: pick(R)) == outcome(lambda: pick(MO))
+
+
+_offset = st.one_of(st.tuples(st.integers(-9, 9), st.integers(-9, 9), st.integers(-9, 9)).map(lambda o: "-".join(str(abs(v)) for v in o)),
+                    st.tuples(st.integers(-9, 9), st.integers(-9, 9), st.integers(-9, 9)).map(list),
+                    st.sampled_from(["1-0", "a-b-c", "", [1, 2], 5]))
+_aff_kwargs = st.fixed_dictionaries({}, optional={"offsets": st.lists(_offset, min_size=0, max_size=4),
+                                                   "affinity_mode": st.sampled_from(["deepem", "banis", "DeepEM", None, "nope"]),
+                                                   "long_range": st.one_of(st.none(), st.integers(0, 12))})
+_task = st.one_of(st.sampled_from(["binary", "affinity", "instance_edt", None, 3]),
+                  st.fixed_dictionaries({"name": st.sampled_from(["binary", "polarity", "affinity", "skeleton"])},
+                                        optional={"kwargs": st.one_of(_aff_kwargs, st.fixed_dictionaries({"exclusive": st.booleans()}))}),
+                  st.fixed_dictionaries({"name": st.just("affinity"), "kwargs": _aff_kwargs}))
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference is only present in the build container")
+@settings(max_examples=400, derandomize=True, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(targets=st.one_of(st.none(), st.just("affinity"), st.lists(_task, min_size=0, max_size=4)), stack=st.booleans(), as_ns=st.booleans(),
+       off=st.tuples(st.integers(-9, 9), st.integers(-9, 9), st.integers(-9, 9)), flips=st.lists(st.integers(0, 2), max_size=3, unique=True),
+       plane=st.sampled_from([None, (0, 1), (1, 2), (0, 2), (2, 1)]), k=st.integers(0, 5),
+       shape=st.tuples(st.integers(1, 9), st.integers(1, 9), st.integers(1, 9)))
+def test_affinity_config_helpers_against_the_real_reference(targets, stack, as_ns, off, flips, plane, k, shape):
+    """The label-stack walk behind the affinity plans (`data/processing/affinity.py:86-256`: task names / kwargs in every
+    container form, offset parsing, affinity mode, stacked channel layout) and the offset geometry of `tta_affinity.py:72-131`
+    (`transform_offset`, `valid_slices_for_shift`): same result or the same error on random label configurations."""
+    import sys
+    from types import SimpleNamespace as NS
+    from oracle.make_tta_affinity_goldens import load
+    from pytorch_connectomics_b200.inference import tta_affinity as A
+    _tc, ta, _te, _w = load()
+    R = sys.modules["connectomics.data.processing.affinity"]
+
+    def outcome(fn):
+        try:
+            return ("ok", fn())
+        except (ValueError, TypeError, KeyError) as e:
+            return (type(e).__name__, str(e))
+
+    def wrap(t):                                     # the same task as an attribute object instead of a dict
+        return NS(**{k: v for k, v in t.items()}) if as_ns and isinstance(t, dict) else t
+
+    tl = [wrap(t) for t in targets] if isinstance(targets, list) else targets
+    cfg = NS(data=NS(label_transform=NS(targets=tl, stack_outputs=stack)))
+    for name in ("resolve_affinity_mode_from_cfg", "resolve_affinity_channel_groups_from_cfg", "resolve_stacked_label_channel_count"):
+        assert outcome(lambda: getattr(R, name)(cfg)) == outcome(lambda: getattr(A, name)(cfg)), name
+    if isinstance(targets, list):
+        for t in targets:
+            kw = t.get("kwargs") if isinstance(t, dict) else None
+            if isinstance(kw, dict):
+                assert outcome(lambda: R.resolve_affinity_offsets_from_kwargs(kw)) == outcome(lambda: A.resolve_affinity_offsets_from_kwargs(kw))
+                if "offsets" in kw:
+                    assert outcome(lambda: R.parse_affinity_offsets(kw["offsets"])) == outcome(lambda: A.parse_affinity_offsets(kw["offsets"]))
+                assert outcome(lambda: R.normalize_affinity_mode(kw.get("affinity_mode"))) == outcome(lambda: A.normalize_affinity_mode(kw.get("affinity_mode")))
+    assert outcome(lambda: ta.transform_offset(off, flip_axes=flips, rotation_plane_spatial=plane, k=k)) == \
+        outcome(lambda: A.transform_offset(off, flip_axes=flips, rotation_plane_spatial=plane, k=k))
+    assert outcome(lambda: ta.valid_slices_for_shift(shape, off)) == outcome(lambda: A.valid_slices_for_shift(shape, off))
