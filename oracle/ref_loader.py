@@ -99,3 +99,17 @@ def ref_artifact():
     _stub("connectomics.utils", os.path.join(c, "utils"))
     _load("connectomics.utils.model_outputs", "connectomics/utils/model_outputs.py")
     return _load("connectomics.inference.artifact", "connectomics/inference/artifact.py")
+
+
+def ref_mednext_models():
+    """``connectomics/models/architectures/mednext_models.py`` executed in place over a stand-in ``nnunet_mednext`` module
+    whose ``MedNeXt`` / ``MedNeXtBlock`` / ``create_mednext_v1`` are the ORACLE restatements (the third-party package is not
+    installable offline).  What this gives the tests is the REAL builders, wrappers, task heads and validation code of the
+    reference; the network arithmetic underneath is the oracle's."""
+    _base_stubs()
+    from . import mednext_oracle as MO
+    if "nnunet_mednext" not in sys.modules:
+        _stub("nnunet_mednext", MedNeXt=MO.MedNeXt, MedNeXtBlock=MO.MedNeXtBlock, create_mednext_v1=MO.create_mednext_v1)
+    ref_registry()
+    ref_base()
+    return _load("connectomics.models.architectures.mednext_models", "connectomics/models/architectures/mednext_models.py")

@@ -1,0 +1,95 @@
+"""The architecture-builder seam against the REAL ``connectomics/models/architectures/mednext_models.py`` (builders, wrappers,
+task heads, validation), executed in place over a stand-in ``nnunet_mednext`` module whose network classes are the oracle
+restatements (``oracle/ref_loader.py::ref_mednext_models``; the third-party package cannot be installed offline).  For every
+configuration: same wrapper type and attributes, same ``get_model_info()``, same ``state_dict`` keys and shapes (so reference
+checkpoints load into this package's modules and vice versa), and — for bad configurations — the same error.  CPU only: the
+modules are built, not run (``tests/test_mednext_gpu.py`` runs them)."""
+
+from types import SimpleNamespace as NS
+
+import pytest
+import torch
+
+from oracle import ref_loader
+
+pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="/root/reference is only present in the build container")
+
+
+def _cfg(arch="mednext", heads=None, primary=None, ds=False, out_channels=2, in_channels=1, **mednext):
+    return NS(model=NS(arch=NS(type=arch), in_channels=in_channels, out_channels=out_channels, heads=heads, primary_head=primary,
+                       mednext=NS(**mednext), loss=NS(deep_supervision=ds)))
+
+
+def _outcome(fn):
+    try:
+        return ("ok", fn())
+    except (ValueError, TypeError, KeyError, NotImplementedError) as e:
+        return (type(e).__name__, str(e))
+
+
+def _describe(m):
+    sd = m.state_dict()
+    d = dict(type=type(m).__name__, ds=m.supports_deep_supervision, scales=m.output_scales, info=m.get_model_info(),
+             keys=[(k, tuple(v.shape)) for k, v in sd.items()], repr_head=repr(m).split("(")[0])
+    for attr in ("primary_head", "feature_channels"):
+        if hasattr(m, attr):
+            d[attr] = getattr(m, attr)
+    if hasattr(m, "head_specs"):
+        d["head_specs"] = {k: dict(v) if isinstance(v, dict) else v for k, v in m.head_specs.items()}
+    if hasattr(m, "heads"):
+        d["heads"] = sorted(m.heads.keys())
+    return d
+
+
+HEADS = {"aff": NS(out_channels=3, num_blocks=1, hidden_channels=16), "sdt": dict(out_channels=1, num_blocks=0)}
+
+GOOD = [
+    _cfg(size="S", kernel_size=3), _cfg(size="B", kernel_size=5, ds=True), _cfg(size="S", kernel_size=3, ds=True, out_channels=3),
+    _cfg(size="S", kernel_size=3, checkpoint_style="outside_block", in_channels=2),
+    _cfg(size="S", kernel_size=3, heads=HEADS, primary="aff"), _cfg(size="S", kernel_size=3, heads={"only": NS(out_channels=2)}),
+    _cfg("mednext_custom", base_channels=16, exp_r=2, kernel_size=3, block_counts=[1] * 9),
+    _cfg("mednext_custom", base_channels=16, exp_r=[2, 3, 4, 4, 4, 4, 4, 3, 2], kernel_size=5, block_counts=[1, 2, 1, 1, 1, 1, 1, 2, 1], ds=True,
+         do_res=False, do_res_up_down=False),
+    _cfg("mednext_custom", base_channels=16, exp_r=2, kernel_size=3, block_counts=[1] * 9, norm="layer", checkpoint_style="outside_block"),
+    _cfg("mednext_custom", base_channels=16, exp_r=2, kernel_size=3, block_counts=[1] * 9, heads=HEADS, primary="sdt"),
+]
+
+BAD = [
+    _cfg(size="XL", kernel_size=3), _cfg(size="S", kernel_size=4), _cfg(size="S", kernel_size=3, checkpoint_style="inside"),
+    _cfg("mednext_custom", base_channels=16, dim="4d"), _cfg("mednext_custom", base_channels=16, norm="batch"),
+    _cfg("mednext_custom", base_channels=16, block_counts=[1] * 8),
+    _cfg(size="S", kernel_size=3, heads=HEADS, primary="aff", ds=True),                       # heads reject deep-supervision trunks
+    _cfg(size="S", kernel_size=3, heads={"a": NS(out_channels=0)}), _cfg(size="S", kernel_size=3, heads={"a": NS(out_channels=2, num_blocks=-1)}),
+    _cfg(size="S", kernel_size=3, heads={"a": NS(out_channels=2, hidden_channels=64)}),
+    _cfg(size="S", kernel_size=3, heads=HEADS, primary="nope"),
+]
+
+
+def _builders():
+    import pytorch_connectomics_b200.architectures as A
+    R = ref_loader.ref_mednext_models()
+    return {"mednext": (R.build_mednext, A.get_architecture_builder("mednext")),
+            "mednext_custom": (R.build_mednext_custom, A.get_architecture_builder("mednext_custom"))}
+
+
+@pytest.mark.parametrize("i", range(len(GOOD)))
+def test_built_modules_match_the_real_builders(i):
+    cfg = GOOD[i]
+    real_fn, ours_fn = _builders()[cfg.model.arch.type]
+    torch.manual_seed(0)
+    real = real_fn(cfg)
+    ours = ours_fn(cfg)
+    want, got = _describe(real), _describe(ours)
+    assert want == got, {k: (want[k], got[k]) for k in want if want[k] != got.get(k)}
+    ours.load_state_dict(real.state_dict(), strict=True)          # a reference checkpoint loads, and the other way round
+    real.load_state_dict(ours.state_dict(), strict=True)
+    assert getattr(real.model, "outside_block_checkpointing", False) == getattr(ours.model, "outside_block_checkpointing", False)
+
+
+@pytest.mark.parametrize("i", range(len(BAD)))
+def test_bad_configurations_fail_like_the_real_builders(i):
+    cfg = BAD[i]
+    real_fn, ours_fn = _builders()[cfg.model.arch.type]
+    want, got = _outcome(lambda: type(real_fn(cfg)).__name__), _outcome(lambda: type(ours_fn(cfg)).__name__)
+    assert want[0] != "ok", "the reference accepts this configuration; move it to GOOD"
+    assert want == got
