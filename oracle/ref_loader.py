@@ -113,3 +113,25 @@ def ref_mednext_models():
     ref_registry()
     ref_base()
     return _load("connectomics.models.architectures.mednext_models", "connectomics/models/architectures/mednext_models.py")
+
+
+def ref_monai_models():
+    """``connectomics/models/architectures/monai_models.py`` executed in place over a stand-in ``monai`` package whose
+    ``UNet`` / ``ResidualUnit`` are the ORACLE restatements (MONAI cannot be installed offline); the classes the path does
+    not use (``BasicUNet``, ``UNETR``, ``SwinUNETR``, ``UpSample``) are placeholders that raise when built."""
+    _base_stubs()
+    from . import monai_unet_oracle as UO
+
+    def _absent(name):
+        def build(*_a, **_k):
+            raise NotImplementedError(f"stand-in monai: {name} is outside the hot path")
+        return build
+
+    if "monai" not in sys.modules:
+        _stub("monai")
+        _stub("monai.networks")
+        _stub("monai.networks.blocks", ResidualUnit=UO.ResidualUnit, UpSample=_absent("UpSample"))
+        _stub("monai.networks.nets", UNet=UO.UNet, BasicUNet=_absent("BasicUNet"), UNETR=_absent("UNETR"), SwinUNETR=_absent("SwinUNETR"))
+    ref_registry()
+    ref_base()
+    return _load("connectomics.models.architectures.monai_models", "connectomics/models/architectures/monai_models.py")

@@ -93,3 +93,28 @@ def test_bad_configurations_fail_like_the_real_builders(i):
     want, got = _outcome(lambda: type(real_fn(cfg)).__name__), _outcome(lambda: type(ours_fn(cfg)).__name__)
     assert want[0] != "ok", "the reference accepts this configuration; move it to GOOD"
     assert want == got
+
+
+# ----------------------------------------------------------------------------- monai_unet (BASELINE configs[0])
+def _ucfg(filters=(16, 32, 64), input_size=(32, 64, 64), in_channels=1, out_channels=1, **monai):
+    return NS(model=NS(arch=NS(type="monai_unet"), in_channels=in_channels, out_channels=out_channels,
+                       input_size=list(input_size) if input_size else None, monai=NS(filters=list(filters), **monai)))
+
+
+UNET_GOOD = [_ucfg(num_res_units=1, kernel_size=3, norm="batch", dropout=0.0),          # tutorials/minimal.yaml
+             _ucfg(filters=(8, 16, 32, 64), in_channels=2, out_channels=3),              # defaults: 2 residual units
+             _ucfg(filters=(16, 32), num_res_units=0), _ucfg(input_size=None, spatial_dims=3, num_res_units=1)]
+
+
+@pytest.mark.parametrize("i", range(len(UNET_GOOD)))
+def test_monai_unet_matches_the_real_builder(i):
+    """`build_monai_unet` (monai_models.py:197-250) executed in place over the oracle `UNet` / `ResidualUnit`: wrapper type,
+    model info, MONAI `state_dict` keys and shapes, checkpoints load both ways."""
+    import pytorch_connectomics_b200.architectures as A
+    R = ref_loader.ref_monai_models()
+    cfg = UNET_GOOD[i]
+    real, ours = R.build_monai_unet(cfg), A.get_architecture_builder("monai_unet")(cfg)
+    want, got = _describe(real), _describe(ours)
+    assert want == got, {k: (want[k], got[k]) for k in want if want[k] != got.get(k)}
+    ours.load_state_dict(real.state_dict(), strict=True)
+    real.load_state_dict(ours.state_dict(), strict=True)
