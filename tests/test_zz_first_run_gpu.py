@@ -216,3 +216,53 @@ def test_input_volume_gradient_matches_oracle():
         assert err < 5e-2, err
     # parameters still get their gradients in the same pass
     assert net.stem.weight.grad is not None and float(net.stem.weight.grad.abs().sum()) > 0
+
+
+# ----------------------------------------------------------------------------- multi-head wrapper vs the REAL reference wrapper
+def test_multihead_wrapper_matches_the_real_reference_wrapper():
+    """`tests/golden/multihead_golden.npz`: outputs of every head and the gradients of all 168 trained parameters from the
+    REAL `MedNeXtMultiHeadWrapper` / `MedNeXtTaskHead` (mednext_models.py:129-273, executed in place over the oracle trunk,
+    fp32 CPU; `oracle/make_multihead_goldens.py`).  Weights are a function of the parameter names, so this package's module is
+    filled identically.  bf16 compute against an fp32 reference: rel-L2 2e-2 on outputs, 5e-2 on gradients (norm and a random
+    projection of every gradient, seven of them element-wise), gradients that are ~0 by construction measured against the
+    largest gradient norm."""
+    import os
+    from conftest import GOLDEN
+    from oracle import make_multihead_goldens as G
+    from pytorch_connectomics_b200.architectures import build_model
+    gold = np.load(os.path.join(GOLDEN, "multihead_golden.npz"))
+    net = build_model(G.make_cfg()).train()
+    G.fill_deterministic(net)
+    net.to(DEV)
+    x, g = G.inputs()
+    out = net(x.to(DEV))["output"]
+    assert set(out) == set(G.HEADS)
+    for k in G.HEADS:
+        want = torch.from_numpy(gold[f"out_{k}"])
+        err = float((out[k].detach().float().cpu() - want).norm() / want.norm())
+        print(f"head {k}: rel-L2 vs the real wrapper {err:.3e}")
+        assert err < 2e-2, (k, err)
+    sum((out[k].float() * g[k].to(DEV)).sum() for k in G.HEADS).backward()
+    params = dict(net.named_parameters())
+    names, norms, dots = list(gold["grad_names"]), gold["grad_norms"], gold["grad_dots"]
+    top = float(norms.max())
+    assert set(names) == {n for n, p in params.items() if p.grad is not None}
+    worst_norm, worst_dot = (0.0, ""), (0.0, "")
+    for name, norm, dot in zip(names, norms, dots):
+        grad = params[str(name)].grad.float().cpu()
+        scale = max(float(norm), 1e-3 * top)
+        worst_norm = max(worst_norm, (abs(float(grad.norm()) - float(norm)) / scale, str(name)))
+        # <grad, probe> with a unit-variance probe: an error vector d moves it by ~N(0, |d|^2), so |delta| / |grad| is the
+        # relative error of the gradient up to a factor of a few (4 sigma allowed)
+        delta = abs(float((grad * G.probe(str(name), grad.shape)).sum()) - float(dot))
+        worst_dot = max(worst_dot, (delta / scale, str(name)))
+    print(f"worst gradient norm error vs the real wrapper {worst_norm[0]:.3e} ({worst_norm[1]}); "
+          f"worst projection error {worst_dot[0]:.3e} ({worst_dot[1]})")
+    assert worst_norm[0] < 5e-2, worst_norm
+    assert worst_dot[0] < 2e-1, worst_dot
+    for key in gold.files:
+        if key.startswith("grad::"):
+            want = torch.from_numpy(gold[key])
+            got = params[key[6:]].grad.float().cpu()
+            err = float((got - want).norm() / max(float(want.norm()), 1e-3 * top))
+            assert err < 5e-2, (key, err)
