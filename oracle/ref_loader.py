@@ -48,7 +48,8 @@ def _base_stubs():
     c = os.path.join(REF_ROOT, "connectomics")
     _stub("connectomics", c)
     _stub("connectomics.config")
-    _stub("connectomics.config.hardware", resolve_accelerator_type=lambda requested="auto": "cpu")
+    _stub("connectomics.config.hardware", resolve_accelerator_type=lambda requested="auto": "cpu",
+          empty_accelerator_cache=lambda *a, **k: None)
     _stub("connectomics.inference", os.path.join(c, "inference"))
     _stub("connectomics.models", os.path.join(c, "models"))
     _stub("connectomics.models.architectures", os.path.join(c, "models", "architectures"))
@@ -135,3 +136,22 @@ def ref_monai_models():
     ref_registry()
     ref_base()
     return _load("connectomics.models.architectures.monai_models", "connectomics/models/architectures/monai_models.py")
+
+
+def ref_tta():
+    """``connectomics/inference/tta.py`` (the REAL ``TTAPredictor``) with its real dependencies ``tta_affinity.py``,
+    ``tta_combinations.py``, ``tta_ensemble.py``, ``window.py``, ``utils/{channel_slices,model_outputs}.py``,
+    ``data/processing/affinity.py``; the one symbol it takes from the config package (``empty_accelerator_cache``) is a no-op."""
+    _base_stubs()
+    c = os.path.join(REF_ROOT, "connectomics")
+    _stub("connectomics.utils", os.path.join(c, "utils"))
+    _load("connectomics.utils.channel_slices", "connectomics/utils/channel_slices.py")
+    _load("connectomics.utils.model_outputs", "connectomics/utils/model_outputs.py")
+    _stub("connectomics.data", os.path.join(c, "data"))
+    _stub("connectomics.data.processing", os.path.join(c, "data", "processing"))
+    _load("connectomics.data.processing.affinity", "connectomics/data/processing/affinity.py")
+    ref_window()
+    _load("connectomics.inference.tta_combinations", "connectomics/inference/tta_combinations.py")
+    _load("connectomics.inference.tta_affinity", "connectomics/inference/tta_affinity.py")
+    _load("connectomics.inference.tta_ensemble", "connectomics/inference/tta_ensemble.py")
+    return _load("connectomics.inference.tta", "connectomics/inference/tta.py")

@@ -50,15 +50,28 @@ def install(monkeypatch) -> None:
 
 
 def oracle_ensemble_predict(self, images, network_fn):
-    """``TTAEnsemble.predict`` with the fold kernels replaced by ``oracle/tta_oracle.py::tta_predict``; the configuration
-    resolvers are the product's own."""
+    """``TTAEnsemble.predict`` with the fold kernels replaced by the oracle chain of ``oracle/tta_oracle.py`` (view ->
+    network -> inverse view -> activations incl. softmax groups -> channel selection -> output dtype -> running mean / min /
+    max); the configuration resolvers are the product's own."""
     from oracle import tta_oracle as TO
     from pytorch_connectomics_b200.inference.tta import (_resolve_ensemble_mode_map, resolve_activation_specs,
                                                          resolve_channel_indices)
     combos = self.combinations(images.dim())
-    n_raw = int(network_fn(images).shape[1])
-    codes, scales, _ = resolve_activation_specs(self.channel_activations, n_raw)
-    sel = resolve_channel_indices(self.select_channel, num_channels=n_raw, context="inference.model.select_channel")
-    mode_cfg = getattr(self.tta_cfg, "ensemble_mode", "mean") if self.tta_cfg is not None else "mean"
-    modes = _resolve_ensemble_mode_map(mode_cfg, n_raw if sel is None else len(sel))
-    return TO.tta_predict(images, network_fn, combos, modes, codes, scales, sel, self.output_dtype or torch.float32)
+    acc, modes = None, None
+    for n_prev, (flip_axes, plane, k) in enumerate(combos):
+        pred = TO.invert_view(network_fn(TO.view(images, flip_axes, plane, k)), flip_axes, plane, k)
+        n_raw = int(pred.shape[1])
+        codes, scales, groups = resolve_activation_specs(self.channel_activations, n_raw)
+        sel = resolve_channel_indices(self.select_channel, num_channels=n_raw, context="inference.model.select_channel")
+        t = pred.clone()
+        done = set()
+        for c in range(n_raw):
+            if codes[c] == 4 and tuple(groups[c]) not in done:          # softmax over the spec's channel list, once
+                done.add(tuple(groups[c]))
+                t[:, groups[c]] = torch.softmax(pred[:, groups[c]], dim=1)
+        t = TO.apply_preprocessing(t, [0 if c == 4 else c for c in codes], scales, sel, self.output_dtype or torch.float32)
+        if modes is None:
+            mode_cfg = getattr(self.tta_cfg, "ensemble_mode", "mean") if self.tta_cfg is not None else "mean"
+            modes = _resolve_ensemble_mode_map(mode_cfg, int(t.shape[1]))
+        acc = TO.fold(acc, t, modes, n_prev)
+    return acc

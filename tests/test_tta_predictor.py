@@ -163,7 +163,7 @@ def test_predict_glue_against_the_oracle_chain(monkeypatch):
         got = p.predict(x[0, 0])                     # (D, H, W) in
         assert got.shape == (1, 2, 6, 8, 8) and torch.equal(got, want)
         assert p.channel_activation_types == ["tanh", "sigmoid"]
-    assert len(calls) == len(combos) + 1             # one engine call per view (+ the stand-in's channel probe)
+    assert len(calls) == len(combos)                 # one engine call per view
     mask = (torch.rand(6, 8, 8) > 0.4).float()
     m = mask[None, None]
     masked = TTAPredictor(cfg, None, net).predict(x, mask=[[mask.numpy()]])          # collated container around the mask
@@ -217,3 +217,91 @@ def test_lazy_seam_through_the_predictor_on_cpu_doubles(tmp_path, monkeypatch):
     cfg.inference.model.channel_activations, cfg.inference.model.select_channel = None, None
     plain = Z.lazy_predict_volume(cfg, net, str(tmp_path / "v.npy"), mask_path=str(tmp_path / "m.npy"), device="cpu")
     assert torch.allclose(plain, raw * m, atol=2e-6)
+
+
+# ----------------------------------------------------------------------------- against the REAL TTAPredictor (tta.py)
+def _real_tta():
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("/root/reference is only present in the build container")
+    return ref_loader.ref_tta()
+
+
+_ACTS = [dict(channels="0:2", activation="sigmoid"), dict(channels="2:3", activation="tanh")]
+_CASES = {
+    "flips_mean": dict(tta=dict(enabled=True, flip_axes="all", rotation90_axes=None, rotate90_k=None, ensemble_mode="mean"), acts=_ACTS),
+    "rot_modes_select": dict(tta=dict(enabled=True, flip_axes=[[0], [1, 2]], rotation90_axes=[[1, 2]], rotate90_k=[0, 1, 3],
+                                      ensemble_mode=[["0:1", "min"], ["1:2", "max"]]), acts=_ACTS, select=[2, 0]),
+    "softmax_scale": dict(tta=dict(enabled=True, flip_axes=[[2]], rotation90_axes=None, rotate90_k=None, ensemble_mode="max"),
+                          acts=[dict(channels=[0, 1], activation="softmax"), dict(channels="2", activation="scale_sigmoid:0.5")], select="1:"),
+    "single_view": dict(tta=dict(enabled=True, flip_axes=None, rotation90_axes=None, rotate90_k=None, ensemble_mode="mean"), acts=_ACTS),
+    "disabled_fp16": dict(tta=dict(enabled=False), acts=_ACTS, odt="float16"),
+    "no_activations": dict(tta=dict(enabled=True, flip_axes=[[1]], rotation90_axes=None, rotate90_k=None, ensemble_mode="mean"), acts=None),
+}
+
+
+@pytest.mark.parametrize("case", sorted(_CASES))
+@pytest.mark.parametrize("with_mask", [False, True])
+def test_predictor_equals_the_real_tta_predictor(case, with_mask, monkeypatch):
+    """This package's `TTAPredictor` (fold kernels replaced by the oracle chain, `tests/cpu_doubles.py`) against the REAL
+    `connectomics/inference/tta.py::TTAPredictor` executed in place, same config object, same forward: equal predictions
+    (views, activations incl. softmax / scale_sigmoid, channel selection, per-channel ensemble modes, output dtype), equal
+    `channel_activation_types`, equal masked result incl. the tanh fill."""
+    from oracle import tta_oracle as O
+    from pytorch_connectomics_b200.inference import tta as T
+    R = _real_tta()
+    monkeypatch.setattr(T.TTAEnsemble, "predict", _oracle_ensemble_predict)
+    spec = _CASES[case]
+    cfg = _cfg(NS(apply_mask=True, patch_first_local=False, distributed_sharding=False, **spec["tta"]), acts=spec.get("acts"),
+               select=spec.get("select"), odt=spec.get("odt"))
+    net = O.ramp_network(3)
+    rs = np.random.RandomState(3)
+    x = torch.from_numpy(rs.rand(1, 1, 6, 8, 8).astype(np.float32))
+    mask = torch.from_numpy((rs.rand(6, 8, 8) > 0.4).astype(np.float32)) if with_mask else None
+    want = R.TTAPredictor(cfg, None, net).predict(x.clone(), mask=mask)
+    mine = TTAPredictor(cfg, None, net)
+    got = mine.predict(x.clone(), mask=mask)
+    assert got.shape == want.shape and got.dtype == want.dtype
+    tol = 2e-3 if want.dtype == torch.float16 else 2e-6
+    assert torch.allclose(got.float(), want.float(), rtol=tol, atol=tol), float((got.float() - want.float()).abs().max())
+    ref_types = R.TTAPredictor(cfg, None, net)
+    ref_types.predict(x.clone())
+    norm = lambda ts: None if ts is None else [None if t is None else t.split(":")[0] for t in ts]
+    assert norm(mine.channel_activation_types) == norm(ref_types.channel_activation_types)
+
+
+def test_predictor_with_the_real_sliding_engine_and_named_heads(monkeypatch):
+    """Volume-first TTA through a sliding-window engine and named-head selection, both predictors driving the REAL
+    `EagerSlidingWindowEngine` of `window.py` on the CPU."""
+    from oracle import ref_loader, tta_oracle as O
+    from pytorch_connectomics_b200.inference import tta as T
+    R = _real_tta()
+    W = ref_loader.ref_window()
+    monkeypatch.setattr(T.TTAEnsemble, "predict", _oracle_ensemble_predict)
+    tta = NS(enabled=True, flip_axes="all", rotation90_axes=None, rotate90_k=None, ensemble_mode="mean", apply_mask=True,
+             patch_first_local=False, distributed_sharding=False)
+    cfg = _cfg(tta, acts=_ACTS, select=[2, 0])
+    cfg.model.heads = {"aff": NS(out_channels=3), "sdt": NS(out_channels=1)}
+    cfg.model.primary_head = "aff"
+    net = O.ramp_network(3)
+    heads = lambda t: {"output": {"aff": net(t), "sdt": net(t)[:, :1] * 2.0}}
+    eng_kw = dict(roi_size=(4, 8, 8), sw_batch_size=2, overlap=0.5, mode="constant", padding_mode="constant", cval=0.0,
+                  sw_device=None, output_device=None)
+    x = torch.from_numpy(np.random.RandomState(4).rand(1, 1, 10, 8, 8).astype(np.float32))
+    want = R.TTAPredictor(cfg, W.EagerSlidingWindowEngine(**eng_kw), heads).predict(x.clone())
+    got = TTAPredictor(cfg, W.EagerSlidingWindowEngine(**eng_kw), heads).predict(x.clone())
+    assert torch.allclose(got, want, rtol=2e-6, atol=2e-6)
+    # an explicit head for one call: activations are written for the 3-channel head, so ask for it by name
+    want = R.TTAPredictor(cfg, None, heads).predict(x.clone(), requested_head="aff")
+    got = TTAPredictor(cfg, None, heads).predict(x.clone(), requested_head="aff")
+    assert torch.allclose(got, want, rtol=2e-6, atol=2e-6)
+
+    def outcome(fn):
+        try:
+            return ("ok", tuple(fn().shape))
+        except (ValueError, TypeError) as e:
+            return (type(e).__name__, str(e))
+
+    for bad in ("nope", "", "aff,sdt"):
+        assert outcome(lambda: R.TTAPredictor(cfg, None, heads).predict(x.clone(), requested_head=bad)) == \
+            outcome(lambda: TTAPredictor(cfg, None, heads).predict(x.clone(), requested_head=bad)), bad
