@@ -305,3 +305,23 @@ def test_predictor_with_the_real_sliding_engine_and_named_heads(monkeypatch):
     for bad in ("nope", "", "aff,sdt"):
         assert outcome(lambda: R.TTAPredictor(cfg, None, heads).predict(x.clone(), requested_head=bad)) == \
             outcome(lambda: TTAPredictor(cfg, None, heads).predict(x.clone(), requested_head=bad)), bad
+
+
+@pytest.mark.parametrize("case", ["volume_first", "direct_rot", "disabled"])
+def test_predictor_reproduces_the_real_predictor_goldens_on_cpu(case, monkeypatch):
+    """`tests/golden/tta_predictor_goldens.npz` (REAL `TTAPredictor` + REAL `EagerSlidingWindowEngine`, bump blending, mask,
+    `oracle/make_tta_predictor_goldens.py`).  This package's predictor with the oracle ensemble, driving the real engine on
+    the CPU, reproduces the volume-first / direct / disabled goldens; the patch-first golden needs the kernels (GPU test)."""
+    import os
+    from conftest import GOLDEN
+    from oracle import make_tta_predictor_goldens as G, ref_loader, tta_oracle as O
+    from pytorch_connectomics_b200.inference import tta as T
+    if not ref_loader.available():
+        pytest.skip("the real window.py engine is only present in the build container")
+    monkeypatch.setattr(T.TTAEnsemble, "predict", _oracle_ensemble_predict)
+    gold = np.load(os.path.join(GOLDEN, "tta_predictor_goldens.npz"))
+    spec = G.CASES[case]
+    x, mask = G.inputs()
+    engine = ref_loader.ref_window().EagerSlidingWindowEngine(sw_device=None, output_device=None, **G.ENGINE) if spec["engine"] else None
+    got = TTAPredictor(G.make_cfg(spec), engine, O.ramp_network(3)).predict(x, mask=mask if spec["mask"] else None)
+    assert torch.allclose(got, torch.from_numpy(gold[case]), rtol=2e-6, atol=2e-6)

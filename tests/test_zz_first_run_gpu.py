@@ -266,3 +266,29 @@ def test_multihead_wrapper_matches_the_real_reference_wrapper():
             got = params[key[6:]].grad.float().cpu()
             err = float((got - want).norm() / max(float(want.norm()), 1e-3 * top))
             assert err < 5e-2, (key, err)
+
+
+# ----------------------------------------------------------------------------- TTAPredictor vs goldens of the REAL predictor
+@pytest.mark.parametrize("case", ["volume_first", "patch_first", "direct_rot", "disabled"])
+def test_predictor_matches_the_real_tta_predictor_goldens(case):
+    """`tests/golden/tta_predictor_goldens.npz`: the REAL `connectomics/inference/tta.py::TTAPredictor` driving the REAL
+    `EagerSlidingWindowEngine` (fp32 CPU; `oracle/make_tta_predictor_goldens.py`) — volume-first flips with a mask and the tanh
+    fill, patch-first-local with rotations and per-channel min / mean, a direct softmax ensemble, the disabled-TTA path.
+    Here: this package's predictor, engine and fold kernels on the GPU.  Not bit-exact only where `exp` is evaluated (bump map,
+    sigmoid / tanh / softmax): 5e-6 absolute on values in [-1, 1]."""
+    import os
+    from conftest import GOLDEN
+    from oracle import make_tta_predictor_goldens as G
+    from oracle import tta_oracle as TO
+    from pytorch_connectomics_b200.inference.window import EagerSlidingWindowEngine
+    gold = np.load(os.path.join(GOLDEN, "tta_predictor_goldens.npz"))
+    spec = G.CASES[case]
+    x, mask = G.inputs()
+    engine = EagerSlidingWindowEngine(sw_device=None, output_device=None, **G.ENGINE) if spec["engine"] else None
+    pred = TTAPredictor(G.make_cfg(spec), engine, TO.ramp_network(3))
+    got = pred.predict(x.to(DEV), mask=mask.to(DEV) if spec["mask"] else None)
+    want = torch.from_numpy(gold[case])
+    assert got.shape == want.shape
+    err = float((got.float().cpu() - want).abs().max())
+    print(f"{case}: max abs difference to the real predictor {err:.2e}")
+    assert err <= 5e-6, err
