@@ -155,3 +155,48 @@ def ref_tta():
     _load("connectomics.inference.tta_affinity", "connectomics/inference/tta_affinity.py")
     _load("connectomics.inference.tta_ensemble", "connectomics/inference/tta_ensemble.py")
     return _load("connectomics.inference.tta", "connectomics/inference/tta.py")
+
+
+class _FakeH5File:
+    """Stand-in for ``h5py.File(path, "r")`` over a ``.npy`` file saved next to it (``<path>.npy``): one dataset ``main``.
+    h5py is not installable offline; the reference's lazy accessor only needs ``keys()``, ``[name]`` (shape + slicing) and
+    ``close()`` from it."""
+
+    def __init__(self, path, mode="r"):
+        import numpy as np
+        self._data = np.load(str(path) + ".npy", mmap_mode="r")
+
+    def keys(self):
+        return ["main"]
+
+    def __getitem__(self, name):
+        return self._data
+
+    def close(self):
+        self._data = None
+
+
+def ref_lazy():
+    """``connectomics/inference/lazy.py`` — the REAL lazy sliding-window engine (``_lazy_sliding_window``,
+    ``lazy_predict_region / volume``, ``LazyVolumeAccessor``, ``_build_accessor``) with the real ``tta.py``,
+    ``lazy_distributed.py``, ``window.py`` and ``data/processing/misc.py``.  What is stood in: ``h5py`` (a ``.npy``-backed
+    file object, above), ``data/io/io.py`` (format detection by extension; its tiff helpers are never reached) and
+    ``smart_normalize`` (raises: the tests use ``normalize: none``)."""
+    ref_tta()
+    c = os.path.join(REF_ROOT, "connectomics")
+    if "h5py" not in sys.modules:
+        _stub("h5py", File=_FakeH5File)
+
+    def _no(name):
+        def fn(*_a, **_k):
+            raise NotImplementedError(f"stand-in: {name} is outside the hot path")
+        return fn
+
+    _stub("connectomics.data.augmentation")
+    _stub("connectomics.data.augmentation.augment_ops", smart_normalize=_no("smart_normalize"))
+    _stub("connectomics.data.io")
+    _stub("connectomics.data.io.io", _detect_format=lambda p: "h5" if str(p).endswith((".h5", ".hdf5")) else "unknown",
+          _get_tiff_volume_shape=_no("_get_tiff_volume_shape"), _tiff_series_are_stackable=_no("_tiff_series_are_stackable"))
+    _load("connectomics.data.processing.misc", "connectomics/data/processing/misc.py")
+    _load("connectomics.inference.lazy_distributed", "connectomics/inference/lazy_distributed.py")
+    return _load("connectomics.inference.lazy", "connectomics/inference/lazy.py")

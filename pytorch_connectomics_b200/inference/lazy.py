@@ -57,7 +57,9 @@ class ArrayVolumeAccessor:
     Same surface the tile loop uses on ``LazyVolumeAccessor``: context manager, ``padded_spatial_shape``,
     ``channel_count``, ``read_patch`` (fp32 ``[C, *patch_size]``, outer padding as ``lazy.py:852-904``), ``load_full``."""
 
-    def __init__(self, data, *, kind: str = "image", binarize: bool = False, threshold: float = 0.0):
+    def __init__(self, data, *, kind: str = "image", binarize: bool = False, threshold: float = 0.0,
+                 context_pad: Sequence[Sequence[int]] = ((0, 0), (0, 0), (0, 0)), context_pad_mode: str = "constant",
+                 transpose_axes: Sequence[int] = ()):
         if isinstance(data, torch.Tensor):
             if data.dim() == 5:
                 if data.shape[0] != 1:
@@ -82,8 +84,21 @@ class ArrayVolumeAccessor:
         self.binarize = bool(binarize)
         self.threshold = float(threshold)
         self.channel_count = int(ref.shape[0])
-        self.padded_spatial_shape = tuple(int(v) for v in ref.shape[1:])
-        self.transformed_spatial_shape = self.padded_spatial_shape
+        # data_transform.val_transpose (lazy.py:922): the logical volume is the stored one with its spatial axes permuted
+        self.transpose_axes = tuple(int(a) for a in (transpose_axes or ()))
+        if self.transpose_axes and sorted(self.transpose_axes) != [0, 1, 2]:
+            raise ValueError(f"transpose_axes must be a permutation of (0, 1, 2), got {self.transpose_axes}")
+        stored = tuple(int(v) for v in ref.shape[1:])
+        self.transformed_spatial_shape = tuple(stored[a] for a in self.transpose_axes) if self.transpose_axes else stored
+        # data_transform.pad_size / pad_mode (lazy.py:924-929): the context border the test-time transform adds around
+        # the volume; window coordinates, the reference shape and the prediction all live in the PADDED frame
+        self.context_pad = tuple((int(b), int(a)) for b, a in context_pad)
+        mode = str(context_pad_mode).lower()
+        self.context_pad_mode = "edge" if mode == "replicate" else mode
+        if self.context_pad_mode not in ("constant", "reflect", "edge"):
+            raise ValueError(f"Unsupported context pad mode '{context_pad_mode}'.")
+        self.padded_spatial_shape = tuple(self.transformed_spatial_shape[a] + self.context_pad[a][0] + self.context_pad[a][1]
+                                          for a in range(3))
 
     def __enter__(self):
         return self
@@ -97,15 +112,52 @@ class ArrayVolumeAccessor:
 
     def as_tensor(self) -> Optional[torch.Tensor]:
         """``[1, C, D, H, W]`` view when the whole volume is a tensor (device-resident fast path), else ``None``."""
-        if self._tensor is not None and not self.binarize:
+        plain = not self.binarize and not self.transpose_axes and not any(b or a for b, a in self.context_pad)
+        if self._tensor is not None and plain:
             return self._tensor.unsqueeze(0)
         return None
 
     def _crop(self, lo, hi) -> np.ndarray:
-        sl = (slice(None),) + tuple(slice(int(a), int(b)) for a, b in zip(lo, hi))
+        """[C, *box] of the LOGICAL (transposed, unpadded) volume"""
+        if self.transpose_axes:            # logical axis i is stored axis transpose_axes[i]
+            raw = [None, None, None]
+            for i, a in enumerate(self.transpose_axes):
+                raw[a] = slice(int(lo[i]), int(hi[i]))
+            sl = (slice(None), *raw)
+        else:
+            sl = (slice(None),) + tuple(slice(int(a), int(b)) for a, b in zip(lo, hi))
         if self._tensor is not None:
-            return self._tensor[sl].detach().to("cpu", torch.float32).numpy()
-        return np.asarray(self._array[sl], dtype=np.float32)
+            out = self._tensor[sl].detach().to("cpu", torch.float32).numpy()
+        else:
+            out = np.asarray(self._array[sl], dtype=np.float32)
+        return np.transpose(out, (0, *[a + 1 for a in self.transpose_axes])) if self.transpose_axes else out
+
+    def _read_padded_inner(self, lo, hi) -> np.ndarray:
+        """``lazy.py:794-850``: the box [lo, hi) of the PADDED volume — every padded index is mapped to the source index the
+        context padding takes its value from (reflect without edge repeat, edge clamp, or zero outside for constant)."""
+        mapped, valid, b0, b1 = [], [], [], []
+        for a in range(3):
+            idx = np.arange(int(lo[a]), int(hi[a]), dtype=np.int64) - self.context_pad[a][0]
+            n = self.transformed_spatial_shape[a]
+            if self.context_pad_mode == "reflect" and n > 1:
+                period = 2 * n - 2
+                m = np.abs(idx) % period
+                m = np.where(m < n, m, period - m)
+                ok = np.ones(idx.shape, dtype=bool)
+            elif self.context_pad_mode == "reflect":
+                m, ok = np.zeros_like(idx), np.ones(idx.shape, dtype=bool)
+            else:
+                m = np.clip(idx, 0, max(n - 1, 0))
+                ok = np.ones(idx.shape, dtype=bool) if self.context_pad_mode == "edge" else (idx >= 0) & (idx < n)
+            mapped.append(m); valid.append(ok)
+            b0.append(int(m.min()) if m.size else 0); b1.append(int(m.max()) + 1 if m.size else 0)
+        region = self._crop(b0, b1)
+        out = region
+        for a in range(3):
+            out = np.take(out, mapped[a] - b0[a], axis=a + 1)
+        if self.context_pad_mode == "constant":
+            out = out * (valid[0][:, None, None] & valid[1][None, :, None] & valid[2][None, None, :])[None].astype(out.dtype)
+        return out
 
     def read_patch(self, location, patch_size, *, outer_pad_mode: str, outer_pad_value: float) -> np.ndarray:
         start = tuple(int(v) for v in location)
@@ -117,7 +169,7 @@ class ArrayVolumeAccessor:
             inner = np.zeros((self.channel_count, 0, 0, 0), dtype=np.float32)
             return np.full((self.channel_count, *size), outer_pad_value, dtype=np.float32) if str(outer_pad_mode) == "constant" \
                 else np.zeros((self.channel_count, *size), dtype=np.float32)
-        inner = self._crop(lo, hi)
+        inner = self._read_padded_inner(lo, hi) if (any(b or a for b, a in self.context_pad)) else self._crop(lo, hi)
         pads = [(max(0, -start[i]), max(0, end[i] - self.padded_spatial_shape[i])) for i in range(3)]
         patch = _pad_channel_first(inner, pads, mode=outer_pad_mode, constant_value=outer_pad_value)
         if self.binarize:
@@ -125,7 +177,23 @@ class ArrayVolumeAccessor:
         return patch.astype(np.float32, copy=False)
 
     def load_full(self) -> np.ndarray:
-        return self._crop((0, 0, 0), self.padded_spatial_shape)
+        """``lazy.py:906-918``: the transformed volume WITHOUT the context border"""
+        full = self._crop((0, 0, 0), self.transformed_spatial_shape)
+        return (full > self.threshold).astype(np.float32) if self.binarize else full
+
+
+def _get_padsize(pad_size, ndim: int = 3):
+    """``data/processing/misc.py:20-41`` get_padsize: int | [p] | [pz, py, px] | [z0, z1, y0, y1, x0, x1] -> per-axis pairs"""
+    if isinstance(pad_size, int):
+        return tuple((pad_size, pad_size) for _ in range(ndim))
+    vals = list(pad_size)
+    if len(vals) not in (1, ndim, 2 * ndim):
+        raise ValueError(f"pad_size length must be 1, {ndim}, or {2 * ndim}, got {len(vals)}")
+    if len(vals) == 1:
+        return tuple((vals[0], vals[0]) for _ in range(ndim))
+    if len(vals) == ndim:
+        return tuple((v, v) for v in vals)
+    return tuple((vals[2 * i], vals[2 * i + 1]) for i in range(ndim))
 
 
 _ACCESSOR_FACTORIES: List[Callable[..., Any]] = []
@@ -144,19 +212,30 @@ def build_accessor(cfg, source, *, kind: str = "image", mode: str = "test"):
         if acc is not None:
             return acc
     binarize, threshold = False, 0.0
+    data_cfg = getattr(cfg, "data", None)
+    dt = getattr(data_cfg, "data_transform", None)
     if kind == "mask":
-        data_cfg = getattr(cfg, "data", None)
-        mask_cfg = getattr(data_cfg, "mask_transform", None) or getattr(data_cfg, "data_transform", None)
+        mask_cfg = getattr(data_cfg, "mask_transform", None) or dt
         binarize = bool(getattr(mask_cfg, "binarize", False))
         threshold = float(getattr(mask_cfg, "threshold", 0.0))
     if hasattr(source, "read_patch") and hasattr(source, "padded_spatial_shape"):
         return source
+    # lazy.py:922-929: transpose, context border (image: data_transform.pad_mode, default reflect; mask: zeros)
+    kw = dict(kind=kind, binarize=binarize, threshold=threshold,
+              transpose_axes=tuple(getattr(dt, "val_transpose", None) or ()),
+              context_pad=_get_padsize(getattr(dt, "pad_size", [0, 0, 0])) if kind in ("image", "mask") else ((0, 0),) * 3,
+              context_pad_mode=getattr(dt, "pad_mode", "reflect") if kind == "image" else "constant")
+    for key, what in (("image_transform", "normalize"),):
+        mode_ = getattr(getattr(data_cfg, key, None), what, "none") if kind == "image" else "none"
+        if str(mode_ or "none").lower() != "none":
+            raise NotImplementedError(f"pcb200 lazy inference: data.image_transform.normalize={mode_!r} (smart_normalize) is a "
+                                      "data-pipeline transform outside this path; normalise the volume beforehand")
     if isinstance(source, (torch.Tensor, np.ndarray)):
-        return ArrayVolumeAccessor(source, kind=kind, binarize=binarize, threshold=threshold)
+        return ArrayVolumeAccessor(source, **kw)
     path = os.fspath(source)
     ext = os.path.splitext(path)[1].lower()
     if ext == ".npy":
-        return ArrayVolumeAccessor(np.load(path, mmap_mode="r"), kind=kind, binarize=binarize, threshold=threshold)
+        return ArrayVolumeAccessor(np.load(path, mmap_mode="r"), **kw)
     if ext in (".h5", ".hdf5"):
         try:
             import h5py  # noqa: F401
@@ -164,7 +243,7 @@ def build_accessor(cfg, source, *, kind: str = "image", mode: str = "test"):
             raise RuntimeError(f"pcb200 lazy inference: reading {path} needs h5py, which is not installed; pass a .npy "
                                "volume, an array, or register_accessor_factory(...)") from exc
         f = h5py.File(path, "r")
-        return ArrayVolumeAccessor(f[next(iter(f.keys()))], kind=kind, binarize=binarize, threshold=threshold)
+        return ArrayVolumeAccessor(f[next(iter(f.keys()))], **kw)
     raise ValueError(f"pcb200 lazy inference: unsupported volume source {source!r}; expected a .npy path, a tensor/array "
                      "or an accessor object (register_accessor_factory adds formats).")
 
