@@ -176,16 +176,32 @@ class _FakeH5File:
         self._data = None
 
 
+class fake_h5py:
+    """``with fake_h5py():`` — the stand-in is visible as ``h5py`` ONLY inside the block (the real accessor imports it lazily
+    when it opens a file), so nothing else in the process — this package's artifact writer probes for h5py — ever sees it."""
+
+    def __enter__(self):
+        self._old = sys.modules.get("h5py")
+        m = types.ModuleType("h5py")
+        m.File = _FakeH5File
+        sys.modules["h5py"] = m
+        return m
+
+    def __exit__(self, *exc):
+        if self._old is None:
+            sys.modules.pop("h5py", None)
+        else:
+            sys.modules["h5py"] = self._old
+        return False
+
+
 def ref_lazy():
     """``connectomics/inference/lazy.py`` — the REAL lazy sliding-window engine (``_lazy_sliding_window``,
     ``lazy_predict_region / volume``, ``LazyVolumeAccessor``, ``_build_accessor``) with the real ``tta.py``,
     ``lazy_distributed.py``, ``window.py`` and ``data/processing/misc.py``.  What is stood in: ``h5py`` (a ``.npy``-backed
-    file object, above), ``data/io/io.py`` (format detection by extension; its tiff helpers are never reached) and
+    file object, visible only inside ``with fake_h5py():``), ``data/io/io.py`` (format detection by extension; its tiff helpers are never reached) and
     ``smart_normalize`` (raises: the tests use ``normalize: none``)."""
     ref_tta()
-    c = os.path.join(REF_ROOT, "connectomics")
-    if "h5py" not in sys.modules:
-        _stub("h5py", File=_FakeH5File)
 
     def _no(name):
         def fn(*_a, **_k):

@@ -84,10 +84,11 @@ def test_lazy_seam_equals_the_real_lazy_engine(name, tmp_path, monkeypatch):
     cfg = _cfg(**case["cfg"])
     kw = dict(mask_path=str(tmp_path / "m.h5") if mask is not None else None, device="cpu")
     region = case.get("region")
-    if region is None:
-        want = Zref.lazy_predict_volume(cfg, case["fwd"], str(tmp_path / "v.h5"), **kw)
-    else:
-        want = Zref.lazy_predict_region(cfg, case["fwd"], str(tmp_path / "v.h5"), region_start=region[0], region_stop=region[1], **kw)
+    with ref_loader.fake_h5py():
+        if region is None:
+            want = Zref.lazy_predict_volume(cfg, case["fwd"], str(tmp_path / "v.h5"), **kw)
+        else:
+            want = Zref.lazy_predict_region(cfg, case["fwd"], str(tmp_path / "v.h5"), region_start=region[0], region_stop=region[1], **kw)
     cpu_doubles.install(monkeypatch)
     kw_ours = dict(kw, mask_path=str(tmp_path / "m.h5.npy") if mask is not None else None)
     if region is None:
