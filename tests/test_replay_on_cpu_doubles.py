@@ -13,7 +13,8 @@ import test_lazy_chunked_gpu as lazy_gpu
 import test_zz_first_run_gpu as first_run_gpu
 
 SKIP = {"test_lazy_sliding_window_matches_eager_inference"}      # drives EagerSlidingWindowEngine's CUDA streams directly
-ZZ = ("test_run_chunked_prediction_inference_streams_one_volume", "test_lazy_seam_runs_patches_through_the_predictor")
+ZZ = ("test_run_chunked_prediction_inference_streams_one_volume", "test_lazy_seam_runs_patches_through_the_predictor",
+      "test_lazy_seam_matches_the_real_lazy_engine_goldens")
 
 
 def _cases(module, names=None):

@@ -292,3 +292,39 @@ def test_predictor_matches_the_real_tta_predictor_goldens(case):
     err = float((got.float().cpu() - want).abs().max())
     print(f"{case}: max abs difference to the real predictor {err:.2e}")
     assert err <= 5e-6, err
+
+
+# ----------------------------------------------------------------------------- lazy seam vs goldens of the REAL lazy.py
+def _lazy_case_names():
+    from oracle import make_lazy_goldens as G
+    return sorted(G.CASES)
+
+
+@pytest.mark.parametrize("name", _lazy_case_names())
+def test_lazy_seam_matches_the_real_lazy_engine_goldens(name, tmp_path):
+    """`tests/golden/lazy_goldens.npz`: the REAL `connectomics/inference/lazy.py` (`lazy_predict_volume / region` with the real
+    accessor, predictor and window helpers, fp32 CPU; `oracle/make_lazy_goldens.py`) on 14 cases — blending modes, snap-to-edge,
+    regions, fp16 accumulators, target context, border mask, reflect edges, TTA + activations + channel selection + mask,
+    test-time context borders (reflect / edge / constant), transposes.  Here the same calls run on the GPU kernels."""
+    import os
+    from conftest import GOLDEN
+    from oracle import make_lazy_goldens as G
+    gold = np.load(os.path.join(GOLDEN, "lazy_goldens.npz"))
+    case = G.CASES[name]
+    vol, mask = G.volumes(name)
+    np.save(tmp_path / "v.npy", vol)
+    if mask is not None:
+        np.save(tmp_path / "m.npy", mask)
+    kw = dict(mask_path=str(tmp_path / "m.npy") if mask is not None else None, device=DEV)
+    cfg = G.make_cfg(**case["cfg"])
+    if case.get("region") is None:
+        got = Z.lazy_predict_volume(cfg, case["fwd"], str(tmp_path / "v.npy"), **kw)
+    else:
+        got = Z.lazy_predict_region(cfg, case["fwd"], str(tmp_path / "v.npy"), region_start=case["region"][0],
+                                    region_stop=case["region"][1], **kw)
+    want = torch.from_numpy(gold[name])
+    assert got.shape == want.shape and got.dtype == want.dtype and got.device.type == "cpu"
+    tol = 2e-3 if want.dtype == torch.float16 else 1e-5
+    err = float((got.float() - want.float()).abs().max())
+    print(f"{name}: max abs difference to the real lazy engine {err:.2e}")
+    assert err <= tol * max(1.0, float(want.float().abs().max())), err
