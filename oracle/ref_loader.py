@@ -23,8 +23,11 @@ def available() -> bool:
 
 
 def _stub(name, path=None, **attrs):
-    if name in sys.modules and not getattr(sys.modules[name], "__pcb_stub__", False):
-        return sys.modules[name]
+    if name in sys.modules:                      # a real module wins; an existing stand-in is kept and extended
+        m = sys.modules[name]
+        if getattr(m, "__pcb_stub__", False):
+            m.__dict__.update(attrs)
+        return m
     m = types.ModuleType(name)
     m.__path__ = [path] if path else []
     m.__pcb_stub__ = True
@@ -157,23 +160,79 @@ def ref_tta():
     return _load("connectomics.inference.tta", "connectomics/inference/tta.py")
 
 
+class _FakeDataset:
+    """what the reference touches on an h5py dataset: shape / dtype, slicing both ways, ``attrs``"""
+
+    def __init__(self, array, attrs):
+        self._a, self.attrs = array, attrs
+
+    shape = property(lambda self: tuple(self._a.shape))
+    dtype = property(lambda self: self._a.dtype)
+    ndim = property(lambda self: self._a.ndim)
+
+    def __getitem__(self, key):
+        return self._a[key]
+
+    def __setitem__(self, key, value):
+        self._a[key] = value
+
+    def __array__(self, dtype=None, copy=None):
+        import numpy as np
+        return np.asarray(self._a, dtype=dtype)
+
+
 class _FakeH5File:
-    """Stand-in for ``h5py.File(path, "r")`` over a ``.npy`` file saved next to it (``<path>.npy``): one dataset ``main``.
-    h5py is not installable offline; the reference's lazy accessor only needs ``keys()``, ``[name]`` (shape + slicing) and
-    ``close()`` from it."""
+    """Stand-in for ``h5py.File`` over plain files next to the path: dataset ``<path>.npy`` (+ attrs ``<path>.attrs.json``).
+    h5py is not installable offline; the reference's lazy accessor and artifact writer / reader need ``keys()``, ``[name]``,
+    ``create_dataset``, ``attrs``, the context-manager protocol and ``close()`` from it."""
 
     def __init__(self, path, mode="r"):
+        import json
         import numpy as np
-        self._data = np.load(str(path) + ".npy", mmap_mode="r")
+        self._path, self._mode, self._sets = str(path), mode, {}
+        if mode == "r":
+            attrs = {}
+            if os.path.exists(self._path + ".attrs.json"):
+                with open(self._path + ".attrs.json") as fh:
+                    attrs = json.load(fh)
+            self._sets["main"] = _FakeDataset(np.load(self._path + ".npy", mmap_mode="r"), attrs)
 
     def keys(self):
-        return ["main"]
+        return list(self._sets.keys())
+
+    def __contains__(self, name):
+        return name in self._sets
 
     def __getitem__(self, name):
-        return self._data
+        return self._sets[name]
+
+    def create_dataset(self, name, shape=None, dtype=None, data=None, chunks=None, compression=None, **_kw):
+        import numpy as np
+        if data is not None:
+            arr = np.array(data)
+            np.save(self._path + ".npy", arr)
+        else:
+            arr = np.lib.format.open_memmap(self._path + ".npy", mode="w+", dtype=np.dtype(dtype), shape=tuple(shape))
+        self._sets[name] = _FakeDataset(arr, {})
+        return self._sets[name]
 
     def close(self):
-        self._data = None
+        import json
+        if self._mode != "r":
+            for ds in self._sets.values():
+                if hasattr(ds._a, "flush"):
+                    ds._a.flush()
+                with open(self._path + ".attrs.json", "w") as fh:
+                    json.dump({k: (v if isinstance(v, (str, int, float, bool)) or v is None else str(v)) for k, v in ds.attrs.items()}, fh)
+                open(self._path, "a").close()          # the reference tests for the artifact path itself
+        self._sets = {}
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
 
 
 class fake_h5py:
@@ -216,3 +275,23 @@ def ref_lazy():
     _load("connectomics.data.processing.misc", "connectomics/data/processing/misc.py")
     _load("connectomics.inference.lazy_distributed", "connectomics/inference/lazy_distributed.py")
     return _load("connectomics.inference.lazy", "connectomics/inference/lazy.py")
+
+
+def ref_chunked():
+    """``connectomics/inference/chunked.py`` — the REAL chunked driver (``run_chunked_prediction_inference``,
+    ``_run_chunked_prediction_per_rank``, ROI filter, external shards, stitching) over the real ``lazy.py``, ``artifact.py``,
+    ``chunk_grid.py`` and ``output.py``.  Stood in: what ``output.py`` imports from the config / data packages at module level
+    (``Config``, ``DictConfig``, ``restore_prediction_to_input_space`` — names only, never called on this path) and h5py
+    (``with fake_h5py():``)."""
+    ref_lazy()
+    c = os.path.join(REF_ROOT, "connectomics")
+    if "omegaconf" not in sys.modules:
+        _stub("omegaconf", DictConfig=type("DictConfig", (), {}))
+    _stub("connectomics.config", Config=type("Config", (), {}))
+    _stub("connectomics.data.processing.nnunet_preprocess", restore_prediction_to_input_space=lambda *a, **k: None)
+    ref_chunk_grid()
+    ref_halo()
+    ref_artifact()
+    _load("connectomics.inference.chunk_grid", "connectomics/inference/chunk_grid.py")
+    _load("connectomics.inference.output", "connectomics/inference/output.py")
+    return _load("connectomics.inference.chunked", "connectomics/inference/chunked.py")

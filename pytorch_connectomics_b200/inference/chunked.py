@@ -225,13 +225,18 @@ def _run_chunked_prediction_per_rank(*, cfg, forward_fn, image_path, output_path
         for c in chunks:
             dset[(slice(None), *c.slices)] = read_prediction_artifact(_chunk_file_path(chunks_dir, c))
 
+    tc = getattr(cfg.inference, "prediction_transform", None)                 # chunked.py:409-426: the stitched volume's attrs
+    transformed = tc is not None and bool(getattr(tc, "enabled", False))
     write_prediction_artifact(output_path, None, shape=(nch, *[int(v) for v in final_shape]), dtype=dt, writer=fill,
                               metadata=build_prediction_artifact_metadata(
                                   cfg, image_path=str(image_path) if isinstance(image_path, (str, Path)) else None,
                                   checkpoint_path=checkpoint_path, output_head=requested_head, input_shape=input_shape,
                                   final_shape=final_shape, crop_pad=crop_pad, chunk_shape=chunk_shape, halo=halo,
-                                  intensity_dtype=str(dt)),
-                              compression=compression)
+                                  intensity_scale=float(getattr(tc, "intensity_scale", -1.0)) if transformed else None,
+                                  intensity_dtype=str(getattr(tc, "intensity_dtype", dt)) if transformed else str(dt),
+                                  extra={"compression": str(compression), "chunk_stitch_source": str(chunks_dir)}),
+                              compression=compression,
+                              chunks=(nch, *[max(1, min(int(h5_spatial_chunks[a]), int(final_shape[a]))) for a in range(3)]))
     return output_path
 
 
