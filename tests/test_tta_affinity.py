@@ -193,3 +193,34 @@ def test_view_sharding_covers_every_view_once_gloo(world):
     assert all(r[2] == list(range(r[0], n, world)) for r in res)
     if world == 3:      # one view over three ranks: ranks 1 and 2 have nothing to do
         assert res[0][3] is None and "empty augmentation shard" in res[1][3] and "empty augmentation shard" in res[2][3]
+
+
+def test_composed_goldens_equal_the_real_tta_predictor():
+    """The affinity goldens were composed from the real `tta_affinity.py` / `tta_ensemble.py` / `window.py` functions because
+    `tta.py` was thought not to load offline.  It does (one config-package symbol stood in), so the REAL `TTAPredictor` is run
+    here on the same inputs: its volume-first results equal the stored goldens, i.e. the composition was the reference."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("/root/reference is only present in the build container")
+    R = ref_loader.ref_tta()
+    x = torch.from_numpy(G["vf_x"])
+    offs = ["1-0-0", "0-1-0", "0-0-1", "2-0-0", "0-3-0", "0-0-3"]
+    for mode in ("deepem", "banis"):
+        cfg = _cfg(offs, mode, 6)
+        cfg.model.primary_head = None
+        cfg.inference = NS(test_time_augmentation=NS(enabled=True, flip_axes="all", rotation90_axes=[[1, 2]], rotate90_k=[0, 1],
+                                                     ensemble_mode=[["0:3", "mean"], ["3:5", "min"], ["5:", "max"]], apply_mask=True,
+                                                     patch_first_local=False, distributed_sharding=False),
+                           sliding_window=NS(keep_input_on_cpu=False),
+                           model=NS(channel_activations=[dict(channels=":", activation="sigmoid")], select_channel=None, output_dtype=None, head=None))
+        got = R.TTAPredictor(cfg, None, TO.ramp_network(6)).predict(x.clone())
+        assert np.allclose(got.numpy(), G[f"vf_{mode}"], rtol=0, atol=1e-6), mode
+    cfg = _cfg(["0-1-0", "0-0-1"], "deepem", 3, ("binary",))
+    cfg.model.primary_head = None
+    cfg.inference = NS(test_time_augmentation=NS(enabled=True, flip_axes=[[1], [2]], rotation90_axes=[[1, 2]], rotate90_k=[0, 1, 2], ensemble_mode="mean",
+                                                 apply_mask=True, patch_first_local=False, distributed_sharding=False),
+                       sliding_window=NS(keep_input_on_cpu=False),
+                       model=NS(channel_activations=[dict(channels=[1, 2], activation="softmax"), dict(channels=[0], activation="tanh")],
+                                select_channel=[2, 0, 1], output_dtype=None, head=None))
+    got = R.TTAPredictor(cfg, None, TO.ramp_network(3)).predict(x.clone())
+    assert np.allclose(got.numpy(), G["vf_select_softmax"], rtol=0, atol=1e-6)
