@@ -224,3 +224,35 @@ def test_composed_goldens_equal_the_real_tta_predictor():
                                 select_channel=[2, 0, 1], output_dtype=None, head=None))
     got = R.TTAPredictor(cfg, None, TO.ramp_network(3)).predict(x.clone())
     assert np.allclose(got.numpy(), G["vf_select_softmax"], rtol=0, atol=1e-6)
+
+
+def test_composed_patch_first_goldens_equal_the_real_tta_predictor():
+    """Same check for the patch-first-local goldens: the REAL `TTAPredictor._predict_patch_first_local` (tta.py:880-1314) with
+    the REAL `EagerSlidingWindowEngine` as its sliding inferer reproduces `pf_deepem_const`, `pf_banis_bump`, `pf_full_only`."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("/root/reference is only present in the build container")
+    R, W = ref_loader.ref_tta(), ref_loader.ref_window()
+    x = torch.from_numpy(G["pf_x"])
+
+    def run(cfg, tta, acts, blend, sw_batch, net):
+        cfg.model.primary_head = None
+        cfg.model.output_size = [8, 12, 12]
+        cfg.data.dataloader = NS(batch_size=sw_batch)
+        cfg.inference = NS(test_time_augmentation=NS(enabled=True, apply_mask=True, patch_first_local=True, distributed_sharding=False, **tta),
+                           sliding_window=NS(window_size=[8, 12, 12], overlap=0.5, sw_batch_size=sw_batch, blending=blend, padding_mode="constant",
+                                             cval=0.0, keep_input_on_cpu=False, sw_device=None, output_device=None),
+                           model=NS(channel_activations=acts, select_channel=None, output_dtype=None, head=None))
+        engine = W.EagerSlidingWindowEngine(roi_size=(8, 12, 12), sw_batch_size=sw_batch, overlap=0.5, mode=blend, padding_mode="constant",
+                                            cval=0.0, sw_device=None, output_device=None)
+        return R.TTAPredictor(cfg, engine, net).predict(x.clone()).numpy()
+
+    rot = dict(flip_axes="all", rotation90_axes=[[1, 2]], rotate90_k=[0, 1], ensemble_mode="mean")
+    sig = [dict(channels=":", activation="sigmoid")]
+    for name, mode, blend in (("deepem_const", "deepem", "constant"), ("banis_bump", "banis", "bump")):
+        got = run(_cfg(["1-0-0", "0-2-0", "0-0-2"], mode, 3), rot, sig, blend, 2, TO.ramp_network(3))
+        assert np.allclose(got, G[f"pf_{name}"], rtol=0, atol=2e-6), name
+    plain = NS(data=NS(label_transform=None), model=NS(out_channels=2, heads={}))
+    got = run(plain, dict(flip_axes="all", rotation90_axes=None, rotate90_k=None, ensemble_mode=[["0", "mean"], ["1", "max"]]),
+              [dict(channels=[0], activation="sigmoid")], "bump", 3, TO.ramp_network(2))
+    assert np.allclose(got, G["pf_full_only"], rtol=0, atol=2e-6)
