@@ -54,7 +54,8 @@ class FusedAdamW:
     not given)."""
 
     def __init__(self, groups: Iterable[dict], *, betas=(0.9, 0.999), eps: float = 1e-8, max_grad_norm: float = 0.0,
-                 ema_decay: Optional[float] = None, arena: Optional[FlatGradArena] = None, world_size: int = 1):
+                 ema_decay: Optional[float] = None, arena: Optional[FlatGradArena] = None, world_size: int = 1,
+                 ema_warmup_steps: int = 0):
         groups = [dict(g) for g in groups]
         params: List[torch.nn.Parameter] = [p for g in groups for p in g["params"] if p.requires_grad]
         if not params:
@@ -89,6 +90,10 @@ class FusedAdamW:
         self.exp_avg_sq = torch.zeros(n, device=dev, dtype=torch.float32)
         self.ema = self.flat.clone() if ema_decay is not None else None
         self.ema_decay = float(ema_decay) if ema_decay is not None else 0.0
+        # callbacks.py:815-817: the first `warmup_steps` updates use decay 0 (the EMA tracks the weights exactly).  The decay
+        # is a launch argument, so the count lives on the host: capture a CUDA graph of the step AFTER the warm-up.
+        self.ema_warmup_steps = max(0, int(ema_warmup_steps))
+        self.ema_updates = 0
         self.step_count = torch.zeros(1, device=dev, dtype=torch.float32)
         self.sumsq = torch.zeros(1, device=dev, dtype=torch.float64)
         self.seg_active = torch.ones(len(ends), device=dev, dtype=torch.int32)      # device scratch of the kernel
@@ -110,6 +115,8 @@ class FusedAdamW:
         lib, st = L.lib(), L.stream_ptr(self.flat.device)
         scale = 1.0 / self.world_size if grads_are_summed and self.world_size > 1 else 1.0
         clip = self.max_grad_norm > 0.0
+        self.ema_updates += 1
+        ema_decay = 0.0 if self.ema_updates <= self.ema_warmup_steps else self.ema_decay
         if clip:
             self.sumsq.zero_()
             L.check(lib.pcb_grad_sumsq(L.ptr(self.arena.buffer), ctypes.c_int64(self.n), L.ptr(self.sumsq), st), "pcb_grad_sumsq")
@@ -118,7 +125,7 @@ class FusedAdamW:
                                    L.ptr(self.seg_wd), ctypes.c_int(int(self.seg_end.numel())), ctypes.c_float(self.betas[0]),
                                    ctypes.c_float(self.betas[1]), ctypes.c_float(self.eps), L.ptr(self.step_count),
                                    L.ptr(self.sumsq) if clip else None, ctypes.c_float(self.max_grad_norm),
-                                   ctypes.c_float(scale), ctypes.c_float(self.ema_decay), L.ptr(self.seg_active), st),
+                                   ctypes.c_float(scale), ctypes.c_float(ema_decay), L.ptr(self.seg_active), st),
                 "pcb_adamw_step")
         L.PARAM_EPOCH[0] += 1          # parameters changed behind autograd's back: kernel-layout weight caches repack
 
@@ -143,7 +150,7 @@ class FusedAdamW:
 
 
 def build_fused_adamw(cfg, model: torch.nn.Module, *, arena: Optional[FlatGradArena] = None, world_size: int = 1,
-                      ema_decay: Optional[float] = None) -> FusedAdamW:
+                      ema_decay: Optional[float] = None, ema_warmup_steps: int = 0) -> FusedAdamW:
     """``build_optimizer(cfg, model)`` (``build.py:47-113``) for ``optimizer.name == 'adamw'`` on the fused kernel."""
     if not (hasattr(cfg, "optimization") and hasattr(cfg.optimization, "optimizer")):
         raise ValueError("Config must have 'optimization.optimizer' section")
@@ -160,4 +167,5 @@ def build_fused_adamw(cfg, model: torch.nn.Module, *, arena: Optional[FlatGradAr
         groups.sort(key=lambda g: order[id(g["params"][0])])
     clip = float(getattr(cfg.optimization, "gradient_clip_val", 0.0) or 0.0)      # trainer.py:321
     return FusedAdamW(groups, betas=tuple(getattr(oc, "betas", (0.9, 0.999))), eps=float(getattr(oc, "eps", 1e-8)),
-                      max_grad_norm=clip, ema_decay=ema_decay, arena=arena, world_size=world_size)
+                      max_grad_norm=clip, ema_decay=ema_decay, arena=arena, world_size=world_size,
+                      ema_warmup_steps=ema_warmup_steps)

@@ -328,3 +328,22 @@ def test_lazy_seam_matches_the_real_lazy_engine_goldens(name, tmp_path):
     err = float((got.float() - want.float()).abs().max())
     print(f"{name}: max abs difference to the real lazy engine {err:.2e}")
     assert err <= tol * max(1.0, float(want.float().abs().max())), err
+
+
+# ----------------------------------------------------------------------------- EMA warm-up (callbacks.py:815-817)
+def test_ema_warmup_tracks_the_weights_then_decays():
+    """The reference's EMA callback uses decay 0 for the first `warmup_steps` updates (the average IS the weights), then
+    `ema = ema * decay + param * (1 - decay)`."""
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(8, 8), torch.nn.Linear(8, 4)).to(DEV)
+    opt = FusedAdamW(reference_param_groups(net, 1e-2, 0.0), arena=FlatGradArena(net.parameters()), ema_decay=0.9, ema_warmup_steps=2)
+    ema_ref = None
+    for step in range(4):
+        opt.arena.zero()
+        net(torch.randn(5, 8, device=DEV)).square().mean().backward()
+        opt.step()
+        torch.cuda.synchronize()
+        flat = opt.flat.clone()
+        ema_ref = flat.clone() if step < 2 else ema_ref * 0.9 + flat * (1.0 - 0.9)
+        assert torch.allclose(opt.ema, ema_ref, rtol=0, atol=1e-7), step
+    assert not torch.equal(opt.ema, opt.flat)
