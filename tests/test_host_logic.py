@@ -303,6 +303,34 @@ def _reduce_worker(rank, world, port, q):
     red = LD.reduce_cpu_tensor_to_rank_zero(big, op=dist.ReduceOp.SUM, reduction_device=cpu, chunk_mb=1, name="value accumulator")
     hook = LD.make_accumulator_reduce_hook(reduction_device=cpu, chunk_mb=1)
     pair = hook(torch.full((4,), float(rank)), torch.ones(4))
+    # the REAL lazy_distributed.py executed in place gives the same results and the same error texts (build container only)
+    from oracle import ref_loader
+    if ref_loader.available():
+        ref_loader._base_stubs()
+        RD = ref_loader._load("connectomics.inference.lazy_distributed", "connectomics/inference/lazy_distributed.py")
+        assert RD.distributed_context() == LD.distributed_context()
+        cfg.data.dataloader.use_lazy_zarr = True
+        assert RD.is_distributed_window_sharding_enabled(cfg) == LD.is_distributed_window_sharding_enabled(cfg) is True
+        assert RD.distributed_reduction_device(cpu) == LD.distributed_reduction_device(cpu)
+
+        def outcome(fn):
+            try:
+                return ("ok", fn())
+            except RuntimeError as e:
+                return ("RuntimeError", str(e))
+
+        for mod_pair in [(lambda M: M.validate_distributed_tensor_shape(torch.zeros(2, 3 + rank), name="acc", reduction_device=cpu)),
+                         (lambda M: M.validate_distributed_tensor_shape(torch.zeros(*([1] * 9)), name="acc", reduction_device=cpu)),
+                         (lambda M: M.validate_distributed_patch_shard(local_count=rank, total_count=1, reduction_device=cpu)),
+                         (lambda M: M.validate_distributed_patch_shard(local_count=2, total_count=4, reduction_device=cpu))]:
+            assert outcome(lambda: mod_pair(RD)) == outcome(lambda: mod_pair(LD))
+        big2 = torch.full((2, 200_000), float(rank + 1)).t()
+        a = RD.reduce_cpu_tensor_to_rank_zero(big2.clone(), op=dist.ReduceOp.SUM, reduction_device=cpu, chunk_mb=1, name="value accumulator")
+        b = LD.reduce_cpu_tensor_to_rank_zero(big2.clone(), op=dist.ReduceOp.SUM, reduction_device=cpu, chunk_mb=1, name="value accumulator")
+        assert (a is None) == (b is None) == (rank != 0) and (a is None or torch.equal(a, b))
+        pa = RD.make_accumulator_reduce_hook(reduction_device=cpu, chunk_mb=1)(torch.full((4,), float(rank)), torch.ones(4))
+        pb = LD.make_accumulator_reduce_hook(reduction_device=cpu, chunk_mb=1)(torch.full((4,), float(rank)), torch.ones(4))
+        assert (pa is None) == (pb is None) and (pa is None or (torch.equal(pa[0], pb[0]) and torch.equal(pa[1], pb[1])))
     q.put((rank, ("ref-names", shape_err, None if red is None else (tuple(red.shape), float(red.min()), float(red.max())),
                   None if pair is None else (pair[0].tolist(), pair[1].tolist()))))
     dist.destroy_process_group()
