@@ -90,7 +90,22 @@ def _shard_worker(rank, world, port, q):
     vol = torch.rand(1, 1, 44, 24, 20)
     plan = S.plan_z_slabs(vol.shape[2:], (16, 16, 16), 0.5, world)[rank]
     val, wacc = _cpu_rank_phase(vol, _net, plan, "bump")
+    # the comm= route (what NativeComm / pcb_sw_exchange_overlap serves on the GPU) through a stand-in with the same
+    # exchange(sends, recvs) contract carried by gloo: same packed messages, same result as the torch.distributed route
+    val2, wacc2 = val.clone(), wacc.clone()
+
+    class GlooComm:
+        rank, world = dist.get_rank(), dist.get_world_size()
+
+        @staticmethod
+        def exchange(sends, recvs):
+            ops = [dist.P2POp(dist.isend, t, peer) for t, peer in sends] + [dist.P2POp(dist.irecv, t, peer) for t, peer in recvs]
+            for req in (dist.batch_isend_irecv(ops) if ops else []):
+                req.wait()
+
+    S.exchange_overlaps(val2, wacc2, plan, comm=GlooComm)
     S.exchange_overlaps(val, wacc, plan)
+    assert torch.equal(val, val2) and torch.equal(wacc, wacc2)
     z0 = plan.slab[0]
     own = O.normalize_accumulator(val[:, :, plan.own[0] - z0:plan.own[1] - z0].clone(),
                                   wacc[:, :, plan.own[0] - z0:plan.own[1] - z0].clone())
