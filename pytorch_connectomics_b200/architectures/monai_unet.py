@@ -9,7 +9,8 @@ parameter/buffer containers; the arithmetic runs in ``csrc/dense_conv.cu`` (impl
 BatchNorm+PReLU, their backward) and ``csrc/mednext_bwd.cu`` (split-K weight-gradient GEMM) on channels-last
 bf16 activations whose channel counts are zero-padded to multiples of 16.  Not yet on hand-written kernels
 (plain tensor plumbing for now): the residual ``+`` and the skip ``cat``.
-Supported: 3-D, ``norm="batch"``, ``dropout=0``, ``upsample_mode="deconv"`` — anything else raises.
+Supported: 3-D, ``norm="batch"`` / ``"instance"``, ``dropout`` (identity at inference; training with p > 0 raises),
+``upsample_mode="deconv"`` — anything else raises.
 """
 
 from __future__ import annotations
@@ -215,19 +216,37 @@ class BnActFn(torch.autograd.Function):
 # ----------------------------------------------------------------------------- MONAI-named module tree
 def _unsupported(what):
     raise NotImplementedError(f"pcb200 monai_unet: {what} is not implemented in the B200 engine yet "
-                              "(3-D, norm='batch', dropout=0, upsample_mode='deconv' only).")
+                              "(3-D, norm='batch' | 'instance', dropout at inference, upsample_mode='deconv' only).")
 
 
 class ADN(nn.Sequential):
-    def __init__(self, channels: int, dropout):
+    """MONAI ``ADN`` with ordering "NDA" (children ``N``, ``D``, ``A``).  ``norm``: ``"batch"`` or ``"instance"`` —
+    ``InstanceNorm3d`` (no affine, no running statistics, as MONAI builds it) is BatchNorm over a batch of ONE, so each
+    sample goes through the same statistics / normalise+PReLU kernels with its own statistics.  ``dropout`` > 0 is the
+    identity at inference; training with it is refused (a random mask would have to reproduce torch's generator)."""
+
+    def __init__(self, channels: int, dropout, norm: str = "batch"):
         super().__init__()
-        self.add_module("N", nn.BatchNorm3d(channels))
+        self.norm_kind = norm
+        self.add_module("N", nn.BatchNorm3d(channels) if norm == "batch" else nn.InstanceNorm3d(channels))
         if dropout is not None:
             self.add_module("D", nn.Dropout(float(dropout)))
         self.add_module("A", nn.PReLU())
+        if norm == "instance":      # constants the kernels read as gamma / beta / running statistics (not in the state_dict)
+            self.register_buffer("_one", torch.ones(channels), persistent=False)
+            self.register_buffer("_zero", torch.zeros(channels), persistent=False)
+            self.register_buffer("_rm", torch.zeros(channels), persistent=False)
+            self.register_buffer("_rv", torch.ones(channels), persistent=False)
 
     def forward(self, x):
+        drop = getattr(self, "D", None)
+        if drop is not None and drop.p > 0 and self.training:
+            _unsupported("training with dropout > 0")
         bn = self.N
+        if self.norm_kind == "instance":
+            outs = [BnActFn.apply(x[n:n + 1], self._one, self._zero, self.A.weight, self._rm, self._rv, True, 0.0,
+                                  float(bn.eps), int(bn.num_features)) for n in range(int(x.shape[0]))]
+            return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
         return BnActFn.apply(x, bn.weight, bn.bias, self.A.weight, bn.running_mean, bn.running_var,
                              bool(self.training and bn.track_running_stats), float(bn.momentum or 0.1), float(bn.eps),
                              int(bn.num_features))
@@ -235,7 +254,7 @@ class ADN(nn.Sequential):
 
 class Convolution(nn.Sequential):
     def __init__(self, in_channels, out_channels, strides=1, kernel_size=3, dropout=0.0, bias=True, conv_only=False,
-                 is_transposed=False):
+                 is_transposed=False, norm: str = "batch"):
         super().__init__()
         pad = (kernel_size - 1) // 2
         if is_transposed:
@@ -245,14 +264,14 @@ class Convolution(nn.Sequential):
             conv = nn.Conv3d(in_channels, out_channels, kernel_size, stride=strides, padding=pad, bias=bias)
         self.add_module("conv", conv)
         if not conv_only:
-            self.add_module("adn", ADN(out_channels, dropout))
+            self.add_module("adn", ADN(out_channels, dropout, norm))
         self._cfg = (kernel_size, strides, pad, bool(is_transposed))
 
     def forward(self, x):
         k, s, p, tr = self._cfg
         y = ConvFn.apply(x, self.conv.weight, self.conv.bias, k, s, p, tr)
         if hasattr(self, "adn"):
-            if self.training and self.adn.N.track_running_stats:
+            if self.training and getattr(self.adn.N, "track_running_stats", False) and self.adn.norm_kind == "batch":
                 with torch.no_grad():
                     self.adn.N.num_batches_tracked += 1
             y = self.adn(y)
@@ -261,14 +280,14 @@ class Convolution(nn.Sequential):
 
 class ResidualUnit(nn.Module):
     def __init__(self, in_channels, out_channels, strides=1, kernel_size=3, subunits=2, dropout=0.0, bias=True,
-                 last_conv_only=False):
+                 last_conv_only=False, norm: str = "batch"):
         super().__init__()
         self.conv = nn.Sequential()
         self.residual: nn.Module = nn.Identity()
         sch, sst = in_channels, strides
         for su in range(max(1, subunits)):
             only = last_conv_only and su == max(1, subunits) - 1
-            self.conv.add_module(f"unit{su:d}", Convolution(sch, out_channels, sst, kernel_size, dropout, bias, only))
+            self.conv.add_module(f"unit{su:d}", Convolution(sch, out_channels, sst, kernel_size, dropout, bias, only, norm=norm))
             sch, sst = out_channels, 1
         self._res_cfg = None
         if strides != 1 or in_channels != out_channels:
@@ -312,10 +331,10 @@ class UNet(nn.Module):
         super().__init__()
         if spatial_dims != 3:
             _unsupported("spatial_dims != 3")
-        if norm != "batch":
+        norm = str(norm[0] if isinstance(norm, (tuple, list)) else norm).lower()
+        if norm not in ("batch", "instance"):
             _unsupported(f"norm={norm!r}")
-        if dropout not in (0, 0.0, None):
-            _unsupported("dropout > 0")
+        self.norm = norm
         if kernel_size != 3 or up_kernel_size != 3:
             _unsupported("kernel_size != 3")
         if len(channels) < 2:
@@ -342,14 +361,15 @@ class UNet(nn.Module):
 
     def _down(self, i, o, s):
         if self.num_res_units > 0:
-            return ResidualUnit(i, o, s, self.kernel_size, self.num_res_units, self.dropout, self.bias)
-        return Convolution(i, o, s, self.kernel_size, self.dropout, self.bias)
+            return ResidualUnit(i, o, s, self.kernel_size, self.num_res_units, self.dropout, self.bias, norm=self.norm)
+        return Convolution(i, o, s, self.kernel_size, self.dropout, self.bias, norm=self.norm)
 
     def _up(self, i, o, s, is_top):
         conv = Convolution(i, o, s, 3, self.dropout, self.bias, conv_only=is_top and self.num_res_units == 0,
-                           is_transposed=True)
+                           is_transposed=True, norm=self.norm)
         if self.num_res_units > 0:
-            return nn.Sequential(conv, ResidualUnit(o, o, 1, self.kernel_size, 1, self.dropout, self.bias, last_conv_only=is_top))
+            return nn.Sequential(conv, ResidualUnit(o, o, 1, self.kernel_size, 1, self.dropout, self.bias, last_conv_only=is_top,
+                                                    norm=self.norm))
         return conv
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:

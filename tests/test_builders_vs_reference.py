@@ -103,7 +103,8 @@ def _ucfg(filters=(16, 32, 64), input_size=(32, 64, 64), in_channels=1, out_chan
 
 UNET_GOOD = [_ucfg(num_res_units=1, kernel_size=3, norm="batch", dropout=0.0),          # tutorials/minimal.yaml
              _ucfg(filters=(8, 16, 32, 64), in_channels=2, out_channels=3),              # defaults: 2 residual units
-             _ucfg(filters=(16, 32), num_res_units=0), _ucfg(input_size=None, spatial_dims=3, num_res_units=1)]
+             _ucfg(filters=(16, 32), num_res_units=0), _ucfg(input_size=None, spatial_dims=3, num_res_units=1),
+             _ucfg(num_res_units=1, norm="instance", dropout=0.1)]                        # no norm parameters; dropout module kept
 
 
 @pytest.mark.parametrize("i", range(len(UNET_GOOD)))

@@ -347,3 +347,48 @@ def test_ema_warmup_tracks_the_weights_then_decays():
         ema_ref = flat.clone() if step < 2 else ema_ref * 0.9 + flat * (1.0 - 0.9)
         assert torch.allclose(opt.ema, ema_ref, rtol=0, atol=1e-7), step
     assert not torch.equal(opt.ema, opt.flat)
+
+
+# ----------------------------------------------------------------------------- monai_unet: instance norm, dropout at inference
+def test_monai_unet_instance_norm_and_inference_dropout():
+    """`model.monai.norm: instance` (MONAI `InstanceNorm3d`: no affine, no running statistics = BatchNorm over a batch of one,
+    run per sample through the same kernels) and `dropout > 0` at inference (identity), forward in both modes and every
+    parameter gradient against the CPU oracle restatement of MONAI's UNet; training with dropout > 0 is refused."""
+    from oracle.monai_unet_oracle import UNet as OracleUNet
+    from pytorch_connectomics_b200.architectures import monai_unet as PM
+    kw = dict(spatial_dims=3, in_channels=1, out_channels=2, channels=[16, 32, 64], strides=[2, 2], num_res_units=1)
+    torch.manual_seed(3)
+    ref = OracleUNet(norm="instance", dropout=0.0, **kw)
+    net = PM.UNet(norm="instance", dropout=0.0, **kw)
+    assert list(ref.state_dict().keys()) == list(net.state_dict().keys())
+    net.load_state_dict(ref.state_dict(), strict=True)
+    net.to(DEV)
+    x = torch.rand(2, 1, 16, 32, 32)                       # two samples: statistics must NOT be pooled over the batch
+    g = torch.randn(2, 2, 16, 32, 32)
+    rel = lambda a, b: float((a.float().cpu() - b).norm() / b.norm().clamp_min(1e-12))
+    for mode in (False, True):
+        ref.train(mode); net.train(mode)
+        with torch.no_grad():
+            want, got = ref(x), net(x.to(DEV))
+            with torch.autocast("cpu", dtype=torch.bfloat16):
+                want_bf = ref(x).float()
+        e, eb = rel(got, want), rel(want_bf, want)
+        print(f"monai_unet instance norm forward (train={mode}): engine {e:.3e}  reference-bf16-path {eb:.3e}")
+        assert e <= 1.5 * eb + 4e-3
+    ref.zero_grad(); net.zero_grad()
+    (ref(x) * g).sum().backward()
+    (net(x.to(DEV)).float() * g.to(DEV)).sum().backward()
+    num = den = 0.0
+    for (k, pr), pn in zip(ref.named_parameters(), net.parameters()):
+        num += float((pn.grad.float().cpu() - pr.grad).norm() ** 2); den += float(pr.grad.norm() ** 2)
+    print(f"monai_unet instance norm: all-parameter gradient rel-L2 vs fp32 oracle {(num / den) ** 0.5:.3e}")
+    assert (num / den) ** 0.5 < 5e-2
+    drop_ref = OracleUNet(norm="batch", dropout=0.3, **kw).eval()
+    drop = PM.UNet(norm="batch", dropout=0.3, **kw)
+    drop.load_state_dict(drop_ref.state_dict(), strict=True)
+    drop.to(DEV).eval()
+    with torch.no_grad():
+        assert rel(drop(x.to(DEV)), drop_ref(x)) < 2e-2
+    drop.train()
+    with pytest.raises(NotImplementedError, match="dropout"):
+        drop(x.to(DEV))
