@@ -225,6 +225,15 @@ def build_accessor(cfg, source, *, kind: str = "image", mode: str = "test"):
               transpose_axes=tuple(getattr(dt, "val_transpose", None) or ()),
               context_pad=_get_padsize(getattr(dt, "pad_size", [0, 0, 0])) if kind in ("image", "mask") else ((0, 0),) * 3,
               context_pad_mode=getattr(dt, "pad_mode", "reflect") if kind == "image" else "constant")
+    # lazy.py:422-453: a configured test-time resize would change the predicted grid — refuse it rather than ignore it
+    resize = getattr(dt, "resize", None) if mode in ("test", "tune") else None
+    if not resize and kind in ("image", "label"):
+        resize = getattr(getattr(data_cfg, "image_transform", None), "resize", None)
+    if not resize and kind == "mask":
+        resize = getattr(getattr(data_cfg, "mask_transform", None) or dt, "resize", None)
+    if resize and any(abs(float(v) - 1.0) > 1e-12 for v in resize):
+        raise NotImplementedError(f"pcb200 lazy inference: test-time resize {list(resize)!r} (interpolated reads of the lazy "
+                                  "accessor) is a data-pipeline transform outside this path; resample the volume beforehand")
     for key, what in (("image_transform", "normalize"),):
         mode_ = getattr(getattr(data_cfg, key, None), what, "none") if kind == "image" else "none"
         if str(mode_ or "none").lower() != "none":
