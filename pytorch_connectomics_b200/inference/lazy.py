@@ -226,14 +226,22 @@ def build_accessor(cfg, source, *, kind: str = "image", mode: str = "test"):
               context_pad=_get_padsize(getattr(dt, "pad_size", [0, 0, 0])) if kind in ("image", "mask") else ((0, 0),) * 3,
               context_pad_mode=getattr(dt, "pad_mode", "reflect") if kind == "image" else "constant")
     # lazy.py:422-453: a configured test-time resize would change the predicted grid — refuse it rather than ignore it
-    resize = getattr(dt, "resize", None) if mode in ("test", "tune") else None
-    if not resize and kind in ("image", "label"):
-        resize = getattr(getattr(data_cfg, "image_transform", None), "resize", None)
-    if not resize and kind == "mask":
-        resize = getattr(getattr(data_cfg, "mask_transform", None) or dt, "resize", None)
-    if resize and any(abs(float(v) - 1.0) > 1e-12 for v in resize):
-        raise NotImplementedError(f"pcb200 lazy inference: test-time resize {list(resize)!r} (interpolated reads of the lazy "
-                                  "accessor) is a data-pipeline transform outside this path; resample the volume beforehand")
+    factors = None
+    target = getattr(dt, "resize", None) if mode in ("test", "tune") else None
+    if target:                                   # data_transform.resize is a SIZE: factor = size / dataloader.patch_size
+        patch = getattr(getattr(data_cfg, "dataloader", None), "patch_size", None)
+        if not (patch and len(patch) == len(target) and all(float(v) > 0 for v in patch)):
+            raise ValueError("Lazy sliding-window inference requires data.dataloader.patch_size when "
+                             "data_transform.resize is configured.")
+        factors = [float(o) / float(i) for o, i in zip(target, patch)]
+    elif kind in ("image", "label"):
+        factors = getattr(getattr(data_cfg, "image_transform", None), "resize", None)
+    elif kind == "mask":
+        factors = getattr(getattr(data_cfg, "mask_transform", None) or dt, "resize", None)
+    if factors and any(abs(float(v) - 1.0) > 1e-12 for v in factors):
+        raise NotImplementedError(f"pcb200 lazy inference: test-time resize by {[float(v) for v in factors]!r} (interpolated "
+                                  "reads of the lazy accessor) is a data-pipeline transform outside this path; resample the "
+                                  "volume beforehand")
     for key, what in (("image_transform", "normalize"),):
         mode_ = getattr(getattr(data_cfg, key, None), what, "none") if kind == "image" else "none"
         if str(mode_ or "none").lower() != "none":
