@@ -17,15 +17,18 @@ import torch
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "lazy_goldens.npz")
 
 
-def make_cfg(window, *, out_channels=1, transpose=None, overlap=0.5, blending="bump", snap=False, sw_batch=2, output_dtype=None, target_context=(), border_mask=None,
+def make_cfg(window, *, out_channels=1, transpose=None, image_resize=None, dt_resize=None, patch=None, overlap=0.5, blending="bump", snap=False, sw_batch=2, output_dtype=None, target_context=(), border_mask=None,
          pad_size=None, pad_mode="reflect", acts=None, select=None, tta=None, padding_mode="constant", cval=0.0):
     sw = NS(window_size=list(window), overlap=overlap, blending=blending, sw_batch_size=sw_batch, padding_mode=padding_mode, cval=cval,
             snap_to_edge=snap, target_context=list(target_context), border_mask=border_mask, distributed_sharding=False)
     dt = NS() if pad_size is None else NS(pad_size=list(pad_size), pad_mode=pad_mode)
     if transpose is not None:
         dt.val_transpose = list(transpose)
+    if dt_resize is not None:
+        dt.resize = list(dt_resize)
     return NS(model=NS(output_size=list(window), arch=NS(type="mednext"), primary_head=None, heads=None, out_channels=out_channels),
-              data=NS(dataloader=NS(batch_size=1, patch_size=list(window), use_lazy_h5=True), data_transform=dt, image_transform=NS()),
+              data=NS(dataloader=NS(batch_size=1, patch_size=list(patch or window), use_lazy_h5=True), data_transform=dt,
+                      image_transform=NS() if image_resize is None else NS(resize=list(image_resize))),
               system=NS(num_workers=1),
               inference=NS(sliding_window=sw, test_time_augmentation=tta if tta is not None else NS(enabled=False),
                            model=NS(output_dtype=output_dtype, channel_activations=acts, select_channel=select, head=None)))
@@ -64,6 +67,9 @@ CASES = {
     "transpose": dict(shape=(6, 9, 12), cfg=dict(window=(4, 4, 4), blending="constant", transpose=(2, 0, 1)), fwd=_patch_mean),
     "transpose_pad_region": dict(shape=(6, 9, 12), cfg=dict(window=(4, 4, 4), blending="constant", transpose=(1, 2, 0), pad_size=(1, 1, 2)),
                                  fwd=_patch_mean, region=((2, 1, 0), (9, 10, 7))),
+    "resize_image": dict(shape=(8, 9, 10), cfg=dict(window=(4, 4, 4), blending="constant", image_resize=(1.5, 1.0, 0.75)), fwd=_patch_mean),
+    "resize_to_size_mask_pad": dict(shape=(8, 8, 8), cfg=dict(window=(4, 4, 4), blending="bump", dt_resize=(6, 4, 5), patch=(4, 4, 4),
+                                                             pad_size=(1, 0, 2)), fwd=_identity, mask=True),
     "context_pad": dict(shape=(8, 9, 10), cfg=dict(window=(4, 4, 4), blending="constant", pad_size=(2, 1, 3), pad_mode="reflect"), fwd=_patch_mean),
 }
 

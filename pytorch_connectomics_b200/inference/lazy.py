@@ -59,7 +59,7 @@ class ArrayVolumeAccessor:
 
     def __init__(self, data, *, kind: str = "image", binarize: bool = False, threshold: float = 0.0,
                  context_pad: Sequence[Sequence[int]] = ((0, 0), (0, 0), (0, 0)), context_pad_mode: str = "constant",
-                 transpose_axes: Sequence[int] = ()):
+                 transpose_axes: Sequence[int] = (), scale_factors: Optional[Sequence[float]] = None):
         if isinstance(data, torch.Tensor):
             if data.dim() == 5:
                 if data.shape[0] != 1:
@@ -89,7 +89,14 @@ class ArrayVolumeAccessor:
         if self.transpose_axes and sorted(self.transpose_axes) != [0, 1, 2]:
             raise ValueError(f"transpose_axes must be a permutation of (0, 1, 2), got {self.transpose_axes}")
         stored = tuple(int(v) for v in ref.shape[1:])
-        self.transformed_spatial_shape = tuple(stored[a] for a in self.transpose_axes) if self.transpose_axes else stored
+        self.logical_spatial_shape = tuple(stored[a] for a in self.transpose_axes) if self.transpose_axes else stored
+        # test-time resize (lazy.py:422-453,508-515): the transformed volume is the logical one resampled by these factors —
+        # trilinear with align_corners for images, nearest for masks / labels — evaluated per read, never materialised
+        self.scale_factors = tuple(float(v) for v in scale_factors) if scale_factors else None
+        if self.scale_factors is not None and any(f <= 0 for f in self.scale_factors):
+            raise ValueError(f"scale factor must be positive, got {min(self.scale_factors)}.")
+        self.transformed_spatial_shape = self.logical_spatial_shape if self.scale_factors is None else tuple(
+            max(1, int(np.floor(float(n) * f + 1e-6))) for n, f in zip(self.logical_spatial_shape, self.scale_factors))
         # data_transform.pad_size / pad_mode (lazy.py:924-929): the context border the test-time transform adds around
         # the volume; window coordinates, the reference shape and the prediction all live in the PADDED frame
         self.context_pad = tuple((int(b), int(a)) for b, a in context_pad)
@@ -112,13 +119,50 @@ class ArrayVolumeAccessor:
 
     def as_tensor(self) -> Optional[torch.Tensor]:
         """``[1, C, D, H, W]`` view when the whole volume is a tensor (device-resident fast path), else ``None``."""
-        plain = not self.binarize and not self.transpose_axes and not any(b or a for b, a in self.context_pad)
+        plain = not self.binarize and not self.transpose_axes and not any(b or a for b, a in self.context_pad) \
+            and self.scale_factors is None
         if self._tensor is not None and plain:
             return self._tensor.unsqueeze(0)
         return None
 
     def _crop(self, lo, hi) -> np.ndarray:
-        """[C, *box] of the LOGICAL (transposed, unpadded) volume"""
+        """[C, *box] of the TRANSFORMED (transposed, resized, unpadded) volume (``lazy.py:738-792``)"""
+        if self.scale_factors is None:
+            return self._raw_crop(lo, hi)
+        shape = tuple(int(hi[a]) - int(lo[a]) for a in range(3))
+        if any(v <= 0 for v in shape):
+            return np.zeros((self.channel_count, *shape), dtype=np.float32)
+        nearest = self.kind in ("label", "mask")
+        coords = []
+        for a in range(3):
+            idx = np.arange(int(lo[a]), int(hi[a]), dtype=np.float32)
+            n_in, n_out = int(self.logical_spatial_shape[a]), int(self.transformed_spatial_shape[a])
+            if n_in <= 1 or n_out <= 1:
+                c = np.zeros_like(idx)
+            elif nearest:
+                c = np.clip(np.floor(idx * float(n_in) / float(n_out)), 0, n_in - 1).astype(np.float32)
+            else:                                   # bilinear, align_corners=True
+                c = (idx * float(n_in - 1) / float(n_out - 1)).astype(np.float32)
+            coords.append(c)
+        r0 = tuple(int(np.floor(float(c.min()))) for c in coords)
+        r1 = tuple(min(int(self.logical_spatial_shape[a]), int(np.ceil(float(coords[a].max()))) + 1) for a in range(3))
+        raw = self._raw_crop(r0, r1)
+        local = [coords[a] - float(r0[a]) for a in range(3)]
+        if nearest:
+            out = raw
+            for a in range(3):
+                out = np.take(out, local[a].astype(np.int64), axis=a + 1)
+            return out.astype(np.float32, copy=False)
+        grid_axes = [(np.zeros_like(local[a]) if raw.shape[a + 1] <= 1 else (2.0 * local[a]) / float(raw.shape[a + 1] - 1) - 1.0)
+                     .astype(np.float32) for a in range(3)]
+        zz, yy, xx = np.meshgrid(grid_axes[0], grid_axes[1], grid_axes[2], indexing="ij")
+        grid = torch.from_numpy(np.stack([xx, yy, zz], axis=-1)).unsqueeze(0)
+        sampled = torch.nn.functional.grid_sample(torch.from_numpy(np.ascontiguousarray(raw)).unsqueeze(0), grid, mode="bilinear",
+                                                  padding_mode="zeros", align_corners=True)
+        return sampled.squeeze(0).numpy().astype(np.float32, copy=False)
+
+    def _raw_crop(self, lo, hi) -> np.ndarray:
+        """[C, *box] of the LOGICAL (transposed, not resized) volume"""
         if self.transpose_axes:            # logical axis i is stored axis transpose_axes[i]
             raw = [None, None, None]
             for i, a in enumerate(self.transpose_axes):
@@ -225,7 +269,7 @@ def build_accessor(cfg, source, *, kind: str = "image", mode: str = "test"):
               transpose_axes=tuple(getattr(dt, "val_transpose", None) or ()),
               context_pad=_get_padsize(getattr(dt, "pad_size", [0, 0, 0])) if kind in ("image", "mask") else ((0, 0),) * 3,
               context_pad_mode=getattr(dt, "pad_mode", "reflect") if kind == "image" else "constant")
-    # lazy.py:422-453: a configured test-time resize would change the predicted grid — refuse it rather than ignore it
+    # lazy.py:422-453: test-time resize factors (data_transform.resize is a SIZE relative to dataloader.patch_size)
     factors = None
     target = getattr(dt, "resize", None) if mode in ("test", "tune") else None
     if target:                                   # data_transform.resize is a SIZE: factor = size / dataloader.patch_size
@@ -238,10 +282,7 @@ def build_accessor(cfg, source, *, kind: str = "image", mode: str = "test"):
         factors = getattr(getattr(data_cfg, "image_transform", None), "resize", None)
     elif kind == "mask":
         factors = getattr(getattr(data_cfg, "mask_transform", None) or dt, "resize", None)
-    if factors and any(abs(float(v) - 1.0) > 1e-12 for v in factors):
-        raise NotImplementedError(f"pcb200 lazy inference: test-time resize by {[float(v) for v in factors]!r} (interpolated "
-                                  "reads of the lazy accessor) is a data-pipeline transform outside this path; resample the "
-                                  "volume beforehand")
+    kw["scale_factors"] = tuple(float(v) for v in factors) if factors else None
     for key, what in (("image_transform", "normalize"),):
         mode_ = getattr(getattr(data_cfg, key, None), what, "none") if kind == "image" else "none"
         if str(mode_ or "none").lower() != "none":
