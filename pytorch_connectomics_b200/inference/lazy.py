@@ -309,6 +309,13 @@ def build_accessor(cfg, source, *, kind: str = "image", mode: str = "test"):
 def get_lazy_image_reference_shape(cfg, image_path, *, mode: str = "test") -> Tuple[int, ...]:
     """``lazy.py:962-978``."""
     with build_accessor(cfg, image_path, kind="image", mode=mode) as acc:
+        patch = getattr(getattr(getattr(cfg, "data", None), "dataloader", None), "patch_size", None)
+        shape = getattr(acc, "transformed_spatial_shape", acc.padded_spatial_shape)
+        if patch and any(int(shape[i]) < int(patch[i]) for i in range(3)):
+            raise ValueError("Lazy sliding-window inference currently requires the transformed test volume "
+                             "to be at least as large as data.dataloader.patch_size in every axis. "
+                             f"Got transformed_shape={tuple(int(v) for v in shape)}, "
+                             f"patch_size={tuple(int(v) for v in patch)}.")
         return (1, int(acc.channel_count), *tuple(int(v) for v in acc.padded_spatial_shape))
 
 

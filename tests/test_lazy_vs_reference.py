@@ -54,3 +54,35 @@ def test_lazy_seam_reproduces_the_committed_goldens(name, tmp_path, monkeypatch)
     gold = np.load(os.path.join(GOLDEN, "lazy_goldens.npz"))
     cpu_doubles.install(monkeypatch)
     _check(_ours(name, tmp_path, "cpu"), torch.from_numpy(gold[name]))
+
+
+def test_reference_shape_and_full_load_equal_the_real_accessor(tmp_path):
+    """`get_lazy_image_reference_shape` (lazy.py:962-978, incl. its refusal of volumes smaller than the patch) and
+    `load_full` of the accessor (`:906-918`) for every transform combination of the case table."""
+    if not ref_loader.available():
+        pytest.skip("/root/reference is only present in the build container")
+    from types import SimpleNamespace as NS
+    from pytorch_connectomics_b200.inference import lazy as Z
+    R = ref_loader.ref_lazy()
+
+    def outcome(fn):
+        try:
+            return ("ok", fn())
+        except ValueError as e:
+            return ("ValueError", str(e))
+
+    for name in sorted(G.CASES):
+        vol, mask = G.volumes(name)
+        np.save(tmp_path / f"{name}.h5.npy", vol)
+        cfg = G.make_cfg(**G.CASES[name]["cfg"])
+        with ref_loader.fake_h5py():
+            want = outcome(lambda: tuple(R.get_lazy_image_reference_shape(cfg, str(tmp_path / f"{name}.h5"))))
+            full = R.load_lazy_volume(cfg, str(tmp_path / f"{name}.h5"), kind="image")
+        assert outcome(lambda: Z.get_lazy_image_reference_shape(cfg, str(tmp_path / f"{name}.h5.npy"))) == want, name
+        with Z.build_accessor(cfg, str(tmp_path / f"{name}.h5.npy"), kind="image", mode="test") as acc:
+            assert np.allclose(acc.load_full(), full, rtol=1e-6, atol=1e-6), name
+    small = G.make_cfg(window=(4, 4, 4), patch=(16, 4, 4))
+    np.save(tmp_path / "small.h5.npy", np.zeros((8, 8, 8), np.float32))
+    with ref_loader.fake_h5py():
+        want = outcome(lambda: R.get_lazy_image_reference_shape(small, str(tmp_path / "small.h5")))
+    assert want[0] == "ValueError" and outcome(lambda: Z.get_lazy_image_reference_shape(small, str(tmp_path / "small.h5.npy"))) == want
