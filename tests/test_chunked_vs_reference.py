@@ -137,3 +137,51 @@ def test_external_shards_and_index_equal_the_real_driver(tmp_path, monkeypatch):
     idx_our = json.load(open(tmp_path / "ours" / "pred.h5.index.json"))
     strip = lambda idx: {**idx, "chunks": [{k: (os.path.basename(v).split(".npy")[0] if k == "path" else v) for k, v in c.items()} for c in idx["chunks"]]}
     assert strip(idx_ref) == strip(idx_our)
+
+
+def _rank_worker(rank, world, port, workdir, q):
+    try:
+        import torch.distributed as dist
+        os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        import pytest as _pt
+        from pytorch_connectomics_b200.inference import chunked as Cours
+        mp = _pt.MonkeyPatch()
+        cpu_doubles.install(mp)
+        cfg = _cfg(chunking=dict(chunk_size=[6, 16, 7], axes="all", halo=[2, 2, 2]), crop_pad=[1, 0, 2])
+        out = Cours.run_chunked_prediction_inference(cfg, _patch_mean, os.path.join(workdir, "v.h5.npy"),
+                                                     output_path=os.path.join(workdir, "dist", "pred.h5"), device="cpu")
+        mp.undo()
+        q.put((rank, str(out)))
+        dist.destroy_process_group()
+    except Exception as e:                                   # noqa: BLE001 - report to the parent instead of hanging it
+        import traceback
+        q.put((rank, f"error: {e!r}\n{traceback.format_exc()}"))
+
+
+def test_two_ranks_share_the_chunks_and_rank0_stitches(tmp_path):
+    """Inside a process group (world 2 over gloo) `run_chunked_prediction_inference` hands the chunks `idx % world == rank` to
+    each rank, the ranks meet in a barrier, rank 0 writes `index.json` and stitches: the volume equals what the REAL driver
+    streams in a single process for the same config."""
+    import torch.multiprocessing as mp
+    from conftest import free_port
+    Cref = ref_loader.ref_chunked()
+    vol = np.random.RandomState(5).rand(12, 10, 14).astype(np.float32)
+    np.save(tmp_path / "v.h5.npy", vol)
+    cfg = _cfg(chunking=dict(chunk_size=[6, 16, 7], axes="all", halo=[2, 2, 2]), crop_pad=[1, 0, 2])
+    want, _ = _read_real(_run(Cref, cfg, str(tmp_path / "v.h5"), tmp_path / "ref" / "pred.h5", h5=True))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = free_port()
+    procs = [ctx.Process(target=_rank_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    assert not any(v.startswith("error") for v in got.values()), got
+    assert got[0].endswith("dist/pred.h5") and got[1].endswith("dist/pred.h5.chunks")     # non-root ranks return the chunk dir
+    data, attrs = _read_ours(tmp_path / "dist" / "pred.h5")
+    assert np.allclose(data, want, rtol=1e-5, atol=2e-6)
+    index = json.load(open(tmp_path / "dist" / "pred.h5.index.json"))
+    assert index["world_size"] == 2 and len(index["chunks"]) == 4
