@@ -86,3 +86,63 @@ def test_reference_shape_and_full_load_equal_the_real_accessor(tmp_path):
     with ref_loader.fake_h5py():
         want = outcome(lambda: R.get_lazy_image_reference_shape(small, str(tmp_path / "small.h5")))
     assert want[0] == "ValueError" and outcome(lambda: Z.get_lazy_image_reference_shape(small, str(tmp_path / "small.h5.npy"))) == want
+
+
+def _shard_worker(rank, world, port, workdir, q):
+    try:
+        import torch.distributed as dist
+        os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        from pytorch_connectomics_b200.inference import lazy as Z
+        out = {}
+        for name in ("mean_constant", "tta_acts_mask"):
+            case = G.CASES[name]
+            cfg = G.make_cfg(**case["cfg"])
+            cfg.inference.sliding_window.distributed_sharding = True
+            vol, mask = G.volumes(name)
+            np.save(os.path.join(workdir, f"{name}_{rank}.h5.npy"), vol)
+            if mask is not None:
+                np.save(os.path.join(workdir, f"{name}_{rank}_m.h5.npy"), mask)
+            mpath = lambda ext: os.path.join(workdir, f"{name}_{rank}_m.h5{ext}") if mask is not None else None   # noqa: E731
+            if ref_loader.available():
+                R = ref_loader.ref_lazy()
+                with ref_loader.fake_h5py():
+                    want = R.lazy_predict_volume(cfg, case["fwd"], os.path.join(workdir, f"{name}_{rank}.h5"), mask_path=mpath(""),
+                                                 device="cpu")
+                out[f"ref_{name}"] = want.numpy()
+            mp = pytest.MonkeyPatch()
+            cpu_doubles.install(mp)
+            got = Z.lazy_predict_volume(cfg, case["fwd"], os.path.join(workdir, f"{name}_{rank}.h5.npy"), mask_path=mpath(".npy"),
+                                        device="cpu")
+            mp.undo()
+            out[f"ours_{name}"] = got.numpy()
+        q.put((rank, out))
+        dist.destroy_process_group()
+    except Exception as e:                                   # noqa: BLE001
+        import traceback
+        q.put((rank, {"error": f"{e!r}\n{traceback.format_exc()}"}))
+
+
+def test_window_sharding_over_two_ranks_equals_the_real_engine_and_the_goldens(tmp_path):
+    """`inference.sliding_window.distributed_sharding` inside a world-2 gloo group (lazy.py:1104, lazy_distributed.py): windows
+    `[rank::world]`, accumulators reduced onto rank 0, empty tensor elsewhere — this package and the REAL engine side by side in
+    the same workers, and rank 0's result equal to the committed single-process goldens."""
+    import torch.multiprocessing as mp
+    from conftest import free_port
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = free_port()
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    assert not any("error" in v for v in got.values()), got
+    gold = np.load(os.path.join(GOLDEN, "lazy_goldens.npz"))
+    for name in ("mean_constant", "tta_acts_mask"):
+        assert got[1][f"ours_{name}"].size == 0                                       # non-root ranks: empty, like the reference
+        assert np.allclose(got[0][f"ours_{name}"], gold[name], rtol=1e-5, atol=1e-5), name
+        if f"ref_{name}" in got[0]:
+            assert got[1][f"ref_{name}"].size == 0
+            assert np.allclose(got[0][f"ours_{name}"], got[0][f"ref_{name}"], rtol=1e-5, atol=1e-5), name
