@@ -59,7 +59,8 @@ class ArrayVolumeAccessor:
 
     def __init__(self, data, *, kind: str = "image", binarize: bool = False, threshold: float = 0.0,
                  context_pad: Sequence[Sequence[int]] = ((0, 0), (0, 0), (0, 0)), context_pad_mode: str = "constant",
-                 transpose_axes: Sequence[int] = (), scale_factors: Optional[Sequence[float]] = None):
+                 transpose_axes: Sequence[int] = (), scale_factors: Optional[Sequence[float]] = None,
+                 layout: str = "channel_first"):
         if isinstance(data, torch.Tensor):
             if data.dim() == 5:
                 if data.shape[0] != 1:
@@ -73,6 +74,14 @@ class ArrayVolumeAccessor:
             arr = data
             if arr.ndim == 5 and arr.shape[0] == 1:
                 arr = arr[0]
+            if arr.ndim == 4 and layout == "infer":
+                # lazy.py:572-586: a 4-D DATASET says nothing about where its channel axis is — the reference takes the
+                # smallest axis (first / last / second), spatial axes keep their order
+                smallest = int(np.argmin(arr.shape))
+                if smallest == 3:
+                    arr = np.moveaxis(arr, -1, 0)
+                elif smallest == 1:
+                    arr = np.transpose(arr, (1, 0, 2, 3))
             if arr.ndim == 3:
                 arr = arr[None]
             self._tensor = None
@@ -209,11 +218,10 @@ class ArrayVolumeAccessor:
         end = tuple(start[i] + size[i] for i in range(3))
         lo = tuple(max(0, start[i]) for i in range(3))
         hi = tuple(min(self.padded_spatial_shape[i], end[i]) for i in range(3))
-        if any(hi[i] <= lo[i] for i in range(3)):
-            inner = np.zeros((self.channel_count, 0, 0, 0), dtype=np.float32)
-            return np.full((self.channel_count, *size), outer_pad_value, dtype=np.float32) if str(outer_pad_mode) == "constant" \
-                else np.zeros((self.channel_count, *size), dtype=np.float32)
-        inner = self._read_padded_inner(lo, hi) if (any(b or a for b, a in self.context_pad)) else self._crop(lo, hi)
+        if any(hi[i] <= lo[i] for i in range(3)):          # a box entirely outside: the reference pads an EMPTY crop (lazy.py:866-867),
+            inner = np.zeros((self.channel_count, 0, 0, 0), dtype=np.float32)     # which numpy only accepts for constant padding
+        else:
+            inner = self._read_padded_inner(lo, hi) if (any(b or a for b, a in self.context_pad)) else self._crop(lo, hi)
         pads = [(max(0, -start[i]), max(0, end[i] - self.padded_spatial_shape[i])) for i in range(3)]
         patch = _pad_channel_first(inner, pads, mode=outer_pad_mode, constant_value=outer_pad_value)
         if self.binarize:
@@ -293,7 +301,7 @@ def build_accessor(cfg, source, *, kind: str = "image", mode: str = "test"):
     path = os.fspath(source)
     ext = os.path.splitext(path)[1].lower()
     if ext == ".npy":
-        return ArrayVolumeAccessor(np.load(path, mmap_mode="r"), **kw)
+        return ArrayVolumeAccessor(np.load(path, mmap_mode="r"), layout="infer", **kw)
     if ext in (".h5", ".hdf5"):
         try:
             import h5py  # noqa: F401
@@ -301,7 +309,7 @@ def build_accessor(cfg, source, *, kind: str = "image", mode: str = "test"):
             raise RuntimeError(f"pcb200 lazy inference: reading {path} needs h5py, which is not installed; pass a .npy "
                                "volume, an array, or register_accessor_factory(...)") from exc
         f = h5py.File(path, "r")
-        return ArrayVolumeAccessor(f[next(iter(f.keys()))], **kw)
+        return ArrayVolumeAccessor(f[next(iter(f.keys()))][...], layout="infer", **kw)
     raise ValueError(f"pcb200 lazy inference: unsupported volume source {source!r}; expected a .npy path, a tensor/array "
                      "or an accessor object (register_accessor_factory adds formats).")
 

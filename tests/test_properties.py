@@ -6,7 +6,7 @@ container).  SURVEY §8 rows a11-a13, a21, §8e."""
 
 import pytest
 import torch
-from hypothesis import HealthCheck, given, settings
+from hypothesis import HealthCheck, Phase, assume, given, settings
 from hypothesis import strategies as st
 
 from oracle import ref_loader
@@ -352,3 +352,72 @@ def test_affinity_config_helpers_against_the_real_reference(targets, stack, as_n
     assert outcome(lambda: ta.transform_offset(off, flip_axes=flips, rotation_plane_spatial=plane, k=k)) == \
         outcome(lambda: A.transform_offset(off, flip_axes=flips, rotation_plane_spatial=plane, k=k))
     assert outcome(lambda: ta.valid_slices_for_shift(shape, off)) == outcome(lambda: A.valid_slices_for_shift(shape, off))
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference is only present in the build container")
+@settings(max_examples=150, derandomize=True, deadline=None, phases=[Phase.explicit, Phase.reuse, Phase.generate],
+          suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
+@given(shape=st.tuples(st.integers(1, 9), st.integers(1, 9), st.integers(1, 9)), channels=st.sampled_from([0, 1, 2]),
+       kind=st.sampled_from(["image", "mask"]), transpose=st.sampled_from([(), (0, 1, 2), (2, 0, 1), (1, 2, 0), (0, 2, 1)]),
+       scale=st.one_of(st.none(), st.tuples(st.sampled_from([0.5, 1.0, 1.5, 2.0]), st.sampled_from([0.75, 1.0, 1.3]), st.sampled_from([1.0, 2.0]))),
+       pad=st.tuples(st.tuples(st.integers(0, 3), st.integers(0, 3)), st.tuples(st.integers(0, 3), st.integers(0, 3)), st.tuples(st.integers(0, 3), st.integers(0, 3))),
+       pad_mode=st.sampled_from(["constant", "reflect", "replicate", "edge"]), outer=st.sampled_from(["constant", "reflect", "replicate", "edge"]),   # "circular" is refused by the reference (numpy has no such mode); here it maps to wrap
+       outer_value=st.sampled_from([0.0, 0.5]), binarize=st.booleans(), data=st.data())
+def test_accessor_reads_equal_the_real_lazy_volume_accessor(tmp_path_factory, shape, channels, kind, transpose, scale, pad, pad_mode, outer,
+                                                            outer_value, binarize, data):
+    """`ArrayVolumeAccessor.read_patch` / shapes against the REAL `LazyVolumeAccessor` (lazy.py:456-918) built with the same
+    arguments on the same array: random volume shapes (with and without a channel axis), transposes, resize factors, context
+    borders in every mode, outer padding in every mode, mask binarisation, read boxes that stick out on any side."""
+    import numpy as np
+    from pytorch_connectomics_b200.inference.lazy import ArrayVolumeAccessor
+    R = ref_loader.ref_lazy()
+    # 4-D datasets: the reference guesses the channel axis from the smallest extent (lazy.py:572-586); keep the guess
+    # unambiguous here (channel-first) — the other two layouts are checked below without transposes, where the reference's own
+    # read path handles them
+    assume(channels == 0 or channels < min(shape))
+    rs = np.random.RandomState(sum(shape) * 7 + channels)
+    arr = rs.rand(*((channels,) if channels else ()), *shape).astype(np.float32)
+    d = tmp_path_factory.mktemp("acc")
+    np.save(d / "a.h5.npy", arr)
+    kw = dict(kind=kind, transpose_axes=transpose, scale_factors=scale, context_pad=pad, context_pad_mode=pad_mode,
+              binarize=binarize and kind == "mask", threshold=0.5)
+    ours = ArrayVolumeAccessor(np.load(d / "a.h5.npy", mmap_mode="r"), layout="infer", **kw)      # a file dataset: layout is inferred
+    with ref_loader.fake_h5py():
+        real = R.LazyVolumeAccessor(str(d / "a.h5"), **kw)
+        assert tuple(real.padded_spatial_shape) == tuple(ours.padded_spatial_shape)
+        assert tuple(real.transformed_spatial_shape) == tuple(ours.transformed_spatial_shape) and real.channel_count == ours.channel_count
+        for _ in range(3):
+            size = tuple(data.draw(st.integers(1, 6)) for _ in range(3))
+            loc = tuple(data.draw(st.integers(-4, ours.padded_spatial_shape[a] + 2)) for a in range(3))
+            def read(acc):
+                try:
+                    return acc.read_patch(loc, size, outer_pad_mode=outer, outer_pad_value=outer_value)
+                except ValueError as e:                      # e.g. numpy refusing to reflect-pad an empty crop
+                    return str(e)
+
+            want, got = read(real), read(ours)
+            if isinstance(want, str) or isinstance(got, str):
+                assert want == got, (loc, size, want, got)
+                continue
+            assert got.shape == want.shape and got.dtype == want.dtype
+            assert np.allclose(got, want, rtol=1e-6, atol=1e-6), (loc, size)
+        assert np.allclose(ours.load_full(), real.load_full(), rtol=1e-6, atol=1e-6)
+        real.close()
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference is only present in the build container")
+def test_dataset_layout_inference_equals_the_real_accessor(tmp_path):
+    """channel-last and channel-second datasets (lazy.py:572-586: the smallest axis is the channel axis)"""
+    import numpy as np
+    from pytorch_connectomics_b200.inference.lazy import ArrayVolumeAccessor
+    R = ref_loader.ref_lazy()
+    for i, shape in enumerate([(5, 6, 7, 2), (5, 2, 6, 7), (2, 5, 6, 7), (6, 6, 6, 6)]):
+        arr = np.random.RandomState(i).rand(*shape).astype(np.float32)
+        np.save(tmp_path / f"l{i}.h5.npy", arr)
+        ours = ArrayVolumeAccessor(np.load(tmp_path / f"l{i}.h5.npy", mmap_mode="r"), layout="infer")
+        with ref_loader.fake_h5py():
+            real = R.LazyVolumeAccessor(str(tmp_path / f"l{i}.h5"), kind="image")
+            assert (real.channel_count, tuple(real.padded_spatial_shape)) == (ours.channel_count, tuple(ours.padded_spatial_shape)), shape
+            want = real.read_patch((-1, 2, 1), (4, 3, 5), outer_pad_mode="constant", outer_pad_value=0.25)
+            assert np.array_equal(ours.read_patch((-1, 2, 1), (4, 3, 5), outer_pad_mode="constant", outer_pad_value=0.25), want), shape
+            assert np.array_equal(ours.load_full(), real.load_full())
