@@ -309,7 +309,10 @@ def build_accessor(cfg, source, *, kind: str = "image", mode: str = "test"):
             raise RuntimeError(f"pcb200 lazy inference: reading {path} needs h5py, which is not installed; pass a .npy "
                                "volume, an array, or register_accessor_factory(...)") from exc
         f = h5py.File(path, "r")
-        return ArrayVolumeAccessor(f[next(iter(f.keys()))][...], layout="infer", **kw)
+        ds = f[next(iter(f.keys()))]
+        if ds.ndim == 4 and int(np.argmin(ds.shape)) in (1, 3):      # channel-second / channel-last: re-laid out in memory;
+            ds = ds[...]                                             # channel-first and 3-D datasets stay lazy (sliced per read)
+        return ArrayVolumeAccessor(ds, layout="infer", **kw)
     raise ValueError(f"pcb200 lazy inference: unsupported volume source {source!r}; expected a .npy path, a tensor/array "
                      "or an accessor object (register_accessor_factory adds formats).")
 
