@@ -19,7 +19,7 @@ from pytorch_connectomics_b200.training import FlatGradArena, FusedAdamW, refere
 
 DEV = "cuda:0"
 first_run = pytest.mark.xfail(strict=False, reason="written without GPU access; first B200 run is the driver's")
-pytestmark = [pytest.mark.gpu, first_run]
+pytestmark = [pytest.mark.gpu, first_run, pytest.mark.timeout(600)]
 
 
 def _patch_mean_forward(x):          # reference tests/unit/test_lazy_inference.py: a context-dependent forward
