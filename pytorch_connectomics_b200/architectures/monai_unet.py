@@ -9,7 +9,7 @@ parameter/buffer containers; the arithmetic runs in ``csrc/dense_conv.cu`` (impl
 BatchNorm+PReLU, their backward) and ``csrc/mednext_bwd.cu`` (split-K weight-gradient GEMM) on channels-last
 bf16 activations whose channel counts are zero-padded to multiples of 16.  Not yet on hand-written kernels
 (plain tensor plumbing for now): the residual ``+`` and the skip ``cat``.
-Supported: 3-D, ``norm="batch"`` / ``"instance"``, ``dropout`` (identity at inference; training with p > 0 raises),
+Supported: 3-D, ``norm="batch"`` / ``"group"`` / ``"instance"``, ``dropout`` (identity at inference; training with p > 0 raises),
 ``upsample_mode="deconv"`` — anything else raises.
 """
 
@@ -213,22 +213,132 @@ class BnActFn(torch.autograd.Function):
         return dx, dgamma, dbeta, dslope, None, None, None, None, None, None
 
 
+# ----------------------------------------------------------------------------- GroupNorm + PReLU (norm=("group", {...}))
+# thin wrappers of the four kernels the function below composes (the CPU suite swaps them for torch stand-ins to check the
+# composition's arithmetic; the kernels themselves are the ones BatchNorm runs through)
+def _k_channel_stats(x, stats):
+    cp = int(x.shape[-1])
+    L.check(L.lib().pcb_channel_stats(L.ptr(x), L.ptr(stats), ctypes.c_int64(cp), ctypes.c_int64(x.numel() // cp),
+                                      L.stream_ptr(x.device)), "pcb_channel_stats")
+
+
+def _k_bn_act_fwd(x, scale, shift, slope, out):
+    cp = int(x.shape[-1])
+    L.check(L.lib().pcb_bn_act_fwd(L.ptr(x), L.ptr(scale), L.ptr(shift), L.ptr(slope), L.ptr(out), ctypes.c_int64(cp),
+                                   ctypes.c_int64(x.numel() // cp), L.stream_ptr(x.device)), "pcb_bn_act_fwd")
+
+
+def _k_bn_act_bwd(dy, x, scale, shift, mean, rstd, slope, dz, red):
+    cp = int(x.shape[-1])
+    L.check(L.lib().pcb_bn_act_bwd(L.ptr(dy), L.ptr(x), L.ptr(scale), L.ptr(shift), L.ptr(mean), L.ptr(rstd), L.ptr(slope),
+                                   L.ptr(dz), L.ptr(red), ctypes.c_int64(cp), ctypes.c_int64(x.numel() // cp),
+                                   L.stream_ptr(x.device)), "pcb_bn_act_bwd")
+
+
+def _k_gn_bwd(g, x, stats, gstats, gamma, dx, dsum):
+    n, cp = int(x.shape[0]), int(x.shape[-1])
+    L.check(L.lib().pcb_gn_bwd(L.ptr(g), L.ptr(x), L.ptr(stats), L.ptr(gstats), L.ptr(gamma), L.ptr(dx), L.ptr(dsum),
+                               ctypes.c_int64(n), ctypes.c_int64(cp), ctypes.c_int64(x.numel() // (n * cp)),
+                               L.stream_ptr(x.device)), "pcb_gn_bwd")
+
+
+class GroupNormActFn(torch.autograd.Function):
+    """ADN "NDA" with ``GroupNorm(num_groups)`` + PReLU on padded channels-last bf16.  Statistics are per (sample, group):
+    the per-channel sums of ``pcb_channel_stats`` are pooled over each group's channels on the host side (tiny f64 tensors),
+    which turns the normalisation into a per-(sample, channel) affine for the BatchNorm apply kernel.  Backward: with
+    ``dz = dy * PReLU'(z)`` and the per-channel sums ``S1 = sum dz``, ``S2 = sum dz * xhat`` (``pcb_bn_act_bwd``),
+    ``dgamma = S2``, ``dbeta = S1`` and ``dx = rstd_g * (gamma_c * dz - M1_g - xhat * M2_g)`` with the group means
+    ``M1 = mean_g(gamma * dz)``, ``M2 = mean_g(gamma * dz * xhat)`` — the GroupNorm-backward kernel evaluates
+    ``gamma_c * rstd * (dz - k1 - xhat * k2)``, so it is fed ``k = M / gamma_c`` (gamma clamped away from zero, where the
+    product ``gamma_c * k`` stays exact in the kernel's f64 coefficient set-up)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, slope, num_groups, eps, c_real):
+        if abs(float(eps) - 1e-5) > 1e-12:
+            _unsupported("GroupNorm eps != 1e-5")
+        n, cp = int(x.shape[0]), int(x.shape[4])
+        v = int(x.shape[1] * x.shape[2] * x.shape[3])
+        g_, cpg = int(num_groups), int(c_real) // int(num_groups)
+        dev = x.device
+        stats = torch.zeros((n, 2, cp), device=dev, dtype=torch.float64)
+        for i in range(n):
+            _k_channel_stats(x[i], stats[i])
+        m = float(v * cpg)
+        pooled = stats[:, :, :c_real].reshape(n, 2, g_, cpg).sum(-1)                      # [n, 2, G]
+        mean_g = pooled[:, 0] / m
+        var_g = (pooled[:, 1] / m - mean_g * mean_g).clamp_min(0.0)
+        rstd_g = 1.0 / torch.sqrt(var_g + 1e-5)
+        mean_c = torch.zeros((n, cp), device=dev, dtype=torch.float64)
+        rstd_c = torch.zeros((n, cp), device=dev, dtype=torch.float64)
+        mean_c[:, :c_real] = mean_g.repeat_interleave(cpg, dim=1)
+        rstd_c[:, :c_real] = rstd_g.repeat_interleave(cpg, dim=1)
+        g64 = torch.zeros(cp, device=dev, dtype=torch.float64)
+        b64 = torch.zeros(cp, device=dev, dtype=torch.float64)
+        g64[:c_real], b64[:c_real] = gamma.detach().double(), beta.detach().double()
+        scale = (g64 * rstd_c).float().contiguous()                                       # [n, cp]; padded channels: 0
+        shift = (b64 - mean_c * g64 * rstd_c).float().contiguous()
+        slope_f = slope.detach().reshape(-1)[:1].float().contiguous()
+        out = torch.empty_like(x)
+        for i in range(n):
+            _k_bn_act_fwd(x[i], scale[i], shift[i], slope_f, out[i])
+        ctx.save_for_backward(x, scale, shift, mean_c.float().contiguous(), rstd_c.float().contiguous(), slope_f, g64, mean_g, var_g)
+        ctx.cfg = (n, cp, v, g_, cpg, int(c_real))
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, scale, shift, mean_f, rstd_f, slope_f, g64, mean_g, var_g = ctx.saved_tensors
+        n, cp, v, g_, cpg, c_real = ctx.cfg
+        dev = x.device
+        dy = dy.contiguous()
+        dz = torch.empty_like(x)
+        red = torch.zeros((n, 2 * cp + 1), device=dev, dtype=torch.float64)
+        for i in range(n):
+            _k_bn_act_bwd(dy[i], x[i], scale[i], shift[i], mean_f[i], rstd_f[i], slope_f, dz[i], red[i])
+        s1, s2 = red[:, :cp], red[:, cp:2 * cp]
+        dbeta = s1[:, :c_real].sum(0).float()
+        dgamma = s2[:, :c_real].sum(0).float()
+        dslope = red[:, 2 * cp].sum().float().reshape(1)
+        m = float(v * cpg)
+        m1 = (g64 * s1)[:, :c_real].reshape(n, g_, cpg).sum(-1) / m                       # [n, G]
+        m2 = (g64 * s2)[:, :c_real].reshape(n, g_, cpg).sum(-1) / m
+        tiny = 1e-20
+        g_safe = torch.where(g64.abs() < tiny, torch.full_like(g64, tiny), g64)
+        stats_k = torch.zeros((n, 2, cp), device=dev, dtype=torch.float64)
+        gstats_k = torch.zeros((n, 2, cp), device=dev, dtype=torch.float64)
+        mean_c = mean_g.repeat_interleave(cpg, dim=1)
+        var_c = var_g.repeat_interleave(cpg, dim=1)
+        stats_k[:, 0, :c_real] = mean_c * v
+        stats_k[:, 1, :c_real] = (var_c + mean_c * mean_c) * v
+        gstats_k[:, 0, :c_real] = m1.repeat_interleave(cpg, dim=1) / g_safe[:c_real] * v
+        gstats_k[:, 1, :c_real] = m2.repeat_interleave(cpg, dim=1) / g_safe[:c_real] * v
+        gamma_k = g_safe.float().contiguous()
+        gamma_k[c_real:] = 0.0                                                            # padded channels: dx stays 0
+        dx = torch.empty_like(x)
+        dsum = torch.zeros(cp, device=dev, dtype=torch.float64)
+        _k_gn_bwd(dz, x, stats_k, gstats_k, gamma_k, dx, dsum)
+        return dx, dgamma, dbeta, dslope, None, None, None
+
+
 # ----------------------------------------------------------------------------- MONAI-named module tree
 def _unsupported(what):
     raise NotImplementedError(f"pcb200 monai_unet: {what} is not implemented in the B200 engine yet "
-                              "(3-D, norm='batch' | 'instance', dropout at inference, upsample_mode='deconv' only).")
+                              "(3-D, norm='batch' | 'group' | 'instance', dropout at inference, upsample_mode='deconv' only).")
 
 
 class ADN(nn.Sequential):
-    """MONAI ``ADN`` with ordering "NDA" (children ``N``, ``D``, ``A``).  ``norm``: ``"batch"`` or ``"instance"`` —
+    """MONAI ``ADN`` with ordering "NDA" (children ``N``, ``D``, ``A``).  ``norm``: ``"batch"``, ``"group"`` (``GroupNormActFn``) or ``"instance"`` —
     ``InstanceNorm3d`` (no affine, no running statistics, as MONAI builds it) is BatchNorm over a batch of ONE, so each
     sample goes through the same statistics / normalise+PReLU kernels with its own statistics.  ``dropout`` > 0 is the
     identity at inference; training with it is refused (a random mask would have to reproduce torch's generator)."""
 
-    def __init__(self, channels: int, dropout, norm: str = "batch"):
+    def __init__(self, channels: int, dropout, norm: str = "batch", num_groups: int = 8):
         super().__init__()
         self.norm_kind = norm
-        self.add_module("N", nn.BatchNorm3d(channels) if norm == "batch" else nn.InstanceNorm3d(channels))
+        if norm == "group":
+            self.add_module("N", nn.GroupNorm(int(num_groups), channels))       # torch refuses channels % num_groups != 0, as MONAI does
+        else:
+            self.add_module("N", nn.BatchNorm3d(channels) if norm == "batch" else nn.InstanceNorm3d(channels))
         if dropout is not None:
             self.add_module("D", nn.Dropout(float(dropout)))
         self.add_module("A", nn.PReLU())
@@ -243,6 +353,8 @@ class ADN(nn.Sequential):
         if drop is not None and drop.p > 0 and self.training:
             _unsupported("training with dropout > 0")
         bn = self.N
+        if self.norm_kind == "group":
+            return GroupNormActFn.apply(x, bn.weight, bn.bias, self.A.weight, int(bn.num_groups), float(bn.eps), int(bn.num_channels))
         if self.norm_kind == "instance":
             outs = [BnActFn.apply(x[n:n + 1], self._one, self._zero, self.A.weight, self._rm, self._rv, True, 0.0,
                                   float(bn.eps), int(bn.num_features)) for n in range(int(x.shape[0]))]
@@ -254,7 +366,7 @@ class ADN(nn.Sequential):
 
 class Convolution(nn.Sequential):
     def __init__(self, in_channels, out_channels, strides=1, kernel_size=3, dropout=0.0, bias=True, conv_only=False,
-                 is_transposed=False, norm: str = "batch"):
+                 is_transposed=False, norm: str = "batch", num_groups: int = 8):
         super().__init__()
         pad = (kernel_size - 1) // 2
         if is_transposed:
@@ -264,7 +376,7 @@ class Convolution(nn.Sequential):
             conv = nn.Conv3d(in_channels, out_channels, kernel_size, stride=strides, padding=pad, bias=bias)
         self.add_module("conv", conv)
         if not conv_only:
-            self.add_module("adn", ADN(out_channels, dropout, norm))
+            self.add_module("adn", ADN(out_channels, dropout, norm, num_groups))
         self._cfg = (kernel_size, strides, pad, bool(is_transposed))
 
     def forward(self, x):
@@ -280,14 +392,15 @@ class Convolution(nn.Sequential):
 
 class ResidualUnit(nn.Module):
     def __init__(self, in_channels, out_channels, strides=1, kernel_size=3, subunits=2, dropout=0.0, bias=True,
-                 last_conv_only=False, norm: str = "batch"):
+                 last_conv_only=False, norm: str = "batch", num_groups: int = 8):
         super().__init__()
         self.conv = nn.Sequential()
         self.residual: nn.Module = nn.Identity()
         sch, sst = in_channels, strides
         for su in range(max(1, subunits)):
             only = last_conv_only and su == max(1, subunits) - 1
-            self.conv.add_module(f"unit{su:d}", Convolution(sch, out_channels, sst, kernel_size, dropout, bias, only, norm=norm))
+            self.conv.add_module(f"unit{su:d}", Convolution(sch, out_channels, sst, kernel_size, dropout, bias, only, norm=norm,
+                                                                num_groups=num_groups))
             sch, sst = out_channels, 1
         self._res_cfg = None
         if strides != 1 or in_channels != out_channels:
@@ -331,10 +444,13 @@ class UNet(nn.Module):
         super().__init__()
         if spatial_dims != 3:
             _unsupported("spatial_dims != 3")
+        norm_kw = dict(norm[1]) if isinstance(norm, (tuple, list)) and len(norm) > 1 else {}
         norm = str(norm[0] if isinstance(norm, (tuple, list)) else norm).lower()
-        if norm not in ("batch", "instance"):
+        if norm not in ("batch", "instance", "group"):
             _unsupported(f"norm={norm!r}")
-        self.norm = norm
+        if norm == "group" and "num_groups" not in norm_kw:
+            raise TypeError("GroupNorm.__init__() missing 1 required positional argument: 'num_groups'")   # MONAI / torch behaviour
+        self.norm, self.num_groups = norm, int(norm_kw.get("num_groups", 8))
         if kernel_size != 3 or up_kernel_size != 3:
             _unsupported("kernel_size != 3")
         if len(channels) < 2:
@@ -361,15 +477,16 @@ class UNet(nn.Module):
 
     def _down(self, i, o, s):
         if self.num_res_units > 0:
-            return ResidualUnit(i, o, s, self.kernel_size, self.num_res_units, self.dropout, self.bias, norm=self.norm)
-        return Convolution(i, o, s, self.kernel_size, self.dropout, self.bias, norm=self.norm)
+            return ResidualUnit(i, o, s, self.kernel_size, self.num_res_units, self.dropout, self.bias, norm=self.norm,
+                                num_groups=self.num_groups)
+        return Convolution(i, o, s, self.kernel_size, self.dropout, self.bias, norm=self.norm, num_groups=self.num_groups)
 
     def _up(self, i, o, s, is_top):
         conv = Convolution(i, o, s, 3, self.dropout, self.bias, conv_only=is_top and self.num_res_units == 0,
-                           is_transposed=True, norm=self.norm)
+                           is_transposed=True, norm=self.norm, num_groups=self.num_groups)
         if self.num_res_units > 0:
             return nn.Sequential(conv, ResidualUnit(o, o, 1, self.kernel_size, 1, self.dropout, self.bias, last_conv_only=is_top,
-                                                    norm=self.norm))
+                                                    norm=self.norm, num_groups=self.num_groups))
         return conv
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -413,6 +530,8 @@ def build_monai_unet(cfg) -> ConnectomicsModel:
     if mode and mode != "deconv":
         _unsupported(f"upsample_mode={mode!r}")
     norm = getattr(m, "norm", "batch")
+    if norm == "group":                                   # monai_models.py:74-81 _resolve_norm
+        norm = ("group", {"num_groups": getattr(m, "num_groups", 8)})
     model = UNet(spatial_dims=dims, in_channels=cfg.model.in_channels, out_channels=cfg.model.out_channels,
                  channels=channels, strides=[2] * (len(channels) - 1), num_res_units=getattr(m, "num_res_units", 2),
                  kernel_size=getattr(m, "kernel_size", 3), norm=norm, dropout=getattr(m, "dropout", 0.0))

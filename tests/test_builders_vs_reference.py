@@ -104,7 +104,8 @@ def _ucfg(filters=(16, 32, 64), input_size=(32, 64, 64), in_channels=1, out_chan
 UNET_GOOD = [_ucfg(num_res_units=1, kernel_size=3, norm="batch", dropout=0.0),          # tutorials/minimal.yaml
              _ucfg(filters=(8, 16, 32, 64), in_channels=2, out_channels=3),              # defaults: 2 residual units
              _ucfg(filters=(16, 32), num_res_units=0), _ucfg(input_size=None, spatial_dims=3, num_res_units=1),
-             _ucfg(num_res_units=1, norm="instance", dropout=0.1)]                        # no norm parameters; dropout module kept
+             _ucfg(num_res_units=1, norm="instance", dropout=0.1),                        # no norm parameters; dropout module kept
+             _ucfg(num_res_units=1, norm="group", num_groups=4, out_channels=4), _ucfg(num_res_units=2, norm="group", out_channels=8)]
 
 
 @pytest.mark.parametrize("i", range(len(UNET_GOOD)))
@@ -138,3 +139,14 @@ def test_multihead_golden_is_reproducible_from_the_real_wrapper():
     for k in G.HEADS:
         assert np.allclose(out[k].detach().numpy(), gold[f"out_{k}"], rtol=1e-5, atol=1e-6)
     assert list(gold["grad_names"]) == [n for n, p in net.named_parameters() if not n.startswith("model.out_") and n != "model.dummy_tensor"]
+
+
+def test_group_norm_needs_divisible_channels_like_the_real_builder():
+    """`norm: group` with the default 8 groups and a 1-channel output: MONAI's top up-sampling layer normalises the OUTPUT
+    channels, so torch refuses the GroupNorm — same refusal from both builders."""
+    import pytorch_connectomics_b200.architectures as A
+    R = ref_loader.ref_monai_models()
+    cfg = _ucfg(num_res_units=1, norm="group", out_channels=1)
+    want = _outcome(lambda: R.build_monai_unet(cfg))
+    got = _outcome(lambda: A.get_architecture_builder("monai_unet")(cfg))
+    assert want[0] == "ValueError" and want == got

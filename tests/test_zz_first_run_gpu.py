@@ -392,3 +392,42 @@ def test_monai_unet_instance_norm_and_inference_dropout():
     drop.train()
     with pytest.raises(NotImplementedError, match="dropout"):
         drop(x.to(DEV))
+
+
+def test_monai_unet_group_norm_matches_oracle():
+    """`model.monai.norm: group` (`monai_models.py:74-81` -> MONAI `("group", {"num_groups": g})`): GroupNorm + PReLU composed
+    from the BatchNorm kernels (`GroupNormActFn`; its arithmetic is checked on the CPU against torch by
+    `test_monai_groupnorm_math.py`), forward in both modes and every parameter gradient against the oracle UNet."""
+    from oracle.monai_unet_oracle import UNet as OracleUNet
+    from pytorch_connectomics_b200.architectures import monai_unet as PM
+    kw = dict(spatial_dims=3, in_channels=1, out_channels=8, channels=[16, 32, 64], strides=[2, 2], num_res_units=1,
+              norm=("group", {"num_groups": 8}))
+    torch.manual_seed(4)
+    ref, net = OracleUNet(**kw), PM.UNet(**kw)
+    assert list(ref.state_dict().keys()) == list(net.state_dict().keys())
+    with torch.no_grad():
+        for k, p in ref.named_parameters():
+            if k.endswith("adn.N.weight"):
+                p.uniform_(0.5, 1.5)
+            elif k.endswith("adn.N.bias"):
+                p.uniform_(-0.3, 0.3)
+    net.load_state_dict(ref.state_dict(), strict=True)
+    net.to(DEV)
+    x = torch.rand(2, 1, 16, 32, 32)
+    g = torch.randn(2, 8, 16, 32, 32)
+    rel = lambda a, b: float((a.detach().float().cpu() - b.detach()).norm() / b.detach().norm().clamp_min(1e-12))
+    with torch.no_grad():
+        want, got = ref(x), net(x.to(DEV))
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            want_bf = ref(x).float()
+    e, eb = rel(got, want), rel(want_bf, want)
+    print(f"monai_unet group norm forward: engine {e:.3e}  reference-bf16-path {eb:.3e}")
+    assert e <= 1.5 * eb + 4e-3
+    ref.zero_grad(); net.zero_grad()
+    (ref(x) * g).sum().backward()
+    (net(x.to(DEV)).float() * g.to(DEV)).sum().backward()
+    num = den = 0.0
+    for (k, pr), pn in zip(ref.named_parameters(), net.parameters()):
+        num += float((pn.grad.float().cpu() - pr.grad).norm() ** 2); den += float(pr.grad.norm() ** 2)
+    print(f"monai_unet group norm: all-parameter gradient rel-L2 vs fp32 oracle {(num / den) ** 0.5:.3e}")
+    assert (num / den) ** 0.5 < 5e-2
