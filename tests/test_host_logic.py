@@ -379,7 +379,10 @@ def test_monai_unet_builder_and_state_dict_keys():
     assert m.get_model_info()["parameters"] == sum(p.numel() for p in ref.parameters())
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(torch.zeros(1, 1, 32, 64, 64))
-    cfg.model.monai.norm = "group"
+    cfg.model.monai.norm = "group"            # 8 groups by default: torch refuses GroupNorm(8, 1) at the 1-channel output, as MONAI does
+    with pytest.raises(ValueError, match="divisible by num_groups"):
+        A.build_model(cfg)
+    cfg.model.monai.norm, cfg.model.monai.upsample_mode = "batch", "nontrainable"
     with pytest.raises(NotImplementedError):
         A.build_model(cfg)
 
