@@ -86,6 +86,15 @@ def as_channels_last(x: torch.Tensor) -> torch.Tensor:
     return y
 
 
+def as_channels_last_2d(x: torch.Tensor) -> torch.Tensor:
+    """2-D networks run as depth-1 volumes: accept the internal [N,1,H,W,C] tensor or an NCHW tensor (lifted to N,C,1,H,W)."""
+    if getattr(x, "_pcb_cl", False):
+        return x
+    if x.dim() != 4:
+        raise ValueError(f"expected a 4-D (N, C, H, W) tensor, got shape {tuple(x.shape)}")
+    return as_channels_last(x.unsqueeze(2))
+
+
 def _mark(t: torch.Tensor) -> torch.Tensor:
     t._pcb_cl = True
     return t

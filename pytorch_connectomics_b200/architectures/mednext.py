@@ -29,7 +29,27 @@ from . import _mednext_ops as ops
 
 def _unsupported(what: str):
     raise NotImplementedError(
-        f"pcb200 MedNeXt: {what} is not implemented in the B200 engine yet (3-D, GroupNorm, no GRN only).")
+        f"pcb200 MedNeXt: {what} is not implemented in the B200 engine yet (3-D / 2-D, GroupNorm(C groups) | LayerNorm, no GRN).")
+
+
+# ----------------------------------------------------------------------------- dim="2d" (upstream blocks.py: Conv2d / ConvTranspose2d)
+# A 2-D network is the 3-D one on a volume of depth 1.  With zero padding only the centre z-plane of a k^3 stencil ever meets
+# data (same, stride-2 and transposed stride-2 alike: out z = 0 pairs input z = 0 with tap k//2), so the 2-D depthwise weight
+# [C,1,k,k] is lifted to [C,1,k,k,k] with zero off-centre planes and every kernel runs unchanged; GroupNorm statistics, the
+# 1x1 convolutions and the heads see the same H*W voxels.  The lift is a differentiable view (unsqueeze + pad), so autograd
+# returns the centre plane of the 3-D weight gradient to the 2-D parameter.  The one geometric difference is the up block:
+# the 3-D kernel front-pads its output along z as well (depth 2, plane 0 = padding) — plane 1 is the 2-D result.
+def _lift_dw(w: torch.Tensor) -> torch.Tensor:
+    p = int(w.shape[-1]) // 2
+    return torch.nn.functional.pad(w.unsqueeze(2), (0, 0, 0, 0, p, p))
+
+
+def _conv(dim: str):
+    return nn.Conv2d if dim == "2d" else nn.Conv3d
+
+
+def _convt(dim: str):
+    return nn.ConvTranspose2d if dim == "2d" else nn.ConvTranspose3d
 
 
 class LayerNorm(nn.Module):
@@ -57,8 +77,8 @@ class MedNeXtBlock(nn.Module):
                  do_res: bool = True, norm_type: str = "group", n_groups=None, dim: str = "3d",
                  grn: bool = False):
         super().__init__()
-        if dim != "3d":
-            _unsupported("dim='2d'")
+        if dim not in ("2d", "3d"):
+            raise ValueError(f"dim must be '2d' or '3d', got {dim!r}")
         if norm_type not in ("group", "layer"):
             raise ValueError(f"norm_type must be 'group' or 'layer', got {norm_type!r}")
         if grn:
@@ -68,16 +88,18 @@ class MedNeXtBlock(nn.Module):
         self.do_res = do_res
         self.dim = dim
         self.grn = grn
-        self.conv1 = nn.Conv3d(in_channels, in_channels, kernel_size, 1, kernel_size // 2, groups=in_channels)
+        conv = _conv(dim)
+        self.conv1 = conv(in_channels, in_channels, kernel_size, 1, kernel_size // 2, groups=in_channels)
         self.norm_type = norm_type
         self.norm = (nn.GroupNorm(num_groups=in_channels, num_channels=in_channels) if norm_type == "group"
                      else LayerNorm(in_channels))
-        self.conv2 = nn.Conv3d(in_channels, exp_r * in_channels, 1)
+        self.conv2 = conv(in_channels, exp_r * in_channels, 1)
         self.act = nn.GELU()
-        self.conv3 = nn.Conv3d(exp_r * in_channels, out_channels, 1)
+        self.conv3 = conv(exp_r * in_channels, out_channels, 1)
 
     def _params(self) -> List[torch.Tensor]:
-        p = [self.conv1.weight, self.conv1.bias, self.norm.weight, self.norm.bias,
+        w1 = _lift_dw(self.conv1.weight) if self.dim == "2d" else self.conv1.weight     # 1x1 weights reshape to [O, I] as they are
+        p = [w1, self.conv1.bias, self.norm.weight, self.norm.bias,
              self.conv2.weight, self.conv2.bias, self.conv3.weight, self.conv3.bias]
         rc = getattr(self, "res_conv", None)
         if rc is not None:
@@ -86,8 +108,13 @@ class MedNeXtBlock(nn.Module):
 
     def forward(self, x: torch.Tensor, skip: Optional[torch.Tensor] = None) -> torch.Tensor:
         has_rc = getattr(self, "res_conv", None) is not None
-        return ops.block_apply(x, skip, self._params(), self._dw_mode, self.conv1.kernel_size[0],
-                               bool(self.do_res), has_rc, self.norm_type)
+        plane = self.dim == "2d" and self._dw_mode == L.DW_UP
+        if plane and skip is not None:      # depth-2 skip whose plane 1 is the encoder feature (plane 0 only meets padding)
+            skip = ops.as_channels_last_2d(skip)
+            skip = ops._mark(torch.cat([torch.zeros_like(skip), skip], dim=1))
+        out = ops.block_apply(x, skip, self._params(), self._dw_mode, self.conv1.kernel_size[0],
+                              bool(self.do_res), has_rc, self.norm_type)
+        return ops._mark(out[:, 1:2].contiguous()) if plane else out
 
 
 class MedNeXtDownBlock(MedNeXtBlock):
@@ -101,8 +128,8 @@ class MedNeXtDownBlock(MedNeXtBlock):
                          norm_type=norm_type, dim=dim, grn=grn)
         self.resample_do_res = do_res
         if do_res:
-            self.res_conv = nn.Conv3d(in_channels, out_channels, 1, stride=2)
-        self.conv1 = nn.Conv3d(in_channels, in_channels, kernel_size, 2, kernel_size // 2, groups=in_channels)
+            self.res_conv = _conv(dim)(in_channels, out_channels, 1, stride=2)
+        self.conv1 = _conv(dim)(in_channels, in_channels, kernel_size, 2, kernel_size // 2, groups=in_channels)
 
 
 class MedNeXtUpBlock(MedNeXtBlock):
@@ -117,23 +144,26 @@ class MedNeXtUpBlock(MedNeXtBlock):
                          norm_type=norm_type, dim=dim, grn=grn)
         self.resample_do_res = do_res
         if do_res:
-            self.res_conv = nn.ConvTranspose3d(in_channels, out_channels, 1, stride=2)
-        self.conv1 = nn.ConvTranspose3d(in_channels, in_channels, kernel_size, 2, kernel_size // 2,
-                                        groups=in_channels)
+            self.res_conv = _convt(dim)(in_channels, out_channels, 1, stride=2)
+        self.conv1 = _convt(dim)(in_channels, in_channels, kernel_size, 2, kernel_size // 2, groups=in_channels)
 
 
 class OutBlock(nn.Module):
-    """upstream blocks.py::OutBlock — ConvTranspose3d(C, n_classes, k=1). channels-last bf16 in,
-    NCDHW out."""
+    """upstream blocks.py::OutBlock — ConvTranspose3d(C, n_classes, k=1) (ConvTranspose2d for ``dim="2d"``).  channels-last
+    bf16 in, NCDHW out (NCHW for 2-D: the depth-1 axis is dropped)."""
 
     def __init__(self, in_channels, n_classes, dim="3d"):
         super().__init__()
-        if dim != "3d":
-            _unsupported("dim='2d'")
-        self.conv_out = nn.ConvTranspose3d(in_channels, n_classes, 1)
+        if dim not in ("2d", "3d"):
+            raise ValueError(f"dim must be '2d' or '3d', got {dim!r}")
+        self.dim = dim
+        self.conv_out = _convt(dim)(in_channels, n_classes, 1)
 
     def forward(self, x: torch.Tensor, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
-        return ops.head_apply(x, self.conv_out.weight, self.conv_out.bias, out_dtype)
+        if self.dim == "2d":
+            x = ops.as_channels_last_2d(x)
+        y = ops.head_apply(x, self.conv_out.weight, self.conv_out.bias, out_dtype)
+        return y.squeeze(2) if self.dim == "2d" else y
 
 
 class MedNeXt(nn.Module):
@@ -153,8 +183,9 @@ class MedNeXt(nn.Module):
         # and the depthwise output, so the flag is kept for API compatibility and changes nothing.
         self.inside_block_checkpointing = False
         self.outside_block_checkpointing = checkpoint_style == "outside_block"
-        if dim != "3d":
-            _unsupported("dim='2d'")
+        if dim not in ("2d", "3d"):
+            raise ValueError(f"dim must be '2d' or '3d', got {dim!r}")
+        self.dim = dim
         if kernel_size is not None:
             enc_kernel_size = dec_kernel_size = kernel_size
         if n_channels % 16 != 0:
@@ -162,7 +193,7 @@ class MedNeXt(nn.Module):
         exp_r = [exp_r] * len(block_counts) if isinstance(exp_r, int) else list(exp_r)
         n = n_channels
         kw = dict(norm_type=norm_type, dim=dim, grn=grn)
-        self.stem = nn.Conv3d(in_channels, n, 1)
+        self.stem = _conv(dim)(in_channels, n, 1)
 
         def stage(c, i, k):
             return nn.Sequential(*[MedNeXtBlock(c, c, exp_r[i], k, do_res=do_res, **kw)
@@ -199,10 +230,15 @@ class MedNeXt(nn.Module):
     # ---- channels-last trunk
     def _trunk(self, x: torch.Tensor) -> List[torch.Tensor]:
         L.require_device(x, "MedNeXt.forward")
-        if x.dim() != 5:
+        if self.dim == "2d":
+            if x.dim() != 4:
+                raise ValueError(f"MedNeXt (dim='2d') expects (B, C, H, W); got shape {tuple(x.shape)}")
+        elif x.dim() != 5:
             raise ValueError(f"MedNeXt expects (B, C, D, H, W); got shape {tuple(x.shape)}")
         if any(int(s) % 16 for s in x.shape[2:]):
             raise ValueError(f"MedNeXt input spatial size must be divisible by 16, got {tuple(x.shape[2:])}")
+        if self.dim == "2d":
+            x = x.unsqueeze(2)        # depth-1 volume; the 1x1 stem weight [n, Cin, 1, 1] flattens to the same [n, Cin]
         x = ops.stem_apply(x, self.stem.weight, self.stem.bias)
         r0 = self.enc_block_0(x)
         x = self.down_0(r0)
@@ -224,11 +260,13 @@ class MedNeXt(nn.Module):
                                      else torch.float32)
 
     def forward_features(self, x: torch.Tensor) -> torch.Tensor:
-        """Shared full-resolution feature map [B, n, D, H, W] (NCDHW view of the channels-last tensor)."""
-        return self._trunk(x)[0].permute(0, 4, 1, 2, 3)
+        """Shared full-resolution feature map [B, n, D, H, W] (NCDHW view of the channels-last tensor; [B, n, H, W] for 2-D)."""
+        f = self._trunk(x)[0].permute(0, 4, 1, 2, 3)
+        return f.squeeze(2) if self.dim == "2d" else f
 
     def forward_output(self, features: torch.Tensor) -> torch.Tensor:
-        return self.out_0(ops.as_channels_last(features), torch.float32 if features.dtype == torch.bfloat16
+        cl = ops.as_channels_last_2d if self.dim == "2d" else ops.as_channels_last
+        return self.out_0(cl(features), torch.float32 if features.dtype == torch.bfloat16
                           and self.output_dtype is None else (self.output_dtype or features.dtype))
 
     def forward(self, x: torch.Tensor):
@@ -335,23 +373,23 @@ class MedNeXtTaskHead(nn.Module):
                              f"({hidden_channels} > {in_channels})")
         if dim not in ("2d", "3d"):
             raise ValueError(f"MedNeXt task head dim must be '2d' or '3d', got {dim}")
-        if dim != "3d":
-            _unsupported("dim='2d'")
-        self.input_projection = (nn.Conv3d(in_channels, hidden_channels, 1)
+        self.dim = dim
+        self.input_projection = (_conv(dim)(in_channels, hidden_channels, 1)
                                  if hidden_channels != in_channels else nn.Identity())
         blocks = [MedNeXtBlock(hidden_channels, hidden_channels, exp_r, kernel_size, do_res=do_res,
                                norm_type=norm_type, dim=dim, grn=grn) for _ in range(num_blocks)]
         self.blocks = nn.Sequential(*blocks) if blocks else nn.Identity()
-        self.projection = nn.Conv3d(hidden_channels, out_channels, 1)
+        self.projection = _conv(dim)(hidden_channels, out_channels, 1)
         self.hidden_channels = hidden_channels
 
     def forward(self, x: torch.Tensor, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
-        x = ops.as_channels_last(x)
+        x = ops.as_channels_last_2d(x) if self.dim == "2d" else ops.as_channels_last(x)
         if not isinstance(self.input_projection, nn.Identity):
             x = ops.pointwise_apply(x, self.input_projection.weight, self.input_projection.bias)
         x = self.blocks(x)
         # Conv3d weight is [out, in, 1,1,1]; the head kernel takes the ConvTranspose layout [in, out]
-        return ops.head_apply(x, self.projection.weight, self.projection.bias, out_dtype, conv_layout=True)
+        y = ops.head_apply(x, self.projection.weight, self.projection.bias, out_dtype, conv_layout=True)
+        return y.squeeze(2) if self.dim == "2d" else y
 
 
 def _infer_head_block_kwargs(model: nn.Module) -> Dict[str, Any]:

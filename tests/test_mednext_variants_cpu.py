@@ -1,0 +1,107 @@
+"""Host logic of the MedNeXt variants that are COMPOSED above the kernels — ``dim="2d"`` (depth-1 lift) and ``grn=True`` —
+checked in fp32 on the CPU against the oracle network (``oracle/mednext_oracle.py``, upstream's blocks restated): same
+``state_dict`` keys and shapes (``strict=True``), same outputs, same parameter gradients.  The kernels are replaced by the
+torch stand-ins of ``tests/mednext_cpu_doubles.py``; the GPU runs of the same modules are in ``test_zz_first_run_gpu.py``."""
+
+import pytest
+import torch
+
+import mednext_cpu_doubles as doubles
+from oracle import mednext_oracle as O
+from pytorch_connectomics_b200.architectures import mednext as M
+
+
+def _pair(monkeypatch, seed=0, **kw):
+    doubles.install(monkeypatch)
+    torch.manual_seed(seed)
+    args = dict(in_channels=2, n_channels=16, n_classes=3, exp_r=2, kernel_size=3, do_res=True, do_res_up_down=True,
+                block_counts=[1] * 9)
+    args.update(kw)
+    ref = O.MedNeXt(**args)
+    with torch.no_grad():
+        for name, p in ref.named_parameters():      # GRN parameters start at zero upstream: make every term count
+            if "grn" in name:
+                p.normal_(0.0, 0.5)
+    net = M.MedNeXt(**args)
+    net.load_state_dict(ref.state_dict(), strict=True)
+    return ref.float(), net.float()
+
+
+def _close(a, b, tol=2e-4, scale=None):
+    a, b = a.detach(), b.detach()
+    scale = max(float(b.abs().max()), 1e-6) if scale is None else scale
+    assert tuple(a.shape) == tuple(b.shape)
+    assert float((a - b).abs().max()) <= tol * scale, (float((a - b).abs().max()), scale)
+
+
+def _compare_grads(ref, net, tol=5e-4):
+    """every parameter gradient, against the largest gradient entry of the network (a bias in front of a normalisation has
+    an analytically zero gradient: fp32 noise there is not an error)"""
+    got = dict(net.named_parameters())
+    want = {n: p for n, p in ref.named_parameters() if n != "dummy_tensor"}
+    scale = max(float(p.grad.abs().max()) for p in want.values())
+    assert scale > 0
+    for name, p in want.items():
+        assert got[name].grad is not None, name
+        _close(got[name].grad, p.grad, tol, scale=max(scale * 1e-2, float(p.grad.abs().max())))
+
+
+@pytest.mark.parametrize("norm_type,ds", [("group", False), ("group", True), ("layer", False)])
+def test_2d_network_equals_the_oracle(monkeypatch, norm_type, ds):
+    ref, net = _pair(monkeypatch, norm_type=norm_type, deep_supervision=ds, dim="2d")
+    assert net.stem.weight.dim() == 4 and net.enc_block_0[0].conv1.weight.shape == (16, 1, 3, 3)
+    x = torch.randn(2, 2, 32, 48)
+    want, got = ref(x), net(x)
+    if ds:
+        assert len(got) == 5
+        for g, w in zip(got, want):
+            _close(g, w)
+        sum(g.square().mean() for g in got).backward()
+        sum(w.square().mean() for w in want).backward()
+    else:
+        _close(got, want)
+        got.square().mean().backward()
+        want.square().mean().backward()
+    _compare_grads(ref, net)
+
+
+def test_2d_features_and_output_split(monkeypatch):
+    ref, net = _pair(monkeypatch, dim="2d")
+    x = torch.randn(1, 2, 16, 32)
+    with torch.no_grad():
+        f = net.forward_features(x)
+        assert tuple(f.shape) == (1, 16, 16, 32)
+        _close(f, ref.forward_features(x))
+        _close(net.forward_output(f), ref(x))
+
+
+def test_2d_refuses_volumes_and_bad_sizes(monkeypatch):
+    _, net = _pair(monkeypatch, dim="2d")
+    with pytest.raises(ValueError, match=r"\(B, C, H, W\)"):
+        net(torch.randn(1, 2, 16, 16, 16))
+    with pytest.raises(ValueError, match="divisible by 16"):
+        net(torch.randn(1, 2, 16, 24))
+    with pytest.raises(ValueError, match="dim must be"):
+        M.MedNeXtBlock(16, 16, dim="4d")
+
+
+def test_2d_task_heads(monkeypatch):
+    """MedNeXtMultiHeadWrapper over a 2-D trunk: head blocks inherit dim from dec_block_0 (mednext_models.py:99-126) and the
+    heads return NCHW maps equal to the same modules evaluated with torch's 2-D convolutions."""
+    import torch.nn.functional as F
+    ref, net = _pair(monkeypatch, dim="2d")
+    wrap = M.MedNeXtMultiHeadWrapper(net, {"a": {"out_channels": 2, "num_blocks": 1}, "b": {"out_channels": 1, "hidden_channels": 16}})
+    assert wrap.head_block_kwargs["dim"] == "2d"
+    x = torch.randn(1, 2, 32, 32)
+    with torch.no_grad():
+        out = wrap(x)["output"]
+        f = ref.forward_features(x)
+        hb = wrap.heads["b"]
+        _close(out["b"], F.conv2d(f, hb.projection.weight, hb.projection.bias))
+        ha = wrap.heads["a"]
+        blk = O.MedNeXtBlock(16, 16, exp_r=2, kernel_size=3, do_res=True, dim="2d")
+        blk.load_state_dict(ha.blocks[0].state_dict(), strict=True)
+        _close(out["a"], F.conv2d(blk(f), ha.projection.weight, ha.projection.bias))
+        assert tuple(out["a"].shape) == (1, 2, 32, 32)
+        heads = wrap.forward_heads(wrap.forward_features(x))
+        _close(heads["a"], out["a"])

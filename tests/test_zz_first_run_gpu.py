@@ -431,3 +431,46 @@ def test_monai_unet_group_norm_matches_oracle():
         num += float((pn.grad.float().cpu() - pr.grad).norm() ** 2); den += float(pr.grad.norm() ** 2)
     print(f"monai_unet group norm: all-parameter gradient rel-L2 vs fp32 oracle {(num / den) ** 0.5:.3e}")
     assert (num / den) ** 0.5 < 5e-2
+
+
+# ----------------------------------------------------------------------------- MedNeXt dim="2d" (depth-1 lift onto the 3-D kernels)
+@pytest.mark.parametrize("norm_type", ["group", "layer"])
+def test_mednext_2d_matches_oracle(norm_type):
+    """``model.mednext.dim: 2d`` (mednext_models.py:461): Conv2d / ConvTranspose2d parameter shapes (``strict=True`` load of the
+    oracle's 2-D ``state_dict``), forward + every parameter gradient against the fp32 CPU oracle's 2-D network.  The kernels
+    are the 3-D ones on a depth-1 volume with the depthwise weight lifted to a centre-plane k^3 stencil; the CPU suite checks
+    that lift in fp32 (``test_mednext_variants_cpu.py``), this run checks it on the kernels (D = 1 tiles, depth-2 up-block
+    output) under the bf16 bound the 3-D tiny net meets."""
+    from oracle.mednext_oracle import MedNeXt as OracleNet
+    from pytorch_connectomics_b200.architectures.mednext import MedNeXt
+    torch.manual_seed(5)
+    kw = dict(in_channels=2, n_channels=16, n_classes=3, exp_r=2, kernel_size=3, deep_supervision=True, do_res=True,
+              do_res_up_down=True, block_counts=[1] * 9, norm_type=norm_type, dim="2d")
+    ref = OracleNet(**kw).train()
+    net = MedNeXt(**kw).train()
+    net.load_state_dict(ref.state_dict(), strict=True)
+    net.to(DEV)
+    x = torch.rand(2, 2, 64, 96)
+    want = ref(x)
+    got = net(x.to(DEV))
+    assert len(got) == 5
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert tuple(g.shape) == tuple(w.shape)
+        err = float((g.float().cpu() - w).norm() / w.norm())
+        print(f"2-D {norm_type} output {i}: rel-L2 vs fp32 oracle {err:.3e}")
+        assert err < 3e-2, (i, err)
+    sum(w.square().mean() for w in want).backward()
+    sum(g.float().square().mean() for g in got).backward()
+    params = dict(net.named_parameters())
+    worst = 0.0
+    for name, p in ref.named_parameters():
+        if name == "dummy_tensor" or float(p.grad.norm()) < 1e-6:
+            continue
+        g = params[name].grad
+        assert g is not None and tuple(g.shape) == tuple(p.shape), name
+        worst = max(worst, float((g.float().cpu() - p.grad).norm() / p.grad.norm()))
+    print(f"2-D {norm_type}: worst parameter-gradient rel-L2 {worst:.3e}")
+    assert worst < 1e-1, worst
+    with torch.no_grad():       # inference path (no autograd wrappers) gives the same maps as the training path
+        again = net.eval()(x.to(DEV))
+    assert float((again[0].float() - got[0].float()).abs().max()) <= 1e-2 * float(got[0].float().abs().max())
