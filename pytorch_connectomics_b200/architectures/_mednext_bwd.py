@@ -253,6 +253,67 @@ class BlockFn(torch.autograd.Function):
         return (dx, dskip, None, None, None, None, None, *grads)
 
 
+class DwConvFn(torch.autograd.Function):
+    """The depthwise stencil alone (composed blocks): forward ``pcb_dwconv_fwd``; backward = the three kernels ``BlockFn``
+    runs for conv1 — tap weight gradient, bias gradient (per-channel sum of dy), data gradient (the dual stencil)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, mode, k):
+        y = ops.dwconv_forward(x, w1, b1, mode, k)
+        ctx.save_for_backward(x, w1)
+        ctx.cfg = (mode, k)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w1 = ctx.saved_tensors
+        mode, k = ctx.cfg
+        dy = _cl_grad(dy)
+        dev, lib, st = x.device, L.lib(), L.stream_ptr(x.device)
+        n, xsize, c = int(x.shape[0]), [int(s) for s in x.shape[1:4]], int(x.shape[4])
+        ysize = [int(s) for s in dy.shape[1:4]]
+        vy = ysize[0] * ysize[1] * ysize[2]
+        dw1 = torch.zeros((k * k * k, c), device=dev, dtype=torch.float64)
+        if mode == L.DW_UP:
+            cen, nei, csz, nsz, stride = x, dy, xsize, ysize, 2
+        else:
+            cen, nei, csz, nsz, stride = dy, x, ysize, xsize, (2 if mode == L.DW_DOWN else 1)
+        L.check(lib.pcb_dwconv_wgrad(L.ptr(cen), L.ptr(nei), L.ptr(dw1), ctypes.c_int64(n), L.i64x(csz), L.i64x(nsz),
+                                     ctypes.c_int64(c), k, stride, st), "pcb_dwconv_wgrad")
+        cs = torch.zeros((2, c), device=dev, dtype=torch.float64)
+        L.check(lib.pcb_channel_stats(L.ptr(dy), L.ptr(cs), ctypes.c_int64(c), ctypes.c_int64(n * vy), st), "pcb_channel_stats")
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            wk = ops.packed(w1, "dw_flip" if mode == L.DW_SAME else "dw")
+            L.check(lib.pcb_dwconv_bwd_data(L.ptr(dy), L.ptr(wk), None, 0, L.ptr(dx), ctypes.c_int64(n), L.i64x(ysize),
+                                            L.i64x(xsize), ctypes.c_int64(c), k, mode, st), "pcb_dwconv_bwd_data")
+        return dx, dw1.t().reshape(w1.shape).float(), cs[0].float(), None, None
+
+
+class LayerNormFn(torch.autograd.Function):
+    """Channels-first LayerNorm alone (composed blocks): ``pcb_layernorm_fwd`` / ``pcb_layernorm_bwd``."""
+
+    @staticmethod
+    def forward(ctx, y, gamma, beta):
+        out = ops.layernorm_forward(y, gamma, beta)
+        ctx.save_for_backward(y, gamma)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        y, gamma = ctx.saved_tensors
+        dout = _cl_grad(dout)
+        c = int(y.shape[-1])
+        dy = torch.empty_like(y)
+        dg64 = torch.zeros((c,), device=y.device, dtype=torch.float64)
+        db64 = torch.zeros((c,), device=y.device, dtype=torch.float64)
+        L.check(L.lib().pcb_layernorm_bwd(L.ptr(dout), L.ptr(y), L.ptr(ops.packed(gamma, "f32")), L.ptr(dy), L.ptr(dg64),
+                                          L.ptr(db64), ctypes.c_int64(c), ctypes.c_int64(y.numel() // c),
+                                          L.stream_ptr(y.device)), "pcb_layernorm_bwd")
+        return dy, dg64.float(), db64.float()
+
+
 class StemFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b):

@@ -218,6 +218,19 @@ def block_forward(x: torch.Tensor, skip: Optional[torch.Tensor], params: List[to
     return _mark(out), y, stats
 
 
+def dwconv_forward(x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, mode: int, k: int) -> torch.Tensor:
+    """The depthwise stencil ALONE (``pcb_dwconv_fwd``: same / stride-2 / transposed stride-2), for blocks that are composed
+    kernel by kernel (GRN) instead of running the fused block."""
+    n, size, c = int(x.shape[0]), [int(s) for s in x.shape[1:4]], int(x.shape[4])
+    ysize, _ = _out_size(mode, k, size)
+    y = torch.empty((n, *ysize, c), device=x.device, dtype=_BF16)
+    stats = torch.zeros((n, 2, c), device=x.device, dtype=torch.float64)
+    L.check(L.lib().pcb_dwconv_fwd(L.ptr(x), L.ptr(packed(w1, "dw")), L.ptr(packed(b1, "f32")), L.ptr(y), L.ptr(stats),
+                                   ctypes.c_int64(n), L.i64x(size), ctypes.c_int64(c), ctypes.c_int(k), ctypes.c_int(mode),
+                                   L.stream_ptr(x.device)), "pcb_dwconv_fwd")
+    return _mark(y)
+
+
 def head_forward(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, out_dtype: torch.dtype,
                  conv_layout: bool = False) -> torch.Tensor:
     n, c = int(x.shape[0]), int(x.shape[4])
@@ -252,6 +265,35 @@ def block_apply(x, skip, params, mode, k, do_res, has_rc, norm="group"):
         from . import _mednext_bwd as B
         return _mark(B.BlockFn.apply(x, skip, mode, k, do_res, has_rc, norm, *params))
     return block_forward(x, skip, params, mode, k, do_res, has_rc, norm)[0]
+
+
+def dwconv_apply(x, w1, b1, mode, k):
+    x = as_channels_last(x)
+    if _needs_grad(x, w1, b1):
+        from . import _mednext_bwd as B
+        return _mark(B.DwConvFn.apply(x, w1, b1, mode, k))
+    return dwconv_forward(x, w1, b1, mode, k)
+
+
+_ONE: Dict[str, torch.Tensor] = {}
+
+
+def norm_apply(y, gamma, beta, norm):
+    """The block's normalisation ALONE on channels-last bf16: ``GroupNorm(C groups)`` through the statistics / per-channel
+    affine kernels (``GroupNormActFn`` of the dense-conv family with a PReLU slope of 1, i.e. no activation) or the
+    channels-first LayerNorm kernel — with their backward kernels under autograd."""
+    y = as_channels_last(y)
+    if norm == "layer":
+        if _needs_grad(y, gamma, beta):
+            from . import _mednext_bwd as B
+            return _mark(B.LayerNormFn.apply(y, gamma, beta))
+        return _mark(layernorm_forward(y, gamma, beta))
+    from .monai_unet import GroupNormActFn
+    one = _ONE.get(str(y.device))
+    if one is None:
+        one = _ONE[str(y.device)] = torch.ones(1, device=y.device, dtype=torch.float32)
+    c = int(y.shape[4])
+    return _mark(GroupNormActFn.apply(y, gamma, beta, one, c, 1e-5, c))
 
 
 def head_apply(x, w, b, out_dtype, conv_layout=False):

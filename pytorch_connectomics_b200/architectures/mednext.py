@@ -29,7 +29,7 @@ from . import _mednext_ops as ops
 
 def _unsupported(what: str):
     raise NotImplementedError(
-        f"pcb200 MedNeXt: {what} is not implemented in the B200 engine yet (3-D / 2-D, GroupNorm(C groups) | LayerNorm, no GRN).")
+        f"pcb200 MedNeXt: {what} is not implemented in the B200 engine yet (3-D / 2-D, GroupNorm(C groups) | LayerNorm, optional GRN).")
 
 
 # ----------------------------------------------------------------------------- dim="2d" (upstream blocks.py: Conv2d / ConvTranspose2d)
@@ -81,8 +81,6 @@ class MedNeXtBlock(nn.Module):
             raise ValueError(f"dim must be '2d' or '3d', got {dim!r}")
         if norm_type not in ("group", "layer"):
             raise ValueError(f"norm_type must be 'group' or 'layer', got {norm_type!r}")
-        if grn:
-            _unsupported("grn=True")
         if n_groups is not None and n_groups != in_channels:
             _unsupported("n_groups != in_channels")
         self.do_res = do_res
@@ -96,6 +94,10 @@ class MedNeXtBlock(nn.Module):
         self.conv2 = conv(in_channels, exp_r * in_channels, 1)
         self.act = nn.GELU()
         self.conv3 = conv(exp_r * in_channels, out_channels, 1)
+        if grn:      # upstream blocks.py: zero-initialised (1, rC, 1, 1[, 1]) parameters
+            shape = (1, exp_r * in_channels) + (1,) * (3 if dim == "3d" else 2)
+            self.grn_beta = nn.Parameter(torch.zeros(shape), requires_grad=True)
+            self.grn_gamma = nn.Parameter(torch.zeros(shape), requires_grad=True)
 
     def _params(self) -> List[torch.Tensor]:
         w1 = _lift_dw(self.conv1.weight) if self.dim == "2d" else self.conv1.weight     # 1x1 weights reshape to [O, I] as they are
@@ -112,9 +114,60 @@ class MedNeXtBlock(nn.Module):
         if plane and skip is not None:      # depth-2 skip whose plane 1 is the encoder feature (plane 0 only meets padding)
             skip = ops.as_channels_last_2d(skip)
             skip = ops._mark(torch.cat([torch.zeros_like(skip), skip], dim=1))
-        out = ops.block_apply(x, skip, self._params(), self._dw_mode, self.conv1.kernel_size[0],
-                              bool(self.do_res), has_rc, self.norm_type)
+        if self.grn:
+            out = self._forward_grn(x, skip, has_rc)
+        else:
+            out = ops.block_apply(x, skip, self._params(), self._dw_mode, self.conv1.kernel_size[0],
+                                  bool(self.do_res), has_rc, self.norm_type)
         return ops._mark(out[:, 1:2].contiguous()) if plane else out
+
+    def _forward_grn(self, x: torch.Tensor, skip: Optional[torch.Tensor], has_rc: bool) -> torch.Tensor:
+        """Block with Global Response Normalisation (upstream blocks.py: between GELU and conv3,
+        ``gx = ||h||_2 over space; nx = gx / (mean_channels gx + 1e-6); h <- gamma * (h * nx) + beta + h``).
+
+        The global reduction sits in the middle of what the fused block kernel keeps on chip, so a GRN block is COMPOSED
+        kernel by kernel: stencil (``pcb_dwconv_fwd``) -> norm kernels -> conv2 (``pcb_pw_fwd``, tcgen05) -> GELU -> GRN
+        statistics -> conv3 (``pcb_pw_fwd``) -> residual.  GRN itself never touches the expanded tensor again: per sample it is
+        a per-channel scale ``s = gamma * nx + 1`` and a shift ``beta``, folded into conv3 as ``W3 diag(s)`` and
+        ``b3 + W3 beta``.  GELU, the norm over space and the residual adds are elementwise / reduction tensor ops on the
+        device (not hand-written kernels yet), the expanded activation makes one HBM round trip, and backward is autograd over
+        the kernels' own backward functions — this path is for coverage of the option, not the measured one."""
+        F = torch.nn.functional
+        mode, k = self._dw_mode, int(self.conv1.kernel_size[0])
+        p = self._params()
+        x = ops.as_channels_last(x)
+        y = ops.dwconv_apply(x, p[0], p[1], mode, k)
+        a = ops.norm_apply(y, p[2], p[3], self.norm_type)
+        h = ops._mark(F.gelu(ops.pointwise_apply(a, p[4], p[5])))
+        hid, co = int(p[4].shape[0]), int(p[6].shape[0])
+        gx = torch.linalg.vector_norm(h, ord=2, dim=(1, 2, 3), dtype=torch.float32)              # [N, rC]
+        nx = gx / (gx.mean(dim=1, keepdim=True) + 1e-6)
+        s = self.grn_gamma.reshape(1, hid).float() * nx + 1.0
+        w3 = p[6].reshape(co, hid).float()
+        b3 = p[7].float() + w3 @ self.grn_beta.reshape(hid).float()
+        outs = [ops.pointwise_apply(ops._mark(h[n:n + 1]), w3 * s[n][None, :], b3) for n in range(int(h.shape[0]))]
+        o = outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
+        if mode == L.DW_SAME:
+            if self.do_res:
+                o = o + x
+            return ops._mark(o)
+        if has_rc:
+            wr, br = self.res_conv.weight, self.res_conv.bias
+            if mode == L.DW_DOWN:       # Conv(C, Co, 1, stride 2): the even-coordinate voxels through the 1x1 GEMM
+                o = o + ops.pointwise_apply(ops._mark(x[:, ::2, ::2, ::2].contiguous()), wr, br)
+            else:                       # ConvTranspose(C, Co, 1, stride 2): even output voxels get W^T x + b, the others b
+                even = ops.pointwise_apply(x, wr.reshape(wr.shape[0], wr.shape[1]).t(), br)
+                r = br.to(o.dtype).reshape(1, 1, 1, 1, co).expand(o.shape).clone()
+                r[:, ::2, ::2, ::2] = even
+                o = o + r
+        if mode == L.DW_UP:
+            o = F.pad(o, (0, 0, 1, 0, 1, 0, 1, 0))      # one voxel at the FRONT of every spatial axis
+            if skip is not None:
+                skip = ops.as_channels_last(skip)
+                if tuple(skip.shape) != tuple(o.shape):
+                    raise ValueError(f"skip shape {tuple(skip.shape)} != up-block output shape {tuple(o.shape)}")
+                o = o + skip
+        return ops._mark(o)
 
 
 class MedNeXtDownBlock(MedNeXtBlock):

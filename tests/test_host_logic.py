@@ -155,7 +155,8 @@ def test_no_cpu_fallback():
     with pytest.raises(ValueError, match="norm_type"):
         MedNeXtBlock(16, 16, 2, 3, norm_type="batch")
     with pytest.raises(NotImplementedError):
-        MedNeXtBlock(16, 16, 2, 3, grn=True)
+        MedNeXtBlock(16, 16, 2, 3, n_groups=4)
+    assert tuple(MedNeXtBlock(16, 16, 2, 3, grn=True).grn_gamma.shape) == (1, 32, 1, 1, 1)      # upstream's GRN parameters
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         blk(torch.zeros(1, 4, 4, 4, 16, dtype=torch.bfloat16))
 

@@ -105,3 +105,38 @@ def test_2d_task_heads(monkeypatch):
         assert tuple(out["a"].shape) == (1, 2, 32, 32)
         heads = wrap.forward_heads(wrap.forward_features(x))
         _close(heads["a"], out["a"])
+
+
+# ----------------------------------------------------------------------------- grn=True (composed block)
+@pytest.mark.parametrize("norm_type,dim,ds", [("group", "3d", False), ("layer", "3d", True), ("group", "2d", False)])
+def test_grn_network_equals_the_oracle(monkeypatch, norm_type, dim, ds):
+    """every block kind (same / down / up with res_conv and skip) through the composed GRN path: GRN folded into conv3 as a
+    per-sample ``W3 diag(gamma * nx + 1)`` and ``b3 + W3 beta`` equals upstream's elementwise form, values and gradients
+    (incl. the GRN parameters, which the test moves away from their zero initialisation)."""
+    ref, net = _pair(monkeypatch, norm_type=norm_type, deep_supervision=ds, dim=dim, grn=True)
+    assert tuple(net.enc_block_0[0].grn_gamma.shape) == ((1, 32, 1, 1, 1) if dim == "3d" else (1, 32, 1, 1))
+    assert float(net.down_1.grn_beta.abs().sum()) > 0
+    x = torch.randn(2, 2, 32, 32, 32) if dim == "3d" else torch.randn(2, 2, 32, 64)
+    want, got = ref(x), net(x)
+    want, got = (want, got) if ds else ([want], [got])
+    for g, w in zip(got, want):
+        _close(g, w)
+    sum(g.square().mean() for g in got).backward()
+    sum(w.square().mean() for w in want).backward()
+    _compare_grads(ref, net)
+    assert net.enc_block_0[0].grn_gamma.grad is not None and float(net.enc_block_0[0].grn_gamma.grad.abs().sum()) > 0
+
+
+def test_grn_without_residual_paths(monkeypatch):
+    ref, net = _pair(monkeypatch, do_res=False, do_res_up_down=False, grn=True)
+    x = torch.randn(1, 2, 32, 32, 32)
+    with torch.no_grad():
+        _close(net(x), ref(x))
+
+
+def test_grn_trunk_is_not_native_eligible(monkeypatch):
+    from pytorch_connectomics_b200.architectures.native import native_eligible
+    _, net = _pair(monkeypatch, grn=True)
+    assert native_eligible(net) is not None
+    _, net2 = _pair(monkeypatch, dim="2d")
+    assert native_eligible(net2) is not None

@@ -474,3 +474,49 @@ def test_mednext_2d_matches_oracle(norm_type):
     with torch.no_grad():       # inference path (no autograd wrappers) gives the same maps as the training path
         again = net.eval()(x.to(DEV))
     assert float((again[0].float() - got[0].float()).abs().max()) <= 1e-2 * float(got[0].float().abs().max())
+
+
+# ----------------------------------------------------------------------------- MedNeXt grn=True (block composed kernel by kernel)
+@pytest.mark.parametrize("norm_type,dim", [("group", "3d"), ("layer", "3d"), ("group", "2d")])
+def test_mednext_grn_matches_oracle(norm_type, dim):
+    """``model.mednext.grn: true`` (mednext_models.py:462): every block kind through ``MedNeXtBlock._forward_grn`` — stencil,
+    norm, conv2 and conv3 kernels with their own backward functions, GRN folded into conv3 per sample — against the fp32 CPU
+    oracle (upstream's elementwise GRN), forward and every parameter gradient incl. ``grn_gamma`` / ``grn_beta`` (moved off
+    their zero initialisation).  The fold itself is checked in fp32 on the CPU (``test_mednext_variants_cpu.py``)."""
+    from oracle.mednext_oracle import MedNeXt as OracleNet
+    from pytorch_connectomics_b200.architectures.mednext import MedNeXt
+    torch.manual_seed(9)
+    kw = dict(in_channels=1, n_channels=16, n_classes=2, exp_r=2, kernel_size=3, deep_supervision=False, do_res=True,
+              do_res_up_down=True, block_counts=[1] * 9, norm_type=norm_type, dim=dim, grn=True)
+    ref = OracleNet(**kw).train()
+    with torch.no_grad():
+        for name, p in ref.named_parameters():
+            if "grn" in name:
+                p.normal_(0.0, 0.5)
+    net = MedNeXt(**kw).train()
+    net.load_state_dict(ref.state_dict(), strict=True)
+    net.to(DEV)
+    x = torch.rand(2, 1, 32, 32, 32) if dim == "3d" else torch.rand(2, 1, 64, 64)
+    want = ref(x)
+    got = net(x.to(DEV))
+    assert tuple(got.shape) == tuple(want.shape)
+    err = float((got.float().cpu() - want).norm() / want.norm())
+    print(f"GRN {norm_type} {dim}: output rel-L2 vs fp32 oracle {err:.3e}")
+    assert err < 3e-2, err
+    want.square().mean().backward()
+    got.float().square().mean().backward()
+    params = dict(net.named_parameters())
+    worst, worst_name = 0.0, ""
+    for name, p in ref.named_parameters():
+        if name == "dummy_tensor" or float(p.grad.norm()) < 1e-6:
+            continue
+        g = params[name].grad
+        assert g is not None and tuple(g.shape) == tuple(p.shape), name
+        e = float((g.float().cpu() - p.grad).norm() / p.grad.norm())
+        if e > worst:
+            worst, worst_name = e, name
+    print(f"GRN {norm_type} {dim}: worst parameter-gradient rel-L2 {worst:.3e} ({worst_name})")
+    assert worst < 1e-1, (worst, worst_name)
+    with torch.no_grad():
+        again = net.eval()(x.to(DEV))
+    assert float((again.float() - got.float()).abs().max()) <= 1e-2 * float(got.float().abs().max())
