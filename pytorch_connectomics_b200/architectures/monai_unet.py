@@ -9,7 +9,8 @@ parameter/buffer containers; the arithmetic runs in ``csrc/dense_conv.cu`` (impl
 BatchNorm+PReLU, their backward) and ``csrc/mednext_bwd.cu`` (split-K weight-gradient GEMM) on channels-last
 bf16 activations whose channel counts are zero-padded to multiples of 16.  Not yet on hand-written kernels
 (plain tensor plumbing for now): the residual ``+`` and the skip ``cat``.
-Supported: 3-D, ``norm="batch"`` / ``"group"`` / ``"instance"``, ``dropout`` (identity at inference; training with p > 0 raises),
+Supported: 3-D, ``norm="batch"`` / ``"group"`` / ``"instance"``, ``dropout`` (identity at inference; in training the mask is
+applied behind the fused norm+PReLU kernel, which equals MONAI's norm -> dropout -> PReLU for the same mask),
 ``upsample_mode="deconv"`` — anything else raises.
 """
 
@@ -323,14 +324,14 @@ class GroupNormActFn(torch.autograd.Function):
 # ----------------------------------------------------------------------------- MONAI-named module tree
 def _unsupported(what):
     raise NotImplementedError(f"pcb200 monai_unet: {what} is not implemented in the B200 engine yet "
-                              "(3-D, norm='batch' | 'group' | 'instance', dropout at inference, upsample_mode='deconv' only).")
+                              "(3-D, norm='batch' | 'group' | 'instance', upsample_mode='deconv' only).")
 
 
 class ADN(nn.Sequential):
     """MONAI ``ADN`` with ordering "NDA" (children ``N``, ``D``, ``A``).  ``norm``: ``"batch"``, ``"group"`` (``GroupNormActFn``) or ``"instance"`` —
     ``InstanceNorm3d`` (no affine, no running statistics, as MONAI builds it) is BatchNorm over a batch of ONE, so each
     sample goes through the same statistics / normalise+PReLU kernels with its own statistics.  ``dropout`` > 0 is the
-    identity at inference; training with it is refused (a random mask would have to reproduce torch's generator)."""
+    identity at inference and a mask behind the fused kernel in training (see ``forward``)."""
 
     def __init__(self, channels: int, dropout, norm: str = "batch", num_groups: int = 8):
         super().__init__()
@@ -349,9 +350,17 @@ class ADN(nn.Sequential):
             self.register_buffer("_rv", torch.ones(channels), persistent=False)
 
     def forward(self, x):
+        y = self._norm_act(x)
         drop = getattr(self, "D", None)
         if drop is not None and drop.p > 0 and self.training:
-            _unsupported("training with dropout > 0")
+            # "NDA" puts the dropout between norm and PReLU; PReLU is positively homogeneous (PReLU(c z) = c PReLU(z) for
+            # c >= 0) and the mask only scales by 0 or 1/(1-p), so PReLU(dropout(z)) == dropout(PReLU(z)) for the same mask:
+            # the mask is applied behind the fused norm+PReLU kernel.  Padded channels are zero and stay zero.  The mask comes
+            # from torch's generator on the channels-LAST tensor: same distribution as the reference's, not the same bits.
+            y = torch.nn.functional.dropout(y, float(drop.p), True)
+        return y
+
+    def _norm_act(self, x):
         bn = self.N
         if self.norm_kind == "group":
             return GroupNormActFn.apply(x, bn.weight, bn.bias, self.A.weight, int(bn.num_groups), float(bn.eps), int(bn.num_channels))

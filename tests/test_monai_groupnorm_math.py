@@ -87,3 +87,37 @@ def test_group_norm_prelu_composition_matches_torch(doubles, c, groups, zero_gam
     assert float(xc.grad[..., c:].abs().max() if cp > c else 0.0) == 0.0
     assert rel(adn.N.weight.grad, ref_n.weight.grad) < 1e-2 and rel(adn.N.bias.grad, ref_n.bias.grad) < 1e-2
     assert rel(adn.A.weight.grad, ref_a.weight.grad) < 1e-2
+
+
+def test_training_dropout_sits_behind_the_fused_norm_prelu(doubles):
+    """MONAI's ADN "NDA" is norm -> dropout -> PReLU; the engine applies the mask BEHIND its fused norm+PReLU kernel.  Equal
+    for the same mask because PReLU is positively homogeneous and a dropout mask only multiplies by 0 or 1/(1-p): checked
+    with torch's generator re-seeded so both orders draw the same mask (values and input gradient), padded channels stay
+    zero, eval is the identity."""
+    c, cp, p = 12, 16, 0.4
+    adn = PM.ADN(c, p, "group", 3)
+    with torch.no_grad():
+        adn.N.weight.normal_(1.0, 0.3)
+        adn.N.bias.normal_(0.0, 0.3)
+        adn.A.weight.fill_(0.2)
+    x = torch.zeros(2, 4, 5, 6, cp, dtype=BF)
+    x[..., :c] = torch.randn(2, 4, 5, 6, c).to(BF)
+    xa = x.clone().requires_grad_(True)
+    adn.train()
+    torch.manual_seed(7)
+    got = adn(xa)
+    got.float().square().sum().backward()
+    assert float(got[..., c:].abs().max()) == 0.0
+    frac = float((got[..., :c] == 0).float().mean())
+    assert abs(frac - p) < 0.05, frac
+    # the reference order on the same normalised tensor with the same mask
+    xb = x.clone().requires_grad_(True)
+    z = torch.nn.functional.group_norm(xb[..., :c].float().permute(0, 4, 1, 2, 3), 3, adn.N.weight, adn.N.bias, 1e-5)
+    z = torch.nn.functional.pad(z.permute(0, 2, 3, 4, 1), (0, cp - c)).to(BF)       # channels-last, padded like the engine's
+    torch.manual_seed(7)
+    want = torch.nn.functional.prelu(torch.nn.functional.dropout(z, p, True).float(), adn.A.weight.detach())
+    assert float((got.float() - want).abs().max()) <= 2e-2 * float(want.abs().max())
+    adn.eval()
+    with torch.no_grad():
+        a, b = adn(x), adn(x)
+    assert torch.equal(a, b)
