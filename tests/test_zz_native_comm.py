@@ -39,6 +39,7 @@ def test_nccl_is_bound_at_run_time_and_no_device_is_loud():
 @pytest.mark.gpu
 @first_run
 @pytest.mark.timeout(300)
+@pytest.mark.isolated(stall=240)
 def test_world1_communicator_scales_in_place():
     dev = torch.device("cuda:0")
     torch.cuda.set_device(dev)
@@ -102,6 +103,7 @@ def _two_gpu_worker(rank, uid, q):
 @pytest.mark.gpu
 @first_run
 @pytest.mark.timeout(600)
+@pytest.mark.isolated(stall=240)
 def test_two_ranks_allreduce_and_overlap_exchange():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
