@@ -18,7 +18,8 @@ OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 
 
 
 def make_cfg(window, *, out_channels=1, transpose=None, image_resize=None, dt_resize=None, patch=None, overlap=0.5, blending="bump", snap=False, sw_batch=2, output_dtype=None, target_context=(), border_mask=None,
-         pad_size=None, pad_mode="reflect", acts=None, select=None, tta=None, padding_mode="constant", cval=0.0):
+         pad_size=None, pad_mode="reflect", acts=None, select=None, tta=None, padding_mode="constant", cval=0.0,
+         normalize=None, clip=None):
     sw = NS(window_size=list(window), overlap=overlap, blending=blending, sw_batch_size=sw_batch, padding_mode=padding_mode, cval=cval,
             snap_to_edge=snap, target_context=list(target_context), border_mask=border_mask, distributed_sharding=False)
     dt = NS() if pad_size is None else NS(pad_size=list(pad_size), pad_mode=pad_mode)
@@ -26,9 +27,14 @@ def make_cfg(window, *, out_channels=1, transpose=None, image_resize=None, dt_re
         dt.val_transpose = list(transpose)
     if dt_resize is not None:
         dt.resize = list(dt_resize)
+    it = NS() if image_resize is None else NS(resize=list(image_resize))
+    if normalize is not None:            # data.image_transform.normalize: smart_normalize of every patch the accessor reads
+        it.normalize = normalize
+    if clip is not None:
+        it.clip_percentile_low, it.clip_percentile_high = clip
     return NS(model=NS(output_size=list(window), arch=NS(type="mednext"), primary_head=None, heads=None, out_channels=out_channels),
               data=NS(dataloader=NS(batch_size=1, patch_size=list(patch or window), use_lazy_h5=True), data_transform=dt,
-                      image_transform=NS() if image_resize is None else NS(resize=list(image_resize))),
+                      image_transform=it),
               system=NS(num_workers=1),
               inference=NS(sliding_window=sw, test_time_augmentation=tta if tta is not None else NS(enabled=False),
                            model=NS(output_dtype=output_dtype, channel_activations=acts, select_channel=select, head=None)))
@@ -70,6 +76,10 @@ CASES = {
     "resize_image": dict(shape=(8, 9, 10), cfg=dict(window=(4, 4, 4), blending="constant", image_resize=(1.5, 1.0, 0.75)), fwd=_patch_mean),
     "resize_to_size_mask_pad": dict(shape=(8, 8, 8), cfg=dict(window=(4, 4, 4), blending="bump", dt_resize=(6, 4, 5), patch=(4, 4, 4),
                                                              pad_size=(1, 0, 2)), fwd=_identity, mask=True),
+    "normalize_zscore_clip": dict(shape=(9, 10, 11), cfg=dict(window=(4, 4, 4), blending="constant", normalize="normal", clip=(0.05, 0.9)), fwd=_identity),
+    "normalize_minmax_pad": dict(shape=(8, 9, 10), cfg=dict(window=(4, 4, 4), blending="bump", normalize="0-1", pad_size=(1, 2, 1), snap=True,
+                                                          overlap=0.25, out_channels=3), fwd=_three),
+    "normalize_divide": dict(shape=(6, 6, 7), cfg=dict(window=(4, 4, 4), blending="constant", normalize="divide-4", clip=(0.0, 0.75)), fwd=_patch_mean),
     "context_pad": dict(shape=(8, 9, 10), cfg=dict(window=(4, 4, 4), blending="constant", pad_size=(2, 1, 3), pad_mode="reflect"), fwd=_patch_mean),
 }
 

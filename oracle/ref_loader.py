@@ -259,7 +259,8 @@ def ref_lazy():
     ``lazy_predict_region / volume``, ``LazyVolumeAccessor``, ``_build_accessor``) with the real ``tta.py``,
     ``lazy_distributed.py``, ``window.py`` and ``data/processing/misc.py``.  What is stood in: ``h5py`` (a ``.npy``-backed
     file object, visible only inside ``with fake_h5py():``), ``data/io/io.py`` (format detection by extension; its tiff helpers are never reached) and
-    ``smart_normalize`` (raises: the tests use ``normalize: none``)."""
+    the ``augment_ops`` MODULE (it imports cv2) — but its ``smart_normalize`` is the REAL function, compiled alone from
+    the reference file (``ref_smart_normalize``)."""
     ref_tta()
 
     def _no(name):
@@ -268,13 +269,28 @@ def ref_lazy():
         return fn
 
     _stub("connectomics.data.augmentation")
-    _stub("connectomics.data.augmentation.augment_ops", smart_normalize=_no("smart_normalize"))
+    _stub("connectomics.data.augmentation.augment_ops", smart_normalize=ref_smart_normalize())
     _stub("connectomics.data.io")
     _stub("connectomics.data.io.io", _detect_format=lambda p: "h5" if str(p).endswith((".h5", ".hdf5")) else "unknown",
           _get_tiff_volume_shape=_no("_get_tiff_volume_shape"), _tiff_series_are_stackable=_no("_tiff_series_are_stackable"))
     _load("connectomics.data.processing.misc", "connectomics/data/processing/misc.py")
     _load("connectomics.inference.lazy_distributed", "connectomics/inference/lazy_distributed.py")
     return _load("connectomics.inference.lazy", "connectomics/inference/lazy.py")
+
+
+def ref_smart_normalize():
+    """The REAL ``smart_normalize`` (``connectomics/data/augmentation/augment_ops.py:552-610``): the module imports cv2, which
+    this image does not have, so the one function (numpy only) is cut out of the reference file's syntax tree and compiled in
+    place — nothing is copied into the repository."""
+    import ast
+    import typing
+    import numpy
+    path = os.path.join(REF_ROOT, "connectomics", "data", "augmentation", "augment_ops.py")
+    tree = ast.parse(open(path).read(), filename=path)
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "smart_normalize")
+    ns = {"np": numpy, "Optional": typing.Optional, "List": typing.List, "Tuple": typing.Tuple}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
+    return ns["smart_normalize"]
 
 
 def ref_chunked():

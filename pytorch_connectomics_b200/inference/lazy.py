@@ -60,7 +60,11 @@ class ArrayVolumeAccessor:
     def __init__(self, data, *, kind: str = "image", binarize: bool = False, threshold: float = 0.0,
                  context_pad: Sequence[Sequence[int]] = ((0, 0), (0, 0), (0, 0)), context_pad_mode: str = "constant",
                  transpose_axes: Sequence[int] = (), scale_factors: Optional[Sequence[float]] = None,
-                 layout: str = "channel_first"):
+                 layout: str = "channel_first", normalize_mode: str = "none", clip_percentile_low: float = 0.0,
+                 clip_percentile_high: float = 1.0):
+        # data.image_transform.normalize (lazy.py:895-902): intensity normalisation of every PATCH an image accessor hands out
+        self.normalize_mode = str(normalize_mode or "none")
+        self.clip_percentile_low, self.clip_percentile_high = float(clip_percentile_low), float(clip_percentile_high)
         if isinstance(data, torch.Tensor):
             if data.dim() == 5:
                 if data.shape[0] != 1:
@@ -129,7 +133,7 @@ class ArrayVolumeAccessor:
     def as_tensor(self) -> Optional[torch.Tensor]:
         """``[1, C, D, H, W]`` view when the whole volume is a tensor (device-resident fast path), else ``None``."""
         plain = not self.binarize and not self.transpose_axes and not any(b or a for b, a in self.context_pad) \
-            and self.scale_factors is None
+            and self.scale_factors is None and not (self.kind == "image" and self.normalize_mode != "none")
         if self._tensor is not None and plain:
             return self._tensor.unsqueeze(0)
         return None
@@ -226,12 +230,47 @@ class ArrayVolumeAccessor:
         patch = _pad_channel_first(inner, pads, mode=outer_pad_mode, constant_value=outer_pad_value)
         if self.binarize:
             patch = (patch > self.threshold).astype(np.float32, copy=False)
+        if self.kind == "image" and self.normalize_mode != "none":
+            patch = normalize_patch(patch, self.normalize_mode, self.clip_percentile_low, self.clip_percentile_high)
         return patch.astype(np.float32, copy=False)
 
     def load_full(self) -> np.ndarray:
         """``lazy.py:906-918``: the transformed volume WITHOUT the context border"""
         full = self._crop((0, 0, 0), self.transformed_spatial_shape)
         return (full > self.threshold).astype(np.float32) if self.binarize else full
+
+
+def normalize_patch(patch: np.ndarray, mode: str, clip_low: float = 0.0, clip_high: float = 1.0) -> np.ndarray:
+    """``smart_normalize`` (``data/augmentation/augment_ops.py:552-610``) as the lazy accessor applies it (``lazy.py:895-902``):
+    statistics of THIS patch (outer padding included), never of the volume.  Percentile clip first (fractions in [0, 1]), then
+    ``"normal"`` (z-score unless std <= 1e-8), ``"0-1"`` (min-max unless flat) or ``"divide-K"``.  numpy's own reductions in
+    the reference's order, so the float results are the reference's bit for bit."""
+    divisor = None
+    if mode.startswith("divide-"):
+        try:
+            divisor = float(mode.split("-", 1)[1])
+        except ValueError as exc:
+            raise ValueError(f"Invalid divide mode '{mode}'. Format should be 'divide-K' where K is a number "
+                             "(e.g., 'divide-255').") from exc
+        mode = "divide"
+    out = np.array(patch, copy=True)
+    if clip_low > 0.0 or clip_high < 1.0:
+        bounds = (np.percentile(out, clip_low * 100), np.percentile(out, clip_high * 100))
+        out = np.clip(out, *bounds)
+    if mode == "normal":
+        mu, sigma = out.mean(), out.std()
+        return (out - mu) / sigma if sigma > 1e-8 else out
+    if mode == "0-1":
+        lo, hi = out.min(), out.max()
+        return (out - lo) / (hi - lo) if hi > lo else out
+    if mode == "divide":
+        if divisor is None or divisor == 0.0:       # the accessor never passes a divide_value: plain "divide" is an error there too
+            raise ValueError("smart_normalize mode='divide' requires a non-zero divide_value (or use 'divide-K' form to "
+                             "embed the divisor in the mode string).")
+        return out / divisor
+    if mode == "none":
+        return out
+    raise ValueError(f"Unknown smart_normalize mode '{mode}'. Expected 'none', 'normal', '0-1', 'divide', or 'divide-K'.")
 
 
 def _get_padsize(pad_size, ndim: int = 3):
@@ -291,11 +330,11 @@ def build_accessor(cfg, source, *, kind: str = "image", mode: str = "test"):
     elif kind == "mask":
         factors = getattr(getattr(data_cfg, "mask_transform", None) or dt, "resize", None)
     kw["scale_factors"] = tuple(float(v) for v in factors) if factors else None
-    for key, what in (("image_transform", "normalize"),):
-        mode_ = getattr(getattr(data_cfg, key, None), what, "none") if kind == "image" else "none"
-        if str(mode_ or "none").lower() != "none":
-            raise NotImplementedError(f"pcb200 lazy inference: data.image_transform.normalize={mode_!r} (smart_normalize) is a "
-                                      "data-pipeline transform outside this path; normalise the volume beforehand")
+    if kind == "image":                          # lazy.py:931-937
+        it = getattr(data_cfg, "image_transform", None)
+        kw["normalize_mode"] = getattr(it, "normalize", "none") or "none"
+        kw["clip_percentile_low"] = float(getattr(it, "clip_percentile_low", 0.0))
+        kw["clip_percentile_high"] = float(getattr(it, "clip_percentile_high", 1.0))
     if isinstance(source, (torch.Tensor, np.ndarray)):
         return ArrayVolumeAccessor(source, **kw)
     path = os.fspath(source)

@@ -146,3 +146,46 @@ def test_window_sharding_over_two_ranks_equals_the_real_engine_and_the_goldens(t
         if f"ref_{name}" in got[0]:
             assert got[1][f"ref_{name}"].size == 0
             assert np.allclose(got[0][f"ours_{name}"], got[0][f"ref_{name}"], rtol=1e-5, atol=1e-5), name
+
+
+def test_normalize_patch_equals_the_real_smart_normalize():
+    """`normalize_patch` (the accessor's per-patch `data.image_transform.normalize`) against the REAL `smart_normalize`
+    (`augment_ops.py:552-610`, compiled alone from the reference file): every mode x percentile clip on random, flat and
+    outlier patches — same dtype, same bits — and the same refusals."""
+    if not ref_loader.available():
+        pytest.skip("/root/reference is only present in the build container")
+    from pytorch_connectomics_b200.inference.lazy import normalize_patch
+    real = ref_loader.ref_smart_normalize()
+    rs = np.random.RandomState(3)
+    patches = [rs.rand(1, 4, 5, 6).astype(np.float32), (rs.randn(2, 3, 3, 3) * 40 + 100).astype(np.float32),
+               np.full((1, 2, 2, 2), 7.0, np.float32), np.zeros((1, 3, 3, 3), np.float32)]
+    patches[1][0, 0, 0, 0] = 1e4
+    for patch in patches:
+        for mode in ("normal", "0-1", "divide-255", "divide-0.5", "none"):
+            for lo, hi in ((0.0, 1.0), (0.02, 0.98), (0.0, 0.9), (0.25, 1.0)):
+                want = real(patch, mode, divide_value=None, clip_percentile_low=lo, clip_percentile_high=hi)
+                got = normalize_patch(patch, mode, lo, hi)
+                assert got.dtype == want.dtype and np.array_equal(got, want), (mode, lo, hi)
+                assert got is not patch
+    for bad in ("divide", "divide-x", "divide-0", "zscore"):
+        with pytest.raises(ValueError) as ours:
+            normalize_patch(patches[0], bad)
+        with pytest.raises(ValueError) as theirs:
+            real(patches[0], bad)
+        assert str(ours.value) == str(theirs.value), bad
+
+
+def test_normalizing_accessor_never_hands_out_the_resident_tensor():
+    """a normalised image is a function of each PATCH: the device-resident whole-volume fast path must be off"""
+    from types import SimpleNamespace as NS
+    from pytorch_connectomics_b200.inference import lazy as Z
+    cfg = G.make_cfg(window=(4, 4, 4), normalize="normal")
+    vol = torch.rand(8, 8, 8)
+    acc = Z.build_accessor(cfg, vol, kind="image", mode="test")
+    assert acc.normalize_mode == "normal" and acc.as_tensor() is None
+    plain = Z.build_accessor(G.make_cfg(window=(4, 4, 4)), vol, kind="image", mode="test")
+    assert plain.as_tensor() is not None
+    p = acc.read_patch((2, 2, 2), (4, 4, 4), outer_pad_mode="constant", outer_pad_value=0.0)
+    assert abs(float(p.mean())) < 1e-5 and abs(float(p.std()) - 1.0) < 1e-4
+    mask = Z.build_accessor(cfg, vol, kind="mask", mode="test")           # masks are never normalised
+    assert np.array_equal(mask.read_patch((0, 0, 0), (4, 4, 4), outer_pad_mode="constant", outer_pad_value=0.0)[0], vol[:4, :4, :4].numpy())
