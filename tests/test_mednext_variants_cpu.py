@@ -140,3 +140,45 @@ def test_grn_trunk_is_not_native_eligible(monkeypatch):
     assert native_eligible(net) is not None
     _, net2 = _pair(monkeypatch, dim="2d")
     assert native_eligible(net2) is not None
+
+
+# ----------------------------------------------------------------------------- what bf16 STORAGE costs the composed paths
+@pytest.mark.parametrize("norm_type,dim,grn", [("group", "3d", True), ("layer", "3d", True), ("group", "2d", True), ("group", "2d", False)])
+def test_bf16_storage_keeps_the_variants_inside_the_gpu_bounds(monkeypatch, norm_type, dim, grn):
+    """The first-run GPU tests bound the variants at 3e-2 (output) and 1e-1 (worst parameter gradient) against the fp32
+    oracle.  Here the stand-ins round every activation they hand back to bf16 — the storage format between kernels, which the
+    composed GRN path crosses more often than the fused block does — and the same comparison has to hold with a 2x margin,
+    so a GPU failure of those bounds would point at a kernel, not at the bound."""
+    from pytorch_connectomics_b200.architectures import _mednext_ops as ops
+    doubles.install(monkeypatch)
+    bf = torch.bfloat16
+
+    def rounding(fn):
+        def call(*a, **k):
+            out = fn(*[t.float() if torch.is_tensor(t) and t.dtype == bf else t for t in a], **k)
+            return ops._mark(out.to(bf)) if fn.__name__ != "head_apply" else out
+        return call
+
+    for name in ("block_apply", "stem_apply", "head_apply", "pointwise_apply", "dwconv_apply", "norm_apply"):
+        monkeypatch.setattr(ops, name, rounding(getattr(doubles, name)))
+    monkeypatch.setattr(ops, "_BF16", bf)
+    torch.manual_seed(9)
+    kw = dict(in_channels=1, n_channels=16, n_classes=2, exp_r=2, kernel_size=3, do_res=True, do_res_up_down=True,
+              block_counts=[1] * 9, norm_type=norm_type, dim=dim, grn=grn)
+    ref = O.MedNeXt(**kw).train()
+    with torch.no_grad():
+        for name, p in ref.named_parameters():
+            if "grn" in name:
+                p.normal_(0.0, 0.5)
+    net = M.MedNeXt(**kw).train()
+    net.load_state_dict(ref.state_dict(), strict=True)
+    x = torch.rand(2, 1, 32, 32, 32) if dim == "3d" else torch.rand(2, 1, 64, 64)
+    want, got = ref(x), net(x)
+    assert float((got.float() - want).norm() / want.norm()) < 1.5e-2
+    want.square().mean().backward()
+    got.float().square().mean().backward()
+    params = dict(net.named_parameters())
+    for name, p in ref.named_parameters():
+        if name == "dummy_tensor" or float(p.grad.norm()) < 1e-6 or (norm_type == "group" and name.endswith("conv1.bias")):
+            continue
+        assert float((params[name].grad.float() - p.grad).norm() / p.grad.norm()) < 5e-2, name

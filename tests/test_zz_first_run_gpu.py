@@ -472,10 +472,12 @@ def test_mednext_2d_matches_oracle(norm_type):
     params = dict(net.named_parameters())
     worst = 0.0
     for name, p in ref.named_parameters():
-        if name == "dummy_tensor" or float(p.grad.norm()) < 1e-6:
+        g = params.get(name, p).grad
+        if name != "dummy_tensor":
+            assert g is not None and tuple(g.shape) == tuple(p.shape), name
+        # a per-channel constant in front of GroupNorm(C groups) has an analytically ZERO gradient: the oracle holds fp32 noise there
+        if name == "dummy_tensor" or float(p.grad.norm()) < 1e-6 or (norm_type == "group" and name.endswith("conv1.bias")):
             continue
-        g = params[name].grad
-        assert g is not None and tuple(g.shape) == tuple(p.shape), name
         worst = max(worst, float((g.float().cpu() - p.grad).norm() / p.grad.norm()))
     print(f"2-D {norm_type}: worst parameter-gradient rel-L2 {worst:.3e}")
     assert worst < 1e-1, worst
@@ -516,10 +518,12 @@ def test_mednext_grn_matches_oracle(norm_type, dim):
     params = dict(net.named_parameters())
     worst, worst_name = 0.0, ""
     for name, p in ref.named_parameters():
-        if name == "dummy_tensor" or float(p.grad.norm()) < 1e-6:
+        g = params.get(name, p).grad
+        if name != "dummy_tensor":
+            assert g is not None and tuple(g.shape) == tuple(p.shape), name
+        # a per-channel constant in front of GroupNorm(C groups) has an analytically ZERO gradient: the oracle holds fp32 noise there
+        if name == "dummy_tensor" or float(p.grad.norm()) < 1e-6 or (norm_type == "group" and name.endswith("conv1.bias")):
             continue
-        g = params[name].grad
-        assert g is not None and tuple(g.shape) == tuple(p.shape), name
         e = float((g.float().cpu() - p.grad).norm() / p.grad.norm())
         if e > worst:
             worst, worst_name = e, name
