@@ -76,8 +76,10 @@ class ResidualUnit(nn.Module):
     """monai.networks.blocks.ResidualUnit: conv = unit0..unit{n-1}; residual = strided k-conv | 1x1 conv | identity."""
 
     def __init__(self, dims, in_channels, out_channels, strides=1, kernel_size=3, subunits=2, norm="batch", dropout=0.0,
-                 bias=True, last_conv_only=False):
+                 bias=True, last_conv_only=False, act="PRELU", adn_ordering="NDA"):
         super().__init__()
+        if str(act).upper() != "PRELU" or adn_ordering != "NDA":
+            raise ValueError("oracle restates MONAI's defaults only: act='PRELU', adn_ordering='NDA'")
         self.conv = nn.Sequential()
         self.residual: nn.Module = nn.Identity()
         subunits = max(1, subunits)
@@ -92,6 +94,31 @@ class ResidualUnit(nn.Module):
 
     def forward(self, x):
         return self.conv(x) + self.residual(x)
+
+
+class UpSample(nn.Sequential):
+    """monai.networks.blocks.UpSample in its ``mode="nontrainable"`` form (the one ``UpsampleModeUNet`` is for,
+    ``monai_models.py:84-139``): ``preconv`` = Conv(in, out, kernel 1) when the channel counts differ, then
+    ``upsample_non_trainable`` = ``nn.Upsample(scale_factor, interp mode, align_corners)``; the linear family resolves to the
+    mode of the dimensionality (3-D: trilinear).  No norm / activation.  Restated from MONAI's published block — like the rest
+    of this file, un-pinned against the wheel."""
+
+    def __init__(self, spatial_dims, in_channels=None, out_channels=None, scale_factor=2, mode="deconv", interp_mode="linear",
+                 align_corners=True, bias=True, **_unused):
+        super().__init__()
+        if spatial_dims != 3:
+            raise ValueError("oracle restates the 3-D variant only")
+        if str(mode).lower() != "nontrainable":
+            raise NotImplementedError(f"oracle UpSample restates mode='nontrainable' only, got {mode!r}")
+        out_channels = in_channels if out_channels is None else out_channels
+        if out_channels != in_channels:
+            self.add_module("preconv", nn.Conv3d(in_channels, out_channels, kernel_size=1, bias=bias))
+        interp = str(getattr(interp_mode, "value", interp_mode)).lower()
+        if interp in ("linear", "bilinear", "trilinear"):
+            interp = "trilinear"
+        sf = tuple(scale_factor) if isinstance(scale_factor, (tuple, list)) else (scale_factor,) * 3
+        self.add_module("upsample_non_trainable", nn.Upsample(scale_factor=tuple(float(v) for v in sf), mode=interp,
+                                                              align_corners=align_corners))
 
 
 class SkipConnection(nn.Module):
@@ -116,16 +143,27 @@ class UNet(nn.Module):
             raise ValueError("the length of `strides` should equal to `len(channels) - 1`.")
         self.dimensions, self.kernel_size, self.up_kernel_size = spatial_dims, kernel_size, up_kernel_size
         self.num_res_units, self.norm, self.dropout, self.bias = num_res_units, norm, dropout, bias
+        self.act, self.adn_ordering = "PRELU", "NDA"            # MONAI's defaults, read by subclasses that build their own layers
 
         def block(inc, outc, ch, st, is_top):
             c, s = ch[0], st[0]
             if len(ch) > 2:
                 sub, upc = block(c, c, ch[1:], st[1:], False), c * 2
             else:
-                sub, upc = self._down(c, ch[1], 1), c + ch[1]
-            return nn.Sequential(self._down(inc, c, s), SkipConnection(sub), self._up(upc, outc, s, is_top))
+                sub, upc = self._get_bottom_layer(c, ch[1]), c + ch[1]
+            return nn.Sequential(self._get_down_layer(inc, c, s, is_top), SkipConnection(sub), self._get_up_layer(upc, outc, s, is_top))
 
         self.model = block(in_channels, out_channels, list(channels), list(strides), True)
+
+    # MONAI's method names: a subclass (the reference's UpsampleModeUNet) overrides _get_up_layer
+    def _get_down_layer(self, in_channels, out_channels, strides, is_top):
+        return self._down(in_channels, out_channels, strides)
+
+    def _get_bottom_layer(self, in_channels, out_channels):
+        return self._down(in_channels, out_channels, 1)
+
+    def _get_up_layer(self, in_channels, out_channels, strides, is_top):
+        return self._up(in_channels, out_channels, strides, is_top)
 
     def _down(self, i, o, s):
         if self.num_res_units > 0:
@@ -143,3 +181,26 @@ class UNet(nn.Module):
 
     def forward(self, x):
         return self.model(x)
+
+
+class UpsampleModeUNet(UNet):
+    """``connectomics/models/architectures/monai_models.py:84-139`` restated: MONAI's UNet whose up layers are
+    ``UpSample(mode=upsample_mode)`` [+ a one-subunit ResidualUnit when ``num_res_units > 0``] unless the mode is "deconv".
+    (Travels to the GPU box, where the reference itself is absent; ``tests/test_builders_vs_reference.py`` holds it against the
+    REAL class executed in place.)"""
+
+    def __init__(self, upsample_mode: str = "deconv", upsample_interp_mode: str = "linear", upsample_align_corners: bool = True,
+                 **kwargs):
+        self.upsample_mode, self.upsample_interp_mode = upsample_mode, upsample_interp_mode
+        self.upsample_align_corners = upsample_align_corners
+        super().__init__(**kwargs)
+
+    def _get_up_layer(self, in_channels, out_channels, strides, is_top):
+        if not self.upsample_mode or self.upsample_mode == "deconv":
+            return super()._get_up_layer(in_channels, out_channels, strides, is_top)
+        up = UpSample(self.dimensions, in_channels, out_channels, strides, mode=self.upsample_mode,
+                      interp_mode=self.upsample_interp_mode, align_corners=self.upsample_align_corners, bias=self.bias)
+        if self.num_res_units == 0:
+            return up
+        return nn.Sequential(up, ResidualUnit(self.dimensions, out_channels, out_channels, 1, self.kernel_size, 1, self.norm,
+                                              self.dropout, self.bias, last_conv_only=is_top))

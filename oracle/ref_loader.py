@@ -134,7 +134,7 @@ def ref_monai_models():
     if "monai" not in sys.modules:
         _stub("monai")
         _stub("monai.networks")
-        _stub("monai.networks.blocks", ResidualUnit=UO.ResidualUnit, UpSample=_absent("UpSample"))
+        _stub("monai.networks.blocks", ResidualUnit=UO.ResidualUnit, UpSample=UO.UpSample)
         _stub("monai.networks.nets", UNet=UO.UNet, BasicUNet=_absent("BasicUNet"), UNETR=_absent("UNETR"), SwinUNETR=_absent("SwinUNETR"))
     ref_registry()
     ref_base()

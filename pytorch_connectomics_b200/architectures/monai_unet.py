@@ -11,7 +11,7 @@ bf16 activations whose channel counts are zero-padded to multiples of 16.  Not y
 (plain tensor plumbing for now): the residual ``+`` and the skip ``cat``.
 Supported: 3-D, ``norm="batch"`` / ``"group"`` / ``"instance"``, ``dropout`` (identity at inference; in training the mask is
 applied behind the fused norm+PReLU kernel, which equals MONAI's norm -> dropout -> PReLU for the same mask),
-``upsample_mode="deconv"`` — anything else raises.
+``upsample_mode="deconv"`` / ``"nontrainable"`` — anything else raises.
 """
 
 from __future__ import annotations
@@ -324,7 +324,7 @@ class GroupNormActFn(torch.autograd.Function):
 # ----------------------------------------------------------------------------- MONAI-named module tree
 def _unsupported(what):
     raise NotImplementedError(f"pcb200 monai_unet: {what} is not implemented in the B200 engine yet "
-                              "(3-D, norm='batch' | 'group' | 'instance', upsample_mode='deconv' only).")
+                              "(3-D, norm='batch' | 'group' | 'instance', upsample_mode='deconv' | 'nontrainable').")
 
 
 class ADN(nn.Sequential):
@@ -444,13 +444,49 @@ class SkipConnection(nn.Module):
         return cat.contiguous()
 
 
+class UpSample(nn.Sequential):
+    """monai.networks.blocks.UpSample, ``mode="nontrainable"`` (what the reference's ``UpsampleModeUNet`` swaps in for the
+    transposed conv, ``monai_models.py:104-139``): children ``preconv`` (Conv3d kernel 1, only when the channel counts differ)
+    and ``upsample_non_trainable`` (``nn.Upsample``; the linear family means trilinear in 3-D).  The 1x1 conv runs on the
+    implicit-GEMM kernel; the interpolation itself is a device tensor op on the padded channels-last tensor (no hand-written
+    resampling kernel yet) — padded channels are zero and stay zero."""
+
+    def __init__(self, in_channels: int, out_channels: int, scale_factor: int, interp_mode: str = "linear",
+                 align_corners: bool = True, bias: bool = True):
+        super().__init__()
+        if out_channels != in_channels:
+            self.add_module("preconv", nn.Conv3d(in_channels, out_channels, kernel_size=1, bias=bias))
+        interp = str(interp_mode).lower()
+        if interp in ("linear", "bilinear", "trilinear"):
+            interp = "trilinear"
+        elif interp != "nearest":
+            _unsupported(f"upsample_interp_mode={interp_mode!r}")
+        self.add_module("upsample_non_trainable", nn.Upsample(scale_factor=(float(scale_factor),) * 3, mode=interp,
+                                                              align_corners=align_corners))
+
+    def forward(self, x):
+        if hasattr(self, "preconv"):
+            x = ConvFn.apply(x, self.preconv.weight, self.preconv.bias, 1, 1, 0, False)
+        up = self.upsample_non_trainable
+        y = torch.nn.functional.interpolate(x.permute(0, 4, 1, 2, 3), scale_factor=up.scale_factor, mode=up.mode,
+                                            align_corners=up.align_corners)
+        return y.permute(0, 2, 3, 4, 1).contiguous()
+
+
 class UNet(nn.Module):
-    """monai.networks.nets.UNet (3-D, batch norm, PReLU, deconv upsampling) on the B200 engine."""
+    """monai.networks.nets.UNet (3-D, PReLU; batch / instance / group norm) on the B200 engine, with the reference's
+    ``UpsampleModeUNet`` switch (``monai_models.py:84-139``): ``upsample_mode="deconv"`` (MONAI's transposed conv + ADN) or
+    ``"nontrainable"`` (``UpSample``: 1x1 conv + interpolation, no norm / activation)."""
 
     def __init__(self, spatial_dims: int, in_channels: int, out_channels: int, channels: Sequence[int], strides: Sequence[int],
                  kernel_size: int = 3, up_kernel_size: int = 3, num_res_units: int = 0, norm="batch", dropout: float = 0.0,
-                 bias: bool = True):
+                 bias: bool = True, upsample_mode: str = "deconv", upsample_interp_mode: str = "linear",
+                 upsample_align_corners: bool = True):
         super().__init__()
+        self.upsample_mode = str(upsample_mode or "deconv").lower()
+        if self.upsample_mode not in ("deconv", "nontrainable"):
+            _unsupported(f"upsample_mode={upsample_mode!r}")
+        self.upsample_interp_mode, self.upsample_align_corners = upsample_interp_mode, upsample_align_corners
         if spatial_dims != 3:
             _unsupported("spatial_dims != 3")
         norm_kw = dict(norm[1]) if isinstance(norm, (tuple, list)) and len(norm) > 1 else {}
@@ -491,8 +527,11 @@ class UNet(nn.Module):
         return Convolution(i, o, s, self.kernel_size, self.dropout, self.bias, norm=self.norm, num_groups=self.num_groups)
 
     def _up(self, i, o, s, is_top):
-        conv = Convolution(i, o, s, 3, self.dropout, self.bias, conv_only=is_top and self.num_res_units == 0,
-                           is_transposed=True, norm=self.norm, num_groups=self.num_groups)
+        if self.upsample_mode == "nontrainable":
+            conv = UpSample(i, o, s, self.upsample_interp_mode, self.upsample_align_corners, self.bias)
+        else:
+            conv = Convolution(i, o, s, 3, self.dropout, self.bias, conv_only=is_top and self.num_res_units == 0,
+                               is_transposed=True, norm=self.norm, num_groups=self.num_groups)
         if self.num_res_units > 0:
             return nn.Sequential(conv, ResidualUnit(o, o, 1, self.kernel_size, 1, self.dropout, self.bias, last_conv_only=is_top,
                                                     norm=self.norm, num_groups=self.num_groups))
@@ -535,15 +574,15 @@ def build_monai_unet(cfg) -> ConnectomicsModel:
     size = getattr(cfg.model, "input_size", None)
     dims = len(size) if size else getattr(m, "spatial_dims", 3)
     channels = list(getattr(m, "filters", [32, 64, 128, 256, 512]))
-    mode = getattr(m, "upsample_mode", "deconv")
-    if mode and mode != "deconv":
-        _unsupported(f"upsample_mode={mode!r}")
     norm = getattr(m, "norm", "batch")
     if norm == "group":                                   # monai_models.py:74-81 _resolve_norm
         norm = ("group", {"num_groups": getattr(m, "num_groups", 8)})
     model = UNet(spatial_dims=dims, in_channels=cfg.model.in_channels, out_channels=cfg.model.out_channels,
                  channels=channels, strides=[2] * (len(channels) - 1), num_res_units=getattr(m, "num_res_units", 2),
-                 kernel_size=getattr(m, "kernel_size", 3), norm=norm, dropout=getattr(m, "dropout", 0.0))
+                 kernel_size=getattr(m, "kernel_size", 3), norm=norm, dropout=getattr(m, "dropout", 0.0),
+                 upsample_mode=getattr(m, "upsample_mode", "deconv"),
+                 upsample_interp_mode=getattr(m, "upsample_interp_mode", "linear"),
+                 upsample_align_corners=getattr(m, "upsample_align_corners", True))
     return MONAIModelWrapper(model)
 
 

@@ -73,12 +73,13 @@ def test_grn_network_passes_the_prototype_checks(monkeypatch, norm_type, dim):
         net.eval()(x)
 
 
-@pytest.mark.parametrize("norm,dropout", [("batch", 0.0), ("instance", 0.0), ("group", 0.0), ("batch", 0.2)])
-def test_monai_unet_passes_the_prototype_checks(monkeypatch, norm, dropout):
+@pytest.mark.parametrize("norm,dropout,up", [("batch", 0.0, "deconv"), ("instance", 0.0, "deconv"), ("group", 0.0, "deconv"),
+                                             ("batch", 0.2, "deconv"), ("batch", 0.0, "nontrainable")])
+def test_monai_unet_passes_the_prototype_checks(monkeypatch, norm, dropout, up):
     abi_dry_run.install(monkeypatch)
     from pytorch_connectomics_b200.architectures.monai_unet import build_monai_unet
     cfg = NS(model=NS(in_channels=1, out_channels=2, monai=NS(filters=[16, 32, 64], num_res_units=2, norm=norm, num_groups=2,
-                                                            dropout=dropout, spatial_dims=3, kernel_size=3)))
+                                                            dropout=dropout, spatial_dims=3, kernel_size=3, upsample_mode=up)))
     model = build_monai_unet(cfg).train()
     x = torch.rand(2, 1, 16, 16, 16)
     out = model(x)

@@ -105,7 +105,11 @@ UNET_GOOD = [_ucfg(num_res_units=1, kernel_size=3, norm="batch", dropout=0.0),  
              _ucfg(filters=(8, 16, 32, 64), in_channels=2, out_channels=3),              # defaults: 2 residual units
              _ucfg(filters=(16, 32), num_res_units=0), _ucfg(input_size=None, spatial_dims=3, num_res_units=1),
              _ucfg(num_res_units=1, norm="instance", dropout=0.1),                        # no norm parameters; dropout module kept
-             _ucfg(num_res_units=1, norm="group", num_groups=4, out_channels=4), _ucfg(num_res_units=2, norm="group", out_channels=8)]
+             _ucfg(num_res_units=1, norm="group", num_groups=4, out_channels=4), _ucfg(num_res_units=2, norm="group", out_channels=8),
+             # UpsampleModeUNet (monai_models.py:84-139): the REAL _get_up_layer override runs over the oracle's UpSample
+             _ucfg(num_res_units=1, upsample_mode="nontrainable"), _ucfg(filters=(8, 16, 32, 64), num_res_units=0, upsample_mode="nontrainable",
+                                                                         upsample_interp_mode="nearest", upsample_align_corners=None),
+             _ucfg(num_res_units=2, upsample_mode="nontrainable", upsample_interp_mode="trilinear", upsample_align_corners=False, out_channels=3)]
 
 
 @pytest.mark.parametrize("i", range(len(UNET_GOOD)))
@@ -120,6 +124,24 @@ def test_monai_unet_matches_the_real_builder(i):
     assert want == got, {k: (want[k], got[k]) for k in want if want[k] != got.get(k)}
     ours.load_state_dict(real.state_dict(), strict=True)
     real.load_state_dict(ours.state_dict(), strict=True)
+
+
+def test_oracle_upsample_mode_unet_equals_the_real_class():
+    """the oracle's restated `UpsampleModeUNet` (what the GPU tests compare with, where the reference is absent) against the
+    REAL class executed in place: same `state_dict`, same output for the same weights, in both modes"""
+    import torch
+    from oracle import monai_unet_oracle as UO
+    R = ref_loader.ref_monai_models()
+    for mode, interp, align in (("nontrainable", "linear", True), ("nontrainable", "nearest", None), ("deconv", "linear", True)):
+        kw = dict(spatial_dims=3, in_channels=1, out_channels=2, channels=[8, 16, 32], strides=[2, 2], num_res_units=1,
+                  kernel_size=3, norm="batch", dropout=0.0, upsample_mode=mode, upsample_interp_mode=interp,
+                  upsample_align_corners=align)
+        torch.manual_seed(0)
+        real, ours = R.UpsampleModeUNet(**kw).eval(), UO.UpsampleModeUNet(**kw).eval()
+        ours.load_state_dict(real.state_dict(), strict=True)
+        x = torch.rand(1, 1, 16, 16, 16)
+        with torch.no_grad():
+            assert torch.equal(real(x), ours(x)), mode
 
 
 def test_multihead_golden_is_reproducible_from_the_real_wrapper():

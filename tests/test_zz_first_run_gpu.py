@@ -441,6 +441,42 @@ def test_monai_unet_group_norm_matches_oracle():
     assert (num / den) ** 0.5 < 5e-2
 
 
+@pytest.mark.parametrize("res_units,interp,align", [(1, "linear", True), (0, "nearest", None), (2, "trilinear", False)])
+def test_monai_unet_nontrainable_upsampling_matches_oracle(res_units, interp, align):
+    """`model.monai.upsample_mode: nontrainable` (`UpsampleModeUNet`, `monai_models.py:84-139`): 1x1 `preconv` on the implicit-GEMM
+    kernel + interpolation of the padded channels-last tensor, no norm / activation on the up path — forward and the
+    all-parameter gradient against the oracle's `UpsampleModeUNet` (held against the REAL class on the CPU)."""
+    from oracle.monai_unet_oracle import UpsampleModeUNet as OracleUNet
+    from pytorch_connectomics_b200.architectures import monai_unet as PM
+    kw = dict(spatial_dims=3, in_channels=1, out_channels=3, channels=[16, 32, 64], strides=[2, 2], num_res_units=res_units,
+              norm="batch", dropout=0.0, upsample_mode="nontrainable", upsample_interp_mode=interp, upsample_align_corners=align)
+    torch.manual_seed(6)
+    ref, net = OracleUNet(**kw), PM.UNet(**kw)
+    assert list(ref.state_dict().keys()) == list(net.state_dict().keys())
+    net.load_state_dict(ref.state_dict(), strict=True)
+    net.to(DEV)
+    x = torch.rand(2, 1, 16, 32, 32)
+    g = torch.randn(2, 3, 16, 32, 32)
+    rel = lambda a, b: float((a.detach().float().cpu() - b.detach()).norm() / b.detach().norm().clamp_min(1e-12))
+    with torch.no_grad():
+        ref.eval(); net.eval()
+        want, got = ref(x), net(x.to(DEV))
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            want_bf = ref(x).float()
+    e, eb = rel(got, want), rel(want_bf, want)
+    print(f"monai_unet nontrainable upsampling ({interp}) forward: engine {e:.3e}  reference-bf16-path {eb:.3e}")
+    assert e <= 1.5 * eb + 4e-3
+    ref.train(); net.train()
+    ref.zero_grad(); net.zero_grad()
+    (ref(x) * g).sum().backward()
+    (net(x.to(DEV)).float() * g.to(DEV)).sum().backward()
+    num = den = 0.0
+    for (k, pr), pn in zip(ref.named_parameters(), net.parameters()):
+        num += float((pn.grad.float().cpu() - pr.grad).norm() ** 2); den += float(pr.grad.norm() ** 2)
+    print(f"monai_unet nontrainable upsampling: all-parameter gradient rel-L2 vs fp32 oracle {(num / den) ** 0.5:.3e}")
+    assert (num / den) ** 0.5 < 5e-2
+
+
 # ----------------------------------------------------------------------------- MedNeXt dim="2d" (depth-1 lift onto the 3-D kernels)
 @pytest.mark.parametrize("norm_type", ["group", "layer"])
 def test_mednext_2d_matches_oracle(norm_type):
