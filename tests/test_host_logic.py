@@ -384,6 +384,8 @@ def test_monai_unet_builder_and_state_dict_keys():
     with pytest.raises(ValueError, match="divisible by num_groups"):
         A.build_model(cfg)
     cfg.model.monai.norm, cfg.model.monai.upsample_mode = "batch", "nontrainable"
+    assert "model.2.0.preconv.weight" in A.build_model(cfg).model.state_dict()        # UpsampleModeUNet's interpolating up path
+    cfg.model.monai.upsample_mode = "pixelshuffle"
     with pytest.raises(NotImplementedError):
         A.build_model(cfg)
 
