@@ -22,6 +22,9 @@ PARITY PINNING.  The restatement is pinned by what the reference itself constrai
   * the identities in the reference's own tests
     (``tests/unit/test_mednext_features.py:26-55``): ``forward_output(forward_features(x))
     == model(x)``, deep supervision returns a 5-list.
+  * one independent numeric check: the block skeleton with the channels-first LayerNorm equals torchvision's ConvNeXt block
+    (``torchvision.models.convnext.CNBlock``, layer scale 1, eps 1e-5) from the same weights —
+    ``tests/test_oracle_mednext.py::test_block_restatement_equals_torchvisions_convnext_block``.
 Numeric outputs of ``nnunet_mednext`` itself are NOT available here: for the network
 arithmetic this oracle is "parity unpinned" against the third-party wheel (stated in
 DESIGN.md); every op is a stock ``torch.nn.functional`` call, which is what upstream runs.

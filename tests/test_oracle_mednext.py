@@ -110,3 +110,35 @@ def test_forward_cost_matches_the_published_table(size, k, gflops):
         net = create_mednext_v1(1, 3, size, kernel_size=k, deep_supervision=False).eval()
     gmac = _conv_macs(net, 128) / 1e9
     assert 0.97 * gflops <= gmac <= 1.0 * gflops, (size, k, gmac)
+
+
+def test_block_restatement_equals_torchvisions_convnext_block():
+    """An independent pin of the block restatement: MedNeXt's block is the ConvNeXt block it is derived from (depthwise k x k
+    conv -> LayerNorm over channels -> 1x1 expand -> GELU -> 1x1 project -> residual).  torchvision ships that block
+    (``torchvision.models.convnext.CNBlock``, written from the ConvNeXt paper, LayerNorm on a channels-LAST permute, Linear
+    layers); with its layer scale set to 1 and MedNeXt's eps the oracle's ``MedNeXtBlock(norm_type="layer", dim="2d", k=7,
+    exp_r=4)`` — channels-FIRST LayerNorm, 1x1 convolutions — must give the same output and the same input gradient from the
+    same weights.  (Covers the block skeleton and the channels-first LayerNorm; GroupNorm and the resampling blocks stay pinned
+    by the parameter counts / cost table above.)"""
+    from functools import partial
+    tv = pytest.importorskip("torchvision.models.convnext")
+    torch.manual_seed(0)
+    c = 16
+    theirs = tv.CNBlock(c, layer_scale=1.0, stochastic_depth_prob=0.0, norm_layer=partial(torch.nn.LayerNorm, eps=1e-5)).eval()
+    ours = MedNeXtBlock(c, c, exp_r=4, kernel_size=7, do_res=True, norm_type="layer", dim="2d").eval()
+    dw, _perm, ln, fc1, _gelu, fc2, _back = theirs.block
+    with torch.no_grad():
+        ln.weight.uniform_(0.5, 1.5)
+        ln.bias.uniform_(-0.2, 0.2)
+        ours.conv1.weight.copy_(dw.weight); ours.conv1.bias.copy_(dw.bias)
+        ours.norm.weight.copy_(ln.weight); ours.norm.bias.copy_(ln.bias)
+        ours.conv2.weight.copy_(fc1.weight[:, :, None, None]); ours.conv2.bias.copy_(fc1.bias)
+        ours.conv3.weight.copy_(fc2.weight[:, :, None, None]); ours.conv3.bias.copy_(fc2.bias)
+    xa = torch.randn(2, c, 12, 10, requires_grad=True)
+    xb = xa.detach().clone().requires_grad_(True)
+    ya, yb = theirs(xa), ours(xb)
+    assert torch.allclose(ya, yb, rtol=1e-5, atol=1e-5), float((ya - yb).abs().max())
+    g = torch.randn_like(ya)
+    (ya * g).sum().backward()
+    (yb * g).sum().backward()
+    assert torch.allclose(xa.grad, xb.grad, rtol=1e-4, atol=1e-5)
