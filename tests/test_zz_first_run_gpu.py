@@ -568,3 +568,39 @@ def test_mednext_grn_matches_oracle(norm_type, dim):
     with torch.no_grad():
         again = net.eval()(x.to(DEV))
     assert float((again.float() - got.float()).abs().max()) <= 1e-2 * float(got.float().abs().max())
+
+
+def test_engine_block_against_torchvisions_convnext_block():
+    """The CUDA path against a third-party implementation directly (no oracle in between): torchvision's ConvNeXt block
+    (``CNBlock``, layer scale 1, eps 1e-5) and this package's ``MedNeXtBlock(norm_type="layer", dim="2d", k=7, exp_r=4)`` from
+    the same weights — the k=7 stencil on a depth-1 volume, the channels-first LayerNorm kernel, the fused tcgen05 MLP with
+    its residual.  bf16 compute against torchvision's fp32: bounded by 1.5x the error of torchvision's own block under bf16
+    autocast plus 4e-3."""
+    from functools import partial
+    tv = pytest.importorskip("torchvision.models.convnext")
+    from pytorch_connectomics_b200.architectures import _mednext_ops as ops
+    from pytorch_connectomics_b200.architectures.mednext import MedNeXtBlock
+    torch.manual_seed(0)
+    c = 32
+    theirs = tv.CNBlock(c, layer_scale=1.0, stochastic_depth_prob=0.0, norm_layer=partial(torch.nn.LayerNorm, eps=1e-5)).eval()
+    ours = MedNeXtBlock(c, c, exp_r=4, kernel_size=7, do_res=True, norm_type="layer", dim="2d").eval()
+    dw, _perm, ln, fc1, _gelu, fc2, _back = theirs.block
+    with torch.no_grad():
+        ln.weight.uniform_(0.5, 1.5)
+        ln.bias.uniform_(-0.2, 0.2)
+        ours.conv1.weight.copy_(dw.weight); ours.conv1.bias.copy_(dw.bias)
+        ours.norm.weight.copy_(ln.weight); ours.norm.bias.copy_(ln.bias)
+        ours.conv2.weight.copy_(fc1.weight[:, :, None, None]); ours.conv2.bias.copy_(fc1.bias)
+        ours.conv3.weight.copy_(fc2.weight[:, :, None, None]); ours.conv3.bias.copy_(fc2.bias)
+    ours.to(DEV)
+    x = torch.randn(2, c, 48, 40)
+    with torch.no_grad():
+        want = theirs(x)
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            want_bf = theirs(x).float()
+        got = ours(ops.as_channels_last_2d(x.to(DEV)))                     # [N, 1, H, W, C] bf16
+    got = got[:, 0].permute(0, 3, 1, 2).float().cpu()
+    e = float((got - want).norm() / want.norm())
+    eb = float((want_bf - want).norm() / want.norm())
+    print(f"engine vs torchvision CNBlock: {e:.3e}  torchvision-under-bf16-autocast {eb:.3e}")
+    assert e <= 1.5 * eb + 4e-3
