@@ -278,6 +278,18 @@ def ref_lazy():
     return _load("connectomics.inference.lazy", "connectomics/inference/lazy.py")
 
 
+def cut_function(relpath: str, name: str, **namespace):
+    """One module-level function of a reference file, cut out of the file's syntax tree and compiled in place with the given
+    globals — for files whose module-level imports need packages this image does not have.  Nothing is copied."""
+    import ast
+    path = os.path.join(REF_ROOT, relpath)
+    tree = ast.parse(open(path).read(), filename=path)
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == name)
+    ns = dict(namespace)
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
+    return ns[name]
+
+
 def ref_smart_normalize():
     """The REAL ``smart_normalize`` (``connectomics/data/augmentation/augment_ops.py:552-610``): the module imports cv2, which
     this image does not have, so the one function (numpy only) is cut out of the reference file's syntax tree and compiled in
