@@ -555,7 +555,9 @@ class UNet(nn.Module):
 
 
 class MONAIModelWrapper(ConnectomicsModel):
-    """``monai_models.py:29-56`` — ConnectomicsModel interface; squeezes a singleton depth for 2-D nets."""
+    """``monai_models.py:29-56`` — ConnectomicsModel interface.  The reference's wrapper also squeezes a singleton depth in
+    front of its 2-D nets and restores it behind them; this engine builds 3-D nets only (``spatial_dims != 3`` is refused at
+    construction), which take and return ``(B, C, D, H, W)`` as they are."""
 
     def __init__(self, model: nn.Module):
         super().__init__()
