@@ -12,7 +12,7 @@ from conftest import ROOT
 PROBE = '''
 import time
 import pytest
-pytestmark = [pytest.mark.isolated(stall=8), pytest.mark.xfail(strict=False, reason="probe")]
+pytestmark = [pytest.mark.isolated(stall=25), pytest.mark.xfail(strict=False, reason="probe")]
 
 def test_a_passes():
     assert True
