@@ -52,6 +52,10 @@ GOOD = [
          do_res=False, do_res_up_down=False),
     _cfg("mednext_custom", base_channels=16, exp_r=2, kernel_size=3, block_counts=[1] * 9, norm="layer", checkpoint_style="outside_block"),
     _cfg("mednext_custom", base_channels=16, exp_r=2, kernel_size=3, block_counts=[1] * 9, heads=HEADS, primary="sdt"),
+    # model.mednext.dim / grn (mednext_models.py:461-462): Conv2d parameter shapes, grn_gamma / grn_beta keys, heads that inherit both
+    _cfg("mednext_custom", base_channels=16, exp_r=2, kernel_size=3, block_counts=[1] * 9, dim="2d", ds=True),
+    _cfg("mednext_custom", base_channels=16, exp_r=2, kernel_size=5, block_counts=[1] * 9, grn=True, norm="layer"),
+    _cfg("mednext_custom", base_channels=16, exp_r=2, kernel_size=3, block_counts=[1] * 9, dim="2d", grn=True, heads=HEADS, primary="aff"),
 ]
 
 BAD = [
