@@ -182,3 +182,42 @@ def test_bf16_storage_keeps_the_variants_inside_the_gpu_bounds(monkeypatch, norm
         if name == "dummy_tensor" or float(p.grad.norm()) < 1e-6 or (norm_type == "group" and name.endswith("conv1.bias")):
             continue
         assert float((params[name].grad.float() - p.grad).norm() / p.grad.norm()) < 5e-2, name
+
+
+@pytest.mark.parametrize("dim,grn", [("2d", False), ("3d", True), ("2d", True)])
+def test_multihead_variants_equal_the_real_wrapper(monkeypatch, dim, grn):
+    """`build_mednext_custom` with named task heads over a 2-D / GRN trunk: this package's wrapper (kernels replaced by the
+    torch stand-ins) against the REAL `MedNeXtMultiHeadWrapper` / `MedNeXtTaskHead` of `mednext_models.py:129-273` executed in
+    place over the oracle trunk — every head's output and every parameter gradient from the same checkpoint."""
+    from types import SimpleNamespace as NS
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("/root/reference is only present in the build container")
+    import pytorch_connectomics_b200.architectures as A
+    doubles.install(monkeypatch)
+    heads = {"aff": NS(out_channels=3, num_blocks=1, hidden_channels=16), "sdt": dict(out_channels=1, num_blocks=0)}
+    cfg = NS(model=NS(arch=NS(type="mednext_custom"), in_channels=1, out_channels=2, heads=heads, primary_head="aff",
+                      mednext=NS(base_channels=16, exp_r=2, kernel_size=3, block_counts=[1] * 9, dim=dim, grn=grn),
+                      loss=NS(deep_supervision=False)))
+    torch.manual_seed(2)
+    real = ref_loader.ref_mednext_models().build_mednext_custom(cfg).train()
+    with torch.no_grad():
+        for name, p in real.named_parameters():
+            if "grn" in name:
+                p.normal_(0.0, 0.5)
+    ours = A.get_architecture_builder("mednext_custom")(cfg).train()
+    ours.load_state_dict(real.state_dict(), strict=True)
+    x = torch.randn(2, 1, 32, 32) if dim == "2d" else torch.randn(1, 1, 32, 32, 32)
+    want, got = real(x)["output"], ours(x)["output"]
+    assert sorted(want) == sorted(got) == ["aff", "sdt"]
+    for k in want:
+        _close(got[k], want[k])
+    sum(v.square().mean() for v in want.values()).backward()
+    sum(v.square().mean() for v in got.values()).backward()
+    theirs = dict(real.named_parameters())
+    scale = max(float(p.grad.abs().max()) for p in theirs.values() if p.grad is not None)
+    for name, p in ours.named_parameters():
+        if theirs[name].grad is None:          # the trunk's own output head is unused under task heads
+            continue
+        assert p.grad is not None, name
+        _close(p.grad, theirs[name].grad, 5e-4, scale=max(scale * 1e-2, float(theirs[name].grad.abs().max())))
